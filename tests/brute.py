@@ -1,0 +1,205 @@
+"""Naive, independent restatement of SURVEY.md Appendix A (D1-D18) used to pin the
+C++ oracle on small inputs.  TEST INFRASTRUCTURE ONLY.
+
+No sorting tricks, no hashing by diagonal, no Invert(): every rule is applied the
+slow, literal way straight from the ASCII sequences, so an agreement between this
+file and oracle/oracle.cpp is evidence that both implement the written rules.
+
+Policy code follows /root/reference/src/UniqueMatchFinder.cpp:36-60 and
+/root/reference/src/SeedMatchEnumerator.h:71-141.
+"""
+from __future__ import annotations
+
+MODE_UNIQUE, MODE_SEED_ENUM, MODE_UNIQUE_COUNT, MODE_PAIRWISE = 0, 1, 2, 3
+_CODE = {"A": 0, "C": 1, "G": 2, "T": 3, "a": 0, "c": 1, "g": 2, "t": 3}
+
+
+def seed_len(pattern: int) -> int:
+    return pattern.bit_length()
+
+
+def care_offsets(pattern: int):
+    L = seed_len(pattern)
+    return [j for j in range(L) if (pattern >> (L - 1 - j)) & 1]
+
+
+def mer_at(seq: str, p: int, pattern: int):
+    """D4: (key, strand) of the L-window at 0-based p."""
+    L = seed_len(pattern)
+    win = [_CODE.get(ch, 0) for ch in seq[p:p + L]]
+    rc = [3 - b for b in reversed(win)]
+    offs = care_offsets(pattern)
+    fwd = 0
+    rev = 0
+    for j in offs:
+        fwd = fwd * 4 + win[j]
+        rev = rev * 4 + rc[j]
+    if rev < fwd:
+        return rev, 1
+    return fwd, 0
+
+
+def all_mers(seqs, pattern):
+    L = seed_len(pattern)
+    return [[mer_at(s, p, pattern) for p in range(len(s) - L + 1)] if len(s) >= L else [] for s in seqs]
+
+
+def _wok(mers, comps, L, length, grow_left):
+    """D13 window predicate for the newly covered window.
+    comps: list of (g, start1 (1-based left end), reverse?) with the *already grown* coordinates."""
+    ref = None
+    for g, start, rev in comps:
+        if grow_left:
+            pos = start if not rev else start + length - L  # match-left = right end of a reverse comp
+        else:
+            pos = start + length - L if not rev else start
+        key, strand = mers[g][pos - 1]
+        par = strand ^ (1 if rev else 0)
+        if ref is None:
+            ref = (key, par)
+        elif ref != (key, par):
+            return False
+    return True
+
+
+def extend(mers, lens, st, L):
+    """D14.  st: dict g -> signed 1-based start.  Returns (st, length)."""
+    comps = [[g, abs(s), s < 0] for g, s in sorted(st.items())]
+    length = L
+
+    def room(left):
+        r = None
+        for g, start, rev in comps:
+            lroom = start - 1
+            rroom = lens[g] - (start + length - 1)
+            v = (lroom if not rev else rroom) if left else (rroom if not rev else lroom)
+            r = v if r is None else min(r, v)
+        return r
+
+    def grow(left, step):
+        nonlocal length
+        # tentatively grow
+        for c in comps:
+            if (left and not c[2]) or (not left and c[2]):
+                c[1] -= step
+        length += step
+        if _wok(mers, comps, L, length, left):
+            return True
+        length -= step
+        for c in comps:
+            if (left and not c[2]) or (not left and c[2]):
+                c[1] += step
+        return False
+
+    for left, step, cap in ((True, L, None), (False, L, None), (True, 1, L), (False, 1, L)):
+        n = 0
+        while (cap is None or n < cap) and room(left) >= step:
+            if not grow(left, step):
+                break
+            n += 1
+    return {g: (-s if rev else s) for g, s, rev in comps}, length
+
+
+def _same_group_contains(e, c, L):
+    """D16: accepted extended match e contains length-L candidate c."""
+    est, elen = e
+    if set(est) != set(c):
+        return False
+    first = min(c)
+    for g in c:
+        if (c[g] < 0) != (est[g] < 0):
+            return False
+    d = c[first] - est[first]
+    if d < 0 or d + L > elen:
+        return False
+    for g in c:
+        if c[g] > 0:
+            if c[g] - est[g] != d:
+                return False
+        else:
+            if abs(c[g]) - abs(est[g]) != elen - L - d:
+                return False
+    return True
+
+
+def find(seqs, pattern, mode, min_multi=2, max_multi=1000, direct_only=False, nway_mask=0):
+    """Returns dict(matches=[(length, [(g, start), ...])], unique_mers=int, unique_per_seq=[...])."""
+    L = seed_len(pattern)
+    N = len(seqs)
+    lens = [len(s) for s in seqs]
+    mers = all_mers(seqs, pattern)
+    buckets = {}
+    for g in range(N):
+        for p, (key, strand) in enumerate(mers[g]):
+            buckets.setdefault(key, []).append((g, p, strand))
+    res = dict(unique_mers=len(buckets), unique_per_seq=[len({k for k, _ in mers[g]}) for g in range(N)], matches=[])
+    if mode == MODE_UNIQUE_COUNT:
+        return res
+    if mode == MODE_SEED_ENUM:
+        if N != 1:
+            return res
+        out = []
+        for key in sorted(buckets):
+            b = sorted(buckets[key], key=lambda t: t[1])
+            m = len(b)
+            if m < 2:
+                continue
+            st = [p + 1 for _, p, _ in b]
+            ref = b[0][2]
+            st = [s if b[i][2] == ref else -s for i, s in enumerate(st)]
+            found_reverse = any(s < 0 for s in st)
+            if m > max_multi or m < min_multi:
+                continue
+            if direct_only and found_reverse:
+                fw = [s for s in st if s > 0]
+                if len(fw) > 1:
+                    out.append((L, fw))
+            else:
+                out.append((L, st))
+        out.sort(key=lambda r: (r[1][0], len(r[1]), r[1][1:]))
+        res["matches"] = [(ln, [(0, s) for s in st]) for ln, st in out]
+        return res
+
+    accepted = []  # (st dict, length)
+
+    def hash_match(entries):
+        first_strand = entries[0][2]
+        st = {}
+        for i, (g, p, strand) in enumerate(entries):
+            st[g] = (p + 1) if strand == first_strand else -(p + 1)
+        for e in accepted:
+            if _same_group_contains(e, st, L):
+                return
+        st2, length = extend(mers, lens, st, L)
+        accepted.append((st2, length))
+
+    for key in sorted(buckets):
+        b = sorted(buckets[key])
+        if len(b) < 2:
+            continue
+        cnt = {}
+        for g, _, _ in b:
+            cnt[g] = cnt.get(g, 0) + 1
+        uniq = [t for t in b if cnt[t[0]] == 1]
+        if len(uniq) < 2:
+            continue
+        if mode == MODE_PAIRWISE:
+            for i in range(len(uniq)):
+                for j in range(i + 1, len(uniq)):
+                    hash_match([uniq[i], uniq[j]])
+            continue
+        if nway_mask:
+            present = 0
+            for g, _, _ in uniq:
+                present |= 1 << g
+            if present != nway_mask:
+                continue
+        hash_match(uniq)
+
+    def sort_key(m):
+        st, length = m
+        return ([abs(st.get(g, 0)) for g in range(N)], [1 if st.get(g, 0) < 0 else 0 for g in range(N)], length)
+
+    accepted.sort(key=sort_key)
+    res["matches"] = [(length, sorted(st.items())) for st, length in accepted]
+    return res
