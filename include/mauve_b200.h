@@ -1,0 +1,144 @@
+/*
+ * mauve_b200.h — C ABI of the B200-native seed-match anchoring path.
+ *
+ * This is the drop-in boundary.  In the reference the path sits
+ * behind a C++ virtual-method protocol, not an FFI; each entry point below names
+ * the reference call it stands in for.  The host classes in include/mems_compat/
+ * (MatchList, MatchFinder, MemHash, UniqueMatchFinder, SeedMatchEnumerator, ...)
+ * are thin C++ over exactly these functions; INTEGRATION.md shows the binding.
+ *
+ * Conventions: plain C types only; 0 = MB_OK, negative = error (mb_strerror);
+ * no exceptions cross the boundary; a context is driven by one host thread;
+ * there is NO CPU fallback and no backend dispatch behind this ABI — every
+ * compute entry point fails with MB_E_CUDA when no sm_100 device is usable.
+ */
+#ifndef MAUVE_B200_H
+#define MAUVE_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mb_ctx mb_ctx;
+
+enum {
+    MB_OK = 0,
+    MB_E_ARG = -1,       /* null / out-of-range argument                                   */
+    MB_E_SEED = -2,      /* pattern not palindromic / weight not odd in [3,31]              */
+    MB_E_NOSEQ = -3,     /* no sequence added                                              */
+    MB_E_SEQCOUNT = -4,  /* SEED_ENUM needs exactly 1 sequence (SeedMatchEnumerator.h:59-65);
+                            UNIQUE / PAIRWISE take at most 64                              */
+    MB_E_TOOLONG = -5,   /* a sequence >= 2^32 bases, or >= 2^31 seed positions in total    */
+    MB_E_CUDA = -6,      /* CUDA runtime error or no usable device (see mb_last_cuda_error) */
+    MB_E_NOMEM = -7,
+    MB_E_STATE = -8      /* call order (e.g. fetch before find)                            */
+};
+
+/* The per-bucket policy.  The reference selects it by which MatchFinder subclass
+ * overrides EnumerateMatches/HashMatch; a virtual call per bucket cannot cross to
+ * the device, so it is an enum here. */
+enum {
+    MB_MODE_UNIQUE = 0,       /* UniqueMatchFinder::EnumerateMatches (src/UniqueMatchFinder.cpp:36-60)
+                                 -> MemHash::HashMatch: extend + containment de-dup.  With nway_mask:
+                                 MaskedMemHash (src/mauveAligner.cpp:523-531).                        */
+    MB_MODE_SEED_ENUM = 1,    /* SeedMatchEnumerator::HashMatch (src/SeedMatchEnumerator.h:71-123)    */
+    MB_MODE_UNIQUE_COUNT = 2, /* SortedMerList::UniqueMerCount (src/uniqueMerCount.cpp:39)            */
+    MB_MODE_PAIRWISE = 3      /* PairwiseMatchFinder (src/progressiveMauve.cpp:496-501)               */
+};
+
+typedef struct mb_params {
+    int32_t mode;
+    int32_t direct_only;  /* SeedMatchEnumerator::FindMatches(..., direct_repeats_only)       */
+    uint64_t min_multi;   /* SeedMatchEnumerator::FindMatches(..., min_multi = 2, ...)         */
+    uint64_t max_multi;   /* SeedMatchEnumerator::FindMatches(..., max_multi = 1000, ...)      */
+    uint64_t nway_mask;   /* MaskedMemHash::SetMask(uint64), 0 = off                           */
+} mb_params;
+
+/* Result of one search, host side (pinned memory owned by the context; valid until
+ * the next mb_find / mb_fetch_result / mb_ctx_destroy on that context).
+ * CSR over matches; canonical order = SURVEY.md Appendix A D18.
+ * Stands in for MemHash::GetMatchList(MatchList&) (src/progressiveMauve.cpp:545)
+ * and SeedMatchEnumerator's mlist (src/SeedMatchEnumerator.h:31-32). */
+typedef struct mb_result {
+    uint64_t n_matches;
+    uint64_t n_comps;
+    const uint32_t* length;     /* [n_matches]                                              */
+    const uint64_t* comp_off;   /* [n_matches + 1]                                          */
+    const uint32_t* comp_seq;   /* [n_comps] sequence index (0 for SEED_ENUM)               */
+    const int64_t* comp_start;  /* [n_comps] signed 1-based left end; < 0 = reverse strand  */
+    uint64_t unique_mers;                /* distinct seeds over all sequences               */
+    const uint64_t* unique_mers_per_seq; /* [nseq] SortedMerList::UniqueMerCount per SML    */
+    uint32_t nseq;
+} mb_result;
+
+typedef struct mb_stats {
+    uint64_t n_seeds, n_runs, n_buckets, n_candidates, n_extended, n_matches, n_comps;
+    uint32_t radix_passes, record_bytes, dedup_batches, dedup_iters;
+    /* device milliseconds per stage of the last mb_find (CUDA events on the context stream) */
+    float ms_h2d, ms_pack, ms_extract, ms_sort, ms_bucket, ms_dedup, ms_output, ms_d2h, ms_total_device;
+    uint64_t h2d_bytes, d2h_bytes;
+    uint64_t kernel_launches;   /* launches of this library's own kernels in the last mb_find */
+} mb_stats;
+
+/* ---- context ----------------------------------------------------------------- */
+int mb_ctx_create(mb_ctx** out, int device);
+int mb_ctx_destroy(mb_ctx* ctx);
+/* Use an existing CUDA stream (cudaStream_t / CUstream handle, e.g. torch's); NULL = own stream. */
+int mb_set_stream(mb_ctx* ctx, void* cuda_stream);
+
+/* ---- inputs ------------------------------------------------------------------ */
+/* MatchFinder::AddSequence(SortedMerList*, gnSequence*) (src/SeedMatchEnumerator.h:25,
+ * src/mauveAligner.cpp:577).  `data` is a HOST buffer: ASCII bases (is_packed = 0; A/C/G/T any
+ * case, anything else reads as A) or 2-bit words (is_packed = 1; 32 bases per uint64, first base
+ * in the top bits).  The library copies to the device; the caller keeps ownership. */
+int mb_add_sequence(mb_ctx* ctx, const uint8_t* data, uint64_t len, int is_packed, int* out_id);
+/* Same, but `dev_ascii` is already DEVICE memory (used by the resident-input benchmark leg). */
+int mb_add_sequence_device(mb_ctx* ctx, const void* dev_ascii, uint64_t len, int* out_id);
+/* MatchFinder::ClearSequences() (src/progressiveMauve.cpp:542) */
+int mb_clear_sequences(mb_ctx* ctx);
+/* getSeed() result handed to LoadSMLs/CreateMemorySMLs (src/mauveAligner.cpp:456,465): the raw
+ * 64-bit pattern, MSB-first from its highest set bit, 1 = care. */
+int mb_set_seed(mb_ctx* ctx, uint64_t pattern);
+
+/* ---- the path ---------------------------------------------------------------- */
+/* Whole path, host to host: stands in for LoadSMLs + XFinder.FindMatches(MatchList&) +
+ * GetMatchList (src/progressiveMauve.cpp:446-451,492-495; src/repeatoire.cpp:1850,1866-1867;
+ * src/mauveAligner.cpp:465,585).  Equivalent to mb_find_device + mb_fetch_result. */
+int mb_find(mb_ctx* ctx, const mb_params* params, const mb_result** out);
+/* Device part only: packed sequences resident in HBM -> canonical match CSR resident in HBM.
+ * Asynchronous on the context stream. */
+int mb_find_device(mb_ctx* ctx, const mb_params* params);
+/* Device -> pinned host copy of the last mb_find_device result (synchronises the stream). */
+int mb_fetch_result(mb_ctx* ctx, const mb_result** out);
+
+/* ---- sorted mer list access (SortedMerList façade; "next" row of SURVEY.md §8f) ---- */
+/* Positions of sequence `seq` sorted by (seed, position): the .sslist position array (a4).
+ * out_pos must hold len-L+1 entries (host). Valid after a mb_find* call in any mode. */
+int mb_get_sml(mb_ctx* ctx, int seq, uint32_t* out_pos, uint64_t capacity, uint64_t* out_n);
+/* SortedMerList::GetMer-style per-position mers (key << (64-2w) | strand) of one sequence, for
+ * record-by-record parity checks of the extraction kernel. */
+int mb_get_mers(mb_ctx* ctx, int seq, uint64_t* out_mers, uint64_t capacity, uint64_t* out_n);
+
+/* ---- diagnostics ------------------------------------------------------------- */
+int mb_get_stats(mb_ctx* ctx, mb_stats* out);
+const char* mb_strerror(int code);
+const char* mb_last_cuda_error(mb_ctx* ctx);
+int mb_device_count(void);
+const char* mb_version(void);
+
+/* ---- synthetic genomes (host only) ------------------------------
+ * Deterministic generator (splitmix64-seeded xoshiro256**, seed 0x4D415556 + config) used by
+ * bench.py and the tests.  config 1..5 = BASELINE.json configs C1..C5; scale divides every
+ * length (1 = full size).  Sequences are ASCII ACGT in host memory owned by the handle. */
+typedef struct mb_synth mb_synth;
+int mb_synth_create(int config, uint64_t scale, mb_synth** out);
+uint32_t mb_synth_nseq(const mb_synth* s);
+uint64_t mb_synth_len(const mb_synth* s, uint32_t i);
+const uint8_t* mb_synth_seq(const mb_synth* s, uint32_t i);
+void mb_synth_free(mb_synth* s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,89 @@
+"""ctypes binding of libmauve_b200.so (the C ABI declared in include/mauve_b200.h).
+
+The library is the product: there is no Python or CPU implementation of the path behind it.
+Loading fails loudly if the shared object has not been built (python -c 'import __graft_entry__ as g; g.build()')."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmauve_b200.so")
+
+MB_OK = 0
+MODE_UNIQUE, MODE_SEED_ENUM, MODE_UNIQUE_COUNT, MODE_PAIRWISE = 0, 1, 2, 3
+SOLID_SEED = 2 ** 31 - 1
+CODING_SEED = 3
+
+
+class MbParams(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("direct_only", C.c_int32), ("min_multi", C.c_uint64), ("max_multi", C.c_uint64),
+                ("nway_mask", C.c_uint64)]
+
+
+class MbResult(C.Structure):
+    _fields_ = [("n_matches", C.c_uint64), ("n_comps", C.c_uint64), ("length", C.POINTER(C.c_uint32)),
+                ("comp_off", C.POINTER(C.c_uint64)), ("comp_seq", C.POINTER(C.c_uint32)), ("comp_start", C.POINTER(C.c_int64)),
+                ("unique_mers", C.c_uint64), ("unique_mers_per_seq", C.POINTER(C.c_uint64)), ("nseq", C.c_uint32)]
+
+
+class MbStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("n_seeds", "n_runs", "n_buckets", "n_candidates", "n_extended", "n_matches", "n_comps")] + \
+               [(n, C.c_uint32) for n in ("radix_passes", "record_bytes", "dedup_batches", "dedup_iters")] + \
+               [(n, C.c_float) for n in ("ms_h2d", "ms_pack", "ms_extract", "ms_sort", "ms_bucket", "ms_dedup", "ms_output", "ms_d2h",
+                                         "ms_total_device")] + \
+               [(n, C.c_uint64) for n in ("h2d_bytes", "d2h_bytes", "kernel_launches")]
+
+
+EXPORTS = ["mb_ctx_create", "mb_ctx_destroy", "mb_set_stream", "mb_add_sequence", "mb_add_sequence_device", "mb_clear_sequences",
+           "mb_set_seed", "mb_find", "mb_find_device", "mb_fetch_result", "mb_get_sml", "mb_get_mers", "mb_get_stats", "mb_strerror",
+           "mb_last_cuda_error", "mb_device_count", "mb_version", "mb_synth_create", "mb_synth_nseq", "mb_synth_len", "mb_synth_seq",
+           "mb_synth_free"]
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: build it with `make -C mauvealigner_b200/csrc` "
+                          "(or __graft_entry__.build()); there is no fallback implementation")
+    L = C.CDLL(LIB_PATH)
+    vp, u64, i32 = C.c_void_p, C.c_uint64, C.c_int
+    L.mb_ctx_create.argtypes = [C.POINTER(vp), i32]
+    L.mb_ctx_destroy.argtypes = [vp]
+    L.mb_set_stream.argtypes = [vp, vp]
+    L.mb_add_sequence.argtypes = [vp, vp, u64, i32, C.POINTER(i32)]
+    L.mb_add_sequence_device.argtypes = [vp, vp, u64, C.POINTER(i32)]
+    L.mb_clear_sequences.argtypes = [vp]
+    L.mb_set_seed.argtypes = [vp, u64]
+    L.mb_find.argtypes = [vp, C.POINTER(MbParams), C.POINTER(C.POINTER(MbResult))]
+    L.mb_find_device.argtypes = [vp, C.POINTER(MbParams)]
+    L.mb_fetch_result.argtypes = [vp, C.POINTER(C.POINTER(MbResult))]
+    L.mb_get_sml.argtypes = [vp, i32, vp, u64, C.POINTER(u64)]
+    L.mb_get_mers.argtypes = [vp, i32, vp, u64, C.POINTER(u64)]
+    L.mb_get_stats.argtypes = [vp, C.POINTER(MbStats)]
+    L.mb_strerror.argtypes = [i32]
+    L.mb_strerror.restype = C.c_char_p
+    L.mb_last_cuda_error.argtypes = [vp]
+    L.mb_last_cuda_error.restype = C.c_char_p
+    L.mb_version.restype = C.c_char_p
+    L.mb_synth_create.argtypes = [i32, u64, C.POINTER(vp)]
+    L.mb_synth_nseq.argtypes = [vp]
+    L.mb_synth_nseq.restype = C.c_uint32
+    L.mb_synth_len.argtypes = [vp, C.c_uint32]
+    L.mb_synth_len.restype = u64
+    L.mb_synth_seq.argtypes = [vp, C.c_uint32]
+    L.mb_synth_seq.restype = vp
+    L.mb_synth_free.argtypes = [vp]
+    _lib = L
+    return L
+
+
+class MauveError(RuntimeError):
+    def __init__(self, code, detail=""):
+        self.code = code
+        msg = lib().mb_strerror(code).decode()
+        super().__init__(f"mauve_b200 error {code}: {msg}{(' — ' + detail) if detail else ''}")

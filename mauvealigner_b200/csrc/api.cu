@@ -1,0 +1,710 @@
+// api.cu — the C ABI of include/mauve_b200.h: context, inputs, the seed-to-multi-MUM pipeline driver,
+// result transfer.  No CPU fallback: every compute entry point needs a CUDA device.
+#include "../../include/mauve_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+namespace {
+
+struct DBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+enum { EV_START, EV_EXTRACT, EV_SORT, EV_BUCKET, EV_DEDUP, EV_OUTPUT, EV_COUNT };
+enum { SC_RUNS = 0 /*u32[2]*/, SC_CAND = 1 /*u32[2]*/, SC_NBUCKETS = 2, SC_UNDECIDED = 3, SC_EXTENDED = 4, SC_NMATCH = 5, SC_NCOMP = 6,
+       SC_BMTOTAL = 7, SC_COUNT = 16 };
+
+} // namespace
+
+struct mb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    char err[512] = {0};
+
+    // inputs
+    std::vector<u64> seq_len;
+    std::vector<u64> seq_word_base;
+    u64 words_used = 0;
+    DBuf packed, ascii_stage;
+    u64 pattern = 0;
+    SeedDev sd{};
+    bool seed_set = false;
+
+    // workspace
+    DBuf keysA, keysB, valsA, valsB, hist, digit_base, lookback, tickets, status, scalars, per_seq, tile_first;
+    DBuf cand_run, cand_off, cand_aux, comp_pos, comp_gs, bitmap, bmrank, slot_of, cand_at, cstate, covered, minrank, ext_l, ext_r;
+    DBuf flags, match_idx, sort_kA, sort_kB, sort_vA, sort_vB, ncomp, mers_tmp;
+    DBuf out_len, out_off, out_seq, out_start;
+    u32 ticket_next = 0;
+    u64 tmp_u64 = 0;
+    size_t status_next = 0;
+
+    // last run
+    GenomeTable gt{};
+    RecFmt fmt{};
+    const u64* sorted_keys = nullptr;
+    const u64* sorted_vals = nullptr;
+    u32 n_seeds = 0;
+    bool have_result = false;
+    u64 r_matches = 0, r_comps = 0, r_unique = 0;
+    int last_mode = 0;
+
+    // host result (pinned)
+    void* h_len = nullptr; void* h_off = nullptr; void* h_seq = nullptr; void* h_start = nullptr; void* h_perseq = nullptr; void* h_scal = nullptr;
+    size_t h_len_cap = 0, h_off_cap = 0, h_seq_cap = 0, h_start_cap = 0;
+    mb_result res{};
+    mb_stats stats{};
+    cudaEvent_t ev[EV_COUNT] = {nullptr};
+    cudaEvent_t ev_x[4] = {nullptr};
+
+    void set_cuda_error(cudaError_t e, const char* what, int line) {
+        snprintf(err, sizeof(err), "%s (%s) at api.cu:%d: %s", cudaGetErrorName(e), cudaGetErrorString(e), line, what);
+    }
+    int reserve(DBuf& b, size_t bytes) {
+        if (bytes <= b.cap) return MB_OK;
+        if (b.p) cudaFree(b.p);
+        b.p = nullptr; b.cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&b.p, want);
+        if (e != cudaSuccess) { set_cuda_error(e, "cudaMalloc", __LINE__); return e == cudaErrorMemoryAllocation ? MB_E_NOMEM : MB_E_CUDA; }
+        b.cap = want;
+        return MB_OK;
+    }
+    int reserve_host(void*& p, size_t& cap, size_t bytes) {
+        if (bytes <= cap) return MB_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e != cudaSuccess) { set_cuda_error(e, "cudaMallocHost", __LINE__); return MB_E_NOMEM; }
+        cap = want;
+        return MB_OK;
+    }
+    u32* ticket() { return tickets.as<u32>() + (ticket_next++); }
+    u64* status_slice(size_t n_tiles) {
+        u64* p = status.as<u64>() + status_next;
+        status_next += n_tiles + 1;
+        return p;
+    }
+};
+
+#define TRY(expr) do { int _rc = (expr); if (_rc != MB_OK) return _rc; } while (0)
+#define LAUNCHED(ctx) do { ++(ctx)->stats.kernel_launches; } while (0)
+#define CHECK_LAUNCH(ctx) CUDA_TRY(ctx, cudaGetLastError())
+
+static void free_buf(DBuf& b) { if (b.p) cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+
+static int build_seed(uint64_t pattern, SeedDev& sd) {
+    int L = 0; { u64 p = pattern; while (p) { ++L; p >>= 1; } }
+    int w = __builtin_popcountll(pattern);
+    if (L == 0 || !(w & 1) || w < 3 || w > 31) return MB_E_SEED;
+    for (int j = 0; j < L; ++j)
+        if (((pattern >> j) & 1) != ((pattern >> (L - 1 - j)) & 1)) return MB_E_SEED;
+    memset(&sd, 0, sizeof(sd));
+    sd.L = L; sd.w = w; sd.wide = L > 32;
+    // window offset j (0 = first base) sits at left-aligned bits [126-2j, 127-2j] of hi:lo
+    auto set2 = [](u64& hi, u64& lo, int j) {
+        int b = 126 - 2 * j;
+        if (b >= 64) hi |= 3ull << (b - 64); else lo |= 3ull << b;
+    };
+    int nrun = 0, j = 0, gaps = 0;
+    while (j < L) {
+        bool care = (pattern >> (L - 1 - j)) & 1;
+        if (!care) { ++gaps; ++j; continue; }
+        u64 hi = 0, lo = 0;
+        while (j < L && ((pattern >> (L - 1 - j)) & 1)) { set2(hi, lo, j); set2(sd.mask_hi, sd.mask_lo, j); ++j; }
+        if (nrun >= 32) return MB_E_SEED;
+        sd.runmask_hi[nrun] = hi; sd.runmask_lo[nrun] = lo; sd.lshift[nrun] = 2 * gaps;
+        ++nrun;
+    }
+    sd.nrun = nrun;
+    return MB_OK;
+}
+
+extern "C" {
+
+const char* mb_version(void) { return "mauvealigner_b200 0.1 (sm_100a)"; }
+
+const char* mb_strerror(int code) {
+    switch (code) {
+    case MB_OK: return "ok";
+    case MB_E_ARG: return "bad argument";
+    case MB_E_SEED: return "seed pattern must be palindromic with odd weight in [3,31]";
+    case MB_E_NOSEQ: return "no sequence added";
+    case MB_E_SEQCOUNT: return "sequence count not supported by this mode";
+    case MB_E_TOOLONG: return "sequence too long";
+    case MB_E_CUDA: return "CUDA error";
+    case MB_E_NOMEM: return "out of memory";
+    case MB_E_STATE: return "call out of order";
+    default: return "unknown error";
+    }
+}
+
+int mb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char* mb_last_cuda_error(mb_ctx* ctx) { return ctx ? ctx->err : ""; }
+
+int mb_ctx_create(mb_ctx** out, int device) {
+    if (!out) return MB_E_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0 || device < 0 || device >= n) { cudaGetLastError(); return MB_E_CUDA; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return MB_E_CUDA;
+    if (prop.major != 10) return MB_E_CUDA; // sm_100a cubins only; no other code path exists
+    mb_ctx* c = new (std::nothrow) mb_ctx();
+    if (!c) return MB_E_NOMEM;
+    c->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { delete c; return MB_E_CUDA; }
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return MB_E_CUDA; }
+    c->own_stream = true;
+    for (int i = 0; i < EV_COUNT; ++i) cudaEventCreate(&c->ev[i]);
+    for (int i = 0; i < 4; ++i) cudaEventCreate(&c->ev_x[i]);
+    cudaMallocHost(&c->h_perseq, MB_MAX_SEQ * sizeof(u64));
+    cudaMallocHost(&c->h_scal, SC_COUNT * sizeof(u64));
+    *out = c;
+    return MB_OK;
+}
+
+int mb_ctx_destroy(mb_ctx* c) {
+    if (!c) return MB_E_ARG;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    DBuf* bufs[] = {&c->packed, &c->ascii_stage, &c->keysA, &c->keysB, &c->valsA, &c->valsB, &c->hist, &c->digit_base, &c->lookback, &c->tickets,
+                    &c->status, &c->scalars, &c->per_seq, &c->tile_first, &c->cand_run, &c->cand_off, &c->cand_aux, &c->comp_pos, &c->comp_gs,
+                    &c->bitmap, &c->bmrank, &c->slot_of, &c->cand_at, &c->cstate, &c->covered, &c->minrank, &c->ext_l, &c->ext_r, &c->flags,
+                    &c->match_idx, &c->sort_kA, &c->sort_kB, &c->sort_vA, &c->sort_vB, &c->ncomp, &c->mers_tmp, &c->out_len, &c->out_off,
+                    &c->out_seq, &c->out_start};
+    for (DBuf* b : bufs) free_buf(*b);
+    void* hs[] = {c->h_len, c->h_off, c->h_seq, c->h_start, c->h_perseq, c->h_scal};
+    for (void* h : hs) if (h) cudaFreeHost(h);
+    for (int i = 0; i < EV_COUNT; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    for (int i = 0; i < 4; ++i) if (c->ev_x[i]) cudaEventDestroy(c->ev_x[i]);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return MB_OK;
+}
+
+int mb_set_stream(mb_ctx* c, void* s) {
+    if (!c) return MB_E_ARG;
+    cudaSetDevice(c->device);
+    if (c->own_stream && c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    if (s) { c->stream = (cudaStream_t)s; c->own_stream = false; }
+    else {
+        CUDA_TRY(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->own_stream = true;
+    }
+    return MB_OK;
+}
+
+int mb_clear_sequences(mb_ctx* c) {
+    if (!c) return MB_E_ARG;
+    c->seq_len.clear(); c->seq_word_base.clear(); c->words_used = 0; c->have_result = false;
+    c->stats.h2d_bytes = 0;
+    return MB_OK;
+}
+
+int mb_set_seed(mb_ctx* c, uint64_t pattern) {
+    if (!c) return MB_E_ARG;
+    SeedDev sd;
+    TRY(build_seed(pattern, sd));
+    c->sd = sd; c->pattern = pattern; c->seed_set = true;
+    return MB_OK;
+}
+
+// grow the packed-genome buffer, keeping its contents
+static int grow_packed(mb_ctx* c, u64 need_words) {
+    const u64 slack = 512; // read-ahead of the extraction tiles past the last genome
+    size_t bytes = (need_words + slack) * 8;
+    if (bytes <= c->packed.cap) return MB_OK;
+    DBuf nb;
+    size_t want = bytes * 2;
+    cudaError_t e = cudaMalloc(&nb.p, want);
+    if (e != cudaSuccess) { c->set_cuda_error(e, "cudaMalloc(packed)", __LINE__); return MB_E_NOMEM; }
+    nb.cap = want;
+    CUDA_TRY(c, cudaMemsetAsync(nb.p, 0, want, c->stream));
+    if (c->packed.p && c->words_used) CUDA_TRY(c, cudaMemcpyAsync(nb.p, c->packed.p, c->words_used * 8, cudaMemcpyDeviceToDevice, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    free_buf(c->packed);
+    c->packed = nb;
+    return MB_OK;
+}
+
+static int add_sequence_common(mb_ctx* c, const void* data, uint64_t len, int kind /*0 host ascii, 1 host packed, 2 device ascii*/, int* out_id) {
+    if (!c || (!data && len)) return MB_E_ARG;
+    if (len >= (1ull << 32)) return MB_E_TOOLONG;
+    if (c->seq_len.size() >= MB_MAX_SEQ) return MB_E_SEQCOUNT;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    u64 n_words = (len + 31) / 32;
+    u64 base = (c->words_used + 1) & ~1ull; // 16-byte aligned
+    u64 end = base + n_words + MB_PAD_WORDS;
+    TRY(grow_packed(c, end));
+    u64* dst = c->packed.as<u64>() + base;
+    // padding after the genome must read as zero
+    CUDA_TRY(c, cudaMemsetAsync(dst, 0, (n_words + MB_PAD_WORDS) * 8, c->stream));
+    if (len) {
+        if (kind == 1) {
+            CUDA_TRY(c, cudaMemcpyAsync(dst, data, n_words * 8, cudaMemcpyHostToDevice, c->stream));
+            c->stats.h2d_bytes += n_words * 8;
+        } else {
+            const u8* d_ascii = (const u8*)data;
+            if (kind == 0) {
+                TRY(c->reserve(c->ascii_stage, len + 16));
+                CUDA_TRY(c, cudaMemcpyAsync(c->ascii_stage.p, data, len, cudaMemcpyHostToDevice, c->stream));
+                c->stats.h2d_bytes += len;
+                d_ascii = c->ascii_stage.as<u8>();
+            }
+            launch_pack(d_ascii, len, dst, n_words, c->stream);
+            CHECK_LAUNCH(c);
+            if (kind == 0) CUDA_TRY(c, cudaStreamSynchronize(c->stream)); // the staging buffer is reused by the next call
+        }
+    }
+    c->seq_len.push_back(len);
+    c->seq_word_base.push_back(base);
+    c->words_used = end;
+    c->have_result = false;
+    if (out_id) *out_id = (int)c->seq_len.size() - 1;
+    return MB_OK;
+}
+
+int mb_add_sequence(mb_ctx* c, const uint8_t* data, uint64_t len, int is_packed, int* out_id) {
+    return add_sequence_common(c, data, len, is_packed ? 1 : 0, out_id);
+}
+int mb_add_sequence_device(mb_ctx* c, const void* dev_ascii, uint64_t len, int* out_id) {
+    return add_sequence_common(c, dev_ascii, len, 2, out_id);
+}
+
+// ---------------------------------------------------------------------------------- sort driver
+// LSD radix sort of n (key[, val]) records on key bits [shift, shift+kbits).  On return *kA/*vA hold
+// the sorted data (the buffers are swapped as needed).
+static int sort_records(mb_ctx* c, u64** kA, u64** kB, u64** vA, u64** vB, u32 n, int shift, int kbits, bool hist_ready) {
+    int npass = (kbits + 7) / 8;
+    if (n == 0 || npass == 0) return MB_OK;
+    if (!hist_ready) {
+        CUDA_TRY(c, cudaMemsetAsync(c->hist.p, 0, 8 * 256 * 4, c->stream));
+        launch_hist(*kA, n, shift, kbits, npass, c->hist.as<u32>(), c->stream); LAUNCHED(c);
+    }
+    launch_scan_hist(c->hist.as<u32>(), c->digit_base.as<u32>(), npass, c->stream); LAUNCHED(c);
+    u32 tiles = div_up(n, radix_tile_size());
+    for (int ps = 0; ps < npass; ++ps) {
+        CUDA_TRY(c, cudaMemsetAsync(c->lookback.p, 0, (size_t)tiles * 256 * 8, c->stream));
+        int bits = std::min(8, kbits - 8 * ps);
+        cudaError_t e = launch_onesweep(*kA, *kB, vA ? *vA : nullptr, vB ? *vB : nullptr, n, c->digit_base.as<u32>() + ps * 256,
+                                        c->lookback.as<u64>(), c->ticket(), shift + 8 * ps, bits, c->stream);
+        LAUNCHED(c);
+        if (e != cudaSuccess) { c->set_cuda_error(e, "onesweep", __LINE__); return MB_E_CUDA; }
+        std::swap(*kA, *kB);
+        if (vA) std::swap(*vA, *vB);
+    }
+    c->stats.radix_passes += npass;
+    return MB_OK;
+}
+
+static int bits_for(u64 maxval) { int b = 0; while (maxval) { ++b; maxval >>= 1; } return b; }
+
+static int read_scalars(mb_ctx* c) {
+    CUDA_TRY(c, cudaMemcpyAsync(c->h_scal, c->scalars.p, SC_COUNT * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return MB_OK;
+}
+
+int mb_find_device(mb_ctx* c, const mb_params* prm) {
+    if (!c || !prm) return MB_E_ARG;
+    if (!c->seed_set) return MB_E_SEED;
+    const u32 nseq = (u32)c->seq_len.size();
+    if (nseq == 0) return MB_E_NOSEQ;
+    const int mode = prm->mode;
+    if (mode < MB_MODE_UNIQUE || mode > MB_MODE_PAIRWISE) return MB_E_ARG;
+    if (mode == MB_MODE_PAIRWISE) return MB_E_ARG; // not built yet
+    if (mode == MB_MODE_SEED_ENUM && nseq != 1) return MB_E_SEQCOUNT;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const SeedDev& sd = c->sd;
+    const u32 L = sd.L;
+
+    u64 h2d = c->stats.h2d_bytes;
+    memset(&c->stats, 0, sizeof(c->stats));
+    c->stats.h2d_bytes = h2d;
+    c->have_result = false;
+    c->ticket_next = 0; c->status_next = 0;
+
+    // ---- genome table, record format
+    GenomeTable& gt = c->gt;
+    memset(&gt, 0, sizeof(gt));
+    gt.nseq = nseq;
+    u64 n64 = 0, bases = 0, maxlen = 0;
+    std::vector<u32> tile_first(nseq + 1);
+    const u32 ET = extract_tile_size();
+    u32 n_tiles = 0;
+    for (u32 g = 0; g < nseq; ++g) {
+        u64 len = c->seq_len[g];
+        gt.word_base[g] = c->seq_word_base[g];
+        gt.base_base[g] = bases;
+        gt.len[g] = (u32)len;
+        gt.seed_base[g] = (u32)n64;
+        u64 ns = len >= L ? len - L + 1 : 0;
+        tile_first[g] = n_tiles;
+        n_tiles += div_up(ns, ET);
+        n64 += ns; bases += len; maxlen = std::max(maxlen, len);
+    }
+    tile_first[nseq] = n_tiles;
+    if (n64 >= (1ull << 31)) return MB_E_TOOLONG;
+    const u32 n = (u32)n64;
+    c->n_seeds = n;
+    c->stats.n_seeds = n;
+    RecFmt& fmt = c->fmt;
+    fmt.kbits = 2 * sd.w;
+    fmt.gbits = bits_for(nseq - 1);
+    fmt.pbits = bits_for(maxlen ? maxlen - 1 : 0);
+    if (fmt.pbits == 0) fmt.pbits = 1;
+    fmt.wide = (fmt.kbits + fmt.gbits + fmt.pbits + 1) > 64;
+    fmt.kshift = fmt.wide ? 0 : fmt.gbits + fmt.pbits + 1;
+    c->stats.record_bytes = fmt.wide ? 16 : 8;
+    const int npass = (fmt.kbits + 7) / 8;
+
+    // ---- workspace
+    const size_t nrec = (size_t)n + 8;
+    TRY(c->reserve(c->keysA, nrec * 8));
+    TRY(c->reserve(c->keysB, nrec * 8));
+    if (fmt.wide) { TRY(c->reserve(c->valsA, nrec * 8)); TRY(c->reserve(c->valsB, nrec * 8)); }
+    TRY(c->reserve(c->hist, 8 * 256 * 4));
+    TRY(c->reserve(c->digit_base, 8 * 256 * 4));
+    TRY(c->reserve(c->lookback, (size_t)(div_up(n, radix_tile_size()) + 1) * 256 * 8));
+    TRY(c->reserve(c->tickets, 256 * 4));
+    size_t status_words = (size_t)div_up(n, find_runs_tile()) + div_up(n, select_tile()) + 3 * (size_t)div_up(n, scan_tile()) +
+                          div_up(bases / 64 + 2, scan_tile()) + 64;
+    TRY(c->reserve(c->status, status_words * 8));
+    TRY(c->reserve(c->scalars, SC_COUNT * 8));
+    TRY(c->reserve(c->per_seq, MB_MAX_SEQ * 8));
+    TRY(c->reserve(c->tile_first, (nseq + 1) * 4));
+    CUDA_TRY(c, cudaMemsetAsync(c->tickets.p, 0, 256 * 4, st));
+    CUDA_TRY(c, cudaMemsetAsync(c->status.p, 0, status_words * 8, st));
+    CUDA_TRY(c, cudaMemsetAsync(c->scalars.p, 0, SC_COUNT * 8, st));
+    CUDA_TRY(c, cudaMemsetAsync(c->per_seq.p, 0, MB_MAX_SEQ * 8, st));
+    CUDA_TRY(c, cudaMemsetAsync(c->hist.p, 0, 8 * 256 * 4, st));
+    CUDA_TRY(c, cudaMemcpyAsync(c->tile_first.p, tile_first.data(), (nseq + 1) * 4, cudaMemcpyHostToDevice, st));
+    u64* scal = c->scalars.as<u64>();
+
+    cudaEventRecord(c->ev[EV_START], st);
+    // ---- a3: extract seed records (+ all digit histograms)
+    u64 *kA = c->keysA.as<u64>(), *kB = c->keysB.as<u64>(), *vA = fmt.wide ? c->valsA.as<u64>() : nullptr, *vB = fmt.wide ? c->valsB.as<u64>() : nullptr;
+    launch_extract_records(c->packed.as<u64>(), kA, vA, c->hist.as<u32>(), npass, gt, sd, fmt, c->tile_first.as<u32>(), n_tiles, st);
+    if (n_tiles) { LAUNCHED(c); CHECK_LAUNCH(c); }
+    cudaEventRecord(c->ev[EV_EXTRACT], st);
+    // ---- a4 + a6: one stable radix sort over the seed bits
+    TRY(sort_records(c, &kA, &kB, fmt.wide ? &vA : nullptr, fmt.wide ? &vB : nullptr, n, fmt.kshift, fmt.kbits, true));
+    c->sorted_keys = kA; c->sorted_vals = vA;
+    cudaEventRecord(c->ev[EV_SORT], st);
+
+    c->last_mode = mode;
+    c->r_matches = 0; c->r_comps = 0; c->r_unique = 0;
+    if (n == 0) {
+        for (int i = EV_BUCKET; i < EV_COUNT; ++i) cudaEventRecord(c->ev[i], st);
+        memset(c->h_perseq, 0, MB_MAX_SEQ * 8);
+        c->have_result = true;
+        return MB_OK;
+    }
+
+    // ---- a5/a6: runs of equal seed.  run arrays live in the now-free ping-pong buffer.
+    u32* run_start = reinterpret_cast<u32*>(kB);
+    u32* run_u = fmt.wide ? reinterpret_cast<u32*>(vB) : run_start + (n + 2);
+    bool need_u = mode == MB_MODE_UNIQUE || mode == MB_MODE_PAIRWISE;
+    bool need_counts = mode == MB_MODE_UNIQUE_COUNT || mode == MB_MODE_UNIQUE;
+    launch_find_runs(kA, vA, n, fmt, run_start, need_u ? run_u : nullptr, c->status_slice(div_up(n, find_runs_tile())), c->ticket(),
+                     need_counts ? c->per_seq.as<u64>() : nullptr, reinterpret_cast<u32*>(scal + SC_RUNS), st);
+    LAUNCHED(c); CHECK_LAUNCH(c);
+
+    if (mode == MB_MODE_UNIQUE_COUNT) {
+        for (int i = EV_BUCKET; i < EV_COUNT; ++i) cudaEventRecord(c->ev[i], st);
+        CUDA_TRY(c, cudaMemcpyAsync(c->h_perseq, c->per_seq.p, MB_MAX_SEQ * 8, cudaMemcpyDeviceToHost, st));
+        TRY(read_scalars(c));
+        c->r_unique = reinterpret_cast<u32*>((u64*)c->h_scal + SC_RUNS)[0];
+        c->stats.n_runs = c->r_unique;
+        c->have_result = true;
+        return MB_OK;
+    }
+
+    // ---- a7/a8: per-bucket policy -> candidates
+    const u32 cand_cap = n / 2 + 2;
+    TRY(c->reserve(c->cand_run, (size_t)cand_cap * 4));
+    TRY(c->reserve(c->cand_off, (size_t)(cand_cap + 1) * 4));
+    SelectArgs sa{};
+    sa.keys = kA; sa.vals = vA; sa.run_start = run_start; sa.run_u = run_u;
+    sa.n_runs_ptr = reinterpret_cast<u32*>(scal + SC_RUNS);
+    sa.mode = mode; sa.direct_only = prm->direct_only;
+    sa.min_multi = prm->min_multi; sa.max_multi = prm->max_multi; sa.nway_mask = prm->nway_mask;
+    sa.status = c->status_slice(div_up(n, select_tile())); sa.ticket = c->ticket();
+    sa.n_buckets = scal + SC_NBUCKETS;
+    sa.totals = reinterpret_cast<u32*>(scal + SC_CAND);
+    sa.cand_run = c->cand_run.as<u32>(); sa.cand_off = c->cand_off.as<u32>(); sa.cand_aux = nullptr;
+    launch_select(sa, fmt, n, st);
+    LAUNCHED(c); CHECK_LAUNCH(c);
+    if (need_counts) CUDA_TRY(c, cudaMemcpyAsync(c->h_perseq, c->per_seq.p, MB_MAX_SEQ * 8, cudaMemcpyDeviceToHost, st));
+    TRY(read_scalars(c));
+    const u32* hs32 = reinterpret_cast<const u32*>(c->h_scal);
+    const u64* hs64 = reinterpret_cast<const u64*>(c->h_scal);
+    const u32 n_runs = hs32[2 * SC_RUNS], n_cand = hs32[2 * SC_CAND], n_ccomp = hs32[2 * SC_CAND + 1];
+    c->stats.n_runs = n_runs; c->stats.n_buckets = hs64[SC_NBUCKETS]; c->stats.n_candidates = n_cand;
+    c->r_unique = n_runs;
+    cudaEventRecord(c->ev[EV_BUCKET], st);
+
+    if (mode == MB_MODE_SEED_ENUM) {
+        cudaEventRecord(c->ev[EV_DEDUP], st);
+        // matches = selected buckets; canonical order (D18) = by first position
+        TRY(c->reserve(c->sort_kA, (size_t)(n_cand + 8) * 8)); TRY(c->reserve(c->sort_kB, (size_t)(n_cand + 8) * 8));
+        TRY(c->reserve(c->sort_vA, (size_t)(n_cand + 8) * 8)); TRY(c->reserve(c->sort_vB, (size_t)(n_cand + 8) * 8));
+        TRY(c->reserve(c->ncomp, (size_t)(n_cand + 8) * 4));
+        TRY(c->reserve(c->out_len, (size_t)(n_cand + 8) * 4));
+        TRY(c->reserve(c->out_off, (size_t)(n_cand + 8) * 8));
+        TRY(c->reserve(c->out_seq, (size_t)(n_ccomp + 8) * 4));
+        TRY(c->reserve(c->out_start, (size_t)(n_ccomp + 8) * 8));
+        if (n_cand) {
+            EmitEnumArgs ea{};
+            ea.keys = kA; ea.vals = vA; ea.run_start = run_start; ea.cand_run = c->cand_run.as<u32>(); ea.cand_off = c->cand_off.as<u32>();
+            ea.totals = reinterpret_cast<u32*>(scal + SC_CAND);
+            u64 *skA = c->sort_kA.as<u64>(), *skB = c->sort_kB.as<u64>(), *svA = c->sort_vA.as<u64>(), *svB = c->sort_vB.as<u64>();
+            ea.sort_key = skA; ea.sort_val = svA; ea.ncomp = c->ncomp.as<u32>();
+            launch_enum_keys(ea, fmt, n_cand, st); LAUNCHED(c); CHECK_LAUNCH(c);
+            TRY(sort_records(c, &skA, &skB, &svA, &svB, n_cand, 0, fmt.pbits, false));
+            // component counts in sorted order -> offsets
+            // (ncomp was written in candidate order; permute through the sorted values inside the gather scan input)
+            OutputArgs oa{};
+            oa.n_cand = n_cand; oa.cand_off = c->cand_off.as<u32>(); oa.ncomp = c->ncomp.as<u32>();
+            oa.n_matches_ptr = scal + SC_NMATCH;
+            c->tmp_u64 = n_cand;
+            CUDA_TRY(c, cudaMemcpyAsync(scal + SC_NMATCH, &c->tmp_u64, 8, cudaMemcpyHostToDevice, st));
+            launch_uniq_ncomp(oa, svA, n_cand, st); LAUNCHED(c); CHECK_LAUNCH(c);
+            launch_scan_u32(c->ncomp.as<u32>(), n_cand, nullptr, c->out_off.as<u64>(), c->status_slice(div_up(n_cand, scan_tile())), c->ticket(),
+                            scal + SC_NCOMP, st);
+            LAUNCHED(c); CHECK_LAUNCH(c);
+            ea.sorted_val = svA; ea.out_off = c->out_off.as<u64>();
+            ea.out_len = c->out_len.as<u32>(); ea.out_seq = c->out_seq.as<u32>(); ea.out_start = c->out_start.as<i64>();
+            launch_enum_gather(ea, fmt, L, n_cand, st); LAUNCHED(c); CHECK_LAUNCH(c);
+        }
+        c->r_matches = n_cand; c->r_comps = n_ccomp;
+        cudaEventRecord(c->ev[EV_OUTPUT], st);
+        c->stats.n_matches = n_cand; c->stats.n_comps = n_ccomp;
+        c->have_result = true;
+        return MB_OK;
+    }
+
+    // ---- MODE_UNIQUE: a9 candidates (HashMatch + SetDirection)
+    const u64 bm_words = bases / 64 + 2;
+    TRY(c->reserve(c->comp_pos, (size_t)(n_ccomp + 8) * 4));
+    TRY(c->reserve(c->comp_gs, (size_t)(n_ccomp + 8)));
+    TRY(c->reserve(c->bitmap, bm_words * 8));
+    TRY(c->reserve(c->bmrank, (bm_words + 1) * 4));
+    TRY(c->reserve(c->slot_of, (size_t)(n_cand + 8) * 4));
+    TRY(c->reserve(c->cand_at, (size_t)(n_cand + 8) * 4));
+    TRY(c->reserve(c->cstate, (size_t)n_cand + 8));
+    TRY(c->reserve(c->covered, (size_t)n_cand + 8));
+    TRY(c->reserve(c->minrank, (size_t)(n_cand + 8) * 4));
+    TRY(c->reserve(c->ext_l, (size_t)(n_cand + 8) * 4));
+    TRY(c->reserve(c->ext_r, (size_t)(n_cand + 8) * 4));
+    u32 n_matches = 0;
+    u64 n_ocomp = 0;
+    if (n_cand) {
+        CUDA_TRY(c, cudaMemsetAsync(c->bitmap.p, 0, bm_words * 8, st));
+        CUDA_TRY(c, cudaMemsetAsync(c->cstate.p, 0xFF, n_cand, st));
+        CUDA_TRY(c, cudaMemsetAsync(c->covered.p, 0, n_cand, st));
+        EmitUniqueArgs eu{};
+        eu.keys = kA; eu.vals = vA; eu.run_start = run_start; eu.run_u = run_u;
+        eu.cand_run = c->cand_run.as<u32>(); eu.cand_off = c->cand_off.as<u32>(); eu.cand_aux = nullptr;
+        eu.totals = reinterpret_cast<u32*>(scal + SC_CAND);
+        eu.mode = mode; eu.comp_pos = c->comp_pos.as<u32>(); eu.comp_gs = c->comp_gs.as<u8>(); eu.bitmap = c->bitmap.as<u64>();
+        launch_emit_unique(eu, fmt, gt, n_cand, st); LAUNCHED(c); CHECK_LAUNCH(c);
+        launch_scan_popc(c->bitmap.as<u64>(), bm_words, c->bmrank.as<u32>(), c->status_slice(div_up(bm_words, scan_tile())), c->ticket(),
+                         scal + SC_BMTOTAL, st);
+        LAUNCHED(c); CHECK_LAUNCH(c);
+        DedupArgs da{};
+        da.packed = c->packed.as<u64>(); da.n_cand = n_cand;
+        da.cand_off = c->cand_off.as<u32>(); da.comp_pos = c->comp_pos.as<u32>(); da.comp_gs = c->comp_gs.as<u8>();
+        da.bitmap = c->bitmap.as<u64>(); da.bmrank = c->bmrank.as<u32>();
+        da.slot_of = c->slot_of.as<u32>(); da.cand_at = c->cand_at.as<u32>();
+        da.cstate = c->cstate.as<u8>(); da.covered = c->covered.as<u8>(); da.minrank = c->minrank.as<u32>();
+        da.ext_l = c->ext_l.as<u32>(); da.ext_r = c->ext_r.as<u32>();
+        da.n_undecided = reinterpret_cast<u32*>(scal + SC_UNDECIDED); da.n_extended = reinterpret_cast<u32*>(scal + SC_EXTENDED);
+        launch_build_slots(da, gt, st); LAUNCHED(c); CHECK_LAUNCH(c);
+        cudaEventRecord(c->ev_x[0], st);
+
+        // ---- a10 + a11: doubling batches in ascending seed order
+        u32 p = 0, batch = 4096;
+        u32* h_und = reinterpret_cast<u32*>((u64*)c->h_scal + SC_UNDECIDED);
+        while (p < n_cand) {
+            u32 q = (u32)std::min<u64>((u64)n_cand, (u64)p + batch);
+            launch_dd_extend(da, gt, sd, p, q, st); LAUNCHED(c);
+            ++c->stats.dedup_batches;
+            for (int iter = 0;; ++iter) {
+                CUDA_TRY(c, cudaMemsetAsync(da.n_undecided, 0, 4, st));
+                launch_dd_claim(da, gt, p, q, st); LAUNCHED(c);
+                launch_dd_decide(da, gt, p, q, st); LAUNCHED(c);
+                CUDA_TRY(c, cudaMemcpyAsync(h_und, da.n_undecided, 4, cudaMemcpyDeviceToHost, st));
+                CUDA_TRY(c, cudaStreamSynchronize(st));
+                ++c->stats.dedup_iters;
+                if (*h_und == 0) break;
+                if (iter > 100000) { snprintf(c->err, sizeof(c->err), "de-dup fix-point did not converge"); return MB_E_STATE; }
+            }
+            p = q;
+            batch = std::max(batch, p);
+        }
+        CHECK_LAUNCH(c);
+        cudaEventRecord(c->ev[EV_DEDUP], st);
+
+        // ---- a12: compact accepted candidates, canonical order, CSR
+        TRY(c->reserve(c->flags, (size_t)(n_cand + 8) * 4));
+        TRY(c->reserve(c->match_idx, (size_t)(n_cand + 8) * 4));
+        OutputArgs oa{};
+        oa.n_cand = n_cand; oa.cstate = da.cstate; oa.cand_off = da.cand_off; oa.comp_pos = da.comp_pos; oa.comp_gs = da.comp_gs;
+        oa.ext_l = da.ext_l; oa.ext_r = da.ext_r; oa.flags = c->flags.as<u32>(); oa.match_idx = c->match_idx.as<u32>();
+        oa.n_matches_ptr = scal + SC_NMATCH;
+        launch_uniq_flags(oa, st); LAUNCHED(c);
+        launch_scan_u32(oa.flags, n_cand, c->match_idx.as<u32>(), nullptr, c->status_slice(div_up(n_cand, scan_tile())), c->ticket(),
+                        scal + SC_NMATCH, st);
+        LAUNCHED(c); CHECK_LAUNCH(c);
+        TRY(read_scalars(c));
+        n_matches = (u32)hs64[SC_NMATCH];
+        c->stats.n_extended = hs32[2 * SC_EXTENDED];
+        TRY(c->reserve(c->sort_kA, (size_t)(n_matches + 8) * 8)); TRY(c->reserve(c->sort_kB, (size_t)(n_matches + 8) * 8));
+        TRY(c->reserve(c->sort_vA, (size_t)(n_matches + 8) * 8)); TRY(c->reserve(c->sort_vB, (size_t)(n_matches + 8) * 8));
+        TRY(c->reserve(c->ncomp, (size_t)(n_matches + 8) * 4));
+        TRY(c->reserve(c->out_len, (size_t)(n_matches + 8) * 4));
+        TRY(c->reserve(c->out_off, (size_t)(n_matches + 8) * 8));
+        if (n_matches) {
+            u64 *skA = c->sort_kA.as<u64>(), *skB = c->sort_kB.as<u64>(), *svA = c->sort_vA.as<u64>(), *svB = c->sort_vB.as<u64>();
+            oa.sort_key = skA; oa.sort_val = svA; oa.ncomp = c->ncomp.as<u32>();
+            int sbits = bits_for(maxlen);
+            launch_uniq_keys(oa, sbits, st); LAUNCHED(c); CHECK_LAUNCH(c);
+            TRY(sort_records(c, &skA, &skB, &svA, &svB, n_matches, 0, sbits + 6, false));
+            launch_uniq_tiefix(oa, skA, svA, L, n_matches, st); LAUNCHED(c);
+            launch_uniq_ncomp(oa, svA, n_matches, st); LAUNCHED(c);
+            launch_scan_u32(oa.ncomp, n_matches, nullptr, c->out_off.as<u64>(), c->status_slice(div_up(n_matches, scan_tile())), c->ticket(),
+                            scal + SC_NCOMP, st);
+            LAUNCHED(c); CHECK_LAUNCH(c);
+            TRY(read_scalars(c));
+            n_ocomp = hs64[SC_NCOMP];
+            TRY(c->reserve(c->out_seq, (size_t)(n_ocomp + 8) * 4));
+            TRY(c->reserve(c->out_start, (size_t)(n_ocomp + 8) * 8));
+            oa.out_off = c->out_off.as<u64>(); oa.out_len = c->out_len.as<u32>(); oa.out_seq = c->out_seq.as<u32>();
+            oa.out_start = c->out_start.as<i64>();
+            launch_uniq_gather(oa, svA, L, n_matches, st); LAUNCHED(c); CHECK_LAUNCH(c);
+        }
+    } else {
+        cudaEventRecord(c->ev_x[0], st);
+        cudaEventRecord(c->ev[EV_DEDUP], st);
+    }
+    cudaEventRecord(c->ev[EV_OUTPUT], st);
+    c->r_matches = n_matches; c->r_comps = n_ocomp;
+    c->stats.n_matches = n_matches; c->stats.n_comps = n_ocomp;
+    c->have_result = true;
+    return MB_OK;
+}
+
+int mb_fetch_result(mb_ctx* c, const mb_result** out) {
+    if (!c || !out) return MB_E_ARG;
+    if (!c->have_result) return MB_E_STATE;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    u64 nm = c->r_matches, nc = c->r_comps;
+    TRY(c->reserve_host(c->h_len, c->h_len_cap, (nm + 1) * 4));
+    TRY(c->reserve_host(c->h_off, c->h_off_cap, (nm + 1) * 8));
+    TRY(c->reserve_host(c->h_seq, c->h_seq_cap, (nc + 1) * 4));
+    TRY(c->reserve_host(c->h_start, c->h_start_cap, (nc + 1) * 8));
+    cudaEventRecord(c->ev_x[1], st);
+    if (nm) {
+        CUDA_TRY(c, cudaMemcpyAsync(c->h_len, c->out_len.p, nm * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(c, cudaMemcpyAsync(c->h_off, c->out_off.p, (nm + 1) * 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(c, cudaMemcpyAsync(c->h_seq, c->out_seq.p, nc * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(c, cudaMemcpyAsync(c->h_start, c->out_start.p, nc * 8, cudaMemcpyDeviceToHost, st));
+    } else {
+        ((u64*)c->h_off)[0] = 0;
+    }
+    cudaEventRecord(c->ev_x[2], st);
+    CUDA_TRY(c, cudaStreamSynchronize(st));
+    c->stats.d2h_bytes = nm ? nm * 4 + (nm + 1) * 8 + nc * 12 : 0;
+    mb_result& r = c->res;
+    r.n_matches = nm; r.n_comps = nc;
+    r.length = (const u32*)c->h_len; r.comp_off = (const u64*)c->h_off; r.comp_seq = (const u32*)c->h_seq; r.comp_start = (const i64*)c->h_start;
+    r.unique_mers = c->r_unique;
+    r.unique_mers_per_seq = (const u64*)c->h_perseq;
+    r.nseq = (u32)c->seq_len.size();
+    // stage timings
+    auto ms = [&](cudaEvent_t a, cudaEvent_t b) { float t = 0; if (cudaEventElapsedTime(&t, a, b) != cudaSuccess) { cudaGetLastError(); t = 0; } return t; };
+    c->stats.ms_extract = ms(c->ev[EV_START], c->ev[EV_EXTRACT]);
+    c->stats.ms_sort = ms(c->ev[EV_EXTRACT], c->ev[EV_SORT]);
+    c->stats.ms_bucket = ms(c->ev[EV_SORT], c->ev[EV_BUCKET]);
+    c->stats.ms_dedup = ms(c->ev[EV_BUCKET], c->ev[EV_DEDUP]);
+    c->stats.ms_output = ms(c->ev[EV_DEDUP], c->ev[EV_OUTPUT]);
+    c->stats.ms_total_device = ms(c->ev[EV_START], c->ev[EV_OUTPUT]);
+    c->stats.ms_d2h = ms(c->ev_x[1], c->ev_x[2]);
+    *out = &c->res;
+    return MB_OK;
+}
+
+int mb_find(mb_ctx* c, const mb_params* prm, const mb_result** out) {
+    TRY(mb_find_device(c, prm));
+    return mb_fetch_result(c, out);
+}
+
+int mb_get_stats(mb_ctx* c, mb_stats* out) {
+    if (!c || !out) return MB_E_ARG;
+    *out = c->stats;
+    return MB_OK;
+}
+
+int mb_get_mers(mb_ctx* c, int seq, uint64_t* out_mers, uint64_t capacity, uint64_t* out_n) {
+    if (!c || seq < 0 || (size_t)seq >= c->seq_len.size() || !out_n) return MB_E_ARG;
+    if (!c->seed_set) return MB_E_SEED;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    u64 len = c->seq_len[seq];
+    u64 n = len >= (u64)c->sd.L ? len - c->sd.L + 1 : 0;
+    *out_n = n;
+    if (n == 0) return MB_OK;
+    if (!out_mers || capacity < n) return MB_E_ARG;
+    GenomeTable gt{};
+    gt.nseq = (u32)c->seq_len.size();
+    for (u32 g = 0; g < gt.nseq; ++g) { gt.word_base[g] = c->seq_word_base[g]; gt.len[g] = (u32)c->seq_len[g]; }
+    RecFmt fmt{}; fmt.kbits = 2 * c->sd.w;
+    TRY(c->reserve(c->mers_tmp, n * 8));
+    launch_mers(c->packed.as<u64>(), gt, c->sd, fmt, seq, c->mers_tmp.as<u64>(), c->stream);
+    CHECK_LAUNCH(c);
+    CUDA_TRY(c, cudaMemcpyAsync(out_mers, c->mers_tmp.p, n * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return MB_OK;
+}
+
+int mb_get_sml(mb_ctx* c, int seq, uint32_t* out_pos, uint64_t capacity, uint64_t* out_n) {
+    if (!c || seq < 0 || (size_t)seq >= c->seq_len.size() || !out_n) return MB_E_ARG;
+    if (!c->have_result || !c->sorted_keys) return MB_E_STATE;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    u64 len = c->seq_len[seq];
+    u64 n = len >= (u64)c->sd.L ? len - c->sd.L + 1 : 0;
+    *out_n = n;
+    if (n == 0) return MB_OK;
+    if (!out_pos || capacity < n) return MB_E_ARG;
+    // debugging / .sslist export path: filter the globally sorted records on the host
+    u32 total = c->n_seeds;
+    std::vector<u64> rec(total);
+    const u64* src = c->fmt.wide ? c->sorted_vals : c->sorted_keys;
+    CUDA_TRY(c, cudaMemcpyAsync(rec.data(), src, (size_t)total * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    u64 k = 0;
+    for (u32 i = 0; i < total; ++i)
+        if (rec_genome(c->fmt, rec[i]) == (u32)seq) out_pos[k++] = rec_pos(c->fmt, rec[i]);
+    return k == n ? MB_OK : MB_E_STATE;
+}
+
+} // extern "C"

@@ -1,0 +1,103 @@
+// kernels.h — host-side launchers of the pipeline kernels (one translation unit per stage).
+#pragma once
+#include "common.cuh"
+
+// internal copies of the public mode constants (kernels do not include the public header)
+#define MB_MODE_UNIQUE_ 0
+#define MB_MODE_SEED_ENUM_ 1
+#define MB_MODE_UNIQUE_COUNT_ 2
+#define MB_MODE_PAIRWISE_ 3
+
+// ---- kernels_seed.cu
+struct ExtractArgs;
+void launch_pack(const u8* d_ascii, u64 len, u64* d_words, u64 n_words, cudaStream_t st);
+u32 extract_tile_size();
+void launch_extract_records(const u64* d_packed, u64* d_keys, u64* d_vals, u32* d_hist, int npass, const GenomeTable& gt,
+                            const SeedDev& sd, const RecFmt& fmt, const u32* d_tile_first, u32 n_tiles, cudaStream_t st);
+void launch_mers(const u64* d_packed, const GenomeTable& gt, const SeedDev& sd, const RecFmt& fmt, int genome, u64* d_mers, cudaStream_t st);
+void launch_hist(const u64* d_keys, u32 n, int shift0, int kbits, int npass, u32* d_hist, cudaStream_t st);
+
+// ---- kernels_radix.cu
+size_t radix_smem_bytes(bool has_val);
+u32 radix_tile_size();
+void launch_scan_hist(const u32* d_hist, u32* d_base, int npass, cudaStream_t st);
+cudaError_t launch_onesweep(const u64* kin, u64* kout, const u64* vin, u64* vout, u32 n, const u32* d_digit_base, u64* d_lookback,
+                            u32* d_ticket, int shift, int bits, cudaStream_t st);
+
+// ---- kernels_bucket.cu
+u32 find_runs_tile();
+void launch_find_runs(const u64* keys, const u64* vals, u32 n, const RecFmt& fmt, u32* run_start, u32* run_u, u64* status, u32* ticket,
+                      u64* per_seq_count, u32* totals, cudaStream_t st);
+struct SelectArgs {
+    const u64* keys; const u64* vals;
+    const u32* run_start; const u32* run_u;
+    const u32* n_runs_ptr;
+    int mode, direct_only;
+    u64 min_multi, max_multi, nway_mask;
+    u64* status; u32* ticket;
+    u64* n_buckets;
+    u32* totals;     // [0] candidates, [1] components
+    u32* cand_run; u32* cand_off; u32* cand_aux;
+};
+u32 select_tile();
+void launch_select(const SelectArgs& a, const RecFmt& fmt, u32 n_runs_upper, cudaStream_t st);
+struct EmitUniqueArgs {
+    const u64* keys; const u64* vals;
+    const u32* run_start; const u32* run_u;
+    const u32* cand_run; const u32* cand_off; const u32* cand_aux;
+    const u32* totals;
+    int mode;
+    u32* comp_pos; u8* comp_gs;
+    u64* bitmap;
+};
+void launch_emit_unique(const EmitUniqueArgs& a, const RecFmt& fmt, const GenomeTable& gt, u32 n_cand_upper, cudaStream_t st);
+struct EmitEnumArgs {
+    const u64* keys; const u64* vals;
+    const u32* run_start; const u32* cand_run; const u32* cand_off; const u32* totals;
+    u64* sort_key; u64* sort_val; u32* ncomp;
+    const u64* sorted_val; const u64* out_off;
+    u32* out_len; u32* out_seq; i64* out_start;
+};
+void launch_enum_keys(const EmitEnumArgs& a, const RecFmt& fmt, u32 n_upper, cudaStream_t st);
+void launch_enum_gather(const EmitEnumArgs& a, const RecFmt& fmt, u32 seedL, u32 n_upper, cudaStream_t st);
+u32 scan_tile();
+void launch_scan_u32(const u32* in, u64 n, u32* out32, u64* out64, u64* status, u32* ticket, u64* total_out, cudaStream_t st);
+void launch_scan_popc(const u64* in, u64 n, u32* out32, u64* status, u32* ticket, u64* total_out, cudaStream_t st);
+
+// ---- kernels_dedup.cu
+struct DedupArgs {
+    const u64* packed;
+    u32 n_cand;
+    const u32* cand_off; const u32* comp_pos; const u8* comp_gs;
+    const u64* bitmap; const u32* bmrank;
+    u32* slot_of;    // candidate -> slot
+    u32* cand_at;    // slot -> candidate
+    u8* cstate;      // 0 undecided, 1 accepted, 2 dropped, 0xFF not reached
+    u8* covered;     // per slot
+    u32* minrank;    // per slot
+    u32* ext_l; u32* ext_r;
+    u32* n_undecided; u32* n_extended;
+};
+void launch_build_slots(const DedupArgs& a, const GenomeTable& gt, cudaStream_t st);
+void launch_dd_extend(const DedupArgs& a, const GenomeTable& gt, const SeedDev& sd, u32 p, u32 q, cudaStream_t st);
+void launch_dd_claim(const DedupArgs& a, const GenomeTable& gt, u32 p, u32 q, cudaStream_t st);
+void launch_dd_decide(const DedupArgs& a, const GenomeTable& gt, u32 p, u32 q, cudaStream_t st);
+
+// ---- kernels_output.cu
+struct OutputArgs {
+    u32 n_cand;
+    const u8* cstate;
+    const u32* cand_off; const u32* comp_pos; const u8* comp_gs;
+    const u32* ext_l; const u32* ext_r;
+    u32* flags; const u32* match_idx;
+    const u64* n_matches_ptr;
+    u64* sort_key; u64* sort_val;
+    u32* ncomp;
+    const u64* out_off;
+    u32* out_len; u32* out_seq; i64* out_start;
+};
+void launch_uniq_flags(const OutputArgs& a, cudaStream_t st);
+void launch_uniq_keys(const OutputArgs& a, int sbits, cudaStream_t st);
+void launch_uniq_tiefix(const OutputArgs& a, const u64* skey, u64* sval, u32 L, u32 n_upper, cudaStream_t st);
+void launch_uniq_ncomp(const OutputArgs& a, const u64* sval, u32 n_upper, cudaStream_t st);
+void launch_uniq_gather(const OutputArgs& a, const u64* sval, u32 L, u32 n_upper, cudaStream_t st);

@@ -1,0 +1,387 @@
+// kernels_bucket.cu — a5, a6 (bucket formation), a7, a8 of SURVEY.md §8a.
+//
+//  k_find_runs      equal-seed runs of the sorted records = the IdmerList buckets that libMems'
+//                   MatchFinder::FindMatchSeeds hands to EnumerateMatches (call site
+//                   /root/reference/src/SeedMatchEnumerator.h:61); counts distinct seeds =
+//                   SortedMerList::UniqueMerCount (/root/reference/src/uniqueMerCount.cpp:39).
+//  k_select         per-bucket policy:
+//                   MODE_UNIQUE   /root/reference/src/UniqueMatchFinder.cpp:36-60 (keep genomes that
+//                                 occur exactly once; need >= 2), MaskedMemHash mask test
+//                                 (/root/reference/src/mauveAligner.cpp:525-531)
+//                   MODE_SEED_ENUM /root/reference/src/SeedMatchEnumerator.h:71-123 (multiplicity
+//                                 window on the un-projected bucket, forward-only projection)
+//  k_emit_unique    MemHash::HashMatch + SetDirection (same body as SeedMatchEnumerator.h:127-141)
+//  k_emit_enum      SeedMatchEnumerator::HashMatch component list (position+1, sign vs first)
+#include "common.cuh"
+#include "kernels.h"
+#include "lookback.cuh"
+
+// ------------------------------------------------------------------------------------ find runs
+#define FR_NT 256
+#define FR_IPT 8
+#define FR_TILE (FR_NT * FR_IPT)
+
+struct Rec { u64 key; u32 g; };
+
+__device__ __forceinline__ Rec load_rec(const RecFmt& f, const u64* __restrict__ k, const u64* __restrict__ v, u64 i) {
+    Rec r;
+    u64 kk = k[i];
+    if (f.wide) { r.key = kk; r.g = (u32)(v[i] >> 33); }
+    else { r.key = kk >> f.kshift; r.g = (u32)((kk >> (f.pbits + 1)) & ((1u << f.gbits) - 1)); }
+    return r;
+}
+
+__global__ void __launch_bounds__(FR_NT) k_find_runs(const u64* __restrict__ keys, const u64* __restrict__ vals, u32 n, RecFmt fmt,
+                                                     u32* __restrict__ run_start, u32* __restrict__ run_u, u64* status, u32* ticket,
+                                                     u64* __restrict__ per_seq_count /*[nseq] or null*/, u32* __restrict__ totals /*[2]*/) {
+    __shared__ u32 sCnt[FR_IPT * (FR_NT / 32)]; // heads | uniq << 16 per (row, warp)
+    __shared__ u32 sPre[FR_IPT * (FR_NT / 32)];
+    __shared__ u32 sSeq[MB_MAX_SEQ];
+    __shared__ u32 sTile;
+    __shared__ u64 sExcl;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) sTile = atomicAdd(ticket, 1u);
+    if (tid < MB_MAX_SEQ) sSeq[tid] = 0;
+    __syncthreads();
+    const u32 tile = sTile;
+    const u64 base = (u64)tile * FR_TILE;
+    u32 headb[FR_IPT], uniqb[FR_IPT];
+#pragma unroll
+    for (int k = 0; k < FR_IPT; ++k) {
+        u64 i = base + (u64)k * FR_NT + tid;
+        bool valid = i < n;
+        Rec c{~0ull, 0xFFFFFFFFu}, p{~0ull, 0xFFFFFFFFu}, q{~0ull, 0xFFFFFFFFu};
+        if (valid) c = load_rec(fmt, keys, vals, i);
+        // neighbours: shuffle inside the warp, global load at the warp edges
+        p.key = __shfl_up_sync(0xFFFFFFFFu, c.key, 1); p.g = __shfl_up_sync(0xFFFFFFFFu, c.g, 1);
+        q.key = __shfl_down_sync(0xFFFFFFFFu, c.key, 1); q.g = __shfl_down_sync(0xFFFFFFFFu, c.g, 1);
+        if (valid && lane == 0 && i > 0) p = load_rec(fmt, keys, vals, i - 1);
+        if (valid && lane == 31 && i + 1 < n) q = load_rec(fmt, keys, vals, i + 1);
+        bool head = valid && (i == 0 || p.key != c.key);
+        bool newg = valid && (head || p.g != c.g);
+        bool last = valid && (i + 1 >= n || q.key != c.key || q.g != c.g);
+        bool uniq = newg && last;
+        if (per_seq_count && newg) atomicAdd(&sSeq[c.g], 1u);
+        headb[k] = __ballot_sync(0xFFFFFFFFu, head);
+        uniqb[k] = __ballot_sync(0xFFFFFFFFu, uniq);
+        if (lane == 0) sCnt[k * (FR_NT / 32) + warp] = __popc(headb[k]) | (__popc(uniqb[k]) << 16);
+    }
+    __syncthreads();
+    if (warp == 0) {
+        // 64 (row, warp) counts, 2 per lane, exclusive scan in (row, warp) order
+        const int NE = FR_IPT * (FR_NT / 32);
+        u32 a = sCnt[2 * lane], b = sCnt[2 * lane + 1];
+        u64 va = (u64)(a & 0xFFFF) | ((u64)(a >> 16) << 31), vb = (u64)(b & 0xFFFF) | ((u64)(b >> 16) << 31);
+        u64 s = va + vb, x = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            u64 y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+            if (lane >= o) x += y;
+        }
+        u64 ex = x - s;
+        // tile-local exclusive prefixes fit 16 bits each (tile = 2048)
+        sPre[2 * lane] = (u32)(ex & 0xFFFF) | ((u32)((ex >> 31) & 0xFFFF) << 16);
+        u64 ex2 = ex + va;
+        sPre[2 * lane + 1] = (u32)(ex2 & 0xFFFF) | ((u32)((ex2 >> 31) & 0xFFFF) << 16);
+        u64 agg = __shfl_sync(0xFFFFFFFFu, x, 31);
+        u64 excl = lookback_exclusive(status, tile, agg);
+        if (lane == 0) {
+            sExcl = excl;
+            if (base + FR_TILE >= n) { // last tile: totals + sentinels
+                u64 tot = excl + agg;
+                u32 nr = (u32)(tot & 0x7FFFFFFFu), nu = (u32)(tot >> 31);
+                totals[0] = nr; totals[1] = nu;
+                run_start[nr] = n;
+                if (run_u) run_u[nr] = nu;
+            }
+        }
+        (void)NE;
+    }
+    __syncthreads();
+    const u64 excl = sExcl;
+    const u32 eh = (u32)(excl & 0x7FFFFFFFu), eu = (u32)(excl >> 31);
+#pragma unroll
+    for (int k = 0; k < FR_IPT; ++k) {
+        if ((headb[k] >> lane) & 1) {
+            u32 pre = sPre[k * (FR_NT / 32) + warp];
+            u32 lt = (1u << lane) - 1;
+            u32 r = eh + (pre & 0xFFFF) + __popc(headb[k] & lt);
+            run_start[r] = (u32)(base + (u64)k * FR_NT + tid);
+            if (run_u) run_u[r] = eu + (pre >> 16) + __popc(uniqb[k] & lt);
+        }
+    }
+    if (per_seq_count && tid < MB_MAX_SEQ && sSeq[tid]) atomicAdd((unsigned long long*)&per_seq_count[tid], (unsigned long long)sSeq[tid]);
+}
+
+void launch_find_runs(const u64* keys, const u64* vals, u32 n, const RecFmt& fmt, u32* run_start, u32* run_u, u64* status,
+                      u32* ticket, u64* per_seq_count, u32* totals, cudaStream_t st) {
+    if (n == 0) return;
+    k_find_runs<<<div_up(n, FR_TILE), FR_NT, 0, st>>>(keys, vals, n, fmt, run_start, run_u, status, ticket, per_seq_count, totals);
+}
+u32 find_runs_tile() { return FR_TILE; }
+
+// --------------------------------------------------------------------------------------- select
+#define SL_NT 256
+#define SL_IPT 4
+#define SL_TILE (SL_NT * SL_IPT)
+
+// value packing for the (candidates, components) pair: 30 + 32 bits
+#define SL_PACK(c, m) ((u64)(c) | ((u64)(m) << 30))
+
+__global__ void __launch_bounds__(SL_NT) k_select(SelectArgs a, RecFmt fmt) {
+    __shared__ u64 scratch[SL_NT / 32 + 1];
+    __shared__ u32 sTile;
+    __shared__ u64 sExcl;
+    const int tid = threadIdx.x;
+    if (tid == 0) sTile = atomicAdd(a.ticket, 1u);
+    __syncthreads();
+    const u32 tile = sTile;
+    const u32 n_runs = *a.n_runs_ptr;
+    if ((u64)tile * SL_TILE >= n_runs) return; // grid is sized for the upper bound n_runs <= n
+    const u64 r0 = (u64)tile * SL_TILE + (u64)tid * SL_IPT;
+    u32 ncand[SL_IPT], ncomp[SL_IPT];
+    u32 nb = 0;
+    u64 mine = 0;
+#pragma unroll
+    for (int j = 0; j < SL_IPT; ++j) {
+        u64 r = r0 + j;
+        ncand[j] = 0; ncomp[j] = 0;
+        if (r >= n_runs) continue;
+        u32 s = a.run_start[r], e = a.run_start[r + 1];
+        u32 len = e - s;
+        if (len < 2) continue;
+        ++nb;
+        if (a.mode == MB_MODE_SEED_ENUM_) {
+            if ((u64)len > a.max_multi || (u64)len < a.min_multi) continue;
+            u32 m = len;
+            if (a.direct_only) {
+                // forward = same strand bit as the first (lowest position) occurrence
+                u64 v0 = fmt.wide ? a.vals[s] : a.keys[s];
+                u32 s0 = rec_strand(v0), fw = 0;
+                for (u32 i = s; i < e; ++i) {
+                    u64 v = fmt.wide ? a.vals[i] : a.keys[i];
+                    fw += rec_strand(v) == s0;
+                }
+                if (fw != len) { // found_reverse: forward-only projection, needs > 1 component
+                    if (fw < 2) continue;
+                    m = fw;
+                }
+            }
+            ncand[j] = 1; ncomp[j] = m;
+        } else {
+            u32 u = a.run_u[r + 1] - a.run_u[r];
+            if (u < 2) continue;
+            if (a.mode == MB_MODE_PAIRWISE_) {
+                ncand[j] = u * (u - 1) / 2; ncomp[j] = u * (u - 1);
+            } else {
+                if (a.nway_mask) {
+                    if (u != (u32)__popcll(a.nway_mask)) continue;
+                    u64 present = 0;
+                    for (u32 i = s; i < e; ++i) {
+                        u32 g = rec_genome(fmt, fmt.wide ? a.vals[i] : a.keys[i]);
+                        bool first = i == s || rec_genome(fmt, fmt.wide ? a.vals[i - 1] : a.keys[i - 1]) != g;
+                        bool lastg = i + 1 == e || rec_genome(fmt, fmt.wide ? a.vals[i + 1] : a.keys[i + 1]) != g;
+                        if (first && lastg) present |= 1ull << g;
+                    }
+                    if (present != a.nway_mask) continue;
+                }
+                ncand[j] = 1; ncomp[j] = u;
+            }
+        }
+        mine += SL_PACK(ncand[j], ncomp[j]);
+    }
+    u64 total;
+    u64 ex = block_excl_scan_u64<SL_NT>(mine, scratch, total);
+    // bucket statistic
+    if (nb) atomicAdd((unsigned long long*)a.n_buckets, (unsigned long long)nb);
+    if (tid < 32) {
+        u64 excl = lookback_exclusive(a.status, tile, total);
+        if (tid == 0) {
+            sExcl = excl;
+            if ((u64)(tile + 1) * SL_TILE >= n_runs) {
+                u64 tot = excl + total;
+                u32 nc = (u32)(tot & ((1u << 30) - 1));
+                u32 nm = (u32)(tot >> 30);
+                a.totals[0] = nc; a.totals[1] = nm;
+                a.cand_off[nc] = nm;
+            }
+        }
+    }
+    __syncthreads();
+    u64 pre = sExcl + ex;
+#pragma unroll
+    for (int j = 0; j < SL_IPT; ++j) {
+        if (!ncand[j]) continue;
+        u32 c = (u32)(pre & ((1u << 30) - 1));
+        u32 off = (u32)(pre >> 30);
+        u32 per = ncomp[j] / ncand[j];
+        for (u32 t = 0; t < ncand[j]; ++t) {
+            a.cand_run[c + t] = (u32)(r0 + j);
+            a.cand_off[c + t] = off + t * per;
+            if (a.cand_aux) a.cand_aux[c + t] = t;
+        }
+        pre += SL_PACK(ncand[j], ncomp[j]);
+    }
+}
+
+void launch_select(const SelectArgs& a, const RecFmt& fmt, u32 n_runs_upper, cudaStream_t st) {
+    if (n_runs_upper == 0) return;
+    k_select<<<div_up(n_runs_upper, SL_TILE), SL_NT, 0, st>>>(a, fmt);
+}
+u32 select_tile() { return SL_TILE; }
+
+// ---------------------------------------------------------------------------------- emit unique
+// One thread per candidate: gather the unique-genome members of its bucket into the candidate CSR
+// (comp_pos, comp_gs = genome | reverse<<7) and set the candidate's bit in the (first genome,
+// position) bitmap used by the de-dup stage.
+__global__ void __launch_bounds__(256) k_emit_unique(EmitUniqueArgs a, RecFmt fmt, GenomeTable gt) {
+    u32 c = blockIdx.x * blockDim.x + threadIdx.x;
+    u32 nc = a.totals[0];
+    if (c >= nc) return;
+    u32 r = a.cand_run[c];
+    u32 s = a.run_start[r], e = a.run_start[r + 1];
+    u32 off = a.cand_off[c];
+    u32 k = 0, strand0 = 0;
+    int pa = -1, pb = -1;
+    if (a.mode == MB_MODE_PAIRWISE_) {
+        // pair index t -> (pa, pb) with pa < pb in lexicographic order over the unique list
+        u32 u = a.run_u[r + 1] - a.run_u[r];
+        u32 t = a.cand_aux[c];
+        u32 x = 0;
+        while (t >= u - 1 - x) { t -= u - 1 - x; ++x; }
+        pa = (int)x; pb = (int)(x + 1 + t);
+    }
+    u32 prev_g = 0xFFFFFFFFu;
+    u32 ui = 0;
+    for (u32 i = s; i < e; ++i) {
+        u64 v = fmt.wide ? a.vals[i] : a.keys[i];
+        u32 g = rec_genome(fmt, v);
+        bool first = g != prev_g;
+        prev_g = g;
+        bool lastg = i + 1 == e || rec_genome(fmt, fmt.wide ? a.vals[i + 1] : a.keys[i + 1]) != g;
+        if (!(first && lastg)) continue;
+        bool take = pa < 0 || (int)ui == pa || (int)ui == pb;
+        ++ui;
+        if (!take) continue;
+        u32 p = rec_pos(fmt, v), sb = rec_strand(v);
+        if (k == 0) {
+            strand0 = sb;
+            u64 gp = gt.base_base[g] + p;
+            atomicOr((unsigned long long*)&a.bitmap[gp >> 6], 1ull << (gp & 63));
+        }
+        a.comp_pos[off + k] = p;
+        a.comp_gs[off + k] = (u8)(g | ((sb != strand0) ? 0x80u : 0u));
+        ++k;
+    }
+}
+
+void launch_emit_unique(const EmitUniqueArgs& a, const RecFmt& fmt, const GenomeTable& gt, u32 n_cand_upper, cudaStream_t st) {
+    if (n_cand_upper == 0) return;
+    k_emit_unique<<<div_up(n_cand_upper, 256), 256, 0, st>>>(a, fmt, gt);
+}
+
+// ------------------------------------------------------------------------------------ emit enum
+// MODE_SEED_ENUM: sort key of a match = its first emitted position (unique per bucket).
+__global__ void __launch_bounds__(256) k_enum_keys(EmitEnumArgs a, RecFmt fmt) {
+    u32 c = blockIdx.x * blockDim.x + threadIdx.x;
+    u32 nc = a.totals[0];
+    if (c >= nc) return;
+    u32 r = a.cand_run[c];
+    u32 s = a.run_start[r];
+    u64 v = fmt.wide ? a.vals[s] : a.keys[s];
+    a.sort_key[c] = (u64)rec_pos(fmt, v);
+    a.sort_val[c] = c;
+    a.ncomp[c] = a.cand_off[c + 1] - a.cand_off[c];
+}
+
+// after sorting: out slot j <- candidate perm[j]; comps written at out_off[j]
+__global__ void __launch_bounds__(256) k_enum_gather(EmitEnumArgs a, RecFmt fmt, u32 seedL) {
+    u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    u32 nc = a.totals[0];
+    if (j >= nc) return;
+    u32 c = (u32)a.sorted_val[j];
+    u32 r = a.cand_run[c];
+    u32 s = a.run_start[r], e = a.run_start[r + 1];
+    u32 m = a.cand_off[c + 1] - a.cand_off[c];
+    bool project = m != e - s;
+    u64 o = a.out_off[j];
+    a.out_len[j] = seedL;
+    u32 s0 = rec_strand(fmt.wide ? a.vals[s] : a.keys[s]);
+    for (u32 i = s; i < e; ++i) {
+        u64 v = fmt.wide ? a.vals[i] : a.keys[i];
+        bool rev = rec_strand(v) != s0;
+        if (project && rev) continue;
+        i64 st = (i64)rec_pos(fmt, v) + 1;
+        a.out_seq[o] = 0;
+        a.out_start[o] = rev ? -st : st;
+        ++o;
+    }
+}
+
+void launch_enum_keys(const EmitEnumArgs& a, const RecFmt& fmt, u32 n_upper, cudaStream_t st) {
+    if (n_upper) k_enum_keys<<<div_up(n_upper, 256), 256, 0, st>>>(a, fmt);
+}
+void launch_enum_gather(const EmitEnumArgs& a, const RecFmt& fmt, u32 seedL, u32 n_upper, cudaStream_t st) {
+    if (n_upper) k_enum_gather<<<div_up(n_upper, 256), 256, 0, st>>>(a, fmt, seedL);
+}
+
+// ---------------------------------------------------------------------------------- generic scan
+// out[i] = sum_{j<i} f(in, j); total -> *total_out.  Single pass, decoupled look-back.
+#define SC_NT 256
+#define SC_IPT 8
+#define SC_TILE (SC_NT * SC_IPT)
+template <int KIND> // 0: u32 values, 1: popcount of u64 words
+__global__ void __launch_bounds__(SC_NT) k_scan(const void* __restrict__ in, u64 n, u32* __restrict__ out32, u64* __restrict__ out64,
+                                                u64* status, u32* ticket, u64* total_out) {
+    __shared__ u64 scratch[SC_NT / 32 + 1];
+    __shared__ u32 sTile;
+    __shared__ u64 sExcl;
+    const int tid = threadIdx.x;
+    if (tid == 0) sTile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const u32 tile = sTile;
+    const u64 i0 = (u64)tile * SC_TILE + (u64)tid * SC_IPT;
+    u32 v[SC_IPT];
+    u64 mine = 0;
+#pragma unroll
+    for (int j = 0; j < SC_IPT; ++j) {
+        u64 i = i0 + j;
+        v[j] = 0;
+        if (i < n) v[j] = KIND == 0 ? reinterpret_cast<const u32*>(in)[i] : (u32)__popcll(reinterpret_cast<const u64*>(in)[i]);
+        mine += v[j];
+    }
+    u64 total;
+    u64 ex = block_excl_scan_u64<SC_NT>(mine, scratch, total);
+    if (tid < 32) {
+        u64 excl = lookback_exclusive(status, tile, total);
+        if (tid == 0) {
+            sExcl = excl;
+            if ((u64)(tile + 1) * SC_TILE >= n) {
+                if (total_out) *total_out = excl + total;
+                if (out64) out64[n] = excl + total;
+                if (out32) out32[n] = (u32)(excl + total);
+            }
+        }
+    }
+    __syncthreads();
+    u64 pre = sExcl + ex;
+#pragma unroll
+    for (int j = 0; j < SC_IPT; ++j) {
+        u64 i = i0 + j;
+        if (i < n) {
+            if (out64) out64[i] = pre;
+            if (out32) out32[i] = (u32)pre;
+        }
+        pre += v[j];
+    }
+}
+
+u32 scan_tile() { return SC_TILE; }
+void launch_scan_u32(const u32* in, u64 n, u32* out32, u64* out64, u64* status, u32* ticket, u64* total_out, cudaStream_t st) {
+    if (n == 0) return;
+    k_scan<0><<<div_up(n, SC_TILE), SC_NT, 0, st>>>(in, n, out32, out64, status, ticket, total_out);
+}
+void launch_scan_popc(const u64* in, u64 n, u32* out32, u64* status, u32* ticket, u64* total_out, cudaStream_t st) {
+    if (n == 0) return;
+    k_scan<1><<<div_up(n, SC_TILE), SC_NT, 0, st>>>(in, n, out32, nullptr, status, ticket, total_out);
+}

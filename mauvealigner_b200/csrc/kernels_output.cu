@@ -1,0 +1,111 @@
+// kernels_output.cu — a12 of SURVEY.md §8a: MemHash::GetMatchList -> MatchList, in the canonical
+// order of SURVEY.md Appendix A D18 (call sites /root/reference/src/progressiveMauve.cpp:545,
+// src/mauveAligner.cpp:583).  Accepted candidates are compacted, sorted by a 64-bit prefix of the
+// D18 key with the radix sort, ties are finished with the full comparator, and the CSR is gathered.
+#include "common.cuh"
+#include "kernels.h"
+
+__global__ void __launch_bounds__(256) k_uniq_flags(OutputArgs a) {
+    u32 c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < a.n_cand) a.flags[c] = a.cstate[c] == 1 ? 1u : 0u;
+}
+
+// D18 for MODE_UNIQUE compares the dense vectors (|start[0]|..|start[N-1]|), 0 = absent.  For sparse
+// matches this is: larger first genome index sorts first; then its start; then the next component...
+__global__ void __launch_bounds__(256) k_uniq_keys(OutputArgs a, int sbits) {
+    u32 c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= a.n_cand || a.cstate[c] != 1) return;
+    u32 mi = a.match_idx[c];
+    u32 off = a.cand_off[c];
+    u32 f = a.comp_gs[off] & 0x7F;
+    u64 st = (u64)a.comp_pos[off] - a.ext_l[c] + 1;
+    a.sort_key[mi] = ((u64)(MB_MAX_SEQ - 1 - f) << sbits) | st;
+    a.sort_val[mi] = c;
+}
+
+struct MView { u32 off, m, el, er; };
+__device__ __forceinline__ MView mview(const OutputArgs& a, u32 c) {
+    MView v; v.off = a.cand_off[c]; v.m = a.cand_off[c + 1] - v.off; v.el = a.ext_l[c]; v.er = a.ext_r[c];
+    return v;
+}
+__device__ __forceinline__ u32 abs_start(const OutputArgs& a, const MView& v, u32 k) {
+    u8 gs = a.comp_gs[v.off + k];
+    return a.comp_pos[v.off + k] - ((gs & 0x80) ? v.er : v.el) + 1;
+}
+// full D18 comparator: A < B ?
+__device__ bool d18_less(const OutputArgs& a, u32 ca, u32 cb, u32 L) {
+    MView A = mview(a, ca), B = mview(a, cb);
+    u32 k = 0;
+    for (;; ++k) {
+        bool ea = k >= A.m, eb = k >= B.m;
+        if (ea || eb) {
+            if (ea && eb) break;
+            return ea; // the one that still has components holds a non-zero where the other has 0
+        }
+        u32 ga = a.comp_gs[A.off + k] & 0x7F, gb = a.comp_gs[B.off + k] & 0x7F;
+        if (ga != gb) return ga > gb; // smaller genome index = non-zero earlier = larger vector
+        u32 sa = abs_start(a, A, k), sb = abs_start(a, B, k);
+        if (sa != sb) return sa < sb;
+    }
+    for (k = 0; k < A.m; ++k) {
+        bool ra = a.comp_gs[A.off + k] & 0x80, rb = a.comp_gs[B.off + k] & 0x80;
+        if (ra != rb) return rb;
+    }
+    return (L + A.el + A.er) < (L + B.el + B.er);
+}
+
+__global__ void __launch_bounds__(256) k_uniq_tiefix(OutputArgs a, const u64* __restrict__ skey, u64* __restrict__ sval, u32 L) {
+    u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    u32 n = (u32)*a.n_matches_ptr;
+    if (j >= n) return;
+    u64 kj = skey[j];
+    if (j > 0 && skey[j - 1] == kj) return;
+    u32 e = j + 1;
+    while (e < n && skey[e] == kj) ++e;
+    for (u32 i = j + 1; i < e; ++i) { // insertion sort of a (tiny) tie run
+        u64 x = sval[i];
+        u32 t = i;
+        while (t > j && d18_less(a, (u32)x, (u32)sval[t - 1], L)) { sval[t] = sval[t - 1]; --t; }
+        sval[t] = x;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_uniq_ncomp(OutputArgs a, const u64* __restrict__ sval) {
+    u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    u32 n = (u32)*a.n_matches_ptr;
+    if (j >= n) return;
+    u32 c = (u32)sval[j];
+    a.ncomp[j] = a.cand_off[c + 1] - a.cand_off[c];
+}
+
+__global__ void __launch_bounds__(256) k_uniq_gather(OutputArgs a, const u64* __restrict__ sval, u32 L) {
+    u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    u32 n = (u32)*a.n_matches_ptr;
+    if (j >= n) return;
+    u32 c = (u32)sval[j];
+    MView v = mview(a, c);
+    u64 o = a.out_off[j];
+    a.out_len[j] = L + v.el + v.er;
+    for (u32 k = 0; k < v.m; ++k) {
+        u8 gs = a.comp_gs[v.off + k];
+        i64 s = (i64)abs_start(a, v, k);
+        a.out_seq[o + k] = gs & 0x7F;
+        a.out_start[o + k] = (gs & 0x80) ? -s : s;
+    }
+}
+
+void launch_uniq_flags(const OutputArgs& a, cudaStream_t st) {
+    if (a.n_cand) k_uniq_flags<<<div_up(a.n_cand, 256), 256, 0, st>>>(a);
+}
+void launch_uniq_keys(const OutputArgs& a, int sbits, cudaStream_t st) {
+    if (a.n_cand) k_uniq_keys<<<div_up(a.n_cand, 256), 256, 0, st>>>(a, sbits);
+}
+void launch_uniq_tiefix(const OutputArgs& a, const u64* skey, u64* sval, u32 L, u32 n_upper, cudaStream_t st) {
+    if (n_upper) k_uniq_tiefix<<<div_up(n_upper, 256), 256, 0, st>>>(a, skey, sval, L);
+}
+void launch_uniq_ncomp(const OutputArgs& a, const u64* sval, u32 n_upper, cudaStream_t st) {
+    if (n_upper) k_uniq_ncomp<<<div_up(n_upper, 256), 256, 0, st>>>(a, sval);
+}
+void launch_uniq_gather(const OutputArgs& a, const u64* sval, u32 L, u32 n_upper, cudaStream_t st) {
+    if (n_upper) k_uniq_gather<<<div_up(n_upper, 256), 256, 0, st>>>(a, sval, L);
+}

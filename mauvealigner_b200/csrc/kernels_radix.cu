@@ -1,0 +1,204 @@
+// kernels_radix.cu — a4 (sorted mer list construction) + a6 (N-way merge) of SURVEY.md §8a as ONE
+// stable LSD radix sort of all genomes' seed records.
+//
+// Replaces libMems DNAMemorySML::Create / FileSML::Create (per-genome sort) and the streaming merge
+// of MatchFinder::FindMatchSeeds (call sites /root/reference/src/SeedMatchEnumerator.h:61,
+// src/mauveAligner.cpp:465,585).  Records are emitted in (genome, position) order and every pass
+// is stable, so equal seeds end up ordered by (genome, position) = Appendix A D6.
+//
+// One pass = one kernel ("onesweep"): tiles are taken in order through an atomic ticket, each tile
+// ranks its keys per 8-bit digit (warp __match_any_sync ranking), publishes its digit counts,
+// resolves its global digit offsets by decoupled look-back over earlier tiles, reorders the tile
+// in shared memory and writes each digit's keys as one contiguous burst.
+// Traffic per pass: one read + one write of every record (2R bytes/record).
+#include "common.cuh"
+#include "kernels.h"
+
+#define RS_NT 512
+#define RS_NW (RS_NT / 32)
+#define RS_IPT 12
+#define RS_TILE (RS_NT * RS_IPT)
+
+#define LB_FLAG_AGG (1ull << 62)
+#define LB_FLAG_INC (2ull << 62)
+#define LB_MASK ((1ull << 62) - 1)
+
+__device__ __forceinline__ u64 ld_volatile_u64(const u64* p) {
+    u64 v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_volatile_u64(u64* p, u64 v) {
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+template <bool HAS_VAL>
+__global__ void __launch_bounds__(RS_NT) k_onesweep(const u64* __restrict__ kin, u64* __restrict__ kout,
+                                                    const u64* __restrict__ vin, u64* __restrict__ vout, u32 n,
+                                                    const u32* __restrict__ digit_base /*[256] exclusive*/,
+                                                    u64* lookback /*[tiles][256]*/, u32* ticket, int shift, u32 dmask) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    u64* sKeys = reinterpret_cast<u64*>(smem_raw);                    // RS_TILE
+    u64* sVals = sKeys + RS_TILE;                                      // RS_TILE when HAS_VAL
+    u32* sWarpHist = reinterpret_cast<u32*>(sKeys + (HAS_VAL ? 2 : 1) * RS_TILE); // RS_NW*256
+    u32* sTilePrefix = sWarpHist + RS_NW * 256;                        // 256 exclusive digit offsets in tile
+    i64* sGlobBase = reinterpret_cast<i64*>(sTilePrefix + 256);        // 256: global index of slot 0 of digit
+    __shared__ u32 sTile;
+    __shared__ u32 sWarpSums[8];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) sTile = atomicAdd(ticket, 1u);
+    for (int i = tid; i < RS_NW * 256; i += RS_NT) sWarpHist[i] = 0;
+    __syncthreads();
+    const u32 tile = sTile;
+    const u64 tile_base = (u64)tile * RS_TILE;
+    const u32 tile_n = (u32)min((u64)RS_TILE, (u64)n - tile_base);
+
+    // warp-striped load
+    u64 key[RS_IPT];
+    u32 rank[RS_IPT];
+    const u32 wbase = warp * (RS_IPT * 32);
+#pragma unroll
+    for (int k = 0; k < RS_IPT; ++k) {
+        u32 o = wbase + k * 32 + lane;
+        key[k] = (o < tile_n) ? kin[tile_base + o] : ~0ull;
+    }
+    // rank within warp, per digit, in (k, lane) order
+    u32* myHist = sWarpHist + warp * 256;
+#pragma unroll
+    for (int k = 0; k < RS_IPT; ++k) {
+        u32 o = wbase + k * 32 + lane;
+        bool valid = o < tile_n;
+        u32 d = (u32)(key[k] >> shift) & dmask;
+        u32 vm = __ballot_sync(0xFFFFFFFFu, valid);
+        u32 peers = __match_any_sync(0xFFFFFFFFu, valid ? d : 0xFFFFFFFFu) & vm;
+        u32 old = 0;
+        if (valid) {
+            int leader = __ffs(peers) - 1;
+            if (lane == leader) { old = myHist[d]; myHist[d] = old + __popc(peers); }
+            old = __shfl_sync(peers, old, leader);
+            rank[k] = old + __popc(peers & ((1u << lane) - 1));
+        } else rank[k] = 0;
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // per digit: exclusive scan across warps, tile total, look-back
+    u32 tile_count = 0;
+    if (tid < 256) {
+        u32 acc = 0;
+#pragma unroll
+        for (int w = 0; w < RS_NW; ++w) {
+            u32 t = sWarpHist[w * 256 + tid];
+            sWarpHist[w * 256 + tid] = acc;
+            acc += t;
+        }
+        tile_count = acc;
+        u64* slot = lookback + (u64)tile * 256 + tid;
+        st_volatile_u64(slot, (tile == 0 ? LB_FLAG_INC : LB_FLAG_AGG) | (u64)acc);
+    }
+    // exclusive scan of tile_count over the 256 digits (threads 0..255 = 8 warps)
+    {
+        u32 v = tile_count, x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            u32 y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (tid < 256 && lane == 31) sWarpSums[warp] = x;
+        __syncthreads();
+        if (tid < 256) {
+            u32 pre = 0;
+            for (int w = 0; w < warp; ++w) pre += sWarpSums[w];
+            sTilePrefix[tid] = pre + x - v;
+        }
+    }
+    if (tid < 256) {
+        u64 excl = 0;
+        if (tile > 0) {
+            i64 t = (i64)tile - 1;
+            while (true) {
+                u64 s = ld_volatile_u64(lookback + (u64)t * 256 + tid);
+                if ((s >> 62) == 0) continue; // not published yet
+                excl += s & LB_MASK;
+                if (s & LB_FLAG_INC) break;
+                --t;
+            }
+            st_volatile_u64(lookback + (u64)tile * 256 + tid, LB_FLAG_INC | (excl + tile_count));
+        }
+        sGlobBase[tid] = (i64)digit_base[tid] + (i64)excl - (i64)sTilePrefix[tid];
+    }
+    __syncthreads();
+
+    // reorder in shared memory
+    u32 slot[RS_IPT];
+#pragma unroll
+    for (int k = 0; k < RS_IPT; ++k) {
+        u32 o = wbase + k * 32 + lane;
+        if (o < tile_n) {
+            u32 d = (u32)(key[k] >> shift) & dmask;
+            slot[k] = sTilePrefix[d] + myHist[d] + rank[k];
+            sKeys[slot[k]] = key[k];
+        }
+    }
+    if (HAS_VAL) {
+#pragma unroll
+        for (int k = 0; k < RS_IPT; ++k) {
+            u32 o = wbase + k * 32 + lane;
+            if (o < tile_n) sVals[slot[k]] = vin[tile_base + o];
+        }
+    }
+    __syncthreads();
+    for (u32 s = tid; s < tile_n; s += RS_NT) {
+        u64 kk = sKeys[s];
+        u32 d = (u32)(kk >> shift) & dmask;
+        i64 dst = sGlobBase[d] + (i64)s;
+        kout[dst] = kk;
+        if (HAS_VAL) vout[dst] = sVals[s];
+    }
+}
+
+// exclusive scan of each pass's 256-bin histogram (one block per pass)
+__global__ void __launch_bounds__(256) k_scan_hist(const u32* __restrict__ hist, u32* __restrict__ base) {
+    __shared__ u32 s[256];
+    const int t = threadIdx.x;
+    const u32* h = hist + blockIdx.x * 256;
+    s[t] = h[t];
+    __syncthreads();
+    for (int o = 1; o < 256; o <<= 1) {
+        u32 v = t >= o ? s[t - o] : 0;
+        __syncthreads();
+        s[t] += v;
+        __syncthreads();
+    }
+    base[blockIdx.x * 256 + t] = s[t] - h[t];
+}
+
+size_t radix_smem_bytes(bool has_val) {
+    return (size_t)(has_val ? 2 : 1) * RS_TILE * 8 + RS_NW * 256 * 4 + 256 * 4 + 256 * 8;
+}
+u32 radix_tile_size() { return RS_TILE; }
+
+void launch_scan_hist(const u32* d_hist, u32* d_base, int npass, cudaStream_t st) {
+    k_scan_hist<<<npass, 256, 0, st>>>(d_hist, d_base);
+}
+
+static bool g_attr_set[2] = {false, false};
+
+cudaError_t launch_onesweep(const u64* kin, u64* kout, const u64* vin, u64* vout, u32 n, const u32* d_digit_base,
+                            u64* d_lookback, u32* d_ticket, int shift, int bits, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    bool hv = vin != nullptr;
+    size_t smem = radix_smem_bytes(hv);
+    if (!g_attr_set[hv]) {
+        cudaError_t e = hv ? cudaFuncSetAttribute(k_onesweep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                           : cudaFuncSetAttribute(k_onesweep<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        g_attr_set[hv] = true;
+    }
+    u32 tiles = div_up(n, RS_TILE);
+    u32 dmask = (1u << bits) - 1;
+    if (hv) k_onesweep<true><<<tiles, RS_NT, smem, st>>>(kin, kout, vin, vout, n, d_digit_base, d_lookback, d_ticket, shift, dmask);
+    else k_onesweep<false><<<tiles, RS_NT, smem, st>>>(kin, kout, vin, vout, n, d_digit_base, d_lookback, d_ticket, shift, dmask);
+    return cudaGetLastError();
+}

@@ -1,0 +1,329 @@
+"""Host-side mirror of the reference's match-finder protocol over the C ABI.
+
+Names and argument meaning follow the reference's plugin interface for this path:
+  MatchList                      (libMems; members used at src/mauveAligner.cpp:450-466)
+  SeedMatchEnumerator.FindMatches(match_list, min_multi=2, max_multi=1000, direct_repeats_only=False)
+                                  /root/reference/src/SeedMatchEnumerator.h:19-33
+  UniqueMatchFinder.FindMatches(match_list)      /root/reference/src/UniqueMatchFinder.h:21-32,
+                                                 call site src/progressiveMauve.cpp:490-495
+  MaskedMemHash.SetMask(mask)                    /root/reference/src/mauveAligner.cpp:523-531
+  SortedMerList.UniqueMerCount()                 /root/reference/src/uniqueMerCount.cpp:39
+The C++ twin of this file is include/mems_compat/mems_compat.h (same names, same calls into libmauve_b200.so).
+All compute happens in the CUDA library; nothing here touches sequence data."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+from .seeds import get_seed, default_seed_weight, seed_length, seed_weight, seed_valid, SOLID_SEED, CODING_SEED  # noqa: F401
+
+NO_MATCH = 0
+
+
+def _check(ctx, rc):
+    if rc != L.MB_OK:
+        detail = L.lib().mb_last_cuda_error(ctx).decode() if ctx else ""
+        raise L.MauveError(rc, detail)
+
+
+class Context:
+    """One CUDA context of the library (one per GPU / process)."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        rc = L.lib().mb_ctx_create(C.byref(self._h), device)
+        if rc != L.MB_OK:
+            raise L.MauveError(rc, "mb_ctx_create: a B200 (sm_100) device is required; there is no CPU path")
+        self.device = device
+
+    def close(self):
+        if self._h:
+            L.lib().mb_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream):
+        _check(self._h, L.lib().mb_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def clear_sequences(self):
+        _check(self._h, L.lib().mb_clear_sequences(self._h))
+
+    def add_sequence(self, data, packed=False):
+        """data: bytes / str / numpy uint8 (ASCII) or numpy uint64 words (packed=True, with length attr)."""
+        if packed:
+            words, length = data
+            words = np.ascontiguousarray(words, dtype=np.uint64)
+            ptr, n = words.ctypes.data, int(length)
+            self._keep = words
+        else:
+            if isinstance(data, str):
+                data = data.encode()
+            if isinstance(data, (bytes, bytearray)):
+                data = np.frombuffer(bytes(data), dtype=np.uint8)
+            data = np.ascontiguousarray(data, dtype=np.uint8)
+            ptr, n = data.ctypes.data, int(data.size)
+            self._keep = data
+        sid = C.c_int(-1)
+        _check(self._h, L.lib().mb_add_sequence(self._h, C.c_void_p(ptr), n, 1 if packed else 0, C.byref(sid)))
+        return sid.value
+
+    def add_sequence_ptr(self, host_ptr, length, packed=False):
+        sid = C.c_int(-1)
+        _check(self._h, L.lib().mb_add_sequence(self._h, C.c_void_p(host_ptr), int(length), 1 if packed else 0, C.byref(sid)))
+        return sid.value
+
+    def add_sequence_device(self, dev_ptr, length):
+        sid = C.c_int(-1)
+        _check(self._h, L.lib().mb_add_sequence_device(self._h, C.c_void_p(dev_ptr), int(length), C.byref(sid)))
+        return sid.value
+
+    def set_seed(self, pattern):
+        _check(self._h, L.lib().mb_set_seed(self._h, int(pattern)))
+
+    def _params(self, mode, min_multi, max_multi, direct_only, nway_mask):
+        return L.MbParams(int(mode), int(bool(direct_only)), int(min_multi), int(max_multi), int(nway_mask))
+
+    def find_device(self, mode, min_multi=2, max_multi=1000, direct_only=False, nway_mask=0):
+        p = self._params(mode, min_multi, max_multi, direct_only, nway_mask)
+        _check(self._h, L.lib().mb_find_device(self._h, C.byref(p)))
+
+    def fetch(self, copy=True):
+        out = C.POINTER(L.MbResult)()
+        _check(self._h, L.lib().mb_fetch_result(self._h, C.byref(out)))
+        return self._wrap(out.contents, copy)
+
+    def find(self, mode, min_multi=2, max_multi=1000, direct_only=False, nway_mask=0, copy=True):
+        p = self._params(mode, min_multi, max_multi, direct_only, nway_mask)
+        out = C.POINTER(L.MbResult)()
+        _check(self._h, L.lib().mb_find(self._h, C.byref(p), C.byref(out)))
+        return self._wrap(out.contents, copy)
+
+    @staticmethod
+    def _wrap(r, copy):
+        nm, nc, ns = int(r.n_matches), int(r.n_comps), int(r.nseq)
+
+        def arr(ptr, n):
+            if n == 0:
+                return np.zeros(0, dtype=np.ctypeslib.as_array(ptr, shape=(1,)).dtype)
+            a = np.ctypeslib.as_array(ptr, shape=(n,))
+            return a.copy() if copy else a
+
+        return dict(n_matches=nm, n_comps=nc, length=arr(r.length, nm), comp_off=arr(r.comp_off, nm + 1), comp_seq=arr(r.comp_seq, nc),
+                    comp_start=arr(r.comp_start, nc), unique_mers=int(r.unique_mers),
+                    unique_mers_per_seq=arr(r.unique_mers_per_seq, ns))
+
+    def stats(self):
+        s = L.MbStats()
+        _check(self._h, L.lib().mb_get_stats(self._h, C.byref(s)))
+        return {n: getattr(s, n) for n, _ in s._fields_}
+
+    def mers(self, seq, length_hint):
+        out = np.zeros(max(1, length_hint), dtype=np.uint64)
+        n = C.c_uint64(0)
+        _check(self._h, L.lib().mb_get_mers(self._h, seq, C.c_void_p(out.ctypes.data), out.size, C.byref(n)))
+        return out[: n.value]
+
+    def sml(self, seq, length_hint):
+        out = np.zeros(max(1, length_hint), dtype=np.uint32)
+        n = C.c_uint64(0)
+        _check(self._h, L.lib().mb_get_sml(self._h, seq, C.c_void_p(out.ctypes.data), out.size, C.byref(n)))
+        return out[: n.value]
+
+
+class Match:
+    """mems::Match as the callers use it (src/SeedMatchEnumerator.h:75-119, src/repeatoire.cpp:1926-1936)."""
+
+    __slots__ = ("_start", "_length")
+
+    def __init__(self, seq_count):
+        self._start = [NO_MATCH] * seq_count
+        self._length = 0
+
+    def SetLength(self, n):
+        self._length = int(n)
+
+    def SetStart(self, i, s):
+        self._start[i] = int(s)
+
+    def __getitem__(self, i):
+        return self._start[i]
+
+    def Start(self, i):
+        return self._start[i]
+
+    def Length(self, i=0):
+        return self._length
+
+    def SeqCount(self):
+        return len(self._start)
+
+    def Multiplicity(self):
+        return sum(1 for s in self._start if s != NO_MATCH)
+
+    def Orientation(self, i):
+        return 0 if self._start[i] > 0 else (1 if self._start[i] < 0 else 2)  # forward, reverse, undefined
+
+    def LeftEnd(self, i):
+        return abs(self._start[i])
+
+    def Copy(self):
+        m = Match(len(self._start))
+        m._start = list(self._start)
+        m._length = self._length
+        return m
+
+    def __repr__(self):
+        return f"{self._length}\t" + "\t".join(str(s) for s in self._start)
+
+
+class MatchList(list):
+    """mems::MatchList: a vector<Match*> plus seq_filename / sml_filename / seq_table / sml_table."""
+
+    def __init__(self):
+        super().__init__()
+        self.seq_filename, self.sml_filename, self.seq_table, self.sml_table = [], [], [], []
+        self.seed_pattern = 0
+
+    def CreateMemorySMLs(self, seed_weight, log=None, seed_rank=0):
+        """MatchList::CreateMemorySMLs(mer_size, ostream*, seed_rank) (src/mauveAligner.cpp:456): here it only fixes
+        the seed; the sorted mer lists are built on the device inside FindMatches."""
+        if seed_weight == 0:
+            avg = sum(len(s) for s in self.seq_table) // max(1, len(self.seq_table))
+            seed_weight = default_seed_weight(avg)
+        self.seed_pattern = get_seed(seed_weight, seed_rank)
+        self.sml_table = [SortedMerList(self, i) for i in range(len(self.seq_table))]
+
+    LoadSMLs = CreateMemorySMLs
+
+
+class SortedMerList:
+    """Façade over the device-built sorted mer list of one sequence (libMems SortedMerList)."""
+
+    def __init__(self, ml, index):
+        self._ml, self._i = ml, index
+
+    def Seed(self):
+        return self._ml.seed_pattern
+
+    def SeedLength(self):
+        return seed_length(self._ml.seed_pattern)
+
+    def SeedWeight(self):
+        return seed_weight(self._ml.seed_pattern)
+
+    def Length(self):
+        return len(self._ml.seq_table[self._i])
+
+    def UniqueMerCount(self, ctx=None):
+        own = ctx is None
+        ctx = ctx or Context()
+        try:
+            ctx.clear_sequences()
+            ctx.add_sequence(self._ml.seq_table[self._i])
+            ctx.set_seed(self._ml.seed_pattern)
+            return ctx.find(L.MODE_UNIQUE_COUNT)["unique_mers"]
+        finally:
+            if own:
+                ctx.close()
+
+
+class MatchFinder:
+    def __init__(self, ctx=None):
+        self._ctx = ctx
+        self._own = ctx is None
+        self.seq_count = 0
+        self._log = None
+        self.last = None
+
+    def _context(self):
+        if self._ctx is None:
+            self._ctx = Context()
+        return self._ctx
+
+    def LogProgress(self, stream):
+        self._log = stream
+
+    def Clear(self):
+        self.last = None
+
+    def ClearSequences(self):
+        self.seq_count = 0
+        if self._ctx is not None:
+            self._ctx.clear_sequences()
+
+    def _load(self, match_list):
+        ctx = self._context()
+        ctx.clear_sequences()
+        for s in match_list.seq_table:
+            ctx.add_sequence(s)
+        self.seq_count = len(match_list.seq_table)
+        if not seed_valid(match_list.seed_pattern):
+            raise L.MauveError(-2)
+        ctx.set_seed(match_list.seed_pattern)
+        return ctx
+
+    @staticmethod
+    def _fill(match_list, res, seq_count, dense):
+        del match_list[:]
+        off, seqs, starts, lens = res["comp_off"], res["comp_seq"], res["comp_start"], res["length"]
+        for i in range(res["n_matches"]):
+            a, b = int(off[i]), int(off[i + 1])
+            m = Match(seq_count if dense else b - a)
+            m.SetLength(int(lens[i]))
+            for k in range(a, b):
+                m.SetStart(int(seqs[k]) if dense else k - a, int(starts[k]))
+            match_list.append(m)
+
+
+class UniqueMatchFinder(MatchFinder):
+    """UniqueMatchFinder / MemHash: multi-MUMs with unique seeds (src/UniqueMatchFinder.cpp:36-60)."""
+
+    def __init__(self, ctx=None):
+        super().__init__(ctx)
+        self._mask = 0
+
+    def FindMatches(self, match_list):
+        ctx = self._load(match_list)
+        self.last = ctx.find(L.MODE_UNIQUE, nway_mask=self._mask)
+        self._fill(match_list, self.last, self.seq_count, dense=True)
+        return True
+
+    def GetMatchList(self, match_list):
+        if self.last is not None:
+            self._fill(match_list, self.last, self.seq_count, dense=True)
+
+    def Clone(self):
+        c = type(self)(self._ctx)
+        c._mask = self._mask
+        return c
+
+
+MemHash = UniqueMatchFinder
+
+
+class MaskedMemHash(UniqueMatchFinder):
+    def SetMask(self, mask):
+        self._mask = int(mask)
+
+
+class SeedMatchEnumerator(MatchFinder):
+    """Every seed match becomes a full match without extension (src/SeedMatchEnumerator.h:11-141)."""
+
+    def FindMatches(self, match_list, min_multi=2, max_multi=1000, direct_repeats_only=False):
+        del match_list[:]
+        if len(match_list.seq_table) != 1:
+            # CreateMatches() is a no-op unless seq_count == 1 (:59-65); the list stays empty
+            return
+        ctx = self._load(match_list)
+        self.last = ctx.find(L.MODE_SEED_ENUM, min_multi=min_multi, max_multi=max_multi, direct_only=direct_repeats_only)
+        self._fill(match_list, self.last, 1, dense=False)
+
+    def Clone(self):
+        return SeedMatchEnumerator(self._ctx)

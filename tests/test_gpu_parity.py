@@ -1,0 +1,193 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+Bit-exact: integer / index work only (no floating point on this path, no tolerance)."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from toygen import family, mutate, rand_seq, revcomp
+
+pytestmark = pytest.mark.gpu
+
+PATTERNS = [0b111, 0b11111, 0b1011101, 0b110111011, 0b11011011111011011, 0b1101110111110111011,
+            0b110110110111011011011, 0b1011101110111110111011101]
+
+
+def wide_pattern():
+    # L = 41, weight 9, palindromic
+    bits = [0] * 41
+    for j in (0, 5, 13, 19, 20, 21, 27, 35, 40):
+        bits[j] = 1
+    p = 0
+    for b in bits:
+        p = (p << 1) | b
+    return p
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import mauvealigner_b200 as mb
+    c = mb.Context(0)
+    yield c
+    c.close()
+
+
+def run(ctx, seqs, pattern, mode, **kw):
+    ctx.clear_sequences()
+    for s in seqs:
+        ctx.add_sequence(s)
+    ctx.set_seed(pattern)
+    return ctx.find(mode, **kw)
+
+
+def assert_same(got, want, what=""):
+    assert got["n_matches"] == want["n_matches"], (what, got["n_matches"], want["n_matches"])
+    assert got["n_comps"] == want["n_comps"], what
+    for k in ("length", "comp_off", "comp_seq", "comp_start"):
+        assert np.array_equal(np.asarray(got[k], dtype=np.int64), np.asarray(want[k], dtype=np.int64)), (what, k)
+
+
+@pytest.mark.parametrize("pattern", PATTERNS + [wide_pattern()])
+def test_mers_and_sml_record_by_record(ctx, pattern):
+    rng = np.random.default_rng(pattern & 0xFFFF)
+    seqs = [rand_seq(rng, 9000), rand_seq(rng, 40, alphabet=2), rand_seq(rng, 4097 + pattern.bit_length())]
+    ctx.clear_sequences()
+    for s in seqs:
+        ctx.add_sequence(s)
+    ctx.set_seed(pattern)
+    for i, s in enumerate(seqs):
+        assert np.array_equal(ctx.mers(i, len(s)), O.mers(s, pattern)), i
+    ctx.find(2)
+    for i, s in enumerate(seqs):
+        assert np.array_equal(ctx.sml(i, len(s)), O.sml(s, pattern)), i
+
+
+def test_non_acgt_and_lowercase(ctx):
+    s = "ACGTNNNNacgtRYKMacgtACGTTTGACCA" * 10
+    ctx.clear_sequences()
+    ctx.add_sequence(s)
+    ctx.set_seed(0b11111)
+    assert np.array_equal(ctx.mers(0, len(s)), O.mers(s, 0b11111))
+
+
+def test_unique_count(ctx):
+    rng = np.random.default_rng(1)
+    seqs = [rand_seq(rng, 5000, alphabet=3), rand_seq(rng, 3000), ""]
+    for pattern in PATTERNS[:5]:
+        got = run(ctx, seqs, pattern, 2)
+        want = O.find(seqs, pattern, O.MODE_UNIQUE_COUNT)
+        assert got["unique_mers"] == want["unique_mers"]
+        assert got["unique_mers_per_seq"].tolist() == want["unique_mers_per_seq"].tolist()
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_unique_vs_oracle_small(ctx, seed):
+    rng = np.random.default_rng(1000 + seed)
+    pattern = PATTERNS[seed % len(PATTERNS)]
+    k = int(rng.integers(2, 7))
+    n = int(rng.integers(300, 3000))
+    seqs = family(rng, n, k, sub=0.03, indel=0.005, inv=seed % 3)
+    if seed % 4 == 0:
+        seqs[1] = revcomp(seqs[1])
+    got = run(ctx, seqs, pattern, 0)
+    want = O.find(seqs, pattern, O.MODE_UNIQUE)
+    assert_same(got, want, f"seed {seed}")
+    assert got["unique_mers"] == want["unique_mers"]
+    assert got["unique_mers_per_seq"].tolist() == want["unique_mers_per_seq"].tolist()
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_unique_low_complexity(ctx, seed):
+    rng = np.random.default_rng(2000 + seed)
+    pattern = PATTERNS[seed % 4]
+    a = rand_seq(rng, 2000, alphabet=2 + seed % 2)
+    seqs = [a, mutate(rng, a, sub=0.05, indel=0.02), mutate(rng, a, sub=0.1, indel=0.0, inv=1)]
+    assert_same(run(ctx, seqs, pattern, 0), O.find(seqs, pattern, O.MODE_UNIQUE))
+
+
+def test_identical_and_near_identical_genomes(ctx):
+    rng = np.random.default_rng(42)
+    s = rand_seq(rng, 200000)
+    for pattern in (0b111111111111111, 0b1101110111110111011):
+        got = run(ctx, [s, s], pattern, 0)
+        assert_same(got, O.find([s, s], pattern, O.MODE_UNIQUE))
+        assert got["n_matches"] == 1 and got["length"][0] == len(s)
+        t = s[:100000] + "A" + s[100001:] if s[100000] != "A" else s[:100000] + "C" + s[100001:]
+        assert_same(run(ctx, [s, t, revcomp(s)], pattern, 0), O.find([s, t, revcomp(s)], pattern, O.MODE_UNIQUE))
+
+
+def test_substitutions_only_long_diagonal(ctx):
+    rng = np.random.default_rng(43)
+    s = rand_seq(rng, 300000)
+    t = mutate(rng, s, sub=0.02, indel=0.0)
+    for pattern in (0b111111111, 0b110110110111011011011):
+        assert_same(run(ctx, [s, t], pattern, 0), O.find([s, t], pattern, O.MODE_UNIQUE))
+
+
+def test_nway_mask(ctx):
+    rng = np.random.default_rng(44)
+    seqs = family(rng, 5000, 4, sub=0.02, indel=0.002, inv=1)
+    pattern = 0b110111011
+    for mask in (0b1111, 0b0101, 0b0011):
+        assert_same(run(ctx, seqs, pattern, 0, nway_mask=mask), O.find(seqs, pattern, O.MODE_UNIQUE, nway_mask=mask), f"mask {mask}")
+
+
+def test_many_genomes(ctx):
+    rng = np.random.default_rng(45)
+    seqs = family(rng, 3000, 40, sub=0.01, indel=0.001, inv=0)
+    pattern = 0b1101110111110111011
+    assert_same(run(ctx, seqs, pattern, 0), O.find(seqs, pattern, O.MODE_UNIQUE))
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_seed_enum_vs_oracle(ctx, seed):
+    rng = np.random.default_rng(3000 + seed)
+    pattern = PATTERNS[seed % 6]
+    unit = rand_seq(rng, 300)
+    s = rand_seq(rng, 3000) + unit + rand_seq(rng, 500) + mutate(rng, unit, sub=0.05, indel=0) + revcomp(unit) + rand_seq(rng, 600) + "AT" * 300 + unit
+    kw = dict(min_multi=2 + seed % 2, max_multi=[1000, 5, 3, 500][seed % 4], direct_only=bool(seed & 1))
+    got = run(ctx, [s], pattern, 1, **kw)
+    want = O.find([s], pattern, O.MODE_SEED_ENUM, **kw)
+    assert_same(got, want, f"seed {seed}")
+    if pattern.bit_length() > 3:
+        assert got["n_matches"] > 0
+
+
+def test_edge_cases(ctx):
+    import mauvealigner_b200 as mb
+    # sequences shorter than the seed, empty sequences
+    got = run(ctx, ["ACG", "ACGTTGCA", ""], 0b11111, 0)
+    assert got["n_matches"] == 0
+    # SEED_ENUM needs exactly one sequence
+    with pytest.raises(mb.MauveError):
+        run(ctx, ["ACGTACGTACGTAAC", "ACGTACGTACGTAAC"], 0b111, 1)
+    # invalid seeds are rejected
+    with pytest.raises(mb.MauveError):
+        ctx.set_seed(0b1111)
+    with pytest.raises(mb.MauveError):
+        ctx.set_seed(0b1101)
+    # a single genome can never produce a UNIQUE match
+    rng = np.random.default_rng(3)
+    s = rand_seq(rng, 5000)
+    assert run(ctx, [s + s], 0b11111, 0)["n_matches"] == 0
+
+
+@pytest.mark.parametrize("config,scale", [(1, 50), (2, 50), (3, 200), (4, 400), (5, 100)])
+def test_baseline_configs_scaled(ctx, config, scale):
+    import mauvealigner_b200 as mb
+    seqs = mb.synth_genomes(config, scale)
+    if config in (1,):
+        pattern, mode, kw = mb.get_seed(15, 0), 0, {}
+    elif config in (2, 5):
+        pattern, mode, kw = mb.get_seed(15, mb.CODING_SEED), 0, {}
+    elif config == 3:
+        pattern, mode, kw = mb.get_seed(19, 0), 2, {}
+    else:
+        pattern, mode, kw = mb.get_seed(15, 0), 1, dict(min_multi=2, max_multi=500)
+    got = run(ctx, seqs, pattern, mode, **kw)
+    want = O.find(seqs, pattern, mode, **kw)
+    assert_same(got, want, f"C{config}")
+    assert got["unique_mers"] == want["unique_mers"]
+    if config == 3:
+        assert got["unique_mers_per_seq"].tolist() == want["unique_mers_per_seq"].tolist()
+        # weight-19 seeds on one genome: the UNIQUE match set is empty by construction (UniqueMatchFinder.cpp:57)
+        assert run(ctx, seqs, pattern, 0)["n_matches"] == 0
