@@ -79,6 +79,10 @@ typedef struct mb_stats {
     float ms_h2d, ms_pack, ms_extract, ms_sort, ms_bucket, ms_dedup, ms_output, ms_d2h, ms_total_device;
     uint64_t h2d_bytes, d2h_bytes;
     uint64_t kernel_launches;   /* launches of this library's own kernels in the last mb_find */
+    /* the dominant kernel (one radix pass over all seed records): summed device time and launch count
+     * of the seed sort's k_onesweep launches, CUDA events on the context stream */
+    float ms_radix_kernels;
+    uint32_t radix_launches;
 } mb_stats;
 
 /* ---- context ----------------------------------------------------------------- */

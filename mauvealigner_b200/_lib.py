@@ -32,7 +32,8 @@ class MbStats(C.Structure):
                [(n, C.c_uint32) for n in ("radix_passes", "record_bytes", "dedup_batches", "dedup_iters")] + \
                [(n, C.c_float) for n in ("ms_h2d", "ms_pack", "ms_extract", "ms_sort", "ms_bucket", "ms_dedup", "ms_output", "ms_d2h",
                                          "ms_total_device")] + \
-               [(n, C.c_uint64) for n in ("h2d_bytes", "d2h_bytes", "kernel_launches")]
+               [(n, C.c_uint64) for n in ("h2d_bytes", "d2h_bytes", "kernel_launches")] + \
+               [("ms_radix_kernels", C.c_float), ("radix_launches", C.c_uint32)]
 
 
 EXPORTS = ["mb_ctx_create", "mb_ctx_destroy", "mb_set_stream", "mb_add_sequence", "mb_add_sequence_device", "mb_clear_sequences",

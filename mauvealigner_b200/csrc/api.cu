@@ -21,7 +21,7 @@ struct DBuf {
 
 enum { EV_START, EV_EXTRACT, EV_SORT, EV_BUCKET, EV_DEDUP, EV_OUTPUT, EV_COUNT };
 enum { SC_RUNS = 0 /*u32[2]*/, SC_CAND = 1 /*u32[2]*/, SC_NBUCKETS = 2, SC_UNDECIDED = 3, SC_EXTENDED = 4, SC_NMATCH = 5, SC_NCOMP = 6,
-       SC_BMTOTAL = 7, SC_COUNT = 16 };
+       SC_BMTOTAL = 7, SC_DDCTR = 8 /* 16 x u32 */, SC_COUNT = 16 };
 
 } // namespace
 
@@ -43,6 +43,8 @@ struct mb_ctx {
     // workspace
     DBuf keysA, keysB, valsA, valsB, hist, digit_base, lookback, tickets, status, scalars, per_seq, tile_first;
     DBuf cand_run, cand_off, cand_aux, comp_pos, comp_gs, bitmap, bmrank, slot_of, cand_at, cstate, covered, minrank, ext_l, ext_r;
+    DBuf trace;
+    DBuf wl_a, wl_b, wl_c, wl_long, wd_a, wd_b, wd_c, batch_bits, ghash, gid, slot_gid, slot_x, gid_table, rng_lo, rng_hi;
     DBuf flags, match_idx, sort_kA, sort_kB, sort_vA, sort_vB, ncomp, mers_tmp;
     DBuf out_len, out_off, out_seq, out_start;
     u32 ticket_next = 0;
@@ -66,6 +68,8 @@ struct mb_ctx {
     mb_stats stats{};
     cudaEvent_t ev[EV_COUNT] = {nullptr};
     cudaEvent_t ev_x[4] = {nullptr};
+    cudaEvent_t ev_r[16] = {nullptr};
+    int n_timed_passes = 0;
 
     void set_cuda_error(cudaError_t e, const char* what, int line) {
         snprintf(err, sizeof(err), "%s (%s) at api.cu:%d: %s", cudaGetErrorName(e), cudaGetErrorString(e), line, what);
@@ -174,6 +178,7 @@ int mb_ctx_create(mb_ctx** out, int device) {
     c->own_stream = true;
     for (int i = 0; i < EV_COUNT; ++i) cudaEventCreate(&c->ev[i]);
     for (int i = 0; i < 4; ++i) cudaEventCreate(&c->ev_x[i]);
+    for (int i = 0; i < 16; ++i) cudaEventCreate(&c->ev_r[i]);
     cudaMallocHost(&c->h_perseq, MB_MAX_SEQ * sizeof(u64));
     cudaMallocHost(&c->h_scal, SC_COUNT * sizeof(u64));
     *out = c;
@@ -186,7 +191,7 @@ int mb_ctx_destroy(mb_ctx* c) {
     cudaStreamSynchronize(c->stream);
     DBuf* bufs[] = {&c->packed, &c->ascii_stage, &c->keysA, &c->keysB, &c->valsA, &c->valsB, &c->hist, &c->digit_base, &c->lookback, &c->tickets,
                     &c->status, &c->scalars, &c->per_seq, &c->tile_first, &c->cand_run, &c->cand_off, &c->cand_aux, &c->comp_pos, &c->comp_gs,
-                    &c->bitmap, &c->bmrank, &c->slot_of, &c->cand_at, &c->cstate, &c->covered, &c->minrank, &c->ext_l, &c->ext_r, &c->flags,
+                    &c->bitmap, &c->bmrank, &c->slot_of, &c->cand_at, &c->cstate, &c->covered, &c->minrank, &c->ext_l, &c->ext_r, &c->wl_a, &c->wl_b, &c->wl_c, &c->wl_long, &c->wd_a, &c->wd_b, &c->wd_c, &c->batch_bits, &c->trace, &c->ghash, &c->gid, &c->slot_gid, &c->slot_x, &c->rng_lo, &c->rng_hi, &c->gid_table, &c->flags,
                     &c->match_idx, &c->sort_kA, &c->sort_kB, &c->sort_vA, &c->sort_vB, &c->ncomp, &c->mers_tmp, &c->out_len, &c->out_off,
                     &c->out_seq, &c->out_start};
     for (DBuf* b : bufs) free_buf(*b);
@@ -194,6 +199,7 @@ int mb_ctx_destroy(mb_ctx* c) {
     for (void* h : hs) if (h) cudaFreeHost(h);
     for (int i = 0; i < EV_COUNT; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (int i = 0; i < 4; ++i) if (c->ev_x[i]) cudaEventDestroy(c->ev_x[i]);
+    for (int i = 0; i < 16; ++i) if (c->ev_r[i]) cudaEventDestroy(c->ev_r[i]);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return MB_OK;
@@ -250,7 +256,8 @@ static int add_sequence_common(mb_ctx* c, const void* data, uint64_t len, int ki
     if (c->seq_len.size() >= MB_MAX_SEQ) return MB_E_SEQCOUNT;
     CUDA_TRY(c, cudaSetDevice(c->device));
     u64 n_words = (len + 31) / 32;
-    u64 base = (c->words_used + 1) & ~1ull; // 16-byte aligned
+    // every genome has >= MB_PAD_WORDS zero words on both sides (the extension reads a little past either end)
+    u64 base = (std::max<u64>(c->words_used, MB_PAD_WORDS) + 1) & ~1ull; // 16-byte aligned
     u64 end = base + n_words + MB_PAD_WORDS;
     TRY(grow_packed(c, end));
     u64* dst = c->packed.as<u64>() + base;
@@ -291,7 +298,8 @@ int mb_add_sequence_device(mb_ctx* c, const void* dev_ascii, uint64_t len, int* 
 // ---------------------------------------------------------------------------------- sort driver
 // LSD radix sort of n (key[, val]) records on key bits [shift, shift+kbits).  On return *kA/*vA hold
 // the sorted data (the buffers are swapped as needed).
-static int sort_records(mb_ctx* c, u64** kA, u64** kB, u64** vA, u64** vB, u32 n, int shift, int kbits, bool hist_ready) {
+static int sort_records(mb_ctx* c, u64** kA, u64** kB, u64** vA, u64** vB, u32 n, int shift, int kbits, bool hist_ready,
+                        bool time_passes = false) {
     int npass = (kbits + 7) / 8;
     if (n == 0 || npass == 0) return MB_OK;
     if (!hist_ready) {
@@ -303,9 +311,11 @@ static int sort_records(mb_ctx* c, u64** kA, u64** kB, u64** vA, u64** vB, u32 n
     for (int ps = 0; ps < npass; ++ps) {
         CUDA_TRY(c, cudaMemsetAsync(c->lookback.p, 0, (size_t)tiles * 256 * 8, c->stream));
         int bits = std::min(8, kbits - 8 * ps);
+        if (time_passes && ps < 8) cudaEventRecord(c->ev_r[2 * ps], c->stream);
         cudaError_t e = launch_onesweep(*kA, *kB, vA ? *vA : nullptr, vB ? *vB : nullptr, n, c->digit_base.as<u32>() + ps * 256,
                                         c->lookback.as<u64>(), c->ticket(), shift + 8 * ps, bits, c->stream);
         LAUNCHED(c);
+        if (time_passes && ps < 8) { cudaEventRecord(c->ev_r[2 * ps + 1], c->stream); c->n_timed_passes = ps + 1; }
         if (e != cudaSuccess) { c->set_cuda_error(e, "onesweep", __LINE__); return MB_E_CUDA; }
         std::swap(*kA, *kB);
         if (vA) std::swap(*vA, *vB);
@@ -340,7 +350,7 @@ int mb_find_device(mb_ctx* c, const mb_params* prm) {
     memset(&c->stats, 0, sizeof(c->stats));
     c->stats.h2d_bytes = h2d;
     c->have_result = false;
-    c->ticket_next = 0; c->status_next = 0;
+    c->ticket_next = 0; c->status_next = 0; c->n_timed_passes = 0;
 
     // ---- genome table, record format
     GenomeTable& gt = c->gt;
@@ -406,7 +416,7 @@ int mb_find_device(mb_ctx* c, const mb_params* prm) {
     if (n_tiles) { LAUNCHED(c); CHECK_LAUNCH(c); }
     cudaEventRecord(c->ev[EV_EXTRACT], st);
     // ---- a4 + a6: one stable radix sort over the seed bits
-    TRY(sort_records(c, &kA, &kB, fmt.wide ? &vA : nullptr, fmt.wide ? &vB : nullptr, n, fmt.kshift, fmt.kbits, true));
+    TRY(sort_records(c, &kA, &kB, fmt.wide ? &vA : nullptr, fmt.wide ? &vB : nullptr, n, fmt.kshift, fmt.kbits, true, true));
     c->sorted_keys = kA; c->sorted_vals = vA;
     cudaEventRecord(c->ev[EV_SORT], st);
 
@@ -423,7 +433,7 @@ int mb_find_device(mb_ctx* c, const mb_params* prm) {
     u32* run_start = reinterpret_cast<u32*>(kB);
     u32* run_u = fmt.wide ? reinterpret_cast<u32*>(vB) : run_start + (n + 2);
     bool need_u = mode == MB_MODE_UNIQUE || mode == MB_MODE_PAIRWISE;
-    bool need_counts = mode == MB_MODE_UNIQUE_COUNT || mode == MB_MODE_UNIQUE;
+    bool need_counts = mode == MB_MODE_UNIQUE_COUNT;
     launch_find_runs(kA, vA, n, fmt, run_start, need_u ? run_u : nullptr, c->status_slice(div_up(n, find_runs_tile())), c->ticket(),
                      need_counts ? c->per_seq.as<u64>() : nullptr, reinterpret_cast<u32*>(scal + SC_RUNS), st);
     LAUNCHED(c); CHECK_LAUNCH(c);
@@ -453,7 +463,7 @@ int mb_find_device(mb_ctx* c, const mb_params* prm) {
     sa.cand_run = c->cand_run.as<u32>(); sa.cand_off = c->cand_off.as<u32>(); sa.cand_aux = nullptr;
     launch_select(sa, fmt, n, st);
     LAUNCHED(c); CHECK_LAUNCH(c);
-    if (need_counts) CUDA_TRY(c, cudaMemcpyAsync(c->h_perseq, c->per_seq.p, MB_MAX_SEQ * 8, cudaMemcpyDeviceToHost, st));
+    memset(c->h_perseq, 0, MB_MAX_SEQ * 8); // per-sequence counts are a MODE_UNIQUE_COUNT product
     TRY(read_scalars(c));
     const u32* hs32 = reinterpret_cast<const u32*>(c->h_scal);
     const u64* hs64 = reinterpret_cast<const u64*>(c->h_scal);
@@ -511,21 +521,33 @@ int mb_find_device(mb_ctx* c, const mb_params* prm) {
     TRY(c->reserve(c->slot_of, (size_t)(n_cand + 8) * 4));
     TRY(c->reserve(c->cand_at, (size_t)(n_cand + 8) * 4));
     TRY(c->reserve(c->cstate, (size_t)n_cand + 8));
-    TRY(c->reserve(c->covered, (size_t)n_cand + 8));
+    TRY(c->reserve(c->covered, ((size_t)n_cand / 64 + 2) * 8));
     TRY(c->reserve(c->minrank, (size_t)(n_cand + 8) * 4));
     TRY(c->reserve(c->ext_l, (size_t)(n_cand + 8) * 4));
     TRY(c->reserve(c->ext_r, (size_t)(n_cand + 8) * 4));
+    TRY(c->reserve(c->ghash, (size_t)(n_cand + 8) * 8));
+    TRY(c->reserve(c->gid, (size_t)(n_cand + 8) * 4));
+    TRY(c->reserve(c->slot_gid, (size_t)(n_cand + 8) * 4));
+    TRY(c->reserve(c->slot_x, (size_t)(n_cand + 8) * 4));
+    TRY(c->reserve(c->rng_lo, (size_t)(n_cand + 8) * 4));
+    TRY(c->reserve(c->rng_hi, (size_t)(n_cand + 8) * 4));
+    TRY(c->reserve(c->sort_kA, (size_t)(n_cand + 8) * 8)); TRY(c->reserve(c->sort_kB, (size_t)(n_cand + 8) * 8));
+    TRY(c->reserve(c->sort_vA, (size_t)(n_cand + 8) * 8)); TRY(c->reserve(c->sort_vB, (size_t)(n_cand + 8) * 8));
+    u32 gid_table_size = 1024;
+    while (gid_table_size < 2 * (u64)n_cand) gid_table_size <<= 1;
+    TRY(c->reserve(c->gid_table, (size_t)gid_table_size * 4));
     u32 n_matches = 0;
     u64 n_ocomp = 0;
     if (n_cand) {
         CUDA_TRY(c, cudaMemsetAsync(c->bitmap.p, 0, bm_words * 8, st));
         CUDA_TRY(c, cudaMemsetAsync(c->cstate.p, 0xFF, n_cand, st));
-        CUDA_TRY(c, cudaMemsetAsync(c->covered.p, 0, n_cand, st));
+        CUDA_TRY(c, cudaMemsetAsync(c->covered.p, 0, ((size_t)n_cand / 64 + 2) * 8, st));
+        CUDA_TRY(c, cudaMemsetAsync(c->gid_table.p, 0, (size_t)gid_table_size * 4, st));
         EmitUniqueArgs eu{};
         eu.keys = kA; eu.vals = vA; eu.run_start = run_start; eu.run_u = run_u;
         eu.cand_run = c->cand_run.as<u32>(); eu.cand_off = c->cand_off.as<u32>(); eu.cand_aux = nullptr;
         eu.totals = reinterpret_cast<u32*>(scal + SC_CAND);
-        eu.mode = mode; eu.comp_pos = c->comp_pos.as<u32>(); eu.comp_gs = c->comp_gs.as<u8>(); eu.bitmap = c->bitmap.as<u64>();
+        eu.mode = mode; eu.comp_pos = c->comp_pos.as<u32>(); eu.comp_gs = c->comp_gs.as<u8>(); eu.bitmap = c->bitmap.as<u64>(); eu.ghash = c->ghash.as<u64>();
         launch_emit_unique(eu, fmt, gt, n_cand, st); LAUNCHED(c); CHECK_LAUNCH(c);
         launch_scan_popc(c->bitmap.as<u64>(), bm_words, c->bmrank.as<u32>(), c->status_slice(div_up(bm_words, scan_tile())), c->ticket(),
                          scal + SC_BMTOTAL, st);
@@ -534,32 +556,46 @@ int mb_find_device(mb_ctx* c, const mb_params* prm) {
         da.packed = c->packed.as<u64>(); da.n_cand = n_cand;
         da.cand_off = c->cand_off.as<u32>(); da.comp_pos = c->comp_pos.as<u32>(); da.comp_gs = c->comp_gs.as<u8>();
         da.bitmap = c->bitmap.as<u64>(); da.bmrank = c->bmrank.as<u32>();
+        da.ghash = c->ghash.as<u64>(); da.gid_table = c->gid_table.as<u32>(); da.gid_table_mask = gid_table_size - 1;
+        da.gid = c->gid.as<u32>(); da.slot_gid = c->slot_gid.as<u32>(); da.slot_x = c->slot_x.as<u32>();
         da.slot_of = c->slot_of.as<u32>(); da.cand_at = c->cand_at.as<u32>();
-        da.cstate = c->cstate.as<u8>(); da.covered = c->covered.as<u8>(); da.minrank = c->minrank.as<u32>();
+        da.cstate = c->cstate.as<u8>(); da.cov_bits = c->covered.as<u64>(); da.rng_lo = c->rng_lo.as<u32>(); da.rng_hi = c->rng_hi.as<u32>(); da.minrank = c->minrank.as<u32>();
         da.ext_l = c->ext_l.as<u32>(); da.ext_r = c->ext_r.as<u32>();
-        da.n_undecided = reinterpret_cast<u32*>(scal + SC_UNDECIDED); da.n_extended = reinterpret_cast<u32*>(scal + SC_EXTENDED);
-        launch_build_slots(da, gt, st); LAUNCHED(c); CHECK_LAUNCH(c);
+        da.n_extended = reinterpret_cast<u32*>(scal + SC_EXTENDED);
+        launch_group_ids(da, st); LAUNCHED(c);
+        {
+            // slot order = (group id, position): list in (first genome, position) order, stable sort by group id
+            u64 *skA = c->sort_kA.as<u64>(), *skB = c->sort_kB.as<u64>(), *svA = c->sort_vA.as<u64>(), *svB = c->sort_vB.as<u64>();
+            launch_slot_keys(da, gt, skA, svA, st); LAUNCHED(c);
+            TRY(sort_records(c, &skA, &skB, &svA, &svB, n_cand, 0, bits_for(n_cand), false));
+            launch_slot_finish(da, skA, svA, st); LAUNCHED(c); CHECK_LAUNCH(c);
+        }
         cudaEventRecord(c->ev_x[0], st);
 
-        // ---- a10 + a11: doubling batches in ascending seed order
-        u32 p = 0, batch = 4096;
-        u32* h_und = reinterpret_cast<u32*>((u64*)c->h_scal + SC_UNDECIDED);
-        while (p < n_cand) {
-            u32 q = (u32)std::min<u64>((u64)n_cand, (u64)p + batch);
-            launch_dd_extend(da, gt, sd, p, q, st); LAUNCHED(c);
-            ++c->stats.dedup_batches;
-            for (int iter = 0;; ++iter) {
-                CUDA_TRY(c, cudaMemsetAsync(da.n_undecided, 0, 4, st));
-                launch_dd_claim(da, gt, p, q, st); LAUNCHED(c);
-                launch_dd_decide(da, gt, p, q, st); LAUNCHED(c);
-                CUDA_TRY(c, cudaMemcpyAsync(h_und, da.n_undecided, 4, cudaMemcpyDeviceToHost, st));
-                CUDA_TRY(c, cudaStreamSynchronize(st));
-                ++c->stats.dedup_iters;
-                if (*h_und == 0) break;
-                if (iter > 100000) { snprintf(c->err, sizeof(c->err), "de-dup fix-point did not converge"); return MB_E_STATE; }
-            }
-            p = q;
-            batch = std::max(batch, p);
+        // ---- a10 + a11: doubling batches in ascending seed order, one cooperative launch
+        TRY(c->reserve(c->wl_a, (size_t)(n_cand + 8) * 4));
+        TRY(c->reserve(c->wl_b, (size_t)(n_cand + 8) * 4));
+        TRY(c->reserve(c->wl_c, (size_t)(n_cand + 8) * 4));
+        TRY(c->reserve(c->wl_long, (size_t)(n_cand + 8) * 4));
+        TRY(c->reserve(c->wd_a, (size_t)(n_cand + 8) * 4));
+        TRY(c->reserve(c->wd_b, (size_t)(n_cand + 8) * 4));
+        TRY(c->reserve(c->wd_c, (size_t)(n_cand + 8) * 4));
+        TRY(c->reserve(c->batch_bits, ((size_t)n_cand / 64 + 2) * 8));
+        da.wl0 = c->wl_a.as<u32>(); da.wl1 = c->wl_b.as<u32>(); da.wl2 = c->wl_c.as<u32>();
+        da.wl_long = c->wl_long.as<u32>();
+        da.wd0 = c->wd_a.as<u32>(); da.wd1 = c->wd_b.as<u32>(); da.wd2 = c->wd_c.as<u32>();
+        da.batch_bits = c->batch_bits.as<u64>();
+        da.ctr = reinterpret_cast<u32*>(scal + SC_DDCTR);
+        const bool want_trace = getenv("MB_DEDUP_TRACE") != nullptr;
+        if (want_trace) {
+            TRY(c->reserve(c->trace, 8200 * 8));
+            CUDA_TRY(c, cudaMemsetAsync(c->trace.p, 0, 8200 * 8, st));
+            da.trace = c->trace.as<u64>();
+        }
+        {
+            cudaError_t e = launch_dedup_all(da, gt, sd, 131072u, st);
+            LAUNCHED(c);
+            if (e != cudaSuccess) { c->set_cuda_error(e, "launch_dedup_all", __LINE__); return MB_E_CUDA; }
         }
         CHECK_LAUNCH(c);
         cudaEventRecord(c->ev[EV_DEDUP], st);
@@ -578,6 +614,18 @@ int mb_find_device(mb_ctx* c, const mb_params* prm) {
         TRY(read_scalars(c));
         n_matches = (u32)hs64[SC_NMATCH];
         c->stats.n_extended = hs32[2 * SC_EXTENDED];
+        c->stats.dedup_batches = hs32[2 * SC_DDCTR + 8]; c->stats.dedup_iters = hs32[2 * SC_DDCTR + 9];
+        if (want_trace) {
+            std::vector<u64> tr(8200);
+            CUDA_TRY(c, cudaMemcpy(tr.data(), c->trace.p, 8200 * 8, cudaMemcpyDeviceToHost));
+            static const char* names[] = {"", "reset", "begin", "extend", "long", "claim", "decide"};
+            u64 prev = 0;
+            for (u64 k = 0; k < tr[0] && k < 4000; ++k) {
+                u64 tag = tr[2 + 2 * k], t = tr[3 + 2 * k];
+                if (k) fprintf(stderr, "[dedup-trace] %-12s %8.1f us\n", names[tag], (double)(t - prev) / 1e3);
+                prev = t;
+            }
+        }
         TRY(c->reserve(c->sort_kA, (size_t)(n_matches + 8) * 8)); TRY(c->reserve(c->sort_kB, (size_t)(n_matches + 8) * 8));
         TRY(c->reserve(c->sort_vA, (size_t)(n_matches + 8) * 8)); TRY(c->reserve(c->sort_vB, (size_t)(n_matches + 8) * 8));
         TRY(c->reserve(c->ncomp, (size_t)(n_matches + 8) * 4));
@@ -650,6 +698,9 @@ int mb_fetch_result(mb_ctx* c, const mb_result** out) {
     c->stats.ms_output = ms(c->ev[EV_DEDUP], c->ev[EV_OUTPUT]);
     c->stats.ms_total_device = ms(c->ev[EV_START], c->ev[EV_OUTPUT]);
     c->stats.ms_d2h = ms(c->ev_x[1], c->ev_x[2]);
+    c->stats.ms_radix_kernels = 0;
+    for (int i = 0; i < c->n_timed_passes; ++i) c->stats.ms_radix_kernels += ms(c->ev_r[2 * i], c->ev_r[2 * i + 1]);
+    c->stats.radix_launches = c->n_timed_passes;
     *out = &c->res;
     return MB_OK;
 }

@@ -49,6 +49,7 @@ struct EmitUniqueArgs {
     int mode;
     u32* comp_pos; u8* comp_gs;
     u64* bitmap;
+    u64* ghash;      // per candidate: hash of (genome set, strands, diagonal)
 };
 void launch_emit_unique(const EmitUniqueArgs& a, const RecFmt& fmt, const GenomeTable& gt, u32 n_cand_upper, cudaStream_t st);
 struct EmitEnumArgs {
@@ -70,18 +71,29 @@ struct DedupArgs {
     u32 n_cand;
     const u32* cand_off; const u32* comp_pos; const u8* comp_gs;
     const u64* bitmap; const u32* bmrank;
+    const u64* ghash; u32* gid_table; u32 gid_table_mask;
+    u32* gid;        // candidate -> exact group id (= a representative candidate of the same D16 group)
+    u32* slot_gid;   // slot -> group id
+    u32* slot_x;     // slot -> position of the candidate in its first genome
     u32* slot_of;    // candidate -> slot
     u32* cand_at;    // slot -> candidate
     u8* cstate;      // 0 undecided, 1 accepted, 2 dropped, 0xFF not reached
-    u8* covered;     // per slot
+    u64* cov_bits;   // one bit per slot: contained in an accepted match
+    u32* rng_lo; u32* rng_hi; // candidate -> slot range of its group inside its extent
     u32* minrank;    // per slot
     u32* ext_l; u32* ext_r;
-    u32* n_undecided; u32* n_extended;
+    u32* n_extended;
+    // device-resident work lists of one batch (three rotating lists of undecided candidates, long extensions,
+    // wide extents) and their counters (layout: see k_dedup_all)
+    u32* wl0; u32* wl1; u32* wl2; u32* wd0; u32* wd1; u32* wd2; u32* wl_long; u32* ctr;
+    u64* batch_bits; // one bit per slot: live candidate of the current batch
+    u64* trace;      // optional phase trace (debug): [0] count, then (tag, ns) pairs
 };
-void launch_build_slots(const DedupArgs& a, const GenomeTable& gt, cudaStream_t st);
-void launch_dd_extend(const DedupArgs& a, const GenomeTable& gt, const SeedDev& sd, u32 p, u32 q, cudaStream_t st);
-void launch_dd_claim(const DedupArgs& a, const GenomeTable& gt, u32 p, u32 q, cudaStream_t st);
-void launch_dd_decide(const DedupArgs& a, const GenomeTable& gt, u32 p, u32 q, cudaStream_t st);
+void launch_group_ids(const DedupArgs& a, cudaStream_t st);
+void launch_slot_keys(const DedupArgs& a, const GenomeTable& gt, u64* skey, u64* sval, cudaStream_t st);
+void launch_slot_finish(const DedupArgs& a, const u64* skey, const u64* sval, cudaStream_t st);
+// the whole batch loop (extend / claim / decide rounds) as one cooperative launch
+cudaError_t launch_dedup_all(const DedupArgs& a, const GenomeTable& gt, const SeedDev& sd, u32 batch0, cudaStream_t st);
 
 // ---- kernels_output.cu
 struct OutputArgs {

@@ -61,7 +61,11 @@ __global__ void __launch_bounds__(FR_NT) k_find_runs(const u64* __restrict__ key
         bool newg = valid && (head || p.g != c.g);
         bool last = valid && (i + 1 >= n || q.key != c.key || q.g != c.g);
         bool uniq = newg && last;
-        if (per_seq_count && newg) atomicAdd(&sSeq[c.g], 1u);
+        if (per_seq_count) { // warp-aggregated: one shared atomic per distinct genome in the warp
+            u32 act = __ballot_sync(0xFFFFFFFFu, newg);
+            u32 peers = __match_any_sync(0xFFFFFFFFu, newg ? c.g : 0xFFFFFFFFu) & act;
+            if (newg && (peers & ((1u << lane) - 1)) == 0) atomicAdd(&sSeq[c.g], (u32)__popc(peers));
+        }
         headb[k] = __ballot_sync(0xFFFFFFFFu, head);
         uniqb[k] = __ballot_sync(0xFFFFFFFFu, uniq);
         if (lane == 0) sCnt[k * (FR_NT / 32) + warp] = __popc(headb[k]) | (__popc(uniqb[k]) << 16);
@@ -193,7 +197,10 @@ __global__ void __launch_bounds__(SL_NT) k_select(SelectArgs a, RecFmt fmt) {
     u64 total;
     u64 ex = block_excl_scan_u64<SL_NT>(mine, scratch, total);
     // bucket statistic
-    if (nb) atomicAdd((unsigned long long*)a.n_buckets, (unsigned long long)nb);
+    {
+        u32 wnb = __reduce_add_sync(0xFFFFFFFFu, nb);
+        if ((tid & 31) == 0 && wnb) atomicAdd((unsigned long long*)a.n_buckets, (unsigned long long)wnb);
+    }
     if (tid < 32) {
         u64 excl = lookback_exclusive(a.status, tile, total);
         if (tid == 0) {
@@ -253,6 +260,8 @@ __global__ void __launch_bounds__(256) k_emit_unique(EmitUniqueArgs a, RecFmt fm
     }
     u32 prev_g = 0xFFFFFFFFu;
     u32 ui = 0;
+    u32 x0 = 0;
+    u64 h = 0x9E3779B97F4A7C15ull;
     for (u32 i = s; i < e; ++i) {
         u64 v = fmt.wide ? a.vals[i] : a.keys[i];
         u32 g = rec_genome(fmt, v);
@@ -266,13 +275,20 @@ __global__ void __launch_bounds__(256) k_emit_unique(EmitUniqueArgs a, RecFmt fm
         u32 p = rec_pos(fmt, v), sb = rec_strand(v);
         if (k == 0) {
             strand0 = sb;
+            x0 = p;
             u64 gp = gt.base_base[g] + p;
             atomicOr((unsigned long long*)&a.bitmap[gp >> 6], 1ull << (gp & 63));
         }
+        bool rev = sb != strand0;
         a.comp_pos[off + k] = p;
-        a.comp_gs[off + k] = (u8)(g | ((sb != strand0) ? 0x80u : 0u));
+        a.comp_gs[off + k] = (u8)(g | (rev ? 0x80u : 0u));
+        // hash of the D16 group key: genome, strand and diagonal of every component
+        u64 dg = rev ? (u64)p + x0 : (u64)(u32)(p - x0);
+        h ^= (dg << 8) | (u64)(g | (rev ? 0x80u : 0u));
+        h *= 0xFF51AFD7ED558CCDull; h ^= h >> 29;
         ++k;
     }
+    a.ghash[c] = h;
 }
 
 void launch_emit_unique(const EmitUniqueArgs& a, const RecFmt& fmt, const GenomeTable& gt, u32 n_cand_upper, cudaStream_t st) {

@@ -63,23 +63,33 @@ __global__ void __launch_bounds__(RS_NT) k_onesweep(const u64* __restrict__ kin,
         u32 o = wbase + k * 32 + lane;
         key[k] = (o < tile_n) ? kin[tile_base + o] : ~0ull;
     }
-    // rank within warp, per digit, in (k, lane) order
+    // rank within warp, per digit, in (k, lane) order.  Phase 1: all peer masks (independent MATCH ops);
+    // phase 2: the ordered per-digit counter updates (every peer reads, the lowest peer lane writes).
     u32* myHist = sWarpHist + warp * 256;
+    const u32 lt_mask = (1u << lane) - 1;
+    u32 peers[RS_IPT];
+    const bool full = tile_n == RS_TILE;
+    if (full) {
+#pragma unroll
+        for (int k = 0; k < RS_IPT; ++k) peers[k] = __match_any_sync(0xFFFFFFFFu, (u32)(key[k] >> shift) & dmask);
+    } else {
+#pragma unroll
+        for (int k = 0; k < RS_IPT; ++k) {
+            bool valid = wbase + k * 32 + lane < tile_n;
+            u32 vm = __ballot_sync(0xFFFFFFFFu, valid);
+            u32 pm = __match_any_sync(0xFFFFFFFFu, valid ? ((u32)(key[k] >> shift) & dmask) : 0xFFFFFFFFu);
+            peers[k] = valid ? (pm & vm) : 0u;
+        }
+    }
 #pragma unroll
     for (int k = 0; k < RS_IPT; ++k) {
-        u32 o = wbase + k * 32 + lane;
-        bool valid = o < tile_n;
         u32 d = (u32)(key[k] >> shift) & dmask;
-        u32 vm = __ballot_sync(0xFFFFFFFFu, valid);
-        u32 peers = __match_any_sync(0xFFFFFFFFu, valid ? d : 0xFFFFFFFFu) & vm;
-        u32 old = 0;
-        if (valid) {
-            int leader = __ffs(peers) - 1;
-            if (lane == leader) { old = myHist[d]; myHist[d] = old + __popc(peers); }
-            old = __shfl_sync(peers, old, leader);
-            rank[k] = old + __popc(peers & ((1u << lane) - 1));
-        } else rank[k] = 0;
+        u32 old = myHist[d];
         __syncwarp();
+        u32 below = peers[k] & lt_mask;
+        if (below == 0 && peers[k] != 0) myHist[d] = old + __popc(peers[k]);
+        __syncwarp();
+        rank[k] = old + __popc(below);
     }
     __syncthreads();
 
@@ -135,7 +145,7 @@ __global__ void __launch_bounds__(RS_NT) k_onesweep(const u64* __restrict__ kin,
 #pragma unroll
     for (int k = 0; k < RS_IPT; ++k) {
         u32 o = wbase + k * 32 + lane;
-        if (o < tile_n) {
+        if (full || o < tile_n) {
             u32 d = (u32)(key[k] >> shift) & dmask;
             slot[k] = sTilePrefix[d] + myHist[d] + rank[k];
             sKeys[slot[k]] = key[k];
