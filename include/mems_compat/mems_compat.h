@@ -1,0 +1,321 @@
+/*
+ * mems_compat.h — host-side C++ mirror of the libMems types the seed-match path is reached through,
+ * as thin wrappers over the C ABI of include/mauve_b200.h (libmauve_b200.so).
+ *
+ * A maintainer replaces `#include "libMems/MemHash.h"` etc. by this header for the hot path; the
+ * downstream LCB / recursive-anchoring / gapped-alignment code keeps consuming `mems::MatchList`.
+ * Names, argument meaning and error behaviour follow the reference call sites:
+ *
+ *   mems::Match            src/SeedMatchEnumerator.h:75-119, src/repeatoire.cpp:1926-1936
+ *   mems::MatchList        src/mauveAligner.cpp:450-466,641-645 (seq_filename, sml_filename, seq_table, sml_table)
+ *   MatchList::CreateMemorySMLs / LoadSMLs     src/mauveAligner.cpp:456,465; src/progressiveMauve.cpp:446-451; src/repeatoire.cpp:1850
+ *   mems::MatchFinder::AddSequence / Clear / ClearSequences / LogProgress      src/SeedMatchEnumerator.h:25, src/progressiveMauve.cpp:492-495,542-547
+ *   mems::MemHash::FindMatches / GetMatchList, MaskedMemHash::SetMask          src/mauveAligner.cpp:523-589, src/progressiveMauve.cpp:545
+ *   UniqueMatchFinder      src/UniqueMatchFinder.h:21-32, src/UniqueMatchFinder.cpp:36-60
+ *   SeedMatchEnumerator    src/SeedMatchEnumerator.h:14-141
+ *   SortedMerList::UniqueMerCount / SeedLength / Seed                          src/uniqueMerCount.cpp:30-39, src/SeedMatchEnumerator.h:76
+ *   WriteList              src/mauveAligner.cpp:603 (line shape: src/MatchRecord.h:349-355)
+ *
+ * The per-bucket virtual callbacks (EnumerateMatches / HashMatch) cannot cross to the device; each
+ * finder class selects the corresponding device policy (mb_params.mode) instead.  There is no CPU
+ * implementation behind these classes: without a B200 every FindMatches reports an error.
+ */
+#ifndef MEMS_COMPAT_H
+#define MEMS_COMPAT_H
+
+#include <cstdint>
+#include <cstdlib>
+#include <iostream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../mauve_b200.h"
+#include "../mauve_b200/seed_masks.h"
+
+typedef bool boolean;
+typedef uint32_t uint32;
+typedef int64_t int64;
+typedef uint64_t uint64;
+typedef unsigned int uint;
+typedef uint64_t gnSeqI;
+
+namespace genome {
+
+inline void ErrorMsg(const std::string& s) { std::cerr << s; }
+
+class gnException : public std::runtime_error {
+public:
+    explicit gnException(const std::string& s) : std::runtime_error(s) {}
+};
+
+/* the little of libGenome's gnSequence the path touches: length() and ToString() (src/repeatoire.cpp:1870,1959) */
+class gnSequence {
+public:
+    gnSequence() {}
+    explicit gnSequence(const std::string& s) : seq_(s) {}
+    gnSeqI length() const { return seq_.size(); }
+    std::string ToString() const { return seq_; }
+    const std::string& data() const { return seq_; }
+private:
+    std::string seq_;
+};
+
+} // namespace genome
+
+namespace mems {
+
+static const int64 NO_MATCH = 0;
+static const int SOLID_SEED = MB_SOLID_SEED;
+static const int CODING_SEED = MB_CODING_SEED;
+
+inline int64 getSeed(int weight, int rank = 0) { return (int64)mb_get_seed(weight, rank); }
+inline uint32 getSeedLength(int64 seed) { return (uint32)mb_seed_length((uint64_t)seed); }
+inline uint32 getDefaultSeedWeight(gnSeqI avg_len) { return (uint32)mb_default_seed_weight(avg_len); }
+
+class Match {
+public:
+    explicit Match(uint seq_count = 0) : start_(seq_count, NO_MATCH), length_(0) {}
+    void SetLength(gnSeqI len) { length_ = len; }
+    void SetStart(uint seqI, int64 s) { start_[seqI] = s; }
+    int64 operator[](uint seqI) const { return start_[seqI]; }
+    int64 Start(uint seqI) const { return start_[seqI]; }
+    gnSeqI Length(uint = 0) const { return length_; }
+    uint SeqCount() const { return (uint)start_.size(); }
+    uint Multiplicity() const { uint m = 0; for (int64 s : start_) m += s != NO_MATCH; return m; }
+    /* 0 = forward, 1 = reverse, 2 = undefined */
+    int Orientation(uint seqI) const { return start_[seqI] > 0 ? 0 : (start_[seqI] < 0 ? 1 : 2); }
+    int64 LeftEnd(uint seqI) const { return start_[seqI] < 0 ? -start_[seqI] : start_[seqI]; }
+    int64 RightEnd(uint seqI) const { return start_[seqI] == NO_MATCH ? NO_MATCH : LeftEnd(seqI) + (int64)length_ - 1; }
+    Match* Copy() const { return new Match(*this); }
+    void Free() { delete this; }
+    friend std::ostream& operator<<(std::ostream& os, const Match& m) {
+        os << m.length_;
+        for (int64 s : m.start_) os << '\t' << s;
+        return os;
+    }
+private:
+    std::vector<int64> start_;
+    gnSeqI length_;
+};
+
+class MatchList;
+
+/* Façade over the device-built sorted mer list of one sequence. */
+class SortedMerList {
+public:
+    SortedMerList(const genome::gnSequence* seq, uint64 seed) : seq_(seq), seed_(seed), unique_(~0ull) {}
+    uint64 Seed() const { return seed_; }
+    uint32 SeedLength() const { return (uint32)mb_seed_length(seed_); }
+    uint32 SeedWeight() const { return (uint32)mb_seed_weight(seed_); }
+    gnSeqI Length() const { return seq_->length(); }
+    const genome::gnSequence* Sequence() const { return seq_; }
+    /* number of distinct seeds of this sequence (src/uniqueMerCount.cpp:39); computed on the device on first use */
+    gnSeqI UniqueMerCount() {
+        if (unique_ != ~0ull) return unique_;
+        mb_ctx* ctx = nullptr;
+        int rc = mb_ctx_create(&ctx, 0);
+        if (rc != MB_OK) throw genome::gnException(std::string("mb_ctx_create: ") + mb_strerror(rc));
+        const std::string& s = seq_->data();
+        mb_params p = {MB_MODE_UNIQUE_COUNT, 0, 2, 1000, 0};
+        const mb_result* r = nullptr;
+        rc = mb_add_sequence(ctx, (const uint8_t*)s.data(), s.size(), 0, nullptr);
+        if (rc == MB_OK) rc = mb_set_seed(ctx, seed_);
+        if (rc == MB_OK) rc = mb_find(ctx, &p, &r);
+        if (rc == MB_OK) unique_ = r->unique_mers;
+        std::string err = rc == MB_OK ? "" : std::string(mb_strerror(rc)) + " " + mb_last_cuda_error(ctx);
+        mb_ctx_destroy(ctx);
+        if (rc != MB_OK) throw genome::gnException(err);
+        return unique_;
+    }
+private:
+    const genome::gnSequence* seq_;
+    uint64 seed_;
+    uint64 unique_;
+};
+
+class MatchList : public std::vector<Match*> {
+public:
+    std::vector<std::string> seq_filename, sml_filename;
+    std::vector<genome::gnSequence*> seq_table;
+    std::vector<SortedMerList*> sml_table;
+
+    /* MatchList::CreateMemorySMLs(mer_size, log, seed_rank): fixes the seed and creates the façades; the sorted
+     * mer lists themselves are built on the device inside FindMatches. mer_size 0 = default weight. */
+    void CreateMemorySMLs(uint32 mer_size, std::ostream* log_stream, int seed_rank = 0) {
+        if (mer_size == 0) mer_size = GetDefaultMerSize(seq_table);
+        uint64 seed = mb_get_seed((int)mer_size, seed_rank);
+        if (!mb_seed_valid(seed)) throw genome::gnException("invalid seed weight / rank");
+        for (SortedMerList* s : sml_table) delete s;
+        sml_table.clear();
+        for (genome::gnSequence* seq : seq_table) sml_table.push_back(new SortedMerList(seq, seed));
+        if (log_stream) *log_stream << "Using weight " << mb_seed_weight(seed) << " mers, length " << mb_seed_length(seed) << "\n";
+    }
+    /* LoadSMLs(mer_size, log, seed_rank[, solid, force_recreate]): no on-disk cache is kept by this path */
+    void LoadSMLs(uint32 mer_size, std::ostream* log_stream, int seed_rank = 0, bool solid = false, bool = false) {
+        CreateMemorySMLs(mer_size, log_stream, solid ? SOLID_SEED : seed_rank);
+    }
+    static uint32 GetDefaultMerSize(const std::vector<genome::gnSequence*>& seqs) {
+        gnSeqI total = 0;
+        for (auto* s : seqs) total += s->length();
+        return getDefaultSeedWeight(seqs.empty() ? 0 : total / seqs.size());
+    }
+};
+
+inline void WriteList(const MatchList& ml, std::ostream& os) {
+    os << "FormatVersion\t3\nSequenceCount\t" << ml.seq_table.size() << "\n";
+    for (size_t i = 0; i < ml.seq_table.size(); ++i) {
+        os << "Sequence" << i << "File\t" << (i < ml.seq_filename.size() ? ml.seq_filename[i] : "") << "\n";
+        os << "Sequence" << i << "Length\t" << ml.seq_table[i]->length() << "\n";
+    }
+    os << "MatchCount\t" << ml.size() << "\n";
+    for (const Match* m : ml) os << *m << "\n";
+}
+
+/* mems::MatchFinder — holds the device context and the sequences added so far. */
+class MatchFinder {
+public:
+    MatchFinder() : ctx_(nullptr), seq_count(0), seed_(0), log_(nullptr) {}
+    MatchFinder(const MatchFinder& o) : ctx_(nullptr), seq_count(0), seed_(o.seed_), log_(o.log_) {}
+    virtual ~MatchFinder() { if (ctx_) mb_ctx_destroy(ctx_); }
+    virtual MatchFinder* Clone() const = 0;
+
+    virtual boolean AddSequence(SortedMerList* sar, genome::gnSequence* seq = nullptr) {
+        if (!sar) return false;
+        if (!ensure_ctx()) return false;
+        if (seq_count == 0) seed_ = sar->Seed();
+        else if (sar->Seed() != seed_) { genome::ErrorMsg("AddSequence: all sorted mer lists must use the same seed\n"); return false; }
+        const genome::gnSequence* s = seq ? seq : sar->Sequence();
+        int rc = mb_add_sequence(ctx_, (const uint8_t*)s->data().data(), s->length(), 0, nullptr);
+        if (rc != MB_OK) { report("AddSequence", rc); return false; }
+        ++seq_count;
+        return true;
+    }
+    virtual void Clear() {}
+    virtual void ClearSequences() { if (ctx_) mb_clear_sequences(ctx_); seq_count = 0; }
+    void LogProgress(std::ostream* os) { log_ = os; }
+    uint32 SeqCount() const { return seq_count; }
+
+protected:
+    bool ensure_ctx() {
+        if (ctx_) return true;
+        int rc = mb_ctx_create(&ctx_, device_from_env());
+        if (rc != MB_OK) { ctx_ = nullptr; report("mb_ctx_create", rc); return false; }
+        return true;
+    }
+    static int device_from_env() { const char* e = getenv("MAUVE_B200_DEVICE"); return e ? atoi(e) : 0; }
+    void report(const char* what, int rc) const {
+        genome::ErrorMsg(std::string(what) + ": " + mb_strerror(rc) + (ctx_ ? std::string(" ") + mb_last_cuda_error(ctx_) : "") + "\n");
+    }
+    /* run one search with the sequences added so far; fills `out` (dense = one column per sequence) */
+    boolean run(const mb_params& p, MatchList& out, bool dense) {
+        if (!ctx_ || seq_count == 0) return false;
+        int rc = mb_set_seed(ctx_, seed_);
+        const mb_result* r = nullptr;
+        if (rc == MB_OK) rc = mb_find(ctx_, &p, &r);
+        if (rc != MB_OK) { report("FindMatches", rc); return false; }
+        if (log_) *log_ << r->n_matches << " matches\n";
+        for (uint64_t i = 0; i < r->n_matches; ++i) {
+            uint64_t a = r->comp_off[i], b = r->comp_off[i + 1];
+            Match* m = new Match(dense ? seq_count : (uint)(b - a));
+            m->SetLength(r->length[i]);
+            for (uint64_t k = a; k < b; ++k) m->SetStart(dense ? r->comp_seq[k] : (uint)(k - a), r->comp_start[k]);
+            out.push_back(m);
+        }
+        return true;
+    }
+    mb_ctx* ctx_;
+    uint32 seq_count;
+    uint64 seed_;
+    std::ostream* log_;
+};
+
+/* mems::MemHash: multi-MUM search = unique-seed filter + extension + containment de-dup. */
+class MemHash : public MatchFinder {
+public:
+    MemHash() : mask_(0) {}
+    MemHash(const MemHash& o) : MatchFinder(o), mask_(o.mask_) {}
+    virtual MemHash* Clone() const { return new MemHash(*this); }
+
+    /* FindMatches(MatchList&): adds every sequence of the list, searches, and appends the matches to the list
+     * (GetMatchList semantics, src/progressiveMauve.cpp:538-547). */
+    virtual boolean FindMatches(MatchList& match_list) {
+        for (size_t i = 0; i < match_list.seq_table.size(); ++i)
+            if (!AddSequence(match_list.sml_table[i], match_list.seq_table[i])) {
+                genome::ErrorMsg("Error adding " + (i < match_list.seq_filename.size() ? match_list.seq_filename[i] : std::string("sequence")) + "\n");
+                return false;
+            }
+        found_.clear();
+        mb_params p = {MB_MODE_UNIQUE, 0, 2, 1000, mask_};
+        if (!run(p, found_, true)) return false;
+        GetMatchList(match_list);
+        return true;
+    }
+    /* FindMatchesFromPosition(match_list, start_offsets): the resumable entry of mauveAligner
+     * (src/mauveAligner.cpp:585).  The device search takes milliseconds, so offsets are ignored. */
+    boolean FindMatchesFromPosition(MatchList& match_list, const std::vector<gnSeqI>&) { return FindMatches(match_list); }
+    virtual void GetMatchList(MatchList& ml) {
+        ml.clear();
+        for (Match* m : found_) ml.push_back(m->Copy());
+    }
+    virtual void Clear() { for (Match* m : found_) m->Free(); found_.clear(); }
+    virtual ~MemHash() { for (Match* m : found_) m->Free(); }
+protected:
+    uint64 mask_;
+    MatchList found_;
+};
+
+class MaskedMemHash : public MemHash {
+public:
+    virtual MaskedMemHash* Clone() const { return new MaskedMemHash(*this); }
+    void SetMask(uint64 mask) { mask_ = mask; }
+};
+
+} // namespace mems
+
+/* src/UniqueMatchFinder.h:21-32 */
+class UniqueMatchFinder : public mems::MemHash {
+public:
+    UniqueMatchFinder() {}
+    ~UniqueMatchFinder() {}
+    UniqueMatchFinder(const UniqueMatchFinder& mh) : mems::MemHash(mh) {}
+    virtual UniqueMatchFinder* Clone() const { return new UniqueMatchFinder(*this); }
+};
+
+/* src/SeedMatchEnumerator.h:14-49 */
+class SeedMatchEnumerator : public mems::MatchFinder {
+public:
+    virtual SeedMatchEnumerator* Clone() const { return new SeedMatchEnumerator(*this); }
+
+    void FindMatches(mems::MatchList& match_list, size_t min_multi = 2, size_t max_multi = 1000, bool direct_repeats_only = false) {
+        this->max_multiplicity = max_multi;
+        this->min_multiplicity = min_multi;
+        this->only_direct = direct_repeats_only;
+        for (size_t seqI = 0; seqI < match_list.seq_table.size(); ++seqI) {
+            if (!AddSequence(match_list.sml_table[seqI], match_list.seq_table[seqI])) {
+                genome::ErrorMsg("Error adding " + (seqI < match_list.seq_filename.size() ? match_list.seq_filename[seqI] : std::string("sequence")) + "\n");
+                return;
+            }
+        }
+        mlist.clear(); /* the reference never clears mlist; fixed here */
+        CreateMatches();
+        match_list.clear();
+        match_list.insert(match_list.end(), mlist.begin(), mlist.end());
+    }
+    /* does nothing unless exactly one sequence was added (src/SeedMatchEnumerator.h:59-65) */
+    virtual boolean CreateMatches() {
+        if (seq_count == 1) {
+            mb_params p = {MB_MODE_SEED_ENUM, only_direct ? 1 : 0, (uint64_t)min_multiplicity, (uint64_t)max_multiplicity, 0};
+            return run(p, mlist, false);
+        }
+        return false;
+    }
+protected:
+    mems::MatchList mlist;
+private:
+    size_t max_multiplicity = 1000;
+    size_t min_multiplicity = 2;
+    bool only_direct = false;
+};
+
+#endif

@@ -190,3 +190,43 @@ def test_baseline_configs_scaled(ctx, config, scale):
         assert got["unique_mers_per_seq"].tolist() == want["unique_mers_per_seq"].tolist()
         # weight-19 seeds on one genome: the UNIQUE match set is empty by construction (UniqueMatchFinder.cpp:57)
         assert run(ctx, seqs, pattern, 0)["n_matches"] == 0
+
+
+def test_cpp_host_api_matches_oracle(tmp_path):
+    """The reference-shaped C++ classes (include/mems_compat) drive the same C ABI: compile the little driver,
+    run UniqueMatchFinder / SeedMatchEnumerator / UniqueMerCount, compare the printed lists with the oracle."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "compat_driver"
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", os.path.join(root, "include"),
+                           os.path.join(root, "tests", "cpp", "compat_driver.cpp"), "-o", str(exe),
+                           "-L", os.path.join(root, "mauvealigner_b200"), "-lmauve_b200",
+                           "-Wl,-rpath," + os.path.join(root, "mauvealigner_b200")])
+    import mauvealigner_b200 as mb
+    rng = np.random.default_rng(77)
+    seqs = family(rng, 6000, 3, sub=0.02, indel=0.002, inv=1)
+    files = []
+    for i, s in enumerate(seqs):
+        f = tmp_path / f"s{i}.txt"
+        f.write_text(s + "\n")
+        files.append(str(f))
+
+    def parse(out):
+        lines = out.strip().split("\n")
+        k = [i for i, l in enumerate(lines) if l.startswith("MatchCount")][0]
+        assert int(lines[k].split()[1]) == len(lines) - k - 1
+        return [[int(x) for x in l.split("\t")] for l in lines[k + 1:]]
+
+    out = subprocess.check_output([str(exe), "umf", "11", "0"] + files, text=True)
+    want = O.find(seqs, mb.get_seed(11, 0), O.MODE_UNIQUE)
+    rows = []
+    for ln, comps in O.matches_as_list(want):
+        d = dict(comps)
+        rows.append([ln] + [d.get(g, 0) for g in range(3)])
+    assert parse(out) == rows and len(rows) > 10
+    out = subprocess.check_output([str(exe), "sme", "9", "0", files[0]], text=True)
+    want = O.find(seqs[:1], mb.get_seed(9, 0), O.MODE_SEED_ENUM, min_multi=2, max_multi=500)
+    assert parse(out) == [[ln] + [s for _, s in comps] for ln, comps in O.matches_as_list(want)]
+    out = subprocess.check_output([str(exe), "count", "9", "0", files[0]], text=True)
+    assert int(out.split()[-1]) == O.find(seqs[:1], mb.get_seed(9, 0), O.MODE_UNIQUE_COUNT)["unique_mers"]

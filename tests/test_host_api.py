@@ -1,0 +1,103 @@
+"""Host-side tests: the C ABI library loads and exports every symbol of include/mauve_b200.h, the C++ mirror of
+the reference classes compiles, seed tables agree between C and Python.  No GPU, no compute calls."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _build():
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as g
+    g.build()
+
+
+def test_library_exports_every_declared_symbol():
+    _build()
+    import mauvealigner_b200 as mb
+    hdr = open(os.path.join(ROOT, "include", "mauve_b200.h")).read()
+    declared = set(re.findall(r"\b(mb_[a-z_0-9]+)\s*\(", hdr))
+    declared -= {"mb_params", "mb_result", "mb_stats", "mb_ctx", "mb_synth"}
+    assert len(declared) >= 20
+    lib = ctypes.CDLL(mb._lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), name
+    assert set(mb._lib.EXPORTS) <= declared
+
+
+def test_no_cpu_fallback_without_gpu():
+    import mauvealigner_b200 as mb
+    if mb.lib().mb_device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(mb.MauveError):
+        mb.Context(0)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "mauvealigner_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "oracle" not in src.lower(), (f, "product code must not reference oracle/")
+    for f in os.listdir(os.path.join(ROOT, "include")):
+        p = os.path.join(ROOT, "include", f)
+        if os.path.isfile(p):
+            assert "oracle" not in open(p).read().lower()
+
+
+def test_seed_tables_agree_c_and_python(tmp_path):
+    import mauvealigner_b200 as mb
+    src = tmp_path / "seeds.c"
+    src.write_text('#include <stdio.h>\n#include "mauve_b200/seed_masks.h"\nint main(){int rk[5]={0,1,2,MB_CODING_SEED,MB_SOLID_SEED};'
+                   'for(int w=3;w<=31;w++)for(int r=0;r<5;r++)printf("%d %d %llu %d\\n",w,r,(unsigned long long)mb_get_seed(w,rk[r]),'
+                   'mb_seed_valid(mb_get_seed(w,rk[r])));for(unsigned long long l=1000;l<4000000000ULL;l*=3)printf("d %llu %d\\n",l,mb_default_seed_weight(l));return 0;}')
+    exe = tmp_path / "seeds"
+    subprocess.check_call(["gcc", "-O1", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = subprocess.check_output([str(exe)], text=True).split("\n")
+    ranks = [0, 1, 2, mb.CODING_SEED, mb.SOLID_SEED]
+    n = 0
+    for line in out:
+        t = line.split()
+        if not t:
+            continue
+        if t[0] == "d":
+            assert mb.default_seed_weight(int(t[1])) == int(t[2]), line
+            continue
+        w, r, pat, valid = int(t[0]), int(t[1]), int(t[2]), int(t[3])
+        assert mb.get_seed(w, ranks[r]) == pat, line
+        if pat:
+            assert valid == 1 and mb.seed_valid(pat)
+            assert mb.seed_weight(pat) == (w if w % 2 else w - 1)
+        n += 1
+    assert n == 29 * 5
+    assert mb.default_seed_weight(5_000_000) == 15
+
+
+def test_cpp_mirror_compiles(tmp_path):
+    _build()
+    exe = tmp_path / "compat_driver"
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "compat_driver.cpp"), "-o", str(exe),
+                           "-L", os.path.join(ROOT, "mauvealigner_b200"), "-lmauve_b200",
+                           "-Wl,-rpath," + os.path.join(ROOT, "mauvealigner_b200")])
+    assert exe.exists()
+
+
+def test_python_mirror_shapes():
+    import mauvealigner_b200 as mb
+    m = mb.Match(3)
+    m.SetLength(21)
+    m.SetStart(0, 5)
+    m.SetStart(2, -9)
+    assert m.Multiplicity() == 2 and m.Orientation(0) == 0 and m.Orientation(2) == 1 and m[1] == mb.NO_MATCH
+    assert m.Copy().Length() == 21 and m.LeftEnd(2) == 9
+    ml = mb.MatchList()
+    ml.seq_table = ["ACGT" * 100, "ACGA" * 100]
+    ml.CreateMemorySMLs(0)
+    assert mb.seed_valid(ml.seed_pattern) and ml.sml_table[0].SeedLength() == mb.seed_length(ml.seed_pattern)
