@@ -1,110 +1,6 @@
 // api.cu — the C ABI of include/mauve_b200.h: context, inputs, the seed-to-multi-MUM pipeline driver,
 // result transfer.  No CPU fallback: every compute entry point needs a CUDA device.
-#include "../../include/mauve_b200.h"
-#include "common.cuh"
-#include "kernels.h"
-
-#include <algorithm>
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
-#include <new>
-#include <vector>
-
-namespace {
-
-struct DBuf {
-    void* p = nullptr;
-    size_t cap = 0;
-    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
-};
-
-enum { EV_START, EV_EXTRACT, EV_SORT, EV_BUCKET, EV_DEDUP, EV_OUTPUT, EV_COUNT };
-enum { SC_RUNS = 0 /*u32[2]*/, SC_CAND = 1 /*u32[2]*/, SC_NBUCKETS = 2, SC_UNDECIDED = 3, SC_EXTENDED = 4, SC_NMATCH = 5, SC_NCOMP = 6,
-       SC_BMTOTAL = 7, SC_DDCTR = 8 /* 16 x u32 */, SC_COUNT = 16 };
-
-} // namespace
-
-struct mb_ctx {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    bool own_stream = false;
-    char err[512] = {0};
-
-    // inputs
-    std::vector<u64> seq_len;
-    std::vector<u64> seq_word_base;
-    u64 words_used = 0;
-    DBuf packed, ascii_stage;
-    u64 pattern = 0;
-    SeedDev sd{};
-    bool seed_set = false;
-
-    // workspace
-    DBuf keysA, keysB, valsA, valsB, hist, digit_base, lookback, tickets, status, scalars, per_seq, tile_first;
-    DBuf cand_run, cand_off, cand_aux, comp_pos, comp_gs, bitmap, bmrank, slot_of, cand_at, cstate, covered, minrank, ext_l, ext_r;
-    DBuf trace;
-    DBuf wl_a, wl_b, wl_c, wl_long, wd_a, wd_b, wd_c, batch_bits, ghash, gid, slot_gid, slot_x, gid_table, rng_lo, rng_hi;
-    DBuf flags, match_idx, sort_kA, sort_kB, sort_vA, sort_vB, ncomp, mers_tmp;
-    DBuf out_len, out_off, out_seq, out_start;
-    u32 ticket_next = 0;
-    u64 tmp_u64 = 0;
-    size_t status_next = 0;
-
-    // last run
-    GenomeTable gt{};
-    RecFmt fmt{};
-    const u64* sorted_keys = nullptr;
-    const u64* sorted_vals = nullptr;
-    u32 n_seeds = 0;
-    bool have_result = false;
-    u64 r_matches = 0, r_comps = 0, r_unique = 0;
-    int last_mode = 0;
-
-    // host result (pinned)
-    void* h_len = nullptr; void* h_off = nullptr; void* h_seq = nullptr; void* h_start = nullptr; void* h_perseq = nullptr; void* h_scal = nullptr;
-    size_t h_len_cap = 0, h_off_cap = 0, h_seq_cap = 0, h_start_cap = 0;
-    mb_result res{};
-    mb_stats stats{};
-    cudaEvent_t ev[EV_COUNT] = {nullptr};
-    cudaEvent_t ev_x[4] = {nullptr};
-    cudaEvent_t ev_r[16] = {nullptr};
-    int n_timed_passes = 0;
-
-    void set_cuda_error(cudaError_t e, const char* what, int line) {
-        snprintf(err, sizeof(err), "%s (%s) at api.cu:%d: %s", cudaGetErrorName(e), cudaGetErrorString(e), line, what);
-    }
-    int reserve(DBuf& b, size_t bytes) {
-        if (bytes <= b.cap) return MB_OK;
-        if (b.p) cudaFree(b.p);
-        b.p = nullptr; b.cap = 0;
-        size_t want = bytes + bytes / 8 + 256;
-        cudaError_t e = cudaMalloc(&b.p, want);
-        if (e != cudaSuccess) { set_cuda_error(e, "cudaMalloc", __LINE__); return e == cudaErrorMemoryAllocation ? MB_E_NOMEM : MB_E_CUDA; }
-        b.cap = want;
-        return MB_OK;
-    }
-    int reserve_host(void*& p, size_t& cap, size_t bytes) {
-        if (bytes <= cap) return MB_OK;
-        if (p) cudaFreeHost(p);
-        p = nullptr; cap = 0;
-        size_t want = bytes + bytes / 8 + 256;
-        cudaError_t e = cudaMallocHost(&p, want);
-        if (e != cudaSuccess) { set_cuda_error(e, "cudaMallocHost", __LINE__); return MB_E_NOMEM; }
-        cap = want;
-        return MB_OK;
-    }
-    u32* ticket() { return tickets.as<u32>() + (ticket_next++); }
-    u64* status_slice(size_t n_tiles) {
-        u64* p = status.as<u64>() + status_next;
-        status_next += n_tiles + 1;
-        return p;
-    }
-};
-
-#define TRY(expr) do { int _rc = (expr); if (_rc != MB_OK) return _rc; } while (0)
-#define LAUNCHED(ctx) do { ++(ctx)->stats.kernel_launches; } while (0)
-#define CHECK_LAUNCH(ctx) CUDA_TRY(ctx, cudaGetLastError())
+#include "ctx.h"
 
 static void free_buf(DBuf& b) { if (b.p) cudaFree(b.p); b.p = nullptr; b.cap = 0; }
 
@@ -295,11 +191,12 @@ int mb_add_sequence_device(mb_ctx* c, const void* dev_ascii, uint64_t len, int* 
     return add_sequence_common(c, dev_ascii, len, 2, out_id);
 }
 
+} // extern "C"
+
 // ---------------------------------------------------------------------------------- sort driver
 // LSD radix sort of n (key[, val]) records on key bits [shift, shift+kbits).  On return *kA/*vA hold
 // the sorted data (the buffers are swapped as needed).
-static int sort_records(mb_ctx* c, u64** kA, u64** kB, u64** vA, u64** vB, u32 n, int shift, int kbits, bool hist_ready,
-                        bool time_passes = false) {
+int mbi_sort_records(mb_ctx* c, u64** kA, u64** kB, u64** vA, u64** vB, u32 n, int shift, int kbits, bool hist_ready, bool time_passes) {
     int npass = (kbits + 7) / 8;
     if (n == 0 || npass == 0) return MB_OK;
     if (!hist_ready) {
@@ -324,13 +221,15 @@ static int sort_records(mb_ctx* c, u64** kA, u64** kB, u64** vA, u64** vB, u32 n
     return MB_OK;
 }
 
-static int bits_for(u64 maxval) { int b = 0; while (maxval) { ++b; maxval >>= 1; } return b; }
+int mbi_bits_for(u64 maxval) { int b = 0; while (maxval) { ++b; maxval >>= 1; } return b; }
 
-static int read_scalars(mb_ctx* c) {
+int mbi_read_scalars(mb_ctx* c) {
     CUDA_TRY(c, cudaMemcpyAsync(c->h_scal, c->scalars.p, SC_COUNT * 8, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return MB_OK;
 }
+
+extern "C" {
 
 int mb_find_device(mb_ctx* c, const mb_params* prm) {
     if (!c || !prm) return MB_E_ARG;
@@ -378,8 +277,8 @@ int mb_find_device(mb_ctx* c, const mb_params* prm) {
     c->stats.n_seeds = n;
     RecFmt& fmt = c->fmt;
     fmt.kbits = 2 * sd.w;
-    fmt.gbits = bits_for(nseq - 1);
-    fmt.pbits = bits_for(maxlen ? maxlen - 1 : 0);
+    fmt.gbits = mbi_bits_for(nseq - 1);
+    fmt.pbits = mbi_bits_for(maxlen ? maxlen - 1 : 0);
     if (fmt.pbits == 0) fmt.pbits = 1;
     fmt.wide = (fmt.kbits + fmt.gbits + fmt.pbits + 1) > 64;
     fmt.kshift = fmt.wide ? 0 : fmt.gbits + fmt.pbits + 1;
@@ -416,7 +315,7 @@ int mb_find_device(mb_ctx* c, const mb_params* prm) {
     if (n_tiles) { LAUNCHED(c); CHECK_LAUNCH(c); }
     cudaEventRecord(c->ev[EV_EXTRACT], st);
     // ---- a4 + a6: one stable radix sort over the seed bits
-    TRY(sort_records(c, &kA, &kB, fmt.wide ? &vA : nullptr, fmt.wide ? &vB : nullptr, n, fmt.kshift, fmt.kbits, true, true));
+    TRY(mbi_sort_records(c, &kA, &kB, fmt.wide ? &vA : nullptr, fmt.wide ? &vB : nullptr, n, fmt.kshift, fmt.kbits, true, true));
     c->sorted_keys = kA; c->sorted_vals = vA;
     cudaEventRecord(c->ev[EV_SORT], st);
 
@@ -441,7 +340,7 @@ int mb_find_device(mb_ctx* c, const mb_params* prm) {
     if (mode == MB_MODE_UNIQUE_COUNT) {
         for (int i = EV_BUCKET; i < EV_COUNT; ++i) cudaEventRecord(c->ev[i], st);
         CUDA_TRY(c, cudaMemcpyAsync(c->h_perseq, c->per_seq.p, MB_MAX_SEQ * 8, cudaMemcpyDeviceToHost, st));
-        TRY(read_scalars(c));
+        TRY(mbi_read_scalars(c));
         c->r_unique = reinterpret_cast<u32*>((u64*)c->h_scal + SC_RUNS)[0];
         c->stats.n_runs = c->r_unique;
         c->have_result = true;
@@ -464,7 +363,7 @@ int mb_find_device(mb_ctx* c, const mb_params* prm) {
     launch_select(sa, fmt, n, st);
     LAUNCHED(c); CHECK_LAUNCH(c);
     memset(c->h_perseq, 0, MB_MAX_SEQ * 8); // per-sequence counts are a MODE_UNIQUE_COUNT product
-    TRY(read_scalars(c));
+    TRY(mbi_read_scalars(c));
     const u32* hs32 = reinterpret_cast<const u32*>(c->h_scal);
     const u64* hs64 = reinterpret_cast<const u64*>(c->h_scal);
     const u32 n_runs = hs32[2 * SC_RUNS], n_cand = hs32[2 * SC_CAND], n_ccomp = hs32[2 * SC_CAND + 1];
@@ -489,7 +388,7 @@ int mb_find_device(mb_ctx* c, const mb_params* prm) {
             u64 *skA = c->sort_kA.as<u64>(), *skB = c->sort_kB.as<u64>(), *svA = c->sort_vA.as<u64>(), *svB = c->sort_vB.as<u64>();
             ea.sort_key = skA; ea.sort_val = svA; ea.ncomp = c->ncomp.as<u32>();
             launch_enum_keys(ea, fmt, n_cand, st); LAUNCHED(c); CHECK_LAUNCH(c);
-            TRY(sort_records(c, &skA, &skB, &svA, &svB, n_cand, 0, fmt.pbits, false));
+            TRY(mbi_sort_records(c, &skA, &skB, &svA, &svB, n_cand, 0, fmt.pbits, false));
             // component counts in sorted order -> offsets
             // (ncomp was written in candidate order; permute through the sorted values inside the gather scan input)
             OutputArgs oa{};
@@ -567,7 +466,7 @@ int mb_find_device(mb_ctx* c, const mb_params* prm) {
             // slot order = (group id, position): list in (first genome, position) order, stable sort by group id
             u64 *skA = c->sort_kA.as<u64>(), *skB = c->sort_kB.as<u64>(), *svA = c->sort_vA.as<u64>(), *svB = c->sort_vB.as<u64>();
             launch_slot_keys(da, gt, skA, svA, st); LAUNCHED(c);
-            TRY(sort_records(c, &skA, &skB, &svA, &svB, n_cand, 0, bits_for(n_cand), false));
+            TRY(mbi_sort_records(c, &skA, &skB, &svA, &svB, n_cand, 0, mbi_bits_for(n_cand), false));
             launch_slot_finish(da, skA, svA, st); LAUNCHED(c); CHECK_LAUNCH(c);
         }
         cudaEventRecord(c->ev_x[0], st);
@@ -611,7 +510,7 @@ int mb_find_device(mb_ctx* c, const mb_params* prm) {
         launch_scan_u32(oa.flags, n_cand, c->match_idx.as<u32>(), nullptr, c->status_slice(div_up(n_cand, scan_tile())), c->ticket(),
                         scal + SC_NMATCH, st);
         LAUNCHED(c); CHECK_LAUNCH(c);
-        TRY(read_scalars(c));
+        TRY(mbi_read_scalars(c));
         n_matches = (u32)hs64[SC_NMATCH];
         c->stats.n_extended = hs32[2 * SC_EXTENDED];
         c->stats.dedup_batches = hs32[2 * SC_DDCTR + 8]; c->stats.dedup_iters = hs32[2 * SC_DDCTR + 9];
@@ -634,15 +533,15 @@ int mb_find_device(mb_ctx* c, const mb_params* prm) {
         if (n_matches) {
             u64 *skA = c->sort_kA.as<u64>(), *skB = c->sort_kB.as<u64>(), *svA = c->sort_vA.as<u64>(), *svB = c->sort_vB.as<u64>();
             oa.sort_key = skA; oa.sort_val = svA; oa.ncomp = c->ncomp.as<u32>();
-            int sbits = bits_for(maxlen);
+            int sbits = mbi_bits_for(maxlen);
             launch_uniq_keys(oa, sbits, st); LAUNCHED(c); CHECK_LAUNCH(c);
-            TRY(sort_records(c, &skA, &skB, &svA, &svB, n_matches, 0, sbits + 6, false));
+            TRY(mbi_sort_records(c, &skA, &skB, &svA, &svB, n_matches, 0, sbits + 6, false));
             launch_uniq_tiefix(oa, skA, svA, L, n_matches, st); LAUNCHED(c);
             launch_uniq_ncomp(oa, svA, n_matches, st); LAUNCHED(c);
             launch_scan_u32(oa.ncomp, n_matches, nullptr, c->out_off.as<u64>(), c->status_slice(div_up(n_matches, scan_tile())), c->ticket(),
                             scal + SC_NCOMP, st);
             LAUNCHED(c); CHECK_LAUNCH(c);
-            TRY(read_scalars(c));
+            TRY(mbi_read_scalars(c));
             n_ocomp = hs64[SC_NCOMP];
             TRY(c->reserve(c->out_seq, (size_t)(n_ocomp + 8) * 4));
             TRY(c->reserve(c->out_start, (size_t)(n_ocomp + 8) * 8));

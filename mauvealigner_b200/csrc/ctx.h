@@ -1,0 +1,113 @@
+// ctx.h — the library context (device buffers, last-run state) shared by api.cu and api_dist.cu.
+#pragma once
+#include "../../include/mauve_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+struct DBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+enum { EV_START, EV_EXTRACT, EV_SORT, EV_BUCKET, EV_DEDUP, EV_OUTPUT, EV_COUNT };
+enum { SC_RUNS = 0 /*u32[2]*/, SC_CAND = 1 /*u32[2]*/, SC_NBUCKETS = 2, SC_UNDECIDED = 3, SC_EXTENDED = 4, SC_NMATCH = 5, SC_NCOMP = 6,
+       SC_BMTOTAL = 7, SC_DDCTR = 8 /* 16 x u32 */, SC_COUNT = 16 };
+
+struct mb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    char err[512] = {0};
+
+    // inputs
+    std::vector<u64> seq_len;
+    std::vector<u64> seq_word_base;
+    u64 words_used = 0;
+    DBuf packed, ascii_stage;
+    u64 pattern = 0;
+    SeedDev sd{};
+    bool seed_set = false;
+
+    // workspace
+    DBuf keysA, keysB, valsA, valsB, hist, digit_base, lookback, tickets, status, scalars, per_seq, tile_first;
+    DBuf cand_run, cand_off, cand_aux, comp_pos, comp_gs, bitmap, bmrank, slot_of, cand_at, cstate, covered, minrank, ext_l, ext_r;
+    DBuf trace;
+    DBuf wl_a, wl_b, wl_c, wl_long, wd_a, wd_b, wd_c, batch_bits, ghash, gid, slot_gid, slot_x, gid_table, rng_lo, rng_hi;
+    DBuf flags, match_idx, sort_kA, sort_kB, sort_vA, sort_vB, ncomp, mers_tmp;
+    DBuf out_len, out_off, out_seq, out_start;
+    u32 ticket_next = 0;
+    u64 tmp_u64 = 0;
+    size_t status_next = 0;
+
+    // last run
+    GenomeTable gt{};
+    RecFmt fmt{};
+    const u64* sorted_keys = nullptr;
+    const u64* sorted_vals = nullptr;
+    u32 n_seeds = 0;
+    bool have_result = false;
+    u64 r_matches = 0, r_comps = 0, r_unique = 0;
+    int last_mode = 0;
+
+    // host result (pinned)
+    void* h_len = nullptr; void* h_off = nullptr; void* h_seq = nullptr; void* h_start = nullptr; void* h_perseq = nullptr; void* h_scal = nullptr;
+    size_t h_len_cap = 0, h_off_cap = 0, h_seq_cap = 0, h_start_cap = 0;
+    mb_result res{};
+    mb_stats stats{};
+    cudaEvent_t ev[EV_COUNT] = {nullptr};
+    cudaEvent_t ev_x[4] = {nullptr};
+    cudaEvent_t ev_r[16] = {nullptr};
+    int n_timed_passes = 0;
+
+    void set_cuda_error(cudaError_t e, const char* what, int line) {
+        snprintf(err, sizeof(err), "%s (%s) at api.cu:%d: %s", cudaGetErrorName(e), cudaGetErrorString(e), line, what);
+    }
+    int reserve(DBuf& b, size_t bytes) {
+        if (bytes <= b.cap) return MB_OK;
+        if (b.p) cudaFree(b.p);
+        b.p = nullptr; b.cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&b.p, want);
+        if (e != cudaSuccess) { set_cuda_error(e, "cudaMalloc", __LINE__); return e == cudaErrorMemoryAllocation ? MB_E_NOMEM : MB_E_CUDA; }
+        b.cap = want;
+        return MB_OK;
+    }
+    int reserve_host(void*& p, size_t& cap, size_t bytes) {
+        if (bytes <= cap) return MB_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e != cudaSuccess) { set_cuda_error(e, "cudaMallocHost", __LINE__); return MB_E_NOMEM; }
+        cap = want;
+        return MB_OK;
+    }
+    u32* ticket() { return tickets.as<u32>() + (ticket_next++); }
+    u64* status_slice(size_t n_tiles) {
+        u64* p = status.as<u64>() + status_next;
+        status_next += n_tiles + 1;
+        return p;
+    }
+};
+
+#define TRY(expr) do { int _rc = (expr); if (_rc != MB_OK) return _rc; } while (0)
+#define LAUNCHED(ctx) do { ++(ctx)->stats.kernel_launches; } while (0)
+#define CHECK_LAUNCH(ctx) CUDA_TRY(ctx, cudaGetLastError())
+
+
+// helpers defined in api.cu
+int mbi_sort_records(mb_ctx* c, u64** kA, u64** kB, u64** vA, u64** vB, u32 n, int shift, int kbits, bool hist_ready, bool time_passes = false);
+int mbi_read_scalars(mb_ctx* c);
+int mbi_bits_for(u64 maxval);
+// stages of the MODE_UNIQUE tail, shared by the single-GPU and the distributed drivers
+int mbi_reserve_candidates(mb_ctx* c, u32 n_cand, u32 n_ccomp, u64 bases);
+int mbi_dedup(mb_ctx* c, u32 n_cand, int owner_rank, int owner_world);
+int mbi_output_unique(mb_ctx* c, u32 n_cand, u64 maxlen);
