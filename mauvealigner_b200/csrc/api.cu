@@ -87,7 +87,7 @@ int mb_ctx_destroy(mb_ctx* c) {
     cudaStreamSynchronize(c->stream);
     DBuf* bufs[] = {&c->packed, &c->ascii_stage, &c->keysA, &c->keysB, &c->valsA, &c->valsB, &c->hist, &c->digit_base, &c->lookback, &c->tickets,
                     &c->status, &c->scalars, &c->per_seq, &c->tile_first, &c->cand_run, &c->cand_off, &c->cand_aux, &c->comp_pos, &c->comp_gs,
-                    &c->bitmap, &c->bmrank, &c->slot_of, &c->cand_at, &c->cstate, &c->covered, &c->minrank, &c->ext_l, &c->ext_r, &c->wl_a, &c->wl_b, &c->wl_c, &c->wl_long, &c->wd_a, &c->wd_b, &c->wd_c, &c->batch_bits, &c->trace, &c->ghash, &c->gid, &c->slot_gid, &c->slot_x, &c->rng_lo, &c->rng_hi, &c->gid_table, &c->flags,
+                    &c->bitmap, &c->bmrank, &c->cand_at, &c->cstate, &c->covered, &c->minrank, &c->ext_l, &c->ext_r, &c->wl_a, &c->wl_b, &c->wl_c, &c->wl_long, &c->wd_a, &c->wd_b, &c->wd_c, &c->live_bits, &c->trace, &c->ghash, &c->slot_gp, &c->slot_hash, &c->link_bits, &c->chain_min, &c->rep_bits, &c->rep_rank, &c->s_hash, &c->s_cand, &c->rng_lo, &c->rng_hi, &c->flags,
                     &c->match_idx, &c->sort_kA, &c->sort_kB, &c->sort_vA, &c->sort_vB, &c->ncomp, &c->mers_tmp, &c->out_len, &c->out_off,
                     &c->out_seq, &c->out_start};
     for (DBuf* b : bufs) free_buf(*b);
@@ -295,7 +295,7 @@ int mb_find_device(mb_ctx* c, const mb_params* prm) {
     TRY(c->reserve(c->lookback, (size_t)(div_up(n, radix_tile_size()) + 1) * 256 * 8));
     TRY(c->reserve(c->tickets, 256 * 4));
     size_t status_words = (size_t)div_up(n, find_runs_tile()) + div_up(n, select_tile()) + 3 * (size_t)div_up(n, scan_tile()) +
-                          div_up(bases / 64 + 2, scan_tile()) + 64;
+                          div_up(bases / 64 + 2, scan_tile()) + 2 * (size_t)div_up(n / 2 + 2, chain_tile()) + div_up(n / 128 + 4, scan_tile()) + 64;
     TRY(c->reserve(c->status, status_words * 8));
     TRY(c->reserve(c->scalars, SC_COUNT * 8));
     TRY(c->reserve(c->per_seq, MB_MAX_SEQ * 8));
@@ -412,143 +412,24 @@ int mb_find_device(mb_ctx* c, const mb_params* prm) {
     }
 
     // ---- MODE_UNIQUE: a9 candidates (HashMatch + SetDirection)
-    const u64 bm_words = bases / 64 + 2;
-    TRY(c->reserve(c->comp_pos, (size_t)(n_ccomp + 8) * 4));
-    TRY(c->reserve(c->comp_gs, (size_t)(n_ccomp + 8)));
-    TRY(c->reserve(c->bitmap, bm_words * 8));
-    TRY(c->reserve(c->bmrank, (bm_words + 1) * 4));
-    TRY(c->reserve(c->slot_of, (size_t)(n_cand + 8) * 4));
-    TRY(c->reserve(c->cand_at, (size_t)(n_cand + 8) * 4));
-    TRY(c->reserve(c->cstate, (size_t)n_cand + 8));
-    TRY(c->reserve(c->covered, ((size_t)n_cand / 64 + 2) * 8));
-    TRY(c->reserve(c->minrank, (size_t)(n_cand + 8) * 4));
-    TRY(c->reserve(c->ext_l, (size_t)(n_cand + 8) * 4));
-    TRY(c->reserve(c->ext_r, (size_t)(n_cand + 8) * 4));
-    TRY(c->reserve(c->ghash, (size_t)(n_cand + 8) * 8));
-    TRY(c->reserve(c->gid, (size_t)(n_cand + 8) * 4));
-    TRY(c->reserve(c->slot_gid, (size_t)(n_cand + 8) * 4));
-    TRY(c->reserve(c->slot_x, (size_t)(n_cand + 8) * 4));
-    TRY(c->reserve(c->rng_lo, (size_t)(n_cand + 8) * 4));
-    TRY(c->reserve(c->rng_hi, (size_t)(n_cand + 8) * 4));
-    TRY(c->reserve(c->sort_kA, (size_t)(n_cand + 8) * 8)); TRY(c->reserve(c->sort_kB, (size_t)(n_cand + 8) * 8));
-    TRY(c->reserve(c->sort_vA, (size_t)(n_cand + 8) * 8)); TRY(c->reserve(c->sort_vB, (size_t)(n_cand + 8) * 8));
-    u32 gid_table_size = 1024;
-    while (gid_table_size < 2 * (u64)n_cand) gid_table_size <<= 1;
-    TRY(c->reserve(c->gid_table, (size_t)gid_table_size * 4));
+    TRY(mbi_reserve_candidates(c, n_cand, n_ccomp, bases));
     u32 n_matches = 0;
     u64 n_ocomp = 0;
     if (n_cand) {
+        const u64 bm_words = bases / 64 + 2;
         CUDA_TRY(c, cudaMemsetAsync(c->bitmap.p, 0, bm_words * 8, st));
-        CUDA_TRY(c, cudaMemsetAsync(c->cstate.p, 0xFF, n_cand, st));
-        CUDA_TRY(c, cudaMemsetAsync(c->covered.p, 0, ((size_t)n_cand / 64 + 2) * 8, st));
-        CUDA_TRY(c, cudaMemsetAsync(c->gid_table.p, 0, (size_t)gid_table_size * 4, st));
         EmitUniqueArgs eu{};
         eu.keys = kA; eu.vals = vA; eu.run_start = run_start; eu.run_u = run_u;
         eu.cand_run = c->cand_run.as<u32>(); eu.cand_off = c->cand_off.as<u32>(); eu.cand_aux = nullptr;
         eu.totals = reinterpret_cast<u32*>(scal + SC_CAND);
         eu.mode = mode; eu.comp_pos = c->comp_pos.as<u32>(); eu.comp_gs = c->comp_gs.as<u8>(); eu.bitmap = c->bitmap.as<u64>(); eu.ghash = c->ghash.as<u64>();
         launch_emit_unique(eu, fmt, gt, n_cand, st); LAUNCHED(c); CHECK_LAUNCH(c);
-        launch_scan_popc(c->bitmap.as<u64>(), bm_words, c->bmrank.as<u32>(), c->status_slice(div_up(bm_words, scan_tile())), c->ticket(),
-                         scal + SC_BMTOTAL, st);
-        LAUNCHED(c); CHECK_LAUNCH(c);
-        DedupArgs da{};
-        da.packed = c->packed.as<u64>(); da.n_cand = n_cand;
-        da.cand_off = c->cand_off.as<u32>(); da.comp_pos = c->comp_pos.as<u32>(); da.comp_gs = c->comp_gs.as<u8>();
-        da.bitmap = c->bitmap.as<u64>(); da.bmrank = c->bmrank.as<u32>();
-        da.ghash = c->ghash.as<u64>(); da.gid_table = c->gid_table.as<u32>(); da.gid_table_mask = gid_table_size - 1;
-        da.gid = c->gid.as<u32>(); da.slot_gid = c->slot_gid.as<u32>(); da.slot_x = c->slot_x.as<u32>();
-        da.slot_of = c->slot_of.as<u32>(); da.cand_at = c->cand_at.as<u32>();
-        da.cstate = c->cstate.as<u8>(); da.cov_bits = c->covered.as<u64>(); da.rng_lo = c->rng_lo.as<u32>(); da.rng_hi = c->rng_hi.as<u32>(); da.minrank = c->minrank.as<u32>();
-        da.ext_l = c->ext_l.as<u32>(); da.ext_r = c->ext_r.as<u32>();
-        da.n_extended = reinterpret_cast<u32*>(scal + SC_EXTENDED);
-        launch_group_ids(da, st); LAUNCHED(c);
-        {
-            // slot order = (group id, position): list in (first genome, position) order, stable sort by group id
-            u64 *skA = c->sort_kA.as<u64>(), *skB = c->sort_kB.as<u64>(), *svA = c->sort_vA.as<u64>(), *svB = c->sort_vB.as<u64>();
-            launch_slot_keys(da, gt, skA, svA, st); LAUNCHED(c);
-            TRY(mbi_sort_records(c, &skA, &skB, &svA, &svB, n_cand, 0, mbi_bits_for(n_cand), false));
-            launch_slot_finish(da, skA, svA, st); LAUNCHED(c); CHECK_LAUNCH(c);
-        }
-        cudaEventRecord(c->ev_x[0], st);
-
-        // ---- a10 + a11: doubling batches in ascending seed order, one cooperative launch
-        TRY(c->reserve(c->wl_a, (size_t)(n_cand + 8) * 4));
-        TRY(c->reserve(c->wl_b, (size_t)(n_cand + 8) * 4));
-        TRY(c->reserve(c->wl_c, (size_t)(n_cand + 8) * 4));
-        TRY(c->reserve(c->wl_long, (size_t)(n_cand + 8) * 4));
-        TRY(c->reserve(c->wd_a, (size_t)(n_cand + 8) * 4));
-        TRY(c->reserve(c->wd_b, (size_t)(n_cand + 8) * 4));
-        TRY(c->reserve(c->wd_c, (size_t)(n_cand + 8) * 4));
-        TRY(c->reserve(c->batch_bits, ((size_t)n_cand / 64 + 2) * 8));
-        da.wl0 = c->wl_a.as<u32>(); da.wl1 = c->wl_b.as<u32>(); da.wl2 = c->wl_c.as<u32>();
-        da.wl_long = c->wl_long.as<u32>();
-        da.wd0 = c->wd_a.as<u32>(); da.wd1 = c->wd_b.as<u32>(); da.wd2 = c->wd_c.as<u32>();
-        da.batch_bits = c->batch_bits.as<u64>();
-        da.ctr = reinterpret_cast<u32*>(scal + SC_DDCTR);
-        const bool want_trace = getenv("MB_DEDUP_TRACE") != nullptr;
-        if (want_trace) {
-            TRY(c->reserve(c->trace, 8200 * 8));
-            CUDA_TRY(c, cudaMemsetAsync(c->trace.p, 0, 8200 * 8, st));
-            da.trace = c->trace.as<u64>();
-        }
-        {
-            cudaError_t e = launch_dedup_all(da, gt, sd, 131072u, st);
-            LAUNCHED(c);
-            if (e != cudaSuccess) { c->set_cuda_error(e, "launch_dedup_all", __LINE__); return MB_E_CUDA; }
-        }
-        CHECK_LAUNCH(c);
+        // ---- a10 + a11
+        TRY(mbi_dedup(c, n_cand, bases));
         cudaEventRecord(c->ev[EV_DEDUP], st);
-
-        // ---- a12: compact accepted candidates, canonical order, CSR
-        TRY(c->reserve(c->flags, (size_t)(n_cand + 8) * 4));
-        TRY(c->reserve(c->match_idx, (size_t)(n_cand + 8) * 4));
-        OutputArgs oa{};
-        oa.n_cand = n_cand; oa.cstate = da.cstate; oa.cand_off = da.cand_off; oa.comp_pos = da.comp_pos; oa.comp_gs = da.comp_gs;
-        oa.ext_l = da.ext_l; oa.ext_r = da.ext_r; oa.flags = c->flags.as<u32>(); oa.match_idx = c->match_idx.as<u32>();
-        oa.n_matches_ptr = scal + SC_NMATCH;
-        launch_uniq_flags(oa, st); LAUNCHED(c);
-        launch_scan_u32(oa.flags, n_cand, c->match_idx.as<u32>(), nullptr, c->status_slice(div_up(n_cand, scan_tile())), c->ticket(),
-                        scal + SC_NMATCH, st);
-        LAUNCHED(c); CHECK_LAUNCH(c);
-        TRY(mbi_read_scalars(c));
-        n_matches = (u32)hs64[SC_NMATCH];
-        c->stats.n_extended = hs32[2 * SC_EXTENDED];
-        c->stats.dedup_batches = hs32[2 * SC_DDCTR + 8]; c->stats.dedup_iters = hs32[2 * SC_DDCTR + 9];
-        if (want_trace) {
-            std::vector<u64> tr(8200);
-            CUDA_TRY(c, cudaMemcpy(tr.data(), c->trace.p, 8200 * 8, cudaMemcpyDeviceToHost));
-            static const char* names[] = {"", "reset", "begin", "extend", "long", "claim", "decide"};
-            u64 prev = 0;
-            for (u64 k = 0; k < tr[0] && k < 4000; ++k) {
-                u64 tag = tr[2 + 2 * k], t = tr[3 + 2 * k];
-                if (k) fprintf(stderr, "[dedup-trace] %-12s %8.1f us\n", names[tag], (double)(t - prev) / 1e3);
-                prev = t;
-            }
-        }
-        TRY(c->reserve(c->sort_kA, (size_t)(n_matches + 8) * 8)); TRY(c->reserve(c->sort_kB, (size_t)(n_matches + 8) * 8));
-        TRY(c->reserve(c->sort_vA, (size_t)(n_matches + 8) * 8)); TRY(c->reserve(c->sort_vB, (size_t)(n_matches + 8) * 8));
-        TRY(c->reserve(c->ncomp, (size_t)(n_matches + 8) * 4));
-        TRY(c->reserve(c->out_len, (size_t)(n_matches + 8) * 4));
-        TRY(c->reserve(c->out_off, (size_t)(n_matches + 8) * 8));
-        if (n_matches) {
-            u64 *skA = c->sort_kA.as<u64>(), *skB = c->sort_kB.as<u64>(), *svA = c->sort_vA.as<u64>(), *svB = c->sort_vB.as<u64>();
-            oa.sort_key = skA; oa.sort_val = svA; oa.ncomp = c->ncomp.as<u32>();
-            int sbits = mbi_bits_for(maxlen);
-            launch_uniq_keys(oa, sbits, st); LAUNCHED(c); CHECK_LAUNCH(c);
-            TRY(mbi_sort_records(c, &skA, &skB, &svA, &svB, n_matches, 0, sbits + 6, false));
-            launch_uniq_tiefix(oa, skA, svA, L, n_matches, st); LAUNCHED(c);
-            launch_uniq_ncomp(oa, svA, n_matches, st); LAUNCHED(c);
-            launch_scan_u32(oa.ncomp, n_matches, nullptr, c->out_off.as<u64>(), c->status_slice(div_up(n_matches, scan_tile())), c->ticket(),
-                            scal + SC_NCOMP, st);
-            LAUNCHED(c); CHECK_LAUNCH(c);
-            TRY(mbi_read_scalars(c));
-            n_ocomp = hs64[SC_NCOMP];
-            TRY(c->reserve(c->out_seq, (size_t)(n_ocomp + 8) * 4));
-            TRY(c->reserve(c->out_start, (size_t)(n_ocomp + 8) * 8));
-            oa.out_off = c->out_off.as<u64>(); oa.out_len = c->out_len.as<u32>(); oa.out_seq = c->out_seq.as<u32>();
-            oa.out_start = c->out_start.as<i64>();
-            launch_uniq_gather(oa, svA, L, n_matches, st); LAUNCHED(c); CHECK_LAUNCH(c);
-        }
+        // ---- a12
+        TRY(mbi_output_unique(c, n_cand, maxlen));
+        n_matches = (u32)c->r_matches; n_ocomp = c->r_comps;
     } else {
         cudaEventRecord(c->ev_x[0], st);
         cudaEventRecord(c->ev[EV_DEDUP], st);
@@ -559,6 +440,190 @@ int mb_find_device(mb_ctx* c, const mb_params* prm) {
     c->have_result = true;
     return MB_OK;
 }
+
+} // extern "C"
+
+// ---------------------------------------------------------------------------- MODE_UNIQUE tail
+// Shared by the single-GPU driver above and the distributed driver (api_dist.cu): the candidate
+// CSR (cand_off, comp_pos, comp_gs, ghash; ascending seed order) is in place on this device.
+int mbi_reserve_candidates(mb_ctx* c, u32 n_cand, u32 n_ccomp, u64 bases) {
+    const u64 bm_words = bases / 64 + 2;
+    const size_t nc = (size_t)n_cand + 8;
+    TRY(c->reserve(c->cand_off, (nc + 1) * 4));
+    TRY(c->reserve(c->comp_pos, (size_t)(n_ccomp + 8) * 4));
+    TRY(c->reserve(c->comp_gs, (size_t)(n_ccomp + 8)));
+    TRY(c->reserve(c->ghash, nc * 8));
+    TRY(c->reserve(c->bitmap, bm_words * 8));
+    TRY(c->reserve(c->bmrank, (bm_words + 1) * 4));
+    TRY(c->reserve(c->rep_bits, (nc / 64 + 2) * 8));
+    TRY(c->reserve(c->rep_rank, (nc / 64 + 4) * 4));
+    TRY(c->reserve(c->s_hash, nc * 8));
+    TRY(c->reserve(c->s_cand, nc * 4));
+    TRY(c->reserve(c->sort_kA, nc * 8));
+    TRY(c->reserve(c->sort_kB, nc * 8));
+    TRY(c->reserve(c->cand_at, nc * 4));
+    TRY(c->reserve(c->slot_gp, nc * 8));
+    TRY(c->reserve(c->slot_hash, nc * 8));
+    TRY(c->reserve(c->link_bits, nc / 8 + 16));
+    TRY(c->reserve(c->chain_min, nc * 4));
+    TRY(c->reserve(c->cstate, nc));
+    TRY(c->reserve(c->live_bits, (nc / 64 + 2) * 8));
+    TRY(c->reserve(c->covered, (nc / 64 + 2) * 8));
+    TRY(c->reserve(c->minrank, nc * 4));
+    TRY(c->reserve(c->ext_l, nc * 4));
+    TRY(c->reserve(c->ext_r, nc * 4));
+    TRY(c->reserve(c->rng_lo, nc * 4));
+    TRY(c->reserve(c->rng_hi, nc * 4));
+    TRY(c->reserve(c->wl_a, nc * 4));
+    TRY(c->reserve(c->wl_b, nc * 4));
+    TRY(c->reserve(c->wl_c, nc * 4));
+    TRY(c->reserve(c->wl_long, nc * 4));
+    TRY(c->reserve(c->wd_a, nc * 4));
+    TRY(c->reserve(c->wd_b, nc * 4));
+    TRY(c->reserve(c->wd_c, nc * 4));
+    return MB_OK;
+}
+
+// a10 + a11: chains -> extension of the chain reps -> resolve (kernels_dedup.cu).  The candidate
+// bitmap must hold one bit per candidate at (first genome, position).
+int mbi_dedup(mb_ctx* c, u32 n_cand, u64 bases) {
+    cudaStream_t st = c->stream;
+    u64* scal = c->scalars.as<u64>();
+    const u64 bm_words = bases / 64 + 2;
+    const size_t cw = (size_t)n_cand / 64 + 2; // 64-bit words of a per-slot / per-rep bitmap
+    CUDA_TRY(c, cudaMemsetAsync(c->covered.p, 0, cw * 8, st));
+    CUDA_TRY(c, cudaMemsetAsync(c->live_bits.p, 0, cw * 8, st));
+    CUDA_TRY(c, cudaMemsetAsync(c->rep_bits.p, 0, cw * 8, st));
+    CUDA_TRY(c, cudaMemsetAsync(scal + SC_DDCTR, 0, 8 * 8, st));
+    launch_scan_popc(c->bitmap.as<u64>(), bm_words, c->bmrank.as<u32>(), c->status_slice(div_up(bm_words, scan_tile())), c->ticket(),
+                     scal + SC_BMTOTAL, st);
+    LAUNCHED(c); CHECK_LAUNCH(c);
+    DedupArgs da{};
+    da.packed = c->packed.as<u64>(); da.n_cand = n_cand;
+    da.cand_off = c->cand_off.as<u32>(); da.comp_pos = c->comp_pos.as<u32>(); da.comp_gs = c->comp_gs.as<u8>();
+    da.bitmap = c->bitmap.as<u64>(); da.bmrank = c->bmrank.as<u32>(); da.ghash = c->ghash.as<u64>();
+    da.cand_at = c->cand_at.as<u32>(); da.slot_gp = c->slot_gp.as<u64>(); da.slot_hash = c->slot_hash.as<u64>();
+    da.link_bits = c->link_bits.as<u8>(); da.chain_min = c->chain_min.as<u32>();
+    da.rep_bits = c->rep_bits.as<u64>(); da.rep_rank = c->rep_rank.as<u32>();
+    da.cstate = c->cstate.as<u8>(); da.live_bits = c->live_bits.as<u64>(); da.cov_bits = c->covered.as<u64>();
+    da.s_hash = c->s_hash.as<u64>(); da.s_cand = c->s_cand.as<u32>();
+    da.rng_lo = c->rng_lo.as<u32>(); da.rng_hi = c->rng_hi.as<u32>(); da.minrank = c->minrank.as<u32>();
+    da.ext_l = c->ext_l.as<u32>(); da.ext_r = c->ext_r.as<u32>();
+    da.wl0 = c->wl_a.as<u32>(); da.wl1 = c->wl_b.as<u32>(); da.wl2 = c->wl_c.as<u32>();
+    da.wl_long = c->wl_long.as<u32>();
+    da.wd0 = c->wd_a.as<u32>(); da.wd1 = c->wd_b.as<u32>(); da.wd2 = c->wd_c.as<u32>();
+    da.ctr = reinterpret_cast<u32*>(scal + SC_DDCTR);
+    // ---- chains: slots, links, reps
+    launch_slot_scatter(da, c->gt, st); LAUNCHED(c);
+    {
+        u32 tiles = div_up(n_cand, chain_tile());
+        u64* sf = c->status_slice(tiles);
+        u64* sb = c->status_slice(tiles);
+        launch_chains(da, sf, c->ticket(), sb, c->ticket(), st);
+        LAUNCHED(c); LAUNCHED(c); CHECK_LAUNCH(c);
+    }
+    launch_scan_popc(c->rep_bits.as<u64>(), cw, c->rep_rank.as<u32>(), c->status_slice(div_up(cw, scan_tile())), c->ticket(), scal + SC_UNDECIDED, st);
+    LAUNCHED(c); CHECK_LAUNCH(c);
+    TRY(mbi_read_scalars(c));
+    const u32 n_rep = (u32)reinterpret_cast<const u64*>(c->h_scal)[SC_UNDECIDED];
+    c->stats.n_extended = n_rep;
+    da.n_rep = n_rep;
+    // ---- reps in (group colour, slot) order
+    u64 *skA = c->sort_kA.as<u64>(), *skB = c->sort_kB.as<u64>();
+    launch_rep_keys(da, skA, st); LAUNCHED(c);
+    TRY(mbi_sort_records(c, &skA, &skB, nullptr, nullptr, n_rep, 32, 16, false));
+    da.s_key = skA;
+    cudaEventRecord(c->ev_x[0], st);
+    // ---- extend every rep, then resolve
+    launch_extend(da, c->gt, c->sd, st);
+    if (n_rep) { LAUNCHED(c); LAUNCHED(c); }
+    CHECK_LAUNCH(c);
+    cudaEventRecord(c->ev_x[3], st);
+    const bool want_trace = getenv("MB_DEDUP_TRACE") != nullptr;
+    if (want_trace) {
+        TRY(c->reserve(c->trace, 8200 * 8));
+        CUDA_TRY(c, cudaMemsetAsync(c->trace.p, 0, 8200 * 8, st));
+        da.trace = c->trace.as<u64>();
+    }
+    {
+        cudaError_t e = launch_resolve(da, st);
+        if (n_rep) LAUNCHED(c);
+        if (e != cudaSuccess) { c->set_cuda_error(e, "launch_resolve", __LINE__); return MB_E_CUDA; }
+    }
+    CHECK_LAUNCH(c);
+    if (want_trace) {
+        std::vector<u64> tr(8200);
+        CUDA_TRY(c, cudaStreamSynchronize(st));
+        CUDA_TRY(c, cudaMemcpy(tr.data(), c->trace.p, 8200 * 8, cudaMemcpyDeviceToHost));
+        static const char* names[] = {"", "enter", "", "extend", "long", "claim", "decide"};
+        u64 prev = 0;
+        for (u64 k = 0; k < tr[0] && k < 4000; ++k) {
+            u64 tag = tr[2 + 2 * k], t = tr[3 + 2 * k];
+            if (k) fprintf(stderr, "[dedup-trace] %-12s %8.1f us\n", names[tag], (double)(t - prev) / 1e3);
+            prev = t;
+        }
+        float t_chain = 0, t_ext = 0;
+        cudaEventElapsedTime(&t_chain, c->ev[EV_BUCKET], c->ev_x[0]);
+        cudaEventElapsedTime(&t_ext, c->ev_x[0], c->ev_x[3]);
+        fprintf(stderr, "[dedup-trace] emit+chains+sort %.1f us, extend %.1f us\n", t_chain * 1e3, t_ext * 1e3);
+    }
+    return MB_OK;
+}
+
+// a12: compact the accepted candidates, canonical order (D18), CSR.  Sets r_matches / r_comps.
+int mbi_output_unique(mb_ctx* c, u32 n_cand, u64 maxlen) {
+    cudaStream_t st = c->stream;
+    u64* scal = c->scalars.as<u64>();
+    const u32* hs32 = reinterpret_cast<const u32*>(c->h_scal);
+    const u64* hs64 = reinterpret_cast<const u64*>(c->h_scal);
+    const u32 L = c->sd.L;
+    TRY(c->reserve(c->flags, (size_t)(n_cand + 8) * 4));
+    TRY(c->reserve(c->match_idx, (size_t)(n_cand + 8) * 4));
+    OutputArgs oa{};
+    oa.n_cand = n_cand; oa.cstate = c->cstate.as<u8>(); oa.cand_off = c->cand_off.as<u32>(); oa.comp_pos = c->comp_pos.as<u32>();
+    oa.comp_gs = c->comp_gs.as<u8>();
+    oa.ext_l = c->ext_l.as<u32>(); oa.ext_r = c->ext_r.as<u32>(); oa.flags = c->flags.as<u32>(); oa.match_idx = c->match_idx.as<u32>();
+    oa.n_matches_ptr = scal + SC_NMATCH;
+    launch_uniq_flags(oa, st); LAUNCHED(c);
+    launch_scan_u32(oa.flags, n_cand, c->match_idx.as<u32>(), nullptr, c->status_slice(div_up(n_cand, scan_tile())), c->ticket(),
+                    scal + SC_NMATCH, st);
+    LAUNCHED(c); CHECK_LAUNCH(c);
+    TRY(mbi_read_scalars(c));
+    const u32 n_matches = (u32)hs64[SC_NMATCH];
+    u64 n_ocomp = 0;
+    c->stats.dedup_batches = 1; c->stats.dedup_iters = hs32[2 * SC_DDCTR + 9];
+    if (getenv("MB_DEDUP_TRACE"))
+        fprintf(stderr, "[dedup] reps %u rounds %u wide %u long %u visited %u claims %u covers %u\n", (u32)c->stats.n_extended, hs32[2 * SC_DDCTR + 9],
+                hs32[2 * SC_DDCTR + 10], hs32[2 * SC_DDCTR + 6], hs32[2 * SC_DDCTR + 12], hs32[2 * SC_DDCTR + 13], hs32[2 * SC_DDCTR + 14]);
+    TRY(c->reserve(c->sort_kA, (size_t)(n_matches + 8) * 8)); TRY(c->reserve(c->sort_kB, (size_t)(n_matches + 8) * 8));
+    TRY(c->reserve(c->sort_vA, (size_t)(n_matches + 8) * 8)); TRY(c->reserve(c->sort_vB, (size_t)(n_matches + 8) * 8));
+    TRY(c->reserve(c->ncomp, (size_t)(n_matches + 8) * 4));
+    TRY(c->reserve(c->out_len, (size_t)(n_matches + 8) * 4));
+    TRY(c->reserve(c->out_off, (size_t)(n_matches + 8) * 8));
+    if (n_matches) {
+        u64 *skA = c->sort_kA.as<u64>(), *skB = c->sort_kB.as<u64>(), *svA = c->sort_vA.as<u64>(), *svB = c->sort_vB.as<u64>();
+        oa.sort_key = skA; oa.sort_val = svA; oa.ncomp = c->ncomp.as<u32>();
+        int sbits = mbi_bits_for(maxlen);
+        launch_uniq_keys(oa, sbits, st); LAUNCHED(c); CHECK_LAUNCH(c);
+        TRY(mbi_sort_records(c, &skA, &skB, &svA, &svB, n_matches, 0, sbits + 6, false));
+        launch_uniq_tiefix(oa, skA, svA, L, n_matches, st); LAUNCHED(c);
+        launch_uniq_ncomp(oa, svA, n_matches, st); LAUNCHED(c);
+        launch_scan_u32(oa.ncomp, n_matches, nullptr, c->out_off.as<u64>(), c->status_slice(div_up(n_matches, scan_tile())), c->ticket(),
+                        scal + SC_NCOMP, st);
+        LAUNCHED(c); CHECK_LAUNCH(c);
+        TRY(mbi_read_scalars(c));
+        n_ocomp = hs64[SC_NCOMP];
+        TRY(c->reserve(c->out_seq, (size_t)(n_ocomp + 8) * 4));
+        TRY(c->reserve(c->out_start, (size_t)(n_ocomp + 8) * 8));
+        oa.out_off = c->out_off.as<u64>(); oa.out_len = c->out_len.as<u32>(); oa.out_seq = c->out_seq.as<u32>();
+        oa.out_start = c->out_start.as<i64>();
+        launch_uniq_gather(oa, svA, L, n_matches, st); LAUNCHED(c); CHECK_LAUNCH(c);
+    }
+    c->r_matches = n_matches; c->r_comps = n_ocomp;
+    return MB_OK;
+}
+
+extern "C" {
 
 int mb_fetch_result(mb_ctx* c, const mb_result** out) {
     if (!c || !out) return MB_E_ARG;

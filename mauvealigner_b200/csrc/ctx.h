@@ -38,9 +38,9 @@ struct mb_ctx {
 
     // workspace
     DBuf keysA, keysB, valsA, valsB, hist, digit_base, lookback, tickets, status, scalars, per_seq, tile_first;
-    DBuf cand_run, cand_off, cand_aux, comp_pos, comp_gs, bitmap, bmrank, slot_of, cand_at, cstate, covered, minrank, ext_l, ext_r;
+    DBuf cand_run, cand_off, cand_aux, comp_pos, comp_gs, bitmap, bmrank, cand_at, cstate, covered, minrank, ext_l, ext_r;
     DBuf trace;
-    DBuf wl_a, wl_b, wl_c, wl_long, wd_a, wd_b, wd_c, batch_bits, ghash, gid, slot_gid, slot_x, gid_table, rng_lo, rng_hi;
+    DBuf wl_a, wl_b, wl_c, wl_long, wd_a, wd_b, wd_c, live_bits, ghash, slot_gp, slot_hash, link_bits, chain_min, rep_bits, rep_rank, s_hash, s_cand, rng_lo, rng_hi;
     DBuf flags, match_idx, sort_kA, sort_kB, sort_vA, sort_vB, ncomp, mers_tmp;
     DBuf out_len, out_off, out_seq, out_start;
     u32 ticket_next = 0;
@@ -109,5 +109,5 @@ int mbi_read_scalars(mb_ctx* c);
 int mbi_bits_for(u64 maxval);
 // stages of the MODE_UNIQUE tail, shared by the single-GPU and the distributed drivers
 int mbi_reserve_candidates(mb_ctx* c, u32 n_cand, u32 n_ccomp, u64 bases);
-int mbi_dedup(mb_ctx* c, u32 n_cand, int owner_rank, int owner_world);
+int mbi_dedup(mb_ctx* c, u32 n_cand, u64 bases);
 int mbi_output_unique(mb_ctx* c, u32 n_cand, u64 maxlen);

@@ -70,30 +70,37 @@ struct DedupArgs {
     const u64* packed;
     u32 n_cand;
     const u32* cand_off; const u32* comp_pos; const u8* comp_gs;
-    const u64* bitmap; const u32* bmrank;
-    const u64* ghash; u32* gid_table; u32 gid_table_mask;
-    u32* gid;        // candidate -> exact group id (= a representative candidate of the same D16 group)
-    u32* slot_gid;   // slot -> group id
-    u32* slot_x;     // slot -> position of the candidate in its first genome
-    u32* slot_of;    // candidate -> slot
-    u32* cand_at;    // slot -> candidate
-    u8* cstate;      // 0 undecided, 1 accepted, 2 dropped, 0xFF not reached
-    u64* cov_bits;   // one bit per slot: contained in an accepted match
-    u32* rng_lo; u32* rng_hi; // candidate -> slot range of its group inside its extent
-    u32* minrank;    // per slot
-    u32* ext_l; u32* ext_r;
-    u32* n_extended;
-    // device-resident work lists of one batch (three rotating lists of undecided candidates, long extensions,
-    // wide extents) and their counters (layout: see k_dedup_all)
+    const u64* bitmap; const u32* bmrank;   // candidates by (first genome, position): bitmap over global bases + word ranks
+    const u64* ghash;   // candidate -> hash of its D16 group (genome set, strands, diagonal)
+    // per slot (candidates in (first genome, position) order)
+    u32* cand_at;       // slot -> candidate
+    u64* slot_gp;       // slot -> global base index of the candidate's first component
+    u64* slot_hash;     // slot -> group hash
+    u8* link_bits;      // one bit per slot: continues the chain of the previous slot
+    u32* chain_min;     // slot -> lowest rank among the earlier members of its chain
+    u64* rep_bits;      // one bit per slot: lowest rank of its chain
+    const u32* rep_rank; // per 64-slot word: reps before it
+    u8* cstate;         // candidate: 0 undecided rep, 1 accepted, 2 dropped
+    // per rep, in (group colour, slot) order
+    u32 n_rep;
+    const u64* s_key;   // colour << 32 | slot
+    u64* s_hash; u32* s_cand;
+    u64* live_bits;     // undecided
+    u64* cov_bits;      // contained in an accepted match
+    u32* rng_lo; u32* rng_hi; // index range of the same-colour reps inside the extent
+    u32* minrank;       // lowest undecided claimer of this round
+    u32* ext_l; u32* ext_r;   // per candidate
+    // device-resident work lists (three rotating lists of undecided reps, long extensions, wide extents)
+    // and their counters (layout: see k_resolve)
     u32* wl0; u32* wl1; u32* wl2; u32* wd0; u32* wd1; u32* wd2; u32* wl_long; u32* ctr;
-    u64* batch_bits; // one bit per slot: live candidate of the current batch
-    u64* trace;      // optional phase trace (debug): [0] count, then (tag, ns) pairs
+    u64* trace;         // optional phase trace (debug): [0] count, then (tag, ns) pairs
 };
-void launch_group_ids(const DedupArgs& a, cudaStream_t st);
-void launch_slot_keys(const DedupArgs& a, const GenomeTable& gt, u64* skey, u64* sval, cudaStream_t st);
-void launch_slot_finish(const DedupArgs& a, const u64* skey, const u64* sval, cudaStream_t st);
-// the whole batch loop (extend / claim / decide rounds) as one cooperative launch
-cudaError_t launch_dedup_all(const DedupArgs& a, const GenomeTable& gt, const SeedDev& sd, u32 batch0, cudaStream_t st);
+void launch_slot_scatter(const DedupArgs& a, const GenomeTable& gt, cudaStream_t st);
+u32 chain_tile();
+void launch_chains(const DedupArgs& a, u64* status_fwd, u32* ticket_fwd, u64* status_bwd, u32* ticket_bwd, cudaStream_t st);
+void launch_rep_keys(const DedupArgs& a, u64* skey, cudaStream_t st);
+void launch_extend(const DedupArgs& a, const GenomeTable& gt, const SeedDev& sd, cudaStream_t st); // 2 launches
+cudaError_t launch_resolve(const DedupArgs& a, cudaStream_t st); // cooperative
 
 // ---- kernels_output.cu
 struct OutputArgs {

@@ -3,22 +3,29 @@
 // (libMems); semantics = SURVEY.md Appendix A D13-D16 and the A.2 pseudo-code.  Reached in the
 // reference from /root/reference/src/UniqueMatchFinder.cpp:58 (HashMatch(unique_list)).
 //
-// The reference decides candidates one at a time in ascending seed order: a candidate is dropped
-// iff an already ACCEPTED extended match on its diagonal contains it, otherwise it is extended and
-// accepted.  Here candidates (already in ascending seed order = rank) are taken in doubling batches:
-//   begin    every not-yet-covered candidate of the batch is extended (pure function of the genomes)
-//   claim    every undecided candidate writes atomicMin(rank) on the slots of all same-group
-//            candidates its extent contains
-//   decide   covered -> dropped;  min claimer == self -> accepted, marks its slots covered;
-//            min claimer dropped -> reset slot and retry
-// until the batch has no undecided candidate.  The fix-point equals the sequential result because a
-// candidate is accepted exactly when every lower-rank container of it has been dropped.
-// Slots: candidates ordered by (first genome, position) via a bitmap + popcount ranks, so "all
-// candidates inside an extent" is a contiguous slot range found in O(1).
-// Groups: candidates with the same genome set, strands and diagonal (D16) get the same exact group id
-// through a hash table whose hits are verified component by component, so the walks compare integers.
+// The reference decides candidates one at a time in ascending seed order (= candidate index here,
+// the "rank"): a candidate is dropped iff an already ACCEPTED extended match of its group (same
+// genome set, strands and diagonal, D16) contains it, otherwise it is extended and accepted.
+// That order-dependent rule is evaluated here in three data-parallel steps:
+//
+//  1 chains   Slots = candidates ordered by (first genome, position) through a bitmap + popcount
+//             ranks.  Candidates of one group at consecutive positions x, x+1, ... form a chain.
+//             Every extent of a same-group match is bounded by a failing window (or a sequence end),
+//             so a match that contains one member of a chain contains all of it; therefore only
+//             the lowest-rank member of a chain (its "rep") can ever be accepted and all other
+//             members are dropped without being extended.  Two segmented min-scans (forward,
+//             backward; single pass, decoupled look-back) find the reps.
+//  2 extend   every rep is extended once (pure function of the packed genomes): one thread on
+//             64-base mismatch maps; long extensions by one warp, 32 chunks per step.
+//  3 resolve  fix-point over the reps, equal to the sequential result: in rounds, every undecided
+//             rep claims (atomicMin of its rank) the undecided higher-rank reps of its group inside
+//             its extent; an unclaimed rep is accepted and marks those reps covered; a covered rep
+//             is dropped.  The lowest undecided rank is never claimed, so every round decides.
 #include "common.cuh"
 #include "kernels.h"
+#include "lookback.cuh"
+
+#define INF32 0xFFFFFFFFu
 
 __device__ __forceinline__ u32 slot_rank(const u64* __restrict__ bitmap, const u32* __restrict__ bmrank, u64 gp) {
     u64 w = bitmap[gp >> 6];
@@ -41,44 +48,167 @@ __device__ __forceinline__ bool same_group(const DedupArgs& a, u32 j, u32 e) {
     return true;
 }
 
-// exact group ids: open-addressing table keyed by the group hash; a hit counts only after the full
-// component-wise comparison with the representative, so hash collisions just probe on.
-__global__ void __launch_bounds__(256) k_group_ids(DedupArgs a) {
-    u32 c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= a.n_cand) return;
-    u64 h = a.ghash[c];
-    u32 slot = (u32)(h ^ (h >> 32)) & a.gid_table_mask;
-    while (true) {
-        u32 old = atomicCAS(&a.gid_table[slot], 0u, c + 1);
-        if (old == 0) { a.gid[c] = c; return; }
-        u32 r = old - 1;
-        if (a.ghash[r] == h && same_group(a, r, c)) { a.gid[c] = r; return; }
-        slot = (slot + 1) & a.gid_table_mask;
-    }
-}
-
-// Slot order = (group id, position in the first genome): the candidates of one group lie next to each
-// other, ordered along their diagonal, so "everything of my group inside my extent" is a short contiguous
-// run of slots around my own.  Step 1 lists (group id, candidate) in (first genome, position) order
-// through the bitmap ranks; a stable radix sort by group id (driver) then yields the final order.
-__global__ void __launch_bounds__(256) k_slot_keys(DedupArgs a, GenomeTable gt, u64* __restrict__ skey, u64* __restrict__ sval) {
+// ---- slots ---------------------------------------------------------------------------------------
+// candidate -> slot (rank of its first-genome position among all candidates), and the slot-ordered
+// copies (candidate id, global position, group hash) the chain and resolve steps stream over.
+__global__ void __launch_bounds__(256) k_slot_scatter(DedupArgs a, GenomeTable gt) {
     u32 c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= a.n_cand) return;
     u32 off = a.cand_off[c];
     u32 g = a.comp_gs[off] & 0x7F;
     u64 gp = gt.base_base[g] + a.comp_pos[off];
     u32 s = slot_rank(a.bitmap, a.bmrank, gp);
-    skey[s] = a.gid[c];
-    sval[s] = c;
+    a.cand_at[s] = c;
+    a.slot_gp[s] = gp;
+    a.slot_hash[s] = a.ghash[c];
 }
-__global__ void __launch_bounds__(256) k_slot_finish(DedupArgs a, const u64* __restrict__ skey, const u64* __restrict__ sval) {
+
+// ---- chains: segmented min-scans over the slots ---------------------------------------------------
+// Element = (head flag, rank).  Exclusive segmented prefix minimum; REV = false scans towards higher
+// slots (segment heads = chain heads) and records the links, REV = true scans towards lower slots
+// (segment heads = chain tails), combines both directions and emits the reps.
+#define CH_NT 256
+#define CH_IPT 8
+#define CH_TILE (CH_NT * CH_IPT)
+
+// Tile carry by decoupled look-back.  Status word: 2 flag bits | head-seen bit (32) | open minimum (32).
+// A predecessor that has seen a head (or holds an inclusive value) ends the walk.
+__device__ __forceinline__ u32 segmin_lookback(u64* status, u32 tile, u32 F, u32 M) {
+    const int lane = threadIdx.x & 31;
+    if (lane == 0) lb_st(status + tile, (tile == 0 ? LB_FLAG_INC : LB_FLAG_AGG) | ((u64)F << 32) | M);
+    if (tile == 0) return INF32;
+    u32 carry = INF32;
+    i64 base = (i64)tile - 1;
+    while (true) {
+        i64 t = base - lane;
+        u64 s = LB_FLAG_INC | INF32;
+        if (t >= 0) {
+            do { s = lb_ld(status + t); } while ((s >> 62) == 0);
+        }
+        bool stop = (s & LB_FLAG_INC) != 0 || ((s >> 32) & 1);
+        u32 stops = __ballot_sync(0xFFFFFFFFu, stop);
+        int first = __ffs(stops) - 1;
+        u32 v = (first < 0 || lane <= first) ? (u32)s : INF32;
+        carry = min(carry, __reduce_min_sync(0xFFFFFFFFu, v));
+        if (first >= 0) break;
+        base -= 32;
+    }
+    if (lane == 0) lb_st(status + tile, LB_FLAG_INC | ((u64)F << 32) | (F ? M : min(carry, M)));
+    return carry;
+}
+
+template <bool REV>
+__global__ void __launch_bounds__(CH_NT) k_chain(DedupArgs a, u64* status, u32* ticket) {
+    __shared__ u32 sF[CH_NT / 32], sM[CH_NT / 32];
+    __shared__ u32 sTile, sCarry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 n = a.n_cand;
+    const u32 ntiles = (n + CH_TILE - 1) / CH_TILE;
+    if (tid == 0) sTile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const u32 ord = sTile;                                // position of this tile in scan order
+    const u32 tile = REV ? ntiles - 1 - ord : ord;
+    // the thread's 8 consecutive slots; scan order inside the thread: ascending (FWD) / descending (REV)
+    const u32 sbase = tile * CH_TILE + (REV ? (CH_NT - 1 - tid) : tid) * CH_IPT;
+    u32 v[CH_IPT];
+    bool f[CH_IPT];
+    u64 gp[CH_IPT + 1], hs[CH_IPT + 1];
+    if (!REV) {
+        // link of slot s: same group as slot s-1 and exactly one base further
+        const u32 s0 = sbase;
+#pragma unroll
+        for (int k = 0; k <= CH_IPT; ++k) {
+            i64 s = (i64)s0 - 1 + k;
+            bool ok = s >= 0 && s < (i64)n;
+            gp[k] = ok ? a.slot_gp[s] : ~0ull - 1;
+            hs[k] = ok ? a.slot_hash[s] : 0;
+        }
+        u32 linkbits = 0;
+#pragma unroll
+        for (int k = 0; k < CH_IPT; ++k) {
+            u32 s = s0 + k;
+            bool valid = s < n;
+            v[k] = valid ? a.cand_at[s] : INF32;
+            bool link = valid && s > 0 && gp[k] + 1 == gp[k + 1] && hs[k] == hs[k + 1];
+#ifdef MB_VERIFY_LINKS
+            if (link) link = same_group(a, a.cand_at[s - 1], v[k]);
+#endif
+            f[k] = !link;
+            linkbits |= (link ? 1u : 0u) << k;
+        }
+        if (s0 < n) a.link_bits[s0 / CH_IPT] = (u8)linkbits; // bit k: slot s0+k continues the chain of s0+k-1
+    } else {
+        // scan order k = 0..7 <-> slot sbase+7-k; head (in this direction) = the chain's last slot
+        u32 lb = sbase < n ? a.link_bits[sbase / CH_IPT] : 0u;
+        u32 lb_next = (sbase + CH_IPT < n) ? a.link_bits[sbase / CH_IPT + 1] : 0u;
+        lb |= (lb_next & 1u) << CH_IPT;
+#pragma unroll
+        for (int k = 0; k < CH_IPT; ++k) {
+            u32 s = sbase + (CH_IPT - 1 - k);
+            bool valid = s < n;
+            v[k] = valid ? a.cand_at[s] : INF32;
+            bool link_next = valid && s + 1 < n && ((lb >> (CH_IPT - k)) & 1u); // slot s+1 continues s
+            f[k] = !link_next;
+        }
+    }
+    // thread aggregate: (any head, minimum after the last head)
+    u32 F = 0, M = INF32;
+#pragma unroll
+    for (int k = 0; k < CH_IPT; ++k) {
+        if (f[k]) { F = 1; M = v[k]; } else M = min(M, v[k]);
+    }
+    // inclusive scan of the aggregates over the block, then exclusive per thread
+    u32 iF = F, iM = M;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        u32 yF = __shfl_up_sync(0xFFFFFFFFu, iF, o), yM = __shfl_up_sync(0xFFFFFFFFu, iM, o);
+        if (lane >= o) { iM = iF ? iM : min(yM, iM); iF |= yF; }
+    }
+    if (lane == 31) { sF[warp] = iF; sM[warp] = iM; }
+    __syncthreads();
+    // exclusive prefix of this thread inside the tile
+    u32 eF = __shfl_up_sync(0xFFFFFFFFu, iF, 1), eM = __shfl_up_sync(0xFFFFFFFFu, iM, 1);
+    if (lane == 0) { eF = 0; eM = INF32; }
+    u32 wF = 0, wM = INF32; // all earlier warps
+    for (int w = 0; w < warp; ++w) { u32 f2 = sF[w], m2 = sM[w]; wM = f2 ? m2 : min(wM, m2); wF |= f2; }
+    u32 pM = eF ? eM : min(wM, eM), pF = wF | eF;
+    if (warp == 0) {
+        u32 tF = 0, tM = INF32;
+        for (int w = 0; w < CH_NT / 32; ++w) { u32 f2 = sF[w], m2 = sM[w]; tM = f2 ? m2 : min(tM, m2); tF |= f2; }
+        u32 carry = segmin_lookback(status, ord, tF, tM);
+        if (lane == 0) sCarry = carry;
+    }
+    __syncthreads();
+    u32 run = pF ? pM : min(sCarry, pM); // open minimum entering this thread's first element
+    u32 repbits = 0;
+#pragma unroll
+    for (int k = 0; k < CH_IPT; ++k) {
+        u32 excl = f[k] ? INF32 : run;
+        u32 s = REV ? sbase + (CH_IPT - 1 - k) : sbase + k;
+        if (s < n) {
+            if (!REV) a.chain_min[s] = excl;
+            else {
+                u32 c = v[k];
+                bool rep = c < excl && c < a.chain_min[s];
+                a.cstate[c] = rep ? 0 : 2;
+                if (rep) repbits |= 1u << (CH_IPT - 1 - k);
+            }
+        }
+        run = f[k] ? v[k] : min(run, v[k]);
+    }
+    if (REV && sbase < n) reinterpret_cast<u8*>(a.rep_bits)[sbase / CH_IPT] = (u8)repbits;
+}
+
+// Reps in slot order (bitmap ranks) -> sort key (group colour = top 16 bits of the group hash, slot).
+// Two stable radix passes on the colour (driver) then put the reps of one group next to each other,
+// ordered along their diagonal, so "the reps of my group inside my extent" is a short index range.
+__global__ void __launch_bounds__(256) k_rep_keys(DedupArgs a, u64* __restrict__ skey) {
     u32 s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= a.n_cand) return;
-    u32 c = (u32)sval[s];
-    a.slot_of[c] = s;
-    a.cand_at[s] = c;
-    a.slot_gid[s] = (u32)skey[s];
-    a.slot_x[s] = a.comp_pos[a.cand_off[c]];
+    u64 w = a.rep_bits[s >> 6];
+    if (!((w >> (s & 63)) & 1)) return;
+    u32 idx = a.rep_rank[s >> 6] + (u32)__popcll(w & ((1ull << (s & 63)) - 1));
+    skey[idx] = ((a.slot_hash[s] >> 48) << 32) | s;
 }
 
 // ---- extension -----------------------------------------------------------------------------------
@@ -97,8 +227,8 @@ __device__ __forceinline__ void oriented_window(const u64* __restrict__ packed, 
     }
 }
 
-// Warp version: number of consecutive steps t = 1..maxcount whose windows agree across all components.
-// dir = -1: grow left in match coordinates, +1: grow right.  Offset of step t: o0 + t*stride.
+// Warp version for L > 32: number of consecutive steps t = 1..maxcount whose windows agree across all
+// components.  dir = -1: grow left in match coordinates, +1: grow right.  Offset of step t: o0 + t*stride.
 __device__ u32 scan_steps(const u64* __restrict__ packed, const GenomeTable& gt, const SeedDev& sd, const u32* __restrict__ cpos,
                           const u8* __restrict__ cgs, u32 m, int dir, u32 o0, u32 stride, u32 maxcount) {
     const int lane = threadIdx.x & 31;
@@ -138,18 +268,15 @@ __device__ __forceinline__ void candidate_room(const GenomeTable& gt, u32 L, con
     room_r = min(room_r, rev ? lroom : rroom);
 }
 
-// D14: four phases.  One warp per candidate (long matches, many genomes, L > 32).
+// D14: four phases.  One warp per candidate, window by window (L > 32).
 __device__ void extend_candidate_warp(const u64* __restrict__ packed, const GenomeTable& gt, const SeedDev& sd, const u32* cpos,
                                       const u8* cgs, u32 m, u32& ext_l, u32& ext_r) {
     const int lane = threadIdx.x & 31;
     const u32 L = sd.L;
-    u32 room_l = 0xFFFFFFFFu, room_r = 0xFFFFFFFFu;
+    u32 room_l = INF32, room_r = INF32;
     for (u32 k = lane; k < m; k += 32) candidate_room(gt, L, cpos, cgs, k, room_l, room_r);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        room_l = min(room_l, __shfl_xor_sync(0xFFFFFFFFu, room_l, o));
-        room_r = min(room_r, __shfl_xor_sync(0xFFFFFFFFu, room_r, o));
-    }
+    room_l = __reduce_min_sync(0xFFFFFFFFu, room_l);
+    room_r = __reduce_min_sync(0xFFFFFFFFu, room_r);
     u32 a = scan_steps(packed, gt, sd, cpos, cgs, m, -1, 0, L, room_l / L);
     u32 b = scan_steps(packed, gt, sd, cpos, cgs, m, +1, 0, L, room_r / L);
     u32 c = scan_steps(packed, gt, sd, cpos, cgs, m, -1, a * L, 1, min(L, room_l - a * L));
@@ -158,16 +285,20 @@ __device__ void extend_candidate_warp(const u64* __restrict__ packed, const Geno
     ext_r = b * L + d;
 }
 
-// ---- one-thread extension on mismatch maps (L <= 32) ----------------------------------------------
-// 32 bases of one component at match offsets [i0, i0+32) (relative to the seed start; the match strand
-// is component 0's), first base in the top bits.  Reads may run up to 128 bases outside the genome:
-// the packed buffer is padded on both sides of every genome and such bases never reach a tested window.
-__device__ __forceinline__ u64 oriented_bases32(const u64* __restrict__ packed, const GenomeTable& gt, u32 L, u32 g, u32 pos, bool rev, int i0) {
-    i64 q = (i64)gt.word_base[g] * 32 + (i64)pos + (rev ? (i64)L - 32 - i0 : (i64)i0);
-    u64 i = (u64)q >> 5;
+// ---- extension on mismatch maps (L <= 32) ----------------------------------------------------------
+// 64 bases of one component at match offsets [i0, i0+64) (relative to the seed start; the match strand
+// is component 0's), first base in the top bits of `a`.  Reads may run up to 128 bases outside the
+// genome: the packed buffer is padded on both sides of every genome and such bases never reach a
+// tested window.
+__device__ __forceinline__ void oriented_bases64(const u64* __restrict__ packed, const GenomeTable& gt, u32 L, u32 g, u32 pos, bool rev, i64 i0,
+                                                 u64& a, u64& b) {
+    i64 q = (i64)gt.word_base[g] * 32 + (i64)pos + (rev ? (i64)L - 64 - i0 : i0);
+    const u64* w = packed + ((u64)q >> 5);
     int sh = (int)(q & 31) * 2;
-    u64 w = shl128_hi(packed[i], packed[i + 1], sh);
-    return rev ? rc_word(w) : w;
+    u64 w0 = w[0], w1 = w[1], w2 = w[2];
+    u64 fa = shl128_hi(w0, w1, sh), fb = shl128_hi(w1, w2, sh);
+    if (rev) { a = rc_word(fb); b = rc_word(fa); }
+    else { a = fa; b = fb; }
 }
 __device__ __forceinline__ u64 spread_nz(u64 x) { return (x | (x >> 1)) & 0x5555555555555555ull; }
 // top 64 bits of the 128-bit map xa:xb shifted left by `idx` bases (0 <= idx < 64)
@@ -176,77 +307,139 @@ __device__ __forceinline__ u64 map_at(u64 xa, u64 xb, u32 idx) { return idx < 32
 // Mismatch map (one flag per base, in the low bit of its 2-bit cell) of the 64 bases at match
 // offsets [o_lo, o_lo + 64): flag set iff some component differs from component 0 there.
 __device__ __forceinline__ void mismatch64(const u64* __restrict__ packed, const GenomeTable& gt, u32 L, const u32* __restrict__ cpos,
-                                           const u8* __restrict__ cgs, u32 m, int o_lo, u64& xa, u64& xb) {
-    u32 g0 = cgs[0] & 0x7F, p0 = cpos[0];
-    u64 a0 = oriented_bases32(packed, gt, L, g0, p0, false, o_lo), b0 = oriented_bases32(packed, gt, L, g0, p0, false, o_lo + 32);
+                                           const u8* __restrict__ cgs, u32 m, i64 o_lo, u64& xa, u64& xb) {
+    u64 a0, b0;
+    oriented_bases64(packed, gt, L, cgs[0] & 0x7F, cpos[0], false, o_lo, a0, b0);
     xa = 0; xb = 0;
     for (u32 k = 1; k < m; ++k) {
         u8 gs = cgs[k];
-        xa |= spread_nz(oriented_bases32(packed, gt, L, gs & 0x7F, cpos[k], gs & 0x80, o_lo) ^ a0);
-        xb |= spread_nz(oriented_bases32(packed, gt, L, gs & 0x7F, cpos[k], gs & 0x80, o_lo + 32) ^ b0);
+        u64 a, b;
+        oriented_bases64(packed, gt, L, gs & 0x7F, cpos[k], gs & 0x80, o_lo, a, b);
+        xa |= spread_nz(a ^ a0);
+        xb |= spread_nz(b ^ b0);
     }
 }
 
-#define DD_THREAD_CHUNKS 12 // 64-base chunks one thread walks per direction before deferring to the warp kernel
+#define DD_THREAD_CHUNKS 8 // 64-base chunks one thread walks per direction before deferring to the warp phase
+
+// chunk geometry of the directional walks.  Right (dir = +1): the chunk after b jumps starts at match
+// offset bL+1, holds jump window b+1 at chunk index L-1 (and b+2 at 2L-1 when 3L <= 65); on a failing
+// jump the single-step windows bL+s start at chunk index s-1 — all inside the same chunk.  Left is the
+// mirror image: offsets [-bL-65+L, -bL+L-1), chunk index i <-> offset -bL-65+L+i.
+__device__ __forceinline__ i64 chunk_lo(int dir, u32 b, u32 L) { return dir > 0 ? (i64)b * L + 1 : -(i64)b * L - 65 + (i64)L; }
+// evaluate one chunk that starts after b0 successful jumps: advances b over the jumps it holds; returns
+// true when the walk ends inside this chunk (growth in `out`)
+__device__ __forceinline__ bool walk_chunk(u64 xa, u64 xb, u64 care, int dir, u32 L, u32 room, u32 maxjumps, u32 per_chunk, u32& b, u32& out) {
+    const u32 b0 = b;
+    bool failed = false;
+    for (u32 w = 0; w < per_chunk && b < maxjumps; ++w) {
+        // right: jump window b+1 covers offsets [(b+1)L, (b+2)L)   -> chunk index (b-b0)L + L-1
+        // left : jump window b+1 covers offsets [-(b+1)L, -bL)     -> chunk index 65 - 2L - (b-b0)L
+        u32 idx = dir > 0 ? (b - b0) * L + L - 1 : 65 - 2 * L - (b - b0) * L;
+        if (map_at(xa, xb, idx) & care) { failed = true; break; }
+        ++b;
+    }
+    if (!(failed || b >= maxjumps)) return false;
+    if (b - b0 == per_chunk && !failed) return false; // the chunk is used up: the single steps need a fresh one
+    // single steps: right window s starts at offset bL+s, left window s at offset -bL-s
+    u32 maxs = min(L, room - b * L), sdone = 0;
+    for (u32 s = 1; s <= maxs; ++s) {
+        u32 idx = dir > 0 ? (b - b0) * L + s - 1 : 65 - L - (b - b0) * L - s;
+        if (map_at(xa, xb, idx) & care) break;
+        sdone = s;
+    }
+    out = b * L + sdone;
+    return true;
+}
 
 // Growth to the right (dir = +1) or left (dir = -1) of the seed: L-jumps, then at most L single steps
-// (phases 1+3 resp. 0+2 of D14; the two directions do not interact).  Returns the growth in bases or
-// 0xFFFFFFFF when the chunk budget ran out.
-// Right: the chunk starts at match offset bL+1 (b = jumps so far), holds jump window b+1 at chunk
-// index L-1 (and b+2 at 2L-1 when 3L <= 65); on a failing jump the single-step windows bL+s start at
-// chunk index s-1 — all inside the same chunk.  Left is the mirror image.
+// (phases 1+3 resp. 0+2 of D14; the two directions do not interact).  One thread; returns the growth
+// in bases or INF32 when the chunk budget ran out.
 __device__ __forceinline__ u32 grow_thread(const u64* __restrict__ packed, const GenomeTable& gt, const SeedDev& sd, const u32* cpos,
                                            const u8* cgs, u32 m, int dir, u32 room) {
     const u32 L = sd.L;
     const u64 care = sd.mask_hi & 0x5555555555555555ull;
     const u32 maxjumps = room / L;
     const u32 per_chunk = (3 * L <= 65) ? 2 : 1;
-    u32 b = 0;
+    u32 b = 0, out = 0;
     for (int chunk = 0; chunk < DD_THREAD_CHUNKS; ++chunk) {
         u64 xa, xb;
-        // right: chunk = offsets [bL+1, bL+65);  left: offsets [-bL-64+L-1, -bL+L-1) (chunk index i <-> offset -bL-65+L+i)
-        int o_lo = dir > 0 ? (int)(b * L) + 1 : -(int)(b * L) - 65 + (int)L;
-        mismatch64(packed, gt, L, cpos, cgs, m, o_lo, xa, xb);
-        u32 b0 = b;
-        bool failed = false;
-        for (u32 w = 0; w < per_chunk && b < maxjumps; ++w) {
-            // right: jump window b+1 covers offsets [(b+1)L, (b+2)L)   -> chunk index (b-b0)L + L-1
-            // left : jump window b+1 covers offsets [-(b+1)L, -bL)     -> chunk index 65 - 2L - (b-b0)L
-            u32 idx = dir > 0 ? (b - b0) * L + L - 1 : 65 - 2 * L - (b - b0) * L;
-            if (map_at(xa, xb, idx) & care) { failed = true; break; }
-            ++b;
+        mismatch64(packed, gt, L, cpos, cgs, m, chunk_lo(dir, b, L), xa, xb);
+        if (walk_chunk(xa, xb, care, dir, L, room, maxjumps, per_chunk, b, out)) return out;
+    }
+    return INF32;
+}
+
+// Same walk by one warp: lane l examines the chunk that follows b_base + l*per_chunk jumps; the first
+// lane whose chunk ends the walk has the answer.  Unbounded.
+__device__ u32 grow_warp(const u64* __restrict__ packed, const GenomeTable& gt, const SeedDev& sd, const u32* cpos, const u8* cgs, u32 m,
+                         int dir, u32 room) {
+    const int lane = threadIdx.x & 31;
+    const u32 L = sd.L;
+    const u64 care = sd.mask_hi & 0x5555555555555555ull;
+    const u32 maxjumps = room / L;
+    const u32 per_chunk = (3 * L <= 65) ? 2 : 1;
+    for (u64 b_base = 0;; b_base += 32 * per_chunk) {
+        u64 b064 = b_base + (u64)lane * per_chunk;
+        bool active = b064 <= maxjumps;
+        u32 b = (u32)b064, out = 0;
+        bool ends = false;
+        if (active) {
+            u64 xa, xb;
+            mismatch64(packed, gt, L, cpos, cgs, m, chunk_lo(dir, b, L), xa, xb);
+            ends = walk_chunk(xa, xb, care, dir, L, room, maxjumps, per_chunk, b, out);
         }
-        if (failed || b >= maxjumps) {
-            if (b - b0 == per_chunk && !failed) continue; // the chunk is used up: the single steps need a fresh one
-            // single steps: right window s starts at offset bL+s, left window s at offset -bL-s
-            u32 maxs = min(L, room - b * L), sdone = 0;
+        u32 em = __ballot_sync(0xFFFFFFFFu, ends);
+        if (em) return __shfl_sync(0xFFFFFFFFu, out, __ffs(em) - 1);
+    }
+}
+
+// One thread, both directions.  For 3L <= 64 one chunk centred on the seed (match offsets [-L, 63-L),
+// chunk index i <-> offset i-L) holds the first jump window and all single-step windows of both
+// directions, which settles every candidate whose first jumps fail (the usual case).
+__device__ __forceinline__ bool extend_thread(const u64* __restrict__ packed, const GenomeTable& gt, const SeedDev& sd, const u32* cpos,
+                                              const u8* cgs, u32 m, u32 room_l, u32 room_r, u32& el, u32& er) {
+    const u32 L = sd.L;
+    bool lj = true, rj = true;
+    if (3 * L <= 64) {
+        const u64 care = sd.mask_hi & 0x5555555555555555ull;
+        u64 xa, xb;
+        mismatch64(packed, gt, L, cpos, cgs, m, -(i64)L, xa, xb);
+        lj = room_l >= L && !(map_at(xa, xb, 0) & care);
+        rj = room_r >= L && !(map_at(xa, xb, 2 * L) & care);
+        if (!lj) {
+            u32 maxs = min(L, room_l), sdone = 0;
             for (u32 s = 1; s <= maxs; ++s) {
-                u32 idx = dir > 0 ? (b - b0) * L + s - 1 : 65 - L - (b - b0) * L - s;
-                if (map_at(xa, xb, idx) & care) break;
+                if (map_at(xa, xb, L - s) & care) break;
                 sdone = s;
             }
-            return b * L + sdone;
+            el = sdone;
+        }
+        if (!rj) {
+            u32 maxs = min(L, room_r), sdone = 0;
+            for (u32 s = 1; s <= maxs; ++s) {
+                if (map_at(xa, xb, L + s) & care) break;
+                sdone = s;
+            }
+            er = sdone;
         }
     }
-    return 0xFFFFFFFFu;
+    if (lj) el = grow_thread(packed, gt, sd, cpos, cgs, m, -1, room_l);
+    if (el == INF32) return false;
+    if (rj) er = grow_thread(packed, gt, sd, cpos, cgs, m, +1, room_r);
+    return er != INF32;
 }
 
 // ------------------------------------------------------------------------------------------------
-// The whole batch loop runs inside ONE cooperative kernel (grid = all co-resident blocks): phases are
-// separated by grid-wide barriers, work lists and their counters live in device memory, and the
-// convergence test of a batch is made on the device, so the host enqueues one launch and never
-// synchronises inside the de-dup stage.
-//
-// Because slots are ordered by (group, position), the candidates an extent contains are ONE contiguous
-// slot range [rng_lo, rng_hi), found once per candidate by a galloping search around its own slot.
-// "claim" then only looks at the set bits of the batch bitmap inside the range (live candidates of this
-// batch), and "cover" ORs range masks into the covered bitmap.
+// Work lists and their counters live in device memory and the convergence test of the resolve rounds
+// is made on the device (one cooperative launch, grid-wide barriers between the phases), so the host
+// never synchronises inside the resolve step.  All per-rep state is indexed by the rep's position i in
+// the (colour, slot) order.
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
 
 #define DD_NT 256
-#define DD_THREAD_COMPS 8
-#define DD_WIDE_SLOTS 1024 // slot ranges longer than this are handled by one warp instead of one thread
+#define DD_WIDE 2048 // index ranges longer than this are handled by one warp instead of one thread
 
 // warp-aggregated append to a device work list (call with the whole warp converged)
 __device__ __forceinline__ void wl_push(u32* list, u32* count, bool pred, u32 value) {
@@ -260,37 +453,6 @@ __device__ __forceinline__ void wl_push(u32* list, u32* count, bool pred, u32 va
     list[base + __popc(m & ((1u << lane) - 1))] = value;
 }
 
-__device__ __forceinline__ u64 slot_key(const DedupArgs& a, u32 s) { return ((u64)a.slot_gid[s] << 33) | a.slot_x[s]; }
-// first slot in (lo, hi] ... standard lower bound on slot_key over [lo, hi)
-__device__ __forceinline__ u32 slot_lower_bound(const DedupArgs& a, u32 lo, u32 hi, u64 key) {
-    while (lo < hi) {
-        u32 mid = lo + (hi - lo) / 2;
-        if (slot_key(a, mid) < key) lo = mid + 1; else hi = mid;
-    }
-    return lo;
-}
-// slot range of c's group with seed starts in [x - ext_l, x + ext_r]; galloping outwards from c's slot
-__device__ __forceinline__ void extent_range(const DedupArgs& a, u32 c, u32 el, u32 er, u32& rlo, u32& rhi) {
-    const u32 s0 = a.slot_of[c];
-    const u32 x = a.comp_pos[a.cand_off[c]];
-    const u64 g = (u64)a.gid[c] << 33;
-    const u64 key_lo = g | (x - el), key_hi = g | ((u64)x + er + 1);
-    u32 step = 1, hi = s0; // invariant: key(hi) >= key_lo
-    while (true) {
-        if (step > hi) { rlo = slot_lower_bound(a, 0, hi, key_lo); break; }
-        u32 probe = hi - step;
-        if (slot_key(a, probe) < key_lo) { rlo = slot_lower_bound(a, probe + 1, hi, key_lo); break; }
-        hi = probe; step *= 2;
-    }
-    u32 lo = s0 + 1; // invariant: key(lo - 1) < key_hi
-    step = 1;
-    while (true) {
-        if (lo + step > a.n_cand) { rhi = slot_lower_bound(a, lo, a.n_cand, key_hi); break; }
-        u32 probe = lo + step - 1;
-        if (slot_key(a, probe) >= key_hi) { rhi = slot_lower_bound(a, lo, probe, key_hi); break; }
-        lo = probe + 1; step *= 2;
-    }
-}
 __device__ __forceinline__ u64 range_mask(u32 word, u32 lo, u32 hi) { // bits of `word` inside [lo, hi)
     u64 m = ~0ull;
     if (lo > word * 64) m &= ~0ull << (lo - word * 64);
@@ -299,50 +461,138 @@ __device__ __forceinline__ u64 range_mask(u32 word, u32 lo, u32 hi) { // bits of
 }
 __device__ __forceinline__ bool bit_of(const u64* bits, u32 s) { return (bits[s >> 6] >> (s & 63)) & 1; }
 
-// claim the undecided higher-rank candidates of this batch among the slots of one bitmap word
-__device__ __forceinline__ void claim_word(const DedupArgs& a, u32 w, u32 rlo, u32 rhi, u32 c) {
-    u64 bits = a.batch_bits[w] & range_mask(w, rlo, rhi);
+__device__ __forceinline__ u32 key_lower_bound(const u64* __restrict__ k, u32 lo, u32 hi, u64 key) {
+    while (lo < hi) {
+        u32 mid = lo + (hi - lo) / 2;
+        if (k[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+// Index range [ilo, ihi) of the reps of rep i's colour whose first-genome position lies in the extent
+// [x - el, x + er] of candidate c: slot range through the candidate bitmap, then a galloping search
+// outwards from i over the (colour, slot) keys.
+__device__ __forceinline__ void extent_range(const DedupArgs& a, const GenomeTable& gt, u32 i, u32 c, u32 el, u32 er, u32& ilo, u32& ihi) {
+    u32 off = a.cand_off[c];
+    u64 gp = gt.base_base[a.comp_gs[off] & 0x7F] + a.comp_pos[off];
+    u32 rlo = slot_rank(a.bitmap, a.bmrank, gp - el);
+    u32 rhi = slot_rank(a.bitmap, a.bmrank, gp + er + 1);
+    const u64* __restrict__ k = a.s_key;
+    const u64 col = k[i] & 0xFFFF00000000ull;
+    const u64 klo = col | rlo, khi = col | rhi;
+    u32 step = 1, hi = i; // invariant: k[hi] >= klo
+    while (true) {
+        if (step > hi) { ilo = key_lower_bound(k, 0, hi, klo); break; }
+        u32 probe = hi - step;
+        if (k[probe] < klo) { ilo = key_lower_bound(k, probe + 1, hi, klo); break; }
+        hi = probe; step *= 2;
+    }
+    u32 lo = i + 1; // invariant: k[lo - 1] < khi
+    step = 1;
+    while (true) {
+        if (lo + step > a.n_rep) { ihi = key_lower_bound(k, lo, a.n_rep, khi); break; }
+        u32 probe = lo + step - 1;
+        if (k[probe] >= khi) { ihi = key_lower_bound(k, lo, probe, khi); break; }
+        lo = probe + 1; step *= 2;
+    }
+}
+
+// ---- extend: one thread per rep; long ones are parked for the warp kernel
+__global__ void __launch_bounds__(DD_NT) k_extend(DedupArgs a, GenomeTable gt, SeedDev sd) {
+    const u32 i = blockIdx.x * DD_NT + threadIdx.x;
+    const bool valid = i < a.n_rep;
+    u32 live = __ballot_sync(0xFFFFFFFFu, valid);
+    if ((threadIdx.x & 31) == 0) reinterpret_cast<u32*>(a.live_bits)[i >> 5] = live;
+    bool is_long = false;
+    if (valid) {
+        u32 s = (u32)a.s_key[i];
+        u32 c = a.cand_at[s];
+        a.s_hash[i] = a.slot_hash[s];
+        a.s_cand[i] = c;
+        a.minrank[i] = INF32;
+        u32 off = a.cand_off[c], m = a.cand_off[c + 1] - off;
+        const u32* cpos = a.comp_pos + off;
+        const u8* cgs = a.comp_gs + off;
+        is_long = sd.L > 32;
+        if (!is_long) {
+            u32 room_l = INF32, room_r = INF32;
+            for (u32 k = 0; k < m; ++k) candidate_room(gt, sd.L, cpos, cgs, k, room_l, room_r);
+            u32 el = 0, er = 0;
+            if (!extend_thread(a.packed, gt, sd, cpos, cgs, m, room_l, room_r, el, er)) is_long = true;
+            else {
+                a.ext_l[c] = el; a.ext_r[c] = er;
+                u32 ilo, ihi;
+                extent_range(a, gt, i, c, el, er, ilo, ihi);
+                a.rng_lo[i] = ilo; a.rng_hi[i] = ihi;
+            }
+        }
+    }
+    wl_push(a.wl_long, a.ctr + 6, is_long, i);
+}
+
+__global__ void __launch_bounds__(DD_NT) k_extend_long(DedupArgs a, GenomeTable gt, SeedDev sd) {
+    const int lane = threadIdx.x & 31;
+    const u32 gwarp = (blockIdx.x * DD_NT + threadIdx.x) >> 5, nwarps = (gridDim.x * DD_NT) >> 5;
+    const u32 n = a.ctr[6];
+    for (u32 t = gwarp; t < n; t += nwarps) {
+        u32 i = a.wl_long[t];
+        u32 c = a.s_cand[i];
+        u32 off = a.cand_off[c], m = a.cand_off[c + 1] - off;
+        const u32* cpos = a.comp_pos + off;
+        const u8* cgs = a.comp_gs + off;
+        u32 el, er;
+        if (sd.L > 32) extend_candidate_warp(a.packed, gt, sd, cpos, cgs, m, el, er);
+        else {
+            u32 room_l = INF32, room_r = INF32;
+            for (u32 k = lane; k < m; k += 32) candidate_room(gt, sd.L, cpos, cgs, k, room_l, room_r);
+            room_l = __reduce_min_sync(0xFFFFFFFFu, room_l);
+            room_r = __reduce_min_sync(0xFFFFFFFFu, room_r);
+            el = grow_warp(a.packed, gt, sd, cpos, cgs, m, -1, room_l);
+            er = grow_warp(a.packed, gt, sd, cpos, cgs, m, +1, room_r);
+        }
+        if (lane == 0) {
+            a.ext_l[c] = el; a.ext_r[c] = er;
+            u32 ilo, ihi;
+            extent_range(a, gt, i, c, el, er, ilo, ihi);
+            a.rng_lo[i] = ilo; a.rng_hi[i] = ihi;
+        }
+    }
+}
+
+// the undecided higher-rank reps of rep i's group among the reps of one bitmap word: claim (atomicMin
+// of i's rank) or cover (i is accepted: they are contained in it, D16)
+template <bool COVER>
+__device__ __forceinline__ void visit_word(const DedupArgs& a, u32 w, u32 ilo, u32 ihi, u32 c, u64 h) {
+    u64 bits = a.live_bits[w] & range_mask(w, ilo, ihi) & ~a.cov_bits[w]; // covered reps are as good as dropped
+    u64 cov = 0;
     while (bits) {
-        u32 s = w * 64 + (u32)__ffsll((long long)bits) - 1;
+        u32 bpos = (u32)__ffsll((long long)bits) - 1;
         bits &= bits - 1;
-        u32 j = a.cand_at[s];
-        if (j > c && a.cstate[j] == 0) atomicMin(&a.minrank[s], c);
+        u32 t = w * 64 + bpos;
+#ifdef MB_DEDUP_COUNT
+        atomicAdd(a.ctr + 12, 1u);
+#endif
+        if (a.s_hash[t] != h) continue;
+        u32 j = a.s_cand[t];
+        if (j <= c) continue;
+#ifdef MB_DEDUP_COUNT
+        atomicAdd(a.ctr + 13 + (COVER ? 1 : 0), 1u);
+#endif
+        // a claim only delays its target, so the hash alone is enough there (a false claim lapses when the
+        // claimer is decided); a cover drops its target and is verified component by component
+        if (COVER) { if (same_group(a, c, j)) cov |= 1ull << bpos; }
+        else atomicMin(&a.minrank[t], c);
     }
-}
-// c is accepted: mark every slot of the range covered, except live lower-rank candidates of this batch
-// (a match only contains candidates of higher rank, D16)
-__device__ __forceinline__ void cover_word(const DedupArgs& a, u32 w, u32 rlo, u32 rhi, u32 c) {
-    u64 m = range_mask(w, rlo, rhi), live = a.batch_bits[w] & m, excl = 0;
-    while (live) {
-        u64 b = live & (~live + 1);
-        live ^= b;
-        u32 s = w * 64 + (u32)__ffsll((long long)b) - 1;
-        if (a.cand_at[s] < c) excl |= b;
-    }
-    atomicOr((unsigned long long*)&a.cov_bits[w], m & ~excl);
-}
-// 0 dropped, 1 accepted, 2 still undecided.  Claims of this round are complete (barrier).  One hop:
-// if the lowest claimer of c is itself unclaimed and uncovered it is accepted in this very phase, so c
-// is contained in an accepted match of lower rank.
-__device__ __forceinline__ int decide_state(const DedupArgs& a, u32 c, u32 s) {
-    if (bit_of(a.cov_bits, s)) return 0;
-    u32 mr = a.minrank[s];
-    if (mr == c) return 1;
-    u32 se = a.slot_of[mr];
-    bool mr_cov = bit_of(a.cov_bits, se);
-    if (!mr_cov && a.minrank[se] == mr) return 0;
-    if (mr_cov || a.cstate[mr] == 2) a.minrank[s] = 0xFFFFFFFFu; // that claimer is out: claim again next round
-    return 2;
+    if (COVER && cov) atomicOr((unsigned long long*)&a.cov_bits[w], cov);
 }
 
 __device__ __forceinline__ u64 gtimer() { u64 t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 // optional phase trace (a.trace != null): thread 0 appends (tag, globaltimer ns) pairs after each barrier
 #define DD_TRACE(tag) do { if (t0 && a.trace) { u64 k = a.trace[0]; if (k < 4000) { a.trace[2 + 2 * k] = (tag); a.trace[3 + 2 * k] = gtimer(); a.trace[0] = k + 1; } } } while (0)
 
-// ctr layout (u32): [0..2] narrow-list counters (rotating), [3..5] wide-list counters (rotating), [6] long list,
-// [8] batches, [9] rounds, [10] wide items, [11] long items.  A counter is reset one round before it is
-// written and never while it may still be read.
-__global__ void __launch_bounds__(DD_NT) k_dedup_all(DedupArgs a, GenomeTable gt, SeedDev sd, u32 batch0) {
+// ctr layout (u32): [0..2] narrow-list counters (rotating; round 0 takes every rep), [3..5] wide-list
+// counters (rotating), [6] long list, [9] rounds, [10] wide items.  A counter is reset one round before
+// it is written and never while it may still be read.
+__global__ void __launch_bounds__(DD_NT) k_resolve(DedupArgs a) {
     cg::grid_group grid = cg::this_grid();
     const bool t0 = blockIdx.x == 0 && threadIdx.x == 0;
     const u32 gtid = blockIdx.x * DD_NT + threadIdx.x, gsz = gridDim.x * DD_NT;
@@ -351,159 +601,112 @@ __global__ void __launch_bounds__(DD_NT) k_dedup_all(DedupArgs a, GenomeTable gt
     u32* ctr = a.ctr;
     u32* nl[3] = {a.wl0, a.wl1, a.wl2};
     u32* wd[3] = {a.wd0, a.wd1, a.wd2};
-    const u32 bb_words = (a.n_cand + 63) / 64;
-    u32 p = 0, batch = batch0;
-    while (p < a.n_cand) {
-        const u32 q = (u32)min((u64)a.n_cand, (u64)p + batch);
-        if (t0) { for (int i = 0; i < 7; ++i) ctr[i] = 0; ctr[8] += 1; }
-        for (u32 w = gtid; w < bb_words; w += gsz) a.batch_bits[w] = 0;
-        grid.sync();
-        DD_TRACE(1);
-        // ---- begin: drop covered candidates, list the live ones, flag their slots
-        for (u32 base = p + blockIdx.x * DD_NT; base < q; base += gsz) {
-            u32 c = base + threadIdx.x;
-            bool live = false;
-            if (c < q) {
-                u32 s = a.slot_of[c];
-                if (bit_of(a.cov_bits, s)) a.cstate[c] = 2;
-                else {
-                    live = true;
-                    a.cstate[c] = 0;
-                    a.minrank[s] = 0xFFFFFFFFu;
-                    atomicOr((unsigned long long*)&a.batch_bits[s >> 6], 1ull << (s & 63));
-                }
-            }
-            wl_push(nl[0], ctr + 0, live, c);
+    DD_TRACE(1);
+    for (u32 r = 0;; ++r) {
+        const u32 cur = r % 3, nxt = (r + 1) % 3, spare = (r + 2) % 3;
+        if (t0) { ctr[spare] = 0; ctr[3 + spare] = 0; ctr[9] += 1; }
+        const u32 n_narrow = r == 0 ? a.n_rep : ctr[cur];
+        // ---- claim, one thread per undecided rep (round 0 also sorts out the wide ranges)
+        for (u32 t = gtid; t < n_narrow; t += gsz) {
+            u32 i = r == 0 ? t : nl[cur][t];
+            u32 ilo = a.rng_lo[i], ihi = a.rng_hi[i];
+            if (r == 0 && ihi - ilo > DD_WIDE) { wd[0][atomicAdd(ctr + 3, 1u)] = i; continue; }
+            if (ihi - ilo < 2 || bit_of(a.cov_bits, i)) continue; // alone in its extent / as good as dropped
+            u32 c = a.s_cand[i];
+            u64 h = a.s_hash[i];
+            for (u32 w = ilo >> 6; w <= (ihi - 1) >> 6; ++w) visit_word<false>(a, w, ilo, ihi, c, h);
+        }
+        if (r == 0) { grid.sync(); if (t0) ctr[10] = ctr[3]; } // the wide list is complete only now
+        const u32 n_wide = ctr[3 + cur];
+        // ---- claim, wide ranges: one warp each, a bitmap word per lane
+        for (u32 t = gwarp; t < n_wide; t += nwarps) {
+            u32 i = wd[cur][t];
+            if (bit_of(a.cov_bits, i)) continue;
+            u32 ilo = a.rng_lo[i], ihi = a.rng_hi[i];
+            u32 c = a.s_cand[i];
+            u64 h = a.s_hash[i];
+            for (u32 w = (ilo >> 6) + lane; w <= (ihi - 1) >> 6; w += 32) visit_word<false>(a, w, ilo, ihi, c, h);
         }
         grid.sync();
-        DD_TRACE(2);
-        // ---- extend: one thread per live candidate; long ones are parked for the warp phase
-        {
-            const u32 n = ctr[0];
-            if (t0) atomicAdd(a.n_extended, n);
-            for (u32 base = blockIdx.x * DD_NT; base < n; base += gsz) {
-                u32 i = base + threadIdx.x;
-                bool is_long = false;
-                u32 c = 0;
-                if (i < n) {
-                    c = nl[0][i];
-                    u32 off = a.cand_off[c], m = a.cand_off[c + 1] - off;
-                    const u32* cpos = a.comp_pos + off;
-                    const u8* cgs = a.comp_gs + off;
-                    is_long = m > DD_THREAD_COMPS || sd.L > 32;
-                    if (!is_long) {
-                        u32 room_l = 0xFFFFFFFFu, room_r = 0xFFFFFFFFu;
-                        for (u32 k = 0; k < m; ++k) candidate_room(gt, sd.L, cpos, cgs, k, room_l, room_r);
-                        u32 el = grow_thread(a.packed, gt, sd, cpos, cgs, m, -1, room_l);
-                        u32 er = el == 0xFFFFFFFFu ? el : grow_thread(a.packed, gt, sd, cpos, cgs, m, +1, room_r);
-                        if (el == 0xFFFFFFFFu || er == 0xFFFFFFFFu) is_long = true;
-                        else {
-                            a.ext_l[c] = el; a.ext_r[c] = er;
-                            u32 rlo, rhi;
-                            extent_range(a, c, el, er, rlo, rhi);
-                            a.rng_lo[c] = rlo; a.rng_hi[c] = rhi;
+        DD_TRACE(5);
+        // ---- decide, narrow: covered -> dropped, unclaimed -> accepted, else still undecided
+        for (u32 base = blockIdx.x * DD_NT; base < n_narrow; base += gsz) {
+            u32 t = base + threadIdx.x;
+            bool keep = false;
+            u32 i = 0;
+            if (t < n_narrow) {
+                i = r == 0 ? t : nl[cur][t];
+                u32 ilo = a.rng_lo[i], ihi = a.rng_hi[i];
+                if (r > 0 || ihi - ilo <= DD_WIDE) {
+                    u32 c = a.s_cand[i];
+                    if (bit_of(a.cov_bits, i)) {
+                        a.cstate[c] = 2;
+                        atomicAnd((unsigned long long*)&a.live_bits[i >> 6], ~(1ull << (i & 63)));
+                    } else if (a.minrank[i] == INF32) {
+                        // accepted: every undecided higher-rank rep of this group inside the extent is contained
+                        if (ihi - ilo >= 2) {
+                            u64 h = a.s_hash[i];
+                            for (u32 w = ilo >> 6; w <= (ihi - 1) >> 6; ++w) visit_word<true>(a, w, ilo, ihi, c, h);
                         }
+                        a.cstate[c] = 1;
+                        atomicAnd((unsigned long long*)&a.live_bits[i >> 6], ~(1ull << (i & 63)));
+                    } else {
+                        a.minrank[i] = INF32;
+                        keep = true;
                     }
                 }
-                wl_push(a.wl_long, ctr + 6, is_long, c);
+            }
+            wl_push(nl[nxt], ctr + nxt, keep, i);
+        }
+        // ---- decide, wide
+        for (u32 t = gwarp; t < n_wide; t += nwarps) {
+            u32 i = wd[cur][t];
+            u32 c = a.s_cand[i];
+            int d = 2;
+            if (lane == 0) {
+                if (bit_of(a.cov_bits, i)) d = 0;
+                else if (a.minrank[i] == INF32) d = 1;
+            }
+            d = __shfl_sync(0xFFFFFFFFu, d, 0);
+            if (d == 1) {
+                u32 ilo = a.rng_lo[i], ihi = a.rng_hi[i];
+                u64 h = a.s_hash[i];
+                for (u32 w = (ilo >> 6) + lane; w <= (ihi - 1) >> 6; w += 32) visit_word<true>(a, w, ilo, ihi, c, h);
+            }
+            if (lane == 0) {
+                if (d == 2) { a.minrank[i] = INF32; wd[nxt][atomicAdd(ctr + 3 + nxt, 1u)] = i; }
+                else {
+                    a.cstate[c] = d == 1 ? 1 : 2;
+                    atomicAnd((unsigned long long*)&a.live_bits[i >> 6], ~(1ull << (i & 63)));
+                }
             }
         }
         grid.sync();
-        DD_TRACE(3);
-        if (ctr[6]) { // uniform across the grid
-            const u32 n = ctr[6];
-            for (u32 i = gwarp; i < n; i += nwarps) {
-                u32 c = a.wl_long[i];
-                u32 off = a.cand_off[c], m = a.cand_off[c + 1] - off;
-                u32 el, er;
-                extend_candidate_warp(a.packed, gt, sd, a.comp_pos + off, a.comp_gs + off, m, el, er);
-                if (lane == 0) {
-                    a.ext_l[c] = el; a.ext_r[c] = er;
-                    u32 rlo, rhi;
-                    extent_range(a, c, el, er, rlo, rhi);
-                    a.rng_lo[c] = rlo; a.rng_hi[c] = rhi;
-                }
-            }
-            if (t0) ctr[11] += n;
-            grid.sync();
-        }
-        DD_TRACE(4);
-        for (u32 r = 0;; ++r) {
-            const u32 cur = r % 3, nxt = (r + 1) % 3, spare = (r + 2) % 3;
-            if (t0) { ctr[spare] = 0; ctr[3 + spare] = 0; ctr[9] += 1; }
-            const u32 n_narrow = ctr[cur];
-            // ---- claim, one thread per candidate (round 0 also sorts out the wide ranges)
-            for (u32 i = gtid; i < n_narrow; i += gsz) {
-                u32 c = nl[cur][i];
-                u32 rlo = a.rng_lo[c], rhi = a.rng_hi[c];
-                if (r == 0 && rhi - rlo > DD_WIDE_SLOTS) { wd[0][atomicAdd(ctr + 3, 1u)] = c; continue; }
-                for (u32 w = rlo >> 6; w <= (rhi - 1) >> 6; ++w) claim_word(a, w, rlo, rhi, c);
-                atomicMin(&a.minrank[a.slot_of[c]], c);
-            }
-            if (r == 0) { grid.sync(); if (t0) ctr[10] += ctr[3]; } // the wide list is complete only now
-            const u32 n_wide = ctr[3 + cur];
-            // ---- claim, wide ranges: one warp each, a bitmap word per lane
-            for (u32 i = gwarp; i < n_wide; i += nwarps) {
-                u32 c = wd[cur][i];
-                u32 rlo = a.rng_lo[c], rhi = a.rng_hi[c];
-                for (u32 w = (rlo >> 6) + lane; w <= (rhi - 1) >> 6; w += 32) claim_word(a, w, rlo, rhi, c);
-                if (lane == 0) atomicMin(&a.minrank[a.slot_of[c]], c);
-            }
-            grid.sync();
-            DD_TRACE(5);
-            // ---- decide, narrow
-            for (u32 base = blockIdx.x * DD_NT; base < n_narrow; base += gsz) {
-                u32 i = base + threadIdx.x;
-                bool keep = false;
-                u32 c = 0;
-                if (i < n_narrow) {
-                    c = nl[cur][i];
-                    u32 rlo = a.rng_lo[c], rhi = a.rng_hi[c];
-                    if (r > 0 || rhi - rlo <= DD_WIDE_SLOTS) {
-                        int d = decide_state(a, c, a.slot_of[c]);
-                        if (d == 0) a.cstate[c] = 2;
-                        else if (d == 1) {
-                            // accepted: everything of this group inside the extent is now contained
-                            for (u32 w = rlo >> 6; w <= (rhi - 1) >> 6; ++w) cover_word(a, w, rlo, rhi, c);
-                            a.cstate[c] = 1;
-                        } else keep = true;
-                    }
-                }
-                wl_push(nl[nxt], ctr + nxt, keep, c);
-            }
-            // ---- decide, wide
-            for (u32 i = gwarp; i < n_wide; i += nwarps) {
-                u32 c = wd[cur][i];
-                int d = 0;
-                if (lane == 0) d = decide_state(a, c, a.slot_of[c]);
-                d = __shfl_sync(0xFFFFFFFFu, d, 0);
-                if (d == 0) { if (lane == 0) a.cstate[c] = 2; }
-                else if (d == 1) {
-                    u32 rlo = a.rng_lo[c], rhi = a.rng_hi[c];
-                    for (u32 w = (rlo >> 6) + lane; w <= (rhi - 1) >> 6; w += 32) cover_word(a, w, rlo, rhi, c);
-                    if (lane == 0) a.cstate[c] = 1;
-                } else if (lane == 0) wd[nxt][atomicAdd(ctr + 3 + nxt, 1u)] = c;
-            }
-            grid.sync();
-            DD_TRACE(6);
-            if (ctr[nxt] + ctr[3 + nxt] == 0) break;
-        }
-        p = q;
-        batch = max(batch, p);
+        DD_TRACE(6);
+        if (ctr[nxt] + ctr[3 + nxt] == 0) break;
     }
 }
 
-void launch_group_ids(const DedupArgs& a, cudaStream_t st) {
-    if (a.n_cand) k_group_ids<<<div_up(a.n_cand, 256), 256, 0, st>>>(a);
+void launch_slot_scatter(const DedupArgs& a, const GenomeTable& gt, cudaStream_t st) {
+    if (a.n_cand) k_slot_scatter<<<div_up(a.n_cand, 256), 256, 0, st>>>(a, gt);
 }
-void launch_slot_keys(const DedupArgs& a, const GenomeTable& gt, u64* skey, u64* sval, cudaStream_t st) {
-    if (a.n_cand) k_slot_keys<<<div_up(a.n_cand, 256), 256, 0, st>>>(a, gt, skey, sval);
+u32 chain_tile() { return CH_TILE; }
+void launch_chains(const DedupArgs& a, u64* status_fwd, u32* ticket_fwd, u64* status_bwd, u32* ticket_bwd, cudaStream_t st) {
+    if (a.n_cand == 0) return;
+    u32 tiles = div_up(a.n_cand, CH_TILE);
+    k_chain<false><<<tiles, CH_NT, 0, st>>>(a, status_fwd, ticket_fwd);
+    k_chain<true><<<tiles, CH_NT, 0, st>>>(a, status_bwd, ticket_bwd);
 }
-void launch_slot_finish(const DedupArgs& a, const u64* skey, const u64* sval, cudaStream_t st) {
-    if (a.n_cand) k_slot_finish<<<div_up(a.n_cand, 256), 256, 0, st>>>(a, skey, sval);
+void launch_rep_keys(const DedupArgs& a, u64* skey, cudaStream_t st) {
+    if (a.n_cand) k_rep_keys<<<div_up(a.n_cand, 256), 256, 0, st>>>(a, skey);
 }
-cudaError_t launch_dedup_all(const DedupArgs& a, const GenomeTable& gt, const SeedDev& sd, u32 batch0, cudaStream_t st) {
-    if (a.n_cand == 0) return cudaSuccess;
+void launch_extend(const DedupArgs& a, const GenomeTable& gt, const SeedDev& sd, cudaStream_t st) {
+    if (a.n_rep == 0) return;
+    k_extend<<<div_up(a.n_rep, DD_NT), DD_NT, 0, st>>>(a, gt, sd);
+    k_extend_long<<<148 * 4, DD_NT, 0, st>>>(a, gt, sd);
+}
+cudaError_t launch_resolve(const DedupArgs& a, cudaStream_t st) {
+    if (a.n_rep == 0) return cudaSuccess;
     static int grid_blocks = 0;
     if (grid_blocks == 0) {
         int dev = 0, sms = 0, per_sm = 0;
@@ -511,14 +714,12 @@ cudaError_t launch_dedup_all(const DedupArgs& a, const GenomeTable& gt, const Se
         if (e != cudaSuccess) return e;
         e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_dedup_all, DD_NT, 0);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_resolve, DD_NT, 0);
         if (e != cudaSuccess) return e;
         if (per_sm < 1) return cudaErrorLaunchOutOfResources;
         grid_blocks = sms * per_sm;
     }
     DedupArgs aa = a;
-    GenomeTable g = gt;
-    SeedDev s = sd;
-    void* args[] = {&aa, &g, &s, &batch0};
-    return cudaLaunchCooperativeKernel((const void*)k_dedup_all, dim3(grid_blocks), dim3(DD_NT), args, 0, st);
+    void* args[] = {&aa};
+    return cudaLaunchCooperativeKernel((const void*)k_resolve, dim3(grid_blocks), dim3(DD_NT), args, 0, st);
 }
