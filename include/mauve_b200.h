@@ -116,6 +116,29 @@ int mb_find_device(mb_ctx* ctx, const mb_params* params);
 /* Device -> pinned host copy of the last mb_find_device result (synchronises the stream). */
 int mb_fetch_result(mb_ctx* ctx, const mb_result** out);
 
+/* ---- multi-GPU path ---------------------------------------------
+ * One context per rank / GPU, the same sequences added to every context (replicated genomes).
+ * The library runs the per-rank stages and owns the exchange buffers; the three exchanges (variable
+ * all-to-alls of uint64 words, NCCL over NVLink) are the caller's, between the stages
+ * (mauvealigner_b200/dist.py drives them over torch.distributed).  MB_MODE_UNIQUE, 8-byte records.
+ * Stands in for the same reference calls as mb_find (the reference is single-process).
+ *   1 mb_dist_extract      -> *d_send: this rank's seed records grouped by destination rank,
+ *                             h_counts[world] records per destination               (exchange 1)
+ *   2 mb_dist_recv_buffer(0, n) is where exchange 1 must deliver (source-rank order);
+ *     mb_dist_local        -> candidate rows grouped by owner rank: headers (2 words each) at
+ *                             *d_hdr, component words at *d_comps, counts per owner (exchange 2)
+ *   3 mb_dist_recv_buffer(1 / 2, n) receive the headers / components;
+ *     mb_dist_dedup        -> accepted matches as rows (*d_hdr, *d_comps)       (gather to rank 0)
+ *   4 mb_dist_recv_buffer(3 / 4, n) on rank 0; mb_dist_output builds the canonical CSR there, after
+ *     which mb_fetch_result works as for mb_find_device. */
+int mb_dist_extract(mb_ctx* ctx, int rank, int world, void** d_send, uint64_t* h_counts);
+int mb_dist_recv_buffer(mb_ctx* ctx, int which, uint64_t n_words, void** d_ptr);
+int mb_dist_local(mb_ctx* ctx, const mb_params* params, uint64_t n_recv, uint64_t* h_cand_counts, uint64_t* h_comp_counts,
+                  void** d_hdr, void** d_comps);
+int mb_dist_dedup(mb_ctx* ctx, uint64_t n_cand, uint64_t n_comp, uint64_t* h_n_match, uint64_t* h_n_mcomp, void** d_hdr, void** d_comps);
+int mb_dist_output(mb_ctx* ctx, uint64_t n_match, uint64_t n_comp);
+int mb_dist_stage_ms(mb_ctx* ctx, float* out4);
+
 /* ---- sorted mer list access (SortedMerList façade; "next" row of SURVEY.md §8f) ---- */
 /* Positions of sequence `seq` sorted by (seed, position): the .sslist position array (a4).
  * out_pos must hold len-L+1 entries (host). Valid after a mb_find* call in any mode. */

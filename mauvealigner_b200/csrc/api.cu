@@ -231,32 +231,27 @@ int mbi_read_scalars(mb_ctx* c) {
 
 extern "C" {
 
-int mb_find_device(mb_ctx* c, const mb_params* prm) {
-    if (!c || !prm) return MB_E_ARG;
+} // extern "C"
+
+// Genome table, record format, small workspaces and counters of one run (shared with api_dist.cu).
+int mbi_setup_run(mb_ctx* c, MbiRun& r) {
     if (!c->seed_set) return MB_E_SEED;
     const u32 nseq = (u32)c->seq_len.size();
     if (nseq == 0) return MB_E_NOSEQ;
-    const int mode = prm->mode;
-    if (mode < MB_MODE_UNIQUE || mode > MB_MODE_PAIRWISE) return MB_E_ARG;
-    if (mode == MB_MODE_PAIRWISE) return MB_E_ARG; // not built yet (SURVEY.md §8f rank 3)
-    if (mode == MB_MODE_SEED_ENUM && nseq != 1) return MB_E_SEQCOUNT;
     CUDA_TRY(c, cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
     const SeedDev& sd = c->sd;
     const u32 L = sd.L;
-
     u64 h2d = c->stats.h2d_bytes;
     memset(&c->stats, 0, sizeof(c->stats));
     c->stats.h2d_bytes = h2d;
     c->have_result = false;
     c->ticket_next = 0; c->status_next = 0; c->n_timed_passes = 0;
-
-    // ---- genome table, record format
     GenomeTable& gt = c->gt;
     memset(&gt, 0, sizeof(gt));
     gt.nseq = nseq;
     u64 n64 = 0, bases = 0, maxlen = 0;
-    std::vector<u32> tile_first(nseq + 1);
+    r.tile_first.assign(nseq + 1, 0);
     const u32 ET = extract_tile_size();
     u32 n_tiles = 0;
     for (u32 g = 0; g < nseq; ++g) {
@@ -266,13 +261,14 @@ int mb_find_device(mb_ctx* c, const mb_params* prm) {
         gt.len[g] = (u32)len;
         gt.seed_base[g] = (u32)n64;
         u64 ns = len >= L ? len - L + 1 : 0;
-        tile_first[g] = n_tiles;
+        r.tile_first[g] = n_tiles;
         n_tiles += div_up(ns, ET);
         n64 += ns; bases += len; maxlen = std::max(maxlen, len);
     }
-    tile_first[nseq] = n_tiles;
+    r.tile_first[nseq] = n_tiles;
     if (n64 >= (1ull << 31)) return MB_E_TOOLONG;
     const u32 n = (u32)n64;
+    r.n = n; r.n_tiles = n_tiles; r.bases = bases; r.maxlen = maxlen;
     c->n_seeds = n;
     c->stats.n_seeds = n;
     RecFmt& fmt = c->fmt;
@@ -283,19 +279,12 @@ int mb_find_device(mb_ctx* c, const mb_params* prm) {
     fmt.wide = (fmt.kbits + fmt.gbits + fmt.pbits + 1) > 64;
     fmt.kshift = fmt.wide ? 0 : fmt.gbits + fmt.pbits + 1;
     c->stats.record_bytes = fmt.wide ? 16 : 8;
-    const int npass = (fmt.kbits + 7) / 8;
-
-    // ---- workspace
-    const size_t nrec = (size_t)n + 8;
-    TRY(c->reserve(c->keysA, nrec * 8));
-    TRY(c->reserve(c->keysB, nrec * 8));
-    if (fmt.wide) { TRY(c->reserve(c->valsA, nrec * 8)); TRY(c->reserve(c->valsB, nrec * 8)); }
     TRY(c->reserve(c->hist, 8 * 256 * 4));
     TRY(c->reserve(c->digit_base, 8 * 256 * 4));
     TRY(c->reserve(c->lookback, (size_t)(div_up(n, radix_tile_size()) + 1) * 256 * 8));
     TRY(c->reserve(c->tickets, 256 * 4));
-    size_t status_words = (size_t)div_up(n, find_runs_tile()) + div_up(n, select_tile()) + 3 * (size_t)div_up(n, scan_tile()) +
-                          div_up(bases / 64 + 2, scan_tile()) + 2 * (size_t)div_up(n / 2 + 2, chain_tile()) + div_up(n / 128 + 4, scan_tile()) + 64;
+    size_t status_words = (size_t)div_up(n, find_runs_tile()) + div_up(n, select_tile()) + 6 * (size_t)div_up(n, scan_tile()) +
+                          div_up(bases / 64 + 2, scan_tile()) + 2 * (size_t)div_up(n, chain_tile()) + 64;
     TRY(c->reserve(c->status, status_words * 8));
     TRY(c->reserve(c->scalars, SC_COUNT * 8));
     TRY(c->reserve(c->per_seq, MB_MAX_SEQ * 8));
@@ -305,7 +294,34 @@ int mb_find_device(mb_ctx* c, const mb_params* prm) {
     CUDA_TRY(c, cudaMemsetAsync(c->scalars.p, 0, SC_COUNT * 8, st));
     CUDA_TRY(c, cudaMemsetAsync(c->per_seq.p, 0, MB_MAX_SEQ * 8, st));
     CUDA_TRY(c, cudaMemsetAsync(c->hist.p, 0, 8 * 256 * 4, st));
-    CUDA_TRY(c, cudaMemcpyAsync(c->tile_first.p, tile_first.data(), (nseq + 1) * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(c, cudaMemcpyAsync(c->tile_first.p, r.tile_first.data(), (nseq + 1) * 4, cudaMemcpyHostToDevice, st));
+    c->last_mode = -1;
+    c->r_matches = 0; c->r_comps = 0; c->r_unique = 0;
+    return MB_OK;
+}
+
+extern "C" {
+
+int mb_find_device(mb_ctx* c, const mb_params* prm) {
+    if (!c || !prm) return MB_E_ARG;
+    const int mode = prm->mode;
+    if (mode < MB_MODE_UNIQUE || mode > MB_MODE_PAIRWISE) return MB_E_ARG;
+    if (mode == MB_MODE_PAIRWISE) return MB_E_ARG; // not built yet (SURVEY.md §8f rank 3)
+    if (mode == MB_MODE_SEED_ENUM && c->seq_len.size() > 1) return MB_E_SEQCOUNT;
+    MbiRun run;
+    TRY(mbi_setup_run(c, run));
+    cudaStream_t st = c->stream;
+    const SeedDev& sd = c->sd;
+    const u32 L = sd.L;
+    GenomeTable& gt = c->gt;
+    RecFmt& fmt = c->fmt;
+    const u32 n = run.n, n_tiles = run.n_tiles;
+    const u64 bases = run.bases, maxlen = run.maxlen;
+    const int npass = (fmt.kbits + 7) / 8;
+    const size_t nrec = (size_t)n + 8;
+    TRY(c->reserve(c->keysA, nrec * 8));
+    TRY(c->reserve(c->keysB, nrec * 8));
+    if (fmt.wide) { TRY(c->reserve(c->valsA, nrec * 8)); TRY(c->reserve(c->valsB, nrec * 8)); }
     u64* scal = c->scalars.as<u64>();
 
     cudaEventRecord(c->ev[EV_START], st);
@@ -320,7 +336,6 @@ int mb_find_device(mb_ctx* c, const mb_params* prm) {
     cudaEventRecord(c->ev[EV_SORT], st);
 
     c->last_mode = mode;
-    c->r_matches = 0; c->r_comps = 0; c->r_unique = 0;
     if (n == 0) {
         for (int i = EV_BUCKET; i < EV_COUNT; ++i) cudaEventRecord(c->ev[i], st);
         memset(c->h_perseq, 0, MB_MAX_SEQ * 8);
@@ -676,6 +691,16 @@ int mb_find(mb_ctx* c, const mb_params* prm, const mb_result** out) {
 
 int mb_get_stats(mb_ctx* c, mb_stats* out) {
     if (!c || !out) return MB_E_ARG;
+    if (c->n_timed_passes) { // the seed sort's per-pass events (complete once the stream has been synchronised)
+        float tot = 0;
+        bool ok = true;
+        for (int i = 0; i < c->n_timed_passes; ++i) {
+            float t = 0;
+            if (cudaEventElapsedTime(&t, c->ev_r[2 * i], c->ev_r[2 * i + 1]) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+            tot += t;
+        }
+        if (ok) { c->stats.ms_radix_kernels = tot; c->stats.radix_launches = c->n_timed_passes; }
+    }
     *out = c->stats;
     return MB_OK;
 }

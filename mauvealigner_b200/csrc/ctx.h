@@ -40,6 +40,11 @@ struct mb_ctx {
     DBuf keysA, keysB, valsA, valsB, hist, digit_base, lookback, tickets, status, scalars, per_seq, tile_first;
     DBuf cand_run, cand_off, cand_aux, comp_pos, comp_gs, bitmap, bmrank, cand_at, cstate, covered, minrank, ext_l, ext_r;
     DBuf trace;
+    DBuf x_lut, x_counts, x_hdr_s, x_comp_s, x_hdr_r, x_comp_r, x_m; // multi-GPU exchange buffers (api_dist.cu)
+    int d_rank = 0, d_world = 1;
+    u32 d_ncand = 0, d_nccomp = 0, d_nmatch = 0, d_nmcomp = 0;
+    u64 d_bases = 0, d_maxlen = 0;
+    cudaEvent_t ev_d[8] = {nullptr};
     DBuf wl_a, wl_b, wl_c, wl_long, wd_a, wd_b, wd_c, live_bits, ghash, slot_gp, slot_hash, link_bits, chain_min, rep_bits, rep_rank, s_hash, s_cand, rng_lo, rng_hi;
     DBuf flags, match_idx, sort_kA, sort_kB, sort_vA, sort_vB, ncomp, mers_tmp;
     DBuf out_len, out_off, out_seq, out_start;
@@ -104,6 +109,8 @@ struct mb_ctx {
 
 
 // helpers defined in api.cu
+struct MbiRun { std::vector<u32> tile_first; u32 n = 0, n_tiles = 0; u64 bases = 0, maxlen = 0; };
+int mbi_setup_run(mb_ctx* c, MbiRun& r);
 int mbi_sort_records(mb_ctx* c, u64** kA, u64** kB, u64** vA, u64** vB, u32 n, int shift, int kbits, bool hist_ready, bool time_passes = false);
 int mbi_read_scalars(mb_ctx* c);
 int mbi_bits_for(u64 maxval);

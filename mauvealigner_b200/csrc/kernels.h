@@ -13,7 +13,8 @@ struct ExtractArgs;
 void launch_pack(const u8* d_ascii, u64 len, u64* d_words, u64 n_words, cudaStream_t st);
 u32 extract_tile_size();
 void launch_extract_records(const u64* d_packed, u64* d_keys, u64* d_vals, u32* d_hist, int npass, const GenomeTable& gt,
-                            const SeedDev& sd, const RecFmt& fmt, const u32* d_tile_first, u32 n_tiles, cudaStream_t st);
+                            const SeedDev& sd, const RecFmt& fmt, const u32* d_tile_first, u32 n_tiles, cudaStream_t st, u32 tile0 = 0,
+                            u32 out_base = 0);
 void launch_mers(const u64* d_packed, const GenomeTable& gt, const SeedDev& sd, const RecFmt& fmt, int genome, u64* d_mers, cudaStream_t st);
 void launch_hist(const u64* d_keys, u32 n, int shift0, int kbits, int npass, u32* d_hist, cudaStream_t st);
 
@@ -21,8 +22,10 @@ void launch_hist(const u64* d_keys, u32 n, int shift0, int kbits, int npass, u32
 size_t radix_smem_bytes(bool has_val);
 u32 radix_tile_size();
 void launch_scan_hist(const u32* d_hist, u32* d_base, int npass, cudaStream_t st);
+// lut (optional, device, 256 bytes): the bin of a record is lut[digit] instead of the digit itself (monotone
+// key-range partition of the multi-GPU path)
 cudaError_t launch_onesweep(const u64* kin, u64* kout, const u64* vin, u64* vout, u32 n, const u32* d_digit_base, u64* d_lookback,
-                            u32* d_ticket, int shift, int bits, cudaStream_t st);
+                            u32* d_ticket, int shift, int bits, cudaStream_t st, const u8* lut = nullptr);
 
 // ---- kernels_bucket.cu
 u32 find_runs_tile();
@@ -120,3 +123,18 @@ void launch_uniq_keys(const OutputArgs& a, int sbits, cudaStream_t st);
 void launch_uniq_tiefix(const OutputArgs& a, const u64* skey, u64* sval, u32 L, u32 n_upper, cudaStream_t st);
 void launch_uniq_ncomp(const OutputArgs& a, const u64* sval, u32 n_upper, cudaStream_t st);
 void launch_uniq_gather(const OutputArgs& a, const u64* sval, u32 L, u32 n_upper, cudaStream_t st);
+
+// ---- kernels_dist.cu (multi-GPU exchange formats)
+void launch_fold_lut(const u32* hist, const u8* lut, u32 nbins, u32 world, u32* digit_base, u64* counts, cudaStream_t st);
+void launch_owner_keys(const u64* ghash, u32 n, u32 world, u64* skey, u64* sval, cudaStream_t st);
+void launch_perm_m(const u64* perm, const u32* cand_off, u32 n, u32* m_out, cudaStream_t st);
+void launch_pack_cand(const u64* perm, const u64* poff, const u32* cand_off, const u32* comp_pos, const u8* comp_gs, const u64* ghash, u32 n,
+                      u64* hdr, u64* comps, cudaStream_t st);
+void launch_hdr_m(const u64* hdr, u32 n, u32* m_out, cudaStream_t st);
+void launch_unpack_cand(const u64* hdr, const u64* comps, const u32* cand_off, u32 n, const GenomeTable& gt, u32* comp_pos, u8* comp_gs,
+                        u64* ghash, u64* bitmap, cudaStream_t st);
+void launch_acc_m(const u8* cstate, const u32* cand_off, u32 n, u32* m_out, cudaStream_t st);
+void launch_pack_match(const u8* cstate, const u32* match_idx, const u32* acomp_off, const u32* cand_off, const u32* comp_pos, const u8* comp_gs,
+                       const u32* ext_l, const u32* ext_r, u32 n, u64* hdr, u64* comps, cudaStream_t st);
+void launch_unpack_match(const u64* hdr, const u64* comps, const u32* cand_off, u32 n, u32* comp_pos, u8* comp_gs, u32* ext_l, u32* ext_r,
+                         u8* cstate, cudaStream_t st);

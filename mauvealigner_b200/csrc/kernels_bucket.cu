@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(256) k_emit_unique(EmitUniqueArgs a, RecFmt fm
             strand0 = sb;
             x0 = p;
             u64 gp = gt.base_base[g] + p;
-            atomicOr((unsigned long long*)&a.bitmap[gp >> 6], 1ull << (gp & 63));
+            if (a.bitmap) atomicOr((unsigned long long*)&a.bitmap[gp >> 6], 1ull << (gp & 63));
         }
         bool rev = sb != strand0;
         a.comp_pos[off + k] = p;

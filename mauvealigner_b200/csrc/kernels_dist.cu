@@ -1,0 +1,155 @@
+// kernels_dist.cu — pack / unpack kernels of the multi-GPU path (api_dist.cu drives them).
+//
+// Exchange formats (all 8-byte granular so every exchange is one all-to-all of u64 words):
+//   seed records    the u64 records of the single-GPU path, partitioned by destination = seed-key range
+//   candidate rows  header 2 x u64 (group hash, component count) + one u64 per component (pos | gs << 32),
+//                   partitioned by owner = f(group hash); rows keep ascending seed order inside a partition
+//   match rows      header 2 x u64 (ext_l | ext_r << 32, component count) + the same component words
+#include "common.cuh"
+#include "kernels.h"
+
+// destination of every value of the top `tb` key bits: analytic splitters of the canonical-seed
+// distribution F(x) = 1 - (1 - x)^2 (minimum of the two strands' keys), identical on every rank.
+// Folds the 2^tb-bin histogram of the slice into per-destination counts and exclusive offsets.
+__global__ void __launch_bounds__(256) k_fold_lut(const u32* __restrict__ hist, const u8* __restrict__ lut, u32 nbins, u32 world,
+                                                  u32* __restrict__ digit_base /*[256]*/, u64* __restrict__ counts /*[world]*/) {
+    __shared__ u32 sCnt[256];
+    const u32 t = threadIdx.x;
+    sCnt[t] = 0;
+    __syncthreads();
+    if (t < nbins && hist[t]) atomicAdd(&sCnt[lut[t]], hist[t]);
+    __syncthreads();
+    if (t == 0) {
+        u32 acc = 0;
+        for (u32 d = 0; d < 256; ++d) {
+            u32 cnt = sCnt[d];
+            digit_base[d] = acc;
+            if (d < world) counts[d] = cnt;
+            acc += cnt;
+        }
+    }
+}
+void launch_fold_lut(const u32* hist, const u8* lut, u32 nbins, u32 world, u32* digit_base, u64* counts, cudaStream_t st) {
+    k_fold_lut<<<1, 256, 0, st>>>(hist, lut, nbins, world, digit_base, counts);
+}
+
+__device__ __forceinline__ u32 owner_of(u64 h, u32 world) { return (u32)((((h >> 16) & 0xFFFFFFFFull) * world) >> 32); }
+
+__global__ void __launch_bounds__(256) k_owner_keys(const u64* __restrict__ ghash, u32 n, u32 world, u64* __restrict__ skey, u64* __restrict__ sval) {
+    u32 c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    skey[c] = owner_of(ghash[c], world);
+    sval[c] = c;
+}
+void launch_owner_keys(const u64* ghash, u32 n, u32 world, u64* skey, u64* sval, cudaStream_t st) {
+    if (n) k_owner_keys<<<div_up(n, 256), 256, 0, st>>>(ghash, n, world, skey, sval);
+}
+
+// m of the j-th row in partition order
+__global__ void __launch_bounds__(256) k_perm_m(const u64* __restrict__ perm, const u32* __restrict__ cand_off, u32 n, u32* __restrict__ m_out) {
+    u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    u32 c = (u32)perm[j];
+    m_out[j] = cand_off[c + 1] - cand_off[c];
+}
+void launch_perm_m(const u64* perm, const u32* cand_off, u32 n, u32* m_out, cudaStream_t st) {
+    if (n) k_perm_m<<<div_up(n, 256), 256, 0, st>>>(perm, cand_off, n, m_out);
+}
+
+__global__ void __launch_bounds__(256) k_pack_cand(const u64* __restrict__ perm, const u64* __restrict__ poff, const u32* __restrict__ cand_off,
+                                                   const u32* __restrict__ comp_pos, const u8* __restrict__ comp_gs, const u64* __restrict__ ghash,
+                                                   u32 n, u64* __restrict__ hdr, u64* __restrict__ comps) {
+    u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    u32 c = (u32)perm[j];
+    u32 off = cand_off[c], m = cand_off[c + 1] - off;
+    hdr[2 * (u64)j] = ghash[c];
+    hdr[2 * (u64)j + 1] = m;
+    u64 o = poff[j];
+    for (u32 k = 0; k < m; ++k) comps[o + k] = (u64)comp_pos[off + k] | ((u64)comp_gs[off + k] << 32);
+}
+void launch_pack_cand(const u64* perm, const u64* poff, const u32* cand_off, const u32* comp_pos, const u8* comp_gs, const u64* ghash, u32 n,
+                      u64* hdr, u64* comps, cudaStream_t st) {
+    if (n) k_pack_cand<<<div_up(n, 256), 256, 0, st>>>(perm, poff, cand_off, comp_pos, comp_gs, ghash, n, hdr, comps);
+}
+
+__global__ void __launch_bounds__(256) k_hdr_m(const u64* __restrict__ hdr, u32 n, u32* __restrict__ m_out) {
+    u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) m_out[j] = (u32)hdr[2 * (u64)j + 1];
+}
+void launch_hdr_m(const u64* hdr, u32 n, u32* m_out, cudaStream_t st) {
+    if (n) k_hdr_m<<<div_up(n, 256), 256, 0, st>>>(hdr, n, m_out);
+}
+
+// received candidate rows -> candidate CSR of the owner + its (first genome, position) bitmap
+__global__ void __launch_bounds__(256) k_unpack_cand(const u64* __restrict__ hdr, const u64* __restrict__ comps, const u32* __restrict__ cand_off,
+                                                     u32 n, GenomeTable gt, u32* __restrict__ comp_pos, u8* __restrict__ comp_gs,
+                                                     u64* __restrict__ ghash, u64* __restrict__ bitmap) {
+    u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    u32 off = cand_off[j], m = cand_off[j + 1] - off;
+    ghash[j] = hdr[2 * (u64)j];
+    for (u32 k = 0; k < m; ++k) {
+        u64 w = comps[off + k];
+        u32 p = (u32)w;
+        u8 gs = (u8)(w >> 32);
+        comp_pos[off + k] = p;
+        comp_gs[off + k] = gs;
+        if (k == 0) {
+            u64 gp = gt.base_base[gs & 0x7F] + p;
+            atomicOr((unsigned long long*)&bitmap[gp >> 6], 1ull << (gp & 63));
+        }
+    }
+}
+void launch_unpack_cand(const u64* hdr, const u64* comps, const u32* cand_off, u32 n, const GenomeTable& gt, u32* comp_pos, u8* comp_gs,
+                        u64* ghash, u64* bitmap, cudaStream_t st) {
+    if (n) k_unpack_cand<<<div_up(n, 256), 256, 0, st>>>(hdr, comps, cand_off, n, gt, comp_pos, comp_gs, ghash, bitmap);
+}
+
+// component count of every accepted candidate (0 for the others)
+__global__ void __launch_bounds__(256) k_acc_m(const u8* __restrict__ cstate, const u32* __restrict__ cand_off, u32 n, u32* __restrict__ m_out) {
+    u32 c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < n) m_out[c] = cstate[c] == 1 ? cand_off[c + 1] - cand_off[c] : 0u;
+}
+void launch_acc_m(const u8* cstate, const u32* cand_off, u32 n, u32* m_out, cudaStream_t st) {
+    if (n) k_acc_m<<<div_up(n, 256), 256, 0, st>>>(cstate, cand_off, n, m_out);
+}
+
+__global__ void __launch_bounds__(256) k_pack_match(const u8* __restrict__ cstate, const u32* __restrict__ match_idx, const u32* __restrict__ acomp_off,
+                                                    const u32* __restrict__ cand_off, const u32* __restrict__ comp_pos, const u8* __restrict__ comp_gs,
+                                                    const u32* __restrict__ ext_l, const u32* __restrict__ ext_r, u32 n, u64* __restrict__ hdr,
+                                                    u64* __restrict__ comps) {
+    u32 c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n || cstate[c] != 1) return;
+    u32 j = match_idx[c];
+    u32 off = cand_off[c], m = cand_off[c + 1] - off;
+    hdr[2 * (u64)j] = (u64)ext_l[c] | ((u64)ext_r[c] << 32);
+    hdr[2 * (u64)j + 1] = m;
+    u32 o = acomp_off[c];
+    for (u32 k = 0; k < m; ++k) comps[o + k] = (u64)comp_pos[off + k] | ((u64)comp_gs[off + k] << 32);
+}
+void launch_pack_match(const u8* cstate, const u32* match_idx, const u32* acomp_off, const u32* cand_off, const u32* comp_pos, const u8* comp_gs,
+                       const u32* ext_l, const u32* ext_r, u32 n, u64* hdr, u64* comps, cudaStream_t st) {
+    if (n) k_pack_match<<<div_up(n, 256), 256, 0, st>>>(cstate, match_idx, acomp_off, cand_off, comp_pos, comp_gs, ext_l, ext_r, n, hdr, comps);
+}
+
+// gathered match rows -> "all accepted" candidate arrays of rank 0 (input of the output stage)
+__global__ void __launch_bounds__(256) k_unpack_match(const u64* __restrict__ hdr, const u64* __restrict__ comps, const u32* __restrict__ cand_off,
+                                                      u32 n, u32* __restrict__ comp_pos, u8* __restrict__ comp_gs, u32* __restrict__ ext_l,
+                                                      u32* __restrict__ ext_r, u8* __restrict__ cstate) {
+    u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    u32 off = cand_off[j], m = cand_off[j + 1] - off;
+    u64 e = hdr[2 * (u64)j];
+    ext_l[j] = (u32)e; ext_r[j] = (u32)(e >> 32);
+    cstate[j] = 1;
+    for (u32 k = 0; k < m; ++k) {
+        u64 w = comps[off + k];
+        comp_pos[off + k] = (u32)w;
+        comp_gs[off + k] = (u8)(w >> 32);
+    }
+}
+void launch_unpack_match(const u64* hdr, const u64* comps, const u32* cand_off, u32 n, u32* comp_pos, u8* comp_gs, u32* ext_l, u32* ext_r,
+                         u8* cstate, cudaStream_t st) {
+    if (n) k_unpack_match<<<div_up(n, 256), 256, 0, st>>>(hdr, comps, cand_off, n, comp_pos, comp_gs, ext_l, ext_r, cstate);
+}

@@ -32,11 +32,12 @@ __device__ __forceinline__ void st_volatile_u64(u64* p, u64 v) {
     asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-template <bool HAS_VAL>
+#define DIGIT(x) (USE_LUT ? (u32)sLut[(u32)((x) >> shift) & dmask] : ((u32)((x) >> shift) & dmask))
+template <bool HAS_VAL, bool USE_LUT>
 __global__ void __launch_bounds__(RS_NT) k_onesweep(const u64* __restrict__ kin, u64* __restrict__ kout,
                                                     const u64* __restrict__ vin, u64* __restrict__ vout, u32 n,
                                                     const u32* __restrict__ digit_base /*[256] exclusive*/,
-                                                    u64* lookback /*[tiles][256]*/, u32* ticket, int shift, u32 dmask) {
+                                                    u64* lookback /*[tiles][256]*/, u32* ticket, int shift, u32 dmask, const u8* __restrict__ lut) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u64* sKeys = reinterpret_cast<u64*>(smem_raw);                    // RS_TILE
     u64* sVals = sKeys + RS_TILE;                                      // RS_TILE when HAS_VAL
@@ -45,9 +46,11 @@ __global__ void __launch_bounds__(RS_NT) k_onesweep(const u64* __restrict__ kin,
     i64* sGlobBase = reinterpret_cast<i64*>(sTilePrefix + 256);        // 256: global index of slot 0 of digit
     __shared__ u32 sTile;
     __shared__ u32 sWarpSums[8];
+    __shared__ u8 sLut[256];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) sTile = atomicAdd(ticket, 1u);
+    if (USE_LUT && tid < 256) sLut[tid] = lut[tid];
     for (int i = tid; i < RS_NW * 256; i += RS_NT) sWarpHist[i] = 0;
     __syncthreads();
     const u32 tile = sTile;
@@ -71,19 +74,19 @@ __global__ void __launch_bounds__(RS_NT) k_onesweep(const u64* __restrict__ kin,
     const bool full = tile_n == RS_TILE;
     if (full) {
 #pragma unroll
-        for (int k = 0; k < RS_IPT; ++k) peers[k] = __match_any_sync(0xFFFFFFFFu, (u32)(key[k] >> shift) & dmask);
+        for (int k = 0; k < RS_IPT; ++k) peers[k] = __match_any_sync(0xFFFFFFFFu, DIGIT(key[k]));
     } else {
 #pragma unroll
         for (int k = 0; k < RS_IPT; ++k) {
             bool valid = wbase + k * 32 + lane < tile_n;
             u32 vm = __ballot_sync(0xFFFFFFFFu, valid);
-            u32 pm = __match_any_sync(0xFFFFFFFFu, valid ? ((u32)(key[k] >> shift) & dmask) : 0xFFFFFFFFu);
+            u32 pm = __match_any_sync(0xFFFFFFFFu, valid ? (DIGIT(key[k])) : 0xFFFFFFFFu);
             peers[k] = valid ? (pm & vm) : 0u;
         }
     }
 #pragma unroll
     for (int k = 0; k < RS_IPT; ++k) {
-        u32 d = (u32)(key[k] >> shift) & dmask;
+        u32 d = DIGIT(key[k]);
         u32 old = myHist[d];
         __syncwarp();
         u32 below = peers[k] & lt_mask;
@@ -146,7 +149,7 @@ __global__ void __launch_bounds__(RS_NT) k_onesweep(const u64* __restrict__ kin,
     for (int k = 0; k < RS_IPT; ++k) {
         u32 o = wbase + k * 32 + lane;
         if (full || o < tile_n) {
-            u32 d = (u32)(key[k] >> shift) & dmask;
+            u32 d = DIGIT(key[k]);
             slot[k] = sTilePrefix[d] + myHist[d] + rank[k];
             sKeys[slot[k]] = key[k];
         }
@@ -161,7 +164,7 @@ __global__ void __launch_bounds__(RS_NT) k_onesweep(const u64* __restrict__ kin,
     __syncthreads();
     for (u32 s = tid; s < tile_n; s += RS_NT) {
         u64 kk = sKeys[s];
-        u32 d = (u32)(kk >> shift) & dmask;
+        u32 d = DIGIT(kk);
         i64 dst = sGlobBase[d] + (i64)s;
         kout[dst] = kk;
         if (HAS_VAL) vout[dst] = sVals[s];
@@ -193,22 +196,26 @@ void launch_scan_hist(const u32* d_hist, u32* d_base, int npass, cudaStream_t st
     k_scan_hist<<<npass, 256, 0, st>>>(d_hist, d_base);
 }
 
-static bool g_attr_set[2] = {false, false};
+static bool g_attr_set[3] = {false, false, false};
 
 cudaError_t launch_onesweep(const u64* kin, u64* kout, const u64* vin, u64* vout, u32 n, const u32* d_digit_base,
-                            u64* d_lookback, u32* d_ticket, int shift, int bits, cudaStream_t st) {
+                            u64* d_lookback, u32* d_ticket, int shift, int bits, cudaStream_t st, const u8* lut) {
     if (n == 0) return cudaSuccess;
     bool hv = vin != nullptr;
+    if (lut && hv) return cudaErrorInvalidValue;
     size_t smem = radix_smem_bytes(hv);
-    if (!g_attr_set[hv]) {
-        cudaError_t e = hv ? cudaFuncSetAttribute(k_onesweep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                           : cudaFuncSetAttribute(k_onesweep<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int variant = lut ? 2 : (hv ? 1 : 0);
+    if (!g_attr_set[variant]) {
+        cudaError_t e = variant == 2 ? cudaFuncSetAttribute(k_onesweep<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                      : variant == 1 ? cudaFuncSetAttribute(k_onesweep<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                     : cudaFuncSetAttribute(k_onesweep<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        g_attr_set[hv] = true;
+        g_attr_set[variant] = true;
     }
     u32 tiles = div_up(n, RS_TILE);
     u32 dmask = (1u << bits) - 1;
-    if (hv) k_onesweep<true><<<tiles, RS_NT, smem, st>>>(kin, kout, vin, vout, n, d_digit_base, d_lookback, d_ticket, shift, dmask);
-    else k_onesweep<false><<<tiles, RS_NT, smem, st>>>(kin, kout, vin, vout, n, d_digit_base, d_lookback, d_ticket, shift, dmask);
+    if (variant == 2) k_onesweep<false, true><<<tiles, RS_NT, smem, st>>>(kin, kout, vin, vout, n, d_digit_base, d_lookback, d_ticket, shift, dmask, lut);
+    else if (variant == 1) k_onesweep<true, false><<<tiles, RS_NT, smem, st>>>(kin, kout, vin, vout, n, d_digit_base, d_lookback, d_ticket, shift, dmask, lut);
+    else k_onesweep<false, false><<<tiles, RS_NT, smem, st>>>(kin, kout, vin, vout, n, d_digit_base, d_lookback, d_ticket, shift, dmask, lut);
     return cudaGetLastError();
 }

@@ -62,6 +62,8 @@ struct ExtractArgs {
     u32* hist;      // [npass][256] or null
     int npass;
     int only_genome; // MODE 2
+    u32 tile0;       // first tile of this launch (a rank's slice of the tiles in the multi-GPU path)
+    u32 out_base;    // record index of the slice's first seed
 };
 
 __device__ __forceinline__ u64 gather_key(const SeedDev& sd, u64 hi, u64 lo) {
@@ -91,14 +93,14 @@ __global__ void __launch_bounds__(EX_NT) k_extract(ExtractArgs a, GenomeTable gt
         u32 g = 0;
         if (MODE == 2) g = a.only_genome;
         else
-            while (g + 1 < gt.nseq && blockIdx.x >= tile_first[g + 1]) ++g;
+            while (g + 1 < gt.nseq && blockIdx.x + a.tile0 >= tile_first[g + 1]) ++g;
         sG = g;
     }
     if (a.hist)
         for (int i = tid; i < a.npass * 256; i += EX_NT) sHist[i] = 0;
     __syncthreads();
     const u32 g = sG;
-    const u32 tile_in_g = (MODE == 2) ? blockIdx.x : blockIdx.x - tile_first[g];
+    const u32 tile_in_g = (MODE == 2) ? blockIdx.x : blockIdx.x + a.tile0 - tile_first[g];
     const u32 len = gt.len[g];
     const u32 nseeds = len >= (u32)sd.L ? len - sd.L + 1 : 0;
     const u32 p0 = tile_in_g * EX_TILE;
@@ -129,7 +131,7 @@ __global__ void __launch_bounds__(EX_NT) k_extract(ExtractArgs a, GenomeTable gt
         if (MODE == 2) {
             a.mers[p] = (key << kshift_la) | (u64)strand;
         } else {
-            u32 idx = gt.seed_base[g] + p;
+            u32 idx = gt.seed_base[g] + p - a.out_base;
             if (MODE == 0) {
                 a.keys[idx] = (((((key << fmt.gbits) | g) << fmt.pbits) | p) << 1) | (u64)strand;
             } else {
@@ -153,10 +155,11 @@ __global__ void __launch_bounds__(EX_NT) k_extract(ExtractArgs a, GenomeTable gt
 u32 extract_tile_size() { return EX_TILE; }
 
 void launch_extract_records(const u64* d_packed, u64* d_keys, u64* d_vals, u32* d_hist, int npass, const GenomeTable& gt,
-                            const SeedDev& sd, const RecFmt& fmt, const u32* d_tile_first, u32 n_tiles, cudaStream_t st) {
+                            const SeedDev& sd, const RecFmt& fmt, const u32* d_tile_first, u32 n_tiles, cudaStream_t st, u32 tile0,
+                            u32 out_base) {
     if (n_tiles == 0) return;
     ExtractArgs a{};
-    a.packed = d_packed; a.keys = d_keys; a.vals = d_vals; a.hist = d_hist; a.npass = npass;
+    a.packed = d_packed; a.keys = d_keys; a.vals = d_vals; a.hist = d_hist; a.npass = npass; a.tile0 = tile0; a.out_base = out_base;
     if (fmt.wide) k_extract<1><<<n_tiles, EX_NT, 0, st>>>(a, gt, sd, fmt, d_tile_first);
     else k_extract<0><<<n_tiles, EX_NT, 0, st>>>(a, gt, sd, fmt, d_tile_first);
 }

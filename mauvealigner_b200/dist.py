@@ -1,0 +1,276 @@
+"""Multi-GPU plumbing of the seed-match path: one process per GPU, torch.distributed (NCCL over
+NVLink) for the three exchanges, the library (libmauve_b200.so, mb_dist_*) for every per-rank stage.
+
+    stage 1  extract this rank's slice of seeds, partition by seed-key range      -> all-to-all of seed records
+    stage 2  sort / runs / policy over the received key range -> candidate rows,
+             partitioned by owner of their de-dup group                            -> all-to-all of rows
+    stage 3  chains / extension / resolve over the owned groups                   -> gather of match rows on rank 0
+    stage 4  rank 0: canonical order + CSR
+
+The orchestration is written over a small "fabric" interface so the same code runs (a) one rank per process over
+torch.distributed (TorchFabric) and (b) all ranks of a world inside ONE process on one GPU (LocalFabric: the
+exchanges are tensor copies), which is how the parity tests check world sizes 2..8 on a single B200.
+Nothing here touches sequence data on the host."""
+from __future__ import annotations
+
+import json
+import os
+import sys
+import time
+
+import torch
+
+from . import _lib as L
+
+
+class _DevWords:
+    """Zero-copy view of library-owned device memory as an int64 torch tensor."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<i8", "data": (int(ptr), False), "version": 2}
+
+
+def dev_words(ptr, n, device):
+    if n == 0 or not ptr:
+        return torch.empty(0, dtype=torch.int64, device=device)
+    return torch.as_tensor(_DevWords(ptr, n), device=device)
+
+
+class LocalFabric:
+    """All ranks of a world inside one process (emulation on one GPU, or any CPU tensors)."""
+
+    def __init__(self, world):
+        self.world = world
+        self.local_ranks = list(range(world))
+
+    def counts(self, send_counts):
+        # k numbers per destination: send_counts[src][dst*k:(dst+1)*k] -> recv_counts[dst][src*k:(src+1)*k]
+        k = len(send_counts[0]) // self.world
+        return [[x for s in range(self.world) for x in send_counts[s][d * k:(d + 1) * k]] for d in range(self.world)]
+
+    def words(self, sends, send_counts, recvs, recv_counts, width=1):
+        for d in range(self.world):
+            o = 0
+            for s in range(self.world):
+                n = send_counts[s][d] * width
+                so = sum(send_counts[s][:d]) * width
+                if n:
+                    recvs[d][o:o + n].copy_(sends[s][so:so + n])
+                o += n
+
+
+class TorchFabric:
+    """One rank per process over torch.distributed (NCCL for CUDA tensors, gloo for CPU tensors)."""
+
+    def __init__(self, group=None, device=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.local_ranks = [self.rank]
+        self.device = device
+
+    def counts(self, send_counts):
+        t = torch.tensor(send_counts[0], dtype=torch.int64, device=self.device)
+        k = t.numel() // self.world
+        out = torch.empty_like(t)
+        self.dist.all_to_all_single(out, t, [k] * self.world, [k] * self.world, group=self.group)
+        return [out.tolist()]
+
+    def words(self, sends, send_counts, recvs, recv_counts, width=1):
+        self.dist.all_to_all_single(recvs[0], sends[0], [c * width for c in recv_counts[0]], [c * width for c in send_counts[0]],
+                                    group=self.group)
+
+
+def find_unique(ctxs, fabric, device, nway_mask=0):
+    """MODE_UNIQUE over the ranks of `fabric`; ctxs[i] is the library context of fabric.local_ranks[i] (sequences and
+    seed already set, identical on every rank).  Leaves the canonical match CSR on rank 0's device (fetch it with
+    ctxs[...].fetch()); returns per-local-rank info dicts."""
+    W, R = fabric.world, fabric.local_ranks
+    info = [dict(rank=r) for r in R]
+    # ---- stage 1 + exchange 1: seed records by key range
+    s1 = [c.dist_extract(r, W) for c, r in zip(ctxs, R)]
+    sc = [cnt for _, cnt in s1]
+    rc = fabric.counts(sc)
+    sends = [dev_words(p, sum(cnt), device) for p, cnt in s1]
+    recvs = [dev_words(c.dist_recv_buffer(0, sum(k)), sum(k), device) for c, k in zip(ctxs, rc)]
+    fabric.words(sends, sc, recvs, rc)
+    for i, k in enumerate(rc):
+        info[i]["seeds_sent"], info[i]["seeds_received"] = sum(sc[i]), sum(k)
+    # ---- stage 2 + exchange 2: candidate rows by group owner
+    s2 = [c.dist_local(W, sum(k), nway_mask=nway_mask) for c, k in zip(ctxs, rc)]
+    both = fabric.counts([[x for pair in zip(cc, mc) for x in pair] for _, _, cc, mc in s2])
+    rcc = [b[0::2] for b in both]
+    rmc = [b[1::2] for b in both]
+    hs = [dev_words(h, 2 * sum(cc), device) for h, _, cc, _ in s2]
+    ms = [dev_words(m, sum(mc), device) for _, m, _, mc in s2]
+    hr = [dev_words(c.dist_recv_buffer(1, 2 * sum(k)), 2 * sum(k), device) for c, k in zip(ctxs, rcc)]
+    mr = [dev_words(c.dist_recv_buffer(2, sum(k)), sum(k), device) for c, k in zip(ctxs, rmc)]
+    fabric.words(hs, [cc for _, _, cc, _ in s2], hr, rcc, width=2)
+    fabric.words(ms, [mc for _, _, _, mc in s2], mr, rmc)
+    for i in range(len(R)):
+        info[i]["candidates_local"], info[i]["candidates_owned"] = sum(s2[i][2]), sum(rcc[i])
+    # ---- stage 3 + gather: accepted matches to rank 0
+    s3 = [c.dist_dedup(sum(k), sum(m)) for c, k, m in zip(ctxs, rcc, rmc)]
+    zeros = [0] * (W - 1)
+    both = fabric.counts([[x for pair in zip([nm] + zeros, [nc] + zeros) for x in pair] for _, _, nm, nc in s3])
+    gcc = [b[0::2] for b in both]
+    gmc = [b[1::2] for b in both]
+    hs = [dev_words(h, 2 * nm, device) for h, _, nm, _ in s3]
+    ms = [dev_words(m, nc, device) for _, m, _, nc in s3]
+    hr = [dev_words(c.dist_recv_buffer(3, 2 * sum(k)), 2 * sum(k), device) for c, k in zip(ctxs, gcc)]
+    mr = [dev_words(c.dist_recv_buffer(4, sum(k)), sum(k), device) for c, k in zip(ctxs, gmc)]
+    fabric.words(hs, [[nm] + zeros for _, _, nm, _ in s3], hr, gcc, width=2)
+    fabric.words(ms, [[nc] + zeros for _, _, _, nc in s3], mr, gmc)
+    # ---- stage 4 on rank 0
+    for i, r in enumerate(R):
+        info[i]["matches_owned"] = s3[i][2]
+        if r == 0:
+            ctxs[i].dist_output(sum(gcc[i]), sum(gmc[i]))
+            info[i]["matches"] = sum(gcc[i])
+    return info
+
+
+def find_unique_emulated(seqs, pattern, world, device=0, nway_mask=0):
+    """All `world` ranks inside this process on one GPU (parity tests): returns rank 0's result dict."""
+    from .finder import Context
+    dev = torch.device("cuda", device)
+    ctxs = [Context(device) for _ in range(world)]
+    try:
+        for c in ctxs:
+            for s in seqs:
+                c.add_sequence(s)
+            c.set_seed(pattern)
+        info = find_unique(ctxs, LocalFabric(world), dev, nway_mask=nway_mask)
+        torch.cuda.synchronize(dev)
+        res = ctxs[0].fetch()
+        res["info"] = info
+        return res
+    finally:
+        for c in ctxs:
+            c.close()
+
+
+# ------------------------------------------------------------------------------------------ bench (N > 1)
+def bench_main(args, CONFIG_NAMES, config_params, peaks, ClockSampler):
+    """bench.py --gpus N under torchrun: strong scaling of one configuration (C5 by default) over N ranks."""
+    import torch.distributed as dist
+    import mauvealigner_b200 as mb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if not dist.is_initialized():
+        dist.init_process_group(backend="nccl", device_id=dev)
+    W = max(3, args.warmup)
+    config = args.config
+    pattern, mode, kw = config_params(mb, config)
+    if mode != mb.MODE_UNIQUE:
+        raise SystemExit("the multi-GPU path covers MODE_UNIQUE (config 1, 2, 5)")
+    seqs = mb.synth_genomes(config, args.scale)
+    bp = sum(len(s) for s in seqs)
+    ctx = mb.Context(local)
+    stream = torch.cuda.current_stream(dev)
+    ctx.set_stream(stream.cuda_stream)
+    ctx.set_seed(pattern)
+    fabric = TorchFabric(device=dev)
+
+    dev_ascii = [torch.from_numpy(s).to(dev) for s in seqs]
+    ctx.clear_sequences()
+    for t in dev_ascii:
+        ctx.add_sequence_device(t.data_ptr(), t.numel())
+    del dev_ascii
+    torch.cuda.synchronize()
+
+    def step():
+        return find_unique([ctx], fabric, dev)
+
+    for _ in range(W):
+        step()
+    sampler = ClockSampler(local)
+    sampler.start()
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        info = step()
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    ms = torch.tensor([max(ev0.elapsed_time(ev1), 0.0)], device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(ms.item()) / args.steps
+    st = ctx.stats()
+    stage = ctx.dist_stage_ms()
+    launches = torch.tensor([float(st["kernel_launches"])], device=dev)
+    dist.all_reduce(launches, op=dist.ReduceOp.SUM)
+    res = ctx.fetch(copy=False) if rank == 0 else None
+    n_matches = res["n_matches"] if res else 0
+
+    # ---- e2e: pinned host ASCII on every rank -> C ABI stages + exchanges -> host CSR on rank 0
+    pinned = [torch.from_numpy(s).pin_memory() for s in seqs]
+
+    def e2e_step():
+        ctx.clear_sequences()
+        for t in pinned:
+            ctx.add_sequence_ptr(t.data_ptr(), t.numel())
+        find_unique([ctx], fabric, dev)
+        return ctx.fetch(copy=False) if rank == 0 else None
+
+    e2e_step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r = e2e_step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    e2e_ms = torch.tensor([(time.perf_counter() - t0) * 1e3 / args.steps], device=dev)
+    dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_ms = float(e2e_ms.item())
+    st2 = ctx.stats()
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        R = st["record_bytes"]
+        radix_ms, radix_launches = st["ms_radix_kernels"], st["radix_launches"]
+        n_local = info[0]["seeds_received"]
+        roofline = None
+        if radix_launches:
+            avg_ms = radix_ms / radix_launches
+            alg = 2.0 * R * n_local
+            ach = alg / (avg_ms * 1e-3) / 1e9
+            roofline = {"bound": "hbm", "kernel": "k_onesweep (one LSD radix pass over this rank's seed records; rank 0)", "achieved": ach,
+                        "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                        "algorithmic_bytes_per_launch": alg, "avg_launch_ms": avg_ms, "launches_per_step": radix_launches}
+        P = (2 * mb.seed_weight(pattern) + 7) // 8
+        b_alg = 0.25 + R * (3 + 2 * P)
+        path = {"b_alg_bytes_per_bp": b_alg, "achieved": b_alg * bp / (ms_per_step * 1e-3) / 1e9, "unit": "GB/s (all GPUs)"}
+        path["frac"] = path["achieved"] / (peak * world)
+        line = {
+            "metric": "seed-to-multi-MUM input throughput", "value": bp / (ms_per_step * 1e-3) / 1e9, "unit": "Gbp/s", "n_gpus": world,
+            "steps": args.steps, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u64", "data": "synthetic",
+            "config": {"workload": CONFIG_NAMES[config], "bp_per_step": bp, "n_genomes": len(seqs), "seed_pattern": mb.seeds.pattern_text(pattern),
+                       "scale": args.scale, "parallelism": f"key-range x{world} (seeds), group-hash x{world} (de-dup), rank-0 output",
+                       "l2": "inputs larger than L2", "n_matches": n_matches},
+            "roofline": roofline, "path_roofline": path, "cpu_baseline": None,
+            "e2e": {"value": bp / (e2e_ms * 1e-3) / 1e9, "unit": "Gbp/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": st2["h2d_bytes"] * world,
+                    "d2h_bytes_per_step": st2["d2h_bytes"]},
+            "gpu_launches": int(launches.item()) * args.steps, "stages_ms_rank0": {k: round(v, 4) for k, v in stage.items()},
+            "rank0": {k: v for k, v in info[0].items()}, "wall_ms_per_step": wall_ms / args.steps, "clocks": sampler.summary(),
+        }
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    dist.barrier()
+    dist.destroy_process_group()

@@ -119,6 +119,42 @@ class Context:
                     comp_start=arr(r.comp_start, nc), unique_mers=int(r.unique_mers),
                     unique_mers_per_seq=arr(r.unique_mers_per_seq, ns))
 
+    # ---- multi-GPU stages (include/mauve_b200.h "multi-GPU path"; driven by mauvealigner_b200/dist.py)
+    def dist_extract(self, rank, world):
+        """-> (device pointer of the partitioned seed records, records per destination rank)"""
+        ptr = C.c_void_p()
+        counts = (C.c_uint64 * world)()
+        _check(self._h, L.lib().mb_dist_extract(self._h, int(rank), int(world), C.byref(ptr), counts))
+        return ptr.value or 0, [int(x) for x in counts]
+
+    def dist_recv_buffer(self, which, n_words):
+        ptr = C.c_void_p()
+        _check(self._h, L.lib().mb_dist_recv_buffer(self._h, int(which), int(n_words), C.byref(ptr)))
+        return ptr.value or 0
+
+    def dist_local(self, world, n_recv, mode=L.MODE_UNIQUE, nway_mask=0):
+        """-> (headers pointer, components pointer, rows per owner, component words per owner)"""
+        p = self._params(mode, 2, 1000, False, nway_mask)
+        hdr, comps = C.c_void_p(), C.c_void_p()
+        cc, mc = (C.c_uint64 * world)(), (C.c_uint64 * world)()
+        _check(self._h, L.lib().mb_dist_local(self._h, C.byref(p), int(n_recv), cc, mc, C.byref(hdr), C.byref(comps)))
+        return hdr.value or 0, comps.value or 0, [int(x) for x in cc], [int(x) for x in mc]
+
+    def dist_dedup(self, n_cand, n_comp):
+        """-> (headers pointer, components pointer, accepted matches, their component words)"""
+        hdr, comps = C.c_void_p(), C.c_void_p()
+        nm, nc = C.c_uint64(0), C.c_uint64(0)
+        _check(self._h, L.lib().mb_dist_dedup(self._h, int(n_cand), int(n_comp), C.byref(nm), C.byref(nc), C.byref(hdr), C.byref(comps)))
+        return hdr.value or 0, comps.value or 0, int(nm.value), int(nc.value)
+
+    def dist_output(self, n_match, n_comp):
+        _check(self._h, L.lib().mb_dist_output(self._h, int(n_match), int(n_comp)))
+
+    def dist_stage_ms(self):
+        out = (C.c_float * 4)()
+        _check(self._h, L.lib().mb_dist_stage_ms(self._h, out))
+        return dict(extract_partition=out[0], sort=out[1], buckets=out[2], dedup=out[3])
+
     def stats(self):
         s = L.MbStats()
         _check(self._h, L.lib().mb_get_stats(self._h, C.byref(s)))

@@ -1,0 +1,77 @@
+"""Host-side logic of the multi-GPU path on CPU: the two fabrics must deliver the same words.  TorchFabric runs as
+two real processes over gloo (world_size 2); LocalFabric is the in-process emulation the GPU parity tests use."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from mauvealigner_b200.dist import LocalFabric, TorchFabric
+
+
+def _payload(world):
+    rng = np.random.default_rng(3)
+    counts = [[int(rng.integers(0, 50)) for _ in range(world)] for _ in range(world)]
+    counts[1][0] = 0
+    sends = [torch.from_numpy(rng.integers(-2 ** 62, 2 ** 62, size=2 * sum(c), dtype=np.int64)) for c in counts]
+    return counts, sends
+
+
+def _expected(world, counts, sends, width):
+    fab = LocalFabric(world)
+    rc = fab.counts(counts)
+    recvs = [torch.zeros(width * sum(k), dtype=torch.int64) for k in rc]
+    fab.words(sends, counts, recvs, rc, width=width)
+    return rc, recvs
+
+
+def test_local_fabric_routes_by_destination():
+    counts, sends = _payload(3)
+    rc, recvs = _expected(3, counts, sends, 2)
+    for d in range(3):
+        parts = []
+        for s in range(3):
+            o = 2 * sum(counts[s][:d])
+            parts.append(sends[s][o:o + 2 * counts[s][d]])
+        assert torch.equal(recvs[d], torch.cat(parts))
+        assert rc[d] == [counts[s][d] for s in range(3)]
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        counts, sends = _payload(world)
+        fab = TorchFabric()
+        rc = fab.counts([counts[rank]])
+        recv = torch.zeros(2 * sum(rc[0]), dtype=torch.int64)
+        fab.words([sends[rank]], [counts[rank]], [recv], rc, width=2)
+        exp_rc, exp = _expected(world, counts, sends, 2)
+        ok = rc[0] == exp_rc[rank] and torch.equal(recv, exp[rank])
+        # interleaved pair counts, as exchanged between stage 2 and 3
+        pairs = [x for p in zip(counts[rank], [c + 1 for c in counts[rank]]) for x in p]
+        both = fab.counts([pairs])[0]
+        ok = ok and both[0::2] == exp_rc[rank] and both[1::2] == [c + 1 for c in exp_rc[rank]]
+        out.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_torch_fabric_gloo_world2():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=100) for _ in range(2))
+    for p in procs:
+        p.join(timeout=30)
+    assert res == {0: True, 1: True}
