@@ -156,7 +156,8 @@ def main():
     seqs = mb.synth_genomes(config, args.scale)
     bp = sum(len(s) for s in seqs)
     ctx = mb.Context(local)
-    stream = torch.cuda.current_stream(dev)
+    stream = torch.cuda.Stream(dev)  # explicit: the library launches on it and the timing events are recorded on it
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
     ctx.set_seed(pattern)
 

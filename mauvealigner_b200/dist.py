@@ -137,14 +137,17 @@ def find_unique_emulated(seqs, pattern, world, device=0, nway_mask=0):
     from .finder import Context
     dev = torch.device("cuda", device)
     ctxs = [Context(device) for _ in range(world)]
+    stream = torch.cuda.Stream(dev)  # one explicit stream for the library and for the exchange copies
     try:
-        for c in ctxs:
-            for s in seqs:
-                c.add_sequence(s)
-            c.set_seed(pattern)
-        info = find_unique(ctxs, LocalFabric(world), dev, nway_mask=nway_mask)
-        torch.cuda.synchronize(dev)
-        res = ctxs[0].fetch()
+        with torch.cuda.stream(stream):
+            for c in ctxs:
+                c.set_stream(stream.cuda_stream)
+                for s in seqs:
+                    c.add_sequence(s)
+                c.set_seed(pattern)
+            info = find_unique(ctxs, LocalFabric(world), dev, nway_mask=nway_mask)
+            stream.synchronize()
+            res = ctxs[0].fetch()
         res["info"] = info
         return res
     finally:
@@ -173,7 +176,10 @@ def bench_main(args, CONFIG_NAMES, config_params, peaks, ClockSampler):
     seqs = mb.synth_genomes(config, args.scale)
     bp = sum(len(s) for s in seqs)
     ctx = mb.Context(local)
-    stream = torch.cuda.current_stream(dev)
+    # one explicit stream for the library kernels, the NCCL exchanges and the timing events (a NULL handle would make
+    # the library create a private stream the exchanges are not ordered against)
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
     ctx.set_seed(pattern)
     fabric = TorchFabric(device=dev)
