@@ -1,0 +1,66 @@
+"""Committed golden vectors (tests/golden/seed_match_golden.json, made by tests/golden/make_golden.py).
+CPU: the oracle must still reproduce them.  GPU: the CUDA path (through the C ABI) must reproduce them bit for bit."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+GOLD = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "seed_match_golden.json")))
+KEYS = ("length", "comp_off", "comp_seq", "comp_start")
+
+
+def _check(res, case):
+    assert int(res["n_matches"]) == case["n_matches"], case["name"]
+    for k in KEYS:
+        assert [int(x) for x in res[k]] == case[k], (case["name"], k)
+    assert int(res["unique_mers"]) == case["unique_mers"], case["name"]
+
+
+@pytest.mark.parametrize("case", GOLD["cases"], ids=[c["name"] for c in GOLD["cases"]])
+def test_oracle_reproduces_golden(case):
+    res = O.find(case["seqs"], case["pattern"], case["mode"], **case["params"])
+    _check(res, case)
+    assert [int(x) for x in res["unique_mers_per_seq"]] == case["unique_mers_per_seq"]
+
+
+def test_oracle_mers_and_sml_golden():
+    g = GOLD["mers"]
+    assert [int(x) for x in O.mers(g["seq"], g["pattern"])] == g["mers"]
+    assert [int(x) for x in O.sml(g["seq"], g["pattern"])] == g["sml"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", GOLD["cases"], ids=[c["name"] for c in GOLD["cases"]])
+def test_cuda_reproduces_golden(case):
+    import mauvealigner_b200 as mb
+    ctx = mb.Context(0)
+    try:
+        for s in case["seqs"]:
+            ctx.add_sequence(s)
+        ctx.set_seed(case["pattern"])
+        if case["mode"] == O.MODE_SEED_ENUM and len(case["seqs"]) != 1:
+            pytest.skip("SeedMatchEnumerator takes one sequence")
+        res = ctx.find(case["mode"], **case["params"])
+        _check(res, case)
+        if case["mode"] == O.MODE_UNIQUE_COUNT:
+            assert [int(x) for x in res["unique_mers_per_seq"]] == case["unique_mers_per_seq"]
+    finally:
+        ctx.close()
+
+
+@pytest.mark.gpu
+def test_cuda_mers_and_sml_golden():
+    import mauvealigner_b200 as mb
+    g = GOLD["mers"]
+    ctx = mb.Context(0)
+    try:
+        ctx.add_sequence(g["seq"])
+        ctx.set_seed(g["pattern"])
+        assert [int(x) for x in ctx.mers(0, len(g["seq"]))] == g["mers"]
+        ctx.find(mb.MODE_UNIQUE_COUNT)
+        assert [int(x) for x in ctx.sml(0, len(g["seq"]))] == g["sml"]
+    finally:
+        ctx.close()
