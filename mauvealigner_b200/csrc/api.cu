@@ -476,9 +476,7 @@ int mbi_reserve_candidates(mb_ctx* c, u32 n_cand, u32 n_ccomp, u64 bases) {
     TRY(c->reserve(c->s_cand, nc * 4));
     TRY(c->reserve(c->sort_kA, nc * 8));
     TRY(c->reserve(c->sort_kB, nc * 8));
-    TRY(c->reserve(c->cand_at, nc * 4));
-    TRY(c->reserve(c->slot_gp, nc * 8));
-    TRY(c->reserve(c->slot_hash, nc * 8));
+    TRY(c->reserve(c->slot_gp, nc * 16));
     TRY(c->reserve(c->link_bits, nc / 8 + 16));
     TRY(c->reserve(c->chain_min, nc * 4));
     TRY(c->reserve(c->cstate, nc));
@@ -517,7 +515,7 @@ int mbi_dedup(mb_ctx* c, u32 n_cand, u64 bases) {
     da.packed = c->packed.as<u64>(); da.n_cand = n_cand;
     da.cand_off = c->cand_off.as<u32>(); da.comp_pos = c->comp_pos.as<u32>(); da.comp_gs = c->comp_gs.as<u8>();
     da.bitmap = c->bitmap.as<u64>(); da.bmrank = c->bmrank.as<u32>(); da.ghash = c->ghash.as<u64>();
-    da.cand_at = c->cand_at.as<u32>(); da.slot_gp = c->slot_gp.as<u64>(); da.slot_hash = c->slot_hash.as<u64>();
+    da.slot_rec = c->slot_gp.as<ulonglong2>();
     da.link_bits = c->link_bits.as<u8>(); da.chain_min = c->chain_min.as<u32>();
     da.rep_bits = c->rep_bits.as<u64>(); da.rep_rank = c->rep_rank.as<u32>();
     da.cstate = c->cstate.as<u8>(); da.live_bits = c->live_bits.as<u64>(); da.cov_bits = c->covered.as<u64>();

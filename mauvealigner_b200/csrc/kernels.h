@@ -76,9 +76,7 @@ struct DedupArgs {
     const u64* bitmap; const u32* bmrank;   // candidates by (first genome, position): bitmap over global bases + word ranks
     const u64* ghash;   // candidate -> hash of its D16 group (genome set, strands, diagonal)
     // per slot (candidates in (first genome, position) order)
-    u32* cand_at;       // slot -> candidate
-    u64* slot_gp;       // slot -> global base index of the candidate's first component
-    u64* slot_hash;     // slot -> group hash
+    ulonglong2* slot_rec; // slot -> (group hash | adjacent-to-previous-slot bit, candidate)
     u8* link_bits;      // one bit per slot: continues the chain of the previous slot
     u32* chain_min;     // slot -> lowest rank among the earlier members of its chain
     u64* rep_bits;      // one bit per slot: lowest rank of its chain

@@ -49,18 +49,23 @@ __device__ __forceinline__ bool same_group(const DedupArgs& a, u32 j, u32 e) {
 }
 
 // ---- slots ---------------------------------------------------------------------------------------
-// candidate -> slot (rank of its first-genome position among all candidates), and the slot-ordered
-// copies (candidate id, global position, group hash) the chain and resolve steps stream over.
+// candidate -> slot (rank of its first-genome position among all candidates).  One 16-byte record per
+// slot: x = group hash with bit 0 replaced by "the previous base of the genome holds a candidate too"
+// (then that candidate is slot s-1), y = candidate id.  One scattered 16-byte store per candidate.
+#define HASH_MASK (~1ull)
 __global__ void __launch_bounds__(256) k_slot_scatter(DedupArgs a, GenomeTable gt) {
     u32 c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= a.n_cand) return;
     u32 off = a.cand_off[c];
     u32 g = a.comp_gs[off] & 0x7F;
     u64 gp = gt.base_base[g] + a.comp_pos[off];
-    u32 s = slot_rank(a.bitmap, a.bmrank, gp);
-    a.cand_at[s] = c;
-    a.slot_gp[s] = gp;
-    a.slot_hash[s] = a.ghash[c];
+    u64 w = a.bitmap[gp >> 6];
+    u32 s = a.bmrank[gp >> 6] + (u32)__popcll(w & ((1ull << (gp & 63)) - 1));
+    // a candidate never sits on the last L-1 bases of a genome, so base gp-1 belongs to the same genome
+    // whenever it holds a candidate
+    u64 adj = 0;
+    if (gp > 0) adj = (gp & 63) ? (w >> ((gp & 63) - 1)) & 1 : (a.bitmap[(gp >> 6) - 1] >> 63) & 1;
+    a.slot_rec[s] = make_ulonglong2((a.ghash[c] & HASH_MASK) | adj, (u64)c);
 }
 
 // ---- chains: segmented min-scans over the slots ---------------------------------------------------
@@ -112,26 +117,22 @@ __global__ void __launch_bounds__(CH_NT) k_chain(DedupArgs a, u64* status, u32* 
     const u32 sbase = tile * CH_TILE + (REV ? (CH_NT - 1 - tid) : tid) * CH_IPT;
     u32 v[CH_IPT];
     bool f[CH_IPT];
-    u64 gp[CH_IPT + 1], hs[CH_IPT + 1];
+    u64 hs[CH_IPT + 1];
     if (!REV) {
         // link of slot s: same group as slot s-1 and exactly one base further
         const u32 s0 = sbase;
-#pragma unroll
-        for (int k = 0; k <= CH_IPT; ++k) {
-            i64 s = (i64)s0 - 1 + k;
-            bool ok = s >= 0 && s < (i64)n;
-            gp[k] = ok ? a.slot_gp[s] : ~0ull - 1;
-            hs[k] = ok ? a.slot_hash[s] : 0;
-        }
+        hs[0] = (s0 > 0 && s0 - 1 < n) ? a.slot_rec[s0 - 1].x : 0;
         u32 linkbits = 0;
 #pragma unroll
         for (int k = 0; k < CH_IPT; ++k) {
             u32 s = s0 + k;
             bool valid = s < n;
-            v[k] = valid ? a.cand_at[s] : INF32;
-            bool link = valid && s > 0 && gp[k] + 1 == gp[k + 1] && hs[k] == hs[k + 1];
+            ulonglong2 r = valid ? a.slot_rec[s] : make_ulonglong2(0, INF32);
+            hs[k + 1] = r.x;
+            v[k] = (u32)r.y;
+            bool link = valid && s > 0 && (r.x & 1) && (hs[k] & HASH_MASK) == (r.x & HASH_MASK);
 #ifdef MB_VERIFY_LINKS
-            if (link) link = same_group(a, a.cand_at[s - 1], v[k]);
+            if (link) link = same_group(a, (u32)a.slot_rec[s - 1].y, v[k]);
 #endif
             f[k] = !link;
             linkbits |= (link ? 1u : 0u) << k;
@@ -146,7 +147,7 @@ __global__ void __launch_bounds__(CH_NT) k_chain(DedupArgs a, u64* status, u32* 
         for (int k = 0; k < CH_IPT; ++k) {
             u32 s = sbase + (CH_IPT - 1 - k);
             bool valid = s < n;
-            v[k] = valid ? a.cand_at[s] : INF32;
+            v[k] = valid ? (u32)a.slot_rec[s].y : INF32;
             bool link_next = valid && s + 1 < n && ((lb >> (CH_IPT - k)) & 1u); // slot s+1 continues s
             f[k] = !link_next;
         }
@@ -208,7 +209,7 @@ __global__ void __launch_bounds__(256) k_rep_keys(DedupArgs a, u64* __restrict__
     u64 w = a.rep_bits[s >> 6];
     if (!((w >> (s & 63)) & 1)) return;
     u32 idx = a.rep_rank[s >> 6] + (u32)__popcll(w & ((1ull << (s & 63)) - 1));
-    skey[idx] = ((a.slot_hash[s] >> 48) << 32) | s;
+    skey[idx] = ((a.slot_rec[s].x >> 48) << 32) | s;
 }
 
 // ---- extension -----------------------------------------------------------------------------------
@@ -496,35 +497,143 @@ __device__ __forceinline__ void extent_range(const DedupArgs& a, const GenomeTab
     }
 }
 
-// ---- extend: one thread per rep; long ones are parked for the warp kernel
+// ---- extend: a warp takes 32 consecutive reps.  Lane j owns rep j's state; the (rep, component) pairs
+// of the warp are spread over all lanes, so every lane builds exactly one component-vs-first mismatch
+// map per step whatever the multiplicities are; maps are OR-ed per rep in shared memory.  Rounds:
+// centred chunk, then further chunks to the left, then to the right, for the reps that still need
+// them (the pairs of the remaining reps fill the lanes again).  Reps that need more than
+// DD_EXT_ROUNDS chunks are parked for the warp-per-rep kernel.
+#define DD_EXT_ROUNDS 10
+enum { ST_CENTER = 0, ST_LEFT = 1, ST_RIGHT = 2, ST_DONE = 3 };
+
 __global__ void __launch_bounds__(DD_NT) k_extend(DedupArgs a, GenomeTable gt, SeedDev sd) {
+    __shared__ u32 sMap[DD_NT / 32][32][4];
+    __shared__ u32 sRoom[DD_NT / 32][32][2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u32 i = blockIdx.x * DD_NT + threadIdx.x;
     const bool valid = i < a.n_rep;
     u32 live = __ballot_sync(0xFFFFFFFFu, valid);
-    if ((threadIdx.x & 31) == 0) reinterpret_cast<u32*>(a.live_bits)[i >> 5] = live;
-    bool is_long = false;
+    if (lane == 0) reinterpret_cast<u32*>(a.live_bits)[i >> 5] = live;
+    const u32 L = sd.L;
+    u32 c = 0, off = 0, m = 1, p0 = 0, g0 = 0;
     if (valid) {
-        u32 s = (u32)a.s_key[i];
-        u32 c = a.cand_at[s];
-        a.s_hash[i] = a.slot_hash[s];
+        ulonglong2 r = a.slot_rec[(u32)a.s_key[i]];
+        c = (u32)r.y;
+        a.s_hash[i] = r.x & HASH_MASK;
         a.s_cand[i] = c;
         a.minrank[i] = INF32;
-        u32 off = a.cand_off[c], m = a.cand_off[c + 1] - off;
-        const u32* cpos = a.comp_pos + off;
-        const u8* cgs = a.comp_gs + off;
-        is_long = sd.L > 32;
-        if (!is_long) {
-            u32 room_l = INF32, room_r = INF32;
-            for (u32 k = 0; k < m; ++k) candidate_room(gt, sd.L, cpos, cgs, k, room_l, room_r);
-            u32 el = 0, er = 0;
-            if (!extend_thread(a.packed, gt, sd, cpos, cgs, m, room_l, room_r, el, er)) is_long = true;
-            else {
-                a.ext_l[c] = el; a.ext_r[c] = er;
-                u32 ilo, ihi;
-                extent_range(a, gt, i, c, el, er, ilo, ihi);
-                a.rng_lo[i] = ilo; a.rng_hi[i] = ihi;
+        off = a.cand_off[c]; m = a.cand_off[c + 1] - off;
+        p0 = a.comp_pos[off]; g0 = a.comp_gs[off] & 0x7F;
+    }
+    if (L > 32) { // uniform: window-by-window warp kernel only
+        wl_push(a.wl_long, a.ctr + 6, valid, i);
+        return;
+    }
+    const u64 care = sd.mask_hi & 0x5555555555555555ull;
+    const u32 per_chunk = (3 * L <= 65) ? 2 : 1;
+    int st = valid ? (3 * L <= 64 ? ST_CENTER : ST_LEFT) : ST_DONE;
+    bool rj = true; // the right side still has to be walked
+    u32 b = 0, el = 0, er = 0, room_l = INF32, room_r = INF32;
+    {
+        u32 rl = INF32, rr = INF32;
+        if (valid) { u32 lroom = p0, rroom = gt.len[g0] - L - p0; rl = lroom; rr = rroom; } // component 0 is forward
+        sRoom[warp][lane][0] = rl; sRoom[warp][lane][1] = rr;
+    }
+    for (int round = 0; round < DD_EXT_ROUNDS; ++round) {
+        const bool want = st != ST_DONE;
+        if (!__any_sync(0xFFFFFFFFu, want)) break;
+        const int o_lo = st == ST_CENTER ? -(int)L : (int)chunk_lo(st == ST_LEFT ? -1 : +1, b, L);
+        const u32 np = want ? m - 1 : 0;
+        u32 incl = np;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            u32 y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += y;
+        }
+        const u32 start = incl - np, T = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        u64 a0 = 0, b0 = 0;
+        if (want) oriented_bases64(a.packed, gt, L, g0, p0, false, o_lo, a0, b0);
+        sMap[warp][lane][0] = 0; sMap[warp][lane][1] = 0; sMap[warp][lane][2] = 0; sMap[warp][lane][3] = 0;
+        __syncwarp();
+        for (u32 base = 0; base < T; base += 32) {
+            const u32 p = base + lane;
+            const bool act = p < T;
+            u32 j = 0; // owner of pair p: the last lane whose first pair index is <= p
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1) {
+                u32 sv = __shfl_sync(0xFFFFFFFFu, start, (j + step) & 31);
+                if (j + step < 32 && sv <= p) j += step;
+            }
+            const u32 k = p - __shfl_sync(0xFFFFFFFFu, start, j) + 1;
+            const u32 offj = __shfl_sync(0xFFFFFFFFu, off, j);
+            const int oj = __shfl_sync(0xFFFFFFFFu, o_lo, j);
+            const u64 a0j = __shfl_sync(0xFFFFFFFFu, a0, j), b0j = __shfl_sync(0xFFFFFFFFu, b0, j);
+            if (act) {
+                u8 gs = a.comp_gs[offj + k];
+                u32 pk = a.comp_pos[offj + k];
+                u64 A, B;
+                oriented_bases64(a.packed, gt, L, gs & 0x7F, pk, gs & 0x80, oj, A, B);
+                u64 xa = spread_nz(A ^ a0j), xb = spread_nz(B ^ b0j);
+                if (xa >> 32) atomicOr(&sMap[warp][j][0], (u32)(xa >> 32));
+                if ((u32)xa) atomicOr(&sMap[warp][j][1], (u32)xa);
+                if (xb >> 32) atomicOr(&sMap[warp][j][2], (u32)(xb >> 32));
+                if ((u32)xb) atomicOr(&sMap[warp][j][3], (u32)xb);
+                if (round == 0) {
+                    u32 len = gt.len[gs & 0x7F];
+                    u32 lroom = pk, rroom = len - L - pk;
+                    bool rev = gs & 0x80;
+                    atomicMin(&sRoom[warp][j][0], rev ? rroom : lroom);
+                    atomicMin(&sRoom[warp][j][1], rev ? lroom : rroom);
+                }
             }
         }
+        __syncwarp();
+        if (round == 0) { room_l = sRoom[warp][lane][0]; room_r = sRoom[warp][lane][1]; }
+        if (want) {
+            const u64 xa = ((u64)sMap[warp][lane][0] << 32) | sMap[warp][lane][1], xb = ((u64)sMap[warp][lane][2] << 32) | sMap[warp][lane][3];
+            if (st == ST_CENTER) {
+                // chunk index i <-> match offset i - L: first jump windows at 0 (left) and 2L (right), single-step
+                // windows s at L - s (left) and L + s (right)
+                const bool lj = room_l >= L && !(map_at(xa, xb, 0) & care);
+                rj = room_r >= L && !(map_at(xa, xb, 2 * L) & care);
+                if (!lj) {
+                    u32 maxs = min(L, room_l), sdone = 0;
+                    for (u32 s = 1; s <= maxs; ++s) {
+                        if (map_at(xa, xb, L - s) & care) break;
+                        sdone = s;
+                    }
+                    el = sdone;
+                }
+                if (!rj) {
+                    u32 maxs = min(L, room_r), sdone = 0;
+                    for (u32 s = 1; s <= maxs; ++s) {
+                        if (map_at(xa, xb, L + s) & care) break;
+                        sdone = s;
+                    }
+                    er = sdone;
+                }
+                b = 1; // the first jump of the side walked next is known to succeed
+                st = lj ? ST_LEFT : (rj ? ST_RIGHT : ST_DONE);
+            } else if (st == ST_LEFT) {
+                u32 out = 0;
+                if (walk_chunk(xa, xb, care, -1, L, room_l, room_l / L, per_chunk, b, out)) {
+                    el = out;
+                    b = (3 * L <= 64) ? 1 : 0;
+                    st = rj ? ST_RIGHT : ST_DONE;
+                }
+            } else {
+                u32 out = 0;
+                if (walk_chunk(xa, xb, care, +1, L, room_r, room_r / L, per_chunk, b, out)) { er = out; st = ST_DONE; }
+            }
+        }
+        __syncwarp();
+    }
+    const bool is_long = valid && st != ST_DONE;
+    if (valid && !is_long) {
+        a.ext_l[c] = el; a.ext_r[c] = er;
+        u32 ilo, ihi;
+        extent_range(a, gt, i, c, el, er, ilo, ihi);
+        a.rng_lo[i] = ilo; a.rng_hi[i] = ihi;
     }
     wl_push(a.wl_long, a.ctr + 6, is_long, i);
 }

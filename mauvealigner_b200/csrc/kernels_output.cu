@@ -78,19 +78,42 @@ __global__ void __launch_bounds__(256) k_uniq_ncomp(OutputArgs a, const u64* __r
     a.ncomp[j] = a.cand_off[c + 1] - a.cand_off[c];
 }
 
+// A warp takes 32 consecutive matches of the final order; their components are consecutive in the CSR, so
+// the lanes walk the component index space together and every store is coalesced.
 __global__ void __launch_bounds__(256) k_uniq_gather(OutputArgs a, const u64* __restrict__ sval, u32 L) {
-    u32 j = blockIdx.x * blockDim.x + threadIdx.x;
-    u32 n = (u32)*a.n_matches_ptr;
-    if (j >= n) return;
-    u32 c = (u32)sval[j];
-    MView v = mview(a, c);
-    u64 o = a.out_off[j];
-    a.out_len[j] = L + v.el + v.er;
-    for (u32 k = 0; k < v.m; ++k) {
-        u8 gs = a.comp_gs[v.off + k];
-        i64 s = (i64)abs_start(a, v, k);
-        a.out_seq[o + k] = gs & 0x7F;
-        a.out_start[o + k] = (gs & 0x80) ? -s : s;
+    const int lane = threadIdx.x & 31;
+    const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 n = (u32)*a.n_matches_ptr;
+    const bool valid = j < n;
+    MView v{0, 0, 0, 0};
+    u64 o = 0;
+    if (valid) {
+        u32 c = (u32)sval[j];
+        v = mview(a, c);
+        o = a.out_off[j];
+        a.out_len[j] = L + v.el + v.er;
+    }
+    const u64 o_first = __shfl_sync(0xFFFFFFFFu, o, 0);
+    u32 start = valid ? (u32)(o - o_first) : 0xFFFFFFFFu;
+    const u32 nv = __popc(__ballot_sync(0xFFFFFFFFu, valid));
+    const u32 last_start = __shfl_sync(0xFFFFFFFFu, start, nv ? nv - 1 : 0), last_m = __shfl_sync(0xFFFFFFFFu, v.m, nv ? nv - 1 : 0);
+    const u32 T = nv ? last_start + last_m : 0;
+    for (u32 base = 0; base < T; base += 32) {
+        const u32 p = base + lane;
+        u32 t = 0; // owner of component p: the last lane whose first component index is <= p
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+            u32 sv = __shfl_sync(0xFFFFFFFFu, start, (t + step) & 31);
+            if (t + step < 32 && sv <= p) t += step;
+        }
+        const u32 k = p - __shfl_sync(0xFFFFFFFFu, start, t);
+        const u32 off = __shfl_sync(0xFFFFFFFFu, v.off, t), el = __shfl_sync(0xFFFFFFFFu, v.el, t), er = __shfl_sync(0xFFFFFFFFu, v.er, t);
+        if (p < T) {
+            u8 gs = a.comp_gs[off + k];
+            i64 s = (i64)(a.comp_pos[off + k] - ((gs & 0x80) ? er : el) + 1);
+            a.out_seq[o_first + p] = gs & 0x7F;
+            a.out_start[o_first + p] = (gs & 0x80) ? -s : s;
+        }
     }
 }
 
