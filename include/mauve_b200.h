@@ -152,6 +152,8 @@ int mb_get_stats(mb_ctx* ctx, mb_stats* out);
 const char* mb_strerror(int code);
 const char* mb_last_cuda_error(mb_ctx* ctx);
 int mb_device_count(void);
+/* tuning aid: mean device ms of one radix pass / one whole sort over n synthetic records (tools/bench_radix.py) */
+int mb_debug_radix(mb_ctx* ctx, uint64_t n, int shift, int kbits, int reps, float* ms_out);
 const char* mb_version(void);
 
 /* ---- synthetic genomes (host only) ------------------------------

@@ -472,16 +472,14 @@ int mbi_reserve_candidates(mb_ctx* c, u32 n_cand, u32 n_ccomp, u64 bases) {
     TRY(c->reserve(c->bmrank, (bm_words + 1) * 4));
     TRY(c->reserve(c->rep_bits, (nc / 64 + 2) * 8));
     TRY(c->reserve(c->rep_rank, (nc / 64 + 4) * 4));
-    TRY(c->reserve(c->s_hash, nc * 8));
-    TRY(c->reserve(c->s_cand, nc * 4));
+    TRY(c->reserve(c->s_hash, nc * 16));
+    TRY(c->reserve(c->s_cand, nc));
     TRY(c->reserve(c->sort_kA, nc * 8));
     TRY(c->reserve(c->sort_kB, nc * 8));
     TRY(c->reserve(c->slot_gp, nc * 16));
     TRY(c->reserve(c->link_bits, nc / 8 + 16));
     TRY(c->reserve(c->chain_min, nc * 4));
     TRY(c->reserve(c->cstate, nc));
-    TRY(c->reserve(c->live_bits, (nc / 64 + 2) * 8));
-    TRY(c->reserve(c->covered, (nc / 64 + 2) * 8));
     TRY(c->reserve(c->minrank, nc * 4));
     TRY(c->reserve(c->ext_l, nc * 4));
     TRY(c->reserve(c->ext_r, nc * 4));
@@ -504,8 +502,6 @@ int mbi_dedup(mb_ctx* c, u32 n_cand, u64 bases) {
     u64* scal = c->scalars.as<u64>();
     const u64 bm_words = bases / 64 + 2;
     const size_t cw = (size_t)n_cand / 64 + 2; // 64-bit words of a per-slot / per-rep bitmap
-    CUDA_TRY(c, cudaMemsetAsync(c->covered.p, 0, cw * 8, st));
-    CUDA_TRY(c, cudaMemsetAsync(c->live_bits.p, 0, cw * 8, st));
     CUDA_TRY(c, cudaMemsetAsync(c->rep_bits.p, 0, cw * 8, st));
     CUDA_TRY(c, cudaMemsetAsync(scal + SC_DDCTR, 0, 8 * 8, st));
     launch_scan_popc(c->bitmap.as<u64>(), bm_words, c->bmrank.as<u32>(), c->status_slice(div_up(bm_words, scan_tile())), c->ticket(),
@@ -518,8 +514,7 @@ int mbi_dedup(mb_ctx* c, u32 n_cand, u64 bases) {
     da.slot_rec = c->slot_gp.as<ulonglong2>();
     da.link_bits = c->link_bits.as<u8>(); da.chain_min = c->chain_min.as<u32>();
     da.rep_bits = c->rep_bits.as<u64>(); da.rep_rank = c->rep_rank.as<u32>();
-    da.cstate = c->cstate.as<u8>(); da.live_bits = c->live_bits.as<u64>(); da.cov_bits = c->covered.as<u64>();
-    da.s_hash = c->s_hash.as<u64>(); da.s_cand = c->s_cand.as<u32>();
+    da.cstate = c->cstate.as<u8>(); da.s_rec = c->s_hash.as<ulonglong2>(); da.rstate = c->s_cand.as<u8>();
     da.rng_lo = c->rng_lo.as<u32>(); da.rng_hi = c->rng_hi.as<u32>(); da.minrank = c->minrank.as<u32>();
     da.ext_l = c->ext_l.as<u32>(); da.ext_r = c->ext_r.as<u32>();
     da.wl0 = c->wl_a.as<u32>(); da.wl1 = c->wl_b.as<u32>(); da.wl2 = c->wl_c.as<u32>();
@@ -743,6 +738,60 @@ int mb_get_sml(mb_ctx* c, int seq, uint32_t* out_pos, uint64_t capacity, uint64_
     for (u32 i = 0; i < total; ++i)
         if (rec_genome(c->fmt, rec[i]) == (u32)seq) out_pos[k++] = rec_pos(c->fmt, rec[i]);
     return k == n ? MB_OK : MB_E_STATE;
+}
+
+// Tuning aid (tools/bench_radix.py): sorts n pseudo-random records on key bits [shift, shift+kbits) `reps` times and
+// returns the mean device time of one radix pass in ms_out[0] (CUDA events around each pass) and of one whole sort
+// in ms_out[1].  Records look like the path's: min of two uniform keys in the key field, payload bits below.
+int mb_debug_radix(mb_ctx* c, uint64_t n64, int shift, int kbits, int reps, float* ms_out) {
+    if (!c || !ms_out || n64 == 0 || n64 >= (1ull << 31) || kbits < 1 || shift + kbits > 64) return MB_E_ARG;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const u32 n = (u32)n64;
+    TRY(c->reserve(c->keysA, ((size_t)n + 8) * 8));
+    TRY(c->reserve(c->keysB, ((size_t)n + 8) * 8));
+    TRY(c->reserve(c->sort_kA, ((size_t)n + 8) * 8));
+    TRY(c->reserve(c->hist, 8 * 256 * 4));
+    TRY(c->reserve(c->digit_base, 8 * 256 * 4));
+    TRY(c->reserve(c->lookback, (size_t)(div_up(n, radix_tile_size()) + 1) * 256 * 8));
+    TRY(c->reserve(c->tickets, 256 * 4));
+    std::vector<u64> h(n);
+    u64 x = 0x9E3779B97F4A7C15ull;
+    auto rnd = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
+    const u64 kmask = kbits >= 64 ? ~0ull : ((1ull << kbits) - 1);
+    for (u32 i = 0; i < n; ++i) {
+        u64 a = rnd() & kmask, b = rnd() & kmask;
+        h[i] = (std::min(a, b) << shift) | (shift ? (rnd() & ((1ull << shift) - 1)) : 0);
+    }
+    CUDA_TRY(c, cudaMemcpy(c->sort_kA.p, h.data(), (size_t)n * 8, cudaMemcpyHostToDevice));
+    float tot_pass = 0, tot_sort = 0;
+    int npass_total = 0;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int r = 0; r < reps + 1; ++r) {
+        CUDA_TRY(c, cudaMemcpyAsync(c->keysA.p, c->sort_kA.p, (size_t)n * 8, cudaMemcpyDeviceToDevice, c->stream));
+        CUDA_TRY(c, cudaMemsetAsync(c->tickets.p, 0, 256 * 4, c->stream));
+        c->ticket_next = 0; c->n_timed_passes = 0;
+        u64 *kA = c->keysA.as<u64>(), *kB = c->keysB.as<u64>();
+        cudaEventRecord(e0, c->stream);
+        TRY(mbi_sort_records(c, &kA, &kB, nullptr, nullptr, n, shift, kbits, false, true));
+        cudaEventRecord(e1, c->stream);
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        if (r == 0) continue; // warm-up
+        float t = 0;
+        cudaEventElapsedTime(&t, e0, e1);
+        tot_sort += t;
+        for (int i = 0; i < c->n_timed_passes; ++i) { cudaEventElapsedTime(&t, c->ev_r[2 * i], c->ev_r[2 * i + 1]); tot_pass += t; ++npass_total; }
+        if (r == reps) { // check order
+            std::vector<u64> out(n);
+            CUDA_TRY(c, cudaMemcpy(out.data(), kA, (size_t)n * 8, cudaMemcpyDeviceToHost));
+            for (u32 i = 1; i < n; ++i)
+                if (((out[i - 1] >> shift) & kmask) > ((out[i] >> shift) & kmask)) { cudaEventDestroy(e0); cudaEventDestroy(e1); return MB_E_STATE; }
+        }
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    ms_out[0] = npass_total ? tot_pass / npass_total : 0;
+    ms_out[1] = reps ? tot_sort / reps : 0;
+    return MB_OK;
 }
 
 } // extern "C"

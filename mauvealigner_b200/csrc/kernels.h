@@ -85,10 +85,9 @@ struct DedupArgs {
     // per rep, in (group colour, slot) order
     u32 n_rep;
     const u64* s_key;   // colour << 32 | slot
-    u64* s_hash; u32* s_cand;
-    u64* live_bits;     // undecided
-    u64* cov_bits;      // contained in an accepted match
-    u32* rng_lo; u32* rng_hi; // index range of the same-colour reps inside the extent
+    ulonglong2* s_rec;  // colour:16 | slot:32 | hash[15:0], hash[47:16] | candidate:32
+    u8* rstate;         // 0 undecided, 1 accepted, 2 dropped, 3 covered; flag bits: see k_resolve
+    u32* rng_lo; u32* rng_hi; // slot range of the extent
     u32* minrank;       // lowest undecided claimer of this round
     u32* ext_l; u32* ext_r;   // per candidate
     // device-resident work lists (three rotating lists of undecided reps, long extensions, wide extents)

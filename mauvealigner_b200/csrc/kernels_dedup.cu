@@ -328,28 +328,60 @@ __device__ __forceinline__ void mismatch64(const u64* __restrict__ packed, const
 // jump the single-step windows bL+s start at chunk index s-1 — all inside the same chunk.  Left is the
 // mirror image: offsets [-bL-65+L, -bL+L-1), chunk index i <-> offset -bL-65+L+i.
 __device__ __forceinline__ i64 chunk_lo(int dir, u32 b, u32 L) { return dir > 0 ? (i64)b * L + 1 : -(i64)b * L - 65 + (i64)L; }
+// Window map of a chunk: cell q (flag in the low bit of the 2-bit cell, cell 0 at the top of hi) is set iff the
+// L-window that starts at chunk index q covers a mismatch on a cared column = OR over the cared offsets o of
+// the mismatch map shifted left by o cells.  Windows that run past the chunk see zeros there; callers only
+// use windows that fit.  The loop is uniform (the pattern is a launch constant).
+__device__ __forceinline__ void window_map(u64 xa, u64 xb, const SeedDev& sd, u64& bhi, u64& blo) {
+    bhi = 0; blo = 0;
+    const u64 care = sd.mask_hi;
+    for (int o = 0; o < sd.L; ++o) {
+        if (!((care >> (62 - 2 * o)) & 1)) continue;
+        bhi |= shl128_hi(xa, xb, 2 * o);
+        blo |= xb << (2 * o);
+    }
+}
+__device__ __forceinline__ bool win_bad(u64 bhi, u64 blo, u32 q) { return ((q < 32 ? bhi >> (62 - 2 * q) : blo >> (62 - 2 * (q - 32))) & 1) != 0; }
+// number of consecutive good windows at chunk indices q, q+1, ... (at most 64 - q)
+__device__ __forceinline__ u32 good_up(u64 bhi, u64 blo, u32 q) {
+    u64 hi = q < 32 ? shl128_hi(bhi, blo, 2 * (int)q) : (blo << (2 * (q - 32)));
+    u64 lo = q < 32 ? (blo << (2 * q)) : 0;
+    if (hi) return (u32)__clzll((long long)hi) >> 1;
+    if (lo) return 32 + ((u32)__clzll((long long)lo) >> 1);
+    return 64 - q;
+}
+// number of consecutive good windows at chunk indices q, q-1, ... (at most q + 1)
+__device__ __forceinline__ u32 good_down(u64 bhi, u64 blo, u32 q) {
+    // shift right so that cell q becomes the lowest cell
+    int s = 2 * (63 - (int)q);
+    u64 lo = s >= 64 ? (bhi >> (s - 64)) : (s ? ((blo >> s) | (bhi << (64 - s))) : blo);
+    u64 hi = s >= 64 ? 0 : (bhi >> s);
+    if (lo) return ((u32)__ffsll((long long)lo) - 1) >> 1;
+    if (hi) return 32 + (((u32)__ffsll((long long)hi) - 1) >> 1);
+    return q + 1;
+}
+
 // evaluate one chunk that starts after b0 successful jumps: advances b over the jumps it holds; returns
 // true when the walk ends inside this chunk (growth in `out`)
-__device__ __forceinline__ bool walk_chunk(u64 xa, u64 xb, u64 care, int dir, u32 L, u32 room, u32 maxjumps, u32 per_chunk, u32& b, u32& out) {
+__device__ __forceinline__ bool walk_chunk(u64 xa, u64 xb, const SeedDev& sd, int dir, u32 L, u32 room, u32 maxjumps, u32 per_chunk, u32& b, u32& out) {
+    u64 bhi, blo;
+    window_map(xa, xb, sd, bhi, blo);
     const u32 b0 = b;
     bool failed = false;
     for (u32 w = 0; w < per_chunk && b < maxjumps; ++w) {
         // right: jump window b+1 covers offsets [(b+1)L, (b+2)L)   -> chunk index (b-b0)L + L-1
         // left : jump window b+1 covers offsets [-(b+1)L, -bL)     -> chunk index 65 - 2L - (b-b0)L
         u32 idx = dir > 0 ? (b - b0) * L + L - 1 : 65 - 2 * L - (b - b0) * L;
-        if (map_at(xa, xb, idx) & care) { failed = true; break; }
+        if (win_bad(bhi, blo, idx)) { failed = true; break; }
         ++b;
     }
     if (!(failed || b >= maxjumps)) return false;
     if (b - b0 == per_chunk && !failed) return false; // the chunk is used up: the single steps need a fresh one
-    // single steps: right window s starts at offset bL+s, left window s at offset -bL-s
-    u32 maxs = min(L, room - b * L), sdone = 0;
-    for (u32 s = 1; s <= maxs; ++s) {
-        u32 idx = dir > 0 ? (b - b0) * L + s - 1 : 65 - L - (b - b0) * L - s;
-        if (map_at(xa, xb, idx) & care) break;
-        sdone = s;
-    }
-    out = b * L + sdone;
+    // single steps: right window s starts at offset bL+s (chunk index (b-b0)L + s - 1, ascending), left window s
+    // at offset -bL-s (chunk index 65 - L - (b-b0)L - s, descending)
+    u32 maxs = min(L, room - b * L);
+    u32 run = dir > 0 ? good_up(bhi, blo, (b - b0) * L) : good_down(bhi, blo, 64 - L - (b - b0) * L);
+    out = b * L + min(run, maxs);
     return true;
 }
 
@@ -366,7 +398,7 @@ __device__ __forceinline__ u32 grow_thread(const u64* __restrict__ packed, const
     for (int chunk = 0; chunk < DD_THREAD_CHUNKS; ++chunk) {
         u64 xa, xb;
         mismatch64(packed, gt, L, cpos, cgs, m, chunk_lo(dir, b, L), xa, xb);
-        if (walk_chunk(xa, xb, care, dir, L, room, maxjumps, per_chunk, b, out)) return out;
+        if (walk_chunk(xa, xb, sd, dir, L, room, maxjumps, per_chunk, b, out)) return out;
     }
     return INF32;
 }
@@ -388,7 +420,7 @@ __device__ u32 grow_warp(const u64* __restrict__ packed, const GenomeTable& gt, 
         if (active) {
             u64 xa, xb;
             mismatch64(packed, gt, L, cpos, cgs, m, chunk_lo(dir, b, L), xa, xb);
-            ends = walk_chunk(xa, xb, care, dir, L, room, maxjumps, per_chunk, b, out);
+            ends = walk_chunk(xa, xb, sd, dir, L, room, maxjumps, per_chunk, b, out);
         }
         u32 em = __ballot_sync(0xFFFFFFFFu, ends);
         if (em) return __shfl_sync(0xFFFFFFFFu, out, __ffs(em) - 1);
@@ -454,47 +486,20 @@ __device__ __forceinline__ void wl_push(u32* list, u32* count, bool pred, u32 va
     list[base + __popc(m & ((1u << lane) - 1))] = value;
 }
 
-__device__ __forceinline__ u64 range_mask(u32 word, u32 lo, u32 hi) { // bits of `word` inside [lo, hi)
-    u64 m = ~0ull;
-    if (lo > word * 64) m &= ~0ull << (lo - word * 64);
-    if (hi < word * 64 + 64) m &= (1ull << (hi - word * 64)) - 1;
-    return m;
-}
-__device__ __forceinline__ bool bit_of(const u64* bits, u32 s) { return (bits[s >> 6] >> (s & 63)) & 1; }
-
-__device__ __forceinline__ u32 key_lower_bound(const u64* __restrict__ k, u32 lo, u32 hi, u64 key) {
-    while (lo < hi) {
-        u32 mid = lo + (hi - lo) / 2;
-        if (k[mid] < key) lo = mid + 1; else hi = mid;
-    }
-    return lo;
-}
-// Index range [ilo, ihi) of the reps of rep i's colour whose first-genome position lies in the extent
-// [x - el, x + er] of candidate c: slot range through the candidate bitmap, then a galloping search
-// outwards from i over the (colour, slot) keys.
-__device__ __forceinline__ void extent_range(const DedupArgs& a, const GenomeTable& gt, u32 i, u32 c, u32 el, u32 er, u32& ilo, u32& ihi) {
+// slot range [rlo, rhi) of all candidates whose first-genome position lies in the extent [x - el, x + er] of
+// candidate c (two rank look-ups in the candidate bitmap)
+__device__ __forceinline__ void extent_slots(const DedupArgs& a, const GenomeTable& gt, u32 c, u32 el, u32 er, u32& rlo, u32& rhi) {
     u32 off = a.cand_off[c];
     u64 gp = gt.base_base[a.comp_gs[off] & 0x7F] + a.comp_pos[off];
-    u32 rlo = slot_rank(a.bitmap, a.bmrank, gp - el);
-    u32 rhi = slot_rank(a.bitmap, a.bmrank, gp + er + 1);
-    const u64* __restrict__ k = a.s_key;
-    const u64 col = k[i] & 0xFFFF00000000ull;
-    const u64 klo = col | rlo, khi = col | rhi;
-    u32 step = 1, hi = i; // invariant: k[hi] >= klo
-    while (true) {
-        if (step > hi) { ilo = key_lower_bound(k, 0, hi, klo); break; }
-        u32 probe = hi - step;
-        if (k[probe] < klo) { ilo = key_lower_bound(k, probe + 1, hi, klo); break; }
-        hi = probe; step *= 2;
-    }
-    u32 lo = i + 1; // invariant: k[lo - 1] < khi
-    step = 1;
-    while (true) {
-        if (lo + step > a.n_rep) { ihi = key_lower_bound(k, lo, a.n_rep, khi); break; }
-        u32 probe = lo + step - 1;
-        if (k[probe] >= khi) { ihi = key_lower_bound(k, lo, probe, khi); break; }
-        lo = probe + 1; step *= 2;
-    }
+    rlo = slot_rank(a.bitmap, a.bmrank, gp - el);
+    rhi = slot_rank(a.bitmap, a.bmrank, gp + er + 1);
+}
+
+// Per-rep record in (colour, slot) order: x = colour:16 | slot:32 | hash[15:0], y = hash[47:16] | candidate:32
+// (the colour IS hash[63:48], so the two words hold the whole group hash).  One 16-byte load per neighbour.
+#define REC_COL(x) ((x) & 0xFFFF000000000000ull)
+__device__ __forceinline__ bool rec_same_hash(const ulonglong2& p, const ulonglong2& q) {
+    return ((p.x ^ q.x) & 0xFFFF00000000FFFFull) == 0 && (p.y >> 32) == (q.y >> 32);
 }
 
 // ---- extend: a warp takes 32 consecutive reps.  Lane j owns rep j's state; the (rep, component) pairs
@@ -512,16 +517,16 @@ __global__ void __launch_bounds__(DD_NT) k_extend(DedupArgs a, GenomeTable gt, S
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u32 i = blockIdx.x * DD_NT + threadIdx.x;
     const bool valid = i < a.n_rep;
-    u32 live = __ballot_sync(0xFFFFFFFFu, valid);
-    if (lane == 0) reinterpret_cast<u32*>(a.live_bits)[i >> 5] = live;
     const u32 L = sd.L;
     u32 c = 0, off = 0, m = 1, p0 = 0, g0 = 0;
     if (valid) {
-        ulonglong2 r = a.slot_rec[(u32)a.s_key[i]];
+        const u32 slot = (u32)a.s_key[i];
+        ulonglong2 r = a.slot_rec[slot];
         c = (u32)r.y;
-        a.s_hash[i] = r.x & HASH_MASK;
-        a.s_cand[i] = c;
+        const u64 h = r.x & HASH_MASK;
+        a.s_rec[i] = make_ulonglong2((h & 0xFFFF000000000000ull) | ((u64)slot << 16) | (h & 0xFFFFull), (((h >> 16) & 0xFFFFFFFFull) << 32) | c);
         a.minrank[i] = INF32;
+        a.rstate[i] = 0;
         off = a.cand_off[c]; m = a.cand_off[c + 1] - off;
         p0 = a.comp_pos[off]; g0 = a.comp_gs[off] & 0x7F;
     }
@@ -529,7 +534,6 @@ __global__ void __launch_bounds__(DD_NT) k_extend(DedupArgs a, GenomeTable gt, S
         wl_push(a.wl_long, a.ctr + 6, valid, i);
         return;
     }
-    const u64 care = sd.mask_hi & 0x5555555555555555ull;
     const u32 per_chunk = (3 * L <= 65) ? 2 : 1;
     int st = valid ? (3 * L <= 64 ? ST_CENTER : ST_LEFT) : ST_DONE;
     bool rj = true; // the right side still has to be walked
@@ -593,37 +597,25 @@ __global__ void __launch_bounds__(DD_NT) k_extend(DedupArgs a, GenomeTable gt, S
             const u64 xa = ((u64)sMap[warp][lane][0] << 32) | sMap[warp][lane][1], xb = ((u64)sMap[warp][lane][2] << 32) | sMap[warp][lane][3];
             if (st == ST_CENTER) {
                 // chunk index i <-> match offset i - L: first jump windows at 0 (left) and 2L (right), single-step
-                // windows s at L - s (left) and L + s (right)
-                const bool lj = room_l >= L && !(map_at(xa, xb, 0) & care);
-                rj = room_r >= L && !(map_at(xa, xb, 2 * L) & care);
-                if (!lj) {
-                    u32 maxs = min(L, room_l), sdone = 0;
-                    for (u32 s = 1; s <= maxs; ++s) {
-                        if (map_at(xa, xb, L - s) & care) break;
-                        sdone = s;
-                    }
-                    el = sdone;
-                }
-                if (!rj) {
-                    u32 maxs = min(L, room_r), sdone = 0;
-                    for (u32 s = 1; s <= maxs; ++s) {
-                        if (map_at(xa, xb, L + s) & care) break;
-                        sdone = s;
-                    }
-                    er = sdone;
-                }
+                // windows s at L - s (left, descending from L - 1) and L + s (right, ascending from L + 1)
+                u64 bhi, blo;
+                window_map(xa, xb, sd, bhi, blo);
+                const bool lj = room_l >= L && !win_bad(bhi, blo, 0);
+                rj = room_r >= L && !win_bad(bhi, blo, 2 * L);
+                if (!lj) el = min(good_down(bhi, blo, L - 1), min(L, room_l));
+                if (!rj) er = min(good_up(bhi, blo, L + 1), min(L, room_r));
                 b = 1; // the first jump of the side walked next is known to succeed
                 st = lj ? ST_LEFT : (rj ? ST_RIGHT : ST_DONE);
             } else if (st == ST_LEFT) {
                 u32 out = 0;
-                if (walk_chunk(xa, xb, care, -1, L, room_l, room_l / L, per_chunk, b, out)) {
+                if (walk_chunk(xa, xb, sd, -1, L, room_l, room_l / L, per_chunk, b, out)) {
                     el = out;
                     b = (3 * L <= 64) ? 1 : 0;
                     st = rj ? ST_RIGHT : ST_DONE;
                 }
             } else {
                 u32 out = 0;
-                if (walk_chunk(xa, xb, care, +1, L, room_r, room_r / L, per_chunk, b, out)) { er = out; st = ST_DONE; }
+                if (walk_chunk(xa, xb, sd, +1, L, room_r, room_r / L, per_chunk, b, out)) { er = out; st = ST_DONE; }
             }
         }
         __syncwarp();
@@ -631,9 +623,9 @@ __global__ void __launch_bounds__(DD_NT) k_extend(DedupArgs a, GenomeTable gt, S
     const bool is_long = valid && st != ST_DONE;
     if (valid && !is_long) {
         a.ext_l[c] = el; a.ext_r[c] = er;
-        u32 ilo, ihi;
-        extent_range(a, gt, i, c, el, er, ilo, ihi);
-        a.rng_lo[i] = ilo; a.rng_hi[i] = ihi;
+        u32 rlo, rhi;
+        extent_slots(a, gt, c, el, er, rlo, rhi);
+        a.rng_lo[i] = rlo; a.rng_hi[i] = rhi;
     }
     wl_push(a.wl_long, a.ctr + 6, is_long, i);
 }
@@ -644,7 +636,7 @@ __global__ void __launch_bounds__(DD_NT) k_extend_long(DedupArgs a, GenomeTable 
     const u32 n = a.ctr[6];
     for (u32 t = gwarp; t < n; t += nwarps) {
         u32 i = a.wl_long[t];
-        u32 c = a.s_cand[i];
+        u32 c = (u32)a.s_rec[i].y;
         u32 off = a.cand_off[c], m = a.cand_off[c + 1] - off;
         const u32* cpos = a.comp_pos + off;
         const u8* cgs = a.comp_gs + off;
@@ -660,38 +652,57 @@ __global__ void __launch_bounds__(DD_NT) k_extend_long(DedupArgs a, GenomeTable 
         }
         if (lane == 0) {
             a.ext_l[c] = el; a.ext_r[c] = er;
-            u32 ilo, ihi;
-            extent_range(a, gt, i, c, el, er, ilo, ihi);
-            a.rng_lo[i] = ilo; a.rng_hi[i] = ihi;
+            u32 rlo, rhi;
+            extent_slots(a, gt, c, el, er, rlo, rhi);
+            a.rng_lo[i] = rlo; a.rng_hi[i] = rhi;
         }
     }
 }
 
-// the undecided higher-rank reps of rep i's group among the reps of one bitmap word: claim (atomicMin
-// of i's rank) or cover (i is accepted: they are contained in it, D16)
-template <bool COVER>
-__device__ __forceinline__ void visit_word(const DedupArgs& a, u32 w, u32 ilo, u32 ihi, u32 c, u64 h) {
-    u64 bits = a.live_bits[w] & range_mask(w, ilo, ihi) & ~a.cov_bits[w]; // covered reps are as good as dropped
-    u64 cov = 0;
-    while (bits) {
-        u32 bpos = (u32)__ffsll((long long)bits) - 1;
-        bits &= bits - 1;
-        u32 t = w * 64 + bpos;
-#ifdef MB_DEDUP_COUNT
-        atomicAdd(a.ctr + 12, 1u);
-#endif
-        if (a.s_hash[t] != h) continue;
-        u32 j = a.s_cand[t];
-        if (j <= c) continue;
-#ifdef MB_DEDUP_COUNT
-        atomicAdd(a.ctr + 13 + (COVER ? 1 : 0), 1u);
-#endif
-        // a claim only delays its target, so the hash alone is enough there (a false claim lapses when the
-        // claimer is decided); a cover drops its target and is verified component by component
-        if (COVER) { if (same_group(a, c, j)) cov |= 1ull << bpos; }
-        else atomicMin(&a.minrank[t], c);
+// Rep state: 0 undecided, 1 accepted, 2 dropped, 3 covered (contained in an accepted match: dropped at its
+// next decide); bit 7: its last claim walk found a target.
+#define RS_MASK 0x0Fu
+#define RS_COVERED 3u
+#define RS_TARGETS 0x80u
+#define RS_WIDE 0x40u
+#define DD_WALK_MAX 192 // neighbours one thread visits per direction before the rep is handed to a warp
+
+// Visit the same-colour reps whose slot lies in rep i's extent [rlo, rhi): they are the neighbours of i in
+// the (colour, slot) order.  `first`/`stride` = 0/1 for one thread, lane/32 for a warp.  CLAIM: atomicMin of
+// i's rank on every undecided higher-rank rep of the same group hash (a claim only delays its target, so
+// the hash alone is enough: a false claim lapses when the claimer is decided).  COVER (i is accepted): those
+// reps are contained in it (D16) — verified component by component, because a cover drops its target.
+// Returns the number of targets, or -1 when a single thread ran out of its walk budget.
+template <bool COVER, bool WARP>
+__device__ __forceinline__ int walk_neighbours(const DedupArgs& a, u32 i, const ulonglong2& me, u32 rlo, u32 rhi) {
+    const u64 klo = REC_COL(me.x) | ((u64)rlo << 16), khi = REC_COL(me.x) | ((u64)rhi << 16);
+    const u32 c = (u32)me.y;
+    const u32 first = WARP ? (threadIdx.x & 31) : 0, stride = WARP ? 32 : 1;
+    int found = 0;
+    for (int dir = 0; dir < 2; ++dir) {
+        u32 steps = 0;
+        for (u32 d = 1 + first;; d += stride) {
+            bool in = dir == 0 ? (u64)i + d < a.n_rep : d <= i;
+            ulonglong2 r = make_ulonglong2(0, 0);
+            if (in) {
+                r = a.s_rec[dir == 0 ? i + d : i - d];
+                in = dir == 0 ? r.x < khi : r.x >= klo;
+            }
+            if (in && rec_same_hash(me, r) && (u32)r.y > c) {
+                const u32 t = dir == 0 ? i + d : i - d;
+                if ((a.rstate[t] & RS_MASK) == 0) {
+                    if (COVER) { if (same_group(a, c, (u32)r.y)) { a.rstate[t] = RS_COVERED; ++found; } }
+                    else { atomicMin(&a.minrank[t], c); ++found; }
+                }
+            }
+            if (WARP) { if (!__any_sync(0xFFFFFFFFu, in)) break; }
+            else {
+                if (!in) break;
+                if (++steps > DD_WALK_MAX) return -1;
+            }
+        }
     }
-    if (COVER && cov) atomicOr((unsigned long long*)&a.cov_bits[w], cov);
+    return found;
 }
 
 __device__ __forceinline__ u64 gtimer() { u64 t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
@@ -715,26 +726,26 @@ __global__ void __launch_bounds__(DD_NT) k_resolve(DedupArgs a) {
         const u32 cur = r % 3, nxt = (r + 1) % 3, spare = (r + 2) % 3;
         if (t0) { ctr[spare] = 0; ctr[3 + spare] = 0; ctr[9] += 1; }
         const u32 n_narrow = r == 0 ? a.n_rep : ctr[cur];
-        // ---- claim, one thread per undecided rep (round 0 also sorts out the wide ranges)
+        // ---- claim, one thread per undecided rep; reps with too many neighbours go to the wide list (round 0)
         for (u32 t = gtid; t < n_narrow; t += gsz) {
             u32 i = r == 0 ? t : nl[cur][t];
-            u32 ilo = a.rng_lo[i], ihi = a.rng_hi[i];
-            if (r == 0 && ihi - ilo > DD_WIDE) { wd[0][atomicAdd(ctr + 3, 1u)] = i; continue; }
-            if (ihi - ilo < 2 || bit_of(a.cov_bits, i)) continue; // alone in its extent / as good as dropped
-            u32 c = a.s_cand[i];
-            u64 h = a.s_hash[i];
-            for (u32 w = ilo >> 6; w <= (ihi - 1) >> 6; ++w) visit_word<false>(a, w, ilo, ihi, c, h);
+            u32 rlo = a.rng_lo[i], rhi = a.rng_hi[i];
+            if (rhi - rlo < 2) continue;                            // alone in its extent
+            if ((a.rstate[i] & RS_MASK) == RS_COVERED) continue;    // as good as dropped
+            ulonglong2 me = a.s_rec[i];
+            int f = walk_neighbours<false, false>(a, i, me, rlo, rhi);
+            if (f < 0) { a.rstate[i] = RS_WIDE; wd[cur][atomicAdd(ctr + 3 + cur, 1u)] = i; } // lives on the wide list from now on
+            else if (f > 0) a.rstate[i] = RS_TARGETS;
         }
-        if (r == 0) { grid.sync(); if (t0) ctr[10] = ctr[3]; } // the wide list is complete only now
+        grid.sync(); // the wide list of this round is complete only now
+        if (t0 && r == 0) ctr[10] = ctr[3];
         const u32 n_wide = ctr[3 + cur];
-        // ---- claim, wide ranges: one warp each, a bitmap word per lane
+        // ---- claim, wide: one warp per rep
         for (u32 t = gwarp; t < n_wide; t += nwarps) {
             u32 i = wd[cur][t];
-            if (bit_of(a.cov_bits, i)) continue;
-            u32 ilo = a.rng_lo[i], ihi = a.rng_hi[i];
-            u32 c = a.s_cand[i];
-            u64 h = a.s_hash[i];
-            for (u32 w = (ilo >> 6) + lane; w <= (ihi - 1) >> 6; w += 32) visit_word<false>(a, w, ilo, ihi, c, h);
+            if ((a.rstate[i] & RS_MASK) == RS_COVERED) continue;
+            ulonglong2 me = a.s_rec[i];
+            walk_neighbours<false, true>(a, i, me, a.rng_lo[i], a.rng_hi[i]);
         }
         grid.sync();
         DD_TRACE(5);
@@ -745,20 +756,15 @@ __global__ void __launch_bounds__(DD_NT) k_resolve(DedupArgs a) {
             u32 i = 0;
             if (t < n_narrow) {
                 i = r == 0 ? t : nl[cur][t];
-                u32 ilo = a.rng_lo[i], ihi = a.rng_hi[i];
-                if (r > 0 || ihi - ilo <= DD_WIDE) {
-                    u32 c = a.s_cand[i];
-                    if (bit_of(a.cov_bits, i)) {
-                        a.cstate[c] = 2;
-                        atomicAnd((unsigned long long*)&a.live_bits[i >> 6], ~(1ull << (i & 63)));
-                    } else if (a.minrank[i] == INF32) {
+                const u32 stt = a.rstate[i];
+                if (!(stt & RS_WIDE)) { // not handed to the wide list
+                    ulonglong2 me = a.s_rec[i];
+                    const u32 c = (u32)me.y;
+                    if ((stt & RS_MASK) == RS_COVERED) { a.rstate[i] = 2; a.cstate[c] = 2; }
+                    else if (a.minrank[i] == INF32) {
                         // accepted: every undecided higher-rank rep of this group inside the extent is contained
-                        if (ihi - ilo >= 2) {
-                            u64 h = a.s_hash[i];
-                            for (u32 w = ilo >> 6; w <= (ihi - 1) >> 6; ++w) visit_word<true>(a, w, ilo, ihi, c, h);
-                        }
-                        a.cstate[c] = 1;
-                        atomicAnd((unsigned long long*)&a.live_bits[i >> 6], ~(1ull << (i & 63)));
+                        a.rstate[i] = 1; a.cstate[c] = 1;
+                        if (stt & RS_TARGETS) walk_neighbours<true, false>(a, i, me, a.rng_lo[i], a.rng_hi[i]);
                     } else {
                         a.minrank[i] = INF32;
                         keep = true;
@@ -770,24 +776,18 @@ __global__ void __launch_bounds__(DD_NT) k_resolve(DedupArgs a) {
         // ---- decide, wide
         for (u32 t = gwarp; t < n_wide; t += nwarps) {
             u32 i = wd[cur][t];
-            u32 c = a.s_cand[i];
+            ulonglong2 me = a.s_rec[i];
+            const u32 c = (u32)me.y;
             int d = 2;
             if (lane == 0) {
-                if (bit_of(a.cov_bits, i)) d = 0;
+                if ((a.rstate[i] & RS_MASK) == RS_COVERED) d = 0;
                 else if (a.minrank[i] == INF32) d = 1;
             }
             d = __shfl_sync(0xFFFFFFFFu, d, 0);
-            if (d == 1) {
-                u32 ilo = a.rng_lo[i], ihi = a.rng_hi[i];
-                u64 h = a.s_hash[i];
-                for (u32 w = (ilo >> 6) + lane; w <= (ihi - 1) >> 6; w += 32) visit_word<true>(a, w, ilo, ihi, c, h);
-            }
+            if (d == 1) walk_neighbours<true, true>(a, i, me, a.rng_lo[i], a.rng_hi[i]);
             if (lane == 0) {
                 if (d == 2) { a.minrank[i] = INF32; wd[nxt][atomicAdd(ctr + 3 + nxt, 1u)] = i; }
-                else {
-                    a.cstate[c] = d == 1 ? 1 : 2;
-                    atomicAnd((unsigned long long*)&a.live_bits[i >> 6], ~(1ull << (i & 63)));
-                }
+                else { a.rstate[i] = d == 1 ? 1 : 2; a.cstate[c] = d == 1 ? 1 : 2; }
             }
         }
         grid.sync();
