@@ -87,7 +87,7 @@ int mb_ctx_destroy(mb_ctx* c) {
     cudaStreamSynchronize(c->stream);
     DBuf* bufs[] = {&c->packed, &c->ascii_stage, &c->keysA, &c->keysB, &c->valsA, &c->valsB, &c->hist, &c->digit_base, &c->lookback, &c->tickets,
                     &c->status, &c->scalars, &c->per_seq, &c->tile_first, &c->cand_run, &c->cand_off, &c->cand_aux, &c->comp_pos, &c->comp_gs,
-                    &c->bitmap, &c->bmrank, &c->cand_at, &c->cstate, &c->covered, &c->minrank, &c->ext_l, &c->ext_r, &c->wl_a, &c->wl_b, &c->wl_c, &c->wl_long, &c->wd_a, &c->wd_b, &c->wd_c, &c->live_bits, &c->trace, &c->ghash, &c->slot_gp, &c->slot_hash, &c->link_bits, &c->chain_min, &c->rep_bits, &c->rep_rank, &c->s_hash, &c->s_cand, &c->rng_lo, &c->rng_hi, &c->flags,
+                    &c->bitmap, &c->bmrank, &c->cand_at, &c->cstate, &c->covered, &c->ghash2, &c->rep_cand, &c->s_h2, &c->reach, &c->xstate, &c->xrec, &c->minrank, &c->ext_l, &c->ext_r, &c->wl_a, &c->wl_b, &c->wl_c, &c->wl_long, &c->wd_a, &c->wd_b, &c->wd_c, &c->live_bits, &c->trace, &c->ghash, &c->slot_gp, &c->slot_hash, &c->link_bits, &c->chain_min, &c->rep_bits, &c->rep_rank, &c->s_hash, &c->s_cand, &c->rng_lo, &c->rng_hi, &c->flags,
                     &c->match_idx, &c->sort_kA, &c->sort_kB, &c->sort_vA, &c->sort_vB, &c->ncomp, &c->mers_tmp, &c->out_len, &c->out_off,
                     &c->out_seq, &c->out_start};
     for (DBuf* b : bufs) free_buf(*b);
@@ -407,7 +407,7 @@ int mb_find_device(mb_ctx* c, const mb_params* prm) {
             // component counts in sorted order -> offsets
             // (ncomp was written in candidate order; permute through the sorted values inside the gather scan input)
             OutputArgs oa{};
-            oa.n_cand = n_cand; oa.cand_off = c->cand_off.as<u32>(); oa.ncomp = c->ncomp.as<u32>();
+            oa.n_items = n_cand; oa.cand_off = c->cand_off.as<u32>(); oa.ncomp = c->ncomp.as<u32>();
             oa.n_matches_ptr = scal + SC_NMATCH;
             c->tmp_u64 = n_cand;
             CUDA_TRY(c, cudaMemcpyAsync(scal + SC_NMATCH, &c->tmp_u64, 8, cudaMemcpyHostToDevice, st));
@@ -437,13 +437,13 @@ int mb_find_device(mb_ctx* c, const mb_params* prm) {
         eu.keys = kA; eu.vals = vA; eu.run_start = run_start; eu.run_u = run_u;
         eu.cand_run = c->cand_run.as<u32>(); eu.cand_off = c->cand_off.as<u32>(); eu.cand_aux = nullptr;
         eu.totals = reinterpret_cast<u32*>(scal + SC_CAND);
-        eu.mode = mode; eu.comp_pos = c->comp_pos.as<u32>(); eu.comp_gs = c->comp_gs.as<u8>(); eu.bitmap = c->bitmap.as<u64>(); eu.ghash = c->ghash.as<u64>();
+        eu.mode = mode; eu.comp_pos = c->comp_pos.as<u32>(); eu.comp_gs = c->comp_gs.as<u8>(); eu.bitmap = c->bitmap.as<u64>(); eu.ghash = c->ghash.as<u64>(); eu.ghash2 = c->ghash2.as<u64>();
         launch_emit_unique(eu, fmt, gt, n_cand, st); LAUNCHED(c); CHECK_LAUNCH(c);
         // ---- a10 + a11
         TRY(mbi_dedup(c, n_cand, bases));
         cudaEventRecord(c->ev[EV_DEDUP], st);
         // ---- a12
-        TRY(mbi_output_unique(c, n_cand, maxlen));
+        TRY(mbi_output_unique(c, c->n_rep, maxlen));
         n_matches = (u32)c->r_matches; n_ocomp = c->r_comps;
     } else {
         cudaEventRecord(c->ev_x[0], st);
@@ -468,19 +468,24 @@ int mbi_reserve_candidates(mb_ctx* c, u32 n_cand, u32 n_ccomp, u64 bases) {
     TRY(c->reserve(c->comp_pos, (size_t)(n_ccomp + 8) * 4));
     TRY(c->reserve(c->comp_gs, (size_t)(n_ccomp + 8)));
     TRY(c->reserve(c->ghash, nc * 8));
+    TRY(c->reserve(c->ghash2, nc * 8));
     TRY(c->reserve(c->bitmap, bm_words * 8));
     TRY(c->reserve(c->bmrank, (bm_words + 1) * 4));
     TRY(c->reserve(c->rep_bits, (nc / 64 + 2) * 8));
     TRY(c->reserve(c->rep_rank, (nc / 64 + 4) * 4));
     TRY(c->reserve(c->s_hash, nc * 16));
     TRY(c->reserve(c->s_cand, nc));
+    TRY(c->reserve(c->rep_cand, nc * 4));
+    TRY(c->reserve(c->s_h2, nc * 8));
+    TRY(c->reserve(c->reach, nc * 4));
+    TRY(c->reserve(c->xstate, nc * 16));
+    TRY(c->reserve(c->xrec, nc * 16));
     TRY(c->reserve(c->sort_kA, nc * 8));
     TRY(c->reserve(c->sort_kB, nc * 8));
     TRY(c->reserve(c->slot_gp, nc * 16));
     TRY(c->reserve(c->link_bits, nc / 8 + 16));
     TRY(c->reserve(c->chain_min, nc * 4));
-    TRY(c->reserve(c->cstate, nc));
-    TRY(c->reserve(c->minrank, nc * 4));
+    TRY(c->reserve(c->minrank, nc * 16));
     TRY(c->reserve(c->ext_l, nc * 4));
     TRY(c->reserve(c->ext_r, nc * 4));
     TRY(c->reserve(c->rng_lo, nc * 4));
@@ -510,12 +515,13 @@ int mbi_dedup(mb_ctx* c, u32 n_cand, u64 bases) {
     DedupArgs da{};
     da.packed = c->packed.as<u64>(); da.n_cand = n_cand;
     da.cand_off = c->cand_off.as<u32>(); da.comp_pos = c->comp_pos.as<u32>(); da.comp_gs = c->comp_gs.as<u8>();
-    da.bitmap = c->bitmap.as<u64>(); da.bmrank = c->bmrank.as<u32>(); da.ghash = c->ghash.as<u64>();
+    da.bitmap = c->bitmap.as<u64>(); da.bmrank = c->bmrank.as<u32>(); da.ghash = c->ghash.as<u64>(); da.ghash2 = c->ghash2.as<u64>();
     da.slot_rec = c->slot_gp.as<ulonglong2>();
     da.link_bits = c->link_bits.as<u8>(); da.chain_min = c->chain_min.as<u32>();
     da.rep_bits = c->rep_bits.as<u64>(); da.rep_rank = c->rep_rank.as<u32>();
-    da.cstate = c->cstate.as<u8>(); da.s_rec = c->s_hash.as<ulonglong2>(); da.rstate = c->s_cand.as<u8>();
-    da.rng_lo = c->rng_lo.as<u32>(); da.rng_hi = c->rng_hi.as<u32>(); da.minrank = c->minrank.as<u32>();
+    da.s_rec = c->s_hash.as<ulonglong2>(); da.rstate = c->s_cand.as<u8>(); da.s_cand = c->rep_cand.as<u32>(); da.s_h2 = c->s_h2.as<u64>();
+    da.reach = c->reach.as<u32>(); da.xstate = c->xstate.as<uint4>(); da.xrec = c->xrec.as<uint4>();
+    da.rng_lo = c->rng_lo.as<u32>(); da.rng_hi = c->rng_hi.as<u32>(); da.minrank = c->minrank.as<u64>();
     da.ext_l = c->ext_l.as<u32>(); da.ext_r = c->ext_r.as<u32>();
     da.wl0 = c->wl_a.as<u32>(); da.wl1 = c->wl_b.as<u32>(); da.wl2 = c->wl_c.as<u32>();
     da.wl_long = c->wl_long.as<u32>();
@@ -535,6 +541,7 @@ int mbi_dedup(mb_ctx* c, u32 n_cand, u64 bases) {
     TRY(mbi_read_scalars(c));
     const u32 n_rep = (u32)reinterpret_cast<const u64*>(c->h_scal)[SC_UNDECIDED];
     c->stats.n_extended = n_rep;
+    c->n_rep = n_rep;
     da.n_rep = n_rep;
     // ---- reps in (group colour, slot) order
     u64 *skA = c->sort_kA.as<u64>(), *skB = c->sort_kB.as<u64>();
@@ -544,7 +551,7 @@ int mbi_dedup(mb_ctx* c, u32 n_cand, u64 bases) {
     cudaEventRecord(c->ev_x[0], st);
     // ---- extend every rep, then resolve
     launch_extend(da, c->gt, c->sd, st);
-    if (n_rep) { LAUNCHED(c); LAUNCHED(c); }
+    if (n_rep) c->stats.kernel_launches += extend_launches();
     CHECK_LAUNCH(c);
     cudaEventRecord(c->ev_x[3], st);
     const bool want_trace = getenv("MB_DEDUP_TRACE") != nullptr;
@@ -578,7 +585,8 @@ int mbi_dedup(mb_ctx* c, u32 n_cand, u64 bases) {
     return MB_OK;
 }
 
-// a12: compact the accepted candidates, canonical order (D18), CSR.  Sets r_matches / r_comps.
+// a12: compact the accepted items (reps; state in s_cand, candidate ids in rep_cand), canonical order (D18), CSR.
+// Sets r_matches / r_comps.
 int mbi_output_unique(mb_ctx* c, u32 n_cand, u64 maxlen) {
     cudaStream_t st = c->stream;
     u64* scal = c->scalars.as<u64>();
@@ -588,7 +596,8 @@ int mbi_output_unique(mb_ctx* c, u32 n_cand, u64 maxlen) {
     TRY(c->reserve(c->flags, (size_t)(n_cand + 8) * 4));
     TRY(c->reserve(c->match_idx, (size_t)(n_cand + 8) * 4));
     OutputArgs oa{};
-    oa.n_cand = n_cand; oa.cstate = c->cstate.as<u8>(); oa.cand_off = c->cand_off.as<u32>(); oa.comp_pos = c->comp_pos.as<u32>();
+    oa.n_items = n_cand; oa.state = c->s_cand.as<u8>(); oa.item_cand = c->rep_cand.as<u32>(); oa.cand_off = c->cand_off.as<u32>();
+    oa.comp_pos = c->comp_pos.as<u32>();
     oa.comp_gs = c->comp_gs.as<u8>();
     oa.ext_l = c->ext_l.as<u32>(); oa.ext_r = c->ext_r.as<u32>(); oa.flags = c->flags.as<u32>(); oa.match_idx = c->match_idx.as<u32>();
     oa.n_matches_ptr = scal + SC_NMATCH;

@@ -141,6 +141,7 @@ int mb_dist_local(mb_ctx* c, const mb_params* prm, uint64_t n_recv, uint64_t* h_
     TRY(c->reserve(c->comp_pos, ((size_t)n_ccomp + 8) * 4));
     TRY(c->reserve(c->comp_gs, (size_t)n_ccomp + 8));
     TRY(c->reserve(c->ghash, nc * 8));
+    TRY(c->reserve(c->ghash2, nc * 8));
     TRY(c->reserve(c->sort_kA, nc * 8)); TRY(c->reserve(c->sort_kB, nc * 8));
     TRY(c->reserve(c->sort_vA, nc * 8)); TRY(c->reserve(c->sort_vB, nc * 8));
     TRY(c->reserve(c->x_m, nc * 4));
@@ -151,7 +152,7 @@ int mb_dist_local(mb_ctx* c, const mb_params* prm, uint64_t n_recv, uint64_t* h_
     eu.keys = kA; eu.vals = nullptr; eu.run_start = run_start; eu.run_u = run_u;
     eu.cand_run = c->cand_run.as<u32>(); eu.cand_off = c->cand_off.as<u32>(); eu.cand_aux = nullptr;
     eu.totals = reinterpret_cast<u32*>(scal + SC_CAND);
-    eu.mode = prm->mode; eu.comp_pos = c->comp_pos.as<u32>(); eu.comp_gs = c->comp_gs.as<u8>(); eu.bitmap = nullptr; eu.ghash = c->ghash.as<u64>();
+    eu.mode = prm->mode; eu.comp_pos = c->comp_pos.as<u32>(); eu.comp_gs = c->comp_gs.as<u8>(); eu.bitmap = nullptr; eu.ghash = c->ghash.as<u64>(); eu.ghash2 = c->ghash2.as<u64>();
     launch_emit_unique(eu, fmt, c->gt, n_cand, st); LAUNCHED(c); CHECK_LAUNCH(c);
     // stable partition of the candidate rows by owner
     u64 *skA = c->sort_kA.as<u64>(), *skB = c->sort_kB.as<u64>(), *svA = c->sort_vA.as<u64>(), *svB = c->sort_vB.as<u64>();
@@ -161,8 +162,8 @@ int mb_dist_local(mb_ctx* c, const mb_params* prm, uint64_t n_recv, uint64_t* h_
     launch_perm_m(svA, c->cand_off.as<u32>(), n_cand, c->x_m.as<u32>(), st); LAUNCHED(c);
     launch_scan_u32(c->x_m.as<u32>(), n_cand, nullptr, c->out_off.as<u64>(), c->status_slice(div_up(n_cand, scan_tile())), c->ticket(), nullptr, st);
     LAUNCHED(c);
-    launch_pack_cand(svA, c->out_off.as<u64>(), c->cand_off.as<u32>(), c->comp_pos.as<u32>(), c->comp_gs.as<u8>(), c->ghash.as<u64>(), n_cand,
-                     c->x_hdr_s.as<u64>(), c->x_comp_s.as<u64>(), st);
+    launch_pack_cand(svA, c->out_off.as<u64>(), c->cand_off.as<u32>(), c->comp_pos.as<u32>(), c->comp_gs.as<u8>(), c->ghash.as<u64>(), c->ghash2.as<u64>(),
+                     n_cand, c->x_hdr_s.as<u64>(), c->x_comp_s.as<u64>(), st);
     LAUNCHED(c); CHECK_LAUNCH(c);
     cudaEventRecord(c->ev_d[4], st);
     // per-owner row and component counts
@@ -203,21 +204,22 @@ int mb_dist_dedup(mb_ctx* c, uint64_t n_cand64, uint64_t n_comp64, uint64_t* h_n
     launch_scan_u32(c->x_m.as<u32>(), n_cand, c->cand_off.as<u32>(), nullptr, c->status_slice(div_up(n_cand, scan_tile())), c->ticket(), nullptr, st);
     LAUNCHED(c);
     launch_unpack_cand(hdr, comps, c->cand_off.as<u32>(), n_cand, c->gt, c->comp_pos.as<u32>(), c->comp_gs.as<u8>(), c->ghash.as<u64>(),
-                       c->bitmap.as<u64>(), st);
+                       c->ghash2.as<u64>(), c->bitmap.as<u64>(), st);
     LAUNCHED(c); CHECK_LAUNCH(c);
     TRY(mbi_dedup(c, n_cand, c->d_bases));
-    // accepted matches -> rows for the gather
-    TRY(c->reserve(c->flags, ((size_t)n_cand + 8) * 4));
-    TRY(c->reserve(c->match_idx, ((size_t)n_cand + 8) * 4));
-    TRY(c->reserve(c->ncomp, ((size_t)n_cand + 8) * 4));
+    // accepted matches (among the reps) -> rows for the gather
+    const u32 n_rep = c->n_rep;
+    TRY(c->reserve(c->flags, ((size_t)n_rep + 8) * 4));
+    TRY(c->reserve(c->match_idx, ((size_t)n_rep + 8) * 4));
+    TRY(c->reserve(c->ncomp, ((size_t)n_rep + 8) * 4));
     OutputArgs oa{};
-    oa.n_cand = n_cand; oa.cstate = c->cstate.as<u8>(); oa.flags = c->flags.as<u32>();
+    oa.n_items = n_rep; oa.state = c->s_cand.as<u8>(); oa.item_cand = c->rep_cand.as<u32>(); oa.flags = c->flags.as<u32>();
     launch_uniq_flags(oa, st); LAUNCHED(c);
-    launch_scan_u32(c->flags.as<u32>(), n_cand, c->match_idx.as<u32>(), nullptr, c->status_slice(div_up(n_cand, scan_tile())), c->ticket(),
+    launch_scan_u32(c->flags.as<u32>(), n_rep, c->match_idx.as<u32>(), nullptr, c->status_slice(div_up(n_rep, scan_tile())), c->ticket(),
                     scal + SC_NMATCH, st);
     LAUNCHED(c);
-    launch_acc_m(c->cstate.as<u8>(), c->cand_off.as<u32>(), n_cand, c->x_m.as<u32>(), st); LAUNCHED(c);
-    launch_scan_u32(c->x_m.as<u32>(), n_cand, c->ncomp.as<u32>(), nullptr, c->status_slice(div_up(n_cand, scan_tile())), c->ticket(),
+    launch_acc_m(c->s_cand.as<u8>(), c->rep_cand.as<u32>(), c->cand_off.as<u32>(), n_rep, c->x_m.as<u32>(), st); LAUNCHED(c);
+    launch_scan_u32(c->x_m.as<u32>(), n_rep, c->ncomp.as<u32>(), nullptr, c->status_slice(div_up(n_rep, scan_tile())), c->ticket(),
                     scal + SC_NCOMP, st);
     LAUNCHED(c); CHECK_LAUNCH(c);
     TRY(mbi_read_scalars(c));
@@ -227,8 +229,9 @@ int mb_dist_dedup(mb_ctx* c, uint64_t n_cand64, uint64_t n_comp64, uint64_t* h_n
     c->stats.dedup_iters = hs32[2 * SC_DDCTR + 9];
     TRY(c->reserve(c->x_hdr_s, ((size_t)n_match + 8) * 16));
     TRY(c->reserve(c->x_comp_s, ((size_t)n_mcomp + 8) * 8));
-    launch_pack_match(c->cstate.as<u8>(), c->match_idx.as<u32>(), c->ncomp.as<u32>(), c->cand_off.as<u32>(), c->comp_pos.as<u32>(),
-                      c->comp_gs.as<u8>(), c->ext_l.as<u32>(), c->ext_r.as<u32>(), n_cand, c->x_hdr_s.as<u64>(), c->x_comp_s.as<u64>(), st);
+    launch_pack_match(c->s_cand.as<u8>(), c->rep_cand.as<u32>(), c->match_idx.as<u32>(), c->ncomp.as<u32>(), c->cand_off.as<u32>(),
+                      c->comp_pos.as<u32>(), c->comp_gs.as<u8>(), c->ext_l.as<u32>(), c->ext_r.as<u32>(), n_rep, c->x_hdr_s.as<u64>(),
+                      c->x_comp_s.as<u64>(), st);
     LAUNCHED(c); CHECK_LAUNCH(c);
     cudaEventRecord(c->ev_d[6], st);
     CUDA_TRY(c, cudaStreamSynchronize(st));
@@ -257,7 +260,7 @@ int mb_dist_output(mb_ctx* c, uint64_t n_match64, uint64_t n_comp64) {
                         st);
         LAUNCHED(c);
         launch_unpack_match(hdr, comps, c->cand_off.as<u32>(), n_match, c->comp_pos.as<u32>(), c->comp_gs.as<u8>(), c->ext_l.as<u32>(),
-                            c->ext_r.as<u32>(), c->cstate.as<u8>(), st);
+                            c->ext_r.as<u32>(), c->s_cand.as<u8>(), c->rep_cand.as<u32>(), st);
         LAUNCHED(c); CHECK_LAUNCH(c);
         TRY(mbi_output_unique(c, n_match, c->d_maxlen));
     }

@@ -53,6 +53,7 @@ struct EmitUniqueArgs {
     u32* comp_pos; u8* comp_gs;
     u64* bitmap;
     u64* ghash;      // per candidate: hash of (genome set, strands, diagonal)
+    u64* ghash2;     // second, independent hash of the same key (low 8 bits cleared)
 };
 void launch_emit_unique(const EmitUniqueArgs& a, const RecFmt& fmt, const GenomeTable& gt, u32 n_cand_upper, cudaStream_t st);
 struct EmitEnumArgs {
@@ -75,20 +76,25 @@ struct DedupArgs {
     const u32* cand_off; const u32* comp_pos; const u8* comp_gs;
     const u64* bitmap; const u32* bmrank;   // candidates by (first genome, position): bitmap over global bases + word ranks
     const u64* ghash;   // candidate -> hash of its D16 group (genome set, strands, diagonal)
+    const u64* ghash2;  // candidate -> second independent hash of the group
     // per slot (candidates in (first genome, position) order)
     ulonglong2* slot_rec; // slot -> (group hash | adjacent-to-previous-slot bit, candidate)
     u8* link_bits;      // one bit per slot: continues the chain of the previous slot
     u32* chain_min;     // slot -> lowest rank among the earlier members of its chain
     u64* rep_bits;      // one bit per slot: lowest rank of its chain
     const u32* rep_rank; // per 64-slot word: reps before it
-    u8* cstate;         // candidate: 0 undecided rep, 1 accepted, 2 dropped
     // per rep, in (group colour, slot) order
     u32 n_rep;
     const u64* s_key;   // colour << 32 | slot
     ulonglong2* s_rec;  // colour:16 | slot:32 | hash[15:0], hash[47:16] | candidate:32
-    u8* rstate;         // 0 undecided, 1 accepted, 2 dropped, 3 covered; flag bits: see k_resolve
+    u8* rstate;         // 0 undecided, 1 accepted, 2 dropped; flag bits: see k_resolve
+    u32* s_cand;        // rep -> candidate
+    u64* s_h2;          // rep -> second group hash
+    u32* reach;         // largest index distance of any claimer of this rep
+    uint4* xrec;        // rep -> (candidate, first component row, components | first genome << 8, first position)
+    uint4* xstate;      // saved walk state of a rep whose extension is continued by k_extend_more
     u32* rng_lo; u32* rng_hi; // slot range of the extent
-    u32* minrank;       // lowest undecided claimer of this round
+    u64* minrank;       // [2][n_rep] lowest undecided claimer (rank << 32 | index) of the even / odd rounds
     u32* ext_l; u32* ext_r;   // per candidate
     // device-resident work lists (three rotating lists of undecided reps, long extensions, wide extents)
     // and their counters (layout: see k_resolve)
@@ -99,13 +105,15 @@ void launch_slot_scatter(const DedupArgs& a, const GenomeTable& gt, cudaStream_t
 u32 chain_tile();
 void launch_chains(const DedupArgs& a, u64* status_fwd, u32* ticket_fwd, u64* status_bwd, u32* ticket_bwd, cudaStream_t st);
 void launch_rep_keys(const DedupArgs& a, u64* skey, cudaStream_t st);
-void launch_extend(const DedupArgs& a, const GenomeTable& gt, const SeedDev& sd, cudaStream_t st); // 2 launches
+int extend_launches();
+void launch_extend(const DedupArgs& a, const GenomeTable& gt, const SeedDev& sd, cudaStream_t st);
 cudaError_t launch_resolve(const DedupArgs& a, cudaStream_t st); // cooperative
 
 // ---- kernels_output.cu
 struct OutputArgs {
-    u32 n_cand;
-    const u8* cstate;
+    u32 n_items;              // reps (or, on rank 0 of the multi-GPU path, gathered matches)
+    const u8* state;          // item accepted iff (state & 15) == 1
+    const u32* item_cand;     // item -> candidate
     const u32* cand_off; const u32* comp_pos; const u8* comp_gs;
     const u32* ext_l; const u32* ext_r;
     u32* flags; const u32* match_idx;
@@ -125,13 +133,13 @@ void launch_uniq_gather(const OutputArgs& a, const u64* sval, u32 L, u32 n_upper
 void launch_fold_lut(const u32* hist, const u8* lut, u32 nbins, u32 world, u32* digit_base, u64* counts, cudaStream_t st);
 void launch_owner_keys(const u64* ghash, u32 n, u32 world, u64* skey, u64* sval, cudaStream_t st);
 void launch_perm_m(const u64* perm, const u32* cand_off, u32 n, u32* m_out, cudaStream_t st);
-void launch_pack_cand(const u64* perm, const u64* poff, const u32* cand_off, const u32* comp_pos, const u8* comp_gs, const u64* ghash, u32 n,
-                      u64* hdr, u64* comps, cudaStream_t st);
+void launch_pack_cand(const u64* perm, const u64* poff, const u32* cand_off, const u32* comp_pos, const u8* comp_gs, const u64* ghash,
+                      const u64* ghash2, u32 n, u64* hdr, u64* comps, cudaStream_t st);
 void launch_hdr_m(const u64* hdr, u32 n, u32* m_out, cudaStream_t st);
 void launch_unpack_cand(const u64* hdr, const u64* comps, const u32* cand_off, u32 n, const GenomeTable& gt, u32* comp_pos, u8* comp_gs,
-                        u64* ghash, u64* bitmap, cudaStream_t st);
-void launch_acc_m(const u8* cstate, const u32* cand_off, u32 n, u32* m_out, cudaStream_t st);
-void launch_pack_match(const u8* cstate, const u32* match_idx, const u32* acomp_off, const u32* cand_off, const u32* comp_pos, const u8* comp_gs,
+                        u64* ghash, u64* ghash2, u64* bitmap, cudaStream_t st);
+void launch_acc_m(const u8* state, const u32* item_cand, const u32* cand_off, u32 n, u32* m_out, cudaStream_t st);
+void launch_pack_match(const u8* state, const u32* item_cand, const u32* match_idx, const u32* acomp_off, const u32* cand_off, const u32* comp_pos, const u8* comp_gs,
                        const u32* ext_l, const u32* ext_r, u32 n, u64* hdr, u64* comps, cudaStream_t st);
 void launch_unpack_match(const u64* hdr, const u64* comps, const u32* cand_off, u32 n, u32* comp_pos, u8* comp_gs, u32* ext_l, u32* ext_r,
-                         u8* cstate, cudaStream_t st);
+                         u8* state, u32* item_cand, cudaStream_t st);

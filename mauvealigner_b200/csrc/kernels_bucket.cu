@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(256) k_emit_unique(EmitUniqueArgs a, RecFmt fm
     u32 prev_g = 0xFFFFFFFFu;
     u32 ui = 0;
     u32 x0 = 0;
-    u64 h = 0x9E3779B97F4A7C15ull;
+    u64 h = 0x9E3779B97F4A7C15ull, h2 = 0xC2B2AE3D27D4EB4Full;
     for (u32 i = s; i < e; ++i) {
         u64 v = fmt.wide ? a.vals[i] : a.keys[i];
         u32 g = rec_genome(fmt, v);
@@ -286,9 +286,11 @@ __global__ void __launch_bounds__(256) k_emit_unique(EmitUniqueArgs a, RecFmt fm
         u64 dg = rev ? (u64)p + x0 : (u64)(u32)(p - x0);
         h ^= (dg << 8) | (u64)(g | (rev ? 0x80u : 0u));
         h *= 0xFF51AFD7ED558CCDull; h ^= h >> 29;
+        h2 = (h2 + ((dg << 8) | (u64)(g | (rev ? 0x80u : 0u)))) * 0x9FB21C651E98DF25ull; h2 ^= h2 >> 32;
         ++k;
     }
     a.ghash[c] = h;
+    a.ghash2[c] = h2 & ~0xFFull;
 }
 
 void launch_emit_unique(const EmitUniqueArgs& a, const RecFmt& fmt, const GenomeTable& gt, u32 n_cand_upper, cudaStream_t st) {

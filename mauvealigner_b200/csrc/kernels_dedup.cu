@@ -26,6 +26,7 @@
 #include "lookback.cuh"
 
 #define INF32 0xFFFFFFFFu
+#define INF64 0xFFFFFFFFFFFFFFFFull
 
 __device__ __forceinline__ u32 slot_rank(const u64* __restrict__ bitmap, const u32* __restrict__ bmrank, u64 gp) {
     u64 w = bitmap[gp >> 6];
@@ -46,6 +47,18 @@ __device__ __forceinline__ bool same_group(const DedupArgs& a, u32 j, u32 e) {
         else if (pj - xj != pe - xe) return false;
     }
     return true;
+}
+
+// Two candidates are taken to be of the same D16 group when both of their independent 64-bit group hashes agree
+// (120 bits compared: a wrong drop needs a simultaneous collision of both); -DMB_VERIFY_GROUPS adds the exact
+// component-wise comparison on top.
+__device__ __forceinline__ bool groups_equal(const DedupArgs& a, u32 c1, u32 c2) {
+#ifdef MB_VERIFY_GROUPS
+    return same_group(a, c1, c2);
+#else
+    (void)a; (void)c1; (void)c2;
+    return true;
+#endif
 }
 
 // ---- slots ---------------------------------------------------------------------------------------
@@ -191,7 +204,6 @@ __global__ void __launch_bounds__(CH_NT) k_chain(DedupArgs a, u64* status, u32* 
             else {
                 u32 c = v[k];
                 bool rep = c < excl && c < a.chain_min[s];
-                a.cstate[c] = rep ? 0 : 2;
                 if (rep) repbits |= 1u << (CH_IPT - 1 - k);
             }
         }
@@ -486,11 +498,9 @@ __device__ __forceinline__ void wl_push(u32* list, u32* count, bool pred, u32 va
     list[base + __popc(m & ((1u << lane) - 1))] = value;
 }
 
-// slot range [rlo, rhi) of all candidates whose first-genome position lies in the extent [x - el, x + er] of
-// candidate c (two rank look-ups in the candidate bitmap)
-__device__ __forceinline__ void extent_slots(const DedupArgs& a, const GenomeTable& gt, u32 c, u32 el, u32 er, u32& rlo, u32& rhi) {
-    u32 off = a.cand_off[c];
-    u64 gp = gt.base_base[a.comp_gs[off] & 0x7F] + a.comp_pos[off];
+// slot range [rlo, rhi) of all candidates whose first-genome position lies in the extent [gp - el, gp + er]
+// (gp = global base index of the first component; two rank look-ups in the candidate bitmap)
+__device__ __forceinline__ void extent_slots(const DedupArgs& a, u64 gp, u32 el, u32 er, u32& rlo, u32& rhi) {
     rlo = slot_rank(a.bitmap, a.bmrank, gp - el);
     rhi = slot_rank(a.bitmap, a.bmrank, gp + er + 1);
 }
@@ -502,52 +512,54 @@ __device__ __forceinline__ bool rec_same_hash(const ulonglong2& p, const ulonglo
     return ((p.x ^ q.x) & 0xFFFF00000000FFFFull) == 0 && (p.y >> 32) == (q.y >> 32);
 }
 
-// ---- extend: a warp takes 32 consecutive reps.  Lane j owns rep j's state; the (rep, component) pairs
-// of the warp are spread over all lanes, so every lane builds exactly one component-vs-first mismatch
-// map per step whatever the multiplicities are; maps are OR-ed per rep in shared memory.  Rounds:
-// centred chunk, then further chunks to the left, then to the right, for the reps that still need
-// them (the pairs of the remaining reps fill the lanes again).  Reps that need more than
-// DD_EXT_ROUNDS chunks are parked for the warp-per-rep kernel.
-#define DD_EXT_ROUNDS 10
-enum { ST_CENTER = 0, ST_LEFT = 1, ST_RIGHT = 2, ST_DONE = 3 };
+// ---- per-rep records in (colour, slot) order: everything the extension and the resolve rounds need about a
+// rep, gathered once by a plain throughput kernel so that those kernels start from one coalesced load
+__global__ void __launch_bounds__(256) k_rep_setup(DedupArgs a) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n_rep) return;
+    const u32 slot = (u32)a.s_key[i];
+    ulonglong2 r = a.slot_rec[slot];
+    const u32 c = (u32)r.y;
+    const u64 h = r.x & HASH_MASK;
+    a.s_rec[i] = make_ulonglong2((h & 0xFFFF000000000000ull) | ((u64)slot << 16) | (h & 0xFFFFull), (((h >> 16) & 0xFFFFFFFFull) << 32) | c);
+    a.s_cand[i] = c;
+    a.s_h2[i] = a.ghash2[c];
+    a.minrank[i] = INF64; a.minrank[(size_t)a.n_rep + i] = INF64;
+    a.reach[i] = 0;
+    a.rstate[i] = 0;
+    const u32 off = a.cand_off[c], m = a.cand_off[c + 1] - off;
+    a.xrec[i] = make_uint4(c, off, m | ((u32)(a.comp_gs[off] & 0x7F) << 8), a.comp_pos[off]);
+}
 
-__global__ void __launch_bounds__(DD_NT) k_extend(DedupArgs a, GenomeTable gt, SeedDev sd) {
-    __shared__ u32 sMap[DD_NT / 32][32][4];
-    __shared__ u32 sRoom[DD_NT / 32][32][2];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const u32 i = blockIdx.x * DD_NT + threadIdx.x;
-    const bool valid = i < a.n_rep;
+// ---- extend: a warp takes 32 reps.  Lane j owns rep j's state; the (rep, component) pairs of the warp
+// are spread over all lanes, so every lane builds exactly one component-vs-first mismatch map per step
+// whatever the multiplicities are; maps are OR-ed per rep in shared memory.  Rounds: centred chunk, then
+// further chunks to the left, then to the right.  k_extend runs the first rounds over all reps; the reps
+// that need more are compacted into a work list and taken up again, densely packed, by k_extend_more
+// (a few launches); what is still unfinished then goes to the warp-per-rep kernel.
+enum { ST_CENTER = 0, ST_LEFT = 1, ST_RIGHT = 2, ST_DONE = 3 };
+struct XLane {
+    u32 c, off, m, p0, g0;      // candidate, its component rows, first component
+    int st; bool rj;            // walk state; rj: the right side still has to be walked
+    u32 b, el, er, room_l, room_r;
+};
+
+template <bool FIRST> // FIRST: round 0 also reduces the rooms of the components
+__device__ __forceinline__ void extend_rounds(const DedupArgs& a, const GenomeTable& gt, const SeedDev& sd, XLane& x, int max_rounds,
+                                              u32 (*sMap)[4], u32 (*sRoom)[2]) {
+    const int lane = threadIdx.x & 31;
     const u32 L = sd.L;
-    u32 c = 0, off = 0, m = 1, p0 = 0, g0 = 0;
-    if (valid) {
-        const u32 slot = (u32)a.s_key[i];
-        ulonglong2 r = a.slot_rec[slot];
-        c = (u32)r.y;
-        const u64 h = r.x & HASH_MASK;
-        a.s_rec[i] = make_ulonglong2((h & 0xFFFF000000000000ull) | ((u64)slot << 16) | (h & 0xFFFFull), (((h >> 16) & 0xFFFFFFFFull) << 32) | c);
-        a.minrank[i] = INF32;
-        a.rstate[i] = 0;
-        off = a.cand_off[c]; m = a.cand_off[c + 1] - off;
-        p0 = a.comp_pos[off]; g0 = a.comp_gs[off] & 0x7F;
-    }
-    if (L > 32) { // uniform: window-by-window warp kernel only
-        wl_push(a.wl_long, a.ctr + 6, valid, i);
-        return;
-    }
     const u32 per_chunk = (3 * L <= 65) ? 2 : 1;
-    int st = valid ? (3 * L <= 64 ? ST_CENTER : ST_LEFT) : ST_DONE;
-    bool rj = true; // the right side still has to be walked
-    u32 b = 0, el = 0, er = 0, room_l = INF32, room_r = INF32;
-    {
-        u32 rl = INF32, rr = INF32;
-        if (valid) { u32 lroom = p0, rroom = gt.len[g0] - L - p0; rl = lroom; rr = rroom; } // component 0 is forward
-        sRoom[warp][lane][0] = rl; sRoom[warp][lane][1] = rr;
+    if (FIRST) {
+        // component 0 is forward
+        sRoom[lane][0] = x.st != ST_DONE ? x.p0 : INF32;
+        sRoom[lane][1] = x.st != ST_DONE ? gt.len[x.g0] - L - x.p0 : INF32;
     }
-    for (int round = 0; round < DD_EXT_ROUNDS; ++round) {
-        const bool want = st != ST_DONE;
+    for (int round = 0; round < max_rounds; ++round) {
+        const bool want = x.st != ST_DONE;
         if (!__any_sync(0xFFFFFFFFu, want)) break;
-        const int o_lo = st == ST_CENTER ? -(int)L : (int)chunk_lo(st == ST_LEFT ? -1 : +1, b, L);
-        const u32 np = want ? m - 1 : 0;
+        const int o_lo = x.st == ST_CENTER ? -(int)L : (int)chunk_lo(x.st == ST_LEFT ? -1 : +1, x.b, L);
+        const u32 np = want ? x.m - 1 : 0;
         u32 incl = np;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -556,8 +568,8 @@ __global__ void __launch_bounds__(DD_NT) k_extend(DedupArgs a, GenomeTable gt, S
         }
         const u32 start = incl - np, T = __shfl_sync(0xFFFFFFFFu, incl, 31);
         u64 a0 = 0, b0 = 0;
-        if (want) oriented_bases64(a.packed, gt, L, g0, p0, false, o_lo, a0, b0);
-        sMap[warp][lane][0] = 0; sMap[warp][lane][1] = 0; sMap[warp][lane][2] = 0; sMap[warp][lane][3] = 0;
+        if (want) oriented_bases64(a.packed, gt, L, x.g0, x.p0, false, o_lo, a0, b0);
+        sMap[lane][0] = 0; sMap[lane][1] = 0; sMap[lane][2] = 0; sMap[lane][3] = 0;
         __syncwarp();
         for (u32 base = 0; base < T; base += 32) {
             const u32 p = base + lane;
@@ -569,7 +581,7 @@ __global__ void __launch_bounds__(DD_NT) k_extend(DedupArgs a, GenomeTable gt, S
                 if (j + step < 32 && sv <= p) j += step;
             }
             const u32 k = p - __shfl_sync(0xFFFFFFFFu, start, j) + 1;
-            const u32 offj = __shfl_sync(0xFFFFFFFFu, off, j);
+            const u32 offj = __shfl_sync(0xFFFFFFFFu, x.off, j);
             const int oj = __shfl_sync(0xFFFFFFFFu, o_lo, j);
             const u64 a0j = __shfl_sync(0xFFFFFFFFu, a0, j), b0j = __shfl_sync(0xFFFFFFFFu, b0, j);
             if (act) {
@@ -578,56 +590,113 @@ __global__ void __launch_bounds__(DD_NT) k_extend(DedupArgs a, GenomeTable gt, S
                 u64 A, B;
                 oriented_bases64(a.packed, gt, L, gs & 0x7F, pk, gs & 0x80, oj, A, B);
                 u64 xa = spread_nz(A ^ a0j), xb = spread_nz(B ^ b0j);
-                if (xa >> 32) atomicOr(&sMap[warp][j][0], (u32)(xa >> 32));
-                if ((u32)xa) atomicOr(&sMap[warp][j][1], (u32)xa);
-                if (xb >> 32) atomicOr(&sMap[warp][j][2], (u32)(xb >> 32));
-                if ((u32)xb) atomicOr(&sMap[warp][j][3], (u32)xb);
-                if (round == 0) {
+                if (xa >> 32) atomicOr(&sMap[j][0], (u32)(xa >> 32));
+                if ((u32)xa) atomicOr(&sMap[j][1], (u32)xa);
+                if (xb >> 32) atomicOr(&sMap[j][2], (u32)(xb >> 32));
+                if ((u32)xb) atomicOr(&sMap[j][3], (u32)xb);
+                if (FIRST && round == 0) {
                     u32 len = gt.len[gs & 0x7F];
                     u32 lroom = pk, rroom = len - L - pk;
                     bool rev = gs & 0x80;
-                    atomicMin(&sRoom[warp][j][0], rev ? rroom : lroom);
-                    atomicMin(&sRoom[warp][j][1], rev ? lroom : rroom);
+                    atomicMin(&sRoom[j][0], rev ? rroom : lroom);
+                    atomicMin(&sRoom[j][1], rev ? lroom : rroom);
                 }
             }
         }
         __syncwarp();
-        if (round == 0) { room_l = sRoom[warp][lane][0]; room_r = sRoom[warp][lane][1]; }
+        if (FIRST && round == 0) { x.room_l = sRoom[lane][0]; x.room_r = sRoom[lane][1]; }
         if (want) {
-            const u64 xa = ((u64)sMap[warp][lane][0] << 32) | sMap[warp][lane][1], xb = ((u64)sMap[warp][lane][2] << 32) | sMap[warp][lane][3];
-            if (st == ST_CENTER) {
+            const u64 xa = ((u64)sMap[lane][0] << 32) | sMap[lane][1], xb = ((u64)sMap[lane][2] << 32) | sMap[lane][3];
+            if (x.st == ST_CENTER) {
                 // chunk index i <-> match offset i - L: first jump windows at 0 (left) and 2L (right), single-step
                 // windows s at L - s (left, descending from L - 1) and L + s (right, ascending from L + 1)
                 u64 bhi, blo;
                 window_map(xa, xb, sd, bhi, blo);
-                const bool lj = room_l >= L && !win_bad(bhi, blo, 0);
-                rj = room_r >= L && !win_bad(bhi, blo, 2 * L);
-                if (!lj) el = min(good_down(bhi, blo, L - 1), min(L, room_l));
-                if (!rj) er = min(good_up(bhi, blo, L + 1), min(L, room_r));
-                b = 1; // the first jump of the side walked next is known to succeed
-                st = lj ? ST_LEFT : (rj ? ST_RIGHT : ST_DONE);
-            } else if (st == ST_LEFT) {
+                const bool lj = x.room_l >= L && !win_bad(bhi, blo, 0);
+                x.rj = x.room_r >= L && !win_bad(bhi, blo, 2 * L);
+                if (!lj) x.el = min(good_down(bhi, blo, L - 1), min(L, x.room_l));
+                if (!x.rj) x.er = min(good_up(bhi, blo, L + 1), min(L, x.room_r));
+                x.b = 1; // the first jump of the side walked next is known to succeed
+                x.st = lj ? ST_LEFT : (x.rj ? ST_RIGHT : ST_DONE);
+            } else if (x.st == ST_LEFT) {
                 u32 out = 0;
-                if (walk_chunk(xa, xb, sd, -1, L, room_l, room_l / L, per_chunk, b, out)) {
-                    el = out;
-                    b = (3 * L <= 64) ? 1 : 0;
-                    st = rj ? ST_RIGHT : ST_DONE;
+                if (walk_chunk(xa, xb, sd, -1, L, x.room_l, x.room_l / L, per_chunk, x.b, out)) {
+                    x.el = out;
+                    x.b = (3 * L <= 64) ? 1 : 0;
+                    x.st = x.rj ? ST_RIGHT : ST_DONE;
                 }
             } else {
                 u32 out = 0;
-                if (walk_chunk(xa, xb, sd, +1, L, room_r, room_r / L, per_chunk, b, out)) { er = out; st = ST_DONE; }
+                if (walk_chunk(xa, xb, sd, +1, L, x.room_r, x.room_r / L, per_chunk, x.b, out)) { x.er = out; x.st = ST_DONE; }
             }
         }
         __syncwarp();
     }
-    const bool is_long = valid && st != ST_DONE;
-    if (valid && !is_long) {
-        a.ext_l[c] = el; a.ext_r[c] = er;
+}
+
+// done: extents + slot range; unfinished: state saved, rep appended to `out_list` (or to the long list when `last`)
+__device__ __forceinline__ void extend_finish(const DedupArgs& a, const GenomeTable& gt, bool valid, u32 i, const XLane& x, u32* out_list,
+                                              u32* out_count, bool last) {
+    const bool more = valid && x.st != ST_DONE;
+    if (valid && !more) {
+        a.ext_l[x.c] = x.el; a.ext_r[x.c] = x.er;
         u32 rlo, rhi;
-        extent_slots(a, gt, c, el, er, rlo, rhi);
+        extent_slots(a, gt.base_base[x.g0] + x.p0, x.el, x.er, rlo, rhi);
         a.rng_lo[i] = rlo; a.rng_hi[i] = rhi;
     }
-    wl_push(a.wl_long, a.ctr + 6, is_long, i);
+    if (more && !last) {
+        a.xstate[i] = make_uint4((u32)x.st | (x.rj ? 4u : 0u), x.b, x.room_l, x.room_r);
+        a.ext_l[x.c] = x.el; a.ext_r[x.c] = x.er;
+    }
+    wl_push(last ? a.wl_long : out_list, last ? a.ctr + 6 : out_count, more, i);
+}
+
+#define DD_EXT_FIRST_ROUNDS 2
+#define DD_EXT_MORE_ROUNDS 4
+
+__global__ void __launch_bounds__(DD_NT) k_extend(DedupArgs a, GenomeTable gt, SeedDev sd, u32* out_list, u32* out_count) {
+    __shared__ u32 sMap[DD_NT / 32][32][4];
+    __shared__ u32 sRoom[DD_NT / 32][32][2];
+    const int warp = threadIdx.x >> 5;
+    const u32 i = blockIdx.x * DD_NT + threadIdx.x;
+    const bool valid = i < a.n_rep;
+    const u32 L = sd.L;
+    XLane x{0, 0, 1, 0, 0, ST_DONE, true, 0, 0, 0, INF32, INF32};
+    if (valid) {
+        uint4 q = a.xrec[i];
+        x.c = q.x; x.off = q.y; x.m = q.z & 0xFFu; x.g0 = q.z >> 8; x.p0 = q.w;
+        x.st = 3 * L <= 64 ? ST_CENTER : ST_LEFT;
+    }
+    if (L > 32) { // uniform: window-by-window warp kernel only
+        wl_push(a.wl_long, a.ctr + 6, valid, i);
+        return;
+    }
+    extend_rounds<true>(a, gt, sd, x, DD_EXT_FIRST_ROUNDS, sMap[warp], sRoom[warp]);
+    extend_finish(a, gt, valid, i, x, out_list, out_count, false);
+}
+
+// the unfinished reps of the previous launch, 32 per warp
+__global__ void __launch_bounds__(DD_NT) k_extend_more(DedupArgs a, GenomeTable gt, SeedDev sd, const u32* in_list, const u32* in_count, u32* out_list,
+                                                       u32* out_count, int last) {
+    __shared__ u32 sMap[DD_NT / 32][32][4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const u32 n = *in_count;
+    const u32 gwarp = (blockIdx.x * DD_NT + threadIdx.x) >> 5, nwarps = (gridDim.x * DD_NT) >> 5;
+    for (u32 base = gwarp * 32; base < n; base += nwarps * 32) {
+        const bool valid = base + lane < n;
+        u32 i = 0;
+        XLane x{0, 0, 1, 0, 0, ST_DONE, true, 0, 0, 0, INF32, INF32};
+        if (valid) {
+            i = in_list[base + lane];
+            uint4 q = a.xrec[i];
+            x.c = q.x; x.off = q.y; x.m = q.z & 0xFFu; x.g0 = q.z >> 8; x.p0 = q.w;
+            uint4 s = a.xstate[i];
+            x.st = (int)(s.x & 3u); x.rj = (s.x & 4u) != 0; x.b = s.y; x.room_l = s.z; x.room_r = s.w;
+            x.el = a.ext_l[x.c]; x.er = a.ext_r[x.c];
+        }
+        extend_rounds<false>(a, gt, sd, x, DD_EXT_MORE_ROUNDS, sMap[warp], nullptr);
+        extend_finish(a, gt, valid, i, x, out_list, out_count, last != 0);
+    }
 }
 
 __global__ void __launch_bounds__(DD_NT) k_extend_long(DedupArgs a, GenomeTable gt, SeedDev sd) {
@@ -653,46 +722,51 @@ __global__ void __launch_bounds__(DD_NT) k_extend_long(DedupArgs a, GenomeTable 
         if (lane == 0) {
             a.ext_l[c] = el; a.ext_r[c] = er;
             u32 rlo, rhi;
-            extent_slots(a, gt, c, el, er, rlo, rhi);
+            extent_slots(a, gt.base_base[cgs[0] & 0x7F] + cpos[0], el, er, rlo, rhi);
             a.rng_lo[i] = rlo; a.rng_hi[i] = rhi;
         }
     }
 }
 
-// Rep state: 0 undecided, 1 accepted, 2 dropped, 3 covered (contained in an accepted match: dropped at its
-// next decide); bit 7: its last claim walk found a target.
+// Rep state: 0 undecided, 1 accepted, 2 dropped; flag bit 6: lives on the wide list.
 #define RS_MASK 0x0Fu
-#define RS_COVERED 3u
-#define RS_TARGETS 0x80u
 #define RS_WIDE 0x40u
 #define DD_WALK_MAX 192 // neighbours one thread visits per direction before the rep is handed to a warp
 
-// Visit the same-colour reps whose slot lies in rep i's extent [rlo, rhi): they are the neighbours of i in
-// the (colour, slot) order.  `first`/`stride` = 0/1 for one thread, lane/32 for a warp.  CLAIM: atomicMin of
-// i's rank on every undecided higher-rank rep of the same group hash (a claim only delays its target, so
-// the hash alone is enough: a false claim lapses when the claimer is decided).  COVER (i is accepted): those
-// reps are contained in it (D16) — verified component by component, because a cover drops its target.
-// Returns the number of targets, or -1 when a single thread ran out of its walk budget.
-template <bool COVER, bool WARP>
-__device__ __forceinline__ int walk_neighbours(const DedupArgs& a, u32 i, const ulonglong2& me, u32 rlo, u32 rhi) {
+// Visit the neighbours of rep i in the (colour, slot) order.  `first`/`stride` = 0/1 for one thread, lane/32 for
+// a warp.
+// CLAIM: over the same-colour reps whose slot lies in i's extent [rlo, rhi): every undecided higher-rank rep of
+//   the same group hash gets atomicMin(rank:index of i) and atomicMax(index distance).  A claim only delays its
+//   target, so the 64-bit hash is enough: a false claim lapses when the claimer is decided.
+// PULL: over the reps within `reach[i]` indices (no claimer of i was ever further away): is there an ACCEPTED
+//   lower-rank rep of i's group (hash + second hash) whose extent contains i's slot?  Then i is contained (D16).
+// Returns the number of hits, or -1 when a single thread ran out of its walk budget.
+template <bool PULL, bool WARP>
+__device__ __forceinline__ int walk_neighbours(const DedupArgs& a, u32 i, const ulonglong2& me, u32 rlo, u32 rhi, u64* __restrict__ mr) {
     const u64 klo = REC_COL(me.x) | ((u64)rlo << 16), khi = REC_COL(me.x) | ((u64)rhi << 16);
-    const u32 c = (u32)me.y;
+    const u32 c = (u32)me.y, myslot = (u32)(me.x >> 16);
     const u32 first = WARP ? (threadIdx.x & 31) : 0, stride = WARP ? 32 : 1;
+    const u32 reach = PULL ? a.reach[i] : 0;
+    const u64 myh2 = PULL ? a.s_h2[i] : 0;
     int found = 0;
     for (int dir = 0; dir < 2; ++dir) {
         u32 steps = 0;
         for (u32 d = 1 + first;; d += stride) {
             bool in = dir == 0 ? (u64)i + d < a.n_rep : d <= i;
+            if (PULL) in = in && d <= reach;
             ulonglong2 r = make_ulonglong2(0, 0);
+            const u32 t = dir == 0 ? i + d : i - d;
             if (in) {
-                r = a.s_rec[dir == 0 ? i + d : i - d];
-                in = dir == 0 ? r.x < khi : r.x >= klo;
+                r = a.s_rec[t];
+                if (!PULL) in = dir == 0 ? r.x < khi : r.x >= klo;
             }
-            if (in && rec_same_hash(me, r) && (u32)r.y > c) {
-                const u32 t = dir == 0 ? i + d : i - d;
-                if ((a.rstate[t] & RS_MASK) == 0) {
-                    if (COVER) { if (same_group(a, c, (u32)r.y)) { a.rstate[t] = RS_COVERED; ++found; } }
-                    else { atomicMin(&a.minrank[t], c); ++found; }
+            if (in && rec_same_hash(me, r)) {
+                if (PULL) {
+                    if ((u32)r.y < c && (a.rstate[t] & RS_MASK) == 1 && a.s_h2[t] == myh2 && myslot >= a.rng_lo[t] && myslot < a.rng_hi[t] && groups_equal(a, c, (u32)r.y)) ++found;
+                } else if ((u32)r.y > c && (a.rstate[t] & RS_MASK) == 0) {
+                    atomicMin((unsigned long long*)&mr[t], ((u64)c << 32) | i);
+                    atomicMax(&a.reach[t], d);
+                    ++found;
                 }
             }
             if (WARP) { if (!__any_sync(0xFFFFFFFFu, in)) break; }
@@ -709,6 +783,19 @@ __device__ __forceinline__ u64 gtimer() { u64 t; asm volatile("mov.u64 %0, %glob
 // optional phase trace (a.trace != null): thread 0 appends (tag, globaltimer ns) pairs after each barrier
 #define DD_TRACE(tag) do { if (t0 && a.trace) { u64 k = a.trace[0]; if (k < 4000) { a.trace[2 + 2 * k] = (tag); a.trace[3 + 2 * k] = gtimer(); a.trace[0] = k + 1; } } } while (0)
 
+// One decide step of an undecided rep i (claims of this round are complete): unclaimed -> accepted; the lowest
+// claimer is itself unclaimed (so it is accepted in this very phase) and of the same group -> contained, dropped;
+// otherwise still undecided.  Returns true when i stays undecided.
+__device__ __forceinline__ bool decide_rep(const DedupArgs& a, u32 i, const u64* __restrict__ mr_cur, u64* __restrict__ mr_nxt) {
+    const u64 m = mr_cur[i];
+    if (m == INF64) { a.rstate[i] = (a.rstate[i] & RS_WIDE) | 1; return false; }
+    const u32 mi = (u32)m;
+    const u32 ms = a.rstate[mi] & RS_MASK; // 0, or 1 when that rep has just been decided in this phase
+    if (ms <= 1 && mr_cur[mi] == INF64 && a.s_h2[mi] == a.s_h2[i] && groups_equal(a, a.s_cand[mi], a.s_cand[i])) { a.rstate[i] = (a.rstate[i] & RS_WIDE) | 2; return false; }
+    mr_nxt[i] = INF64;
+    return true;
+}
+
 // ctr layout (u32): [0..2] narrow-list counters (rotating; round 0 takes every rep), [3..5] wide-list
 // counters (rotating), [6] long list, [9] rounds, [10] wide items.  A counter is reset one round before
 // it is written and never while it may still be read.
@@ -724,71 +811,60 @@ __global__ void __launch_bounds__(DD_NT) k_resolve(DedupArgs a) {
     DD_TRACE(1);
     for (u32 r = 0;; ++r) {
         const u32 cur = r % 3, nxt = (r + 1) % 3, spare = (r + 2) % 3;
+        u64* mr_cur = a.minrank + (size_t)(r & 1) * a.n_rep;
+        u64* mr_nxt = a.minrank + (size_t)((r + 1) & 1) * a.n_rep;
         if (t0) { ctr[spare] = 0; ctr[3 + spare] = 0; ctr[9] += 1; }
         const u32 n_narrow = r == 0 ? a.n_rep : ctr[cur];
-        // ---- claim, one thread per undecided rep; reps with too many neighbours go to the wide list (round 0)
-        for (u32 t = gtid; t < n_narrow; t += gsz) {
-            u32 i = r == 0 ? t : nl[cur][t];
-            u32 rlo = a.rng_lo[i], rhi = a.rng_hi[i];
-            if (rhi - rlo < 2) continue;                            // alone in its extent
-            if ((a.rstate[i] & RS_MASK) == RS_COVERED) continue;    // as good as dropped
-            ulonglong2 me = a.s_rec[i];
-            int f = walk_neighbours<false, false>(a, i, me, rlo, rhi);
-            if (f < 0) { a.rstate[i] = RS_WIDE; wd[cur][atomicAdd(ctr + 3 + cur, 1u)] = i; } // lives on the wide list from now on
-            else if (f > 0) a.rstate[i] = RS_TARGETS;
+        // ---- round 0: claim, one thread per rep; reps with too many neighbours go to the wide list.
+        // Later rounds: few reps are left, each takes a whole warp (pull, then claim).
+        if (r == 0) {
+            for (u32 i = gtid; i < n_narrow; i += gsz) {
+                u32 rlo = a.rng_lo[i], rhi = a.rng_hi[i];
+                if (rhi - rlo < 2) continue; // alone in its extent
+                ulonglong2 me = a.s_rec[i];
+                if (walk_neighbours<false, false>(a, i, me, rlo, rhi, mr_cur) < 0) { a.rstate[i] = RS_WIDE; wd[cur][atomicAdd(ctr + 3 + cur, 1u)] = i; }
+            }
+        } else {
+            for (u32 t = gwarp; t < n_narrow; t += nwarps) {
+                u32 i = nl[cur][t];
+                ulonglong2 me = a.s_rec[i];
+                u32 rlo = a.rng_lo[i], rhi = a.rng_hi[i];
+                int f = walk_neighbours<true, true>(a, i, me, rlo, rhi, mr_cur);
+                if (__any_sync(0xFFFFFFFFu, f > 0)) { if (lane == 0) a.rstate[i] = 2; continue; } // contained in an accepted match
+                if (rhi - rlo >= 2) walk_neighbours<false, true>(a, i, me, rlo, rhi, mr_cur);
+            }
         }
         grid.sync(); // the wide list of this round is complete only now
         if (t0 && r == 0) ctr[10] = ctr[3];
         const u32 n_wide = ctr[3 + cur];
-        // ---- claim, wide: one warp per rep
+        // ---- pull + claim, wide: one warp per rep
         for (u32 t = gwarp; t < n_wide; t += nwarps) {
             u32 i = wd[cur][t];
-            if ((a.rstate[i] & RS_MASK) == RS_COVERED) continue;
             ulonglong2 me = a.s_rec[i];
-            walk_neighbours<false, true>(a, i, me, a.rng_lo[i], a.rng_hi[i]);
+            u32 rlo = a.rng_lo[i], rhi = a.rng_hi[i];
+            if (r > 0) {
+                int f = walk_neighbours<true, true>(a, i, me, rlo, rhi, mr_cur);
+                if (__any_sync(0xFFFFFFFFu, f > 0)) { if (lane == 0) a.rstate[i] = RS_WIDE | 2; continue; }
+            }
+            walk_neighbours<false, true>(a, i, me, rlo, rhi, mr_cur);
         }
         grid.sync();
         DD_TRACE(5);
-        // ---- decide, narrow: covered -> dropped, unclaimed -> accepted, else still undecided
+        // ---- decide, narrow
         for (u32 base = blockIdx.x * DD_NT; base < n_narrow; base += gsz) {
             u32 t = base + threadIdx.x;
             bool keep = false;
             u32 i = 0;
             if (t < n_narrow) {
                 i = r == 0 ? t : nl[cur][t];
-                const u32 stt = a.rstate[i];
-                if (!(stt & RS_WIDE)) { // not handed to the wide list
-                    ulonglong2 me = a.s_rec[i];
-                    const u32 c = (u32)me.y;
-                    if ((stt & RS_MASK) == RS_COVERED) { a.rstate[i] = 2; a.cstate[c] = 2; }
-                    else if (a.minrank[i] == INF32) {
-                        // accepted: every undecided higher-rank rep of this group inside the extent is contained
-                        a.rstate[i] = 1; a.cstate[c] = 1;
-                        if (stt & RS_TARGETS) walk_neighbours<true, false>(a, i, me, a.rng_lo[i], a.rng_hi[i]);
-                    } else {
-                        a.minrank[i] = INF32;
-                        keep = true;
-                    }
-                }
+                if (a.rstate[i] == 0) keep = decide_rep(a, i, mr_cur, mr_nxt); // undecided and not on the wide list
             }
             wl_push(nl[nxt], ctr + nxt, keep, i);
         }
         // ---- decide, wide
-        for (u32 t = gwarp; t < n_wide; t += nwarps) {
+        for (u32 t = gwarp * 32 + lane; t < n_wide; t += nwarps * 32) {
             u32 i = wd[cur][t];
-            ulonglong2 me = a.s_rec[i];
-            const u32 c = (u32)me.y;
-            int d = 2;
-            if (lane == 0) {
-                if ((a.rstate[i] & RS_MASK) == RS_COVERED) d = 0;
-                else if (a.minrank[i] == INF32) d = 1;
-            }
-            d = __shfl_sync(0xFFFFFFFFu, d, 0);
-            if (d == 1) walk_neighbours<true, true>(a, i, me, a.rng_lo[i], a.rng_hi[i]);
-            if (lane == 0) {
-                if (d == 2) { a.minrank[i] = INF32; wd[nxt][atomicAdd(ctr + 3 + nxt, 1u)] = i; }
-                else { a.rstate[i] = d == 1 ? 1 : 2; a.cstate[c] = d == 1 ? 1 : 2; }
-            }
+            if ((a.rstate[i] & RS_MASK) == 0 && decide_rep(a, i, mr_cur, mr_nxt)) wd[nxt][atomicAdd(ctr + 3 + nxt, 1u)] = i;
         }
         grid.sync();
         DD_TRACE(6);
@@ -809,9 +885,21 @@ void launch_chains(const DedupArgs& a, u64* status_fwd, u32* ticket_fwd, u64* st
 void launch_rep_keys(const DedupArgs& a, u64* skey, cudaStream_t st) {
     if (a.n_cand) k_rep_keys<<<div_up(a.n_cand, 256), 256, 0, st>>>(a, skey);
 }
+// k_extend over all reps, then DD_EXT_MORE launches over the shrinking list of unfinished reps (ping-pong lists
+// wd0 / wd1 with counters ctr[12] / ctr[13]), then the warp-per-rep kernel for what is left
+#define DD_EXT_MORE 3
+int extend_launches() { return 3 + DD_EXT_MORE; }
 void launch_extend(const DedupArgs& a, const GenomeTable& gt, const SeedDev& sd, cudaStream_t st) {
     if (a.n_rep == 0) return;
-    k_extend<<<div_up(a.n_rep, DD_NT), DD_NT, 0, st>>>(a, gt, sd);
+    u32* list[2] = {a.wd0, a.wd1};
+    u32* cnt[2] = {a.ctr + 12, a.ctr + 13};
+    k_rep_setup<<<div_up(a.n_rep, 256), 256, 0, st>>>(a);
+    k_extend<<<div_up(a.n_rep, DD_NT), DD_NT, 0, st>>>(a, gt, sd, list[0], cnt[0]);
+    for (int r = 0; r < DD_EXT_MORE; ++r) {
+        int in = r & 1, out = in ^ 1;
+        cudaMemsetAsync(cnt[out], 0, 4, st);
+        k_extend_more<<<148 * 4, DD_NT, 0, st>>>(a, gt, sd, list[in], cnt[in], list[out], cnt[out], r == DD_EXT_MORE - 1);
+    }
     k_extend_long<<<148 * 4, DD_NT, 0, st>>>(a, gt, sd);
 }
 cudaError_t launch_resolve(const DedupArgs& a, cudaStream_t st) {

@@ -58,24 +58,24 @@ void launch_perm_m(const u64* perm, const u32* cand_off, u32 n, u32* m_out, cuda
 
 __global__ void __launch_bounds__(256) k_pack_cand(const u64* __restrict__ perm, const u64* __restrict__ poff, const u32* __restrict__ cand_off,
                                                    const u32* __restrict__ comp_pos, const u8* __restrict__ comp_gs, const u64* __restrict__ ghash,
-                                                   u32 n, u64* __restrict__ hdr, u64* __restrict__ comps) {
+                                                   const u64* __restrict__ ghash2, u32 n, u64* __restrict__ hdr, u64* __restrict__ comps) {
     u32 j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     u32 c = (u32)perm[j];
     u32 off = cand_off[c], m = cand_off[c + 1] - off;
     hdr[2 * (u64)j] = ghash[c];
-    hdr[2 * (u64)j + 1] = m;
+    hdr[2 * (u64)j + 1] = (ghash2[c] & ~0xFFull) | m; // m <= 64
     u64 o = poff[j];
     for (u32 k = 0; k < m; ++k) comps[o + k] = (u64)comp_pos[off + k] | ((u64)comp_gs[off + k] << 32);
 }
-void launch_pack_cand(const u64* perm, const u64* poff, const u32* cand_off, const u32* comp_pos, const u8* comp_gs, const u64* ghash, u32 n,
-                      u64* hdr, u64* comps, cudaStream_t st) {
-    if (n) k_pack_cand<<<div_up(n, 256), 256, 0, st>>>(perm, poff, cand_off, comp_pos, comp_gs, ghash, n, hdr, comps);
+void launch_pack_cand(const u64* perm, const u64* poff, const u32* cand_off, const u32* comp_pos, const u8* comp_gs, const u64* ghash,
+                      const u64* ghash2, u32 n, u64* hdr, u64* comps, cudaStream_t st) {
+    if (n) k_pack_cand<<<div_up(n, 256), 256, 0, st>>>(perm, poff, cand_off, comp_pos, comp_gs, ghash, ghash2, n, hdr, comps);
 }
 
 __global__ void __launch_bounds__(256) k_hdr_m(const u64* __restrict__ hdr, u32 n, u32* __restrict__ m_out) {
     u32 j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < n) m_out[j] = (u32)hdr[2 * (u64)j + 1];
+    if (j < n) m_out[j] = (u32)(hdr[2 * (u64)j + 1] & 0xFFu);
 }
 void launch_hdr_m(const u64* hdr, u32 n, u32* m_out, cudaStream_t st) {
     if (n) k_hdr_m<<<div_up(n, 256), 256, 0, st>>>(hdr, n, m_out);
@@ -84,11 +84,12 @@ void launch_hdr_m(const u64* hdr, u32 n, u32* m_out, cudaStream_t st) {
 // received candidate rows -> candidate CSR of the owner + its (first genome, position) bitmap
 __global__ void __launch_bounds__(256) k_unpack_cand(const u64* __restrict__ hdr, const u64* __restrict__ comps, const u32* __restrict__ cand_off,
                                                      u32 n, GenomeTable gt, u32* __restrict__ comp_pos, u8* __restrict__ comp_gs,
-                                                     u64* __restrict__ ghash, u64* __restrict__ bitmap) {
+                                                     u64* __restrict__ ghash, u64* __restrict__ ghash2, u64* __restrict__ bitmap) {
     u32 j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     u32 off = cand_off[j], m = cand_off[j + 1] - off;
     ghash[j] = hdr[2 * (u64)j];
+    ghash2[j] = hdr[2 * (u64)j + 1] & ~0xFFull;
     for (u32 k = 0; k < m; ++k) {
         u64 w = comps[off + k];
         u32 p = (u32)w;
@@ -102,47 +103,52 @@ __global__ void __launch_bounds__(256) k_unpack_cand(const u64* __restrict__ hdr
     }
 }
 void launch_unpack_cand(const u64* hdr, const u64* comps, const u32* cand_off, u32 n, const GenomeTable& gt, u32* comp_pos, u8* comp_gs,
-                        u64* ghash, u64* bitmap, cudaStream_t st) {
-    if (n) k_unpack_cand<<<div_up(n, 256), 256, 0, st>>>(hdr, comps, cand_off, n, gt, comp_pos, comp_gs, ghash, bitmap);
+                        u64* ghash, u64* ghash2, u64* bitmap, cudaStream_t st) {
+    if (n) k_unpack_cand<<<div_up(n, 256), 256, 0, st>>>(hdr, comps, cand_off, n, gt, comp_pos, comp_gs, ghash, ghash2, bitmap);
 }
 
 // component count of every accepted candidate (0 for the others)
-__global__ void __launch_bounds__(256) k_acc_m(const u8* __restrict__ cstate, const u32* __restrict__ cand_off, u32 n, u32* __restrict__ m_out) {
-    u32 c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c < n) m_out[c] = cstate[c] == 1 ? cand_off[c + 1] - cand_off[c] : 0u;
+__global__ void __launch_bounds__(256) k_acc_m(const u8* __restrict__ state, const u32* __restrict__ item_cand, const u32* __restrict__ cand_off, u32 n,
+                                               u32* __restrict__ m_out) {
+    u32 it = blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= n) return;
+    u32 c = item_cand[it];
+    m_out[it] = (state[it] & 15u) == 1u ? cand_off[c + 1] - cand_off[c] : 0u;
 }
-void launch_acc_m(const u8* cstate, const u32* cand_off, u32 n, u32* m_out, cudaStream_t st) {
-    if (n) k_acc_m<<<div_up(n, 256), 256, 0, st>>>(cstate, cand_off, n, m_out);
+void launch_acc_m(const u8* state, const u32* item_cand, const u32* cand_off, u32 n, u32* m_out, cudaStream_t st) {
+    if (n) k_acc_m<<<div_up(n, 256), 256, 0, st>>>(state, item_cand, cand_off, n, m_out);
 }
 
-__global__ void __launch_bounds__(256) k_pack_match(const u8* __restrict__ cstate, const u32* __restrict__ match_idx, const u32* __restrict__ acomp_off,
+__global__ void __launch_bounds__(256) k_pack_match(const u8* __restrict__ state, const u32* __restrict__ item_cand, const u32* __restrict__ match_idx, const u32* __restrict__ acomp_off,
                                                     const u32* __restrict__ cand_off, const u32* __restrict__ comp_pos, const u8* __restrict__ comp_gs,
                                                     const u32* __restrict__ ext_l, const u32* __restrict__ ext_r, u32 n, u64* __restrict__ hdr,
                                                     u64* __restrict__ comps) {
-    u32 c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= n || cstate[c] != 1) return;
-    u32 j = match_idx[c];
+    u32 it = blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= n || (state[it] & 15u) != 1u) return;
+    u32 c = item_cand[it];
+    u32 j = match_idx[it];
     u32 off = cand_off[c], m = cand_off[c + 1] - off;
     hdr[2 * (u64)j] = (u64)ext_l[c] | ((u64)ext_r[c] << 32);
     hdr[2 * (u64)j + 1] = m;
-    u32 o = acomp_off[c];
+    u32 o = acomp_off[it];
     for (u32 k = 0; k < m; ++k) comps[o + k] = (u64)comp_pos[off + k] | ((u64)comp_gs[off + k] << 32);
 }
-void launch_pack_match(const u8* cstate, const u32* match_idx, const u32* acomp_off, const u32* cand_off, const u32* comp_pos, const u8* comp_gs,
+void launch_pack_match(const u8* state, const u32* item_cand, const u32* match_idx, const u32* acomp_off, const u32* cand_off, const u32* comp_pos, const u8* comp_gs,
                        const u32* ext_l, const u32* ext_r, u32 n, u64* hdr, u64* comps, cudaStream_t st) {
-    if (n) k_pack_match<<<div_up(n, 256), 256, 0, st>>>(cstate, match_idx, acomp_off, cand_off, comp_pos, comp_gs, ext_l, ext_r, n, hdr, comps);
+    if (n) k_pack_match<<<div_up(n, 256), 256, 0, st>>>(state, item_cand, match_idx, acomp_off, cand_off, comp_pos, comp_gs, ext_l, ext_r, n, hdr, comps);
 }
 
 // gathered match rows -> "all accepted" candidate arrays of rank 0 (input of the output stage)
 __global__ void __launch_bounds__(256) k_unpack_match(const u64* __restrict__ hdr, const u64* __restrict__ comps, const u32* __restrict__ cand_off,
                                                       u32 n, u32* __restrict__ comp_pos, u8* __restrict__ comp_gs, u32* __restrict__ ext_l,
-                                                      u32* __restrict__ ext_r, u8* __restrict__ cstate) {
+                                                      u32* __restrict__ ext_r, u8* __restrict__ state, u32* __restrict__ item_cand) {
     u32 j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     u32 off = cand_off[j], m = cand_off[j + 1] - off;
     u64 e = hdr[2 * (u64)j];
     ext_l[j] = (u32)e; ext_r[j] = (u32)(e >> 32);
-    cstate[j] = 1;
+    state[j] = 1;
+    item_cand[j] = j;
     for (u32 k = 0; k < m; ++k) {
         u64 w = comps[off + k];
         comp_pos[off + k] = (u32)w;
@@ -150,6 +156,6 @@ __global__ void __launch_bounds__(256) k_unpack_match(const u64* __restrict__ hd
     }
 }
 void launch_unpack_match(const u64* hdr, const u64* comps, const u32* cand_off, u32 n, u32* comp_pos, u8* comp_gs, u32* ext_l, u32* ext_r,
-                         u8* cstate, cudaStream_t st) {
-    if (n) k_unpack_match<<<div_up(n, 256), 256, 0, st>>>(hdr, comps, cand_off, n, comp_pos, comp_gs, ext_l, ext_r, cstate);
+                         u8* state, u32* item_cand, cudaStream_t st) {
+    if (n) k_unpack_match<<<div_up(n, 256), 256, 0, st>>>(hdr, comps, cand_off, n, comp_pos, comp_gs, ext_l, ext_r, state, item_cand);
 }

@@ -7,15 +7,16 @@
 
 __global__ void __launch_bounds__(256) k_uniq_flags(OutputArgs a) {
     u32 c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c < a.n_cand) a.flags[c] = a.cstate[c] == 1 ? 1u : 0u;
+    if (c < a.n_items) a.flags[c] = (a.state[c] & 15u) == 1u ? 1u : 0u;
 }
 
 // D18 for MODE_UNIQUE compares the dense vectors (|start[0]|..|start[N-1]|), 0 = absent.  For sparse
 // matches this is: larger first genome index sorts first; then its start; then the next component...
 __global__ void __launch_bounds__(256) k_uniq_keys(OutputArgs a, int sbits) {
-    u32 c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= a.n_cand || a.cstate[c] != 1) return;
-    u32 mi = a.match_idx[c];
+    u32 it = blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= a.n_items || (a.state[it] & 15u) != 1u) return;
+    u32 mi = a.match_idx[it];
+    u32 c = a.item_cand[it];
     u32 off = a.cand_off[c];
     u32 f = a.comp_gs[off] & 0x7F;
     u64 st = (u64)a.comp_pos[off] - a.ext_l[c] + 1;
@@ -118,10 +119,10 @@ __global__ void __launch_bounds__(256) k_uniq_gather(OutputArgs a, const u64* __
 }
 
 void launch_uniq_flags(const OutputArgs& a, cudaStream_t st) {
-    if (a.n_cand) k_uniq_flags<<<div_up(a.n_cand, 256), 256, 0, st>>>(a);
+    if (a.n_items) k_uniq_flags<<<div_up(a.n_items, 256), 256, 0, st>>>(a);
 }
 void launch_uniq_keys(const OutputArgs& a, int sbits, cudaStream_t st) {
-    if (a.n_cand) k_uniq_keys<<<div_up(a.n_cand, 256), 256, 0, st>>>(a, sbits);
+    if (a.n_items) k_uniq_keys<<<div_up(a.n_items, 256), 256, 0, st>>>(a, sbits);
 }
 void launch_uniq_tiefix(const OutputArgs& a, const u64* skey, u64* sval, u32 L, u32 n_upper, cudaStream_t st) {
     if (n_upper) k_uniq_tiefix<<<div_up(n_upper, 256), 256, 0, st>>>(a, skey, sval, L);
