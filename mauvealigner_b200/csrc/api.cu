@@ -28,6 +28,9 @@ static int build_seed(uint64_t pattern, SeedDev& sd) {
         ++nrun;
     }
     sd.nrun = nrun;
+    int t = 0;
+    for (int o = 0; o < L; ++o)
+        if ((pattern >> (L - 1 - o)) & 1) sd.care_off[t++] = (u8)o;
     return MB_OK;
 }
 
@@ -482,7 +485,7 @@ int mbi_reserve_candidates(mb_ctx* c, u32 n_cand, u32 n_ccomp, u64 bases) {
     TRY(c->reserve(c->xrec, nc * 16));
     TRY(c->reserve(c->sort_kA, nc * 8));
     TRY(c->reserve(c->sort_kB, nc * 8));
-    TRY(c->reserve(c->slot_gp, nc * 16));
+    TRY(c->reserve(c->slot_gp, nc * 32));
     TRY(c->reserve(c->link_bits, nc / 8 + 16));
     TRY(c->reserve(c->chain_min, nc * 4));
     TRY(c->reserve(c->minrank, nc * 16));

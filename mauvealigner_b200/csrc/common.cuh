@@ -30,6 +30,7 @@ struct SeedDev {
     // result left-aligned in 64 bits (2w <= 62 significant bits)
     u64 runmask_hi[32], runmask_lo[32];
     int lshift[32];
+    u8 care_off[32];  // the w cared window offsets, ascending
 };
 
 // Record format

@@ -62,23 +62,27 @@ __device__ __forceinline__ bool groups_equal(const DedupArgs& a, u32 c1, u32 c2)
 }
 
 // ---- slots ---------------------------------------------------------------------------------------
-// candidate -> slot (rank of its first-genome position among all candidates).  One 16-byte record per
-// slot: x = group hash with bit 0 replaced by "the previous base of the genome holds a candidate too"
-// (then that candidate is slot s-1), y = candidate id.  One scattered 16-byte store per candidate.
+// candidate -> slot (rank of its first-genome position among all candidates).  One 32-byte record per slot
+// (one full-sector scattered store per candidate; everything later steps need about the candidate, so that
+// they never chase the candidate CSR again):
+//   a.x = group hash with bit 0 replaced by "the previous base of the genome holds a candidate too" (then
+//         that candidate is slot s-1),  a.y = candidate | components << 32 | first genome << 40
+//   b.x = second group hash,             b.y = first component row | first position << 32
 #define HASH_MASK (~1ull)
 __global__ void __launch_bounds__(256) k_slot_scatter(DedupArgs a, GenomeTable gt) {
     u32 c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= a.n_cand) return;
-    u32 off = a.cand_off[c];
-    u32 g = a.comp_gs[off] & 0x7F;
-    u64 gp = gt.base_base[g] + a.comp_pos[off];
+    u32 off = a.cand_off[c], m = a.cand_off[c + 1] - off;
+    u32 g = a.comp_gs[off] & 0x7F, p = a.comp_pos[off];
+    u64 gp = gt.base_base[g] + p;
     u64 w = a.bitmap[gp >> 6];
     u32 s = a.bmrank[gp >> 6] + (u32)__popcll(w & ((1ull << (gp & 63)) - 1));
     // a candidate never sits on the last L-1 bases of a genome, so base gp-1 belongs to the same genome
     // whenever it holds a candidate
     u64 adj = 0;
     if (gp > 0) adj = (gp & 63) ? (w >> ((gp & 63) - 1)) & 1 : (a.bitmap[(gp >> 6) - 1] >> 63) & 1;
-    a.slot_rec[s] = make_ulonglong2((a.ghash[c] & HASH_MASK) | adj, (u64)c);
+    a.slot_rec[2 * (size_t)s] = make_ulonglong2((a.ghash[c] & HASH_MASK) | adj, (u64)c | ((u64)m << 32) | ((u64)g << 40));
+    a.slot_rec[2 * (size_t)s + 1] = make_ulonglong2(a.ghash2[c], (u64)off | ((u64)p << 32));
 }
 
 // ---- chains: segmented min-scans over the slots ---------------------------------------------------
@@ -134,18 +138,18 @@ __global__ void __launch_bounds__(CH_NT) k_chain(DedupArgs a, u64* status, u32* 
     if (!REV) {
         // link of slot s: same group as slot s-1 and exactly one base further
         const u32 s0 = sbase;
-        hs[0] = (s0 > 0 && s0 - 1 < n) ? a.slot_rec[s0 - 1].x : 0;
+        hs[0] = (s0 > 0 && s0 - 1 < n) ? a.slot_rec[2 * (size_t)(s0 - 1)].x : 0;
         u32 linkbits = 0;
 #pragma unroll
         for (int k = 0; k < CH_IPT; ++k) {
             u32 s = s0 + k;
             bool valid = s < n;
-            ulonglong2 r = valid ? a.slot_rec[s] : make_ulonglong2(0, INF32);
+            ulonglong2 r = valid ? a.slot_rec[2 * (size_t)s] : make_ulonglong2(0, INF32);
             hs[k + 1] = r.x;
             v[k] = (u32)r.y;
             bool link = valid && s > 0 && (r.x & 1) && (hs[k] & HASH_MASK) == (r.x & HASH_MASK);
 #ifdef MB_VERIFY_LINKS
-            if (link) link = same_group(a, (u32)a.slot_rec[s - 1].y, v[k]);
+            if (link) link = same_group(a, (u32)a.slot_rec[2 * (size_t)(s - 1)].y, v[k]);
 #endif
             f[k] = !link;
             linkbits |= (link ? 1u : 0u) << k;
@@ -160,7 +164,7 @@ __global__ void __launch_bounds__(CH_NT) k_chain(DedupArgs a, u64* status, u32* 
         for (int k = 0; k < CH_IPT; ++k) {
             u32 s = sbase + (CH_IPT - 1 - k);
             bool valid = s < n;
-            v[k] = valid ? (u32)a.slot_rec[s].y : INF32;
+            v[k] = valid ? (u32)a.slot_rec[2 * (size_t)s].y : INF32;
             bool link_next = valid && s + 1 < n && ((lb >> (CH_IPT - k)) & 1u); // slot s+1 continues s
             f[k] = !link_next;
         }
@@ -221,7 +225,7 @@ __global__ void __launch_bounds__(256) k_rep_keys(DedupArgs a, u64* __restrict__
     u64 w = a.rep_bits[s >> 6];
     if (!((w >> (s & 63)) & 1)) return;
     u32 idx = a.rep_rank[s >> 6] + (u32)__popcll(w & ((1ull << (s & 63)) - 1));
-    skey[idx] = ((a.slot_rec[s].x >> 48) << 32) | s;
+    skey[idx] = ((a.slot_rec[2 * (size_t)s].x >> 48) << 32) | s;
 }
 
 // ---- extension -----------------------------------------------------------------------------------
@@ -346,11 +350,10 @@ __device__ __forceinline__ i64 chunk_lo(int dir, u32 b, u32 L) { return dir > 0 
 // use windows that fit.  The loop is uniform (the pattern is a launch constant).
 __device__ __forceinline__ void window_map(u64 xa, u64 xb, const SeedDev& sd, u64& bhi, u64& blo) {
     bhi = 0; blo = 0;
-    const u64 care = sd.mask_hi;
-    for (int o = 0; o < sd.L; ++o) {
-        if (!((care >> (62 - 2 * o)) & 1)) continue;
-        bhi |= shl128_hi(xa, xb, 2 * o);
-        blo |= xb << (2 * o);
+    for (int t = 0; t < sd.w; ++t) {
+        const int s = 2 * (int)sd.care_off[t];
+        bhi |= shl128_hi(xa, xb, s);
+        blo |= xb << s;
     }
 }
 __device__ __forceinline__ bool win_bad(u64 bhi, u64 blo, u32 q) { return ((q < 32 ? bhi >> (62 - 2 * q) : blo >> (62 - 2 * (q - 32))) & 1) != 0; }
@@ -375,9 +378,7 @@ __device__ __forceinline__ u32 good_down(u64 bhi, u64 blo, u32 q) {
 
 // evaluate one chunk that starts after b0 successful jumps: advances b over the jumps it holds; returns
 // true when the walk ends inside this chunk (growth in `out`)
-__device__ __forceinline__ bool walk_chunk(u64 xa, u64 xb, const SeedDev& sd, int dir, u32 L, u32 room, u32 maxjumps, u32 per_chunk, u32& b, u32& out) {
-    u64 bhi, blo;
-    window_map(xa, xb, sd, bhi, blo);
+__device__ __forceinline__ bool walk_chunk(u64 bhi, u64 blo, int dir, u32 L, u32 room, u32 maxjumps, u32 per_chunk, u32& b, u32& out) {
     const u32 b0 = b;
     bool failed = false;
     for (u32 w = 0; w < per_chunk && b < maxjumps; ++w) {
@@ -410,7 +411,9 @@ __device__ __forceinline__ u32 grow_thread(const u64* __restrict__ packed, const
     for (int chunk = 0; chunk < DD_THREAD_CHUNKS; ++chunk) {
         u64 xa, xb;
         mismatch64(packed, gt, L, cpos, cgs, m, chunk_lo(dir, b, L), xa, xb);
-        if (walk_chunk(xa, xb, sd, dir, L, room, maxjumps, per_chunk, b, out)) return out;
+        u64 bhi, blo;
+        window_map(xa, xb, sd, bhi, blo);
+        if (walk_chunk(bhi, blo, dir, L, room, maxjumps, per_chunk, b, out)) return out;
     }
     return INF32;
 }
@@ -432,7 +435,9 @@ __device__ u32 grow_warp(const u64* __restrict__ packed, const GenomeTable& gt, 
         if (active) {
             u64 xa, xb;
             mismatch64(packed, gt, L, cpos, cgs, m, chunk_lo(dir, b, L), xa, xb);
-            ends = walk_chunk(xa, xb, sd, dir, L, room, maxjumps, per_chunk, b, out);
+            u64 bhi, blo;
+            window_map(xa, xb, sd, bhi, blo);
+            ends = walk_chunk(bhi, blo, dir, L, room, maxjumps, per_chunk, b, out);
         }
         u32 em = __ballot_sync(0xFFFFFFFFu, ends);
         if (em) return __shfl_sync(0xFFFFFFFFu, out, __ffs(em) - 1);
@@ -518,17 +523,16 @@ __global__ void __launch_bounds__(256) k_rep_setup(DedupArgs a) {
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n_rep) return;
     const u32 slot = (u32)a.s_key[i];
-    ulonglong2 r = a.slot_rec[slot];
-    const u32 c = (u32)r.y;
+    const ulonglong2 r = a.slot_rec[2 * (size_t)slot], q = a.slot_rec[2 * (size_t)slot + 1];
+    const u32 c = (u32)r.y, m = (u32)(r.y >> 32) & 0xFFu, g0 = (u32)(r.y >> 40) & 0xFFu;
     const u64 h = r.x & HASH_MASK;
     a.s_rec[i] = make_ulonglong2((h & 0xFFFF000000000000ull) | ((u64)slot << 16) | (h & 0xFFFFull), (((h >> 16) & 0xFFFFFFFFull) << 32) | c);
     a.s_cand[i] = c;
-    a.s_h2[i] = a.ghash2[c];
+    a.s_h2[i] = q.x;
     a.minrank[i] = INF64; a.minrank[(size_t)a.n_rep + i] = INF64;
     a.reach[i] = 0;
     a.rstate[i] = 0;
-    const u32 off = a.cand_off[c], m = a.cand_off[c + 1] - off;
-    a.xrec[i] = make_uint4(c, off, m | ((u32)(a.comp_gs[off] & 0x7F) << 8), a.comp_pos[off]);
+    a.xrec[i] = make_uint4(c, (u32)q.y, m | (g0 << 8), (u32)(q.y >> 32));
 }
 
 // ---- extend: a warp takes 32 reps.  Lane j owns rep j's state; the (rep, component) pairs of the warp
@@ -607,27 +611,25 @@ __device__ __forceinline__ void extend_rounds(const DedupArgs& a, const GenomeTa
         if (FIRST && round == 0) { x.room_l = sRoom[lane][0]; x.room_r = sRoom[lane][1]; }
         if (want) {
             const u64 xa = ((u64)sMap[lane][0] << 32) | sMap[lane][1], xb = ((u64)sMap[lane][2] << 32) | sMap[lane][3];
+            u64 bhi, blo;
+            window_map(xa, xb, sd, bhi, blo); // one call site for the three states: the lanes of a warp differ in state
             if (x.st == ST_CENTER) {
                 // chunk index i <-> match offset i - L: first jump windows at 0 (left) and 2L (right), single-step
                 // windows s at L - s (left, descending from L - 1) and L + s (right, ascending from L + 1)
-                u64 bhi, blo;
-                window_map(xa, xb, sd, bhi, blo);
                 const bool lj = x.room_l >= L && !win_bad(bhi, blo, 0);
                 x.rj = x.room_r >= L && !win_bad(bhi, blo, 2 * L);
                 if (!lj) x.el = min(good_down(bhi, blo, L - 1), min(L, x.room_l));
                 if (!x.rj) x.er = min(good_up(bhi, blo, L + 1), min(L, x.room_r));
                 x.b = 1; // the first jump of the side walked next is known to succeed
                 x.st = lj ? ST_LEFT : (x.rj ? ST_RIGHT : ST_DONE);
-            } else if (x.st == ST_LEFT) {
-                u32 out = 0;
-                if (walk_chunk(xa, xb, sd, -1, L, x.room_l, x.room_l / L, per_chunk, x.b, out)) {
-                    x.el = out;
-                    x.b = (3 * L <= 64) ? 1 : 0;
-                    x.st = x.rj ? ST_RIGHT : ST_DONE;
-                }
             } else {
+                const bool left = x.st == ST_LEFT;
+                const u32 room = left ? x.room_l : x.room_r;
                 u32 out = 0;
-                if (walk_chunk(xa, xb, sd, +1, L, x.room_r, x.room_r / L, per_chunk, x.b, out)) { x.er = out; x.st = ST_DONE; }
+                if (walk_chunk(bhi, blo, left ? -1 : +1, L, room, room / L, per_chunk, x.b, out)) {
+                    if (left) { x.el = out; x.b = (3 * L <= 64) ? 1 : 0; x.st = x.rj ? ST_RIGHT : ST_DONE; }
+                    else { x.er = out; x.st = ST_DONE; }
+                }
             }
         }
         __syncwarp();
