@@ -128,14 +128,19 @@ int mb_fetch_result(mb_ctx* ctx, const mb_result** out);
  *     mb_dist_local        -> candidate rows grouped by owner rank: headers (2 words each) at
  *                             *d_hdr, component words at *d_comps, counts per owner (exchange 2)
  *   3 mb_dist_recv_buffer(1 / 2, n) receive the headers / components;
- *     mb_dist_dedup        -> accepted matches as rows (*d_hdr, *d_comps)       (gather to rank 0)
- *   4 mb_dist_recv_buffer(3 / 4, n) on rank 0; mb_dist_output builds the canonical CSR there, after
- *     which mb_fetch_result works as for mb_find_device. */
+ *     mb_dist_dedup        -> de-dup of the owned groups; *d_hist = 4096 uint64 counts (device) of the
+ *                             accepted matches' canonical keys: sum it over all ranks IN PLACE (all-reduce)
+ *     mb_dist_match_partition -> match rows grouped by destination = range of the canonical order
+ *                             (*d_hdr 2 words per row, *d_comps), counts per destination     (exchange 3)
+ *   4 mb_dist_recv_buffer(3 / 4, n) receive them; mb_dist_output builds the canonical CSR of this rank's
+ *     range, after which mb_fetch_result works as for mb_find_device.  The ranks' pieces, concatenated in
+ *     rank order, are the result. */
 int mb_dist_extract(mb_ctx* ctx, int rank, int world, void** d_send, uint64_t* h_counts);
 int mb_dist_recv_buffer(mb_ctx* ctx, int which, uint64_t n_words, void** d_ptr);
 int mb_dist_local(mb_ctx* ctx, const mb_params* params, uint64_t n_recv, uint64_t* h_cand_counts, uint64_t* h_comp_counts,
                   void** d_hdr, void** d_comps);
-int mb_dist_dedup(mb_ctx* ctx, uint64_t n_cand, uint64_t n_comp, uint64_t* h_n_match, uint64_t* h_n_mcomp, void** d_hdr, void** d_comps);
+int mb_dist_dedup(mb_ctx* ctx, uint64_t n_cand, uint64_t n_comp, void** d_hist);
+int mb_dist_match_partition(mb_ctx* ctx, uint64_t* h_match_counts, uint64_t* h_comp_counts, void** d_hdr, void** d_comps);
 int mb_dist_output(mb_ctx* ctx, uint64_t n_match, uint64_t n_comp);
 int mb_dist_stage_ms(mb_ctx* ctx, float* out4);
 

@@ -39,7 +39,7 @@ class MbStats(C.Structure):
 EXPORTS = ["mb_ctx_create", "mb_ctx_destroy", "mb_set_stream", "mb_add_sequence", "mb_add_sequence_device", "mb_clear_sequences",
            "mb_set_seed", "mb_find", "mb_find_device", "mb_fetch_result", "mb_get_sml", "mb_get_mers", "mb_get_stats", "mb_strerror",
            "mb_last_cuda_error", "mb_device_count", "mb_version", "mb_synth_create", "mb_synth_nseq", "mb_synth_len", "mb_synth_seq",
-           "mb_synth_free", "mb_dist_extract", "mb_dist_recv_buffer", "mb_dist_local", "mb_dist_dedup", "mb_dist_output", "mb_dist_stage_ms", "mb_debug_radix"]
+           "mb_synth_free", "mb_dist_extract", "mb_dist_recv_buffer", "mb_dist_local", "mb_dist_dedup", "mb_dist_match_partition", "mb_dist_output", "mb_dist_stage_ms", "mb_debug_radix"]
 
 _lib = None
 
@@ -83,7 +83,8 @@ def lib():
     L.mb_dist_extract.argtypes = [vp, i32, i32, C.POINTER(vp), pu64]
     L.mb_dist_recv_buffer.argtypes = [vp, i32, u64, C.POINTER(vp)]
     L.mb_dist_local.argtypes = [vp, C.POINTER(MbParams), u64, pu64, pu64, C.POINTER(vp), C.POINTER(vp)]
-    L.mb_dist_dedup.argtypes = [vp, u64, u64, pu64, pu64, C.POINTER(vp), C.POINTER(vp)]
+    L.mb_dist_dedup.argtypes = [vp, u64, u64, C.POINTER(vp)]
+    L.mb_dist_match_partition.argtypes = [vp, pu64, pu64, C.POINTER(vp), C.POINTER(vp)]
     L.mb_dist_output.argtypes = [vp, u64, u64]
     L.mb_dist_stage_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.mb_debug_radix.argtypes = [vp, u64, i32, i32, i32, C.POINTER(C.c_float)]

@@ -12,8 +12,10 @@
 //                                                                                 --> exchange 2
 //   stage 3  mb_dist_dedup     chains / extension / resolve over the owned groups (ranks keep the
 //                              global seed order: rows arrive in source-rank order) -> accepted
-//                              matches                                            --> gather to rank 0
-//   stage 4  mb_dist_output    rank 0: canonical order (D18) + CSR; then mb_fetch_result as usual
+//                              matches + histogram of their canonical keys        --> all-reduce (sum)
+//            mb_dist_match_partition  match rows by destination = key range       --> exchange 3
+//   stage 4  mb_dist_output    every rank: canonical order (D18) + CSR of its key range; the pieces in
+//                              rank order are the result (mb_fetch_result per rank)
 // MODE_UNIQUE with 8-byte records only (every BASELINE config that names several GPUs).
 #include "ctx.h"
 
@@ -182,18 +184,22 @@ int mb_dist_local(mb_ctx* c, const mb_params* prm, uint64_t n_recv, uint64_t* h_
     return MB_OK;
 }
 
-// stage 3: n_cand rows (headers in receive buffer 1, n_comp component words in buffer 2), source-rank order
-int mb_dist_dedup(mb_ctx* c, uint64_t n_cand64, uint64_t n_comp64, uint64_t* h_n_match, uint64_t* h_n_mcomp, void** d_hdr, void** d_comps) {
-    if (!c || !h_n_match || !h_n_mcomp || !d_hdr || !d_comps) return MB_E_ARG;
+// stage 3a: n_cand rows (headers in receive buffer 1, n_comp component words in buffer 2), source-rank order.
+// De-dup of the owned groups; leaves a 4096-bin histogram of the accepted matches' canonical sort keys at
+// *d_hist (uint64 counts, library-owned) for the caller to sum over all ranks IN PLACE before stage 3b.
+int mb_dist_dedup(mb_ctx* c, uint64_t n_cand64, uint64_t n_comp64, void** d_hist) {
+    if (!c || !d_hist) return MB_E_ARG;
     if (n_cand64 >= (1ull << 31) || n_comp64 >= (1ull << 32)) return MB_E_TOOLONG;
     CUDA_TRY(c, cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
     u64* scal = c->scalars.as<u64>();
     const u32 n_cand = (u32)n_cand64, n_ccomp = (u32)n_comp64;
-    *h_n_match = 0; *h_n_mcomp = 0; *d_hdr = nullptr; *d_comps = nullptr;
-    c->d_nmatch = 0; c->d_nmcomp = 0;
+    c->d_nmatch = 0; c->d_nmcomp = 0; c->n_rep = 0;
+    TRY(c->reserve(c->x_counts, 4096 * 8));
+    CUDA_TRY(c, cudaMemsetAsync(c->x_counts.p, 0, 4096 * 8, st));
+    *d_hist = c->x_counts.p;
     cudaEventRecord(c->ev_d[5], st);
-    if (n_cand == 0) { cudaEventRecord(c->ev_d[6], st); return MB_OK; }
+    if (n_cand == 0) { cudaEventRecord(c->ev_d[6], st); CUDA_TRY(c, cudaStreamSynchronize(st)); return MB_OK; }
     TRY(mbi_reserve_candidates(c, n_cand, n_ccomp, c->d_bases));
     TRY(c->reserve(c->x_m, ((size_t)n_cand + 8) * 4));
     const u64 bm_words = c->d_bases / 64 + 2;
@@ -207,41 +213,99 @@ int mb_dist_dedup(mb_ctx* c, uint64_t n_cand64, uint64_t n_comp64, uint64_t* h_n
                        c->ghash2.as<u64>(), c->bitmap.as<u64>(), st);
     LAUNCHED(c); CHECK_LAUNCH(c);
     TRY(mbi_dedup(c, n_cand, c->d_bases));
-    // accepted matches (among the reps) -> rows for the gather
+    // accepted matches (among the reps): index, canonical key, key histogram
     const u32 n_rep = c->n_rep;
     TRY(c->reserve(c->flags, ((size_t)n_rep + 8) * 4));
     TRY(c->reserve(c->match_idx, ((size_t)n_rep + 8) * 4));
-    TRY(c->reserve(c->ncomp, ((size_t)n_rep + 8) * 4));
     OutputArgs oa{};
     oa.n_items = n_rep; oa.state = c->s_cand.as<u8>(); oa.item_cand = c->rep_cand.as<u32>(); oa.flags = c->flags.as<u32>();
     launch_uniq_flags(oa, st); LAUNCHED(c);
     launch_scan_u32(c->flags.as<u32>(), n_rep, c->match_idx.as<u32>(), nullptr, c->status_slice(div_up(n_rep, scan_tile())), c->ticket(),
                     scal + SC_NMATCH, st);
-    LAUNCHED(c);
-    launch_acc_m(c->s_cand.as<u8>(), c->rep_cand.as<u32>(), c->cand_off.as<u32>(), n_rep, c->x_m.as<u32>(), st); LAUNCHED(c);
-    launch_scan_u32(c->x_m.as<u32>(), n_rep, c->ncomp.as<u32>(), nullptr, c->status_slice(div_up(n_rep, scan_tile())), c->ticket(),
-                    scal + SC_NCOMP, st);
     LAUNCHED(c); CHECK_LAUNCH(c);
     TRY(mbi_read_scalars(c));
     const u64* hs64 = reinterpret_cast<const u64*>(c->h_scal);
     const u32* hs32 = reinterpret_cast<const u32*>(c->h_scal);
-    const u32 n_match = (u32)hs64[SC_NMATCH], n_mcomp = (u32)hs64[SC_NCOMP];
+    const u32 n_match = (u32)hs64[SC_NMATCH];
     c->stats.dedup_iters = hs32[2 * SC_DDCTR + 9];
-    TRY(c->reserve(c->x_hdr_s, ((size_t)n_match + 8) * 16));
-    TRY(c->reserve(c->x_comp_s, ((size_t)n_mcomp + 8) * 8));
-    launch_pack_match(c->s_cand.as<u8>(), c->rep_cand.as<u32>(), c->match_idx.as<u32>(), c->ncomp.as<u32>(), c->cand_off.as<u32>(),
-                      c->comp_pos.as<u32>(), c->comp_gs.as<u8>(), c->ext_l.as<u32>(), c->ext_r.as<u32>(), n_rep, c->x_hdr_s.as<u64>(),
-                      c->x_comp_s.as<u64>(), st);
+    c->d_nmatch = n_match;
+    const size_t nm = (size_t)n_match + 8;
+    TRY(c->reserve(c->sort_kA, nm * 8)); TRY(c->reserve(c->sort_kB, nm * 8));
+    TRY(c->reserve(c->sort_vA, nm * 8)); TRY(c->reserve(c->sort_vB, nm * 8));
+    TRY(c->reserve(c->x_key, nm * 8));
+    TRY(c->reserve(c->x_item, nm * 4));
+    const int sbits = mbi_bits_for(c->d_maxlen);
+    launch_match_keys(c->s_cand.as<u8>(), c->rep_cand.as<u32>(), c->match_idx.as<u32>(), c->cand_off.as<u32>(), c->comp_gs.as<u8>(),
+                      c->comp_pos.as<u32>(), c->ext_l.as<u32>(), n_rep, sbits, std::max(0, sbits + 6 - 12), c->x_key.as<u64>(), c->x_item.as<u32>(),
+                      c->x_counts.as<u64>(), st);
     LAUNCHED(c); CHECK_LAUNCH(c);
     cudaEventRecord(c->ev_d[6], st);
     CUDA_TRY(c, cudaStreamSynchronize(st));
-    c->d_nmatch = n_match; c->d_nmcomp = n_mcomp;
-    *h_n_match = n_match; *h_n_mcomp = n_mcomp;
+    return MB_OK;
+}
+
+// stage 3b: *d_hist now holds the histogram summed over all ranks.  Partition the accepted matches by
+// destination = range of the canonical sort key (ranks hold ascending ranges of the final order) and pack
+// their rows; per-destination row / component-word counts go to the host arrays.
+int mb_dist_match_partition(mb_ctx* c, uint64_t* h_match_counts, uint64_t* h_comp_counts, void** d_hdr, void** d_comps) {
+    if (!c || !h_match_counts || !h_comp_counts || !d_hdr || !d_comps) return MB_E_ARG;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const int world = c->d_world;
+    const u32 n_match = c->d_nmatch;
+    for (int r = 0; r < world; ++r) { h_match_counts[r] = 0; h_comp_counts[r] = 0; }
+    *d_hdr = nullptr; *d_comps = nullptr;
+    // destination of every key bin: equal shares of the global match count, whole bins
+    std::vector<u64> gh(4096);
+    CUDA_TRY(c, cudaMemcpyAsync(gh.data(), c->x_counts.p, 4096 * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaStreamSynchronize(st));
+    u64 total = 0;
+    for (u64 v : gh) total += v;
+    std::vector<uint8_t> lut(4096, 0);
+    u64 before = 0;
+    for (int b = 0; b < 4096; ++b) {
+        u64 d = total ? (before * (u64)world) / total : 0;
+        lut[b] = (uint8_t)std::min<u64>(d, (u64)world - 1);
+        before += gh[b];
+    }
+    if (n_match == 0) return MB_OK;
+    TRY(c->reserve(c->x_lut, 4096));
+    CUDA_TRY(c, cudaMemcpyAsync(c->x_lut.p, lut.data(), 4096, cudaMemcpyHostToDevice, st));
+    const int sbits = mbi_bits_for(c->d_maxlen);
+    u64 *skA = c->sort_kA.as<u64>(), *skB = c->sort_kB.as<u64>(), *svA = c->sort_vA.as<u64>(), *svB = c->sort_vB.as<u64>();
+    launch_dest_keys(c->x_key.as<u64>(), n_match, std::max(0, sbits + 6 - 12), c->x_lut.as<u8>(), skA, svA, st); LAUNCHED(c);
+    const int obits = std::max(1, mbi_bits_for((u64)world - 1));
+    TRY(mbi_sort_records(c, &skA, &skB, &svA, &svB, n_match, 0, obits, false)); // leaves the destination histogram in c->hist
+    TRY(c->reserve(c->x_m, ((size_t)n_match + 8) * 4));
+    TRY(c->reserve(c->out_off, ((size_t)n_match + 8) * 8));
+    launch_match_perm_m(svA, c->x_item.as<u32>(), c->rep_cand.as<u32>(), c->cand_off.as<u32>(), n_match, c->x_m.as<u32>(), st); LAUNCHED(c);
+    launch_scan_u32(c->x_m.as<u32>(), n_match, nullptr, c->out_off.as<u64>(), c->status_slice(div_up(n_match, scan_tile())), c->ticket(), nullptr, st);
+    LAUNCHED(c);
+    std::vector<u32> oh(256);
+    CUDA_TRY(c, cudaMemcpyAsync(oh.data(), c->hist.p, 256 * 4, cudaMemcpyDeviceToHost, st));
+    u64 n_mcomp = 0;
+    CUDA_TRY(c, cudaMemcpyAsync(&n_mcomp, c->out_off.as<u64>() + n_match, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaStreamSynchronize(st));
+    std::vector<u64> bound(world + 1, 0);
+    u64 acc = 0;
+    for (int r = 0; r < world; ++r) { h_match_counts[r] = oh[r]; acc += oh[r]; bound[r + 1] = acc; }
+    if (acc != n_match) return MB_E_STATE;
+    std::vector<u64> cb(world + 1, 0);
+    for (int r = 1; r <= world; ++r) CUDA_TRY(c, cudaMemcpyAsync(&cb[r], c->out_off.as<u64>() + bound[r], 8, cudaMemcpyDeviceToHost, st));
+    TRY(c->reserve(c->x_hdr_s, ((size_t)n_match + 8) * 16));
+    TRY(c->reserve(c->x_comp_s, ((size_t)n_mcomp + 8) * 8));
+    launch_pack_match_perm(svA, c->x_item.as<u32>(), c->rep_cand.as<u32>(), c->out_off.as<u64>(), c->cand_off.as<u32>(), c->comp_pos.as<u32>(),
+                           c->comp_gs.as<u8>(), c->ext_l.as<u32>(), c->ext_r.as<u32>(), n_match, c->x_hdr_s.as<u64>(), c->x_comp_s.as<u64>(), st);
+    LAUNCHED(c); CHECK_LAUNCH(c);
+    CUDA_TRY(c, cudaStreamSynchronize(st));
+    for (int r = 0; r < world; ++r) h_comp_counts[r] = cb[r + 1] - cb[r];
+    c->d_nmcomp = (u32)n_mcomp;
     *d_hdr = c->x_hdr_s.p; *d_comps = c->x_comp_s.p;
     return MB_OK;
 }
 
-// stage 4 (rank 0): n_match rows in receive buffers 3 / 4 -> canonical match CSR on the device
+// stage 4 (every rank): the n_match rows of this rank's key range (receive buffers 3 / 4) -> canonical match CSR
+// on the device; the ranks' pieces, in rank order, are the whole result
 int mb_dist_output(mb_ctx* c, uint64_t n_match64, uint64_t n_comp64) {
     if (!c) return MB_E_ARG;
     if (n_match64 >= (1ull << 31) || n_comp64 >= (1ull << 32)) return MB_E_TOOLONG;

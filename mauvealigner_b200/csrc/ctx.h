@@ -41,7 +41,7 @@ struct mb_ctx {
     DBuf cand_run, cand_off, cand_aux, comp_pos, comp_gs, bitmap, bmrank, cand_at, cstate, covered, minrank, ext_l, ext_r;
     DBuf trace, ghash2, rep_cand, s_h2, reach, xstate, xrec;
     u32 n_rep = 0;
-    DBuf x_lut, x_counts, x_hdr_s, x_comp_s, x_hdr_r, x_comp_r, x_m; // multi-GPU exchange buffers (api_dist.cu)
+    DBuf x_lut, x_counts, x_hdr_s, x_comp_s, x_hdr_r, x_comp_r, x_m, x_key, x_item; // multi-GPU exchange buffers (api_dist.cu)
     int d_rank = 0, d_world = 1;
     u32 d_ncand = 0, d_nccomp = 0, d_nmatch = 0, d_nmcomp = 0;
     u64 d_bases = 0, d_maxlen = 0;

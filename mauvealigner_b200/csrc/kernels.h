@@ -143,3 +143,9 @@ void launch_pack_match(const u8* state, const u32* item_cand, const u32* match_i
                        const u32* ext_l, const u32* ext_r, u32 n, u64* hdr, u64* comps, cudaStream_t st);
 void launch_unpack_match(const u64* hdr, const u64* comps, const u32* cand_off, u32 n, u32* comp_pos, u8* comp_gs, u32* ext_l, u32* ext_r,
                          u8* state, u32* item_cand, cudaStream_t st);
+void launch_match_keys(const u8* state, const u32* item_cand, const u32* match_idx, const u32* cand_off, const u8* comp_gs, const u32* comp_pos,
+                       const u32* ext_l, u32 n_items, int sbits, int binshift, u64* key, u32* item_of, u64* hist, cudaStream_t st);
+void launch_dest_keys(const u64* key, u32 n, int binshift, const u8* lut, u64* skey, u64* sval, cudaStream_t st);
+void launch_match_perm_m(const u64* perm, const u32* item_of, const u32* item_cand, const u32* cand_off, u32 n, u32* m_out, cudaStream_t st);
+void launch_pack_match_perm(const u64* perm, const u32* item_of, const u32* item_cand, const u64* poff, const u32* cand_off, const u32* comp_pos,
+                            const u8* comp_gs, const u32* ext_l, const u32* ext_r, u32 n, u64* hdr, u64* comps, cudaStream_t st);

@@ -159,3 +159,64 @@ void launch_unpack_match(const u64* hdr, const u64* comps, const u32* cand_off, 
                          u8* state, u32* item_cand, cudaStream_t st) {
     if (n) k_unpack_match<<<div_up(n, 256), 256, 0, st>>>(hdr, comps, cand_off, n, comp_pos, comp_gs, ext_l, ext_r, state, item_cand);
 }
+
+// ---- distributed output: canonical key of every accepted match, and its key histogram (top 12 key bits)
+__global__ void __launch_bounds__(256) k_match_keys(const u8* __restrict__ state, const u32* __restrict__ item_cand, const u32* __restrict__ match_idx,
+                                                    const u32* __restrict__ cand_off, const u8* __restrict__ comp_gs, const u32* __restrict__ comp_pos,
+                                                    const u32* __restrict__ ext_l, u32 n_items, int sbits, int binshift, u64* __restrict__ key,
+                                                    u32* __restrict__ item_of, u64* __restrict__ hist) {
+    u32 it = blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= n_items || (state[it] & 15u) != 1u) return;
+    u32 c = item_cand[it], j = match_idx[it];
+    u32 off = cand_off[c];
+    u32 f = comp_gs[off] & 0x7F;
+    u64 st = (u64)comp_pos[off] - ext_l[c] + 1;
+    u64 k = ((u64)(MB_MAX_SEQ - 1 - f) << sbits) | st; // same key as k_uniq_keys: the ranks' ranges concatenate to D18
+    key[j] = k;
+    item_of[j] = it;
+    atomicAdd((unsigned long long*)&hist[(k >> binshift) & 4095u], 1ull);
+}
+void launch_match_keys(const u8* state, const u32* item_cand, const u32* match_idx, const u32* cand_off, const u8* comp_gs, const u32* comp_pos,
+                       const u32* ext_l, u32 n_items, int sbits, int binshift, u64* key, u32* item_of, u64* hist, cudaStream_t st) {
+    if (n_items) k_match_keys<<<div_up(n_items, 256), 256, 0, st>>>(state, item_cand, match_idx, cand_off, comp_gs, comp_pos, ext_l, n_items, sbits, binshift, key, item_of, hist);
+}
+
+__global__ void __launch_bounds__(256) k_dest_keys(const u64* __restrict__ key, u32 n, int binshift, const u8* __restrict__ lut, u64* __restrict__ skey,
+                                                   u64* __restrict__ sval) {
+    u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    skey[j] = lut[(key[j] >> binshift) & 4095u];
+    sval[j] = j;
+}
+void launch_dest_keys(const u64* key, u32 n, int binshift, const u8* lut, u64* skey, u64* sval, cudaStream_t st) {
+    if (n) k_dest_keys<<<div_up(n, 256), 256, 0, st>>>(key, n, binshift, lut, skey, sval);
+}
+
+__global__ void __launch_bounds__(256) k_match_perm_m(const u64* __restrict__ perm, const u32* __restrict__ item_of, const u32* __restrict__ item_cand,
+                                                      const u32* __restrict__ cand_off, u32 n, u32* __restrict__ m_out) {
+    u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    u32 c = item_cand[item_of[(u32)perm[t]]];
+    m_out[t] = cand_off[c + 1] - cand_off[c];
+}
+void launch_match_perm_m(const u64* perm, const u32* item_of, const u32* item_cand, const u32* cand_off, u32 n, u32* m_out, cudaStream_t st) {
+    if (n) k_match_perm_m<<<div_up(n, 256), 256, 0, st>>>(perm, item_of, item_cand, cand_off, n, m_out);
+}
+
+__global__ void __launch_bounds__(256) k_pack_match_perm(const u64* __restrict__ perm, const u32* __restrict__ item_of, const u32* __restrict__ item_cand,
+                                                         const u64* __restrict__ poff, const u32* __restrict__ cand_off, const u32* __restrict__ comp_pos,
+                                                         const u8* __restrict__ comp_gs, const u32* __restrict__ ext_l, const u32* __restrict__ ext_r, u32 n,
+                                                         u64* __restrict__ hdr, u64* __restrict__ comps) {
+    u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    u32 c = item_cand[item_of[(u32)perm[t]]];
+    u32 off = cand_off[c], m = cand_off[c + 1] - off;
+    hdr[2 * (u64)t] = (u64)ext_l[c] | ((u64)ext_r[c] << 32);
+    hdr[2 * (u64)t + 1] = m;
+    u64 o = poff[t];
+    for (u32 k = 0; k < m; ++k) comps[o + k] = (u64)comp_pos[off + k] | ((u64)comp_gs[off + k] << 32);
+}
+void launch_pack_match_perm(const u64* perm, const u32* item_of, const u32* item_cand, const u64* poff, const u32* cand_off, const u32* comp_pos,
+                            const u8* comp_gs, const u32* ext_l, const u32* ext_r, u32 n, u64* hdr, u64* comps, cudaStream_t st) {
+    if (n) k_pack_match_perm<<<div_up(n, 256), 256, 0, st>>>(perm, item_of, item_cand, poff, cand_off, comp_pos, comp_gs, ext_l, ext_r, n, hdr, comps);
+}

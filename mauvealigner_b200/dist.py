@@ -4,8 +4,9 @@ NVLink) for the three exchanges, the library (libmauve_b200.so, mb_dist_*) for e
     stage 1  extract this rank's slice of seeds, partition by seed-key range      -> all-to-all of seed records
     stage 2  sort / runs / policy over the received key range -> candidate rows,
              partitioned by owner of their de-dup group                            -> all-to-all of rows
-    stage 3  chains / extension / resolve over the owned groups                   -> gather of match rows on rank 0
-    stage 4  rank 0: canonical order + CSR
+    stage 3  chains / extension / resolve over the owned groups; histogram of the accepted matches' canonical
+             keys (all-reduce) -> match rows by range of the canonical order       -> all-to-all of rows
+    stage 4  every rank: canonical order + CSR of its range (the pieces in rank order are the result)
 
 The orchestration is written over a small "fabric" interface so the same code runs (a) one rank per process over
 torch.distributed (TorchFabric) and (b) all ranks of a world inside ONE process on one GPU (LocalFabric: the
@@ -48,6 +49,13 @@ class LocalFabric:
         k = len(send_counts[0]) // self.world
         return [[x for s in range(self.world) for x in send_counts[s][d * k:(d + 1) * k]] for d in range(self.world)]
 
+    def allreduce_sum(self, tensors):
+        total = tensors[0].clone()
+        for t in tensors[1:]:
+            total += t
+        for t in tensors:
+            t.copy_(total)
+
     def words(self, sends, send_counts, recvs, recv_counts, width=1):
         for d in range(self.world):
             o = 0
@@ -77,6 +85,9 @@ class TorchFabric:
         out = torch.empty_like(t)
         self.dist.all_to_all_single(out, t, [k] * self.world, [k] * self.world, group=self.group)
         return [out.tolist()]
+
+    def allreduce_sum(self, tensors):
+        self.dist.all_reduce(tensors[0], group=self.group)
 
     def words(self, sends, send_counts, recvs, recv_counts, width=1):
         self.dist.all_to_all_single(recvs[0], sends[0], [c * width for c in recv_counts[0]], [c * width for c in send_counts[0]],
@@ -111,25 +122,40 @@ def find_unique(ctxs, fabric, device, nway_mask=0):
     fabric.words(ms, [mc for _, _, _, mc in s2], mr, rmc)
     for i in range(len(R)):
         info[i]["candidates_local"], info[i]["candidates_owned"] = sum(s2[i][2]), sum(rcc[i])
-    # ---- stage 3 + gather: accepted matches to rank 0
-    s3 = [c.dist_dedup(sum(k), sum(m)) for c, k, m in zip(ctxs, rcc, rmc)]
-    zeros = [0] * (W - 1)
-    both = fabric.counts([[x for pair in zip([nm] + zeros, [nc] + zeros) for x in pair] for _, _, nm, nc in s3])
+    # ---- stage 3: de-dup of the owned groups; accepted matches go to the rank that owns their range of the canonical order
+    hists = [c.dist_dedup(sum(k), sum(m)) for c, k, m in zip(ctxs, rcc, rmc)]
+    fabric.allreduce_sum([dev_words(p, 4096, device) for p in hists])
+    s3 = [c.dist_match_partition(W) for c in ctxs]
+    both = fabric.counts([[x for pair in zip(cc, mc) for x in pair] for _, _, cc, mc in s3])
     gcc = [b[0::2] for b in both]
     gmc = [b[1::2] for b in both]
-    hs = [dev_words(h, 2 * nm, device) for h, _, nm, _ in s3]
-    ms = [dev_words(m, nc, device) for _, m, _, nc in s3]
+    hs = [dev_words(h, 2 * sum(cc), device) for h, _, cc, _ in s3]
+    ms = [dev_words(m, sum(mc), device) for _, m, _, mc in s3]
     hr = [dev_words(c.dist_recv_buffer(3, 2 * sum(k)), 2 * sum(k), device) for c, k in zip(ctxs, gcc)]
     mr = [dev_words(c.dist_recv_buffer(4, sum(k)), sum(k), device) for c, k in zip(ctxs, gmc)]
-    fabric.words(hs, [[nm] + zeros for _, _, nm, _ in s3], hr, gcc, width=2)
-    fabric.words(ms, [[nc] + zeros for _, _, _, nc in s3], mr, gmc)
-    # ---- stage 4 on rank 0
-    for i, r in enumerate(R):
-        info[i]["matches_owned"] = s3[i][2]
-        if r == 0:
-            ctxs[i].dist_output(sum(gcc[i]), sum(gmc[i]))
-            info[i]["matches"] = sum(gcc[i])
+    fabric.words(hs, [cc for _, _, cc, _ in s3], hr, gcc, width=2)
+    fabric.words(ms, [mc for _, _, _, mc in s3], mr, gmc)
+    # ---- stage 4: every rank builds the canonical CSR of its range
+    for i in range(len(R)):
+        info[i]["matches_accepted"] = sum(s3[i][2])
+        ctxs[i].dist_output(sum(gcc[i]), sum(gmc[i]))
+        info[i]["matches"] = sum(gcc[i])
     return info
+
+
+def concat_results(pieces):
+    """The ranks' CSR pieces in rank order -> one result dict (numpy, host)."""
+    import numpy as np
+    out = dict(n_matches=sum(p["n_matches"] for p in pieces), n_comps=sum(p["n_comps"] for p in pieces))
+    out["length"] = np.concatenate([p["length"] for p in pieces])
+    out["comp_seq"] = np.concatenate([p["comp_seq"] for p in pieces])
+    out["comp_start"] = np.concatenate([p["comp_start"] for p in pieces])
+    offs, base = [], 0
+    for p in pieces:
+        offs.append(np.asarray(p["comp_off"][:-1], dtype=np.uint64) + np.uint64(base))
+        base += p["n_comps"]
+    out["comp_off"] = np.concatenate(offs + [np.array([base], dtype=np.uint64)])
+    return out
 
 
 def find_unique_emulated(seqs, pattern, world, device=0, nway_mask=0):
@@ -147,7 +173,7 @@ def find_unique_emulated(seqs, pattern, world, device=0, nway_mask=0):
                 c.set_seed(pattern)
             info = find_unique(ctxs, LocalFabric(world), dev, nway_mask=nway_mask)
             stream.synchronize()
-            res = ctxs[0].fetch()
+            res = concat_results([c.fetch() for c in ctxs])
         res["info"] = info
         return res
     finally:
@@ -218,8 +244,10 @@ def bench_main(args, CONFIG_NAMES, config_params, peaks, ClockSampler):
     stage = ctx.dist_stage_ms()
     launches = torch.tensor([float(st["kernel_launches"])], device=dev)
     dist.all_reduce(launches, op=dist.ReduceOp.SUM)
-    res = ctx.fetch(copy=False) if rank == 0 else None
-    n_matches = res["n_matches"] if res else 0
+    res = ctx.fetch(copy=False)
+    nm = torch.tensor([float(res["n_matches"])], device=dev)
+    dist.all_reduce(nm, op=dist.ReduceOp.SUM)
+    n_matches = int(nm.item())
 
     # ---- e2e: pinned host ASCII on every rank -> C ABI stages + exchanges -> host CSR on rank 0
     pinned = [torch.from_numpy(s).pin_memory() for s in seqs]
@@ -229,7 +257,7 @@ def bench_main(args, CONFIG_NAMES, config_params, peaks, ClockSampler):
         for t in pinned:
             ctx.add_sequence_ptr(t.data_ptr(), t.numel())
         find_unique([ctx], fabric, dev)
-        return ctx.fetch(copy=False) if rank == 0 else None
+        return ctx.fetch(copy=False)
 
     e2e_step()
     torch.cuda.synchronize()
@@ -243,6 +271,8 @@ def bench_main(args, CONFIG_NAMES, config_params, peaks, ClockSampler):
     dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_ms = float(e2e_ms.item())
     st2 = ctx.stats()
+    d2h = torch.tensor([float(st2["d2h_bytes"])], device=dev)
+    dist.all_reduce(d2h, op=dist.ReduceOp.SUM)
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
@@ -268,11 +298,11 @@ def bench_main(args, CONFIG_NAMES, config_params, peaks, ClockSampler):
             "steps": args.steps, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic",
             "config": {"workload": CONFIG_NAMES[config], "bp_per_step": bp, "n_genomes": len(seqs), "seed_pattern": mb.seeds.pattern_text(pattern),
-                       "scale": args.scale, "parallelism": f"key-range x{world} (seeds), group-hash x{world} (de-dup), rank-0 output",
+                       "scale": args.scale, "parallelism": f"key-range x{world} (seeds), group-hash x{world} (de-dup), canonical-range x{world} (output)",
                        "l2": "inputs larger than L2", "n_matches": n_matches},
             "roofline": roofline, "path_roofline": path, "cpu_baseline": None,
             "e2e": {"value": bp / (e2e_ms * 1e-3) / 1e9, "unit": "Gbp/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": st2["h2d_bytes"] * world,
-                    "d2h_bytes_per_step": st2["d2h_bytes"]},
+                    "d2h_bytes_per_step": int(d2h.item())},
             "gpu_launches": int(launches.item()) * args.steps, "stages_ms_rank0": {k: round(v, 4) for k, v in stage.items()},
             "rank0": {k: v for k, v in info[0].items()}, "wall_ms_per_step": wall_ms / args.steps, "clocks": sampler.summary(),
         }

@@ -141,11 +141,18 @@ class Context:
         return hdr.value or 0, comps.value or 0, [int(x) for x in cc], [int(x) for x in mc]
 
     def dist_dedup(self, n_cand, n_comp):
-        """-> (headers pointer, components pointer, accepted matches, their component words)"""
+        """-> device pointer of the 4096-bin histogram (uint64) of this rank's accepted matches' canonical keys"""
+        hist = C.c_void_p()
+        _check(self._h, L.lib().mb_dist_dedup(self._h, int(n_cand), int(n_comp), C.byref(hist)))
+        return hist.value or 0
+
+    def dist_match_partition(self, world):
+        """after the histogram has been summed over the ranks in place
+        -> (headers pointer, components pointer, rows per destination, component words per destination)"""
         hdr, comps = C.c_void_p(), C.c_void_p()
-        nm, nc = C.c_uint64(0), C.c_uint64(0)
-        _check(self._h, L.lib().mb_dist_dedup(self._h, int(n_cand), int(n_comp), C.byref(nm), C.byref(nc), C.byref(hdr), C.byref(comps)))
-        return hdr.value or 0, comps.value or 0, int(nm.value), int(nc.value)
+        cc, mc = (C.c_uint64 * world)(), (C.c_uint64 * world)()
+        _check(self._h, L.lib().mb_dist_match_partition(self._h, cc, mc, C.byref(hdr), C.byref(comps)))
+        return hdr.value or 0, comps.value or 0, [int(x) for x in cc], [int(x) for x in mc]
 
     def dist_output(self, n_match, n_comp):
         _check(self._h, L.lib().mb_dist_output(self._h, int(n_match), int(n_comp)))

@@ -39,6 +39,14 @@ def test_local_fabric_routes_by_destination():
         assert rc[d] == [counts[s][d] for s in range(3)]
 
 
+def test_local_fabric_allreduce():
+    fab = LocalFabric(3)
+    ts = [torch.arange(5, dtype=torch.int64) * (r + 1) for r in range(3)]
+    fab.allreduce_sum(ts)
+    for t in ts:
+        assert t.tolist() == [0, 6, 12, 18, 24]
+
+
 def _worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     import torch.distributed as dist
@@ -55,6 +63,9 @@ def _worker(rank, world, port, out):
         pairs = [x for p in zip(counts[rank], [c + 1 for c in counts[rank]]) for x in p]
         both = fab.counts([pairs])[0]
         ok = ok and both[0::2] == exp_rc[rank] and both[1::2] == [c + 1 for c in exp_rc[rank]]
+        h = torch.arange(4, dtype=torch.int64) + rank
+        fab.allreduce_sum([h])
+        ok = ok and h.tolist() == [1, 3, 5, 7]
         out.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()

@@ -49,3 +49,6 @@ def test_emulated_baseline_configs(config, scale, world):
     # the key-range partition is balanced to a few percent on these inputs
     recv = [i["seeds_received"] for i in got["info"]]
     assert max(recv) < 1.25 * (sum(recv) / world)
+    # ... and so is the range partition of the result
+    out = [i["matches"] for i in got["info"]]
+    assert sum(out) == got["n_matches"] and max(out) < 1.5 * (sum(out) / world) + 64

@@ -32,11 +32,17 @@ def main():
     info = find_unique([ctx], TorchFabric(device=dev), dev)
     torch.cuda.synchronize()
     print(f"[rank {rank}] {info[0]} stages {ctx.dist_stage_ms()}", flush=True)
+    piece = ctx.fetch()
+    pieces = [None] * world
+    dist.all_gather_object(pieces, {k: piece[k] for k in ("n_matches", "n_comps", "length", "comp_off", "comp_seq", "comp_start")})
     if rank == 0:
-        got = ctx.fetch()
+        from mauvealigner_b200.dist import concat_results
+        got = concat_results(pieces)
         want = ctx.find(mb.MODE_UNIQUE)
-        ok = got["n_matches"] == want["n_matches"] and all(np.array_equal(got[k], want[k]) for k in ("length", "comp_off", "comp_seq", "comp_start"))
-        print(f"DIST_CHECK world={world} config=C{config}/{scale} matches={got['n_matches']} {'OK bit-exact vs single-GPU path' if ok else 'MISMATCH'}", flush=True)
+        ok = got["n_matches"] == want["n_matches"] and all(np.array_equal(np.asarray(got[k], dtype=np.int64), np.asarray(want[k], dtype=np.int64))
+                                                           for k in ("length", "comp_off", "comp_seq", "comp_start"))
+        print(f"DIST_CHECK world={world} config=C{config}/{scale} matches={got['n_matches']} pieces={[p['n_matches'] for p in pieces]} "
+              f"{'OK bit-exact vs single-GPU path' if ok else 'MISMATCH'}", flush=True)
     dist.barrier()
     ctx.close()
     dist.destroy_process_group()
