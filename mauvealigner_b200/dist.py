@@ -100,17 +100,29 @@ def find_unique(ctxs, fabric, device, nway_mask=0):
     ctxs[...].fetch()); returns per-local-rank info dicts."""
     W, R = fabric.world, fabric.local_ranks
     info = [dict(rank=r) for r in R]
+    trace = os.environ.get("MB_DIST_TRACE")
+    marks = []
+
+    def mark(name):
+        if trace:
+            torch.cuda.synchronize(device)
+            marks.append((name, time.perf_counter()))
+
+    mark("start")
     # ---- stage 1 + exchange 1: seed records by key range
     s1 = [c.dist_extract(r, W) for c, r in zip(ctxs, R)]
     sc = [cnt for _, cnt in s1]
+    mark("stage1 extract+partition")
     rc = fabric.counts(sc)
     sends = [dev_words(p, sum(cnt), device) for p, cnt in s1]
     recvs = [dev_words(c.dist_recv_buffer(0, sum(k)), sum(k), device) for c, k in zip(ctxs, rc)]
     fabric.words(sends, sc, recvs, rc)
+    mark("exchange1 seeds")
     for i, k in enumerate(rc):
         info[i]["seeds_sent"], info[i]["seeds_received"] = sum(sc[i]), sum(k)
     # ---- stage 2 + exchange 2: candidate rows by group owner
     s2 = [c.dist_local(W, sum(k), nway_mask=nway_mask) for c, k in zip(ctxs, rc)]
+    mark("stage2 sort+buckets+rows")
     both = fabric.counts([[x for pair in zip(cc, mc) for x in pair] for _, _, cc, mc in s2])
     rcc = [b[0::2] for b in both]
     rmc = [b[1::2] for b in both]
@@ -120,12 +132,15 @@ def find_unique(ctxs, fabric, device, nway_mask=0):
     mr = [dev_words(c.dist_recv_buffer(2, sum(k)), sum(k), device) for c, k in zip(ctxs, rmc)]
     fabric.words(hs, [cc for _, _, cc, _ in s2], hr, rcc, width=2)
     fabric.words(ms, [mc for _, _, _, mc in s2], mr, rmc)
+    mark("exchange2 candidate rows")
     for i in range(len(R)):
         info[i]["candidates_local"], info[i]["candidates_owned"] = sum(s2[i][2]), sum(rcc[i])
     # ---- stage 3: de-dup of the owned groups; accepted matches go to the rank that owns their range of the canonical order
     hists = [c.dist_dedup(sum(k), sum(m)) for c, k, m in zip(ctxs, rcc, rmc)]
+    mark("stage3a dedup")
     fabric.allreduce_sum([dev_words(p, 4096, device) for p in hists])
     s3 = [c.dist_match_partition(W) for c in ctxs]
+    mark("stage3b match rows")
     both = fabric.counts([[x for pair in zip(cc, mc) for x in pair] for _, _, cc, mc in s3])
     gcc = [b[0::2] for b in both]
     gmc = [b[1::2] for b in both]
@@ -135,11 +150,15 @@ def find_unique(ctxs, fabric, device, nway_mask=0):
     mr = [dev_words(c.dist_recv_buffer(4, sum(k)), sum(k), device) for c, k in zip(ctxs, gmc)]
     fabric.words(hs, [cc for _, _, cc, _ in s3], hr, gcc, width=2)
     fabric.words(ms, [mc for _, _, _, mc in s3], mr, gmc)
+    mark("exchange3 match rows")
     # ---- stage 4: every rank builds the canonical CSR of its range
     for i in range(len(R)):
         info[i]["matches_accepted"] = sum(s3[i][2])
         ctxs[i].dist_output(sum(gcc[i]), sum(gmc[i]))
         info[i]["matches"] = sum(gcc[i])
+    mark("stage4 output")
+    if trace and R[0] == 0:
+        print("[dist-trace] " + ", ".join(f"{n} {1e3 * (t - marks[k][1]):.2f} ms" for k, (n, t) in enumerate(marks[1:])), file=sys.stderr, flush=True)
     return info
 
 
