@@ -797,7 +797,11 @@ int mb_debug_radix(mb_ctx* c, uint64_t n64, int shift, int kbits, int reps, floa
             std::vector<u64> out(n);
             CUDA_TRY(c, cudaMemcpy(out.data(), kA, (size_t)n * 8, cudaMemcpyDeviceToHost));
             for (u32 i = 1; i < n; ++i)
-                if (((out[i - 1] >> shift) & kmask) > ((out[i] >> shift) & kmask)) { cudaEventDestroy(e0); cudaEventDestroy(e1); return MB_E_STATE; }
+                if (((out[i - 1] >> shift) & kmask) > ((out[i] >> shift) & kmask)) {
+                    cudaEventDestroy(e0); cudaEventDestroy(e1);
+                    ms_out[0] = npass_total ? tot_pass / npass_total : 0; ms_out[1] = reps ? tot_sort / reps : 0;
+                    return MB_E_STATE;
+                }
         }
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1);

@@ -17,6 +17,9 @@
 #include "lookback.cuh"
 
 // ------------------------------------------------------------------------------------ find runs
+// Thread = FR_IPT consecutive records (16-byte loads), so all neighbour comparisons but the two at the thread's
+// ends are in registers; per-thread head / unique counts are scanned over the warp, the block and (decoupled
+// look-back) the tiles, and every thread writes its run heads at consecutive ranks.
 #define FR_NT 256
 #define FR_IPT 8
 #define FR_TILE (FR_NT * FR_IPT)
@@ -34,8 +37,7 @@ __device__ __forceinline__ Rec load_rec(const RecFmt& f, const u64* __restrict__
 __global__ void __launch_bounds__(FR_NT) k_find_runs(const u64* __restrict__ keys, const u64* __restrict__ vals, u32 n, RecFmt fmt,
                                                      u32* __restrict__ run_start, u32* __restrict__ run_u, u64* status, u32* ticket,
                                                      u64* __restrict__ per_seq_count /*[nseq] or null*/, u32* __restrict__ totals /*[2]*/) {
-    __shared__ u32 sCnt[FR_IPT * (FR_NT / 32)]; // heads | uniq << 16 per (row, warp)
-    __shared__ u32 sPre[FR_IPT * (FR_NT / 32)];
+    __shared__ u32 sWarp[FR_NT / 32];
     __shared__ u32 sSeq[MB_MAX_SEQ];
     __shared__ u32 sTile;
     __shared__ u64 sExcl;
@@ -45,74 +47,102 @@ __global__ void __launch_bounds__(FR_NT) k_find_runs(const u64* __restrict__ key
     __syncthreads();
     const u32 tile = sTile;
     const u64 base = (u64)tile * FR_TILE;
-    u32 headb[FR_IPT], uniqb[FR_IPT];
+    const u64 i0 = base + (u64)tid * FR_IPT;
+    // records i0 .. i0+7 (keys beyond n read as a key no record has)
+    u64 key[FR_IPT];
+    u32 g[FR_IPT];
+    if (i0 + FR_IPT <= n) {
+        u64 raw[FR_IPT], rv[FR_IPT];
+#pragma unroll
+        for (int k = 0; k < FR_IPT; k += 2) {
+            ulonglong2 q = *reinterpret_cast<const ulonglong2*>(keys + i0 + k);
+            raw[k] = q.x; raw[k + 1] = q.y;
+            if (fmt.wide) {
+                ulonglong2 w = *reinterpret_cast<const ulonglong2*>(vals + i0 + k);
+                rv[k] = w.x; rv[k + 1] = w.y;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < FR_IPT; ++k) {
+            if (fmt.wide) { key[k] = raw[k]; g[k] = (u32)(rv[k] >> 33); }
+            else { key[k] = raw[k] >> fmt.kshift; g[k] = (u32)((raw[k] >> (fmt.pbits + 1)) & ((1u << fmt.gbits) - 1)); }
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < FR_IPT; ++k) {
+            key[k] = ~0ull; g[k] = 0xFFFFFFFFu;
+            if (i0 + k < n) { Rec r = load_rec(fmt, keys, vals, i0 + k); key[k] = r.key; g[k] = r.g; }
+        }
+    }
+    // neighbours across the thread ends: shuffles inside the warp, global loads at the warp edges
+    u64 pkey = __shfl_up_sync(0xFFFFFFFFu, key[FR_IPT - 1], 1);
+    u32 pg = __shfl_up_sync(0xFFFFFFFFu, g[FR_IPT - 1], 1);
+    u64 nkey = __shfl_down_sync(0xFFFFFFFFu, key[0], 1);
+    u32 ng = __shfl_down_sync(0xFFFFFFFFu, g[0], 1);
+    if (lane == 0) { pkey = ~0ull; pg = 0xFFFFFFFFu; if (i0 > 0 && i0 <= n) { Rec r = load_rec(fmt, keys, vals, i0 - 1); pkey = r.key; pg = r.g; } }
+    if (lane == 31) { nkey = ~0ull; ng = 0xFFFFFFFFu; if (i0 + FR_IPT < n) { Rec r = load_rec(fmt, keys, vals, i0 + FR_IPT); nkey = r.key; ng = r.g; } }
+    u32 headm = 0, uniqm = 0;
+    u32 run_g = 0xFFFFFFFFu, run_c = 0; // per-genome count of "first record of its genome in its bucket", flushed on change
 #pragma unroll
     for (int k = 0; k < FR_IPT; ++k) {
-        u64 i = base + (u64)k * FR_NT + tid;
-        bool valid = i < n;
-        Rec c{~0ull, 0xFFFFFFFFu}, p{~0ull, 0xFFFFFFFFu}, q{~0ull, 0xFFFFFFFFu};
-        if (valid) c = load_rec(fmt, keys, vals, i);
-        // neighbours: shuffle inside the warp, global load at the warp edges
-        p.key = __shfl_up_sync(0xFFFFFFFFu, c.key, 1); p.g = __shfl_up_sync(0xFFFFFFFFu, c.g, 1);
-        q.key = __shfl_down_sync(0xFFFFFFFFu, c.key, 1); q.g = __shfl_down_sync(0xFFFFFFFFu, c.g, 1);
-        if (valid && lane == 0 && i > 0) p = load_rec(fmt, keys, vals, i - 1);
-        if (valid && lane == 31 && i + 1 < n) q = load_rec(fmt, keys, vals, i + 1);
-        bool head = valid && (i == 0 || p.key != c.key);
-        bool newg = valid && (head || p.g != c.g);
-        bool last = valid && (i + 1 >= n || q.key != c.key || q.g != c.g);
-        bool uniq = newg && last;
-        if (per_seq_count) { // warp-aggregated: one shared atomic per distinct genome in the warp
-            u32 act = __ballot_sync(0xFFFFFFFFu, newg);
-            u32 peers = __match_any_sync(0xFFFFFFFFu, newg ? c.g : 0xFFFFFFFFu) & act;
-            if (newg && (peers & ((1u << lane) - 1)) == 0) atomicAdd(&sSeq[c.g], (u32)__popc(peers));
+        const u64 i = i0 + k;
+        const bool valid = i < n;
+        const u64 pk = k ? key[k - 1] : pkey, nk = k + 1 < FR_IPT ? key[k + 1] : nkey;
+        const u32 pgk = k ? g[k - 1] : pg, ngk = k + 1 < FR_IPT ? g[k + 1] : ng;
+        const bool head = valid && (i == 0 || pk != key[k]);
+        const bool newg = valid && (head || pgk != g[k]);
+        const bool last = valid && (i + 1 >= n || nk != key[k] || ngk != g[k]);
+        headm |= (head ? 1u : 0u) << k;
+        uniqm |= (newg && last ? 1u : 0u) << k;
+        if (per_seq_count && newg) {
+            if (g[k] != run_g) { if (run_c) atomicAdd(&sSeq[run_g], run_c); run_g = g[k]; run_c = 0; }
+            ++run_c;
         }
-        headb[k] = __ballot_sync(0xFFFFFFFFu, head);
-        uniqb[k] = __ballot_sync(0xFFFFFFFFu, uniq);
-        if (lane == 0) sCnt[k * (FR_NT / 32) + warp] = __popc(headb[k]) | (__popc(uniqb[k]) << 16);
     }
+    if (per_seq_count && run_c) atomicAdd(&sSeq[run_g], run_c);
+    // scan of (heads | uniques << 16) over the block
+    const u32 mine = (u32)__popc(headm) | ((u32)__popc(uniqm) << 16);
+    u32 x = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        u32 y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) sWarp[warp] = x;
     __syncthreads();
     if (warp == 0) {
-        // 64 (row, warp) counts, 2 per lane, exclusive scan in (row, warp) order
-        const int NE = FR_IPT * (FR_NT / 32);
-        u32 a = sCnt[2 * lane], b = sCnt[2 * lane + 1];
-        u64 va = (u64)(a & 0xFFFF) | ((u64)(a >> 16) << 31), vb = (u64)(b & 0xFFFF) | ((u64)(b >> 16) << 31);
-        u64 s = va + vb, x = s;
+        u32 w = lane < FR_NT / 32 ? sWarp[lane] : 0, xs = w;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            u64 y = __shfl_up_sync(0xFFFFFFFFu, x, o);
-            if (lane >= o) x += y;
+        for (int o = 1; o < FR_NT / 32; o <<= 1) {
+            u32 y = __shfl_up_sync(0xFFFFFFFFu, xs, o);
+            if (lane >= o) xs += y;
         }
-        u64 ex = x - s;
-        // tile-local exclusive prefixes fit 16 bits each (tile = 2048)
-        sPre[2 * lane] = (u32)(ex & 0xFFFF) | ((u32)((ex >> 31) & 0xFFFF) << 16);
-        u64 ex2 = ex + va;
-        sPre[2 * lane + 1] = (u32)(ex2 & 0xFFFF) | ((u32)((ex2 >> 31) & 0xFFFF) << 16);
-        u64 agg = __shfl_sync(0xFFFFFFFFu, x, 31);
+        if (lane < FR_NT / 32) sWarp[lane] = xs - w;
+        u32 tot = __shfl_sync(0xFFFFFFFFu, xs, FR_NT / 32 - 1);
+        u64 agg = (u64)(tot & 0xFFFF) | ((u64)(tot >> 16) << 31);
         u64 excl = lookback_exclusive(status, tile, agg);
         if (lane == 0) {
             sExcl = excl;
             if (base + FR_TILE >= n) { // last tile: totals + sentinels
-                u64 tot = excl + agg;
-                u32 nr = (u32)(tot & 0x7FFFFFFFu), nu = (u32)(tot >> 31);
+                u64 t2 = excl + agg;
+                u32 nr = (u32)(t2 & 0x7FFFFFFFu), nu = (u32)(t2 >> 31);
                 totals[0] = nr; totals[1] = nu;
                 run_start[nr] = n;
                 if (run_u) run_u[nr] = nu;
             }
         }
-        (void)NE;
     }
     __syncthreads();
-    const u64 excl = sExcl;
-    const u32 eh = (u32)(excl & 0x7FFFFFFFu), eu = (u32)(excl >> 31);
+    const u32 pre = sWarp[warp] + x - mine;
+    u32 rh = (u32)(sExcl & 0x7FFFFFFFu) + (pre & 0xFFFF), ru = (u32)(sExcl >> 31) + (pre >> 16);
 #pragma unroll
     for (int k = 0; k < FR_IPT; ++k) {
-        if ((headb[k] >> lane) & 1) {
-            u32 pre = sPre[k * (FR_NT / 32) + warp];
-            u32 lt = (1u << lane) - 1;
-            u32 r = eh + (pre & 0xFFFF) + __popc(headb[k] & lt);
-            run_start[r] = (u32)(base + (u64)k * FR_NT + tid);
-            if (run_u) run_u[r] = eu + (pre >> 16) + __popc(uniqb[k] & lt);
+        if ((headm >> k) & 1) {
+            run_start[rh] = (u32)(i0 + k);
+            if (run_u) run_u[rh] = ru;
+            ++rh;
         }
+        ru += (uniqm >> k) & 1;
     }
     if (per_seq_count && tid < MB_MAX_SEQ && sSeq[tid]) atomicAdd((unsigned long long*)&per_seq_count[tid], (unsigned long long)sSeq[tid]);
 }
