@@ -122,6 +122,25 @@ def test_substitutions_only_long_diagonal(ctx):
         assert_same(run(ctx, [s, t], pattern, 0), O.find([s, t], pattern, O.MODE_UNIQUE))
 
 
+@pytest.mark.parametrize("which", range(4))
+def test_wide_records_all_modes(ctx, which):
+    """Seeds of weight >= 29 do not fit key + genome + position in 64 bits: 16-byte records (key word + value word)."""
+    import mauvealigner_b200 as mb
+    pattern = [(1 << 31) - 1, (1 << 29) - 1, mb.get_seed(31, 0), mb.get_seed(29, mb.CODING_SEED)][which]
+    rng = np.random.default_rng(pattern & 0xFFFF)
+    seqs = family(rng, 30000, 3, sub=0.01, indel=0.001, inv=1)
+    seqs[1] = revcomp(seqs[1])
+    assert_same(run(ctx, seqs, pattern, 0), O.find(seqs, pattern, O.MODE_UNIQUE), "unique")
+    got = run(ctx, seqs, pattern, 2)
+    want = O.find(seqs, pattern, O.MODE_UNIQUE_COUNT)
+    assert got["unique_mers"] == want["unique_mers"] and got["unique_mers_per_seq"].tolist() == want["unique_mers_per_seq"].tolist()
+    unit = rand_seq(rng, 400)
+    s = rand_seq(rng, 5000) + unit + rand_seq(rng, 777) + unit + revcomp(unit) + rand_seq(rng, 100)
+    assert_same(run(ctx, [s], pattern, 1, min_multi=2, max_multi=100), O.find([s], pattern, O.MODE_SEED_ENUM, min_multi=2, max_multi=100), "enum")
+    for i, q in enumerate([s]):
+        assert np.array_equal(ctx.sml(i, len(q)), O.sml(q, pattern))
+
+
 def test_nway_mask(ctx):
     rng = np.random.default_rng(44)
     seqs = family(rng, 5000, 4, sub=0.02, indel=0.002, inv=1)
