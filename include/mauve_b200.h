@@ -44,7 +44,7 @@ enum {
                                  MaskedMemHash (src/mauveAligner.cpp:523-531).                        */
     MB_MODE_SEED_ENUM = 1,    /* SeedMatchEnumerator::HashMatch (src/SeedMatchEnumerator.h:71-123)    */
     MB_MODE_UNIQUE_COUNT = 2, /* SortedMerList::UniqueMerCount (src/uniqueMerCount.cpp:39)            */
-    MB_MODE_PAIRWISE = 3      /* PairwiseMatchFinder (src/progressiveMauve.cpp:496-501)               */
+    MB_MODE_PAIRWISE = 3      /* PairwiseMatchFinder (src/progressiveMauve.cpp:496-501); at most 8 sequences */
 };
 
 typedef struct mb_params {

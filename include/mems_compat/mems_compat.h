@@ -265,6 +265,22 @@ protected:
     MatchList found_;
 };
 
+/* mems::PairwiseMatchFinder (src/progressiveMauve.cpp:496-501): MemHash's unique filter, then one two-genome match
+ * per pair of the bucket's unique genomes. */
+class PairwiseMatchFinder : public MemHash {
+public:
+    virtual PairwiseMatchFinder* Clone() const { return new PairwiseMatchFinder(*this); }
+    virtual boolean FindMatches(MatchList& match_list) {
+        for (size_t i = 0; i < match_list.seq_table.size(); ++i)
+            if (!AddSequence(match_list.sml_table[i], match_list.seq_table[i])) return false;
+        found_.clear();
+        mb_params p = {MB_MODE_PAIRWISE, 0, 2, 1000, 0};
+        if (!run(p, found_, true)) return false;
+        GetMatchList(match_list);
+        return true;
+    }
+};
+
 class MaskedMemHash : public MemHash {
 public:
     virtual MaskedMemHash* Clone() const { return new MaskedMemHash(*this); }

@@ -269,6 +269,8 @@ int mbi_setup_run(mb_ctx* c, MbiRun& r) {
         n64 += ns; bases += len; maxlen = std::max(maxlen, len);
     }
     r.tile_first[nseq] = n_tiles;
+    gt.pairwise = 0;
+    for (u32 g = 0; g < nseq; ++g) gt.vbase[g] = gt.base_base[g];
     if (n64 >= (1ull << 31)) return MB_E_TOOLONG;
     const u32 n = (u32)n64;
     r.n = n; r.n_tiles = n_tiles; r.bases = bases; r.maxlen = maxlen;
@@ -287,7 +289,7 @@ int mbi_setup_run(mb_ctx* c, MbiRun& r) {
     TRY(c->reserve(c->lookback, (size_t)(div_up(n, radix_tile_size()) + 1) * 256 * 8));
     TRY(c->reserve(c->tickets, 256 * 4));
     size_t status_words = (size_t)div_up(n, find_runs_tile()) + div_up(n, select_tile()) + 6 * (size_t)div_up(n, scan_tile()) +
-                          div_up(bases / 64 + 2, scan_tile()) + 2 * (size_t)div_up(n, chain_tile()) + 64;
+                          div_up(bases * std::min<u64>(nseq, 8) / 64 + 2, scan_tile()) + 2 * (size_t)div_up(n, chain_tile()) + 64;
     TRY(c->reserve(c->status, status_words * 8));
     TRY(c->reserve(c->scalars, SC_COUNT * 8));
     TRY(c->reserve(c->per_seq, MB_MAX_SEQ * 8));
@@ -309,7 +311,7 @@ int mb_find_device(mb_ctx* c, const mb_params* prm) {
     if (!c || !prm) return MB_E_ARG;
     const int mode = prm->mode;
     if (mode < MB_MODE_UNIQUE || mode > MB_MODE_PAIRWISE) return MB_E_ARG;
-    if (mode == MB_MODE_PAIRWISE) return MB_E_ARG; // not built yet
+    if (mode == MB_MODE_PAIRWISE && c->seq_len.size() > 8) return MB_E_SEQCOUNT; // the reference uses it for <= 4 genomes
     if (mode == MB_MODE_SEED_ENUM && c->seq_len.size() > 1) return MB_E_SEQCOUNT;
     MbiRun run;
     TRY(mbi_setup_run(c, run));
@@ -319,7 +321,14 @@ int mb_find_device(mb_ctx* c, const mb_params* prm) {
     GenomeTable& gt = c->gt;
     RecFmt& fmt = c->fmt;
     const u32 n = run.n, n_tiles = run.n_tiles;
-    const u64 bases = run.bases, maxlen = run.maxlen;
+    u64 bases = run.bases; // length of the candidate bitmap axis
+    const u64 maxlen = run.maxlen;
+    if (mode == MB_MODE_PAIRWISE) {
+        gt.pairwise = 1;
+        bases = 0;
+        for (u32 g0 = 0; g0 < gt.nseq; ++g0)
+            for (u32 g1 = g0 + 1; g1 < gt.nseq; ++g1) { gt.vbase[vgenome(gt, g0, g1)] = bases; bases += gt.len[g0]; }
+    }
     const int npass = (fmt.kbits + 7) / 8;
     const size_t nrec = (size_t)n + 8;
     TRY(c->reserve(c->keysA, nrec * 8));
@@ -366,9 +375,12 @@ int mb_find_device(mb_ctx* c, const mb_params* prm) {
     }
 
     // ---- a7/a8: per-bucket policy -> candidates
-    const u32 cand_cap = n / 2 + 2;
-    TRY(c->reserve(c->cand_run, (size_t)cand_cap * 4));
-    TRY(c->reserve(c->cand_off, (size_t)(cand_cap + 1) * 4));
+    // one candidate per bucket; PAIRWISE: one per pair of unique genomes of a bucket (u (u-1) / 2 <= records * (nseq-1) / 2)
+    const size_t cand_cap = mode == MB_MODE_PAIRWISE ? (size_t)n * (c->seq_len.size() - 1) / 2 + 2 : (size_t)n / 2 + 2;
+    if (cand_cap >= (1ull << 30)) return MB_E_TOOLONG;
+    TRY(c->reserve(c->cand_run, cand_cap * 4));
+    TRY(c->reserve(c->cand_off, (cand_cap + 1) * 4));
+    if (mode == MB_MODE_PAIRWISE) TRY(c->reserve(c->cand_aux, cand_cap * 4));
     SelectArgs sa{};
     sa.keys = kA; sa.vals = vA; sa.run_start = run_start; sa.run_u = run_u;
     sa.n_runs_ptr = reinterpret_cast<u32*>(scal + SC_RUNS);
@@ -377,7 +389,7 @@ int mb_find_device(mb_ctx* c, const mb_params* prm) {
     sa.status = c->status_slice(div_up(n, select_tile())); sa.ticket = c->ticket();
     sa.n_buckets = scal + SC_NBUCKETS;
     sa.totals = reinterpret_cast<u32*>(scal + SC_CAND);
-    sa.cand_run = c->cand_run.as<u32>(); sa.cand_off = c->cand_off.as<u32>(); sa.cand_aux = nullptr;
+    sa.cand_run = c->cand_run.as<u32>(); sa.cand_off = c->cand_off.as<u32>(); sa.cand_aux = mode == MB_MODE_PAIRWISE ? c->cand_aux.as<u32>() : nullptr;
     launch_select(sa, fmt, n, st);
     LAUNCHED(c); CHECK_LAUNCH(c);
     memset(c->h_perseq, 0, MB_MAX_SEQ * 8); // per-sequence counts are a MODE_UNIQUE_COUNT product
@@ -438,7 +450,7 @@ int mb_find_device(mb_ctx* c, const mb_params* prm) {
         CUDA_TRY(c, cudaMemsetAsync(c->bitmap.p, 0, bm_words * 8, st));
         EmitUniqueArgs eu{};
         eu.keys = kA; eu.vals = vA; eu.run_start = run_start; eu.run_u = run_u;
-        eu.cand_run = c->cand_run.as<u32>(); eu.cand_off = c->cand_off.as<u32>(); eu.cand_aux = nullptr;
+        eu.cand_run = c->cand_run.as<u32>(); eu.cand_off = c->cand_off.as<u32>(); eu.cand_aux = mode == MB_MODE_PAIRWISE ? c->cand_aux.as<u32>() : nullptr;
         eu.totals = reinterpret_cast<u32*>(scal + SC_CAND);
         eu.mode = mode; eu.comp_pos = c->comp_pos.as<u32>(); eu.comp_gs = c->comp_gs.as<u8>(); eu.bitmap = c->bitmap.as<u64>(); eu.ghash = c->ghash.as<u64>(); eu.ghash2 = c->ghash2.as<u64>();
         launch_emit_unique(eu, fmt, gt, n_cand, st); LAUNCHED(c); CHECK_LAUNCH(c);

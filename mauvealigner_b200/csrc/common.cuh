@@ -56,7 +56,14 @@ struct GenomeTable {
     u32 len[MB_MAX_SEQ];
     u32 seed_base[MB_MAX_SEQ];   // first record index of genome g in extraction order
     u32 nseq;
+    // candidate bitmap axis: one "virtual genome" per first genome (MODE_UNIQUE) or per genome pair (MODE_PAIRWISE,
+    // where several candidates of one bucket share their first component)
+    u32 pairwise;
+    u64 vbase[MB_MAX_SEQ];       // first bitmap index of virtual genome v
 };
+__host__ __device__ __forceinline__ u32 vgenome(const GenomeTable& gt, u32 g0, u32 g1) {
+    return gt.pairwise ? g0 * gt.nseq - g0 * (g0 + 1) / 2 + (g1 - g0 - 1) : g0;
+}
 
 // ---- device helpers ---------------------------------------------------------------------------
 __device__ __forceinline__ u64 shl128_hi(u64 hi, u64 lo, int s) { // top 64 bits of (hi:lo) << s, 0 <= s < 64

@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(256) k_emit_unique(EmitUniqueArgs a, RecFmt fm
     }
     u32 prev_g = 0xFFFFFFFFu;
     u32 ui = 0;
-    u32 x0 = 0;
+    u32 x0 = 0, g_first = 0, g_second = 0;
     u64 h = 0x9E3779B97F4A7C15ull, h2 = 0xC2B2AE3D27D4EB4Full;
     for (u32 i = s; i < e; ++i) {
         u64 v = fmt.wide ? a.vals[i] : a.keys[i];
@@ -303,12 +303,8 @@ __global__ void __launch_bounds__(256) k_emit_unique(EmitUniqueArgs a, RecFmt fm
         ++ui;
         if (!take) continue;
         u32 p = rec_pos(fmt, v), sb = rec_strand(v);
-        if (k == 0) {
-            strand0 = sb;
-            x0 = p;
-            u64 gp = gt.base_base[g] + p;
-            if (a.bitmap) atomicOr((unsigned long long*)&a.bitmap[gp >> 6], 1ull << (gp & 63));
-        }
+        if (k == 0) { strand0 = sb; x0 = p; g_first = g; }
+        if (k == 1) g_second = g;
         bool rev = sb != strand0;
         a.comp_pos[off + k] = p;
         a.comp_gs[off + k] = (u8)(g | (rev ? 0x80u : 0u));
@@ -321,6 +317,10 @@ __global__ void __launch_bounds__(256) k_emit_unique(EmitUniqueArgs a, RecFmt fm
     }
     a.ghash[c] = h;
     a.ghash2[c] = h2 & ~0xFFull;
+    if (a.bitmap) {
+        u64 gp = gt.vbase[vgenome(gt, g_first, g_second)] + x0;
+        atomicOr((unsigned long long*)&a.bitmap[gp >> 6], 1ull << (gp & 63));
+    }
 }
 
 void launch_emit_unique(const EmitUniqueArgs& a, const RecFmt& fmt, const GenomeTable& gt, u32 n_cand_upper, cudaStream_t st) {

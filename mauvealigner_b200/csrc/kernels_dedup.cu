@@ -66,7 +66,7 @@ __device__ __forceinline__ bool groups_equal(const DedupArgs& a, u32 c1, u32 c2)
 // (one full-sector scattered store per candidate; everything later steps need about the candidate, so that
 // they never chase the candidate CSR again):
 //   a.x = group hash with bit 0 replaced by "the previous base of the genome holds a candidate too" (then
-//         that candidate is slot s-1),  a.y = candidate | components << 32 | first genome << 40
+//         that candidate is slot s-1),  a.y = candidate | components << 32 | first genome << 40 | virtual genome << 48
 //   b.x = second group hash,             b.y = first component row | first position << 32
 #define HASH_MASK (~1ull)
 __global__ void __launch_bounds__(256) k_slot_scatter(DedupArgs a, GenomeTable gt) {
@@ -74,14 +74,15 @@ __global__ void __launch_bounds__(256) k_slot_scatter(DedupArgs a, GenomeTable g
     if (c >= a.n_cand) return;
     u32 off = a.cand_off[c], m = a.cand_off[c + 1] - off;
     u32 g = a.comp_gs[off] & 0x7F, p = a.comp_pos[off];
-    u64 gp = gt.base_base[g] + p;
+    const u32 vg = vgenome(gt, g, a.comp_gs[off + 1] & 0x7F); // a candidate has >= 2 components
+    u64 gp = gt.vbase[vg] + p;
     u64 w = a.bitmap[gp >> 6];
     u32 s = a.bmrank[gp >> 6] + (u32)__popcll(w & ((1ull << (gp & 63)) - 1));
     // a candidate never sits on the last L-1 bases of a genome, so base gp-1 belongs to the same genome
     // whenever it holds a candidate
     u64 adj = 0;
     if (gp > 0) adj = (gp & 63) ? (w >> ((gp & 63) - 1)) & 1 : (a.bitmap[(gp >> 6) - 1] >> 63) & 1;
-    a.slot_rec[2 * (size_t)s] = make_ulonglong2((a.ghash[c] & HASH_MASK) | adj, (u64)c | ((u64)m << 32) | ((u64)g << 40));
+    a.slot_rec[2 * (size_t)s] = make_ulonglong2((a.ghash[c] & HASH_MASK) | adj, (u64)c | ((u64)m << 32) | ((u64)g << 40) | ((u64)vg << 48));
     a.slot_rec[2 * (size_t)s + 1] = make_ulonglong2(a.ghash2[c], (u64)off | ((u64)p << 32));
 }
 
@@ -524,7 +525,7 @@ __global__ void __launch_bounds__(256) k_rep_setup(DedupArgs a) {
     if (i >= a.n_rep) return;
     const u32 slot = (u32)a.s_key[i];
     const ulonglong2 r = a.slot_rec[2 * (size_t)slot], q = a.slot_rec[2 * (size_t)slot + 1];
-    const u32 c = (u32)r.y, m = (u32)(r.y >> 32) & 0xFFu, g0 = (u32)(r.y >> 40) & 0xFFu;
+    const u32 c = (u32)r.y, m = (u32)(r.y >> 32) & 0xFFu, g0 = (u32)(r.y >> 40) & 0xFFu, vg = (u32)(r.y >> 48) & 0xFFu;
     const u64 h = r.x & HASH_MASK;
     a.s_rec[i] = make_ulonglong2((h & 0xFFFF000000000000ull) | ((u64)slot << 16) | (h & 0xFFFFull), (((h >> 16) & 0xFFFFFFFFull) << 32) | c);
     a.s_cand[i] = c;
@@ -532,7 +533,7 @@ __global__ void __launch_bounds__(256) k_rep_setup(DedupArgs a) {
     a.minrank[i] = INF64; a.minrank[(size_t)a.n_rep + i] = INF64;
     a.reach[i] = 0;
     a.rstate[i] = 0;
-    a.xrec[i] = make_uint4(c, (u32)q.y, m | (g0 << 8), (u32)(q.y >> 32));
+    a.xrec[i] = make_uint4(c, (u32)q.y, m | (g0 << 8) | (vg << 16), (u32)(q.y >> 32));
 }
 
 // ---- extend: a warp takes 32 reps.  Lane j owns rep j's state; the (rep, component) pairs of the warp
@@ -543,7 +544,7 @@ __global__ void __launch_bounds__(256) k_rep_setup(DedupArgs a) {
 // (a few launches); what is still unfinished then goes to the warp-per-rep kernel.
 enum { ST_CENTER = 0, ST_LEFT = 1, ST_RIGHT = 2, ST_DONE = 3 };
 struct XLane {
-    u32 c, off, m, p0, g0;      // candidate, its component rows, first component
+    u32 c, off, m, p0, g0, vg;  // candidate, its component rows, first component, virtual genome of the bitmap axis
     int st; bool rj;            // walk state; rj: the right side still has to be walked
     u32 b, el, er, room_l, room_r;
 };
@@ -643,7 +644,7 @@ __device__ __forceinline__ void extend_finish(const DedupArgs& a, const GenomeTa
     if (valid && !more) {
         a.ext_l[x.c] = x.el; a.ext_r[x.c] = x.er;
         u32 rlo, rhi;
-        extent_slots(a, gt.base_base[x.g0] + x.p0, x.el, x.er, rlo, rhi);
+        extent_slots(a, gt.vbase[x.vg] + x.p0, x.el, x.er, rlo, rhi);
         a.rng_lo[i] = rlo; a.rng_hi[i] = rhi;
     }
     if (more && !last) {
@@ -663,10 +664,10 @@ __global__ void __launch_bounds__(DD_NT) k_extend(DedupArgs a, GenomeTable gt, S
     const u32 i = blockIdx.x * DD_NT + threadIdx.x;
     const bool valid = i < a.n_rep;
     const u32 L = sd.L;
-    XLane x{0, 0, 1, 0, 0, ST_DONE, true, 0, 0, 0, INF32, INF32};
+    XLane x{0, 0, 1, 0, 0, 0, ST_DONE, true, 0, 0, 0, INF32, INF32};
     if (valid) {
         uint4 q = a.xrec[i];
-        x.c = q.x; x.off = q.y; x.m = q.z & 0xFFu; x.g0 = q.z >> 8; x.p0 = q.w;
+        x.c = q.x; x.off = q.y; x.m = q.z & 0xFFu; x.g0 = (q.z >> 8) & 0xFFu; x.vg = q.z >> 16; x.p0 = q.w;
         x.st = 3 * L <= 64 ? ST_CENTER : ST_LEFT;
     }
     if (L > 32) { // uniform: window-by-window warp kernel only
@@ -687,11 +688,11 @@ __global__ void __launch_bounds__(DD_NT) k_extend_more(DedupArgs a, GenomeTable 
     for (u32 base = gwarp * 32; base < n; base += nwarps * 32) {
         const bool valid = base + lane < n;
         u32 i = 0;
-        XLane x{0, 0, 1, 0, 0, ST_DONE, true, 0, 0, 0, INF32, INF32};
+        XLane x{0, 0, 1, 0, 0, 0, ST_DONE, true, 0, 0, 0, INF32, INF32};
         if (valid) {
             i = in_list[base + lane];
             uint4 q = a.xrec[i];
-            x.c = q.x; x.off = q.y; x.m = q.z & 0xFFu; x.g0 = q.z >> 8; x.p0 = q.w;
+            x.c = q.x; x.off = q.y; x.m = q.z & 0xFFu; x.g0 = (q.z >> 8) & 0xFFu; x.vg = q.z >> 16; x.p0 = q.w;
             uint4 s = a.xstate[i];
             x.st = (int)(s.x & 3u); x.rj = (s.x & 4u) != 0; x.b = s.y; x.room_l = s.z; x.room_r = s.w;
             x.el = a.ext_l[x.c]; x.er = a.ext_r[x.c];
@@ -724,7 +725,7 @@ __global__ void __launch_bounds__(DD_NT) k_extend_long(DedupArgs a, GenomeTable 
         if (lane == 0) {
             a.ext_l[c] = el; a.ext_r[c] = er;
             u32 rlo, rhi;
-            extent_slots(a, gt.base_base[cgs[0] & 0x7F] + cpos[0], el, er, rlo, rhi);
+            extent_slots(a, gt.vbase[vgenome(gt, cgs[0] & 0x7F, cgs[1] & 0x7F)] + cpos[0], el, er, rlo, rhi);
             a.rng_lo[i] = rlo; a.rng_hi[i] = rhi;
         }
     }

@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(256) k_unpack_cand(const u64* __restrict__ hdr
         comp_pos[off + k] = p;
         comp_gs[off + k] = gs;
         if (k == 0) {
-            u64 gp = gt.base_base[gs & 0x7F] + p;
+            u64 gp = gt.vbase[gs & 0x7F] + p; // MODE_UNIQUE only: virtual genome = first genome
             atomicOr((unsigned long long*)&bitmap[gp >> 6], 1ull << (gp & 63));
         }
     }

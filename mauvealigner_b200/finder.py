@@ -351,6 +351,17 @@ class UniqueMatchFinder(MatchFinder):
 MemHash = UniqueMatchFinder
 
 
+class PairwiseMatchFinder(UniqueMatchFinder):
+    """libMems PairwiseMatchFinder (src/progressiveMauve.cpp:496-501: used when <= 4 genomes are aligned): the unique
+    filter of MemHash, then one two-genome match per PAIR of the bucket's unique genomes."""
+
+    def FindMatches(self, match_list):
+        ctx = self._load(match_list)
+        self.last = ctx.find(L.MODE_PAIRWISE)
+        self._fill(match_list, self.last, self.seq_count, dense=True)
+        return True
+
+
 class MaskedMemHash(UniqueMatchFinder):
     def SetMask(self, mask):
         self._mask = int(mask)

@@ -43,6 +43,7 @@ def main():
     f[2] = revcomp(f[2])
     cases.append(case("four_genomes_one_reverse", f, 0b110110110111011011011, O.MODE_UNIQUE))
     cases.append(case("nway_mask", f, 0b1011101, O.MODE_UNIQUE, nway_mask=0b0101))
+    cases.append(case("pairwise_four_genomes", f, 0b110111011, O.MODE_PAIRWISE))
     cases.append(case("identical_pair_solid", [a, a], 0b1111111, O.MODE_UNIQUE))
     cases.append(case("short_and_empty", ["ACG", "ACGTTGCAGT", "", "TTGCAGTACG"], 0b11111, O.MODE_UNIQUE))
     unit = rand_seq(rng, 120)

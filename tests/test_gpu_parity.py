@@ -141,6 +141,20 @@ def test_wide_records_all_modes(ctx, which):
         assert np.array_equal(ctx.sml(i, len(q)), O.sml(q, pattern))
 
 
+@pytest.mark.parametrize("k", [2, 3, 4, 6])
+def test_pairwise_vs_oracle(ctx, k):
+    """PairwiseMatchFinder policy: several candidates of one bucket share their first component."""
+    rng = np.random.default_rng(600 + k)
+    seqs = family(rng, 6000, k, sub=0.02, indel=0.003, inv=1)
+    if k > 2:
+        seqs[2] = revcomp(seqs[2])
+    for pattern in (0b110111011, 0b1101110111110111011):
+        got = run(ctx, seqs, pattern, 3)
+        want = O.find(seqs, pattern, O.MODE_PAIRWISE)
+        assert_same(got, want, f"pairwise k={k}")
+        assert got["n_matches"] > 0 and set(np.diff(got["comp_off"]).tolist()) == {2}
+
+
 def test_nway_mask(ctx):
     rng = np.random.default_rng(44)
     seqs = family(rng, 5000, 4, sub=0.02, indel=0.002, inv=1)
