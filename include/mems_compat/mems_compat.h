@@ -25,6 +25,8 @@
 
 #include <cstdint>
 #include <cstdlib>
+#include <cstring>
+#include <fstream>
 #include <iostream>
 #include <stdexcept>
 #include <string>
@@ -111,7 +113,8 @@ public:
     gnSeqI Length() const { return seq_->length(); }
     const genome::gnSequence* Sequence() const { return seq_; }
     /* number of distinct seeds of this sequence (src/uniqueMerCount.cpp:39); computed on the device on first use */
-    gnSeqI UniqueMerCount() {
+    virtual ~SortedMerList() {}
+    virtual gnSeqI UniqueMerCount() {
         if (unique_ != ~0ull) return unique_;
         mb_ctx* ctx = nullptr;
         int rc = mb_ctx_create(&ctx, 0);
@@ -128,10 +131,84 @@ public:
         if (rc != MB_OK) throw genome::gnException(err);
         return unique_;
     }
-private:
+protected:
     const genome::gnSequence* seq_;
     uint64 seed_;
     uint64 unique_;
+};
+
+/* mems::DNAFileSML — a sorted mer list kept in a file (".sslist"; src/uniqueMerCount.cpp:30-39, default naming
+ * src/progressiveMauve.cpp:215-224).  libMems' own file layout is not available, so this is a
+ * versioned format of this project: little-endian header { char magic[8] = "MBSSLIST"; u32 version = 1; u32 reserved;
+ * u64 seed pattern; u64 sequence length; u64 positions; u64 unique mers }, then the 2-bit packed sequence (32 bases
+ * per u64, first base in the top bits), then the positions (u32) sorted by (seed, position).  Create() builds the
+ * list on the device (k_extract + k_onesweep + k_find_runs) through the C ABI. */
+class DNAFileSML : public SortedMerList {
+public:
+    DNAFileSML() : SortedMerList(nullptr, 0) {}
+    void Create(const genome::gnSequence& seq, uint64 seed) {
+        own_ = seq; seq_ = &own_; seed_ = seed;
+        if (!mb_seed_valid(seed)) throw genome::gnException("DNAFileSML::Create: invalid seed");
+        mb_ctx* ctx = nullptr;
+        int rc = mb_ctx_create(&ctx, 0);
+        if (rc != MB_OK) throw genome::gnException(std::string("mb_ctx_create: ") + mb_strerror(rc));
+        const std::string& s = own_.data();
+        mb_params p = {MB_MODE_UNIQUE_COUNT, 0, 2, 1000, 0};
+        const mb_result* r = nullptr;
+        rc = mb_add_sequence(ctx, (const uint8_t*)s.data(), s.size(), 0, nullptr);
+        if (rc == MB_OK) rc = mb_set_seed(ctx, seed);
+        if (rc == MB_OK) rc = mb_find(ctx, &p, &r);
+        if (rc == MB_OK) {
+            unique_ = r->unique_mers;
+            uint64_t n = s.size() >= (size_t)mb_seed_length(seed) ? s.size() - mb_seed_length(seed) + 1 : 0, got = 0;
+            pos_.assign(n ? n : 1, 0);
+            rc = mb_get_sml(ctx, 0, pos_.data(), n ? n : 1, &got);
+            pos_.resize(n);
+        }
+        std::string err = rc == MB_OK ? "" : std::string(mb_strerror(rc)) + " " + mb_last_cuda_error(ctx);
+        mb_ctx_destroy(ctx);
+        if (rc != MB_OK) throw genome::gnException(err);
+    }
+    void WriteFile(const std::string& path) const {
+        std::ofstream f(path.c_str(), std::ios::binary);
+        if (!f) throw genome::gnException("cannot write " + path);
+        const std::string& s = own_.data();
+        uint64_t hdr[6] = {0, 1, seed_, (uint64_t)s.size(), (uint64_t)pos_.size(), unique_};
+        memcpy(&hdr[0], "MBSSLIST", 8);
+        f.write((const char*)hdr, sizeof(hdr));
+        std::vector<uint64_t> words((s.size() + 31) / 32, 0);
+        for (size_t i = 0; i < s.size(); ++i) {
+            char c = s[i] & 0xDF;
+            uint64_t code = c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : 0;
+            words[i / 32] |= code << (62 - 2 * (i % 32));
+        }
+        f.write((const char*)words.data(), words.size() * 8);
+        f.write((const char*)pos_.data(), pos_.size() * 4);
+        if (!f) throw genome::gnException("short write " + path);
+    }
+    void LoadFile(const std::string& path) {
+        std::ifstream f(path.c_str(), std::ios::binary);
+        if (!f) throw genome::gnException("cannot open " + path);
+        uint64_t hdr[6];
+        f.read((char*)hdr, sizeof(hdr));
+        if (!f || memcmp(&hdr[0], "MBSSLIST", 8) != 0 || (uint32_t)hdr[1] != 1) throw genome::gnException(path + ": not a version-1 sorted mer list");
+        seed_ = hdr[2]; unique_ = hdr[5];
+        std::vector<uint64_t> words((hdr[3] + 31) / 32);
+        f.read((char*)words.data(), words.size() * 8);
+        pos_.resize(hdr[4]);
+        f.read((char*)pos_.data(), pos_.size() * 4);
+        if (!f) throw genome::gnException(path + ": truncated");
+        std::string s(hdr[3], 'A');
+        for (size_t i = 0; i < s.size(); ++i) s[i] = "ACGT"[(words[i / 32] >> (62 - 2 * (i % 32))) & 3];
+        own_ = genome::gnSequence(s); seq_ = &own_;
+    }
+    virtual gnSeqI UniqueMerCount() { return unique_ != ~0ull ? unique_ : SortedMerList::UniqueMerCount(); }
+    /* the sorted position array (libMems: operator[] / Read) */
+    const std::vector<uint32_t>& Positions() const { return pos_; }
+    gnSeqI SMLLength() const { return pos_.size(); }
+private:
+    genome::gnSequence own_;
+    std::vector<uint32_t> pos_;
 };
 
 class MatchList : public std::vector<Match*> {
@@ -151,9 +228,30 @@ public:
         for (genome::gnSequence* seq : seq_table) sml_table.push_back(new SortedMerList(seq, seed));
         if (log_stream) *log_stream << "Using weight " << mb_seed_weight(seed) << " mers, length " << mb_seed_length(seed) << "\n";
     }
-    /* LoadSMLs(mer_size, log, seed_rank[, solid, force_recreate]): no on-disk cache is kept by this path */
-    void LoadSMLs(uint32 mer_size, std::ostream* log_stream, int seed_rank = 0, bool solid = false, bool = false) {
-        CreateMemorySMLs(mer_size, log_stream, solid ? SOLID_SEED : seed_rank);
+    /* LoadSMLs(mer_size, log, seed_rank[, solid, force_recreate]) (src/mauveAligner.cpp:456, src/repeatoire.cpp:1850): with
+     * sml_filename set, each list is loaded from its file when that exists and was built with the same seed, otherwise
+     * (or with force_recreate) built on the device and written there; without file names it is CreateMemorySMLs. */
+    void LoadSMLs(uint32 mer_size, std::ostream* log_stream, int seed_rank = 0, bool solid = false, bool force_recreate = false) {
+        if (sml_filename.size() != seq_table.size()) { CreateMemorySMLs(mer_size, log_stream, solid ? SOLID_SEED : seed_rank); return; }
+        if (mer_size == 0) mer_size = GetDefaultMerSize(seq_table);
+        uint64 seed = mb_get_seed((int)mer_size, solid ? SOLID_SEED : seed_rank);
+        if (!mb_seed_valid(seed)) throw genome::gnException("invalid seed weight / rank");
+        for (SortedMerList* s : sml_table) delete s;
+        sml_table.clear();
+        for (size_t i = 0; i < seq_table.size(); ++i) {
+            DNAFileSML* sml = new DNAFileSML();
+            bool ok = false;
+            if (!force_recreate) {
+                try { sml->LoadFile(sml_filename[i]); ok = sml->Seed() == seed && sml->Length() == seq_table[i]->length(); }
+                catch (const genome::gnException&) { ok = false; }
+            }
+            if (!ok) {
+                if (log_stream) *log_stream << "Creating sorted mer list " << sml_filename[i] << "\n";
+                sml->Create(*seq_table[i], seed);
+                sml->WriteFile(sml_filename[i]);
+            }
+            sml_table.push_back(sml);
+        }
     }
     static uint32 GetDefaultMerSize(const std::vector<genome::gnSequence*>& seqs) {
         gnSeqI total = 0;
@@ -170,6 +268,34 @@ inline void WriteList(const MatchList& ml, std::ostream& os) {
     }
     os << "MatchCount\t" << ml.size() << "\n";
     for (const Match* m : ml) os << *m << "\n";
+}
+
+/* ReadList: the inverse of WriteList (match lines only; the header's file names refill seq_filename).  Used for the
+ * --match-input hand-off (src/mauveAligner.cpp:489-503). */
+inline void ReadList(MatchList& ml, std::istream& is) {
+    std::string key;
+    size_t nseq = 0, nmatch = 0;
+    for (Match* m : ml) m->Free();
+    ml.clear();
+    ml.seq_filename.clear();
+    if (!(is >> key) || key != "FormatVersion") throw genome::gnException("ReadList: not a match list");
+    int version; is >> version;
+    is >> key >> nseq;
+    for (size_t i = 0; i < nseq; ++i) {
+        std::string line;
+        is >> key; std::getline(is, line);
+        ml.seq_filename.push_back(line.size() > 1 ? line.substr(1) : std::string());
+        gnSeqI len; is >> key >> len;
+    }
+    is >> key >> nmatch;
+    for (size_t k = 0; k < nmatch; ++k) {
+        gnSeqI len; is >> len;
+        Match* m = new Match((uint)nseq);
+        m->SetLength(len);
+        for (size_t i = 0; i < nseq; ++i) { int64 st; is >> st; m->SetStart((uint)i, st); }
+        if (!is) { m->Free(); throw genome::gnException("ReadList: truncated match list"); }
+        ml.push_back(m);
+    }
 }
 
 /* mems::MatchFinder — holds the device context and the sequences added so far. */

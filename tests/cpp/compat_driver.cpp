@@ -19,16 +19,47 @@ static string read_seq(const char* path) {
 }
 
 int main(int argc, char** argv) {
-    if (argc < 5) { cerr << "usage: compat_driver <umf|sme|count> <weight> <rank> <seq files...>\n"; return -1; }
+    if (argc < 3) { cerr << "usage: compat_driver <umf|pmf|sme|count|sml> <weight> <rank> <seq files...> | smlcount <file.sslist> | readlist <file>\n"; return -1; }
     string what = argv[1];
+    if (what == "smlcount") {
+        // src/uniqueMerCount.cpp:29-39, line for line
+        DNAFileSML file_sml;
+        try { file_sml.LoadFile(argv[2]); }
+        catch (gnException& gne) { cerr << gne.what() << endl; return -2; }
+        cout << endl << file_sml.UniqueMerCount() << endl;
+        for (uint32_t p : file_sml.Positions()) cout << p << "\n";
+        return 0;
+    }
+    if (what == "readlist") {
+        MatchList in;
+        ifstream f(argv[2]);
+        ReadList(in, f);
+        for (const string& n : in.seq_filename) in.seq_table.push_back(new gnSequence(read_seq(n.c_str())));
+        WriteList(in, cout);
+        return 0;
+    }
+    if (argc < 5) return -1;
     int weight = atoi(argv[2]), rank = atoi(argv[3]);
     MatchList ml;
     for (int i = 4; i < argc; ++i) {
         ml.seq_filename.push_back(argv[i]);
         ml.seq_table.push_back(new gnSequence(read_seq(argv[i])));
     }
+    if (what == "sml") {
+        // LoadSMLs with on-disk sorted mer lists (src/mauveAligner.cpp:450-456): <seq>.sslist next to every sequence
+        for (int i = 4; i < argc; ++i) ml.sml_filename.push_back(string(argv[i]) + ".sslist");
+        ml.LoadSMLs(weight, &cerr, rank);
+        ml.LoadSMLs(weight, &cerr, rank); // second call must find the files and not rebuild
+        cout << endl << ml.sml_table[0]->UniqueMerCount() << endl;
+        return 0;
+    }
     ml.CreateMemorySMLs(weight, nullptr, rank);
-    if (what == "umf") {
+    if (what == "pmf") {
+        PairwiseMatchFinder pmf;
+        if (!pmf.FindMatches(ml)) return -2;
+        pmf.Clear();
+        WriteList(ml, cout);
+    } else if (what == "umf") {
         UniqueMatchFinder umf;
         umf.LogProgress(nullptr);
         if (!umf.FindMatches(ml)) return -2;

@@ -263,3 +263,24 @@ def test_cpp_host_api_matches_oracle(tmp_path):
     assert parse(out) == [[ln] + [s for _, s in comps] for ln, comps in O.matches_as_list(want)]
     out = subprocess.check_output([str(exe), "count", "9", "0", files[0]], text=True)
     assert int(out.split()[-1]) == O.find(seqs[:1], mb.get_seed(9, 0), O.MODE_UNIQUE_COUNT)["unique_mers"]
+    # PairwiseMatchFinder
+    out = subprocess.check_output([str(exe), "pmf", "11", "0"] + files, text=True)
+    want = O.find(seqs, mb.get_seed(11, 0), O.MODE_PAIRWISE)
+    rows = []
+    for ln, comps in O.matches_as_list(want):
+        d = dict(comps)
+        rows.append([ln] + [d.get(g, 0) for g in range(3)])
+    assert parse(out) == rows and len(rows) > 10
+    # .sslist files: LoadSMLs creates them (second call loads), DNAFileSML::LoadFile + UniqueMerCount reads them back
+    res = subprocess.run([str(exe), "sml", "11", "0"] + files, text=True, capture_output=True, check=True)
+    assert res.stderr.count("Creating sorted mer list") == 3
+    uniq = O.find(seqs[:1], mb.get_seed(11, 0), O.MODE_UNIQUE_COUNT)["unique_mers"]
+    assert int(res.stdout.split()[-1]) == uniq
+    out = subprocess.check_output([str(exe), "smlcount", files[0] + ".sslist"], text=True).split()
+    assert int(out[0]) == uniq
+    assert [int(x) for x in out[1:]] == O.sml(seqs[0], mb.get_seed(11, 0)).tolist()
+    # WriteList -> ReadList -> WriteList round trip
+    first = subprocess.check_output([str(exe), "umf", "11", "0"] + files, text=True)
+    lst = tmp_path / "matches.mums"
+    lst.write_text(first)
+    assert subprocess.check_output([str(exe), "readlist", str(lst)], text=True) == first
