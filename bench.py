@@ -223,11 +223,17 @@ def main():
     n_seeds = st["n_seeds"]
     alg_bytes_per_launch = 2.0 * R * n_seeds
     roofline = None
+    traffic = None  # DRAM bytes per launch of the same kernel from the committed ncu --set full capture (same workload only)
+    try:
+        if config == 2 and args.scale == 1:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_full_c2.json")))["k_onesweep_traffic_bytes_per_launch"]
+    except Exception:
+        traffic = None
     if radix_launches:
         avg_ms = radix_ms / radix_launches
         achieved = alg_bytes_per_launch / (avg_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": "k_onesweep (one LSD radix pass over all seed records)", "achieved": achieved, "peak": peak,
-                    "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg_bytes_per_launch, "avg_launch_ms": avg_ms, "launches_per_step": radix_launches,
                     "share_of_step": radix_ms / st["ms_total_device"] if st["ms_total_device"] else None}
     # whole-path figure of SURVEY.md §8d: B_alg = 0.25 + R (3 + 2P) bytes per input base
