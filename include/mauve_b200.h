@@ -118,31 +118,55 @@ int mb_fetch_result(mb_ctx* ctx, const mb_result** out);
 
 /* ---- multi-GPU path ---------------------------------------------
  * One context per rank / GPU, the same sequences added to every context (replicated genomes).
- * The library runs the per-rank stages and owns the exchange buffers; the three exchanges (variable
- * all-to-alls of uint64 words, NCCL over NVLink) are the caller's, between the stages
- * (mauvealigner_b200/dist.py drives them over torch.distributed).  MB_MODE_UNIQUE, 8-byte records.
- * Stands in for the same reference calls as mb_find (the reference is single-process).
- *   1 mb_dist_extract      -> *d_send: this rank's seed records grouped by destination rank,
- *                             h_counts[world] records per destination               (exchange 1)
+ * The library runs the per-rank stages and owns the exchange buffers; the exchanges between the stages are
+ * either the caller's (variable all-to-alls over NCCL/NVLink; mauvealigner_b200/dist.py drives them over
+ * torch.distributed) or, for exchange 1, fused into the partition kernel as NVLink peer stores.
+ * MB_MODE_UNIQUE, 8-byte records.  Stands in for the same reference calls as mb_find (the reference is
+ * single-process).
+ *   1 mb_dist_extract      -> *d_send: this rank's seed records grouped by destination rank (= seed-key range),
+ *                             h_counts[world] records per destination               (exchange 1: 1 word / record)
+ *     or mb_dist_extract_count + mb_dist_partition(peer arrays): the same, with the exchange fused into the kernel
  *   2 mb_dist_recv_buffer(0, n) is where exchange 1 must deliver (source-rank order);
- *     mb_dist_local        -> candidate rows grouped by owner rank: headers (2 words each) at
- *                             *d_hdr, component words at *d_comps, counts per owner (exchange 2)
- *   3 mb_dist_recv_buffer(1 / 2, n) receive the headers / components;
- *     mb_dist_dedup        -> de-dup of the owned groups; *d_hist = 4096 uint64 counts (device) of the
- *                             accepted matches' canonical keys: sum it over all ranks IN PLACE (all-reduce)
+ *     mb_dist_local        -> sort / runs / policy over the key range, EVERY candidate extended at its source;
+ *                             4-word candidate rows (two group hashes, first component, extents) grouped by owner
+ *                             of the de-dup group at *d_rows, h_row_counts[world]     (exchange 2: 4 words / row)
+ *   3 mb_dist_recv_buffer(1, 4 n) receives the rows (source-rank order);
+ *     mb_dist_resolve      -> chains / resolve over the owned groups; *d_verdict = one byte per received row
+ *                             (1 accepted), to go back to the sources in row order    (exchange 2b: 1 byte / row)
+ *     mb_dist_recv_buffer(5, n_bytes) receives this rank's verdicts (the row order of stage 2);
+ *     mb_dist_accept       -> *d_hist = 4096 uint64 counts (device) of the accepted matches' canonical keys:
+ *                             sum it over all ranks IN PLACE (all-reduce)
  *     mb_dist_match_partition -> match rows grouped by destination = range of the canonical order
- *                             (*d_hdr 2 words per row, *d_comps), counts per destination     (exchange 3)
+ *                             (*d_hdr 2 words per row, *d_comps 1 word per component), counts per destination
+ *                                                                                      (exchange 3)
  *   4 mb_dist_recv_buffer(3 / 4, n) receive them; mb_dist_output builds the canonical CSR of this rank's
  *     range, after which mb_fetch_result works as for mb_find_device.  The ranks' pieces, concatenated in
  *     rank order, are the result. */
 int mb_dist_extract(mb_ctx* ctx, int rank, int world, void** d_send, uint64_t* h_counts);
-int mb_dist_recv_buffer(mb_ctx* ctx, int which, uint64_t n_words, void** d_ptr);
-int mb_dist_local(mb_ctx* ctx, const mb_params* params, uint64_t n_recv, uint64_t* h_cand_counts, uint64_t* h_comp_counts,
-                  void** d_hdr, void** d_comps);
-int mb_dist_dedup(mb_ctx* ctx, uint64_t n_cand, uint64_t n_comp, void** d_hist);
+/* Stage 1 in two steps, for the fused exchange: mb_dist_extract_count extracts the slice and counts it per
+ * destination; after the ranks have shared their counts, mb_dist_partition either fills the local send buffer
+ * (peer_bases = NULL, as mb_dist_extract does) or writes every record straight into its destination rank's
+ * receive array over NVLink peer stores (peer_bases[d] = rank d's array mapped into this process, peer_offsets[d] =
+ * record index of this rank's block in it).  All ranks must be synchronised before stage 2 reads the arrays
+ * (mb_dist_use_p2p_recv(ctx, 1) makes mb_dist_local read from the array of mb_dist_p2p_recv_array). */
+int mb_dist_extract_count(mb_ctx* ctx, int rank, int world, uint64_t* h_counts);
+int mb_dist_partition(mb_ctx* ctx, void* const* peer_bases, const uint64_t* peer_offsets, void** d_send);
+int mb_dist_p2p_recv_array(mb_ctx* ctx, uint64_t capacity_records, void** d_ptr);
+int mb_dist_use_p2p_recv(mb_ctx* ctx, int on);
+/* CUDA IPC plumbing for the peer arrays (64-byte handles; cudaIpcGetMemHandle / OpenMemHandle / CloseMemHandle) */
+int mb_ipc_export(mb_ctx* ctx, void* d_ptr, uint8_t* handle64);
+int mb_ipc_import(mb_ctx* ctx, const uint8_t* handle64, void** d_ptr);
+int mb_ipc_close(mb_ctx* ctx, void* d_ptr);
+/* which: 0 seed records, 1 candidate rows, 3 match headers, 4 match components (n = 8-byte words), 5 verdicts (n = bytes) */
+int mb_dist_recv_buffer(mb_ctx* ctx, int which, uint64_t n, void** d_ptr);
+int mb_dist_local(mb_ctx* ctx, const mb_params* params, uint64_t n_recv, uint64_t* h_row_counts, void** d_rows);
+int mb_dist_resolve(mb_ctx* ctx, uint64_t n_rows, void** d_verdict);
+int mb_dist_accept(mb_ctx* ctx, void** d_hist);
 int mb_dist_match_partition(mb_ctx* ctx, uint64_t* h_match_counts, uint64_t* h_comp_counts, void** d_hdr, void** d_comps);
 int mb_dist_output(mb_ctx* ctx, uint64_t n_match, uint64_t n_comp);
-int mb_dist_stage_ms(mb_ctx* ctx, float* out4);
+/* device ms of this rank's stages of the last run: [0] extract+partition, [1] sort, [2] runs/policy/candidates,
+ * [3] extension, [4] chains + resolve; [5..7] reserved (0) */
+int mb_dist_stage_ms(mb_ctx* ctx, float* out8);
 
 /* ---- sorted mer list access (SortedMerList façade; "next" row of SURVEY.md §8f) ---- */
 /* Positions of sequence `seq` sorted by (seed, position): the .sslist position array (a4).

@@ -90,7 +90,7 @@ int mb_ctx_destroy(mb_ctx* c) {
     cudaStreamSynchronize(c->stream);
     DBuf* bufs[] = {&c->packed, &c->ascii_stage, &c->keysA, &c->keysB, &c->valsA, &c->valsB, &c->hist, &c->digit_base, &c->lookback, &c->tickets,
                     &c->status, &c->scalars, &c->per_seq, &c->tile_first, &c->cand_run, &c->cand_off, &c->cand_aux, &c->comp_pos, &c->comp_gs,
-                    &c->bitmap, &c->bmrank, &c->cand_at, &c->cstate, &c->covered, &c->ghash2, &c->rep_cand, &c->s_h2, &c->reach, &c->xstate, &c->xrec, &c->minrank, &c->ext_l, &c->ext_r, &c->wl_a, &c->wl_b, &c->wl_c, &c->wl_long, &c->wd_a, &c->wd_b, &c->wd_c, &c->live_bits, &c->trace, &c->ghash, &c->slot_gp, &c->slot_hash, &c->link_bits, &c->chain_min, &c->rep_bits, &c->rep_rank, &c->s_hash, &c->s_cand, &c->rng_lo, &c->rng_hi, &c->flags,
+                    &c->bitmap, &c->bmrank, &c->cand_at, &c->cstate, &c->covered, &c->ghash2, &c->rep_cand, &c->s_h2, &c->reach, &c->xstate, &c->xrec, &c->x_lut, &c->x_counts, &c->x_hdr_s, &c->x_comp_s, &c->x_hdr_r, &c->x_comp_r, &c->x_m, &c->x_key, &c->x_item, &c->x_peers, &c->x_recv, &c->q_off, &c->q_pos, &c->q_gs, &c->q_el, &c->q_er, &c->q_perm, &c->q_state, &c->q_item, &c->x_acc_s, &c->x_acc_r, &c->minrank, &c->ext_l, &c->ext_r, &c->wl_a, &c->wl_b, &c->wl_c, &c->wl_long, &c->wd_a, &c->wd_b, &c->wd_c, &c->live_bits, &c->trace, &c->ghash, &c->slot_gp, &c->slot_hash, &c->link_bits, &c->chain_min, &c->rep_bits, &c->rep_rank, &c->s_hash, &c->s_cand, &c->rng_lo, &c->rng_hi, &c->flags,
                     &c->match_idx, &c->sort_kA, &c->sort_kB, &c->sort_vA, &c->sort_vB, &c->ncomp, &c->mers_tmp, &c->out_len, &c->out_off,
                     &c->out_seq, &c->out_start};
     for (DBuf* b : bufs) free_buf(*b);
@@ -517,7 +517,9 @@ int mbi_reserve_candidates(mb_ctx* c, u32 n_cand, u32 n_ccomp, u64 bases) {
 
 // a10 + a11: chains -> extension of the chain reps -> resolve (kernels_dedup.cu).  The candidate
 // bitmap must hold one bit per candidate at (first genome, position).
-int mbi_dedup(mb_ctx* c, u32 n_cand, u64 bases) {
+// rows != null (multi-GPU owner side): the candidates are 4-word rows carrying their extents; no component lists,
+// no extension here.
+int mbi_dedup(mb_ctx* c, u32 n_cand, u64 bases, const u64* rows) {
     cudaStream_t st = c->stream;
     u64* scal = c->scalars.as<u64>();
     const u64 bm_words = bases / 64 + 2;
@@ -542,6 +544,7 @@ int mbi_dedup(mb_ctx* c, u32 n_cand, u64 bases) {
     da.wl_long = c->wl_long.as<u32>();
     da.wd0 = c->wd_a.as<u32>(); da.wd1 = c->wd_b.as<u32>(); da.wd2 = c->wd_c.as<u32>();
     da.ctr = reinterpret_cast<u32*>(scal + SC_DDCTR);
+    da.rows = rows;
     // ---- chains: slots, links, reps
     launch_slot_scatter(da, c->gt, st); LAUNCHED(c);
     {
@@ -565,8 +568,14 @@ int mbi_dedup(mb_ctx* c, u32 n_cand, u64 bases) {
     da.s_key = skA;
     cudaEventRecord(c->ev_x[0], st);
     // ---- extend every rep, then resolve
-    launch_extend(da, c->gt, c->sd, st);
-    if (n_rep) c->stats.kernel_launches += extend_launches();
+    if (rows) {
+        launch_rep_setup(da, st);
+        launch_extent_ranges(da, c->gt, st);
+        if (n_rep) c->stats.kernel_launches += 2;
+    } else {
+        launch_extend(da, c->gt, c->sd, st);
+        if (n_rep) c->stats.kernel_launches += extend_launches();
+    }
     CHECK_LAUNCH(c);
     cudaEventRecord(c->ev_x[3], st);
     const bool want_trace = getenv("MB_DEDUP_TRACE") != nullptr;

@@ -41,8 +41,12 @@ struct mb_ctx {
     DBuf cand_run, cand_off, cand_aux, comp_pos, comp_gs, bitmap, bmrank, cand_at, cstate, covered, minrank, ext_l, ext_r;
     DBuf trace, ghash2, rep_cand, s_h2, reach, xstate, xrec;
     u32 n_rep = 0;
-    DBuf x_lut, x_counts, x_hdr_s, x_comp_s, x_hdr_r, x_comp_r, x_m, x_key, x_item; // multi-GPU exchange buffers (api_dist.cu)
+    DBuf x_lut, x_counts, x_hdr_s, x_comp_s, x_hdr_r, x_comp_r, x_m, x_key, x_item, x_peers, x_recv; // multi-GPU exchange buffers (api_dist.cu)
+    // source-side candidate arrays of the distributed path: they must outlive the owner stage that runs in between
+    DBuf q_off, q_pos, q_gs, q_el, q_er, q_perm, q_state, q_item, x_acc_s, x_acc_r;
     int d_rank = 0, d_world = 1;
+    u32 d_nslice = 0;
+    bool d_use_p2p = false;
     u32 d_ncand = 0, d_nccomp = 0, d_nmatch = 0, d_nmcomp = 0;
     u64 d_bases = 0, d_maxlen = 0;
     cudaEvent_t ev_d[8] = {nullptr};
@@ -117,5 +121,5 @@ int mbi_read_scalars(mb_ctx* c);
 int mbi_bits_for(u64 maxval);
 // stages of the MODE_UNIQUE tail, shared by the single-GPU and the distributed drivers
 int mbi_reserve_candidates(mb_ctx* c, u32 n_cand, u32 n_ccomp, u64 bases);
-int mbi_dedup(mb_ctx* c, u32 n_cand, u64 bases);
+int mbi_dedup(mb_ctx* c, u32 n_cand, u64 bases, const u64* rows = nullptr);
 int mbi_output_unique(mb_ctx* c, u32 n_cand, u64 maxlen);

@@ -23,9 +23,10 @@ size_t radix_smem_bytes(bool has_val);
 u32 radix_tile_size();
 void launch_scan_hist(const u32* d_hist, u32* d_base, int npass, cudaStream_t st);
 // lut (optional, device, 256 bytes): the bin of a record is lut[digit] instead of the digit itself (monotone
-// key-range partition of the multi-GPU path)
+// key-range partition of the multi-GPU path); peers (optional, device, 256 pointers): bin b is written to peers[b],
+// which may be another GPU's memory — digit_base[b] is then the index of this rank's block inside that array
 cudaError_t launch_onesweep(const u64* kin, u64* kout, const u64* vin, u64* vout, u32 n, const u32* d_digit_base, u64* d_lookback,
-                            u32* d_ticket, int shift, int bits, cudaStream_t st, const u8* lut = nullptr);
+                            u32* d_ticket, int shift, int bits, cudaStream_t st, const u8* lut = nullptr, u64* const* peers = nullptr);
 
 // ---- kernels_bucket.cu
 u32 find_runs_tile();
@@ -100,13 +101,22 @@ struct DedupArgs {
     // and their counters (layout: see k_resolve)
     u32* wl0; u32* wl1; u32* wl2; u32* wd0; u32* wd1; u32* wd2; u32* wl_long; u32* ctr;
     u64* trace;         // optional phase trace (debug): [0] count, then (tag, ns) pairs
+    // multi-GPU owner side: the candidates arrive as 4-word rows (kernels_dist.cu) with their extents already
+    // known and without component lists; null on the single-GPU path
+    const u64* rows;
 };
 void launch_slot_scatter(const DedupArgs& a, const GenomeTable& gt, cudaStream_t st);
 u32 chain_tile();
 void launch_chains(const DedupArgs& a, u64* status_fwd, u32* ticket_fwd, u64* status_bwd, u32* ticket_bwd, cudaStream_t st);
 void launch_rep_keys(const DedupArgs& a, u64* skey, cudaStream_t st);
 int extend_launches();
-void launch_extend(const DedupArgs& a, const GenomeTable& gt, const SeedDev& sd, cudaStream_t st);
+// setup: gather the per-rep records first (k_rep_setup); false when a.xrec is already filled (launch_cand_xrec)
+void launch_extend(const DedupArgs& a, const GenomeTable& gt, const SeedDev& sd, cudaStream_t st, bool setup = true);
+void launch_rep_setup(const DedupArgs& a, cudaStream_t st);
+// multi-GPU source side: every candidate is its own "rep" (a.n_rep = a.n_cand, extension records straight from the CSR)
+void launch_cand_xrec(const DedupArgs& a, const GenomeTable& gt, cudaStream_t st);
+// multi-GPU owner side: slot ranges of the reps' extents from the extents that came with the rows
+void launch_extent_ranges(const DedupArgs& a, const GenomeTable& gt, cudaStream_t st);
 cudaError_t launch_resolve(const DedupArgs& a, cudaStream_t st); // cooperative
 
 // ---- kernels_output.cu
@@ -145,6 +155,13 @@ void launch_unpack_match(const u64* hdr, const u64* comps, const u32* cand_off, 
                          u8* state, u32* item_cand, cudaStream_t st);
 void launch_match_keys(const u8* state, const u32* item_cand, const u32* match_idx, const u32* cand_off, const u8* comp_gs, const u32* comp_pos,
                        const u32* ext_l, u32 n_items, int sbits, int binshift, u64* key, u32* item_of, u64* hist, cudaStream_t st);
+// 4-word candidate rows of the extend-at-source protocol: [group hash, second hash, g0 | vg << 8 | m << 24 | p0 << 32,
+// ext_l | ext_r << 32], written in partition (owner) order; perm_out[j] = candidate of row j
+void launch_pack_rows(const u64* perm, u32 n, const u64* ghash, const u64* ghash2, const u32* cand_off, const u32* comp_pos, const u8* comp_gs,
+                      const GenomeTable& gt, const u32* ext_l, const u32* ext_r, u64* rows, u32* perm_out, cudaStream_t st);
+void launch_rows_bitmap(const u64* rows, u32 n, const GenomeTable& gt, u64* bitmap, cudaStream_t st);
+void launch_accept_mark(const u8* rstate, const u32* s_cand, u32 n_rep, u8* acc, cudaStream_t st);
+void launch_apply_accept(const u8* acc, const u32* perm, u32 n, u8* state, u32* item_cand, cudaStream_t st);
 void launch_dest_keys(const u64* key, u32 n, int binshift, const u8* lut, u64* skey, u64* sval, cudaStream_t st);
 void launch_match_perm_m(const u64* perm, const u32* item_of, const u32* item_cand, const u32* cand_off, u32 n, u32* m_out, cudaStream_t st);
 void launch_pack_match_perm(const u64* perm, const u32* item_of, const u32* item_cand, const u64* poff, const u32* cand_off, const u32* comp_pos,

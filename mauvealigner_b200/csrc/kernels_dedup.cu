@@ -72,9 +72,19 @@ __device__ __forceinline__ bool groups_equal(const DedupArgs& a, u32 c1, u32 c2)
 __global__ void __launch_bounds__(256) k_slot_scatter(DedupArgs a, GenomeTable gt) {
     u32 c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= a.n_cand) return;
-    u32 off = a.cand_off[c], m = a.cand_off[c + 1] - off;
-    u32 g = a.comp_gs[off] & 0x7F, p = a.comp_pos[off];
-    const u32 vg = vgenome(gt, g, a.comp_gs[off + 1] & 0x7F); // a candidate has >= 2 components
+    u32 off, m, g, p, vg;
+    u64 h1, h2;
+    if (a.rows) { // multi-GPU owner: the row carries what the CSR would tell
+        const ulonglong2 r0 = reinterpret_cast<const ulonglong2*>(a.rows)[2 * (size_t)c], r1 = reinterpret_cast<const ulonglong2*>(a.rows)[2 * (size_t)c + 1];
+        h1 = r0.x; h2 = r0.y;
+        g = (u32)r1.x & 0xFFu; vg = (u32)(r1.x >> 8) & 0xFFFFu; m = (u32)(r1.x >> 24) & 0xFFu; p = (u32)(r1.x >> 32);
+        off = 0;
+    } else {
+        off = a.cand_off[c]; m = a.cand_off[c + 1] - off;
+        g = a.comp_gs[off] & 0x7F; p = a.comp_pos[off];
+        vg = vgenome(gt, g, a.comp_gs[off + 1] & 0x7F); // a candidate has >= 2 components
+        h1 = a.ghash[c]; h2 = a.ghash2[c];
+    }
     u64 gp = gt.vbase[vg] + p;
     u64 w = a.bitmap[gp >> 6];
     u32 s = a.bmrank[gp >> 6] + (u32)__popcll(w & ((1ull << (gp & 63)) - 1));
@@ -82,8 +92,8 @@ __global__ void __launch_bounds__(256) k_slot_scatter(DedupArgs a, GenomeTable g
     // whenever it holds a candidate
     u64 adj = 0;
     if (gp > 0) adj = (gp & 63) ? (w >> ((gp & 63) - 1)) & 1 : (a.bitmap[(gp >> 6) - 1] >> 63) & 1;
-    a.slot_rec[2 * (size_t)s] = make_ulonglong2((a.ghash[c] & HASH_MASK) | adj, (u64)c | ((u64)m << 32) | ((u64)g << 40) | ((u64)vg << 48));
-    a.slot_rec[2 * (size_t)s + 1] = make_ulonglong2(a.ghash2[c], (u64)off | ((u64)p << 32));
+    a.slot_rec[2 * (size_t)s] = make_ulonglong2((h1 & HASH_MASK) | adj, (u64)c | ((u64)m << 32) | ((u64)g << 40) | ((u64)vg << 48));
+    a.slot_rec[2 * (size_t)s + 1] = make_ulonglong2(h2, (u64)off | ((u64)p << 32));
 }
 
 // ---- chains: segmented min-scans over the slots ---------------------------------------------------
@@ -536,6 +546,28 @@ __global__ void __launch_bounds__(256) k_rep_setup(DedupArgs a) {
     a.xrec[i] = make_uint4(c, (u32)q.y, m | (g0 << 8) | (vg << 16), (u32)(q.y >> 32));
 }
 
+// multi-GPU source side: extension record of every candidate, straight from the CSR (rep index = candidate)
+__global__ void __launch_bounds__(256) k_cand_xrec(DedupArgs a, GenomeTable gt) {
+    const u32 c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= a.n_cand) return;
+    const u32 off = a.cand_off[c], m = a.cand_off[c + 1] - off;
+    const u32 g0 = a.comp_gs[off] & 0x7F;
+    const u32 vg = vgenome(gt, g0, a.comp_gs[off + 1] & 0x7F);
+    a.xrec[c] = make_uint4(c, off, m | (g0 << 8) | (vg << 16), a.comp_pos[off]);
+}
+// multi-GPU owner side: the extents came with the rows; only the slot ranges are left to derive
+__global__ void __launch_bounds__(256) k_extent_ranges(DedupArgs a, GenomeTable gt) {
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n_rep) return;
+    const uint4 q = a.xrec[i];
+    const u64 e = a.rows[4 * (size_t)q.x + 3];
+    const u32 el = (u32)e, er = (u32)(e >> 32);
+    a.ext_l[q.x] = el; a.ext_r[q.x] = er;
+    u32 rlo, rhi;
+    extent_slots(a, gt.vbase[q.z >> 16] + q.w, el, er, rlo, rhi);
+    a.rng_lo[i] = rlo; a.rng_hi[i] = rhi;
+}
+
 // ---- extend: a warp takes 32 reps.  Lane j owns rep j's state; the (rep, component) pairs of the warp
 // are spread over all lanes, so every lane builds exactly one component-vs-first mismatch map per step
 // whatever the multiplicities are; maps are OR-ed per rep in shared memory.  Rounds: centred chunk, then
@@ -643,9 +675,11 @@ __device__ __forceinline__ void extend_finish(const DedupArgs& a, const GenomeTa
     const bool more = valid && x.st != ST_DONE;
     if (valid && !more) {
         a.ext_l[x.c] = x.el; a.ext_r[x.c] = x.er;
-        u32 rlo, rhi;
-        extent_slots(a, gt.vbase[x.vg] + x.p0, x.el, x.er, rlo, rhi);
-        a.rng_lo[i] = rlo; a.rng_hi[i] = rhi;
+        if (a.bitmap) { // (the multi-GPU source side extends without the slot axis: the owner derives the ranges)
+            u32 rlo, rhi;
+            extent_slots(a, gt.vbase[x.vg] + x.p0, x.el, x.er, rlo, rhi);
+            a.rng_lo[i] = rlo; a.rng_hi[i] = rhi;
+        }
     }
     if (more && !last) {
         a.xstate[i] = make_uint4((u32)x.st | (x.rj ? 4u : 0u), x.b, x.room_l, x.room_r);
@@ -708,7 +742,7 @@ __global__ void __launch_bounds__(DD_NT) k_extend_long(DedupArgs a, GenomeTable 
     const u32 n = a.ctr[6];
     for (u32 t = gwarp; t < n; t += nwarps) {
         u32 i = a.wl_long[t];
-        u32 c = (u32)a.s_rec[i].y;
+        u32 c = a.xrec[i].x;
         u32 off = a.cand_off[c], m = a.cand_off[c + 1] - off;
         const u32* cpos = a.comp_pos + off;
         const u8* cgs = a.comp_gs + off;
@@ -724,9 +758,11 @@ __global__ void __launch_bounds__(DD_NT) k_extend_long(DedupArgs a, GenomeTable 
         }
         if (lane == 0) {
             a.ext_l[c] = el; a.ext_r[c] = er;
-            u32 rlo, rhi;
-            extent_slots(a, gt.vbase[vgenome(gt, cgs[0] & 0x7F, cgs[1] & 0x7F)] + cpos[0], el, er, rlo, rhi);
-            a.rng_lo[i] = rlo; a.rng_hi[i] = rhi;
+            if (a.bitmap) {
+                u32 rlo, rhi;
+                extent_slots(a, gt.vbase[vgenome(gt, cgs[0] & 0x7F, cgs[1] & 0x7F)] + cpos[0], el, er, rlo, rhi);
+                a.rng_lo[i] = rlo; a.rng_hi[i] = rhi;
+            }
         }
     }
 }
@@ -892,11 +928,20 @@ void launch_rep_keys(const DedupArgs& a, u64* skey, cudaStream_t st) {
 // wd0 / wd1 with counters ctr[12] / ctr[13]), then the warp-per-rep kernel for what is left
 #define DD_EXT_MORE 3
 int extend_launches() { return 3 + DD_EXT_MORE; }
-void launch_extend(const DedupArgs& a, const GenomeTable& gt, const SeedDev& sd, cudaStream_t st) {
+void launch_rep_setup(const DedupArgs& a, cudaStream_t st) {
+    if (a.n_rep) k_rep_setup<<<div_up(a.n_rep, 256), 256, 0, st>>>(a);
+}
+void launch_cand_xrec(const DedupArgs& a, const GenomeTable& gt, cudaStream_t st) {
+    if (a.n_cand) k_cand_xrec<<<div_up(a.n_cand, 256), 256, 0, st>>>(a, gt);
+}
+void launch_extent_ranges(const DedupArgs& a, const GenomeTable& gt, cudaStream_t st) {
+    if (a.n_rep) k_extent_ranges<<<div_up(a.n_rep, 256), 256, 0, st>>>(a, gt);
+}
+void launch_extend(const DedupArgs& a, const GenomeTable& gt, const SeedDev& sd, cudaStream_t st, bool setup) {
     if (a.n_rep == 0) return;
     u32* list[2] = {a.wd0, a.wd1};
     u32* cnt[2] = {a.ctr + 12, a.ctr + 13};
-    k_rep_setup<<<div_up(a.n_rep, 256), 256, 0, st>>>(a);
+    if (setup) k_rep_setup<<<div_up(a.n_rep, 256), 256, 0, st>>>(a);
     k_extend<<<div_up(a.n_rep, DD_NT), DD_NT, 0, st>>>(a, gt, sd, list[0], cnt[0]);
     for (int r = 0; r < DD_EXT_MORE; ++r) {
         int in = r & 1, out = in ^ 1;

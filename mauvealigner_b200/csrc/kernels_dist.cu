@@ -160,6 +160,61 @@ void launch_unpack_match(const u64* hdr, const u64* comps, const u32* cand_off, 
     if (n) k_unpack_match<<<div_up(n, 256), 256, 0, st>>>(hdr, comps, cand_off, n, comp_pos, comp_gs, ext_l, ext_r, state, item_cand);
 }
 
+// ---- extend-at-source protocol: 4-word candidate rows (the extents travel, the component lists stay at the source)
+__global__ void __launch_bounds__(256) k_pack_rows(const u64* __restrict__ perm, u32 n, const u64* __restrict__ ghash, const u64* __restrict__ ghash2,
+                                                   const u32* __restrict__ cand_off, const u32* __restrict__ comp_pos, const u8* __restrict__ comp_gs,
+                                                   GenomeTable gt, const u32* __restrict__ ext_l, const u32* __restrict__ ext_r,
+                                                   ulonglong2* __restrict__ rows, u32* __restrict__ perm_out) {
+    u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const u32 c = (u32)perm[j];
+    const u32 off = cand_off[c], m = cand_off[c + 1] - off;
+    const u32 g0 = comp_gs[off] & 0x7F;
+    const u32 vg = vgenome(gt, g0, comp_gs[off + 1] & 0x7F);
+    rows[2 * (size_t)j] = make_ulonglong2(ghash[c], ghash2[c]);
+    rows[2 * (size_t)j + 1] = make_ulonglong2((u64)g0 | ((u64)vg << 8) | ((u64)m << 24) | ((u64)comp_pos[off] << 32), (u64)ext_l[c] | ((u64)ext_r[c] << 32));
+    perm_out[j] = c;
+}
+void launch_pack_rows(const u64* perm, u32 n, const u64* ghash, const u64* ghash2, const u32* cand_off, const u32* comp_pos, const u8* comp_gs,
+                      const GenomeTable& gt, const u32* ext_l, const u32* ext_r, u64* rows, u32* perm_out, cudaStream_t st) {
+    if (n) k_pack_rows<<<div_up(n, 256), 256, 0, st>>>(perm, n, ghash, ghash2, cand_off, comp_pos, comp_gs, gt, ext_l, ext_r,
+                                                      reinterpret_cast<ulonglong2*>(rows), perm_out);
+}
+
+// owner: one bit per received candidate at (virtual genome, position) — the slot axis of the chains
+__global__ void __launch_bounds__(256) k_rows_bitmap(const u64* __restrict__ rows, u32 n, GenomeTable gt, u64* __restrict__ bitmap) {
+    u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const u64 w = rows[4 * (size_t)j + 2];
+    const u64 gp = gt.vbase[(u32)(w >> 8) & 0xFFFFu] + (u32)(w >> 32);
+    atomicOr((unsigned long long*)&bitmap[gp >> 6], 1ull << (gp & 63));
+}
+void launch_rows_bitmap(const u64* rows, u32 n, const GenomeTable& gt, u64* bitmap, cudaStream_t st) {
+    if (n) k_rows_bitmap<<<div_up(n, 256), 256, 0, st>>>(rows, n, gt, bitmap);
+}
+
+// owner: acc[row] = 1 for every accepted rep (acc zeroed before)
+__global__ void __launch_bounds__(256) k_accept_mark(const u8* __restrict__ rstate, const u32* __restrict__ s_cand, u32 n_rep, u8* __restrict__ acc) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_rep && (rstate[i] & 15u) == 1u) acc[s_cand[i]] = 1;
+}
+void launch_accept_mark(const u8* rstate, const u32* s_cand, u32 n_rep, u8* acc, cudaStream_t st) {
+    if (n_rep) k_accept_mark<<<div_up(n_rep, 256), 256, 0, st>>>(rstate, s_cand, n_rep, acc);
+}
+
+// source: verdicts come back in row order; candidate c = perm[row]
+__global__ void __launch_bounds__(256) k_apply_accept(const u8* __restrict__ acc, const u32* __restrict__ perm, u32 n, u8* __restrict__ state,
+                                                      u32* __restrict__ item_cand) {
+    u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const u32 c = perm[j];
+    state[c] = acc[j] ? 1 : 2;
+    item_cand[c] = c;
+}
+void launch_apply_accept(const u8* acc, const u32* perm, u32 n, u8* state, u32* item_cand, cudaStream_t st) {
+    if (n) k_apply_accept<<<div_up(n, 256), 256, 0, st>>>(acc, perm, n, state, item_cand);
+}
+
 // ---- distributed output: canonical key of every accepted match, and its key histogram (top 12 key bits)
 __global__ void __launch_bounds__(256) k_match_keys(const u8* __restrict__ state, const u32* __restrict__ item_cand, const u32* __restrict__ match_idx,
                                                     const u32* __restrict__ cand_off, const u8* __restrict__ comp_gs, const u32* __restrict__ comp_pos,

@@ -44,7 +44,8 @@ template <bool HAS_VAL, bool USE_LUT>
 __global__ void __launch_bounds__(RS_NT, RS_MINB) k_onesweep(const u64* __restrict__ kin, u64* __restrict__ kout,
                                                     const u64* __restrict__ vin, u64* __restrict__ vout, u32 n,
                                                     const u32* __restrict__ digit_base /*[256] exclusive*/,
-                                                    u64* lookback /*[tiles][256]*/, u32* ticket, int shift, u32 dmask, const u8* __restrict__ lut) {
+                                                    u64* lookback /*[tiles][256]*/, u32* ticket, int shift, u32 dmask, const u8* __restrict__ lut,
+                                                    u64* const* __restrict__ peers /*[256] or null: output array of every bin */) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u64* sKeys = reinterpret_cast<u64*>(smem_raw);                    // RS_TILE
     u64* sVals = sKeys + RS_TILE;                                      // RS_TILE when HAS_VAL
@@ -54,10 +55,11 @@ __global__ void __launch_bounds__(RS_NT, RS_MINB) k_onesweep(const u64* __restri
     __shared__ u32 sTile;
     __shared__ u32 sWarpSums[8];
     __shared__ u8 sLut[256];
+    __shared__ u64* sPeer[USE_LUT ? 256 : 1];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) sTile = atomicAdd(ticket, 1u);
-    if (USE_LUT && tid < 256) sLut[tid] = lut[tid];
+    if (USE_LUT && tid < 256) { sLut[tid] = lut[tid]; sPeer[tid] = peers ? peers[tid] : kout; }
     for (int i = tid; i < RS_NW * 256; i += RS_NT) sWarpHist[i] = 0;
     __syncthreads();
     const u32 tile = sTile;
@@ -184,7 +186,8 @@ __global__ void __launch_bounds__(RS_NT, RS_MINB) k_onesweep(const u64* __restri
         u64 kk = sKeys[s];
         u32 d = DIGIT(kk);
         u32 dst = sGlobBase[d] + s; // n < 2^31: 32-bit wrap-around arithmetic is exact
-        kout[dst] = kk;
+        if (USE_LUT) sPeer[d][dst] = kk; // the bins may live in other GPUs' memory (NVLink peer stores)
+        else kout[dst] = kk;
         if (HAS_VAL) vout[dst] = sVals[s];
     }
 }
@@ -217,7 +220,7 @@ void launch_scan_hist(const u32* d_hist, u32* d_base, int npass, cudaStream_t st
 static bool g_attr_set[3] = {false, false, false};
 
 cudaError_t launch_onesweep(const u64* kin, u64* kout, const u64* vin, u64* vout, u32 n, const u32* d_digit_base,
-                            u64* d_lookback, u32* d_ticket, int shift, int bits, cudaStream_t st, const u8* lut) {
+                            u64* d_lookback, u32* d_ticket, int shift, int bits, cudaStream_t st, const u8* lut, u64* const* peers) {
     if (n == 0) return cudaSuccess;
     bool hv = vin != nullptr;
     if (lut && hv) return cudaErrorInvalidValue;
@@ -232,8 +235,8 @@ cudaError_t launch_onesweep(const u64* kin, u64* kout, const u64* vin, u64* vout
     }
     u32 tiles = div_up(n, RS_TILE);
     u32 dmask = (1u << bits) - 1;
-    if (variant == 2) k_onesweep<false, true><<<tiles, RS_NT, smem, st>>>(kin, kout, vin, vout, n, d_digit_base, d_lookback, d_ticket, shift, dmask, lut);
-    else if (variant == 1) k_onesweep<true, false><<<tiles, RS_NT, smem, st>>>(kin, kout, vin, vout, n, d_digit_base, d_lookback, d_ticket, shift, dmask, lut);
-    else k_onesweep<false, false><<<tiles, RS_NT, smem, st>>>(kin, kout, vin, vout, n, d_digit_base, d_lookback, d_ticket, shift, dmask, lut);
+    if (variant == 2) k_onesweep<false, true><<<tiles, RS_NT, smem, st>>>(kin, kout, vin, vout, n, d_digit_base, d_lookback, d_ticket, shift, dmask, lut, peers);
+    else if (variant == 1) k_onesweep<true, false><<<tiles, RS_NT, smem, st>>>(kin, kout, vin, vout, n, d_digit_base, d_lookback, d_ticket, shift, dmask, lut, peers);
+    else k_onesweep<false, false><<<tiles, RS_NT, smem, st>>>(kin, kout, vin, vout, n, d_digit_base, d_lookback, d_ticket, shift, dmask, lut, peers);
     return cudaGetLastError();
 }

@@ -31,6 +31,17 @@ class _DevWords:
         self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<i8", "data": (int(ptr), False), "version": 2}
 
 
+class _DevBytes:
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+def dev_bytes(ptr, n, device):
+    if n == 0 or not ptr:
+        return torch.empty(0, dtype=torch.uint8, device=device)
+    return torch.as_tensor(_DevBytes(ptr, n), device=device)
+
+
 def dev_words(ptr, n, device):
     if n == 0 or not ptr:
         return torch.empty(0, dtype=torch.int64, device=device)
@@ -48,6 +59,23 @@ class LocalFabric:
         # k numbers per destination: send_counts[src][dst*k:(dst+1)*k] -> recv_counts[dst][src*k:(src+1)*k]
         k = len(send_counts[0]) // self.world
         return [[x for s in range(self.world) for x in send_counts[s][d * k:(d + 1) * k]] for d in range(self.world)]
+
+    def gather_counts(self, send_counts):
+        # the whole count matrix M[src][dst], the same on every rank
+        return [list(c) for c in send_counts]
+
+    def barrier(self):
+        pass  # one process, one stream
+
+    def peer_arrays(self, ctxs, capacity):
+        """Every rank's fixed receive array for the fused exchange #1, addressable from every rank: here plain pointers."""
+        if getattr(self, "_p2p_cap", -1) < capacity:
+            self._p2p_ptrs = [c.dist_p2p_recv_array(capacity) for c in ctxs]
+            self._p2p_cap = capacity
+        return [self._p2p_ptrs for _ in ctxs]
+
+    def release_peer_arrays(self, ctxs):
+        self._p2p_cap = -1
 
     def allreduce_sum(self, tensors):
         total = tensors[0].clone()
@@ -86,6 +114,45 @@ class TorchFabric:
         self.dist.all_to_all_single(out, t, [k] * self.world, [k] * self.world, group=self.group)
         return [out.tolist()]
 
+    def gather_counts(self, send_counts):
+        t = torch.tensor(send_counts[0], dtype=torch.int64, device=self.device)
+        out = [torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(out, t, group=self.group)
+        return torch.stack(out).tolist()
+
+    def barrier(self):
+        # stream-ordered: completes on this rank only after every rank's earlier work on its stream (the peer stores
+        # of its partition kernel) has completed
+        if not hasattr(self, "_token"):
+            self._token = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self.dist.all_reduce(self._token, group=self.group)
+
+    def peer_arrays(self, ctxs, capacity):
+        """Every rank's fixed receive array for the fused exchange #1, mapped into this process through CUDA IPC
+        (NVLink peer access).  Collective; re-done only when the capacity grows."""
+        if getattr(self, "_p2p_cap", -1) >= capacity:
+            return [self._p2p_ptrs]
+        self.release_peer_arrays(ctxs)
+        c = ctxs[0]
+        mine = c.dist_p2p_recv_array(capacity)
+        h = torch.frombuffer(bytearray(c.ipc_export(mine)), dtype=torch.uint8).to(self.device)
+        out = [torch.empty_like(h) for _ in range(self.world)]
+        self.dist.all_gather(out, h, group=self.group)
+        self._p2p_ptrs = [mine if r == self.rank else c.ipc_import(bytes(out[r].cpu().numpy().tobytes())) for r in range(self.world)]
+        self._p2p_cap = capacity
+        return [self._p2p_ptrs]
+
+    def release_peer_arrays(self, ctxs):
+        """Unmap the peers' arrays (before any rank frees or regrows its own); collective."""
+        if getattr(self, "_p2p_cap", -1) >= 0:
+            for r, p in enumerate(self._p2p_ptrs):
+                if r != self.rank:
+                    ctxs[0].ipc_close(p)
+            self._p2p_cap = -1
+            self._p2p_ptrs = None
+            torch.cuda.synchronize(self.device)
+            self.dist.barrier(group=self.group)
+
     def allreduce_sum(self, tensors):
         self.dist.all_reduce(tensors[0], group=self.group)
 
@@ -94,11 +161,18 @@ class TorchFabric:
                                     group=self.group)
 
 
-def find_unique(ctxs, fabric, device, nway_mask=0):
+def p2p_default():
+    return os.environ.get("MB_DIST_P2P", "1") != "0"
+
+
+def find_unique(ctxs, fabric, device, nway_mask=0, p2p=None):
     """MODE_UNIQUE over the ranks of `fabric`; ctxs[i] is the library context of fabric.local_ranks[i] (sequences and
-    seed already set, identical on every rank).  Leaves the canonical match CSR on rank 0's device (fetch it with
-    ctxs[...].fetch()); returns per-local-rank info dicts."""
+    seed already set, identical on every rank).  Leaves every rank's piece of the canonical match CSR on its device
+    (fetch it with ctxs[...].fetch()); returns per-local-rank info dicts.
+    p2p: exchange #1 fused into the partition kernel (peer stores over NVLink) instead of an all-to-all."""
     W, R = fabric.world, fabric.local_ranks
+    if p2p is None:
+        p2p = p2p_default()
     info = [dict(rank=r) for r in R]
     trace = os.environ.get("MB_DIST_TRACE")
     marks = []
@@ -110,34 +184,53 @@ def find_unique(ctxs, fabric, device, nway_mask=0):
 
     mark("start")
     # ---- stage 1 + exchange 1: seed records by key range
-    s1 = [c.dist_extract(r, W) for c, r in zip(ctxs, R)]
-    sc = [cnt for _, cnt in s1]
-    mark("stage1 extract+partition")
-    rc = fabric.counts(sc)
-    sends = [dev_words(p, sum(cnt), device) for p, cnt in s1]
-    recvs = [dev_words(c.dist_recv_buffer(0, sum(k)), sum(k), device) for c, k in zip(ctxs, rc)]
-    fabric.words(sends, sc, recvs, rc)
-    mark("exchange1 seeds")
+    if p2p:
+        # fused: every rank counts its slice per destination, the ranks share the count matrix, and the partition
+        # kernel itself stores each record into its destination's receive array (source-rank order there)
+        sc = [c.dist_extract_count(r, W) for c, r in zip(ctxs, R)]
+        mark("stage1a extract+count")
+        M = fabric.gather_counts(sc)
+        need = max(sum(M[s][d] for s in range(W)) for d in range(W))
+        peers = fabric.peer_arrays(ctxs, need + need // 8 + 4096)
+        for c, r, pp in zip(ctxs, R, peers):
+            c.dist_partition_p2p(pp, [sum(M[s][d] for s in range(r)) for d in range(W)])
+        fabric.barrier()
+        rc = [[M[s][r] for s in range(W)] for r in R]
+        for c in ctxs:
+            c.dist_use_p2p_recv(True)
+        mark("stage1b partition with peer stores")
+    else:
+        s1 = [c.dist_extract(r, W) for c, r in zip(ctxs, R)]
+        sc = [cnt for _, cnt in s1]
+        mark("stage1 extract+partition")
+        rc = fabric.counts(sc)
+        sends = [dev_words(p, sum(cnt), device) for p, cnt in s1]
+        recvs = [dev_words(c.dist_recv_buffer(0, sum(k)), sum(k), device) for c, k in zip(ctxs, rc)]
+        fabric.words(sends, sc, recvs, rc)
+        for c in ctxs:
+            c.dist_use_p2p_recv(False)
+        mark("exchange1 seeds")
     for i, k in enumerate(rc):
         info[i]["seeds_sent"], info[i]["seeds_received"] = sum(sc[i]), sum(k)
-    # ---- stage 2 + exchange 2: candidate rows by group owner
+    # ---- stage 2 + exchange 2: every candidate extended at its source; 4-word rows to the owner of the de-dup group
     s2 = [c.dist_local(W, sum(k), nway_mask=nway_mask) for c, k in zip(ctxs, rc)]
-    mark("stage2 sort+buckets+rows")
-    both = fabric.counts([[x for pair in zip(cc, mc) for x in pair] for _, _, cc, mc in s2])
-    rcc = [b[0::2] for b in both]
-    rmc = [b[1::2] for b in both]
-    hs = [dev_words(h, 2 * sum(cc), device) for h, _, cc, _ in s2]
-    ms = [dev_words(m, sum(mc), device) for _, m, _, mc in s2]
-    hr = [dev_words(c.dist_recv_buffer(1, 2 * sum(k)), 2 * sum(k), device) for c, k in zip(ctxs, rcc)]
-    mr = [dev_words(c.dist_recv_buffer(2, sum(k)), sum(k), device) for c, k in zip(ctxs, rmc)]
-    fabric.words(hs, [cc for _, _, cc, _ in s2], hr, rcc, width=2)
-    fabric.words(ms, [mc for _, _, _, mc in s2], mr, rmc)
+    mark("stage2 sort+buckets+extend+rows")
+    scc = [cc for _, cc in s2]
+    rcc = fabric.counts(scc)
+    rs = [dev_words(p, 4 * sum(cc), device) for p, cc in s2]
+    rr = [dev_words(c.dist_recv_buffer(1, 4 * sum(k)), 4 * sum(k), device) for c, k in zip(ctxs, rcc)]
+    fabric.words(rs, scc, rr, rcc, width=4)
     mark("exchange2 candidate rows")
     for i in range(len(R)):
-        info[i]["candidates_local"], info[i]["candidates_owned"] = sum(s2[i][2]), sum(rcc[i])
-    # ---- stage 3: de-dup of the owned groups; accepted matches go to the rank that owns their range of the canonical order
-    hists = [c.dist_dedup(sum(k), sum(m)) for c, k, m in zip(ctxs, rcc, rmc)]
-    mark("stage3a dedup")
+        info[i]["candidates_local"], info[i]["candidates_owned"] = sum(scc[i]), sum(rcc[i])
+    # ---- stage 3a (owner): chains / resolve; one verdict byte per row goes back to the row's source
+    vs = [dev_bytes(c.dist_resolve(sum(k)), sum(k), device) for c, k in zip(ctxs, rcc)]
+    mark("stage3a chains+resolve")
+    vr = [dev_bytes(c.dist_recv_buffer(5, sum(cc)), sum(cc), device) for c, cc in zip(ctxs, scc)]
+    fabric.words(vs, rcc, vr, scc)
+    mark("exchange2b verdicts")
+    # ---- stage 3b (source): accepted candidates = matches; they go to the rank that owns their range of the canonical order
+    hists = [c.dist_accept() for c in ctxs]
     fabric.allreduce_sum([dev_words(p, 4096, device) for p in hists])
     s3 = [c.dist_match_partition(W) for c in ctxs]
     mark("stage3b match rows")
@@ -177,7 +270,7 @@ def concat_results(pieces):
     return out
 
 
-def find_unique_emulated(seqs, pattern, world, device=0, nway_mask=0):
+def find_unique_emulated(seqs, pattern, world, device=0, nway_mask=0, p2p=None):
     """All `world` ranks inside this process on one GPU (parity tests): returns rank 0's result dict."""
     from .finder import Context
     dev = torch.device("cuda", device)
@@ -190,7 +283,7 @@ def find_unique_emulated(seqs, pattern, world, device=0, nway_mask=0):
                 for s in seqs:
                     c.add_sequence(s)
                 c.set_seed(pattern)
-            info = find_unique(ctxs, LocalFabric(world), dev, nway_mask=nway_mask)
+            info = find_unique(ctxs, LocalFabric(world), dev, nway_mask=nway_mask, p2p=p2p)
             stream.synchronize()
             res = concat_results([c.fetch() for c in ctxs])
         res["info"] = info
@@ -326,6 +419,7 @@ def bench_main(args, CONFIG_NAMES, config_params, peaks, ClockSampler):
             "rank0": {k: v for k, v in info[0].items()}, "wall_ms_per_step": wall_ms / args.steps, "clocks": sampler.summary(),
         }
         print(json.dumps(line), flush=True)
+    fabric.release_peer_arrays([ctx])
     ctx.close()
     dist.barrier()
     dist.destroy_process_group()

@@ -127,23 +127,64 @@ class Context:
         _check(self._h, L.lib().mb_dist_extract(self._h, int(rank), int(world), C.byref(ptr), counts))
         return ptr.value or 0, [int(x) for x in counts]
 
+    def dist_extract_count(self, rank, world):
+        """stage 1a -> records of this rank's slice per destination rank (the slice stays in library memory)"""
+        counts = (C.c_uint64 * world)()
+        _check(self._h, L.lib().mb_dist_extract_count(self._h, int(rank), int(world), counts))
+        return [int(x) for x in counts]
+
+    def dist_partition_p2p(self, peer_ptrs, peer_offsets):
+        """stage 1b fused with exchange #1: the partition pass stores every record into its destination rank's
+        receive array (peer_ptrs[d], at record index peer_offsets[d] + ...) over NVLink; asynchronous"""
+        n = len(peer_ptrs)
+        pp = (C.c_void_p * n)(*[C.c_void_p(int(p)) for p in peer_ptrs])
+        po = (C.c_uint64 * n)(*[int(o) for o in peer_offsets])
+        _check(self._h, L.lib().mb_dist_partition(self._h, pp, po, None))
+
+    def dist_p2p_recv_array(self, capacity_records):
+        ptr = C.c_void_p()
+        _check(self._h, L.lib().mb_dist_p2p_recv_array(self._h, int(capacity_records), C.byref(ptr)))
+        return ptr.value or 0
+
+    def dist_use_p2p_recv(self, on):
+        _check(self._h, L.lib().mb_dist_use_p2p_recv(self._h, 1 if on else 0))
+
+    def ipc_export(self, dev_ptr):
+        buf = C.create_string_buffer(64)
+        _check(self._h, L.lib().mb_ipc_export(self._h, C.c_void_p(int(dev_ptr)), buf))
+        return buf.raw
+
+    def ipc_import(self, handle):
+        ptr = C.c_void_p()
+        _check(self._h, L.lib().mb_ipc_import(self._h, bytes(handle), C.byref(ptr)))
+        return ptr.value or 0
+
+    def ipc_close(self, dev_ptr):
+        _check(self._h, L.lib().mb_ipc_close(self._h, C.c_void_p(int(dev_ptr))))
+
     def dist_recv_buffer(self, which, n_words):
         ptr = C.c_void_p()
         _check(self._h, L.lib().mb_dist_recv_buffer(self._h, int(which), int(n_words), C.byref(ptr)))
         return ptr.value or 0
 
     def dist_local(self, world, n_recv, mode=L.MODE_UNIQUE, nway_mask=0):
-        """-> (headers pointer, components pointer, rows per owner, component words per owner)"""
+        """stage 2 -> (pointer of the 4-word candidate rows grouped by owner, rows per owner)"""
         p = self._params(mode, 2, 1000, False, nway_mask)
-        hdr, comps = C.c_void_p(), C.c_void_p()
-        cc, mc = (C.c_uint64 * world)(), (C.c_uint64 * world)()
-        _check(self._h, L.lib().mb_dist_local(self._h, C.byref(p), int(n_recv), cc, mc, C.byref(hdr), C.byref(comps)))
-        return hdr.value or 0, comps.value or 0, [int(x) for x in cc], [int(x) for x in mc]
+        rows = C.c_void_p()
+        cc = (C.c_uint64 * world)()
+        _check(self._h, L.lib().mb_dist_local(self._h, C.byref(p), int(n_recv), cc, C.byref(rows)))
+        return rows.value or 0, [int(x) for x in cc]
 
-    def dist_dedup(self, n_cand, n_comp):
-        """-> device pointer of the 4096-bin histogram (uint64) of this rank's accepted matches' canonical keys"""
+    def dist_resolve(self, n_rows):
+        """stage 3a (owner) -> device pointer of one verdict byte per received row (1 accepted)"""
+        v = C.c_void_p()
+        _check(self._h, L.lib().mb_dist_resolve(self._h, int(n_rows), C.byref(v)))
+        return v.value or 0
+
+    def dist_accept(self):
+        """stage 3b (source) -> device pointer of the 4096-bin histogram (uint64) of this rank's matches' canonical keys"""
         hist = C.c_void_p()
-        _check(self._h, L.lib().mb_dist_dedup(self._h, int(n_cand), int(n_comp), C.byref(hist)))
+        _check(self._h, L.lib().mb_dist_accept(self._h, C.byref(hist)))
         return hist.value or 0
 
     def dist_match_partition(self, world):
@@ -158,9 +199,9 @@ class Context:
         _check(self._h, L.lib().mb_dist_output(self._h, int(n_match), int(n_comp)))
 
     def dist_stage_ms(self):
-        out = (C.c_float * 4)()
+        out = (C.c_float * 8)()
         _check(self._h, L.lib().mb_dist_stage_ms(self._h, out))
-        return dict(extract_partition=out[0], sort=out[1], buckets=out[2], dedup=out[3])
+        return dict(extract_partition=out[0], sort=out[1], buckets=out[2], extend=out[3], resolve=out[4])
 
     def stats(self):
         s = L.MbStats()

@@ -39,6 +39,18 @@ def test_local_fabric_routes_by_destination():
         assert rc[d] == [counts[s][d] for s in range(3)]
 
 
+def test_local_fabric_count_matrix_and_offsets():
+    counts, _ = _payload(3)
+    fab = LocalFabric(3)
+    M = fab.gather_counts(counts)
+    assert M == counts
+    # block of source r inside destination d's receive array starts after the blocks of the lower ranks
+    rc = fab.counts(counts)
+    for d in range(3):
+        for r in range(3):
+            assert sum(M[s][d] for s in range(r)) == sum(rc[d][:r])
+
+
 def test_local_fabric_allreduce():
     fab = LocalFabric(3)
     ts = [torch.arange(5, dtype=torch.int64) * (r + 1) for r in range(3)]
@@ -66,6 +78,15 @@ def _worker(rank, world, port, out):
         h = torch.arange(4, dtype=torch.int64) + rank
         fab.allreduce_sum([h])
         ok = ok and h.tolist() == [1, 3, 5, 7]
+        # the count matrix of the fused exchange 1, and the verdict bytes of exchange 2b (uint8, reversed counts)
+        ok = ok and fab.gather_counts([counts[rank]]) == counts
+        fab.barrier()
+        vb = [torch.arange(sum(exp_rc[r]), dtype=torch.uint8) + r for r in range(world)]
+        back = torch.zeros(sum(counts[rank]), dtype=torch.uint8)
+        fab.words([vb[rank]], [exp_rc[rank]], [back], [counts[rank]])
+        exp_back = [torch.zeros(sum(counts[r]), dtype=torch.uint8) for r in range(world)]
+        LocalFabric(world).words(vb, exp_rc, exp_back, counts)
+        ok = ok and torch.equal(back, exp_back[rank])
         out.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()

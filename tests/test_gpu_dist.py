@@ -28,6 +28,17 @@ def test_emulated_world_matches_oracle(world):
         assert sum(i["seeds_received"] for i in got["info"]) == sum(max(0, len(s) - pattern.bit_length() + 1) for s in seqs)
 
 
+def test_emulated_world_nccl_style_exchange1():
+    """exchange 1 as a separate all-to-all of a local send buffer (p2p=False) gives the same result as the fused one"""
+    from mauvealigner_b200 import dist
+    rng = np.random.default_rng(77)
+    seqs = family(rng, 30000, 4, sub=0.03, indel=0.002, inv=1)
+    want = O.find(seqs, 0b1101110111110111011, O.MODE_UNIQUE)
+    for p2p in (False, True):
+        got = dist.find_unique_emulated(seqs, 0b1101110111110111011, 3, p2p=p2p)
+        assert_same(got, want, f"p2p={p2p}")
+
+
 def test_emulated_edge_cases():
     from mauvealigner_b200 import dist
     rng = np.random.default_rng(9)

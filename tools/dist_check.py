@@ -29,7 +29,8 @@ def main():
     for s in seqs:
         ctx.add_sequence(s)
     ctx.set_seed(pattern)
-    info = find_unique([ctx], TorchFabric(device=dev), dev)
+    fabric = TorchFabric(device=dev)
+    info = find_unique([ctx], fabric, dev)
     torch.cuda.synchronize()
     print(f"[rank {rank}] {info[0]} stages {ctx.dist_stage_ms()}", flush=True)
     piece = ctx.fetch()
@@ -44,6 +45,7 @@ def main():
         print(f"DIST_CHECK world={world} config=C{config}/{scale} matches={got['n_matches']} pieces={[p['n_matches'] for p in pieces]} "
               f"{'OK bit-exact vs single-GPU path' if ok else 'MISMATCH'}", flush=True)
     dist.barrier()
+    fabric.release_peer_arrays([ctx])
     ctx.close()
     dist.destroy_process_group()
 
