@@ -435,7 +435,7 @@ int mb_dist_output(mb_ctx* c, uint64_t n_match64, uint64_t n_comp64) {
         launch_scan_u32(c->x_m.as<u32>(), n_match, c->cand_off.as<u32>(), nullptr, c->status_slice(div_up(n_match, scan_tile())), c->ticket(), nullptr,
                         st);
         LAUNCHED(c);
-        launch_unpack_match(hdr, comps, c->cand_off.as<u32>(), n_match, c->comp_pos.as<u32>(), c->comp_gs.as<u8>(), c->ext_l.as<u32>(),
+        launch_unpack_match(hdr, comps, c->cand_off.as<u32>(), n_match, n_mcomp, c->comp_pos.as<u32>(), c->comp_gs.as<u8>(), c->ext_l.as<u32>(),
                             c->ext_r.as<u32>(), c->s_cand.as<u8>(), c->rep_cand.as<u32>(), st);
         LAUNCHED(c); CHECK_LAUNCH(c);
         TRY(mbi_output_unique(c, n_match, c->d_maxlen));

@@ -142,16 +142,8 @@ void launch_uniq_gather(const OutputArgs& a, const u64* sval, u32 L, u32 n_upper
 // ---- kernels_dist.cu (multi-GPU exchange formats)
 void launch_fold_lut(const u32* hist, const u8* lut, u32 nbins, u32 world, u32* digit_base, u64* counts, cudaStream_t st);
 void launch_owner_keys(const u64* ghash, u32 n, u32 world, u64* skey, u64* sval, cudaStream_t st);
-void launch_perm_m(const u64* perm, const u32* cand_off, u32 n, u32* m_out, cudaStream_t st);
-void launch_pack_cand(const u64* perm, const u64* poff, const u32* cand_off, const u32* comp_pos, const u8* comp_gs, const u64* ghash,
-                      const u64* ghash2, u32 n, u64* hdr, u64* comps, cudaStream_t st);
 void launch_hdr_m(const u64* hdr, u32 n, u32* m_out, cudaStream_t st);
-void launch_unpack_cand(const u64* hdr, const u64* comps, const u32* cand_off, u32 n, const GenomeTable& gt, u32* comp_pos, u8* comp_gs,
-                        u64* ghash, u64* ghash2, u64* bitmap, cudaStream_t st);
-void launch_acc_m(const u8* state, const u32* item_cand, const u32* cand_off, u32 n, u32* m_out, cudaStream_t st);
-void launch_pack_match(const u8* state, const u32* item_cand, const u32* match_idx, const u32* acomp_off, const u32* cand_off, const u32* comp_pos, const u8* comp_gs,
-                       const u32* ext_l, const u32* ext_r, u32 n, u64* hdr, u64* comps, cudaStream_t st);
-void launch_unpack_match(const u64* hdr, const u64* comps, const u32* cand_off, u32 n, u32* comp_pos, u8* comp_gs, u32* ext_l, u32* ext_r,
+void launch_unpack_match(const u64* hdr, const u64* comps, const u32* cand_off, u32 n, u32 n_comp, u32* comp_pos, u8* comp_gs, u32* ext_l, u32* ext_r,
                          u8* state, u32* item_cand, cudaStream_t st);
 void launch_match_keys(const u8* state, const u32* item_cand, const u32* match_idx, const u32* cand_off, const u8* comp_gs, const u32* comp_pos,
                        const u32* ext_l, u32 n_items, int sbits, int binshift, u64* key, u32* item_of, u64* hist, cudaStream_t st);

@@ -2,9 +2,11 @@
 //
 // Exchange formats (all 8-byte granular so every exchange is one all-to-all of u64 words):
 //   seed records    the u64 records of the single-GPU path, partitioned by destination = seed-key range
-//   candidate rows  header 2 x u64 (group hash, component count) + one u64 per component (pos | gs << 32),
-//                   partitioned by owner = f(group hash); rows keep ascending seed order inside a partition
-//   match rows      header 2 x u64 (ext_l | ext_r << 32, component count) + the same component words
+//   candidate rows  4 x u64 (group hash, second hash, first component, extents) — the candidates are extended at
+//                   their source and their component lists never travel; partitioned by owner = f(group hash),
+//                   rows keep ascending seed order inside a partition
+//   verdicts        one byte per candidate row, back from the owner to the source, in row order
+//   match rows      header 2 x u64 (ext_l | ext_r << 32, component count) + one u64 per component (pos | gs << 32)
 #include "common.cuh"
 #include "kernels.h"
 
@@ -45,34 +47,6 @@ void launch_owner_keys(const u64* ghash, u32 n, u32 world, u64* skey, u64* sval,
     if (n) k_owner_keys<<<div_up(n, 256), 256, 0, st>>>(ghash, n, world, skey, sval);
 }
 
-// m of the j-th row in partition order
-__global__ void __launch_bounds__(256) k_perm_m(const u64* __restrict__ perm, const u32* __restrict__ cand_off, u32 n, u32* __restrict__ m_out) {
-    u32 j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    u32 c = (u32)perm[j];
-    m_out[j] = cand_off[c + 1] - cand_off[c];
-}
-void launch_perm_m(const u64* perm, const u32* cand_off, u32 n, u32* m_out, cudaStream_t st) {
-    if (n) k_perm_m<<<div_up(n, 256), 256, 0, st>>>(perm, cand_off, n, m_out);
-}
-
-__global__ void __launch_bounds__(256) k_pack_cand(const u64* __restrict__ perm, const u64* __restrict__ poff, const u32* __restrict__ cand_off,
-                                                   const u32* __restrict__ comp_pos, const u8* __restrict__ comp_gs, const u64* __restrict__ ghash,
-                                                   const u64* __restrict__ ghash2, u32 n, u64* __restrict__ hdr, u64* __restrict__ comps) {
-    u32 j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    u32 c = (u32)perm[j];
-    u32 off = cand_off[c], m = cand_off[c + 1] - off;
-    hdr[2 * (u64)j] = ghash[c];
-    hdr[2 * (u64)j + 1] = (ghash2[c] & ~0xFFull) | m; // m <= 64
-    u64 o = poff[j];
-    for (u32 k = 0; k < m; ++k) comps[o + k] = (u64)comp_pos[off + k] | ((u64)comp_gs[off + k] << 32);
-}
-void launch_pack_cand(const u64* perm, const u64* poff, const u32* cand_off, const u32* comp_pos, const u8* comp_gs, const u64* ghash,
-                      const u64* ghash2, u32 n, u64* hdr, u64* comps, cudaStream_t st) {
-    if (n) k_pack_cand<<<div_up(n, 256), 256, 0, st>>>(perm, poff, cand_off, comp_pos, comp_gs, ghash, ghash2, n, hdr, comps);
-}
-
 __global__ void __launch_bounds__(256) k_hdr_m(const u64* __restrict__ hdr, u32 n, u32* __restrict__ m_out) {
     u32 j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j < n) m_out[j] = (u32)(hdr[2 * (u64)j + 1] & 0xFFu);
@@ -81,83 +55,31 @@ void launch_hdr_m(const u64* hdr, u32 n, u32* m_out, cudaStream_t st) {
     if (n) k_hdr_m<<<div_up(n, 256), 256, 0, st>>>(hdr, n, m_out);
 }
 
-// received candidate rows -> candidate CSR of the owner + its (first genome, position) bitmap
-__global__ void __launch_bounds__(256) k_unpack_cand(const u64* __restrict__ hdr, const u64* __restrict__ comps, const u32* __restrict__ cand_off,
-                                                     u32 n, GenomeTable gt, u32* __restrict__ comp_pos, u8* __restrict__ comp_gs,
-                                                     u64* __restrict__ ghash, u64* __restrict__ ghash2, u64* __restrict__ bitmap) {
-    u32 j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    u32 off = cand_off[j], m = cand_off[j + 1] - off;
-    ghash[j] = hdr[2 * (u64)j];
-    ghash2[j] = hdr[2 * (u64)j + 1] & ~0xFFull;
-    for (u32 k = 0; k < m; ++k) {
-        u64 w = comps[off + k];
-        u32 p = (u32)w;
-        u8 gs = (u8)(w >> 32);
-        comp_pos[off + k] = p;
-        comp_gs[off + k] = gs;
-        if (k == 0) {
-            u64 gp = gt.vbase[gs & 0x7F] + p; // MODE_UNIQUE only: virtual genome = first genome
-            atomicOr((unsigned long long*)&bitmap[gp >> 6], 1ull << (gp & 63));
-        }
-    }
-}
-void launch_unpack_cand(const u64* hdr, const u64* comps, const u32* cand_off, u32 n, const GenomeTable& gt, u32* comp_pos, u8* comp_gs,
-                        u64* ghash, u64* ghash2, u64* bitmap, cudaStream_t st) {
-    if (n) k_unpack_cand<<<div_up(n, 256), 256, 0, st>>>(hdr, comps, cand_off, n, gt, comp_pos, comp_gs, ghash, ghash2, bitmap);
-}
-
-// component count of every accepted candidate (0 for the others)
-__global__ void __launch_bounds__(256) k_acc_m(const u8* __restrict__ state, const u32* __restrict__ item_cand, const u32* __restrict__ cand_off, u32 n,
-                                               u32* __restrict__ m_out) {
-    u32 it = blockIdx.x * blockDim.x + threadIdx.x;
-    if (it >= n) return;
-    u32 c = item_cand[it];
-    m_out[it] = (state[it] & 15u) == 1u ? cand_off[c + 1] - cand_off[c] : 0u;
-}
-void launch_acc_m(const u8* state, const u32* item_cand, const u32* cand_off, u32 n, u32* m_out, cudaStream_t st) {
-    if (n) k_acc_m<<<div_up(n, 256), 256, 0, st>>>(state, item_cand, cand_off, n, m_out);
-}
-
-__global__ void __launch_bounds__(256) k_pack_match(const u8* __restrict__ state, const u32* __restrict__ item_cand, const u32* __restrict__ match_idx, const u32* __restrict__ acomp_off,
-                                                    const u32* __restrict__ cand_off, const u32* __restrict__ comp_pos, const u8* __restrict__ comp_gs,
-                                                    const u32* __restrict__ ext_l, const u32* __restrict__ ext_r, u32 n, u64* __restrict__ hdr,
-                                                    u64* __restrict__ comps) {
-    u32 it = blockIdx.x * blockDim.x + threadIdx.x;
-    if (it >= n || (state[it] & 15u) != 1u) return;
-    u32 c = item_cand[it];
-    u32 j = match_idx[it];
-    u32 off = cand_off[c], m = cand_off[c + 1] - off;
-    hdr[2 * (u64)j] = (u64)ext_l[c] | ((u64)ext_r[c] << 32);
-    hdr[2 * (u64)j + 1] = m;
-    u32 o = acomp_off[it];
-    for (u32 k = 0; k < m; ++k) comps[o + k] = (u64)comp_pos[off + k] | ((u64)comp_gs[off + k] << 32);
-}
-void launch_pack_match(const u8* state, const u32* item_cand, const u32* match_idx, const u32* acomp_off, const u32* cand_off, const u32* comp_pos, const u8* comp_gs,
-                       const u32* ext_l, const u32* ext_r, u32 n, u64* hdr, u64* comps, cudaStream_t st) {
-    if (n) k_pack_match<<<div_up(n, 256), 256, 0, st>>>(state, item_cand, match_idx, acomp_off, cand_off, comp_pos, comp_gs, ext_l, ext_r, n, hdr, comps);
-}
-
-// gathered match rows -> "all accepted" candidate arrays of rank 0 (input of the output stage)
-__global__ void __launch_bounds__(256) k_unpack_match(const u64* __restrict__ hdr, const u64* __restrict__ comps, const u32* __restrict__ cand_off,
-                                                      u32 n, u32* __restrict__ comp_pos, u8* __restrict__ comp_gs, u32* __restrict__ ext_l,
+// received match rows -> "all accepted" candidate arrays (input of the output stage).  The component words of
+// row j sit at cand_off[j] in the receive buffer AND in the candidate arrays, so the components are one flat
+// elementwise pass; the headers are a second one.
+__global__ void __launch_bounds__(256) k_unpack_match(const ulonglong2* __restrict__ hdr, const u64* __restrict__ comps, u32 n, u32 n_comp,
+                                                      u32* __restrict__ comp_pos, u8* __restrict__ comp_gs, u32* __restrict__ ext_l,
                                                       u32* __restrict__ ext_r, u8* __restrict__ state, u32* __restrict__ item_cand) {
-    u32 j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    u32 off = cand_off[j], m = cand_off[j + 1] - off;
-    u64 e = hdr[2 * (u64)j];
-    ext_l[j] = (u32)e; ext_r[j] = (u32)(e >> 32);
-    state[j] = 1;
-    item_cand[j] = j;
-    for (u32 k = 0; k < m; ++k) {
-        u64 w = comps[off + k];
-        comp_pos[off + k] = (u32)w;
-        comp_gs[off + k] = (u8)(w >> 32);
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_comp) {
+        const u64 w = comps[i];
+        comp_pos[i] = (u32)w;
+        comp_gs[i] = (u8)(w >> 32);
+    }
+    if (i < n) {
+        const u64 e = hdr[i].x;
+        ext_l[i] = (u32)e; ext_r[i] = (u32)(e >> 32);
+        state[i] = 1;
+        item_cand[i] = i;
     }
 }
-void launch_unpack_match(const u64* hdr, const u64* comps, const u32* cand_off, u32 n, u32* comp_pos, u8* comp_gs, u32* ext_l, u32* ext_r,
+void launch_unpack_match(const u64* hdr, const u64* comps, const u32* cand_off, u32 n, u32 n_comp, u32* comp_pos, u8* comp_gs, u32* ext_l, u32* ext_r,
                          u8* state, u32* item_cand, cudaStream_t st) {
-    if (n) k_unpack_match<<<div_up(n, 256), 256, 0, st>>>(hdr, comps, cand_off, n, comp_pos, comp_gs, ext_l, ext_r, state, item_cand);
+    (void)cand_off;
+    const u32 items = n > n_comp ? n : n_comp;
+    if (items) k_unpack_match<<<div_up(items, 256), 256, 0, st>>>(reinterpret_cast<const ulonglong2*>(hdr), comps, n, n_comp, comp_pos, comp_gs, ext_l, ext_r,
+                                                                 state, item_cand);
 }
 
 // ---- extend-at-source protocol: 4-word candidate rows (the extents travel, the component lists stay at the source)
@@ -215,25 +137,36 @@ void launch_apply_accept(const u8* acc, const u32* perm, u32 n, u8* state, u32* 
     if (n) k_apply_accept<<<div_up(n, 256), 256, 0, st>>>(acc, perm, n, state, item_cand);
 }
 
-// ---- distributed output: canonical key of every accepted match, and its key histogram (top 12 key bits)
+// ---- distributed output: canonical key of every accepted match, and its key histogram (top 12 key bits).
+// The matches of one run crowd into few bins (most share their first genome), so the histogram is built per
+// block in shared memory and flushed once.
 __global__ void __launch_bounds__(256) k_match_keys(const u8* __restrict__ state, const u32* __restrict__ item_cand, const u32* __restrict__ match_idx,
                                                     const u32* __restrict__ cand_off, const u8* __restrict__ comp_gs, const u32* __restrict__ comp_pos,
                                                     const u32* __restrict__ ext_l, u32 n_items, int sbits, int binshift, u64* __restrict__ key,
                                                     u32* __restrict__ item_of, u64* __restrict__ hist) {
-    u32 it = blockIdx.x * blockDim.x + threadIdx.x;
-    if (it >= n_items || (state[it] & 15u) != 1u) return;
-    u32 c = item_cand[it], j = match_idx[it];
-    u32 off = cand_off[c];
-    u32 f = comp_gs[off] & 0x7F;
-    u64 st = (u64)comp_pos[off] - ext_l[c] + 1;
-    u64 k = ((u64)(MB_MAX_SEQ - 1 - f) << sbits) | st; // same key as k_uniq_keys: the ranks' ranges concatenate to D18
-    key[j] = k;
-    item_of[j] = it;
-    atomicAdd((unsigned long long*)&hist[(k >> binshift) & 4095u], 1ull);
+    __shared__ u32 sHist[4096];
+    for (u32 b = threadIdx.x; b < 4096; b += blockDim.x) sHist[b] = 0;
+    __syncthreads();
+    for (u32 it = blockIdx.x * blockDim.x + threadIdx.x; it < n_items; it += gridDim.x * blockDim.x) {
+        if ((state[it] & 15u) != 1u) continue;
+        u32 c = item_cand[it], j = match_idx[it];
+        u32 off = cand_off[c];
+        u32 f = comp_gs[off] & 0x7F;
+        u64 st = (u64)comp_pos[off] - ext_l[c] + 1;
+        u64 k = ((u64)(MB_MAX_SEQ - 1 - f) << sbits) | st; // same key as k_uniq_keys: the ranks' ranges concatenate to D18
+        key[j] = k;
+        item_of[j] = it;
+        atomicAdd(&sHist[(k >> binshift) & 4095u], 1u);
+    }
+    __syncthreads();
+    for (u32 b = threadIdx.x; b < 4096; b += blockDim.x) {
+        u32 v = sHist[b];
+        if (v) atomicAdd((unsigned long long*)&hist[b], (unsigned long long)v);
+    }
 }
 void launch_match_keys(const u8* state, const u32* item_cand, const u32* match_idx, const u32* cand_off, const u8* comp_gs, const u32* comp_pos,
                        const u32* ext_l, u32 n_items, int sbits, int binshift, u64* key, u32* item_of, u64* hist, cudaStream_t st) {
-    if (n_items) k_match_keys<<<div_up(n_items, 256), 256, 0, st>>>(state, item_cand, match_idx, cand_off, comp_gs, comp_pos, ext_l, n_items, sbits, binshift, key, item_of, hist);
+    if (n_items) k_match_keys<<<std::min<u32>(div_up(n_items, 256), 148 * 8), 256, 0, st>>>(state, item_cand, match_idx, cand_off, comp_gs, comp_pos, ext_l, n_items, sbits, binshift, key, item_of, hist);
 }
 
 __global__ void __launch_bounds__(256) k_dest_keys(const u64* __restrict__ key, u32 n, int binshift, const u8* __restrict__ lut, u64* __restrict__ skey,
@@ -258,20 +191,32 @@ void launch_match_perm_m(const u64* perm, const u32* item_of, const u32* item_ca
     if (n) k_match_perm_m<<<div_up(n, 256), 256, 0, st>>>(perm, item_of, item_cand, cand_off, n, m_out);
 }
 
+// lane = row for the header; the component words of the warp's 32 rows are copied by all lanes together
+// (coalesced on both sides)
 __global__ void __launch_bounds__(256) k_pack_match_perm(const u64* __restrict__ perm, const u32* __restrict__ item_of, const u32* __restrict__ item_cand,
                                                          const u64* __restrict__ poff, const u32* __restrict__ cand_off, const u32* __restrict__ comp_pos,
                                                          const u8* __restrict__ comp_gs, const u32* __restrict__ ext_l, const u32* __restrict__ ext_r, u32 n,
-                                                         u64* __restrict__ hdr, u64* __restrict__ comps) {
-    u32 t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n) return;
-    u32 c = item_cand[item_of[(u32)perm[t]]];
-    u32 off = cand_off[c], m = cand_off[c + 1] - off;
-    hdr[2 * (u64)t] = (u64)ext_l[c] | ((u64)ext_r[c] << 32);
-    hdr[2 * (u64)t + 1] = m;
-    u64 o = poff[t];
-    for (u32 k = 0; k < m; ++k) comps[o + k] = (u64)comp_pos[off + k] | ((u64)comp_gs[off + k] << 32);
+                                                         ulonglong2* __restrict__ hdr, u64* __restrict__ comps) {
+    const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 lane = threadIdx.x & 31;
+    u32 off = 0, m = 0;
+    u64 o = 0;
+    if (t < n) {
+        const u32 c = item_cand[item_of[(u32)perm[t]]];
+        off = cand_off[c]; m = cand_off[c + 1] - off;
+        hdr[t] = make_ulonglong2((u64)ext_l[c] | ((u64)ext_r[c] << 32), m);
+        o = poff[t];
+    }
+    for (int j = 0; j < 32; ++j) {
+        const u32 mj = __shfl_sync(0xFFFFFFFFu, m, j);
+        if (mj == 0) continue; // uniform
+        const u32 offj = __shfl_sync(0xFFFFFFFFu, off, j);
+        const u64 oj = __shfl_sync(0xFFFFFFFFu, o, j);
+        for (u32 k = lane; k < mj; k += 32) comps[oj + k] = (u64)comp_pos[offj + k] | ((u64)comp_gs[offj + k] << 32);
+    }
 }
 void launch_pack_match_perm(const u64* perm, const u32* item_of, const u32* item_cand, const u64* poff, const u32* cand_off, const u32* comp_pos,
                             const u8* comp_gs, const u32* ext_l, const u32* ext_r, u32 n, u64* hdr, u64* comps, cudaStream_t st) {
-    if (n) k_pack_match_perm<<<div_up(n, 256), 256, 0, st>>>(perm, item_of, item_cand, poff, cand_off, comp_pos, comp_gs, ext_l, ext_r, n, hdr, comps);
+    if (n) k_pack_match_perm<<<div_up(n, 256), 256, 0, st>>>(perm, item_of, item_cand, poff, cand_off, comp_pos, comp_gs, ext_l, ext_r, n,
+                                                            reinterpret_cast<ulonglong2*>(hdr), comps);
 }

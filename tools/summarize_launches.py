@@ -4,13 +4,13 @@ import csv
 import sys
 
 
-def main(path, marker="k_extract"):
+def main(path, marker="k_extract", nth_last=1):
     with open(path) as f:
         lines = [l for l in f if not l.startswith("==")]
     rows = list(csv.DictReader(lines))
     names = [x["Kernel Name"] for x in rows]
     idx = [i for i, n in enumerate(names) if marker in n]
-    start = idx[-1] if idx else 0
+    start = idx[-int(nth_last)] if len(idx) >= int(nth_last) else 0
     agg = collections.OrderedDict()
     for x in rows[start:]:
         n = x["Kernel Name"].split("(")[0]
