@@ -54,25 +54,54 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clocks / throttle reasons of the GPUs in use, sampled during the timed region through NVML in-process
+    (pynvml; a `nvidia-smi` subprocess per sample stalls the driver for milliseconds and showed up as multi-ms
+    outliers in the per-step times).  Falls back to the nvidia-smi query line of B200_PROFILING.md without pynvml."""
 
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
-    def __init__(self, index):
+    def __init__(self, indices, period=0.05):
         super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], False
+        self.indices = [indices] if isinstance(indices, int) else list(indices)
+        self.period, self.samples, self.stop_flag = period, [], False
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.handles = [pynvml.nvmlDeviceGetHandleByIndex(i) for i in self.indices]
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        N = self.nvml
+        bits = (("hw_slowdown", getattr(N, "nvmlClocksEventReasonHwSlowdown", 0x8)),
+                ("hw_thermal_slowdown", getattr(N, "nvmlClocksEventReasonHwThermalSlowdown", 0x40)),
+                ("sw_thermal_slowdown", getattr(N, "nvmlClocksEventReasonSwThermalSlowdown", 0x20)),
+                ("sw_power_cap", getattr(N, "nvmlClocksEventReasonSwPowerCap", 0x4)))
+        for h in self.handles:
+            sm = N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)
+            mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+            r = N.nvmlDeviceGetCurrentClocksEventReasons(h)
+            self.samples.append([str(sm), str(mx)] + ["Active" if r & b else "Not Active" for _, b in bits])
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", "-i", ",".join(str(i) for i in self.indices), f"--query-gpu={self.Q}",
+                              "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout.strip()
+        for line in out.splitlines():
+            self.samples.append([x.strip() for x in line.split(",")])
 
     def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                if self.nvml:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(self.period if self.nvml else 0.25)
 
     def summary(self):
         sm, mx, reasons = [], 0.0, set()
@@ -86,7 +115,7 @@ class ClockSampler(threading.Thread):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvml" if self.nvml else "nvidia-smi", "gpus": self.indices}
 
 
 def run_reference(args):

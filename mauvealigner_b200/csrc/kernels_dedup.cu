@@ -688,10 +688,13 @@ __device__ __forceinline__ void extend_finish(const DedupArgs& a, const GenomeTa
     wl_push(last ? a.wl_long : out_list, last ? a.ctr + 6 : out_count, more, i);
 }
 
+#ifndef DD_EXT_MINB
+#define DD_EXT_MINB 1
+#endif
 #define DD_EXT_FIRST_ROUNDS 2
 #define DD_EXT_MORE_ROUNDS 4
 
-__global__ void __launch_bounds__(DD_NT) k_extend(DedupArgs a, GenomeTable gt, SeedDev sd, u32* out_list, u32* out_count) {
+__global__ void __launch_bounds__(DD_NT, DD_EXT_MINB) k_extend(DedupArgs a, GenomeTable gt, SeedDev sd, u32* out_list, u32* out_count) {
     __shared__ u32 sMap[DD_NT / 32][32][4];
     __shared__ u32 sRoom[DD_NT / 32][32][2];
     const int warp = threadIdx.x >> 5;
@@ -713,7 +716,7 @@ __global__ void __launch_bounds__(DD_NT) k_extend(DedupArgs a, GenomeTable gt, S
 }
 
 // the unfinished reps of the previous launch, 32 per warp
-__global__ void __launch_bounds__(DD_NT) k_extend_more(DedupArgs a, GenomeTable gt, SeedDev sd, const u32* in_list, const u32* in_count, u32* out_list,
+__global__ void __launch_bounds__(DD_NT, DD_EXT_MINB) k_extend_more(DedupArgs a, GenomeTable gt, SeedDev sd, const u32* in_list, const u32* in_count, u32* out_list,
                                                        u32* out_count, int last) {
     __shared__ u32 sMap[DD_NT / 32][32][4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

@@ -334,8 +334,10 @@ def bench_main(args, CONFIG_NAMES, config_params, peaks, ClockSampler):
 
     for _ in range(W):
         step()
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler = None
+    if rank == 0:  # one sampler for the whole job: all GPUs in use, through NVML
+        sampler = ClockSampler(list(range(world)))
+        sampler.start()
     torch.cuda.synchronize()
     dist.barrier()
     torch.cuda.synchronize()
@@ -385,8 +387,9 @@ def bench_main(args, CONFIG_NAMES, config_params, peaks, ClockSampler):
     st2 = ctx.stats()
     d2h = torch.tensor([float(st2["d2h_bytes"])], device=dev)
     dist.all_reduce(d2h, op=dist.ReduceOp.SUM)
-    sampler.stop_flag = True
-    sampler.join(timeout=2)
+    if sampler:
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
 
     if rank == 0:
         peak, peak_src = peaks()
