@@ -128,17 +128,18 @@ int mb_fetch_result(mb_ctx* ctx, const mb_result** out);
  *     or mb_dist_extract_count + mb_dist_partition(peer arrays): the same, with the exchange fused into the kernel
  *   2 mb_dist_recv_buffer(0, n) is where exchange 1 must deliver (source-rank order);
  *     mb_dist_local        -> sort / runs / policy over the key range, EVERY candidate extended at its source;
- *                             4-word candidate rows (two group hashes, first component, extents) grouped by owner
- *                             of the de-dup group at *d_rows, h_row_counts[world]     (exchange 2: 4 words / row)
+ *                             h_row_counts[world] = candidates per owner of their de-dup group;
+ *     mb_dist_rows_pack    -> 4-word candidate rows (two group hashes, first component, extents) grouped by owner:
+ *                             at *d_rows (exchange 2: 4 words / row), or stored into the owners' buffers directly
  *   3 mb_dist_recv_buffer(1, 4 n) receives the rows (source-rank order);
  *     mb_dist_resolve      -> chains / resolve over the owned groups; *d_verdict = one byte per received row
  *                             (1 accepted), to go back to the sources in row order    (exchange 2b: 1 byte / row)
  *     mb_dist_recv_buffer(5, n_bytes) receives this rank's verdicts (the row order of stage 2);
  *     mb_dist_accept       -> *d_hist = 4096 uint64 counts (device) of the accepted matches' canonical keys:
  *                             sum it over all ranks IN PLACE (all-reduce)
- *     mb_dist_match_partition -> match rows grouped by destination = range of the canonical order
- *                             (*d_hdr 2 words per row, *d_comps 1 word per component), counts per destination
- *                                                                                      (exchange 3)
+ *     mb_dist_match_partition -> matches grouped by destination = range of the canonical order: counts per destination;
+ *     mb_dist_match_pack   -> their rows (*d_hdr 2 words per row, *d_comps 1 word per component)   (exchange 3),
+ *                             or stored into the destinations' buffers directly
  *   4 mb_dist_recv_buffer(3 / 4, n) receive them; mb_dist_output builds the canonical CSR of this rank's
  *     range, after which mb_fetch_result works as for mb_find_device.  The ranks' pieces, concatenated in
  *     rank order, are the result. */
@@ -159,10 +160,18 @@ int mb_ipc_import(mb_ctx* ctx, const uint8_t* handle64, void** d_ptr);
 int mb_ipc_close(mb_ctx* ctx, void* d_ptr);
 /* which: 0 seed records, 1 candidate rows, 3 match headers, 4 match components (n = 8-byte words), 5 verdicts (n = bytes) */
 int mb_dist_recv_buffer(mb_ctx* ctx, int which, uint64_t n, void** d_ptr);
-int mb_dist_local(mb_ctx* ctx, const mb_params* params, uint64_t n_recv, uint64_t* h_row_counts, void** d_rows);
+int mb_dist_local(mb_ctx* ctx, const mb_params* params, uint64_t n_recv, uint64_t* h_row_counts);
+/* Last step of stage 2: write the rows in owner order into this rank's send buffer (*d_rows; peer_bases = NULL) or,
+ * fused with exchange 2, straight into the owners' receive buffers 1 over NVLink (peer_bases[d] mapped with
+ * mb_ipc_import, peer_row_offsets[d] = row index of this rank's block in rank d's buffer).  Asynchronous. */
+int mb_dist_rows_pack(mb_ctx* ctx, void* const* peer_bases, const uint64_t* peer_row_offsets, void** d_rows);
 int mb_dist_resolve(mb_ctx* ctx, uint64_t n_rows, void** d_verdict);
 int mb_dist_accept(mb_ctx* ctx, void** d_hist);
-int mb_dist_match_partition(mb_ctx* ctx, uint64_t* h_match_counts, uint64_t* h_comp_counts, void** d_hdr, void** d_comps);
+int mb_dist_match_partition(mb_ctx* ctx, uint64_t* h_match_counts, uint64_t* h_comp_counts);
+/* Last step of stage 3c: write the match rows in destination order into this rank's send buffers (*d_hdr, *d_comps;
+ * bases = NULL) or, fused with exchange 3, into the destination ranks' receive buffers 3 / 4 over NVLink. */
+int mb_dist_match_pack(mb_ctx* ctx, void* const* hdr_bases, const uint64_t* hdr_row_offsets, void* const* comp_bases,
+                       const uint64_t* comp_word_offsets, void** d_hdr, void** d_comps);
 int mb_dist_output(mb_ctx* ctx, uint64_t n_match, uint64_t n_comp);
 /* device ms of this rank's stages of the last run: [0] extract+partition, [1] sort, [2] runs/policy/candidates,
  * [3] extension, [4] chains + resolve; [5..7] reserved (0) */

@@ -185,8 +185,8 @@ int mb_dist_recv_buffer(mb_ctx* c, int which, uint64_t n_words, void** d_ptr) {
 // buffer 0 or the p2p receive array).  Sort / runs / policy -> candidates in ascending seed order; EVERY candidate
 // is extended here (a pure function of the candidate and the replicated genomes), so that only 4-word rows
 // (two group hashes, first component, extents) travel to the owner of the de-dup group — the component lists stay.
-int mb_dist_local(mb_ctx* c, const mb_params* prm, uint64_t n_recv, uint64_t* h_row_counts, void** d_rows) {
-    if (!c || !prm || !h_row_counts || !d_rows) return MB_E_ARG;
+int mb_dist_local(mb_ctx* c, const mb_params* prm, uint64_t n_recv, uint64_t* h_row_counts) {
+    if (!c || !prm || !h_row_counts) return MB_E_ARG;
     if (prm->mode != MB_MODE_UNIQUE) return MB_E_ARG;
     if (n_recv >= (1ull << 31)) return MB_E_TOOLONG;
     CUDA_TRY(c, cudaSetDevice(c->device));
@@ -196,8 +196,8 @@ int mb_dist_local(mb_ctx* c, const mb_params* prm, uint64_t n_recv, uint64_t* h_
     const u32 n = (u32)n_recv;
     u64* scal = c->scalars.as<u64>();
     for (int r = 0; r < world; ++r) h_row_counts[r] = 0;
-    *d_rows = nullptr;
     c->d_ncand = 0; c->d_nccomp = 0;
+    c->d_bound.assign(world + 1, 0); c->d_cbound.assign(world + 1, 0);
     cudaEventRecord(c->ev_d[2], st);
     TRY(c->reserve(c->keysB, ((size_t)n + 8) * 8));
     u64 *kA = c->d_use_p2p ? c->x_recv.as<u64>() : c->keysA.as<u64>(), *kB = c->keysB.as<u64>();
@@ -272,16 +272,52 @@ int mb_dist_local(mb_ctx* c, const mb_params* prm, uint64_t n_recv, uint64_t* h_
     launch_owner_keys(c->ghash.as<u64>(), n_cand, (u32)world, skA, svA, st); LAUNCHED(c);
     const int obits = std::max(1, mbi_bits_for((u64)world - 1));
     TRY(mbi_sort_records(c, &skA, &skB, &svA, &svB, n_cand, 0, obits, false)); // leaves the owner histogram in c->hist
-    launch_pack_rows(svA, n_cand, c->ghash.as<u64>(), c->ghash2.as<u64>(), c->q_off.as<u32>(), c->q_pos.as<u32>(), c->q_gs.as<u8>(), c->gt,
-                     c->q_el.as<u32>(), c->q_er.as<u32>(), c->x_hdr_s.as<u64>(), c->q_perm.as<u32>(), st);
-    LAUNCHED(c); CHECK_LAUNCH(c);
+    c->d_sperm = svA;
     std::vector<u32> oh(256);
     CUDA_TRY(c, cudaMemcpyAsync(oh.data(), c->hist.p, 256 * 4, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(c, cudaStreamSynchronize(st));
     u64 acc = 0;
-    for (int r = 0; r < world; ++r) { h_row_counts[r] = oh[r]; acc += oh[r]; }
+    for (int r = 0; r < world; ++r) { h_row_counts[r] = oh[r]; acc += oh[r]; c->d_bound[r + 1] = acc; }
     if (acc != n_cand) return MB_E_STATE;
-    *d_rows = c->x_hdr_s.p;
+    return MB_OK;
+}
+
+// destination table of a pack kernel -> device (x_peers).  bases == NULL: everything into this rank's own send
+// buffers (the caller's all-to-all moves it); otherwise bases[d] / offsets[d] = rank d's receive buffer mapped
+// into this process and the row (word) index where this rank's block starts in it.
+static int upload_peer_table(mb_ctx* c, void* const* bases, const uint64_t* offs, void* local, void* const* bases2, const uint64_t* offs2, void* local2,
+                             u64 n_rows) {
+    const int world = c->d_world;
+    std::vector<PeerDst> tab(world + 1);
+    for (int d = 0; d <= world; ++d) {
+        PeerDst& t = tab[d];
+        const int e = std::min(d, world - 1);
+        t.bound = (u32)(d < world ? c->d_bound[d] : n_rows);
+        t.cbound = d < world ? c->d_cbound[d] : 0;
+        t.base = (u64*)(bases ? bases[e] : local); t.off = bases ? offs[e] : c->d_bound[e];
+        t.base2 = (u64*)(bases2 ? bases2[e] : local2); t.off2 = bases2 ? offs2[e] : c->d_cbound[e];
+        t.pad = 0;
+    }
+    TRY(c->reserve(c->x_peers, 257 * sizeof(PeerDst)));
+    CUDA_TRY(c, cudaMemcpyAsync(c->x_peers.p, tab.data(), tab.size() * sizeof(PeerDst), cudaMemcpyHostToDevice, c->stream)); // pageable: staged before return
+    return MB_OK;
+}
+
+// stage 2, last step: write the candidate rows in owner order — into this rank's send buffer (*d_rows, for the
+// caller's all-to-all; peer_bases = NULL) or, fused with exchange 2, straight into the owners' receive buffers over
+// NVLink (peer_bases[d] = rank d's receive buffer 1 mapped into this process, peer_row_offsets[d] = row index of this
+// rank's block there).  Asynchronous; with peer stores all ranks must synchronise before stage 3a.
+int mb_dist_rows_pack(mb_ctx* c, void* const* peer_bases, const uint64_t* peer_row_offsets, void** d_rows) {
+    if (!c || (peer_bases && !peer_row_offsets) || (!peer_bases && !d_rows)) return MB_E_ARG;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const u32 n_cand = c->d_ncand;
+    if (d_rows) *d_rows = c->x_hdr_s.p;
+    if (n_cand == 0) return MB_OK;
+    TRY(upload_peer_table(c, peer_bases, peer_row_offsets, c->x_hdr_s.p, nullptr, nullptr, nullptr, n_cand));
+    launch_pack_rows(c->d_sperm, n_cand, c->ghash.as<u64>(), c->ghash2.as<u64>(), c->q_off.as<u32>(), c->q_pos.as<u32>(), c->q_gs.as<u8>(), c->gt,
+                     c->q_el.as<u32>(), c->q_er.as<u32>(), c->x_peers.as<PeerDst>(), (u32)c->d_world, c->q_perm.as<u32>(), st);
+    LAUNCHED(c); CHECK_LAUNCH(c);
     return MB_OK;
 }
 
@@ -359,14 +395,15 @@ int mb_dist_accept(mb_ctx* c, void** d_hist) {
 // stage 3c: *d_hist now holds the histogram summed over all ranks.  Partition the accepted matches by
 // destination = range of the canonical sort key (ranks hold ascending ranges of the final order) and pack
 // their rows; per-destination row / component-word counts go to the host arrays.
-int mb_dist_match_partition(mb_ctx* c, uint64_t* h_match_counts, uint64_t* h_comp_counts, void** d_hdr, void** d_comps) {
-    if (!c || !h_match_counts || !h_comp_counts || !d_hdr || !d_comps) return MB_E_ARG;
+int mb_dist_match_partition(mb_ctx* c, uint64_t* h_match_counts, uint64_t* h_comp_counts) {
+    if (!c || !h_match_counts || !h_comp_counts) return MB_E_ARG;
     CUDA_TRY(c, cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
     const int world = c->d_world;
     const u32 n_match = c->d_nmatch;
     for (int r = 0; r < world; ++r) { h_match_counts[r] = 0; h_comp_counts[r] = 0; }
-    *d_hdr = nullptr; *d_comps = nullptr;
+    c->d_bound.assign(world + 1, 0); c->d_cbound.assign(world + 1, 0);
+    c->d_nmcomp = 0;
     // destination of every key bin: equal shares of the global match count, whole bins
     std::vector<u64> gh(4096);
     CUDA_TRY(c, cudaMemcpyAsync(gh.data(), c->x_counts.p, 4096 * 8, cudaMemcpyDeviceToHost, st));
@@ -398,21 +435,36 @@ int mb_dist_match_partition(mb_ctx* c, uint64_t* h_match_counts, uint64_t* h_com
     u64 n_mcomp = 0;
     CUDA_TRY(c, cudaMemcpyAsync(&n_mcomp, c->out_off.as<u64>() + n_match, 8, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(c, cudaStreamSynchronize(st));
-    std::vector<u64> bound(world + 1, 0);
     u64 acc = 0;
-    for (int r = 0; r < world; ++r) { h_match_counts[r] = oh[r]; acc += oh[r]; bound[r + 1] = acc; }
+    for (int r = 0; r < world; ++r) { h_match_counts[r] = oh[r]; acc += oh[r]; c->d_bound[r + 1] = acc; }
     if (acc != n_match) return MB_E_STATE;
-    std::vector<u64> cb(world + 1, 0);
-    for (int r = 1; r <= world; ++r) CUDA_TRY(c, cudaMemcpyAsync(&cb[r], c->out_off.as<u64>() + bound[r], 8, cudaMemcpyDeviceToHost, st));
-    TRY(c->reserve(c->x_hdr_s, ((size_t)n_match + 8) * 16));
-    TRY(c->reserve(c->x_comp_s, ((size_t)n_mcomp + 8) * 8));
-    launch_pack_match_perm(svA, c->x_item.as<u32>(), c->q_item.as<u32>(), c->out_off.as<u64>(), c->q_off.as<u32>(), c->q_pos.as<u32>(),
-                           c->q_gs.as<u8>(), c->q_el.as<u32>(), c->q_er.as<u32>(), n_match, c->x_hdr_s.as<u64>(), c->x_comp_s.as<u64>(), st);
-    LAUNCHED(c); CHECK_LAUNCH(c);
+    for (int r = 1; r <= world; ++r) CUDA_TRY(c, cudaMemcpyAsync(&c->d_cbound[r], c->out_off.as<u64>() + c->d_bound[r], 8, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(c, cudaStreamSynchronize(st));
-    for (int r = 0; r < world; ++r) h_comp_counts[r] = cb[r + 1] - cb[r];
+    for (int r = 0; r < world; ++r) h_comp_counts[r] = c->d_cbound[r + 1] - c->d_cbound[r];
     c->d_nmcomp = (u32)n_mcomp;
-    *d_hdr = c->x_hdr_s.p; *d_comps = c->x_comp_s.p;
+    c->d_sperm = svA;
+    return MB_OK;
+}
+
+// stage 3c, last step: write the match rows in destination order — into this rank's send buffers (*d_hdr, *d_comps;
+// bases = NULL) or, fused with exchange 3, into the destination ranks' receive buffers 3 / 4 over NVLink
+// (hdr_row_offsets[d] / comp_word_offsets[d] = where this rank's block starts there).  Asynchronous.
+int mb_dist_match_pack(mb_ctx* c, void* const* hdr_bases, const uint64_t* hdr_row_offsets, void* const* comp_bases, const uint64_t* comp_word_offsets,
+                       void** d_hdr, void** d_comps) {
+    const bool peers = hdr_bases != nullptr;
+    if (!c || (peers && (!hdr_row_offsets || !comp_bases || !comp_word_offsets)) || (!peers && (!d_hdr || !d_comps))) return MB_E_ARG;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const u32 n_match = c->d_nmatch;
+    TRY(c->reserve(c->x_hdr_s, ((size_t)n_match + 8) * 16));
+    TRY(c->reserve(c->x_comp_s, ((size_t)c->d_nmcomp + 8) * 8));
+    if (d_hdr) *d_hdr = c->x_hdr_s.p;
+    if (d_comps) *d_comps = c->x_comp_s.p;
+    if (n_match == 0) return MB_OK;
+    TRY(upload_peer_table(c, hdr_bases, hdr_row_offsets, c->x_hdr_s.p, comp_bases, comp_word_offsets, c->x_comp_s.p, n_match));
+    launch_pack_match_perm(c->d_sperm, c->x_item.as<u32>(), c->q_item.as<u32>(), c->out_off.as<u64>(), c->q_off.as<u32>(), c->q_pos.as<u32>(),
+                           c->q_gs.as<u8>(), c->q_el.as<u32>(), c->q_er.as<u32>(), n_match, c->x_peers.as<PeerDst>(), (u32)c->d_world, st);
+    LAUNCHED(c); CHECK_LAUNCH(c);
     return MB_OK;
 }
 

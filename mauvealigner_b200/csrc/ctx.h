@@ -44,6 +44,8 @@ struct mb_ctx {
     DBuf x_lut, x_counts, x_hdr_s, x_comp_s, x_hdr_r, x_comp_r, x_m, x_key, x_item, x_peers, x_recv; // multi-GPU exchange buffers (api_dist.cu)
     // source-side candidate arrays of the distributed path: they must outlive the owner stage that runs in between
     DBuf q_off, q_pos, q_gs, q_el, q_er, q_perm, q_state, q_item, x_acc_s, x_acc_r;
+    const u64* d_sperm = nullptr;           // partition order of the rows being packed (between the count and the pack call)
+    std::vector<u64> d_bound, d_cbound;     // rows / component words before every destination's block
     int d_rank = 0, d_world = 1;
     u32 d_nslice = 0;
     bool d_use_p2p = false;

@@ -147,14 +147,19 @@ void launch_unpack_match(const u64* hdr, const u64* comps, const u32* cand_off, 
                          u8* state, u32* item_cand, cudaStream_t st);
 void launch_match_keys(const u8* state, const u32* item_cand, const u32* match_idx, const u32* cand_off, const u8* comp_gs, const u32* comp_pos,
                        const u32* ext_l, u32 n_items, int sbits, int binshift, u64* key, u32* item_of, u64* hist, cudaStream_t st);
+// Destination table of a pack kernel (device memory, world + 1 entries, entry `world` is the sentinel with
+// bound = number of rows): the rows [bound[d], bound[d+1]) of the partition order go to rank d — into `base`
+// (this rank's own send buffer, or rank d's receive buffer mapped over NVLink) at row `off` + (row - bound);
+// base2 / off2 / cbound: the same for the component words of the match rows.
+struct PeerDst { u64* base; u64 off; u64* base2; u64 off2; u64 cbound; u32 bound; u32 pad; };
 // 4-word candidate rows of the extend-at-source protocol: [group hash, second hash, g0 | vg << 8 | m << 24 | p0 << 32,
 // ext_l | ext_r << 32], written in partition (owner) order; perm_out[j] = candidate of row j
 void launch_pack_rows(const u64* perm, u32 n, const u64* ghash, const u64* ghash2, const u32* cand_off, const u32* comp_pos, const u8* comp_gs,
-                      const GenomeTable& gt, const u32* ext_l, const u32* ext_r, u64* rows, u32* perm_out, cudaStream_t st);
+                      const GenomeTable& gt, const u32* ext_l, const u32* ext_r, const PeerDst* tab, u32 world, u32* perm_out, cudaStream_t st);
 void launch_rows_bitmap(const u64* rows, u32 n, const GenomeTable& gt, u64* bitmap, cudaStream_t st);
 void launch_accept_mark(const u8* rstate, const u32* s_cand, u32 n_rep, u8* acc, cudaStream_t st);
 void launch_apply_accept(const u8* acc, const u32* perm, u32 n, u8* state, u32* item_cand, cudaStream_t st);
 void launch_dest_keys(const u64* key, u32 n, int binshift, const u8* lut, u64* skey, u64* sval, cudaStream_t st);
 void launch_match_perm_m(const u64* perm, const u32* item_of, const u32* item_cand, const u32* cand_off, u32 n, u32* m_out, cudaStream_t st);
 void launch_pack_match_perm(const u64* perm, const u32* item_of, const u32* item_cand, const u64* poff, const u32* cand_off, const u32* comp_pos,
-                            const u8* comp_gs, const u32* ext_l, const u32* ext_r, u32 n, u64* hdr, u64* comps, cudaStream_t st);
+                            const u8* comp_gs, const u32* ext_l, const u32* ext_r, u32 n, const PeerDst* tab, u32 world, cudaStream_t st);

@@ -82,25 +82,37 @@ void launch_unpack_match(const u64* hdr, const u64* comps, const u32* cand_off, 
                                                                  state, item_cand);
 }
 
+// destination rank of row j: the last d with bound[d] <= j (world + 1 entries, the last one is the sentinel)
+__device__ __forceinline__ u32 dest_of(const PeerDst* __restrict__ tab, u32 world, u32 j) {
+    u32 lo = 0, hi = world; // invariant: bound[lo] <= j < bound[hi]
+    while (hi - lo > 1) {
+        u32 mid = (lo + hi) >> 1;
+        if (tab[mid].bound <= j) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
 // ---- extend-at-source protocol: 4-word candidate rows (the extents travel, the component lists stay at the source)
 __global__ void __launch_bounds__(256) k_pack_rows(const u64* __restrict__ perm, u32 n, const u64* __restrict__ ghash, const u64* __restrict__ ghash2,
                                                    const u32* __restrict__ cand_off, const u32* __restrict__ comp_pos, const u8* __restrict__ comp_gs,
                                                    GenomeTable gt, const u32* __restrict__ ext_l, const u32* __restrict__ ext_r,
-                                                   ulonglong2* __restrict__ rows, u32* __restrict__ perm_out) {
+                                                   const PeerDst* __restrict__ tab, u32 world, u32* __restrict__ perm_out) {
     u32 j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
+    const PeerDst dst = tab[dest_of(tab, world, j)];
+    ulonglong2* rows = reinterpret_cast<ulonglong2*>(dst.base); // this rank's send buffer or, fused with exchange 2, a peer's receive buffer
+    const size_t rj = (size_t)dst.off + (j - dst.bound);
     const u32 c = (u32)perm[j];
     const u32 off = cand_off[c], m = cand_off[c + 1] - off;
     const u32 g0 = comp_gs[off] & 0x7F;
     const u32 vg = vgenome(gt, g0, comp_gs[off + 1] & 0x7F);
-    rows[2 * (size_t)j] = make_ulonglong2(ghash[c], ghash2[c]);
-    rows[2 * (size_t)j + 1] = make_ulonglong2((u64)g0 | ((u64)vg << 8) | ((u64)m << 24) | ((u64)comp_pos[off] << 32), (u64)ext_l[c] | ((u64)ext_r[c] << 32));
+    rows[2 * rj] = make_ulonglong2(ghash[c], ghash2[c]);
+    rows[2 * rj + 1] = make_ulonglong2((u64)g0 | ((u64)vg << 8) | ((u64)m << 24) | ((u64)comp_pos[off] << 32), (u64)ext_l[c] | ((u64)ext_r[c] << 32));
     perm_out[j] = c;
 }
 void launch_pack_rows(const u64* perm, u32 n, const u64* ghash, const u64* ghash2, const u32* cand_off, const u32* comp_pos, const u8* comp_gs,
-                      const GenomeTable& gt, const u32* ext_l, const u32* ext_r, u64* rows, u32* perm_out, cudaStream_t st) {
-    if (n) k_pack_rows<<<div_up(n, 256), 256, 0, st>>>(perm, n, ghash, ghash2, cand_off, comp_pos, comp_gs, gt, ext_l, ext_r,
-                                                      reinterpret_cast<ulonglong2*>(rows), perm_out);
+                      const GenomeTable& gt, const u32* ext_l, const u32* ext_r, const PeerDst* tab, u32 world, u32* perm_out, cudaStream_t st) {
+    if (n) k_pack_rows<<<div_up(n, 256), 256, 0, st>>>(perm, n, ghash, ghash2, cand_off, comp_pos, comp_gs, gt, ext_l, ext_r, tab, world, perm_out);
 }
 
 // owner: one bit per received candidate at (virtual genome, position) — the slot axis of the chains
@@ -192,31 +204,32 @@ void launch_match_perm_m(const u64* perm, const u32* item_of, const u32* item_ca
 }
 
 // lane = row for the header; the component words of the warp's 32 rows are copied by all lanes together
-// (coalesced on both sides)
+// (coalesced on both sides).  Destinations through the PeerDst table: the local send buffers or, fused with
+// exchange 3, the destination ranks' receive buffers over NVLink.
 __global__ void __launch_bounds__(256) k_pack_match_perm(const u64* __restrict__ perm, const u32* __restrict__ item_of, const u32* __restrict__ item_cand,
                                                          const u64* __restrict__ poff, const u32* __restrict__ cand_off, const u32* __restrict__ comp_pos,
                                                          const u8* __restrict__ comp_gs, const u32* __restrict__ ext_l, const u32* __restrict__ ext_r, u32 n,
-                                                         ulonglong2* __restrict__ hdr, u64* __restrict__ comps) {
+                                                         const PeerDst* __restrict__ tab, u32 world) {
     const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
     const u32 lane = threadIdx.x & 31;
     u32 off = 0, m = 0;
-    u64 o = 0;
+    u64* o = nullptr;
     if (t < n) {
         const u32 c = item_cand[item_of[(u32)perm[t]]];
         off = cand_off[c]; m = cand_off[c + 1] - off;
-        hdr[t] = make_ulonglong2((u64)ext_l[c] | ((u64)ext_r[c] << 32), m);
-        o = poff[t];
+        const PeerDst dst = tab[dest_of(tab, world, t)];
+        reinterpret_cast<ulonglong2*>(dst.base)[dst.off + t - dst.bound] = make_ulonglong2((u64)ext_l[c] | ((u64)ext_r[c] << 32), m);
+        o = dst.base2 + dst.off2 + (poff[t] - dst.cbound);
     }
     for (int j = 0; j < 32; ++j) {
         const u32 mj = __shfl_sync(0xFFFFFFFFu, m, j);
         if (mj == 0) continue; // uniform
         const u32 offj = __shfl_sync(0xFFFFFFFFu, off, j);
-        const u64 oj = __shfl_sync(0xFFFFFFFFu, o, j);
-        for (u32 k = lane; k < mj; k += 32) comps[oj + k] = (u64)comp_pos[offj + k] | ((u64)comp_gs[offj + k] << 32);
+        u64* oj = reinterpret_cast<u64*>(__shfl_sync(0xFFFFFFFFu, reinterpret_cast<unsigned long long>(o), j));
+        for (u32 k = lane; k < mj; k += 32) oj[k] = (u64)comp_pos[offj + k] | ((u64)comp_gs[offj + k] << 32);
     }
 }
 void launch_pack_match_perm(const u64* perm, const u32* item_of, const u32* item_cand, const u64* poff, const u32* cand_off, const u32* comp_pos,
-                            const u8* comp_gs, const u32* ext_l, const u32* ext_r, u32 n, u64* hdr, u64* comps, cudaStream_t st) {
-    if (n) k_pack_match_perm<<<div_up(n, 256), 256, 0, st>>>(perm, item_of, item_cand, poff, cand_off, comp_pos, comp_gs, ext_l, ext_r, n,
-                                                            reinterpret_cast<ulonglong2*>(hdr), comps);
+                            const u8* comp_gs, const u32* ext_l, const u32* ext_r, u32 n, const PeerDst* tab, u32 world, cudaStream_t st) {
+    if (n) k_pack_match_perm<<<div_up(n, 256), 256, 0, st>>>(perm, item_of, item_cand, poff, cand_off, comp_pos, comp_gs, ext_l, ext_r, n, tab, world);
 }

@@ -67,15 +67,14 @@ class LocalFabric:
     def barrier(self):
         pass  # one process, one stream
 
-    def peer_arrays(self, ctxs, capacity):
-        """Every rank's fixed receive array for the fused exchange #1, addressable from every rank: here plain pointers."""
-        if getattr(self, "_p2p_cap", -1) < capacity:
-            self._p2p_ptrs = [c.dist_p2p_recv_array(capacity) for c in ctxs]
-            self._p2p_cap = capacity
-        return [self._p2p_ptrs for _ in ctxs]
+    def peer_buffers(self, ctxs, key, need):
+        """The receive buffer `key` ("seed" records, "hdr" row words, "comp" component words) of every rank, addressable
+        from every rank: here plain pointers of one process.  need[d] = units rank d must hold."""
+        ptrs = [_alloc_recv(c, key, n) for c, n in zip(ctxs, need)]
+        return [ptrs for _ in ctxs]
 
-    def release_peer_arrays(self, ctxs):
-        self._p2p_cap = -1
+    def release_peer_buffers(self, ctxs):
+        pass
 
     def allreduce_sum(self, tensors):
         total = tensors[0].clone()
@@ -127,31 +126,42 @@ class TorchFabric:
             self._token = torch.zeros(1, dtype=torch.int64, device=self.device)
         self.dist.all_reduce(self._token, group=self.group)
 
-    def peer_arrays(self, ctxs, capacity):
-        """Every rank's fixed receive array for the fused exchange #1, mapped into this process through CUDA IPC
-        (NVLink peer access).  Collective; re-done only when the capacity grows."""
-        if getattr(self, "_p2p_cap", -1) >= capacity:
-            return [self._p2p_ptrs]
-        self.release_peer_arrays(ctxs)
+    def peer_buffers(self, ctxs, key, need):
+        """The receive buffer `key` ("seed" records, "hdr" row words, "comp" component words) of every rank, mapped into
+        this process through CUDA IPC (NVLink peer access).  need[d] = units rank d must hold — known to every rank from
+        the count matrix, so all ranks take the same decision without talking: the mapping is redone (collectively)
+        only when some rank's need outgrows the capacity it exported."""
+        pb = self.__dict__.setdefault("_pb", {})
+        st = pb.setdefault(key, dict(cap=[-1] * self.world, ptrs=None))
+        if st["ptrs"] is not None and all(n <= cp for n, cp in zip(need, st["cap"])):
+            return [st["ptrs"]]
         c = ctxs[0]
-        mine = c.dist_p2p_recv_array(capacity)
+        self._unmap(c, st)
+        st["cap"] = [max(cp, n + n // 8 + 4096) for n, cp in zip(need, st["cap"])]
+        mine = _alloc_recv(c, key, st["cap"][self.rank])
         h = torch.frombuffer(bytearray(c.ipc_export(mine)), dtype=torch.uint8).to(self.device)
         out = [torch.empty_like(h) for _ in range(self.world)]
         self.dist.all_gather(out, h, group=self.group)
-        self._p2p_ptrs = [mine if r == self.rank else c.ipc_import(bytes(out[r].cpu().numpy().tobytes())) for r in range(self.world)]
-        self._p2p_cap = capacity
-        return [self._p2p_ptrs]
+        st["ptrs"] = [mine if r == self.rank else c.ipc_import(out[r].cpu().numpy().tobytes()) for r in range(self.world)]
+        return [st["ptrs"]]
 
-    def release_peer_arrays(self, ctxs):
-        """Unmap the peers' arrays (before any rank frees or regrows its own); collective."""
-        if getattr(self, "_p2p_cap", -1) >= 0:
-            for r, p in enumerate(self._p2p_ptrs):
+    def _unmap(self, c, st):
+        # unmap the peers' buffers before any rank frees or regrows its own
+        if st["ptrs"] is not None:
+            for r, p in enumerate(st["ptrs"]):
                 if r != self.rank:
-                    ctxs[0].ipc_close(p)
-            self._p2p_cap = -1
-            self._p2p_ptrs = None
-            torch.cuda.synchronize(self.device)
-            self.dist.barrier(group=self.group)
+                    c.ipc_close(p)
+            st["ptrs"] = None
+        torch.cuda.synchronize(self.device)
+        self.dist.barrier(group=self.group)
+
+    def release_peer_buffers(self, ctxs):
+        """Collective: unmap every peer buffer (before the contexts are destroyed)."""
+        for key in sorted(self.__dict__.get("_pb", {})):
+            st = self._pb[key]
+            if st["ptrs"] is not None:
+                self._unmap(ctxs[0], st)
+            st["cap"] = [-1] * self.world
 
     def allreduce_sum(self, tensors):
         self.dist.all_reduce(tensors[0], group=self.group)
@@ -159,6 +169,12 @@ class TorchFabric:
     def words(self, sends, send_counts, recvs, recv_counts, width=1):
         self.dist.all_to_all_single(recvs[0], sends[0], [c * width for c in recv_counts[0]], [c * width for c in send_counts[0]],
                                     group=self.group)
+
+
+def _alloc_recv(ctx, key, n):
+    if key == "seed":
+        return ctx.dist_p2p_recv_array(n)
+    return ctx.dist_recv_buffer(1 if key == "hdr" else 4, n)
 
 
 def p2p_default():
@@ -169,7 +185,9 @@ def find_unique(ctxs, fabric, device, nway_mask=0, p2p=None):
     """MODE_UNIQUE over the ranks of `fabric`; ctxs[i] is the library context of fabric.local_ranks[i] (sequences and
     seed already set, identical on every rank).  Leaves every rank's piece of the canonical match CSR on its device
     (fetch it with ctxs[...].fetch()); returns per-local-rank info dicts.
-    p2p: exchange #1 fused into the partition kernel (peer stores over NVLink) instead of an all-to-all."""
+    p2p: exchanges #1, #2 and #3 fused into the kernels that produce the data (the partition pass / the row pack
+    kernels store straight into the destination ranks' receive buffers over NVLink; the ranks share the count matrix
+    first and meet at a stream-ordered barrier afterwards) instead of NCCL all-to-alls of local send buffers."""
     W, R = fabric.world, fabric.local_ranks
     if p2p is None:
         p2p = p2p_default()
@@ -190,8 +208,7 @@ def find_unique(ctxs, fabric, device, nway_mask=0, p2p=None):
         sc = [c.dist_extract_count(r, W) for c, r in zip(ctxs, R)]
         mark("stage1a extract+count")
         M = fabric.gather_counts(sc)
-        need = max(sum(M[s][d] for s in range(W)) for d in range(W))
-        peers = fabric.peer_arrays(ctxs, need + need // 8 + 4096)
+        peers = fabric.peer_buffers(ctxs, "seed", [sum(M[s][d] for s in range(W)) for d in range(W)])
         for c, r, pp in zip(ctxs, R, peers):
             c.dist_partition_p2p(pp, [sum(M[s][d] for s in range(r)) for d in range(W)])
         fabric.barrier()
@@ -213,14 +230,22 @@ def find_unique(ctxs, fabric, device, nway_mask=0, p2p=None):
     for i, k in enumerate(rc):
         info[i]["seeds_sent"], info[i]["seeds_received"] = sum(sc[i]), sum(k)
     # ---- stage 2 + exchange 2: every candidate extended at its source; 4-word rows to the owner of the de-dup group
-    s2 = [c.dist_local(W, sum(k), nway_mask=nway_mask) for c, k in zip(ctxs, rc)]
-    mark("stage2 sort+buckets+extend+rows")
-    scc = [cc for _, cc in s2]
-    rcc = fabric.counts(scc)
-    rs = [dev_words(p, 4 * sum(cc), device) for p, cc in s2]
-    rr = [dev_words(c.dist_recv_buffer(1, 4 * sum(k)), 4 * sum(k), device) for c, k in zip(ctxs, rcc)]
-    fabric.words(rs, scc, rr, rcc, width=4)
-    mark("exchange2 candidate rows")
+    scc = [c.dist_local(W, sum(k), nway_mask=nway_mask) for c, k in zip(ctxs, rc)]
+    mark("stage2 sort+buckets+extend")
+    if p2p:
+        M2 = fabric.gather_counts(scc)
+        peers = fabric.peer_buffers(ctxs, "hdr", [4 * sum(M2[s][d] for s in range(W)) for d in range(W)])
+        for c, r, pp in zip(ctxs, R, peers):
+            c.dist_rows_pack(pp, [sum(M2[s][d] for s in range(r)) for d in range(W)])
+        fabric.barrier()
+        rcc = [[M2[s][r] for s in range(W)] for r in R]
+        mark("rows packed into the owners' buffers")
+    else:
+        rs = [dev_words(c.dist_rows_pack(), 4 * sum(cc), device) for c, cc in zip(ctxs, scc)]
+        rcc = fabric.counts(scc)
+        rr = [dev_words(c.dist_recv_buffer(1, 4 * sum(k)), 4 * sum(k), device) for c, k in zip(ctxs, rcc)]
+        fabric.words(rs, scc, rr, rcc, width=4)
+        mark("rows + exchange2")
     for i in range(len(R)):
         info[i]["candidates_local"], info[i]["candidates_owned"] = sum(scc[i]), sum(rcc[i])
     # ---- stage 3a (owner): chains / resolve; one verdict byte per row goes back to the row's source
@@ -233,20 +258,34 @@ def find_unique(ctxs, fabric, device, nway_mask=0, p2p=None):
     hists = [c.dist_accept() for c in ctxs]
     fabric.allreduce_sum([dev_words(p, 4096, device) for p in hists])
     s3 = [c.dist_match_partition(W) for c in ctxs]
-    mark("stage3b match rows")
-    both = fabric.counts([[x for pair in zip(cc, mc) for x in pair] for _, _, cc, mc in s3])
-    gcc = [b[0::2] for b in both]
-    gmc = [b[1::2] for b in both]
-    hs = [dev_words(h, 2 * sum(cc), device) for h, _, cc, _ in s3]
-    ms = [dev_words(m, sum(mc), device) for _, m, _, mc in s3]
-    hr = [dev_words(c.dist_recv_buffer(3, 2 * sum(k)), 2 * sum(k), device) for c, k in zip(ctxs, gcc)]
-    mr = [dev_words(c.dist_recv_buffer(4, sum(k)), sum(k), device) for c, k in zip(ctxs, gmc)]
-    fabric.words(hs, [cc for _, _, cc, _ in s3], hr, gcc, width=2)
-    fabric.words(ms, [mc for _, _, _, mc in s3], mr, gmc)
-    mark("exchange3 match rows")
+    mark("stage3b matches")
+    pairs = [[x for pair in zip(cc, mc) for x in pair] for cc, mc in s3]
+    if p2p:
+        M3 = fabric.gather_counts(pairs)
+        ph = fabric.peer_buffers(ctxs, "hdr", [2 * sum(M3[s][2 * d] for s in range(W)) for d in range(W)])
+        pc = fabric.peer_buffers(ctxs, "comp", [sum(M3[s][2 * d + 1] for s in range(W)) for d in range(W)])
+        for c, r, hh, cc_ in zip(ctxs, R, ph, pc):
+            c.dist_match_pack(hh, [sum(M3[s][2 * d] for s in range(r)) for d in range(W)],
+                              cc_, [sum(M3[s][2 * d + 1] for s in range(r)) for d in range(W)])
+        fabric.barrier()
+        gcc = [[M3[s][2 * r] for s in range(W)] for r in R]
+        gmc = [[M3[s][2 * r + 1] for s in range(W)] for r in R]
+        mark("match rows packed into the destinations' buffers")
+    else:
+        both = fabric.counts(pairs)
+        gcc = [b[0::2] for b in both]
+        gmc = [b[1::2] for b in both]
+        packed = [c.dist_match_pack() for c in ctxs]
+        hs = [dev_words(h, 2 * sum(cc), device) for (h, _), (cc, _mc) in zip(packed, s3)]
+        ms = [dev_words(m, sum(mc), device) for (_, m), (_cc, mc) in zip(packed, s3)]
+        hr = [dev_words(c.dist_recv_buffer(3, 2 * sum(k)), 2 * sum(k), device) for c, k in zip(ctxs, gcc)]
+        mr = [dev_words(c.dist_recv_buffer(4, sum(k)), sum(k), device) for c, k in zip(ctxs, gmc)]
+        fabric.words(hs, [cc for cc, _ in s3], hr, gcc, width=2)
+        fabric.words(ms, [mc for _, mc in s3], mr, gmc)
+        mark("match rows + exchange3")
     # ---- stage 4: every rank builds the canonical CSR of its range
     for i in range(len(R)):
-        info[i]["matches_accepted"] = sum(s3[i][2])
+        info[i]["matches_accepted"] = sum(s3[i][0])
         ctxs[i].dist_output(sum(gcc[i]), sum(gmc[i]))
         info[i]["matches"] = sum(gcc[i])
     mark("stage4 output")
@@ -422,7 +461,7 @@ def bench_main(args, CONFIG_NAMES, config_params, peaks, ClockSampler):
             "rank0": {k: v for k, v in info[0].items()}, "wall_ms_per_step": wall_ms / args.steps, "clocks": sampler.summary(),
         }
         print(json.dumps(line), flush=True)
-    fabric.release_peer_arrays([ctx])
+    fabric.release_peer_buffers([ctx])
     ctx.close()
     dist.barrier()
     dist.destroy_process_group()

@@ -168,12 +168,29 @@ class Context:
         return ptr.value or 0
 
     def dist_local(self, world, n_recv, mode=L.MODE_UNIQUE, nway_mask=0):
-        """stage 2 -> (pointer of the 4-word candidate rows grouped by owner, rows per owner)"""
+        """stage 2 -> candidate rows per owner rank (the rows are written by dist_rows_pack)"""
         p = self._params(mode, 2, 1000, False, nway_mask)
-        rows = C.c_void_p()
         cc = (C.c_uint64 * world)()
-        _check(self._h, L.lib().mb_dist_local(self._h, C.byref(p), int(n_recv), cc, C.byref(rows)))
-        return rows.value or 0, [int(x) for x in cc]
+        _check(self._h, L.lib().mb_dist_local(self._h, C.byref(p), int(n_recv), cc))
+        return [int(x) for x in cc]
+
+    @staticmethod
+    def _ptr_array(ptrs):
+        return (C.c_void_p * len(ptrs))(*[C.c_void_p(int(p)) for p in ptrs])
+
+    @staticmethod
+    def _u64_array(vals):
+        return (C.c_uint64 * len(vals))(*[int(v) for v in vals])
+
+    def dist_rows_pack(self, peer_ptrs=None, peer_row_offsets=None):
+        """-> device pointer of the 4-word rows in owner order (local send buffer), or None after storing them straight
+        into the owners' receive buffers (peer_ptrs[d], at row peer_row_offsets[d]) over NVLink"""
+        if peer_ptrs is None:
+            rows = C.c_void_p()
+            _check(self._h, L.lib().mb_dist_rows_pack(self._h, None, None, C.byref(rows)))
+            return rows.value or 0
+        _check(self._h, L.lib().mb_dist_rows_pack(self._h, self._ptr_array(peer_ptrs), self._u64_array(peer_row_offsets), None))
+        return None
 
     def dist_resolve(self, n_rows):
         """stage 3a (owner) -> device pointer of one verdict byte per received row (1 accepted)"""
@@ -188,12 +205,22 @@ class Context:
         return hist.value or 0
 
     def dist_match_partition(self, world):
-        """after the histogram has been summed over the ranks in place
-        -> (headers pointer, components pointer, rows per destination, component words per destination)"""
-        hdr, comps = C.c_void_p(), C.c_void_p()
+        """after the histogram has been summed over the ranks in place -> (match rows per destination, component words
+        per destination); the rows are written by dist_match_pack"""
         cc, mc = (C.c_uint64 * world)(), (C.c_uint64 * world)()
-        _check(self._h, L.lib().mb_dist_match_partition(self._h, cc, mc, C.byref(hdr), C.byref(comps)))
-        return hdr.value or 0, comps.value or 0, [int(x) for x in cc], [int(x) for x in mc]
+        _check(self._h, L.lib().mb_dist_match_partition(self._h, cc, mc))
+        return [int(x) for x in cc], [int(x) for x in mc]
+
+    def dist_match_pack(self, hdr_ptrs=None, hdr_offsets=None, comp_ptrs=None, comp_offsets=None):
+        """-> (headers pointer, components pointer) of the local send buffers, or None after storing the rows straight
+        into the destinations' receive buffers over NVLink"""
+        if hdr_ptrs is None:
+            hdr, comps = C.c_void_p(), C.c_void_p()
+            _check(self._h, L.lib().mb_dist_match_pack(self._h, None, None, None, None, C.byref(hdr), C.byref(comps)))
+            return hdr.value or 0, comps.value or 0
+        _check(self._h, L.lib().mb_dist_match_pack(self._h, self._ptr_array(hdr_ptrs), self._u64_array(hdr_offsets), self._ptr_array(comp_ptrs),
+                                                   self._u64_array(comp_offsets), None, None))
+        return None
 
     def dist_output(self, n_match, n_comp):
         _check(self._h, L.lib().mb_dist_output(self._h, int(n_match), int(n_comp)))

@@ -45,7 +45,7 @@ def main():
         print(f"DIST_CHECK world={world} config=C{config}/{scale} matches={got['n_matches']} pieces={[p['n_matches'] for p in pieces]} "
               f"{'OK bit-exact vs single-GPU path' if ok else 'MISMATCH'}", flush=True)
     dist.barrier()
-    fabric.release_peer_arrays([ctx])
+    fabric.release_peer_buffers([ctx])
     ctx.close()
     dist.destroy_process_group()
 
