@@ -23,6 +23,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"  # keeps NCCL's version banner out of stdout: the bench prints ONE JSON line there
 
 CONFIG_NAMES = {
     1: "C1 mauveAligner 2 x 5 Mbp, weight-15 spaced seed, MODE_UNIQUE",

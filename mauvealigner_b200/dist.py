@@ -178,19 +178,26 @@ def _alloc_recv(ctx, key, n):
 
 
 def p2p_default():
-    return os.environ.get("MB_DIST_P2P", "1") != "0"
+    """MB_DIST_P2P: 0 = every exchange is an NCCL all-to-all of a local send buffer; 1 (default) = exchange 1 (seed
+    records, the largest) is fused into the partition kernel as NVLink peer stores; 2 = exchanges 2 and 3 (candidate
+    rows, match rows) too.  Measured at 8 x B200 on C5: level 1 is the fastest — the partition pass keeps enough
+    stores in flight to beat the all-to-all (0.9 vs 2.4 ms), the gather-bound row pack kernels do not (rows 1.05 vs
+    0.6 ms, match rows 1.6 vs 1.2 ms), so level 2 stays an option, not the default."""
+    return int(os.environ.get("MB_DIST_P2P", "1"))
 
 
 def find_unique(ctxs, fabric, device, nway_mask=0, p2p=None):
     """MODE_UNIQUE over the ranks of `fabric`; ctxs[i] is the library context of fabric.local_ranks[i] (sequences and
     seed already set, identical on every rank).  Leaves every rank's piece of the canonical match CSR on its device
     (fetch it with ctxs[...].fetch()); returns per-local-rank info dicts.
-    p2p: exchanges #1, #2 and #3 fused into the kernels that produce the data (the partition pass / the row pack
-    kernels store straight into the destination ranks' receive buffers over NVLink; the ranks share the count matrix
-    first and meet at a stream-ordered barrier afterwards) instead of NCCL all-to-alls of local send buffers."""
+    p2p (see p2p_default): 1 = exchange #1 fused into the partition pass, 2 = exchanges #2 and #3 fused into the row
+    pack kernels as well (the kernels store straight into the destination ranks' receive buffers over NVLink; the
+    ranks share the count matrix first and meet at a stream-ordered barrier afterwards), 0 = NCCL all-to-alls of
+    local send buffers only."""
     W, R = fabric.world, fabric.local_ranks
     if p2p is None:
         p2p = p2p_default()
+    p2p = int(p2p)
     info = [dict(rank=r) for r in R]
     trace = os.environ.get("MB_DIST_TRACE")
     marks = []
@@ -232,7 +239,7 @@ def find_unique(ctxs, fabric, device, nway_mask=0, p2p=None):
     # ---- stage 2 + exchange 2: every candidate extended at its source; 4-word rows to the owner of the de-dup group
     scc = [c.dist_local(W, sum(k), nway_mask=nway_mask) for c, k in zip(ctxs, rc)]
     mark("stage2 sort+buckets+extend")
-    if p2p:
+    if p2p >= 2:
         M2 = fabric.gather_counts(scc)
         peers = fabric.peer_buffers(ctxs, "hdr", [4 * sum(M2[s][d] for s in range(W)) for d in range(W)])
         for c, r, pp in zip(ctxs, R, peers):
@@ -260,7 +267,7 @@ def find_unique(ctxs, fabric, device, nway_mask=0, p2p=None):
     s3 = [c.dist_match_partition(W) for c in ctxs]
     mark("stage3b matches")
     pairs = [[x for pair in zip(cc, mc) for x in pair] for cc, mc in s3]
-    if p2p:
+    if p2p >= 2:
         M3 = fabric.gather_counts(pairs)
         ph = fabric.peer_buffers(ctxs, "hdr", [2 * sum(M3[s][2 * d] for s in range(W)) for d in range(W)])
         pc = fabric.peer_buffers(ctxs, "comp", [sum(M3[s][2 * d + 1] for s in range(W)) for d in range(W)])

@@ -29,12 +29,13 @@ def test_emulated_world_matches_oracle(world):
 
 
 def test_emulated_world_nccl_style_exchange1():
-    """exchange 1 as a separate all-to-all of a local send buffer (p2p=False) gives the same result as the fused one"""
+    """all-to-alls of local send buffers (0), exchange 1 fused into the partition pass (1), exchanges 2 / 3 fused into
+    the pack kernels too (2): same result"""
     from mauvealigner_b200 import dist
     rng = np.random.default_rng(77)
     seqs = family(rng, 30000, 4, sub=0.03, indel=0.002, inv=1)
     want = O.find(seqs, 0b1101110111110111011, O.MODE_UNIQUE)
-    for p2p in (False, True):
+    for p2p in (0, 1, 2):
         got = dist.find_unique_emulated(seqs, 0b1101110111110111011, 3, p2p=p2p)
         assert_same(got, want, f"p2p={p2p}")
 
@@ -55,7 +56,7 @@ def test_emulated_baseline_configs(config, scale, world):
     from mauvealigner_b200 import dist
     seqs = mb.synth_genomes(config, scale)
     pattern = mb.get_seed(15, 0) if config == 1 else mb.get_seed(15, mb.CODING_SEED)
-    got = dist.find_unique_emulated(seqs, pattern, world)
+    got = dist.find_unique_emulated(seqs, pattern, world, p2p=2 if config == 5 else None)  # C5: every exchange fused
     assert_same(got, O.find(seqs, pattern, O.MODE_UNIQUE), f"C{config}")
     # the key-range partition is balanced to a few percent on these inputs
     recv = [i["seeds_received"] for i in got["info"]]
