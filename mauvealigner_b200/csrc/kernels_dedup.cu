@@ -773,7 +773,9 @@ __global__ void __launch_bounds__(DD_NT) k_extend_long(DedupArgs a, GenomeTable 
 // Rep state: 0 undecided, 1 accepted, 2 dropped; flag bit 6: lives on the wide list.
 #define RS_MASK 0x0Fu
 #define RS_WIDE 0x40u
+#ifndef DD_WALK_MAX
 #define DD_WALK_MAX 192 // neighbours one thread visits per direction before the rep is handed to a warp
+#endif
 
 // Visit the neighbours of rep i in the (colour, slot) order.  `first`/`stride` = 0/1 for one thread, lane/32 for
 // a warp.

@@ -437,6 +437,21 @@ def bench_main(args, CONFIG_NAMES, config_params, peaks, ClockSampler):
         sampler.stop_flag = True
         sampler.join(timeout=2)
 
+    # ---- the same workload through the single-GPU path on rank 0 (outside every timed region): the denominator of
+    # the strong-scaling figure, since the N = 1 line of this bench is quoted on another configuration (C2)
+    single_ms = None
+    if rank == 0:
+        ctx.find_device(mode, **kw)
+        torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(stream)
+        for _ in range(2):
+            ctx.find_device(mode, **kw)
+        s1.record(stream)
+        torch.cuda.synchronize()
+        single_ms = s0.elapsed_time(s1) / 2
+    dist.barrier()
+
     if rank == 0:
         peak, peak_src = peaks()
         R = st["record_bytes"]
@@ -466,6 +481,8 @@ def bench_main(args, CONFIG_NAMES, config_params, peaks, ClockSampler):
                     "d2h_bytes_per_step": int(d2h.item())},
             "gpu_launches": int(launches.item()) * args.steps, "stages_ms_rank0": {k: round(v, 4) for k, v in stage.items()},
             "rank0": {k: v for k, v in info[0].items()}, "wall_ms_per_step": wall_ms / args.steps, "clocks": sampler.summary(),
+            "single_gpu_same_workload": {"ms_per_step": single_ms, "value": bp / (single_ms * 1e-3) / 1e9, "unit": "Gbp/s",
+                                         "speedup": single_ms / ms_per_step, "note": "mb_find_device on rank 0, untimed region"},
         }
         print(json.dumps(line), flush=True)
     fabric.release_peer_buffers([ctx])
