@@ -76,6 +76,9 @@ class LocalFabric:
     def release_peer_buffers(self, ctxs):
         pass
 
+    def p2p_ok(self, ctxs):
+        return True
+
     def allreduce_sum(self, tensors):
         total = tensors[0].clone()
         for t in tensors[1:]:
@@ -145,6 +148,22 @@ class TorchFabric:
         st["ptrs"] = [mine if r == self.rank else c.ipc_import(out[r].cpu().numpy().tobytes()) for r in range(self.world)]
         return [st["ptrs"]]
 
+    def p2p_ok(self, ctxs):
+        """Collective capability probe, once per fabric: can every rank map every other rank's device memory (CUDA IPC +
+        peer access over NVLink)?  If not, the exchanges stay NCCL all-to-alls (still GPU to GPU; nothing moves to
+        the host)."""
+        if "_p2p_ok" not in self.__dict__:
+            ok = 1
+            try:
+                self.peer_buffers(ctxs, "seed", [0] * self.world)
+            except Exception as e:  # the other ranks may be waiting in the handle all-gather: it has completed by now
+                print(f"[mauve_b200.dist] rank {self.rank}: peer mapping unavailable ({e}); exchanges stay on NCCL", file=sys.stderr, flush=True)
+                ok = 0
+            t = torch.tensor([ok], dtype=torch.int64, device=self.device)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN, group=self.group)
+            self._p2p_ok = bool(int(t.item()))
+        return self._p2p_ok
+
     def _unmap(self, c, st):
         # unmap the peers' buffers before any rank frees or regrows its own
         if st["ptrs"] is not None:
@@ -198,6 +217,8 @@ def find_unique(ctxs, fabric, device, nway_mask=0, p2p=None):
     if p2p is None:
         p2p = p2p_default()
     p2p = int(p2p)
+    if p2p and W > 1 and not fabric.p2p_ok(ctxs):
+        p2p = 0
     info = [dict(rank=r) for r in R]
     trace = os.environ.get("MB_DIST_TRACE")
     marks = []
