@@ -253,6 +253,17 @@ public:
             sml_table.push_back(sml);
         }
     }
+    /* MatchList::MultiplicityFilter(mult) (src/mauveAligner.cpp:600, src/transposeCoordinates.cpp:48): keep only the
+     * matches present in exactly `mult` sequences; the others are released (the list owns what it drops). */
+    void MultiplicityFilter(unsigned mult) {
+        size_t kept = 0;
+        for (size_t i = 0; i < size(); ++i) {
+            Match* m = (*this)[i];
+            if (m->Multiplicity() == mult) (*this)[kept++] = m;
+            else m->Free();
+        }
+        resize(kept);
+    }
     static uint32 GetDefaultMerSize(const std::vector<genome::gnSequence*>& seqs) {
         gnSeqI total = 0;
         for (auto* s : seqs) total += s->length();

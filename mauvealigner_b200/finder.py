@@ -302,6 +302,10 @@ class MatchList(list):
         self.seq_filename, self.sml_filename, self.seq_table, self.sml_table = [], [], [], []
         self.seed_pattern = 0
 
+    def MultiplicityFilter(self, mult):
+        """MatchList::MultiplicityFilter (src/mauveAligner.cpp:600): keep the matches present in exactly `mult` sequences."""
+        self[:] = [m for m in self if m.Multiplicity() == mult]
+
     def CreateMemorySMLs(self, seed_weight, log=None, seed_rank=0):
         """MatchList::CreateMemorySMLs(mer_size, ostream*, seed_rank) (src/mauveAligner.cpp:456): here it only fixes
         the seed; the sorted mer lists are built on the device inside FindMatches."""
@@ -449,3 +453,54 @@ class SeedMatchEnumerator(MatchFinder):
 
     def Clone(self):
         return SeedMatchEnumerator(self._ctx)
+
+
+class ContextPool:
+    """Many small problems (the aligners re-run the MUM search inside every inter-anchor gap,
+    src/mauveAligner.cpp:94,698, src/progressiveMauve.cpp:661-664): a pool of library contexts, each with its own CUDA
+    stream and workspace, driven by one host thread each.  A small search is launch- and latency-bound (about 40 short
+    kernels and 5 scalar read-backs), so independent searches overlap on the device; the C ABI calls release the GIL.
+    Every problem runs through the same mb_find as a single search, so the results are the same bit for bit."""
+
+    def __init__(self, n_contexts=8, device=0):
+        self.ctxs = [Context(device) for _ in range(n_contexts)]
+
+    def close(self):
+        for c in self.ctxs:
+            c.close()
+        self.ctxs = []
+
+    def find_many(self, problems, pattern, mode=L.MODE_UNIQUE, **kw):
+        """problems: iterable of sequence lists -> list of result dicts, in order."""
+        import queue
+        import threading
+        problems = list(problems)
+        out = [None] * len(problems)
+        work = queue.SimpleQueue()
+        for i in range(len(problems)):
+            work.put(i)
+        errors = []
+
+        def run(ctx):
+            try:
+                ctx.set_seed(pattern)
+                while True:
+                    try:
+                        i = work.get_nowait()
+                    except queue.Empty:
+                        return
+                    ctx.clear_sequences()
+                    for s in problems[i]:
+                        ctx.add_sequence(s)
+                    out[i] = ctx.find(mode, **kw)
+            except Exception as e:  # surfaced to the caller below
+                errors.append(e)
+
+        threads = [threading.Thread(target=run, args=(c,)) for c in self.ctxs[:max(1, min(len(self.ctxs), len(problems)))]]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+        return out

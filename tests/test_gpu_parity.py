@@ -284,3 +284,29 @@ def test_cpp_host_api_matches_oracle(tmp_path):
     lst = tmp_path / "matches.mums"
     lst.write_text(first)
     assert subprocess.check_output([str(exe), "readlist", str(lst)], text=True) == first
+
+
+def test_context_pool_many_small_problems():
+    """f4 (many small problems, one search per inter-anchor gap): a pool of contexts on concurrent streams gives the
+    results of the one-at-a-time searches, in order, for problems of mixed sizes (including empty ones)."""
+    import mauvealigner_b200 as mb
+    rng = np.random.default_rng(2024)
+    problems = []
+    for i in range(40):
+        n = int(rng.integers(0, 3000))
+        k = int(rng.integers(2, 5))
+        seqs = family(rng, n, k, sub=0.03, indel=0.004, inv=0) if n > 50 else [rand_seq(rng, n) for _ in range(k)]
+        if i % 5 == 0:
+            seqs[-1] = revcomp(seqs[-1])
+        problems.append(seqs)
+    pattern = 0b110111011
+    pool = mb.ContextPool(6)
+    try:
+        got = pool.find_many(problems, pattern, mb.MODE_UNIQUE)
+        again = pool.find_many(problems[::-1], pattern, mb.MODE_UNIQUE)[::-1]
+    finally:
+        pool.close()
+    for seqs, g, g2 in zip(problems, got, again):
+        want = O.find(seqs, pattern, O.MODE_UNIQUE)
+        assert_same(g, want, "pool")
+        assert_same(g2, want, "pool, reversed order")

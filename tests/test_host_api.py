@@ -101,3 +101,18 @@ def test_python_mirror_shapes():
     ml.seq_table = ["ACGT" * 100, "ACGA" * 100]
     ml.CreateMemorySMLs(0)
     assert mb.seed_valid(ml.seed_pattern) and ml.sml_table[0].SeedLength() == mb.seed_length(ml.seed_pattern)
+
+
+def test_multiplicity_filter():
+    import mauvealigner_b200 as mb
+    ml = mb.MatchList()
+    for starts in ([5, 0, -7], [1, 2, 3], [0, 0, 9], [4, -4, 0]):
+        m = mb.Match(3)
+        m.SetLength(21)
+        for i, st in enumerate(starts):
+            m.SetStart(i, st)
+        ml.append(m)
+    ml.MultiplicityFilter(2)
+    assert [[m.Start(i) for i in range(3)] for m in ml] == [[5, 0, -7], [4, -4, 0]]
+    ml.MultiplicityFilter(3)
+    assert len(ml) == 0
