@@ -165,6 +165,11 @@ int mb_dist_local(mb_ctx* ctx, const mb_params* params, uint64_t n_recv, uint64_
  * fused with exchange 2, straight into the owners' receive buffers 1 over NVLink (peer_bases[d] mapped with
  * mb_ipc_import, peer_row_offsets[d] = row index of this rank's block in rank d's buffer).  Asynchronous. */
 int mb_dist_rows_pack(mb_ctx* ctx, void* const* peer_bases, const uint64_t* peer_row_offsets, void** d_rows);
+/* Push the destination blocks of a local send buffer (counts[d] units of unit_words 8-byte words, back to back) into
+ * the destination ranks' mapped receive buffers with device-to-device copies (copy engines over NVLink) on the
+ * context stream; dst_offsets[d] = unit index of this rank's block in rank d's buffer.  Asynchronous. */
+int mb_dist_push(mb_ctx* ctx, const void* d_src, const uint64_t* counts, uint32_t unit_words, void* const* peer_bases,
+                 const uint64_t* dst_offsets);
 int mb_dist_resolve(mb_ctx* ctx, uint64_t n_rows, void** d_verdict);
 int mb_dist_accept(mb_ctx* ctx, void** d_hist);
 int mb_dist_match_partition(mb_ctx* ctx, uint64_t* h_match_counts, uint64_t* h_comp_counts);

@@ -40,7 +40,7 @@ EXPORTS = ["mb_ctx_create", "mb_ctx_destroy", "mb_set_stream", "mb_add_sequence"
            "mb_set_seed", "mb_find", "mb_find_device", "mb_fetch_result", "mb_get_sml", "mb_get_mers", "mb_get_stats", "mb_strerror",
            "mb_last_cuda_error", "mb_device_count", "mb_version", "mb_synth_create", "mb_synth_nseq", "mb_synth_len", "mb_synth_seq",
            "mb_synth_free", "mb_dist_extract", "mb_dist_extract_count", "mb_dist_partition", "mb_dist_p2p_recv_array",
-           "mb_dist_use_p2p_recv", "mb_ipc_export", "mb_ipc_import", "mb_ipc_close", "mb_dist_recv_buffer", "mb_dist_local", "mb_dist_rows_pack", "mb_dist_resolve", "mb_dist_accept", "mb_dist_match_pack", "mb_dist_match_partition", "mb_dist_output", "mb_dist_stage_ms", "mb_debug_radix"]
+           "mb_dist_use_p2p_recv", "mb_ipc_export", "mb_ipc_import", "mb_ipc_close", "mb_dist_recv_buffer", "mb_dist_local", "mb_dist_rows_pack", "mb_dist_push", "mb_dist_resolve", "mb_dist_accept", "mb_dist_match_pack", "mb_dist_match_partition", "mb_dist_output", "mb_dist_stage_ms", "mb_debug_radix"]
 
 _lib = None
 
@@ -91,6 +91,7 @@ def lib():
     L.mb_ipc_close.argtypes = [vp, vp]
     L.mb_dist_recv_buffer.argtypes = [vp, i32, u64, C.POINTER(vp)]
     L.mb_dist_local.argtypes = [vp, C.POINTER(MbParams), u64, pu64]
+    L.mb_dist_push.argtypes = [vp, vp, pu64, C.c_uint32, C.POINTER(vp), pu64]
     L.mb_dist_rows_pack.argtypes = [vp, C.POINTER(vp), pu64, C.POINTER(vp)]
     L.mb_dist_match_pack.argtypes = [vp, C.POINTER(vp), pu64, C.POINTER(vp), pu64, C.POINTER(vp), C.POINTER(vp)]
     L.mb_dist_resolve.argtypes = [vp, u64, C.POINTER(vp)]

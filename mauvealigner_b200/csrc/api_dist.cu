@@ -321,6 +321,31 @@ int mb_dist_rows_pack(mb_ctx* c, void* const* peer_bases, const uint64_t* peer_r
     return MB_OK;
 }
 
+// Push the blocks of a local send buffer (as laid out by mb_dist_rows_pack / mb_dist_match_pack with bases = NULL:
+// destination blocks back to back, counts[d] units of `unit_words` 8-byte words each) into the destination ranks'
+// receive buffers with device-to-device copies on the context stream: the copy engines move the bytes over NVLink
+// while the SMs are free.  peer_bases[d] = rank d's receive buffer mapped into this process, dst_offsets[d] = unit
+// index of this rank's block there.  Asynchronous; all ranks must synchronise before the receivers read.
+int mb_dist_push(mb_ctx* c, const void* d_src, const uint64_t* counts, uint32_t unit_words, void* const* peer_bases, const uint64_t* dst_offsets) {
+    if (!c || !counts || !peer_bases || !dst_offsets || unit_words == 0) return MB_E_ARG;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const size_t unit = (size_t)unit_words * 8;
+    size_t src_off = 0;
+    // start with the next rank so that the ranks do not all push to the same destination at the same time
+    const int world = c->d_world;
+    std::vector<size_t> so(world + 1, 0);
+    for (int d = 0; d < world; ++d) so[d + 1] = so[d] + (size_t)counts[d] * unit;
+    (void)src_off;
+    for (int k = 0; k < world; ++k) {
+        const int d = (c->d_rank + 1 + k) % world;
+        if (counts[d] == 0) continue;
+        if (!d_src || !peer_bases[d]) return MB_E_ARG;
+        CUDA_TRY(c, cudaMemcpyAsync((char*)peer_bases[d] + (size_t)dst_offsets[d] * unit, (const char*)d_src + so[d], (size_t)counts[d] * unit,
+                                    cudaMemcpyDeviceToDevice, c->stream));
+    }
+    return MB_OK;
+}
+
 // stage 3a (owner side): n_rows candidate rows in receive buffer 1, in source-rank order (= ascending seed order
 // inside every group).  Chains / reps / resolve over the owned groups (no extension: the extents came with the rows);
 // *d_verdict = one byte per row, in row order (1 accepted, 0 dropped), to be returned to the rows' sources.

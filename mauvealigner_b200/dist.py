@@ -199,7 +199,8 @@ def _alloc_recv(ctx, key, n):
 def p2p_default():
     """MB_DIST_P2P: 0 = every exchange is an NCCL all-to-all of a local send buffer; 1 (default) = exchange 1 (seed
     records, the largest) is fused into the partition kernel as NVLink peer stores; 2 = exchanges 2 and 3 (candidate
-    rows, match rows) too.  Measured at 8 x B200 on C5: level 1 is the fastest — the partition pass keeps enough
+    rows, match rows) too; 3 = exchange 1 fused, exchanges 2 and 3 packed locally and pushed into the peers' buffers by
+    the copy engines (cudaMemcpyAsync device to device over NVLink).  Measured at 8 x B200 on C5: level 1 is the fastest — the partition pass keeps enough
     stores in flight to beat the all-to-all (0.9 vs 2.4 ms), the gather-bound row pack kernels do not (rows 1.05 vs
     0.6 ms, match rows 1.6 vs 1.2 ms), so level 2 stays an option, not the default."""
     return int(os.environ.get("MB_DIST_P2P", "1"))
@@ -263,8 +264,12 @@ def find_unique(ctxs, fabric, device, nway_mask=0, p2p=None):
     if p2p >= 2:
         M2 = fabric.gather_counts(scc)
         peers = fabric.peer_buffers(ctxs, "hdr", [4 * sum(M2[s][d] for s in range(W)) for d in range(W)])
-        for c, r, pp in zip(ctxs, R, peers):
-            c.dist_rows_pack(pp, [sum(M2[s][d] for s in range(r)) for d in range(W)])
+        for c, r, pp, cc in zip(ctxs, R, peers, scc):
+            offs = [sum(M2[s][d] for s in range(r)) for d in range(W)]
+            if p2p == 2:
+                c.dist_rows_pack(pp, offs)            # the pack kernel stores into the owners' buffers
+            else:
+                c.dist_push(c.dist_rows_pack(), cc, 4, pp, offs)  # local pack, then copy-engine pushes
         fabric.barrier()
         rcc = [[M2[s][r] for s in range(W)] for r in R]
         mark("rows packed into the owners' buffers")
@@ -292,9 +297,15 @@ def find_unique(ctxs, fabric, device, nway_mask=0, p2p=None):
         M3 = fabric.gather_counts(pairs)
         ph = fabric.peer_buffers(ctxs, "hdr", [2 * sum(M3[s][2 * d] for s in range(W)) for d in range(W)])
         pc = fabric.peer_buffers(ctxs, "comp", [sum(M3[s][2 * d + 1] for s in range(W)) for d in range(W)])
-        for c, r, hh, cc_ in zip(ctxs, R, ph, pc):
-            c.dist_match_pack(hh, [sum(M3[s][2 * d] for s in range(r)) for d in range(W)],
-                              cc_, [sum(M3[s][2 * d + 1] for s in range(r)) for d in range(W)])
+        for c, r, hh, cc_, (nh, nc) in zip(ctxs, R, ph, pc, s3):
+            oh = [sum(M3[s][2 * d] for s in range(r)) for d in range(W)]
+            oc = [sum(M3[s][2 * d + 1] for s in range(r)) for d in range(W)]
+            if p2p == 2:
+                c.dist_match_pack(hh, oh, cc_, oc)
+            else:
+                hsrc, csrc = c.dist_match_pack()
+                c.dist_push(hsrc, nh, 2, hh, oh)
+                c.dist_push(csrc, nc, 1, cc_, oc)
         fabric.barrier()
         gcc = [[M3[s][2 * r] for s in range(W)] for r in R]
         gmc = [[M3[s][2 * r + 1] for s in range(W)] for r in R]

@@ -192,6 +192,11 @@ class Context:
         _check(self._h, L.lib().mb_dist_rows_pack(self._h, self._ptr_array(peer_ptrs), self._u64_array(peer_row_offsets), None))
         return None
 
+    def dist_push(self, src_ptr, counts, unit_words, peer_ptrs, dst_offsets):
+        """copy-engine push of a local send buffer's destination blocks into the peers' mapped receive buffers"""
+        _check(self._h, L.lib().mb_dist_push(self._h, C.c_void_p(int(src_ptr)), self._u64_array(counts), int(unit_words),
+                                             self._ptr_array(peer_ptrs), self._u64_array(dst_offsets)))
+
     def dist_resolve(self, n_rows):
         """stage 3a (owner) -> device pointer of one verdict byte per received row (1 accepted)"""
         v = C.c_void_p()

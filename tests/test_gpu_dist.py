@@ -35,7 +35,7 @@ def test_emulated_world_nccl_style_exchange1():
     rng = np.random.default_rng(77)
     seqs = family(rng, 30000, 4, sub=0.03, indel=0.002, inv=1)
     want = O.find(seqs, 0b1101110111110111011, O.MODE_UNIQUE)
-    for p2p in (0, 1, 2):
+    for p2p in (0, 1, 2, 3):
         got = dist.find_unique_emulated(seqs, 0b1101110111110111011, 3, p2p=p2p)
         assert_same(got, want, f"p2p={p2p}")
 
