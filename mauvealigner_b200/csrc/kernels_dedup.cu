@@ -318,12 +318,28 @@ __device__ void extend_candidate_warp(const u64* __restrict__ packed, const Geno
 // is component 0's), first base in the top bits of `a`.  Reads may run up to 128 bases outside the
 // genome: the packed buffer is padded on both sides of every genome and such bases never reach a
 // tested window.
+// The packed genomes (0.25 B/bp: 10 MB at C2, 80 MB at C5) are the only data of the extension that is re-read — at
+// random, by every component of every rep — while the rep records, component rows and extents stream through once.
+// Genome words are therefore loaded with an L2 evict-last policy (ncu before: 30 % L2 hit rate and 1.5 GB of DRAM
+// reads in k_extend at C2).  Measured effect: small (extension 1025 -> 995 us at C2, none at C5); streaming hints
+// (ld.cs / st.cs) on the rep records, component rows and extents on top of it made it slower and were dropped.
+__device__ __forceinline__ u64 l2_keep_policy() {
+    u64 pol;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ u64 ld_keep(const u64* p, u64 pol) {
+    u64 v;
+    asm("ld.global.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol));
+    return v;
+}
 __device__ __forceinline__ void oriented_bases64(const u64* __restrict__ packed, const GenomeTable& gt, u32 L, u32 g, u32 pos, bool rev, i64 i0,
                                                  u64& a, u64& b) {
     i64 q = (i64)gt.word_base[g] * 32 + (i64)pos + (rev ? (i64)L - 64 - i0 : i0);
     const u64* w = packed + ((u64)q >> 5);
     int sh = (int)(q & 31) * 2;
-    u64 w0 = w[0], w1 = w[1], w2 = w[2];
+    const u64 pol = l2_keep_policy();
+    u64 w0 = ld_keep(w, pol), w1 = ld_keep(w + 1, pol), w2 = ld_keep(w + 2, pol);
     u64 fa = shl128_hi(w0, w1, sh), fb = shl128_hi(w1, w2, sh);
     if (rev) { a = rc_word(fb); b = rc_word(fa); }
     else { a = fa; b = fb; }
@@ -688,13 +704,10 @@ __device__ __forceinline__ void extend_finish(const DedupArgs& a, const GenomeTa
     wl_push(last ? a.wl_long : out_list, last ? a.ctr + 6 : out_count, more, i);
 }
 
-#ifndef DD_EXT_MINB
-#define DD_EXT_MINB 1
-#endif
 #define DD_EXT_FIRST_ROUNDS 2
 #define DD_EXT_MORE_ROUNDS 4
 
-__global__ void __launch_bounds__(DD_NT, DD_EXT_MINB) k_extend(DedupArgs a, GenomeTable gt, SeedDev sd, u32* out_list, u32* out_count) {
+__global__ void __launch_bounds__(DD_NT) k_extend(DedupArgs a, GenomeTable gt, SeedDev sd, u32* out_list, u32* out_count) {
     __shared__ u32 sMap[DD_NT / 32][32][4];
     __shared__ u32 sRoom[DD_NT / 32][32][2];
     const int warp = threadIdx.x >> 5;
@@ -716,7 +729,7 @@ __global__ void __launch_bounds__(DD_NT, DD_EXT_MINB) k_extend(DedupArgs a, Geno
 }
 
 // the unfinished reps of the previous launch, 32 per warp
-__global__ void __launch_bounds__(DD_NT, DD_EXT_MINB) k_extend_more(DedupArgs a, GenomeTable gt, SeedDev sd, const u32* in_list, const u32* in_count, u32* out_list,
+__global__ void __launch_bounds__(DD_NT) k_extend_more(DedupArgs a, GenomeTable gt, SeedDev sd, const u32* in_list, const u32* in_count, u32* out_list,
                                                        u32* out_count, int last) {
     __shared__ u32 sMap[DD_NT / 32][32][4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
