@@ -905,7 +905,7 @@ __global__ void __launch_bounds__(DD_NT) k_resolve(DedupArgs a) {
             }
             walk_neighbours<false, true>(a, i, me, rlo, rhi, mr_cur);
         }
-        grid.sync();
+        if (n_wide) grid.sync(); // uniform (read after the barrier above); without wide reps all claims are already complete
         DD_TRACE(5);
         // ---- decide, narrow
         for (u32 base = blockIdx.x * DD_NT; base < n_narrow; base += gsz) {
