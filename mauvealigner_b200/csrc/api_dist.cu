@@ -330,12 +330,10 @@ int mb_dist_push(mb_ctx* c, const void* d_src, const uint64_t* counts, uint32_t 
     if (!c || !counts || !peer_bases || !dst_offsets || unit_words == 0) return MB_E_ARG;
     CUDA_TRY(c, cudaSetDevice(c->device));
     const size_t unit = (size_t)unit_words * 8;
-    size_t src_off = 0;
-    // start with the next rank so that the ranks do not all push to the same destination at the same time
     const int world = c->d_world;
-    std::vector<size_t> so(world + 1, 0);
+    std::vector<size_t> so(world + 1, 0); // byte offset of every destination's block in the send buffer
     for (int d = 0; d < world; ++d) so[d + 1] = so[d] + (size_t)counts[d] * unit;
-    (void)src_off;
+    // start with the next rank so that the ranks do not all push to the same destination at the same time
     for (int k = 0; k < world; ++k) {
         const int d = (c->d_rank + 1 + k) % world;
         if (counts[d] == 0) continue;
