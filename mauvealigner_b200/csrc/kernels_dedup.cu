@@ -577,8 +577,7 @@ __global__ void __launch_bounds__(256) k_extent_ranges(DedupArgs a, GenomeTable 
     if (i >= a.n_rep) return;
     const uint4 q = a.xrec[i];
     const u64 e = a.rows[4 * (size_t)q.x + 3];
-    const u32 el = (u32)e, er = (u32)(e >> 32);
-    a.ext_l[q.x] = el; a.ext_r[q.x] = er;
+    const u32 el = (u32)e, er = (u32)(e >> 32); // (the owner never needs per-candidate extent arrays: the rows keep them)
     u32 rlo, rhi;
     extent_slots(a, gt.vbase[q.z >> 16] + q.w, el, er, rlo, rhi);
     a.rng_lo[i] = rlo; a.rng_hi[i] = rhi;
