@@ -969,11 +969,14 @@ void launch_extend(const DedupArgs& a, const GenomeTable& gt, const SeedDev& sd,
 }
 cudaError_t launch_resolve(const DedupArgs& a, cudaStream_t st) {
     if (a.n_rep == 0) return cudaSuccess;
-    static int grid_blocks = 0;
+    static int grid_blocks_of[64] = {}; // per device: co-resident blocks of the cooperative launch
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    int local_blocks = 0;
+    int& grid_blocks = (dev >= 0 && dev < 64) ? grid_blocks_of[dev] : local_blocks;
     if (grid_blocks == 0) {
-        int dev = 0, sms = 0, per_sm = 0;
-        cudaError_t e = cudaGetDevice(&dev);
-        if (e != cudaSuccess) return e;
+        int sms = 0, per_sm = 0;
         e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (e != cudaSuccess) return e;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_resolve, DD_NT, 0);

@@ -217,7 +217,9 @@ void launch_scan_hist(const u32* d_hist, u32* d_base, int npass, cudaStream_t st
     k_scan_hist<<<npass, 256, 0, st>>>(d_hist, d_base);
 }
 
-static bool g_attr_set[3] = {false, false, false};
+// the dynamic shared memory opt-in is per function AND per device (a process may hold contexts on several devices)
+#define RS_MAX_DEV 64
+static bool g_attr_set[RS_MAX_DEV][3] = {};
 
 cudaError_t launch_onesweep(const u64* kin, u64* kout, const u64* vin, u64* vout, u32 n, const u32* d_digit_base,
                             u64* d_lookback, u32* d_ticket, int shift, int bits, cudaStream_t st, const u8* lut, u64* const* peers) {
@@ -226,12 +228,16 @@ cudaError_t launch_onesweep(const u64* kin, u64* kout, const u64* vin, u64* vout
     if (lut && hv) return cudaErrorInvalidValue;
     size_t smem = radix_smem_bytes(hv);
     int variant = lut ? 2 : (hv ? 1 : 0);
-    if (!g_attr_set[variant]) {
+    int dev = 0;
+    cudaError_t de = cudaGetDevice(&dev);
+    if (de != cudaSuccess) return de;
+    const bool tracked = dev >= 0 && dev < RS_MAX_DEV;
+    if (!tracked || !g_attr_set[dev][variant]) {
         cudaError_t e = variant == 2 ? cudaFuncSetAttribute(k_onesweep<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                       : variant == 1 ? cudaFuncSetAttribute(k_onesweep<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                                      : cudaFuncSetAttribute(k_onesweep<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        g_attr_set[variant] = true;
+        if (tracked) g_attr_set[dev][variant] = true;
     }
     u32 tiles = div_up(n, RS_TILE);
     u32 dmask = (1u << bits) - 1;
