@@ -182,6 +182,14 @@ int mb_dist_output(mb_ctx* ctx, uint64_t n_match, uint64_t n_comp);
  * [3] extension, [4] chains + resolve; [5..7] reserved (0) */
 int mb_dist_stage_ms(mb_ctx* ctx, float* out8);
 
+/* The same multi-GPU search driven from C++ inside ONE process: ctxs[r] = the context of rank r (normally one per GPU;
+ * contexts may share a device), the same sequences and seed set on every context.  One host thread per context runs
+ * the stages above; every exchange goes device to device over NVLink peer access (exchange 1 fused into the partition
+ * kernel, the others pushed by the copy engines), no NCCL, no torch.  Blocks until every rank's piece of the result is
+ * on its device: then mb_fetch_result(ctxs[r]) per rank, pieces concatenated in rank order = the result of mb_find
+ * (same reference calls as mb_find; MB_MODE_UNIQUE only). */
+int mb_find_multi(mb_ctx* const* ctxs, int world, const mb_params* params);
+
 /* ---- sorted mer list access (SortedMerList façade; "next" row of SURVEY.md §8f) ---- */
 /* Positions of sequence `seq` sorted by (seed, position): the .sslist position array (a4).
  * out_pos must hold len-L+1 entries (host). Valid after a mb_find* call in any mode. */

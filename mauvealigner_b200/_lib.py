@@ -40,7 +40,7 @@ EXPORTS = ["mb_ctx_create", "mb_ctx_destroy", "mb_set_stream", "mb_add_sequence"
            "mb_set_seed", "mb_find", "mb_find_device", "mb_fetch_result", "mb_get_sml", "mb_get_mers", "mb_get_stats", "mb_strerror",
            "mb_last_cuda_error", "mb_device_count", "mb_version", "mb_synth_create", "mb_synth_nseq", "mb_synth_len", "mb_synth_seq",
            "mb_synth_free", "mb_dist_extract", "mb_dist_extract_count", "mb_dist_partition", "mb_dist_p2p_recv_array",
-           "mb_dist_use_p2p_recv", "mb_ipc_export", "mb_ipc_import", "mb_ipc_close", "mb_dist_recv_buffer", "mb_dist_local", "mb_dist_rows_pack", "mb_dist_push", "mb_dist_resolve", "mb_dist_accept", "mb_dist_match_pack", "mb_dist_match_partition", "mb_dist_output", "mb_dist_stage_ms", "mb_debug_radix"]
+           "mb_dist_use_p2p_recv", "mb_ipc_export", "mb_ipc_import", "mb_ipc_close", "mb_dist_recv_buffer", "mb_dist_local", "mb_dist_rows_pack", "mb_dist_push", "mb_dist_resolve", "mb_dist_accept", "mb_dist_match_pack", "mb_dist_match_partition", "mb_dist_output", "mb_dist_stage_ms", "mb_find_multi", "mb_debug_radix"]
 
 _lib = None
 
@@ -98,6 +98,7 @@ def lib():
     L.mb_dist_accept.argtypes = [vp, C.POINTER(vp)]
     L.mb_dist_match_partition.argtypes = [vp, pu64, pu64]
     L.mb_dist_output.argtypes = [vp, u64, u64]
+    L.mb_find_multi.argtypes = [C.POINTER(vp), i32, C.POINTER(MbParams)]
     L.mb_dist_stage_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.mb_debug_radix.argtypes = [vp, u64, i32, i32, i32, C.POINTER(C.c_float)]
     _lib = L

@@ -460,6 +460,17 @@ class SeedMatchEnumerator(MatchFinder):
         return SeedMatchEnumerator(self._ctx)
 
 
+def find_multi(ctxs, nway_mask=0):
+    """mb_find_multi: MODE_UNIQUE over one context per GPU (or several per GPU), driven by the library's own host threads
+    with every exchange device to device over NVLink peer access — no torch.distributed, no NCCL.  The same sequences
+    and seed must be set on every context.  -> the whole result (the ranks' pieces concatenated in rank order)."""
+    from .dist import concat_results
+    p = ctxs[0]._params(L.MODE_UNIQUE, 2, 1000, False, nway_mask)
+    arr = (C.c_void_p * len(ctxs))(*[c._h for c in ctxs])
+    _check(ctxs[0]._h, L.lib().mb_find_multi(arr, len(ctxs), C.byref(p)))
+    return concat_results([c.fetch() for c in ctxs])
+
+
 class ContextPool:
     """Many small problems (the aligners re-run the MUM search inside every inter-anchor gap,
     src/mauveAligner.cpp:94,698, src/progressiveMauve.cpp:661-664): a pool of library contexts, each with its own CUDA

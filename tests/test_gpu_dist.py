@@ -64,3 +64,29 @@ def test_emulated_baseline_configs(config, scale, world):
     # ... and so is the range partition of the result
     out = [i["matches"] for i in got["info"]]
     assert sum(out) == got["n_matches"] and max(out) < 1.5 * (sum(out) / world) + 64
+
+
+@pytest.mark.parametrize("world", [1, 2, 5])
+def test_find_multi_cpp_driver(world):
+    """mb_find_multi: the same stages driven by the library's own host threads (one per context), every exchange device
+    to device — here all contexts on the GPUs present (device r % n_devices), so a single-GPU box runs it too."""
+    import mauvealigner_b200 as mb
+    ndev = mb.lib().mb_device_count()
+    rng = np.random.default_rng(900 + world)
+    seqs = family(rng, 25000, 4, sub=0.02, indel=0.003, inv=1)
+    seqs[1] = revcomp(seqs[1])
+    pattern = 0b1101110111110111011
+    ctxs = [mb.Context(r % max(1, ndev)) for r in range(world)]
+    try:
+        for c in ctxs:
+            for s in seqs:
+                c.add_sequence(s)
+            c.set_seed(pattern)
+        got = mb.find_multi(ctxs)
+        again = mb.find_multi(ctxs)  # buffers and peer mappings reused
+    finally:
+        for c in ctxs:
+            c.close()
+    want = O.find(seqs, pattern, O.MODE_UNIQUE)
+    assert_same(got, want, f"find_multi world {world}")
+    assert_same(again, want, f"find_multi world {world}, second run")
