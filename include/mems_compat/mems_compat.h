@@ -28,6 +28,7 @@
 #include <cstring>
 #include <fstream>
 #include <iostream>
+#include <sstream>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -309,12 +310,16 @@ inline void ReadList(MatchList& ml, std::istream& is) {
     }
 }
 
-/* mems::MatchFinder — holds the device context and the sequences added so far. */
+/* mems::MatchFinder — holds the device context(s) and the sequences added so far.
+ * One GPU by default (MAUVE_B200_DEVICE, default 0).  MAUVE_B200_DEVICES=0,1,2,... makes every finder hold one context
+ * per listed device (a device may be listed more than once) and run its MB_MODE_UNIQUE searches — UniqueMatchFinder,
+ * MemHash, MaskedMemHash — through mb_find_multi: one process, one host thread per GPU, exchanges over NVLink peer
+ * access; the other policies keep running on the first device.  The match list is the same either way. */
 class MatchFinder {
 public:
     MatchFinder() : ctx_(nullptr), seq_count(0), seed_(0), log_(nullptr) {}
     MatchFinder(const MatchFinder& o) : ctx_(nullptr), seq_count(0), seed_(o.seed_), log_(o.log_) {}
-    virtual ~MatchFinder() { if (ctx_) mb_ctx_destroy(ctx_); }
+    virtual ~MatchFinder() { destroy_ctxs(); }
     virtual MatchFinder* Clone() const = 0;
 
     virtual boolean AddSequence(SortedMerList* sar, genome::gnSequence* seq = nullptr) {
@@ -324,34 +329,55 @@ public:
         else if (sar->Seed() != seed_) { genome::ErrorMsg("AddSequence: all sorted mer lists must use the same seed\n"); return false; }
         const genome::gnSequence* s = seq ? seq : sar->Sequence();
         int rc = mb_add_sequence(ctx_, (const uint8_t*)s->data().data(), s->length(), 0, nullptr);
+        for (size_t k = 0; rc == MB_OK && k < more_.size(); ++k) rc = mb_add_sequence(more_[k], (const uint8_t*)s->data().data(), s->length(), 0, nullptr);
         if (rc != MB_OK) { report("AddSequence", rc); return false; }
         ++seq_count;
         return true;
     }
     virtual void Clear() {}
-    virtual void ClearSequences() { if (ctx_) mb_clear_sequences(ctx_); seq_count = 0; }
+    virtual void ClearSequences() {
+        if (ctx_) mb_clear_sequences(ctx_);
+        for (mb_ctx* c : more_) mb_clear_sequences(c);
+        seq_count = 0;
+    }
     void LogProgress(std::ostream* os) { log_ = os; }
     uint32 SeqCount() const { return seq_count; }
 
 protected:
     bool ensure_ctx() {
         if (ctx_) return true;
-        int rc = mb_ctx_create(&ctx_, device_from_env());
+        std::vector<int> devs = devices_from_env();
+        int rc = mb_ctx_create(&ctx_, devs[0]);
         if (rc != MB_OK) { ctx_ = nullptr; report("mb_ctx_create", rc); return false; }
+        for (size_t k = 1; k < devs.size(); ++k) {
+            mb_ctx* c = nullptr;
+            rc = mb_ctx_create(&c, devs[k]);
+            if (rc != MB_OK) { report("mb_ctx_create", rc); destroy_ctxs(); return false; }
+            more_.push_back(c);
+        }
         return true;
     }
+    void destroy_ctxs() {
+        for (mb_ctx* c : more_) mb_ctx_destroy(c);
+        more_.clear();
+        if (ctx_) mb_ctx_destroy(ctx_);
+        ctx_ = nullptr;
+    }
     static int device_from_env() { const char* e = getenv("MAUVE_B200_DEVICE"); return e ? atoi(e) : 0; }
+    static std::vector<int> devices_from_env() {
+        std::vector<int> devs;
+        if (const char* e = getenv("MAUVE_B200_DEVICES")) {
+            std::stringstream ss(e);
+            std::string tok;
+            while (std::getline(ss, tok, ',')) if (!tok.empty()) devs.push_back(atoi(tok.c_str()));
+        }
+        if (devs.empty()) devs.push_back(device_from_env());
+        return devs;
+    }
     void report(const char* what, int rc) const {
         genome::ErrorMsg(std::string(what) + ": " + mb_strerror(rc) + (ctx_ ? std::string(" ") + mb_last_cuda_error(ctx_) : "") + "\n");
     }
-    /* run one search with the sequences added so far; fills `out` (dense = one column per sequence) */
-    boolean run(const mb_params& p, MatchList& out, bool dense) {
-        if (!ctx_ || seq_count == 0) return false;
-        int rc = mb_set_seed(ctx_, seed_);
-        const mb_result* r = nullptr;
-        if (rc == MB_OK) rc = mb_find(ctx_, &p, &r);
-        if (rc != MB_OK) { report("FindMatches", rc); return false; }
-        if (log_) *log_ << r->n_matches << " matches\n";
+    void append(const mb_result* r, MatchList& out, bool dense) const {
         for (uint64_t i = 0; i < r->n_matches; ++i) {
             uint64_t a = r->comp_off[i], b = r->comp_off[i + 1];
             Match* m = new Match(dense ? seq_count : (uint)(b - a));
@@ -359,9 +385,38 @@ protected:
             for (uint64_t k = a; k < b; ++k) m->SetStart(dense ? r->comp_seq[k] : (uint)(k - a), r->comp_start[k]);
             out.push_back(m);
         }
+    }
+    /* run one search with the sequences added so far; fills `out` (dense = one column per sequence) */
+    boolean run(const mb_params& p, MatchList& out, bool dense) {
+        if (!ctx_ || seq_count == 0) return false;
+        int rc = mb_set_seed(ctx_, seed_);
+        if (!more_.empty() && p.mode == MB_MODE_UNIQUE) {
+            // every GPU: the ranks' pieces are ascending ranges of the canonical order, appended in rank order
+            std::vector<mb_ctx*> all(1, ctx_);
+            all.insert(all.end(), more_.begin(), more_.end());
+            for (size_t k = 1; rc == MB_OK && k < all.size(); ++k) rc = mb_set_seed(all[k], seed_);
+            if (rc == MB_OK) rc = mb_find_multi(all.data(), (int)all.size(), &p);
+            if (rc != MB_OK) { report("FindMatches (multi-GPU)", rc); return false; }
+            uint64_t total = 0;
+            for (mb_ctx* c : all) {
+                const mb_result* r = nullptr;
+                rc = mb_fetch_result(c, &r);
+                if (rc != MB_OK) { report("mb_fetch_result", rc); return false; }
+                append(r, out, dense);
+                total += r->n_matches;
+            }
+            if (log_) *log_ << total << " matches\n";
+            return true;
+        }
+        const mb_result* r = nullptr;
+        if (rc == MB_OK) rc = mb_find(ctx_, &p, &r);
+        if (rc != MB_OK) { report("FindMatches", rc); return false; }
+        if (log_) *log_ << r->n_matches << " matches\n";
+        append(r, out, dense);
         return true;
     }
     mb_ctx* ctx_;
+    std::vector<mb_ctx*> more_;   /* ranks 1.. of the multi-GPU search */
     uint32 seq_count;
     uint64 seed_;
     std::ostream* log_;

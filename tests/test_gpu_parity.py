@@ -263,6 +263,9 @@ def test_cpp_host_api_matches_oracle(tmp_path):
     assert parse(out) == [[ln] + [s for _, s in comps] for ln, comps in O.matches_as_list(want)]
     out = subprocess.check_output([str(exe), "count", "9", "0", files[0]], text=True)
     assert int(out.split()[-1]) == O.find(seqs[:1], mb.get_seed(9, 0), O.MODE_UNIQUE_COUNT)["unique_mers"]
+    # the same UniqueMatchFinder over several contexts (MAUVE_B200_DEVICES: here three ranks on device 0) = mb_find_multi
+    multi = subprocess.check_output([str(exe), "umf", "11", "0"] + files, text=True, env=dict(os.environ, MAUVE_B200_DEVICES="0,0,0"))
+    assert parse(multi) == rows
     # PairwiseMatchFinder
     out = subprocess.check_output([str(exe), "pmf", "11", "0"] + files, text=True)
     want = O.find(seqs, mb.get_seed(11, 0), O.MODE_PAIRWISE)
