@@ -222,3 +222,45 @@ def test_genome_permutation_equivariance_two_genomes():
 
     s2 = sorted((ln, swap(c)) for ln, c in r2)
     assert s1 == s2
+
+
+def _normalised(ln, comps):
+    """a match as a set element: components by genome, the first one positive (orientation is relative to it)"""
+    d = sorted(comps)
+    if d[0][1] < 0:
+        d = [(g, -s) for g, s in d]
+    return (ln, tuple(d))
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_reverse_complement_equivariance(seed):
+    """Replacing one genome by its reverse complement maps the multi-MUM set onto itself: that genome's components
+    change strand and their left ends mirror (n - start - length + 2); everything else is unchanged.  Holds for the first
+    genome too (the whole match is then read on the other strand), because canonical seeds, the ascending-seed
+    de-dup order and the four-phase extension are all strand-symmetric."""
+    rng = np.random.default_rng(4000 + seed)
+    for pattern in (0b110111011, 0b1101110111110111011):
+        seqs = family(rng, 2500, 3, sub=0.03, indel=0.003, inv=1)
+        base = sorted(_normalised(ln, c) for ln, c in O.matches_as_list(O.find(seqs, pattern, O.MODE_UNIQUE)))
+        assert len(base) > 10
+        for k in range(3):
+            s2 = list(seqs)
+            s2[k] = revcomp(seqs[k])
+            n = len(seqs[k])
+            back = []
+            for ln, comps in O.matches_as_list(O.find(s2, pattern, O.MODE_UNIQUE)):
+                back.append(_normalised(ln, [(g, (-1 if s > 0 else 1) * (n - abs(s) - ln + 2)) if g == k else (g, s) for g, s in comps]))
+            assert sorted(back) == base, (bin(pattern), k)
+
+
+def test_genome_permutation_equivariance_three_genomes():
+    """Relabelling the genomes permutes the columns of every match and nothing else (the seed order, hence the
+    de-dup order, does not depend on the labels)."""
+    import itertools
+    rng = np.random.default_rng(4100)
+    pattern = 0b1101110111110111011
+    seqs = family(rng, 2000, 3, sub=0.03, indel=0.003, inv=1)
+    base = sorted(_normalised(ln, c) for ln, c in O.matches_as_list(O.find(seqs, pattern, O.MODE_UNIQUE)))
+    for perm in itertools.permutations(range(3)):
+        got = O.matches_as_list(O.find([seqs[p] for p in perm], pattern, O.MODE_UNIQUE))  # new genome i = old genome perm[i]
+        assert sorted(_normalised(ln, [(perm[g], s) for g, s in comps]) for ln, comps in got) == base, perm
