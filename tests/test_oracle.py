@@ -264,3 +264,25 @@ def test_genome_permutation_equivariance_three_genomes():
     for perm in itertools.permutations(range(3)):
         got = O.matches_as_list(O.find([seqs[p] for p in perm], pattern, O.MODE_UNIQUE))  # new genome i = old genome perm[i]
         assert sorted(_normalised(ln, [(perm[g], s) for g, s in comps]) for ln, comps in got) == base, perm
+
+
+def test_property_helpers_on_scaled_baseline_configs():
+    """tests/properties.py (the checks the CUDA path must pass at full size, tests/test_gpu_zz_properties.py) on the
+    oracle, over the synthetic generator's C1 and C2 at reduced length."""
+    import mauvealigner_b200 as mb
+    import properties as P
+
+    def rc(a):
+        lut = np.arange(256, dtype=np.uint8)
+        for x, y in zip(b"ACGT", b"TGCA"):
+            lut[x] = y
+        return np.ascontiguousarray(lut[np.asarray(a, dtype=np.uint8)][::-1])
+
+    seqs = mb.synth_genomes(1, 50)
+    pat = mb.get_seed(15, 0)
+    assert P.check_reverse_complement_equivariance(lambda s: O.find(s, pat, O.MODE_UNIQUE), seqs, rc) > 1000
+    seqs = mb.synth_genomes(2, 100)
+    pat = mb.get_seed(15, mb.CODING_SEED)
+    find = lambda s: O.find(s, pat, O.MODE_UNIQUE)  # noqa: E731
+    assert P.check_reverse_complement_equivariance(find, seqs, rc, genomes=(0, 5)) > 5000
+    assert P.check_permutation_equivariance(find, seqs, (3, 1, 7, 0, 2, 6, 5, 4)) > 5000
