@@ -116,3 +116,19 @@ def test_multiplicity_filter():
     assert [[m.Start(i) for i in range(3)] for m in ml] == [[5, 0, -7], [4, -4, 0]]
     ml.MultiplicityFilter(3)
     assert len(ml) == 0
+
+
+def test_multi_gpu_entry_points_reject_bad_arguments():
+    """argument checks of the multi-GPU entry points run before any device work (no GPU needed)"""
+    import ctypes as C
+    import mauvealigner_b200 as mb
+    from mauvealigner_b200 import _lib as L
+    lib = mb.lib()
+    p = L.MbParams(L.MODE_UNIQUE, 0, 2, 1000, 0)
+    assert lib.mb_find_multi(None, 2, C.byref(p)) == -1            # MB_E_ARG: no contexts
+    arr = (C.c_void_p * 2)(None, None)
+    assert lib.mb_find_multi(arr, 2, C.byref(p)) == -1             # null context
+    assert lib.mb_find_multi(arr, 0, C.byref(p)) == -1             # world < 1
+    assert lib.mb_dist_push(None, None, None, 1, None, None) == -1
+    assert lib.mb_dist_rows_pack(None, None, None, None) == -1
+    assert lib.mb_dist_match_pack(None, None, None, None, None, None, None) == -1
