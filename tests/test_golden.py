@@ -64,3 +64,21 @@ def test_cuda_mers_and_sml_golden():
         assert [int(x) for x in ctx.sml(0, len(g["seq"]))] == g["sml"]
     finally:
         ctx.close()
+
+
+def test_oracle_reproduces_fullsize_digest_c1():
+    """tests/golden/fullsize_digests.json (the oracle at the FULL BASELINE sizes, pinned as SHA-256 digests for the CUDA
+    tests in tests/test_gpu_zz_properties.py) is what the oracle gives today: C1 re-derived here (the larger ones take
+    minutes; their generator is tests/golden/make_fullsize_digests.py)."""
+    import importlib.util
+    import mauvealigner_b200 as mb
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "make_fullsize_digests.py")
+    spec = importlib.util.spec_from_file_location("make_fullsize_digests", path)
+    tool = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tool)
+    gold = json.load(open(os.path.join(os.path.dirname(path), "fullsize_digests.json")))
+    assert sorted(gold) == ["1", "2", "3", "4", "5"]
+    pattern, mode, kw = tool.config_params(mb, 1)
+    res = O.find(mb.synth_genomes(1, 1), pattern, mode, **kw)
+    assert (res["n_matches"], res["n_comps"]) == (gold["1"]["n_matches"], gold["1"]["n_comps"])
+    assert tool.digest(res) == gold["1"]["sha256"]
