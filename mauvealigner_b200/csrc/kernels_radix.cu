@@ -56,6 +56,9 @@ __global__ void __launch_bounds__(RS_NT, RS_MINB) k_onesweep(const u64* __restri
     __shared__ u32 sWarpSums[8];
     __shared__ u8 sLut[256];
     __shared__ u64* sPeer[USE_LUT ? 256 : 1];
+#ifdef RS_CLAIM_RANK
+    __shared__ u8 sClaim[RS_NW][256];
+#endif
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) sTile = atomicAdd(ticket, 1u);
@@ -95,6 +98,36 @@ __global__ void __launch_bounds__(RS_NT, RS_MINB) k_onesweep(const u64* __restri
     // running digit counter, the lowest peer lane advances it.
     u32* myHist = sWarpHist + warp * 256;
     const u32 lt_mask = (1u << lane) - 1;
+#ifdef RS_CLAIM_RANK
+    // EXPERIMENTAL (build with EXTRA=-DRS_CLAIM_RANK; not the default: written at the end of r01 without GPU time left to
+    // measure it, logic checked lane by lane in a host simulation).  Per-warp claim table: every lane stores its lane id at
+    // its digit and reads the entry back.  A lane that reads itself back either holds its digit alone in this round — the
+    // usual case with 256 bins and 32 lanes — or is the one winner of a colliding group; the lanes that read someone
+    // else's id know they collide.  Only the colliding groups (about two per round on uniform digits) cost a ballot each.
+#pragma unroll
+    for (int k = 0; k < RS_IPT; ++k) {
+        const u32 d = rk[k] >> 16;
+        const bool valid = full || wbase + k * 32 + lane < tile_n;
+        if (valid) sClaim[warp][d] = (u8)lane;
+        __syncwarp();
+        const u32 w = valid ? (u32)sClaim[warp][d] : (u32)lane;
+        u32 lost = __ballot_sync(0xFFFFFFFFu, w != (u32)lane); // also orders this round's loads before the next round's stores
+        u32 below = 0, size = 1;
+        while (lost) { // warp-uniform
+            const int leader = __ffs(lost) - 1;
+            const u32 dl = __shfl_sync(0xFFFFFFFFu, d, leader);
+            const bool in = valid && d == dl;
+            const u32 grp = __ballot_sync(0xFFFFFFFFu, in);
+            if (in) { below = __popc(grp & lt_mask); size = __popc(grp); }
+            lost &= ~grp;
+        }
+        const u32 old = valid ? myHist[d] : 0u;
+        __syncwarp();
+        if (valid && below == 0) myHist[d] = old + size;
+        __syncwarp();
+        rk[k] |= old + below;
+    }
+#else
 #pragma unroll
     for (int k = 0; k < RS_IPT; ++k) {
         const u32 d = rk[k] >> 16;
@@ -116,6 +149,7 @@ __global__ void __launch_bounds__(RS_NT, RS_MINB) k_onesweep(const u64* __restri
         __syncwarp();
         rk[k] |= old + __popc(below);
     }
+#endif
     __syncthreads();
 
     // per digit: exclusive scan across warps, tile total, look-back
