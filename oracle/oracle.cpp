@@ -385,6 +385,33 @@ static bool less_enum(const MatchRec& a, const MatchRec& b) {
     return false;
 }
 
+/* match records -> the CSR arrays of orc_result */
+static void pack_result(const Ctx& c, int mode, orc_result* r) {
+    r->n_buckets = c.n_buckets; r->n_candidates = c.n_candidates; r->n_contained = c.n_contained;
+    r->n_matches = c.out.size();
+    r->length = (uint32_t*)malloc(sizeof(uint32_t) * (r->n_matches + 1));
+    r->comp_off = (uint64_t*)malloc(sizeof(uint64_t) * (r->n_matches + 1));
+    uint64_t nc = 0;
+    for (const MatchRec& m : c.out)
+        for (int64_t s : m.start) nc += s != 0;
+    r->n_comps = nc;
+    r->comp_seq = (uint32_t*)malloc(sizeof(uint32_t) * (nc + 1));
+    r->comp_start = (int64_t*)malloc(sizeof(int64_t) * (nc + 1));
+    uint64_t k = 0;
+    for (size_t i = 0; i < c.out.size(); ++i) {
+        const MatchRec& m = c.out[i];
+        r->length[i] = m.length;
+        r->comp_off[i] = k;
+        for (size_t g = 0; g < m.start.size(); ++g)
+            if (m.start[g] != 0) {
+                r->comp_seq[k] = mode == ORC_MODE_SEED_ENUM ? 0u : (uint32_t)g;
+                r->comp_start[k] = m.start[g];
+                ++k;
+            }
+    }
+    r->comp_off[r->n_matches] = k;
+}
+
 } // namespace
 
 extern "C" {
@@ -479,30 +506,50 @@ int orc_find(uint32_t nseq, const uint8_t* const* ascii, const uint64_t* lens,
     else std::sort(c.out.begin(), c.out.end(), less_unique);
     double t3 = now_s();
 
-    r->n_buckets = c.n_buckets; r->n_candidates = c.n_candidates; r->n_contained = c.n_contained;
-    r->n_matches = c.out.size();
-    r->length = (uint32_t*)malloc(sizeof(uint32_t) * (r->n_matches + 1));
-    r->comp_off = (uint64_t*)malloc(sizeof(uint64_t) * (r->n_matches + 1));
-    uint64_t nc = 0;
-    for (const MatchRec& m : c.out)
-        for (int64_t s : m.start) nc += s != 0;
-    r->n_comps = nc;
-    r->comp_seq = (uint32_t*)malloc(sizeof(uint32_t) * (nc + 1));
-    r->comp_start = (int64_t*)malloc(sizeof(int64_t) * (nc + 1));
-    uint64_t k = 0;
-    for (size_t i = 0; i < c.out.size(); ++i) {
-        const MatchRec& m = c.out[i];
-        r->length[i] = m.length;
-        r->comp_off[i] = k;
-        for (size_t g = 0; g < m.start.size(); ++g)
-            if (m.start[g] != 0) {
-                r->comp_seq[k] = mode == ORC_MODE_SEED_ENUM ? 0u : (uint32_t)g;
-                r->comp_start[k] = m.start[g];
-                ++k;
-            }
-    }
-    r->comp_off[r->n_matches] = k;
+    pack_result(c, mode, r);
     r->t_mers = t1 - t0; r->t_sort = t2 - t1; r->t_match = t3 - t2; r->t_total = t3 - t0;
+    *out = r;
+    return 0;
+}
+
+/* Seed-family search (src/progressiveMauve.cpp:503-548): ONE UniqueMatchFinder runs FindMatches once per seed
+ * pattern, in the order given (the reference sorts the family by seed length and searches the longest first, "so
+ * that overlapping matches tend to get contained"), ClearSequences() in between and one GetMatchList at the end.
+ * The MemHash table persists across the passes (only Clear() empties it), so a candidate of a later pattern is
+ * dropped when an accepted match of ANY earlier pattern contains its seed (same group, D16), it is extended with
+ * its own pattern's window predicate otherwise, and the result is the union of the accepted matches of all passes
+ * in canonical order (D18).  [LM-recall for the persistence; the call sequence is in the tree.] */
+int orc_find_family(uint32_t nseq, const uint8_t* const* ascii, const uint64_t* lens,
+                    const uint64_t* patterns, uint32_t npat, uint64_t nway_mask, orc_result** out) {
+    if (!out || !patterns || npat == 0) return -1;
+    *out = nullptr;
+    for (uint32_t p = 0; p < npat; ++p) if (!seed_valid(patterns[p])) return -2;
+    if (nseq == 0) return -3;
+    if (nseq > 64) return -4;
+    for (uint32_t g = 0; g < nseq; ++g) if (lens[g] >= (1ull << 32)) return -5;
+    Ctx c;
+    c.nseq = nseq; c.lens.assign(lens, lens + nseq);
+    c.mode = ORC_MODE_UNIQUE; c.min_multi = 2; c.max_multi = 1000; c.direct_only = 0; c.nway_mask = nway_mask;
+    orc_result* r = (orc_result*)calloc(1, sizeof(orc_result));
+    r->nseq = nseq;
+    r->unique_mers_per_seq = (uint64_t*)calloc(nseq, sizeof(uint64_t));
+    double t0 = now_s();
+    for (uint32_t p = 0; p < npat; ++p) {
+        seed_init(c.seed, patterns[p]);
+        c.mers.assign(nseq, std::vector<uint64_t>());
+        c.sml.assign(nseq, std::vector<uint32_t>());
+        for (uint32_t g = 0; g < nseq; ++g) {
+            uint64_t n = lens[g] >= (uint64_t)c.seed.L ? lens[g] - c.seed.L + 1 : 0;
+            c.mers[g].resize(n);
+            compute_mers(ascii[g], lens[g], c.seed, c.mers[g].data());
+            r->n_seeds += n;
+            sort_sml(c.mers[g].data(), c.mers[g].size(), c.seed, c.sml[g]);
+        }
+        find_match_seeds(c); /* c.table and c.out carry over to the next pattern */
+    }
+    std::sort(c.out.begin(), c.out.end(), less_unique);
+    pack_result(c, ORC_MODE_UNIQUE, r);
+    r->t_total = r->t_match = now_s() - t0;
     *out = r;
     return 0;
 }

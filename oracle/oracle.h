@@ -53,6 +53,11 @@ int orc_find(uint32_t nseq, const uint8_t* const* ascii, const uint64_t* lens,
              uint64_t pattern, int mode,
              uint64_t min_multi, uint64_t max_multi, int direct_only, uint64_t nway_mask,
              orc_result** out);
+/* Seed-family search: MODE_UNIQUE once per pattern, in the given order, with ONE persistent MemHash table
+ * (src/progressiveMauve.cpp:503-548).  The statistics fields other than n_seeds / n_buckets / n_candidates /
+ * n_contained are not filled. */
+int orc_find_family(uint32_t nseq, const uint8_t* const* ascii, const uint64_t* lens,
+                    const uint64_t* patterns, uint32_t npat, uint64_t nway_mask, orc_result** out);
 void orc_result_free(orc_result* r);
 
 /* Per-position canonical seed mers of one genome: out[p] = key<<(64-2w) | strand,

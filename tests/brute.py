@@ -203,3 +203,47 @@ def find(seqs, pattern, mode, min_multi=2, max_multi=1000, direct_only=False, nw
     accepted.sort(key=sort_key)
     res["matches"] = [(length, sorted(st.items())) for st, length in accepted]
     return res
+
+
+def find_family(seqs, patterns, nway_mask=0):
+    """Seed-family search (src/progressiveMauve.cpp:503-548), the naive way: MODE_UNIQUE once per pattern in the given
+    order, with ONE list of accepted matches that persists across the patterns — a candidate of a later pattern is
+    dropped when an accepted match of any earlier pattern (or an earlier one of its own pass) contains its seed window."""
+    N = len(seqs)
+    lens = [len(s) for s in seqs]
+    accepted = []
+    for pattern in patterns:
+        L = seed_len(pattern)
+        mers = all_mers(seqs, pattern)
+        buckets = {}
+        for g in range(N):
+            for p, (key, strand) in enumerate(mers[g]):
+                buckets.setdefault(key, []).append((g, p, strand))
+        for key in sorted(buckets):
+            b = sorted(buckets[key])
+            if len(b) < 2:
+                continue
+            cnt = {}
+            for g, _, _ in b:
+                cnt[g] = cnt.get(g, 0) + 1
+            uniq = [t for t in b if cnt[t[0]] == 1]
+            if len(uniq) < 2:
+                continue
+            if nway_mask:
+                present = 0
+                for g, _, _ in uniq:
+                    present |= 1 << g
+                if present != nway_mask:
+                    continue
+            first_strand = uniq[0][2]
+            st = {g: (p + 1) if strand == first_strand else -(p + 1) for g, p, strand in uniq}
+            if any(_same_group_contains(e, st, L) for e in accepted):
+                continue
+            accepted.append(extend(mers, lens, st, L))
+
+    def sort_key(m):
+        st, length = m
+        return ([abs(st.get(g, 0)) for g in range(N)], [1 if st.get(g, 0) < 0 else 0 for g in range(N)], length)
+
+    accepted.sort(key=sort_key)
+    return dict(matches=[(length, sorted(st.items())) for st, length in accepted])

@@ -43,6 +43,9 @@ def lib():
         _lib.orc_find.restype = C.c_int
         _lib.orc_find.argtypes = [C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.c_uint64, C.c_int,
                                   C.c_uint64, C.c_uint64, C.c_int, C.c_uint64, C.POINTER(C.POINTER(_Result))]
+        _lib.orc_find_family.restype = C.c_int
+        _lib.orc_find_family.argtypes = [C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_uint32,
+                                         C.c_uint64, C.POINTER(C.POINTER(_Result))]
         _lib.orc_result_free.argtypes = [C.POINTER(_Result)]
         _lib.orc_mers.restype = C.c_int64
         _lib.orc_mers.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]
@@ -87,6 +90,30 @@ def find(seqs, pattern, mode, min_multi=2, max_multi=1000, direct_only=False, nw
         n_seeds=r.n_seeds, n_buckets=r.n_buckets, n_candidates=r.n_candidates, n_contained=r.n_contained,
         t_mers=r.t_mers, t_sort=r.t_sort, t_match=r.t_match, t_total=r.t_total,
     )
+    L.orc_result_free(out)
+    return res
+
+
+def find_family(seqs, patterns, nway_mask=0):
+    """Seed-family search (orc_find_family): MODE_UNIQUE once per pattern, in order, one persistent MemHash table."""
+    L = lib()
+    arrs = [_as_u8(s) for s in seqs]
+    n = len(arrs)
+    ptrs = (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
+    lens = (C.c_uint64 * n)(*[a.size for a in arrs])
+    pats = (C.c_uint64 * len(patterns))(*[int(p) for p in patterns])
+    out = C.POINTER(_Result)()
+    rc = L.orc_find_family(n, ptrs, lens, pats, len(patterns), nway_mask, C.byref(out))
+    if rc != 0:
+        raise RuntimeError(f"orc_find_family failed: {rc}")
+    r = out.contents
+    nm, nc = r.n_matches, r.n_comps
+    res = dict(n_matches=nm, n_comps=nc,
+               length=np.ctypeslib.as_array(r.length, shape=(nm + 1,))[:nm].copy(),
+               comp_off=np.ctypeslib.as_array(r.comp_off, shape=(nm + 1,)).copy(),
+               comp_seq=np.ctypeslib.as_array(r.comp_seq, shape=(nc + 1,))[:nc].copy(),
+               comp_start=np.ctypeslib.as_array(r.comp_start, shape=(nc + 1,))[:nc].copy(),
+               n_candidates=r.n_candidates, n_contained=r.n_contained)
     L.orc_result_free(out)
     return res
 

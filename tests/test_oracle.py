@@ -286,3 +286,36 @@ def test_property_helpers_on_scaled_baseline_configs():
     find = lambda s: O.find(s, pat, O.MODE_UNIQUE)  # noqa: E731
     assert P.check_reverse_complement_equivariance(find, seqs, rc, genomes=(0, 5)) > 5000
     assert P.check_permutation_equivariance(find, seqs, (3, 1, 7, 0, 2, 6, 5, 4)) > 5000
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_seed_family_vs_brute(seed):
+    """Seed-family search (src/progressiveMauve.cpp:503-548): one persistent de-dup table across
+    the patterns, longest seed first.  Oracle against the naive restatement; the GPU path does not have this mode yet."""
+    rng = np.random.default_rng(7000 + seed)
+    seqs = family(rng, 900, 3, sub=0.04, indel=0.004, inv=1 if seed % 2 else 0)
+    if seed == 3:
+        seqs[2] = revcomp(seqs[2])
+    fams = [[0b1101110111110111011, 0b110111011, 0b11111], [0b110010110011010011, 0b1011101, 0b111]]
+    # palindromic patterns of odd weight only
+    pats = [p for p in fams[seed % 2] if O.lib().orc_seed_valid(p)]
+    assert len(pats) >= 2
+    pats.sort(key=lambda p: -p.bit_length())
+    got = as_brute_list(O.find_family(seqs, pats))
+    want = brute.find_family(seqs, pats)["matches"]
+    assert got == want
+    assert len(got) > 5
+    # one pattern alone = the plain search; the family finds at least the matches of its first pattern
+    single = as_brute_list(O.find(seqs, pats[0], O.MODE_UNIQUE))
+    assert as_brute_list(O.find_family(seqs, pats[:1])) == single
+    assert set((ln, tuple(c)) for ln, c in single) <= set((ln, tuple(c)) for ln, c in got)
+
+
+def test_seed_family_later_patterns_are_contained():
+    """two identical genomes: the first (longest) pattern's single match contains every candidate of the later ones"""
+    rng = np.random.default_rng(11)
+    s = rand_seq(rng, 600)
+    pats = [0b1101110111110111011, 0b110111011, 0b111]
+    r = O.find_family([s, s], pats)
+    assert as_brute_list(r) == [(600, [(0, 1), (1, 1)])]
+    assert r["n_contained"] > 1000
