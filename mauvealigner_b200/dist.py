@@ -36,15 +36,32 @@ class _DevBytes:
         self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
 
 
+def _is_host(device):
+    return device is not None and torch.device(device).type == "cpu"
+
+
+def _host_view(ptr, n, ctype, dtype):
+    # host memory (the CPU tests of the orchestration drive it with stand-in contexts whose buffers live on the host)
+    import ctypes
+    import numpy as np
+    return torch.from_numpy(np.ctypeslib.as_array((ctype * int(n)).from_address(int(ptr)))).view(dtype)
+
+
 def dev_bytes(ptr, n, device):
     if n == 0 or not ptr:
         return torch.empty(0, dtype=torch.uint8, device=device)
+    if _is_host(device):
+        import ctypes
+        return _host_view(ptr, n, ctypes.c_uint8, torch.uint8)
     return torch.as_tensor(_DevBytes(ptr, n), device=device)
 
 
 def dev_words(ptr, n, device):
     if n == 0 or not ptr:
         return torch.empty(0, dtype=torch.int64, device=device)
+    if _is_host(device):
+        import ctypes
+        return _host_view(ptr, n, ctypes.c_int64, torch.int64)
     return torch.as_tensor(_DevWords(ptr, n), device=device)
 
 

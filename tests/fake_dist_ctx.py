@@ -1,0 +1,105 @@
+"""A stand-in for mauvealigner_b200.Context on the HOST, for the CPU tests of the multi-GPU orchestration
+(mauvealigner_b200/dist.py::find_unique).  It has no sequence semantics: every stage emits synthetic, self-describing
+words — (kind, source rank, destination rank, index) — and every stage that consumes an exchange checks that exactly the
+words its peers addressed to it arrived, in source-rank order.  That pins the count / offset / width book-keeping of the
+orchestration (the part that runs on the host) without a GPU; the CUDA stages themselves are covered by the GPU tests."""
+import numpy as np
+
+
+def n_seeds(src, dst):
+    return 3 + (src * 7 + dst * 3) % 5
+
+
+def n_rows(src, dst):
+    return (src + 2 * dst) % 4  # some pairs exchange nothing
+
+
+def n_match(src, dst):
+    return 1 + (3 * src + dst) % 3
+
+
+def n_mcomp(src, dst):
+    return 2 * n_match(src, dst) + (src + dst) % 2
+
+
+def word(kind, src, dst, i):
+    return (kind << 56) | (src << 40) | (dst << 24) | i
+
+
+class FakeCtx:
+    def __init__(self, log=None):
+        self.bufs = {}      # receive buffers by `which`
+        self.keep = []      # send buffers stay alive until the next run
+        self.rank = self.world = None
+        self.done = False
+        self.log = log if log is not None else []
+
+    # ---- helpers
+    def _send(self, arr):
+        self.keep.append(arr)
+        return arr.ctypes.data
+
+    def _expect(self, which, kind, count_fn, width=1, what=""):
+        buf = self.bufs[which]
+        exp = []
+        for s in range(self.world):
+            for i in range(count_fn(s, self.rank)):
+                exp += [word(kind, s, self.rank, i * width + k) for k in range(width)]
+        got = buf[:len(exp)].tolist()
+        assert got == exp, (what, self.rank, got[:6], exp[:6])
+
+    # ---- the stage interface find_unique drives (NCCL-style exchanges, p2p = 0)
+    def dist_extract(self, rank, world):
+        self.rank, self.world, self.keep, self.done = rank, world, [], False
+        counts = [n_seeds(rank, d) for d in range(world)]
+        arr = np.array([word(1, rank, d, i) for d in range(world) for i in range(counts[d])], dtype=np.int64)
+        return self._send(arr), counts
+
+    def dist_recv_buffer(self, which, n):
+        self.bufs[which] = np.full(int(n) + 4, 255, dtype=np.uint8) if which == 5 else np.full(int(n) + 4, -1, dtype=np.int64)
+        return self.bufs[which].ctypes.data
+
+    def dist_use_p2p_recv(self, on):
+        assert not on
+
+    def dist_local(self, world, n_recv, nway_mask=0):
+        assert n_recv == sum(n_seeds(s, self.rank) for s in range(world))
+        self._expect(0, 1, n_seeds, what="seed records")
+        self.log.append("local")
+        return [n_rows(self.rank, d) for d in range(world)]
+
+    def dist_rows_pack(self, peer_ptrs=None, peer_row_offsets=None):
+        assert peer_ptrs is None
+        arr = np.array([word(2, self.rank, d, 4 * i + k) for d in range(self.world) for i in range(n_rows(self.rank, d)) for k in range(4)],
+                       dtype=np.int64)
+        return self._send(arr if arr.size else np.zeros(1, dtype=np.int64))
+
+    def dist_resolve(self, n):
+        assert n == sum(n_rows(s, self.rank) for s in range(self.world))
+        self._expect(1, 2, n_rows, width=4, what="candidate rows")
+        # verdict of the i-th row that came from source s
+        v = np.array([(s + i + self.rank) % 2 for s in range(self.world) for i in range(n_rows(s, self.rank))], dtype=np.uint8)
+        return self._send(v if v.size else np.zeros(1, dtype=np.uint8))
+
+    def dist_accept(self):
+        exp = [(self.rank + i + d) % 2 for d in range(self.world) for i in range(n_rows(self.rank, d))]  # by owner, row order
+        assert self.bufs[5][:len(exp)].tolist() == exp, ("verdicts", self.rank)
+        self.hist = np.zeros(4096, dtype=np.int64)
+        self.hist[:4] = self.rank + 1
+        return self.hist.ctypes.data
+
+    def dist_match_partition(self, world):
+        assert self.hist[:4].tolist() == [sum(r + 1 for r in range(world))] * 4 and not self.hist[4:].any(), "histogram all-reduce"
+        return [n_match(self.rank, d) for d in range(world)], [n_mcomp(self.rank, d) for d in range(world)]
+
+    def dist_match_pack(self, *peers):
+        assert not peers
+        h = np.array([word(3, self.rank, d, 2 * i + k) for d in range(self.world) for i in range(n_match(self.rank, d)) for k in range(2)], dtype=np.int64)
+        c = np.array([word(4, self.rank, d, i) for d in range(self.world) for i in range(n_mcomp(self.rank, d))], dtype=np.int64)
+        return self._send(h), self._send(c)
+
+    def dist_output(self, n_m, n_c):
+        assert n_m == sum(n_match(s, self.rank) for s in range(self.world)) and n_c == sum(n_mcomp(s, self.rank) for s in range(self.world))
+        self._expect(3, 3, n_match, width=2, what="match headers")
+        self._expect(4, 4, n_mcomp, what="match components")
+        self.done = True

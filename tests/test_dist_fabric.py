@@ -59,6 +59,60 @@ def test_local_fabric_allreduce():
         assert t.tolist() == [0, 6, 12, 18, 24]
 
 
+def test_orchestration_in_process_world3():
+    """find_unique over stand-in contexts on the host (tests/fake_dist_ctx.py): every stage checks that exactly its
+    peers' words arrived in source-rank order — seeds, 4-word rows, verdict bytes going back, summed histogram, match
+    headers and components."""
+    from fake_dist_ctx import FakeCtx, n_match, n_rows, n_seeds
+    from mauvealigner_b200.dist import find_unique
+    world = 3
+    ctxs = [FakeCtx() for _ in range(world)]
+    for _ in range(2):  # twice: buffers are re-requested every run
+        info = find_unique(ctxs, LocalFabric(world), torch.device("cpu"), p2p=0)
+        assert all(c.done for c in ctxs)
+        for r in range(world):
+            assert info[r]["seeds_sent"] == sum(n_seeds(r, d) for d in range(world))
+            assert info[r]["seeds_received"] == sum(n_seeds(s, r) for s in range(world))
+            assert info[r]["candidates_local"] == sum(n_rows(r, d) for d in range(world))
+            assert info[r]["candidates_owned"] == sum(n_rows(s, r) for s in range(world))
+            assert info[r]["matches"] == sum(n_match(s, r) for s in range(world))
+
+
+def _orchestration_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from fake_dist_ctx import FakeCtx, n_match
+        from mauvealigner_b200.dist import find_unique
+        ctx = FakeCtx()
+        info = find_unique([ctx], TorchFabric(), torch.device("cpu"), p2p=0)
+        ok = ctx.done and info[0]["rank"] == rank and info[0]["matches"] == sum(n_match(s, rank) for s in range(world))
+        out.put((rank, bool(ok)))
+    except Exception as e:  # surfaced by the parent as a failed rank
+        out.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_orchestration_gloo_world2():
+    """the same over two real processes and torch.distributed (gloo): the N > 1 host path of the bench, without a GPU"""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_orchestration_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=100) for _ in range(2))
+    for p in procs:
+        p.join(timeout=30)
+    assert res == {0: True, 1: True}
+
+
 def _worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     import torch.distributed as dist
