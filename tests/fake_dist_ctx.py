@@ -26,6 +26,12 @@ def word(kind, src, dst, i):
     return (kind << 56) | (src << 40) | (dst << 24) | i
 
 
+def _store(base, byte_offset, arr):
+    import ctypes
+    if arr.size:
+        ctypes.memmove(int(base) + int(byte_offset), arr.ctypes.data, arr.nbytes)
+
+
 class FakeCtx:
     def __init__(self, log=None):
         self.bufs = {}      # receive buffers by `which`
@@ -60,7 +66,8 @@ class FakeCtx:
         return self.bufs[which].ctypes.data
 
     def dist_use_p2p_recv(self, on):
-        assert not on
+        if on:
+            self.bufs[0] = self.p2p  # stage 2 reads the array the peers stored into
 
     def dist_local(self, world, n_recv, nway_mask=0):
         assert n_recv == sum(n_seeds(s, self.rank) for s in range(world))
@@ -69,10 +76,39 @@ class FakeCtx:
         return [n_rows(self.rank, d) for d in range(world)]
 
     def dist_rows_pack(self, peer_ptrs=None, peer_row_offsets=None):
-        assert peer_ptrs is None
-        arr = np.array([word(2, self.rank, d, 4 * i + k) for d in range(self.world) for i in range(n_rows(self.rank, d)) for k in range(4)],
-                       dtype=np.int64)
-        return self._send(arr if arr.size else np.zeros(1, dtype=np.int64))
+        blocks = [np.array([word(2, self.rank, d, 4 * i + k) for i in range(n_rows(self.rank, d)) for k in range(4)], dtype=np.int64)
+                  for d in range(self.world)]
+        if peer_ptrs is not None:  # fused exchange 2: rows straight into the owners' buffers
+            for d, b in enumerate(blocks):
+                _store(peer_ptrs[d], 32 * peer_row_offsets[d], b)
+            return None
+        arr = np.concatenate(blocks) if sum(b.size for b in blocks) else np.zeros(1, dtype=np.int64)
+        return self._send(arr)
+
+    # ---- peer-memory variants (p2p levels 1..3; in-process pointers)
+    def dist_extract_count(self, rank, world):
+        self.rank, self.world, self.keep, self.done = rank, world, [], False
+        return [n_seeds(rank, d) for d in range(world)]
+
+    def dist_p2p_recv_array(self, capacity):
+        if getattr(self, "p2p", None) is None or self.p2p.size < capacity + 4:
+            self.p2p = np.full(int(capacity) + 4, -1, dtype=np.int64)
+        else:
+            self.p2p[:] = -1
+        return self.p2p.ctypes.data
+
+    def dist_partition_p2p(self, peer_ptrs, peer_offsets):
+        for d in range(self.world):
+            _store(peer_ptrs[d], 8 * peer_offsets[d], np.array([word(1, self.rank, d, i) for i in range(n_seeds(self.rank, d))], dtype=np.int64))
+
+    def dist_push(self, src_ptr, counts, unit_words, peer_ptrs, dst_offsets):
+        import ctypes
+        off = 0
+        for d in range(self.world):
+            nbytes = counts[d] * unit_words * 8
+            if nbytes:
+                ctypes.memmove(int(peer_ptrs[d]) + dst_offsets[d] * unit_words * 8, int(src_ptr) + off, nbytes)
+            off += nbytes
 
     def dist_resolve(self, n):
         assert n == sum(n_rows(s, self.rank) for s in range(self.world))
@@ -92,11 +128,16 @@ class FakeCtx:
         assert self.hist[:4].tolist() == [sum(r + 1 for r in range(world))] * 4 and not self.hist[4:].any(), "histogram all-reduce"
         return [n_match(self.rank, d) for d in range(world)], [n_mcomp(self.rank, d) for d in range(world)]
 
-    def dist_match_pack(self, *peers):
-        assert not peers
-        h = np.array([word(3, self.rank, d, 2 * i + k) for d in range(self.world) for i in range(n_match(self.rank, d)) for k in range(2)], dtype=np.int64)
-        c = np.array([word(4, self.rank, d, i) for d in range(self.world) for i in range(n_mcomp(self.rank, d))], dtype=np.int64)
-        return self._send(h), self._send(c)
+    def dist_match_pack(self, hdr_ptrs=None, hdr_offsets=None, comp_ptrs=None, comp_offsets=None):
+        hb = [np.array([word(3, self.rank, d, 2 * i + k) for i in range(n_match(self.rank, d)) for k in range(2)], dtype=np.int64)
+              for d in range(self.world)]
+        cb = [np.array([word(4, self.rank, d, i) for i in range(n_mcomp(self.rank, d))], dtype=np.int64) for d in range(self.world)]
+        if hdr_ptrs is not None:  # fused exchange 3
+            for d in range(self.world):
+                _store(hdr_ptrs[d], 16 * hdr_offsets[d], hb[d])
+                _store(comp_ptrs[d], 8 * comp_offsets[d], cb[d])
+            return None
+        return self._send(np.concatenate(hb)), self._send(np.concatenate(cb))
 
     def dist_output(self, n_m, n_c):
         assert n_m == sum(n_match(s, self.rank) for s in range(self.world)) and n_c == sum(n_mcomp(s, self.rank) for s in range(self.world))

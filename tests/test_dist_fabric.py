@@ -62,13 +62,14 @@ def test_local_fabric_allreduce():
 def test_orchestration_in_process_world3():
     """find_unique over stand-in contexts on the host (tests/fake_dist_ctx.py): every stage checks that exactly its
     peers' words arrived in source-rank order — seeds, 4-word rows, verdict bytes going back, summed histogram, match
-    headers and components."""
+    headers and components — for the all-to-all exchanges and for the three peer-memory levels (block offsets from the
+    count matrix, stores / pushes into the peers' buffers)."""
     from fake_dist_ctx import FakeCtx, n_match, n_rows, n_seeds
     from mauvealigner_b200.dist import find_unique
     world = 3
     ctxs = [FakeCtx() for _ in range(world)]
-    for _ in range(2):  # twice: buffers are re-requested every run
-        info = find_unique(ctxs, LocalFabric(world), torch.device("cpu"), p2p=0)
+    for p2p in (0, 0, 1, 2, 3):  # NCCL-style twice (buffers are re-requested every run), then the three peer-memory levels
+        info = find_unique(ctxs, LocalFabric(world), torch.device("cpu"), p2p=p2p)
         assert all(c.done for c in ctxs)
         for r in range(world):
             assert info[r]["seeds_sent"] == sum(n_seeds(r, d) for d in range(world))
