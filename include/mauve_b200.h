@@ -207,17 +207,6 @@ int mb_device_count(void);
 int mb_debug_radix(mb_ctx* ctx, uint64_t n, int shift, int kbits, int reps, float* ms_out);
 const char* mb_version(void);
 
-/* ---- synthetic genomes (host only) ------------------------------
- * Deterministic generator (splitmix64-seeded xoshiro256**, seed 0x4D415556 + config) used by
- * bench.py and the tests.  config 1..5 = BASELINE.json configs C1..C5; scale divides every
- * length (1 = full size).  Sequences are ASCII ACGT in host memory owned by the handle. */
-typedef struct mb_synth mb_synth;
-int mb_synth_create(int config, uint64_t scale, mb_synth** out);
-uint32_t mb_synth_nseq(const mb_synth* s);
-uint64_t mb_synth_len(const mb_synth* s, uint32_t i);
-const uint8_t* mb_synth_seq(const mb_synth* s, uint32_t i);
-void mb_synth_free(mb_synth* s);
-
 #ifdef __cplusplus
 }
 #endif

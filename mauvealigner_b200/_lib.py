@@ -38,8 +38,8 @@ class MbStats(C.Structure):
 
 EXPORTS = ["mb_ctx_create", "mb_ctx_destroy", "mb_set_stream", "mb_add_sequence", "mb_add_sequence_device", "mb_clear_sequences",
            "mb_set_seed", "mb_find", "mb_find_device", "mb_fetch_result", "mb_get_sml", "mb_get_mers", "mb_get_stats", "mb_strerror",
-           "mb_last_cuda_error", "mb_device_count", "mb_version", "mb_synth_create", "mb_synth_nseq", "mb_synth_len", "mb_synth_seq",
-           "mb_synth_free", "mb_dist_extract", "mb_dist_extract_count", "mb_dist_partition", "mb_dist_p2p_recv_array",
+           "mb_last_cuda_error", "mb_device_count", "mb_version",
+           "mb_dist_extract", "mb_dist_extract_count", "mb_dist_partition", "mb_dist_p2p_recv_array",
            "mb_dist_use_p2p_recv", "mb_ipc_export", "mb_ipc_import", "mb_ipc_close", "mb_dist_recv_buffer", "mb_dist_local", "mb_dist_rows_pack", "mb_dist_push", "mb_dist_resolve", "mb_dist_accept", "mb_dist_match_pack", "mb_dist_match_partition", "mb_dist_output", "mb_dist_stage_ms", "mb_find_multi", "mb_debug_radix"]
 
 _lib = None
@@ -72,14 +72,6 @@ def lib():
     L.mb_last_cuda_error.argtypes = [vp]
     L.mb_last_cuda_error.restype = C.c_char_p
     L.mb_version.restype = C.c_char_p
-    L.mb_synth_create.argtypes = [i32, u64, C.POINTER(vp)]
-    L.mb_synth_nseq.argtypes = [vp]
-    L.mb_synth_nseq.restype = C.c_uint32
-    L.mb_synth_len.argtypes = [vp, C.c_uint32]
-    L.mb_synth_len.restype = u64
-    L.mb_synth_seq.argtypes = [vp, C.c_uint32]
-    L.mb_synth_seq.restype = vp
-    L.mb_synth_free.argtypes = [vp]
     pu64 = C.POINTER(u64)
     L.mb_dist_extract.argtypes = [vp, i32, i32, C.POINTER(vp), pu64]
     L.mb_dist_extract_count.argtypes = [vp, i32, i32, pu64]

@@ -389,8 +389,41 @@ def find_unique_emulated(seqs, pattern, world, device=0, nway_mask=0, p2p=None):
 
 
 # ------------------------------------------------------------------------------------------ bench (N > 1)
-def bench_main(args, CONFIG_NAMES, config_params, peaks, ClockSampler):
-    """bench.py --gpus N under torchrun: strong scaling of one configuration (C5 by default) over N ranks."""
+def gather_result_digest(res, world, rank, B, config, mode, scale):
+    """Rank 0 receives every rank's CSR piece over a gloo group (host memory, outside every timed region), joins them in
+    rank order (= canonical order) and hashes the whole result exactly like the single-GPU line does: the only proof that
+    the NCCL + peer-memory path is bit-exact on real GPUs."""
+    import numpy as np
+    import torch.distributed as dist
+    g = dist.new_group(backend="gloo")
+    keys = (("length", np.uint32), ("comp_off", np.uint64), ("comp_seq", np.uint32), ("comp_start", np.int64))
+    mine = {k: np.ascontiguousarray(np.asarray(res[k]).astype(dt, copy=False)) for k, dt in keys}
+    sizes = torch.tensor([mine[k].size for k, _ in keys], dtype=torch.int64)
+    all_sizes = [torch.zeros_like(sizes) for _ in range(world)]
+    dist.all_gather(all_sizes, sizes, group=g)
+    pieces = [dict(n_matches=int(all_sizes[r][0]), n_comps=int(all_sizes[r][2])) for r in range(world)]
+    for j, (k, dt) in enumerate(keys):
+        t = torch.from_numpy(mine[k].view(np.uint8))
+        if rank == 0:
+            bufs = [torch.empty(int(all_sizes[r][j]) * np.dtype(dt).itemsize, dtype=torch.uint8) for r in range(world)]
+            bufs[0] = t
+            reqs = [dist.irecv(bufs[r], src=r, group=g) for r in range(1, world)]
+            for q in reqs:
+                q.wait()
+            for r in range(world):
+                pieces[r][k] = bufs[r].numpy().view(dt)
+        else:
+            dist.send(t, dst=0, group=g)
+    out = None
+    if rank == 0:
+        out = B.parity_of(concat_results(pieces), config, mode, scale)
+    dist.barrier(group=g)
+    return out
+
+
+def bench_main(args, B):
+    """bench.py --gpus N under torchrun: strong scaling of one configuration (C5 by default, the same as N = 1) over N
+    ranks.  B = the bench module (config tables, parity check, rooflines, CPU leg)."""
     import torch.distributed as dist
     import mauvealigner_b200 as mb
 
@@ -403,10 +436,10 @@ def bench_main(args, CONFIG_NAMES, config_params, peaks, ClockSampler):
         dist.init_process_group(backend="nccl", device_id=dev)
     W = max(3, args.warmup)
     config = args.config
-    pattern, mode, kw = config_params(mb, config)
+    pattern, mode, kw = B.config_params(None, config)
     if mode != mb.MODE_UNIQUE:
         raise SystemExit("the multi-GPU path covers MODE_UNIQUE (config 1, 2, 5)")
-    seqs = mb.synth_genomes(config, args.scale)
+    seqs = B.synth.synth_genomes(config, args.scale)
     bp = sum(len(s) for s in seqs)
     ctx = mb.Context(local)
     # one explicit stream for the library kernels, the NCCL exchanges and the timing events (a NULL handle would make
@@ -431,7 +464,7 @@ def bench_main(args, CONFIG_NAMES, config_params, peaks, ClockSampler):
         step()
     sampler = None
     if rank == 0:  # one sampler for the whole job: all GPUs in use, through NVML
-        sampler = ClockSampler(list(range(world)))
+        sampler = B.ClockSampler(list(range(world)))
         sampler.start()
     torch.cuda.synchronize()
     dist.barrier()
@@ -454,11 +487,9 @@ def bench_main(args, CONFIG_NAMES, config_params, peaks, ClockSampler):
     launches = torch.tensor([float(st["kernel_launches"])], device=dev)
     dist.all_reduce(launches, op=dist.ReduceOp.SUM)
     res = ctx.fetch(copy=False)
-    nm = torch.tensor([float(res["n_matches"])], device=dev)
-    dist.all_reduce(nm, op=dist.ReduceOp.SUM)
-    n_matches = int(nm.item())
+    parity = gather_result_digest(res, world, rank, B, config, mode, args.scale)
 
-    # ---- e2e: pinned host ASCII on every rank -> C ABI stages + exchanges -> host CSR on rank 0
+    # ---- e2e: pinned host ASCII on every rank -> C ABI stages + exchanges -> every rank's piece of the CSR in host memory
     pinned = [torch.from_numpy(s).pin_memory() for s in seqs]
 
     def e2e_step():
@@ -482,27 +513,13 @@ def bench_main(args, CONFIG_NAMES, config_params, peaks, ClockSampler):
     st2 = ctx.stats()
     d2h = torch.tensor([float(st2["d2h_bytes"])], device=dev)
     dist.all_reduce(d2h, op=dist.ReduceOp.SUM)
+    e2e_parity = gather_result_digest(r, world, rank, B, config, mode, args.scale)
     if sampler:
         sampler.stop_flag = True
         sampler.join(timeout=2)
 
-    # ---- the same workload through the single-GPU path on rank 0 (outside every timed region): the denominator of
-    # the strong-scaling figure, since the N = 1 line of this bench is quoted on another configuration (C2)
-    single_ms = None
     if rank == 0:
-        ctx.find_device(mode, **kw)
-        torch.cuda.synchronize()
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s0.record(stream)
-        for _ in range(2):
-            ctx.find_device(mode, **kw)
-        s1.record(stream)
-        torch.cuda.synchronize()
-        single_ms = s0.elapsed_time(s1) / 2
-    dist.barrier()
-
-    if rank == 0:
-        peak, peak_src = peaks()
+        peak, peak_src = B.peaks()
         R = st["record_bytes"]
         radix_ms, radix_launches = st["ms_radix_kernels"], st["radix_launches"]
         n_local = info[0]["seeds_received"]
@@ -518,20 +535,19 @@ def bench_main(args, CONFIG_NAMES, config_params, peaks, ClockSampler):
         b_alg = 0.25 + R * (3 + 2 * P)
         path = {"b_alg_bytes_per_bp": b_alg, "achieved": b_alg * bp / (ms_per_step * 1e-3) / 1e9, "unit": "GB/s (all GPUs)"}
         path["frac"] = path["achieved"] / (peak * world)
+        cpu = None if args.no_cpu_baseline else B.cpu_baseline(config, args.scale)
+        cfg = B.config_dict(config, args.scale)
         line = {
-            "metric": "seed-to-multi-MUM input throughput", "value": bp / (ms_per_step * 1e-3) / 1e9, "unit": "Gbp/s", "n_gpus": world,
+            "metric": B.METRIC, "value": bp / (ms_per_step * 1e-3) / 1e9, "unit": "Gbp/s", "n_gpus": world,
             "steps": args.steps, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "u64", "data": "synthetic",
-            "config": {"workload": CONFIG_NAMES[config], "bp_per_step": bp, "n_genomes": len(seqs), "seed_pattern": mb.seeds.pattern_text(pattern),
-                       "scale": args.scale, "parallelism": f"key-range x{world} (seeds), group-hash x{world} (de-dup), canonical-range x{world} (output)",
-                       "l2": "inputs larger than L2", "n_matches": n_matches},
-            "roofline": roofline, "path_roofline": path, "cpu_baseline": None,
+            "dtype": "u64", "data": "synthetic", "config": cfg,
+            "parallelism": f"key-range x{world} (seeds), group-hash x{world} (de-dup), canonical-range x{world} (output); result = the ranks' CSR "
+                           "pieces in rank order (BASELINE.md §3)",
+            "parity": parity, "roofline": roofline, "path_roofline": path, "cpu_baseline": cpu,
             "e2e": {"value": bp / (e2e_ms * 1e-3) / 1e9, "unit": "Gbp/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": st2["h2d_bytes"] * world,
-                    "d2h_bytes_per_step": int(d2h.item())},
+                    "d2h_bytes_per_step": int(d2h.item()), "digest_ok": e2e_parity["digest_ok"]},
             "gpu_launches": int(launches.item()) * args.steps, "stages_ms_rank0": {k: round(v, 4) for k, v in stage.items()},
             "rank0": {k: v for k, v in info[0].items()}, "wall_ms_per_step": wall_ms / args.steps, "clocks": sampler.summary(),
-            "single_gpu_same_workload": {"ms_per_step": single_ms, "value": bp / (single_ms * 1e-3) / 1e9, "unit": "Gbp/s",
-                                         "speedup": single_ms / ms_per_step, "note": "mb_find_device on rank 0, untimed region"},
         }
         print(json.dumps(line), flush=True)
     fabric.release_peer_buffers([ctx])

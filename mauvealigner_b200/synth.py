@@ -1,23 +1,10 @@
-"""Synthetic genomes for BASELINE.json configs C1..C5 (generated by the C++ generator in csrc/synth.cpp)."""
-import ctypes as C
+"""Synthetic genomes for BASELINE.json configs C1..C5: re-export of tools/synth (own host library libmbsynth.so;
+the generator is bench / test infrastructure and is not part of libmauve_b200.so)."""
+import importlib.util
+import os
 
-import numpy as np
-
-from . import _lib as L
-
-
-def synth_genomes(config, scale=1):
-    """Returns a list of numpy uint8 arrays (ASCII ACGT). Deterministic in (config, scale)."""
-    h = C.c_void_p()
-    rc = L.lib().mb_synth_create(int(config), int(scale), C.byref(h))
-    if rc != L.MB_OK:
-        raise L.MauveError(rc)
-    try:
-        out = []
-        for i in range(L.lib().mb_synth_nseq(h)):
-            n = L.lib().mb_synth_len(h, i)
-            p = L.lib().mb_synth_seq(h, i)
-            out.append(np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(n,)).copy())
-        return out
-    finally:
-        L.lib().mb_synth_free(h)
+_path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "synth", "__init__.py")
+_spec = importlib.util.spec_from_file_location("mb_synth_tools", _path)
+_mod = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(_mod)
+synth_genomes = _mod.synth_genomes

@@ -82,3 +82,17 @@ def test_oracle_reproduces_fullsize_digest_c1():
     res = O.find(mb.synth_genomes(1, 1), pattern, mode, **kw)
     assert (res["n_matches"], res["n_comps"]) == (gold["1"]["n_matches"], gold["1"]["n_comps"])
     assert tool.digest(res) == gold["1"]["sha256"]
+
+
+def test_generator_reproduces_genome_digests():
+    """the synthetic genomes are pinned by SHA-256 (tests/golden/genome_sha256.json, tools/genome_hashes.py)."""
+    import hashlib
+    import json
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from tools.synth import synth_genomes
+    want = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "genome_sha256.json")))
+    for c in (1, 2, 5):
+        seqs = synth_genomes(c, 1)
+        assert [hashlib.sha256(s.tobytes()).hexdigest() for s in seqs] == want[f"C{c}"]["sha256"], c
+        assert [len(s) for s in seqs] == want[f"C{c}"]["lengths"]

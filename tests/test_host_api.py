@@ -132,3 +132,26 @@ def test_multi_gpu_entry_points_reject_bad_arguments():
     assert lib.mb_dist_push(None, None, None, 1, None, None) == -1
     assert lib.mb_dist_rows_pack(None, None, None, None) == -1
     assert lib.mb_dist_match_pack(None, None, None, None, None, None, None) == -1
+
+
+def test_product_library_holds_no_generator_and_reference_arm_maps_no_product_library():
+    """The synthetic-genome generator lives in tools/synth/libmbsynth.so, and `bench.py --impl reference` (the CPU arm)
+    must run without mapping libmauve_b200.so."""
+    _build()
+    import mauvealigner_b200 as mb
+    lib = ctypes.CDLL(mb._lib.LIB_PATH)
+    assert not hasattr(lib, "mb_synth_create")
+    code = ("import sys, runpy; sys.argv = ['bench.py', '--impl', 'reference', '--config', '1', '--ref-scale', '200', '--steps', '1', '--warmup', '0'];"
+            "runpy.run_path('bench.py', run_name='__main__');"
+            "maps = open('/proc/self/maps').read();"
+            "assert 'libmauve_b200' not in maps, 'product library mapped by the reference arm';"
+            "assert 'liboracle' in maps and 'libmbsynth' in maps")
+    import subprocess
+    out = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    import json
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "port" and line["value"] > 0
+    sys.path.insert(0, ROOT)
+    import bench
+    assert line["config"] == bench.config_dict(1, 1)  # the same `config` the repo arm prints

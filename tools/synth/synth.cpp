@@ -2,7 +2,7 @@
 // Host only.  PRNG = xoshiro256** seeded by splitmix64(0x4D415556 + config).  Alphabet ACGT.
 // Evolution along a branch: substitutions and geometric-length indels by skip sampling, then
 // inversions (reverse complement in place) and translocations (cut + paste).
-#include "../../include/mauve_b200.h"
+#include "mb_synth.h"
 
 #include <algorithm>
 #include <cmath>
@@ -151,10 +151,10 @@ struct mb_synth { std::vector<Seq> seqs; };
 extern "C" {
 
 int mb_synth_create(int config, uint64_t scale, mb_synth** out) {
-    if (!out || config < 1 || config > 5 || scale == 0) return MB_E_ARG;
+    if (!out || config < 1 || config > 5 || scale == 0) return -1;
     *out = nullptr;
     mb_synth* h = new (std::nothrow) mb_synth();
-    if (!h) return MB_E_NOMEM;
+    if (!h) return -2;
     Rng r(0x4D415556ull + (uint64_t)config);
     try {
         if (config == 1 || config == 2 || config == 5) {
@@ -202,10 +202,10 @@ int mb_synth_create(int config, uint64_t scale, mb_synth** out) {
         }
     } catch (const std::bad_alloc&) {
         delete h;
-        return MB_E_NOMEM;
+        return -2;
     }
     *out = h;
-    return MB_OK;
+    return 0;
 }
 
 uint32_t mb_synth_nseq(const mb_synth* s) { return s ? (uint32_t)s->seqs.size() : 0; }
