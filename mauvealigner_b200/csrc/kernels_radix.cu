@@ -6,11 +6,13 @@
 // src/mauveAligner.cpp:465,585).  Records are emitted in (genome, position) order and every pass
 // is stable, so equal seeds end up ordered by (genome, position) = Appendix A D6.
 //
-// One pass = one kernel ("onesweep"): tiles are taken in order through an atomic ticket, each tile
-// ranks its keys per 8-bit digit (warp __match_any_sync ranking), publishes its digit counts,
-// resolves its global digit offsets by decoupled look-back over earlier tiles, reorders the tile
-// in shared memory and writes each digit's keys as one contiguous burst.
-// Traffic per pass: one read + one write of every record (2R bytes/record).
+// One pass = one kernel ("onesweep"): tiles are taken in order through an atomic ticket; each warp counts its
+// digits with shared atomics, the tile total is published for the decoupled look-back of later tiles, the ranking
+// (atomicOr peer masks in shared memory alternating with ballot rounds — the two load different pipes) yields the
+// tile slot of every record directly, and each digit's records leave the reordered tile as one contiguous burst.
+// Traffic per pass: one read + one write of every record (2R bytes/record); measured limits: the shared-memory
+// data pipe (~75 % busy, bank conflicts of the digit-indexed tables and of the key scatter) and the ALU pipe (~53 %).
+#include <algorithm>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -19,9 +21,21 @@
 #endif
 #define RS_NW (RS_NT / 32)
 #ifndef RS_IPT
-#define RS_IPT 12
+#define RS_IPT 14
 #endif
 #define RS_TILE (RS_NT * RS_IPT)
+#ifndef RS_MINB
+#define RS_MINB 2
+#endif
+#ifndef RS_OR_EVERY
+#define RS_OR_EVERY 2 // every RS_OR_EVERY-th ranking round finds its digit peers through shared-memory atomicOr, the others by ballots
+#endif                // (0: ballots only, 1: atomicOr only); the two load different pipes (ALU / shared memory)
+#ifndef RS_LB
+#define RS_LB 4       // predecessors read per look-back step (independent loads in flight)
+#endif
+#ifndef RS_LB_FIRST
+#define RS_LB_FIRST 1 // warps 0..7 resolve the look-back before they rank (it overlaps the ranking of the other warps)
+#endif
 
 #define LB_FLAG_AGG (1ull << 62)
 #define LB_FLAG_INC (2ull << 62)
@@ -35,11 +49,16 @@ __device__ __forceinline__ u64 ld_volatile_u64(const u64* p) {
 __device__ __forceinline__ void st_volatile_u64(u64* p, u64 v) {
     asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+__device__ __forceinline__ void bar_sync_256() { asm volatile("bar.sync 1, 256;" ::: "memory"); } // warps 0..7 only
 
 #define DIGIT(x) (USE_LUT ? (u32)sLut[(u32)((x) >> shift) & dmask] : ((u32)((x) >> shift) & dmask))
-#ifndef RS_MINB
-#define RS_MINB 2
-#endif
+
+// One CTA = one tile, taken in order through an atomic ticket.  Shared memory: the tile (RS_TILE records: keys and then —
+// HAS_VAL — the values through the same buffer), one table of 256 {lo, hi} entries per warp, 256 global bases.
+//   entry of (warp, digit):  hi = first the warp's count of the digit (shared atomics, before anything else), then — after
+//                                 the scan over digits and warps — the tile slot of the warp's next record of the digit;
+//                            lo = mask of the lanes that hold the digit in the current ranking round (atomicOr rounds)
+// so that the ranking yields the tile slot of every record directly and the keys leave the registers at once.
 template <bool HAS_VAL, bool USE_LUT>
 __global__ void __launch_bounds__(RS_NT, RS_MINB) k_onesweep(const u64* __restrict__ kin, u64* __restrict__ kout,
                                                     const u64* __restrict__ vin, u64* __restrict__ vout, u32 n,
@@ -48,181 +67,155 @@ __global__ void __launch_bounds__(RS_NT, RS_MINB) k_onesweep(const u64* __restri
                                                     u64* const* __restrict__ peers /*[256] or null: output array of every bin */) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u64* sKeys = reinterpret_cast<u64*>(smem_raw);                    // RS_TILE
-    u64* sVals = sKeys + RS_TILE;                                      // RS_TILE when HAS_VAL
-    u32* sWarpHist = reinterpret_cast<u32*>(sKeys + (HAS_VAL ? 2 : 1) * RS_TILE); // RS_NW*256
-    u32* sTilePrefix = sWarpHist + RS_NW * 256;                        // 256 exclusive digit offsets in tile
-    u32* sGlobBase = sTilePrefix + 256;                                // 256: global index of slot 0 of digit (mod 2^32)
+    u64* sMH = sKeys + RS_TILE;                                        // RS_NW * 256 entries
+    u32* sBase = reinterpret_cast<u32*>(sMH + RS_NW * 256);            // 256: global index of tile slot 0 of the digit
     __shared__ u32 sTile;
     __shared__ u32 sWarpSums[8];
     __shared__ u8 sLut[256];
     __shared__ u64* sPeer[USE_LUT ? 256 : 1];
-#ifdef RS_CLAIM_RANK
-    __shared__ u8 sClaim[RS_NW][256];
-#endif
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) sTile = atomicAdd(ticket, 1u);
     if (USE_LUT && tid < 256) { sLut[tid] = lut[tid]; sPeer[tid] = peers ? peers[tid] : kout; }
-    for (int i = tid; i < RS_NW * 256; i += RS_NT) sWarpHist[i] = 0;
+    for (int i = tid; i < RS_NW * 256; i += RS_NT) sMH[i] = 0;
     __syncthreads();
     const u32 tile = sTile;
     const u64 tile_base = (u64)tile * RS_TILE;
     const u32 tile_n = (u32)min((u64)RS_TILE, (u64)n - tile_base);
-
-    // warp-striped load; rk[k] = digit << 16 | rank (the rank is filled in below; a tile has < 65536 records)
-    u64 key[RS_IPT];
-    u32 rk[RS_IPT];
-    const u32 wbase = warp * (RS_IPT * 32);
     const bool full = tile_n == RS_TILE;
-#pragma unroll
-    for (int k = 0; k < RS_IPT; ++k) {
-        u32 o = wbase + k * 32 + lane;
-        key[k] = (o < tile_n) ? kin[tile_base + o] : ~0ull;
-        rk[k] = DIGIT(key[k]) << 16;
-    }
-    // early counts: the tile's digit histogram by shared atomics, published before the (slower) ranking so that
-    // the look-back of later tiles never waits for this tile's ranking
+    const u32 lt_mask = (1u << lane) - 1;
+    const u32 lane_bit = 1u << lane;
+    u64* myMH = sMH + warp * 256;
+    const u32 wbase = warp * (RS_IPT * 32);
+
+    // warp-striped load; the warp's digit counts by shared atomics
+    u64 key[RS_IPT];
+    u32 slot[HAS_VAL ? RS_IPT : 1];
     {
-        u32* sEarly = reinterpret_cast<u32*>(sGlobBase); // 256 x u32, overwritten by sGlobBase only after the look-back
-        if (tid < 256) sEarly[tid] = 0;
-        __syncthreads();
+        const u64* src = kin + tile_base + wbase + lane;
+#pragma unroll
+        for (int k = 0; k < RS_IPT; ++k) key[k] = (full || wbase + k * 32 + lane < tile_n) ? src[k * 32] : ~0ull;
 #pragma unroll
         for (int k = 0; k < RS_IPT; ++k)
-            if (full || wbase + k * 32 + lane < tile_n) atomicAdd(&sEarly[rk[k] >> 16], 1u);
-        __syncthreads();
-        if (tid < 256) st_volatile_u64(lookback + (u64)tile * 256 + tid, (tile == 0 ? LB_FLAG_INC : LB_FLAG_AGG) | (u64)sEarly[tid]);
+            if (full || wbase + k * 32 + lane < tile_n) atomicAdd(reinterpret_cast<u32*>(myMH + DIGIT(key[k])) + 1, 1u);
     }
-    // rank within the warp, per digit, in (k, lane) order.  Peers of a record = lanes holding the same digit:
-    // 8 ballots (one per digit bit; lanes whose bit equals mine = ballot ^ (bit ? 0 : ~0)) are much cheaper
-    // than MATCH.ANY here (measured: 0.44 -> 0.33 ms per pass over 40 M records).  Every peer reads the warp's
-    // running digit counter, the lowest peer lane advances it.
-    u32* myHist = sWarpHist + warp * 256;
-    const u32 lt_mask = (1u << lane) - 1;
-#ifdef RS_CLAIM_RANK
-    // EXPERIMENTAL (build with EXTRA=-DRS_CLAIM_RANK; not the default: written at the end of r01 without GPU time left to
-    // measure it, logic checked lane by lane in a host simulation).  Per-warp claim table: every lane stores its lane id at
-    // its digit and reads the entry back.  A lane that reads itself back either holds its digit alone in this round — the
-    // usual case with 256 bins and 32 lanes — or is the one winner of a colliding group; the lanes that read someone
-    // else's id know they collide.  Only the colliding groups (about two per round on uniform digits) cost a ballot each.
-#pragma unroll
-    for (int k = 0; k < RS_IPT; ++k) {
-        const u32 d = rk[k] >> 16;
-        const bool valid = full || wbase + k * 32 + lane < tile_n;
-        if (valid) sClaim[warp][d] = (u8)lane;
-        __syncwarp();
-        const u32 w = valid ? (u32)sClaim[warp][d] : (u32)lane;
-        u32 lost = __ballot_sync(0xFFFFFFFFu, w != (u32)lane); // also orders this round's loads before the next round's stores
-        u32 below = 0, size = 1;
-        while (lost) { // warp-uniform
-            const int leader = __ffs(lost) - 1;
-            const u32 dl = __shfl_sync(0xFFFFFFFFu, d, leader);
-            const bool in = valid && d == dl;
-            const u32 grp = __ballot_sync(0xFFFFFFFFu, in);
-            if (in) { below = __popc(grp & lt_mask); size = __popc(grp); }
-            lost &= ~grp;
-        }
-        const u32 old = valid ? myHist[d] : 0u;
-        __syncwarp();
-        if (valid && below == 0) myHist[d] = old + size;
-        __syncwarp();
-        rk[k] |= old + below;
-    }
-#else
-#pragma unroll
-    for (int k = 0; k < RS_IPT; ++k) {
-        const u32 d = rk[k] >> 16;
-        u32 pm = 0xFFFFFFFFu;
-#pragma unroll
-        for (int bit = 0; bit < 8; ++bit) {
-            const bool b = (d >> bit) & 1u;
-            pm &= __ballot_sync(0xFFFFFFFFu, b) ^ (b ? 0u : 0xFFFFFFFFu);
-        }
-        if (!full) {
-            const bool valid = wbase + k * 32 + lane < tile_n;
-            pm &= __ballot_sync(0xFFFFFFFFu, valid);
-            if (!valid) pm = 0;
-        }
-        const u32 old = myHist[d];
-        __syncwarp();
-        const u32 below = pm & lt_mask;
-        if (below == 0 && pm != 0) myHist[d] = old + __popc(pm);
-        __syncwarp();
-        rk[k] |= old + __popc(below);
-    }
-#endif
     __syncthreads();
 
-    // per digit: exclusive scan across warps, tile total, look-back
-    u32 tile_count = 0;
+    // warps 0..7, thread = digit: tile count (published at once), exclusive scan over the digits, slot bases of the warps
+    u32 tile_count = 0, tile_prefix = 0;
     if (tid < 256) {
-        u32 acc = 0;
+        u32 c[RS_NW];
 #pragma unroll
-        for (int w = 0; w < RS_NW; ++w) {
-            u32 t = sWarpHist[w * 256 + tid];
-            sWarpHist[w * 256 + tid] = acc;
-            acc += t;
-        }
-        tile_count = acc;
-    }
-    // exclusive scan of tile_count over the 256 digits (threads 0..255 = 8 warps)
-    {
-        u32 v = tile_count, x = v;
+        for (int w = 0; w < RS_NW; ++w) { c[w] = reinterpret_cast<const u32*>(sMH + w * 256 + tid)[1]; tile_count += c[w]; }
+        st_volatile_u64(lookback + (u64)tile * 256 + tid, (tile == 0 ? LB_FLAG_INC : LB_FLAG_AGG) | (u64)tile_count);
+        u32 x = tile_count;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             u32 y = __shfl_up_sync(0xFFFFFFFFu, x, o);
             if (lane >= o) x += y;
         }
-        if (tid < 256 && lane == 31) sWarpSums[warp] = x;
-        __syncthreads();
-        if (tid < 256) {
-            u32 pre = 0;
-            for (int w = 0; w < warp; ++w) pre += sWarpSums[w];
-            sTilePrefix[tid] = pre + x - v;
-        }
-    }
-    if (tid < 256) {
-        u64 excl = 0;
-        if (tile > 0) {
-            i64 t = (i64)tile - 1;
-            while (true) {
-                u64 s = ld_volatile_u64(lookback + (u64)t * 256 + tid);
-                if ((s >> 62) == 0) continue; // not published yet
-                excl += s & LB_MASK;
-                if (s & LB_FLAG_INC) break;
-                --t;
-            }
-            st_volatile_u64(lookback + (u64)tile * 256 + tid, LB_FLAG_INC | (excl + tile_count));
-        }
-        sGlobBase[tid] = digit_base[tid] + (u32)excl - sTilePrefix[tid];
+        if (lane == 31) sWarpSums[warp] = x;
+        bar_sync_256();
+        u32 pre = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) pre += (w < warp) ? sWarpSums[w] : 0u;
+        tile_prefix = pre + x - tile_count;
+        u32 acc = tile_prefix;
+#pragma unroll
+        for (int w = 0; w < RS_NW; ++w) { sMH[w * 256 + tid] = (u64)acc << 32; acc += c[w]; }
     }
     __syncthreads();
 
-    // reorder in shared memory
-    u32 slot[RS_IPT];
+    auto look_back = [&]() {
+        u64 excl = 0;
+        if (tile > 0) {
+            i64 t = (i64)tile - 1;
+            bool done = false;
+            while (!done) {
+                u64 s[RS_LB];
+#pragma unroll
+                for (int j = 0; j < RS_LB; ++j) s[j] = ld_volatile_u64(lookback + (u64)(t - j > 0 ? t - j : 0) * 256 + tid);
+#pragma unroll
+                for (int j = 0; j < RS_LB; ++j) {
+                    if (done || (s[j] >> 62) == 0) break; // not published yet: read again from there
+                    excl += s[j] & LB_MASK;
+                    if (s[j] & LB_FLAG_INC) done = true;
+                    --t;
+                }
+            }
+            st_volatile_u64(lookback + (u64)tile * 256 + tid, LB_FLAG_INC | (excl + tile_count));
+        }
+        sBase[tid] = digit_base[tid] + (u32)excl - tile_prefix; // n < 2^31: 32-bit wrap-around arithmetic is exact
+    };
+    if (RS_LB_FIRST && tid < 256) look_back();
+
+    // ---- rank within the warp, per digit, in (k, lane) order.  Peers of a record = lanes holding the same digit in this
+    // round, found either by an atomicOr of the lane bit into the entry of the digit (shared-memory pipe) or by 8 ballots
+    // (ALU pipe; both measured in tools/ubench/ub_rank.cu); the lowest peer advances the warp's next slot of the digit.
 #pragma unroll
     for (int k = 0; k < RS_IPT; ++k) {
-        u32 o = wbase + k * 32 + lane;
-        if (full || o < tile_n) {
-            u32 d = rk[k] >> 16;
-            slot[k] = sTilePrefix[d] + myHist[d] + (rk[k] & 0xFFFFu);
-            sKeys[slot[k]] = key[k];
+        const u32 d = DIGIT(key[k]);
+        const bool valid = full || wbase + k * 32 + lane < tile_n;
+        u32* e32 = reinterpret_cast<u32*>(myMH + d);
+        u32 pm, old;
+        if (RS_OR_EVERY != 0 && (k % RS_OR_EVERY) == RS_OR_EVERY - 1) {
+            if (valid) atomicOr(e32, lane_bit);
+            __syncwarp();
+            const u64 e = myMH[d];
+            __syncwarp();
+            pm = valid ? (u32)e : 0u; old = (u32)(e >> 32);
+            if (valid && (pm & lt_mask) == 0) myMH[d] = (u64)(old + __popc(pm)) << 32;
+        } else {
+            u32 differ = 0;
+#pragma unroll
+            for (int bit = 0; bit < 8; ++bit) {
+                const bool b = (d >> bit) & 1u;
+                differ |= __ballot_sync(0xFFFFFFFFu, b) ^ (b ? 0xFFFFFFFFu : 0u);
+            }
+            pm = ~differ;
+            if (!full) { pm &= __ballot_sync(0xFFFFFFFFu, valid); if (!valid) pm = 0; }
+            old = e32[1];
+            __syncwarp();
+            if (pm != 0 && (pm & lt_mask) == 0) e32[1] = old + __popc(pm);
+        }
+        __syncwarp();
+        const u32 sl = old + __popc(pm & lt_mask);
+        if (valid) sKeys[sl] = key[k];
+        if (HAS_VAL) slot[k] = sl;
+    }
+    if (HAS_VAL) { // the values follow through the same buffer; their loads overlap the key stores
+        const u64* src = vin + tile_base + wbase + lane;
+#pragma unroll
+        for (int k = 0; k < RS_IPT; ++k) key[k] = (full || wbase + k * 32 + lane < tile_n) ? src[k * 32] : 0ull;
+    }
+    if (!RS_LB_FIRST && tid < 256) look_back();
+    __syncthreads();
+
+    // every digit's records leave as one contiguous burst
+    u32 dst[HAS_VAL ? RS_IPT : 1];
+#pragma unroll
+    for (int j = 0; j < RS_IPT; ++j) {
+        const u32 s = tid + j * RS_NT;
+        if (full || s < tile_n) {
+            const u64 kk = sKeys[s];
+            const u32 d = DIGIT(kk);
+            const u32 o = sBase[d] + s;
+            if (USE_LUT) sPeer[d][o] = kk; // the bins may live in other GPUs' memory (NVLink peer stores)
+            else kout[o] = kk;
+            if (HAS_VAL) dst[j] = o;
         }
     }
     if (HAS_VAL) {
+        __syncthreads();
 #pragma unroll
-        for (int k = 0; k < RS_IPT; ++k) {
-            u32 o = wbase + k * 32 + lane;
-            if (o < tile_n) sVals[slot[k]] = vin[tile_base + o];
+        for (int k = 0; k < RS_IPT; ++k)
+            if (full || wbase + k * 32 + lane < tile_n) sKeys[slot[k]] = key[k];
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < RS_IPT; ++j) {
+            const u32 s = tid + j * RS_NT;
+            if (full || s < tile_n) vout[dst[j]] = sKeys[s];
         }
-    }
-    __syncthreads();
-    for (u32 s = tid; s < tile_n; s += RS_NT) {
-        u64 kk = sKeys[s];
-        u32 d = DIGIT(kk);
-        u32 dst = sGlobBase[d] + s; // n < 2^31: 32-bit wrap-around arithmetic is exact
-        if (USE_LUT) sPeer[d][dst] = kk; // the bins may live in other GPUs' memory (NVLink peer stores)
-        else kout[dst] = kk;
-        if (HAS_VAL) vout[dst] = sVals[s];
     }
 }
 
@@ -242,9 +235,7 @@ __global__ void __launch_bounds__(256) k_scan_hist(const u32* __restrict__ hist,
     base[blockIdx.x * 256 + t] = s[t] - h[t];
 }
 
-size_t radix_smem_bytes(bool has_val) {
-    return (size_t)(has_val ? 2 : 1) * RS_TILE * 8 + RS_NW * 256 * 4 + 256 * 4 + 256 * 8;
-}
+size_t radix_smem_bytes(bool) { return (size_t)RS_TILE * 8 + RS_NW * 256 * 8 + 256 * 4; }
 u32 radix_tile_size() { return RS_TILE; }
 
 void launch_scan_hist(const u32* d_hist, u32* d_base, int npass, cudaStream_t st) {
