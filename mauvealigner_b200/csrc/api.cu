@@ -561,21 +561,23 @@ int mbi_dedup(mb_ctx* c, u32 n_cand, u64 bases, const u64* rows) {
     c->stats.n_extended = n_rep;
     c->n_rep = n_rep;
     da.n_rep = n_rep;
-    // ---- reps in (group colour, slot) order
+    // ---- sort keys of the reps (group colour, slot) and, single-GPU path, their extension records in slot order
     u64 *skA = c->sort_kA.as<u64>(), *skB = c->sort_kB.as<u64>();
     launch_rep_keys(da, skA, st); LAUNCHED(c);
-    TRY(mbi_sort_records(c, &skA, &skB, nullptr, nullptr, n_rep, 32, 16, false));
-    da.s_key = skA;
     cudaEventRecord(c->ev_x[0], st);
-    // ---- extend every rep, then resolve
-    if (rows) {
-        launch_rep_setup(da, st);
-        launch_extent_ranges(da, c->gt, st);
-        if (n_rep) c->stats.kernel_launches += 2;
-    } else {
-        launch_extend(da, c->gt, c->sd, st);
+    // ---- extend every rep (in slot order: neighbouring reps share genome sectors)
+    if (!rows) {
+        DedupArgs dx = da;
+        dx.bitmap = nullptr; // extents only; the slot ranges follow in (colour, slot) order below
+        launch_extend(dx, c->gt, c->sd, st);
         if (n_rep) c->stats.kernel_launches += extend_launches();
     }
+    // ---- reps in (group colour, slot) order, per-rep records, slot ranges of the extents
+    TRY(mbi_sort_records(c, &skA, &skB, nullptr, nullptr, n_rep, 32, 16, false));
+    da.s_key = skA;
+    launch_rep_setup(da, c->gt, st);
+    if (n_rep) LAUNCHED(c);
+    if (rows) { launch_extent_ranges(da, c->gt, st); if (n_rep) LAUNCHED(c); }
     CHECK_LAUNCH(c);
     cudaEventRecord(c->ev_x[3], st);
     const bool want_trace = getenv("MB_DEDUP_TRACE") != nullptr;

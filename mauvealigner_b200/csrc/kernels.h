@@ -110,9 +110,10 @@ u32 chain_tile();
 void launch_chains(const DedupArgs& a, u64* status_fwd, u32* ticket_fwd, u64* status_bwd, u32* ticket_bwd, cudaStream_t st);
 void launch_rep_keys(const DedupArgs& a, u64* skey, cudaStream_t st);
 int extend_launches();
-// setup: gather the per-rep records first (k_rep_setup); false when a.xrec is already filled (launch_cand_xrec)
-void launch_extend(const DedupArgs& a, const GenomeTable& gt, const SeedDev& sd, cudaStream_t st, bool setup = true);
-void launch_rep_setup(const DedupArgs& a, cudaStream_t st);
+// extends the a.n_rep items of a.xrec (filled by launch_rep_keys in slot order, or by launch_cand_xrec); a.bitmap == null:
+// extents only, the slot ranges are derived later (launch_rep_setup / launch_extent_ranges)
+void launch_extend(const DedupArgs& a, const GenomeTable& gt, const SeedDev& sd, cudaStream_t st);
+void launch_rep_setup(const DedupArgs& a, const GenomeTable& gt, cudaStream_t st);
 // multi-GPU source side: every candidate is its own "rep" (a.n_rep = a.n_cand, extension records straight from the CSR)
 void launch_cand_xrec(const DedupArgs& a, const GenomeTable& gt, cudaStream_t st);
 // multi-GPU owner side: slot ranges of the reps' extents from the extents that came with the rows

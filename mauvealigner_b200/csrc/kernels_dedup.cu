@@ -230,13 +230,22 @@ __global__ void __launch_bounds__(CH_NT) k_chain(DedupArgs a, u64* status, u32* 
 // Reps in slot order (bitmap ranks) -> sort key (group colour = top 16 bits of the group hash, slot).
 // Two stable radix passes on the colour (driver) then put the reps of one group next to each other,
 // ordered along their diagonal, so "the reps of my group inside my extent" is a short index range.
+// Single-GPU path: also the extension record of the rep, in SLOT order — the extension runs over the reps in
+// (first genome, position) order, where neighbouring reps read the same genome sectors (L1 hits) instead of the
+// (colour, slot) order of the resolve step, where every component window is a random L2 access.
 __global__ void __launch_bounds__(256) k_rep_keys(DedupArgs a, u64* __restrict__ skey) {
     u32 s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= a.n_cand) return;
     u64 w = a.rep_bits[s >> 6];
     if (!((w >> (s & 63)) & 1)) return;
     u32 idx = a.rep_rank[s >> 6] + (u32)__popcll(w & ((1ull << (s & 63)) - 1));
-    skey[idx] = ((a.slot_rec[2 * (size_t)s].x >> 48) << 32) | s;
+    const ulonglong2 r = a.slot_rec[2 * (size_t)s];
+    skey[idx] = ((r.x >> 48) << 32) | s;
+    if (!a.rows) {
+        const ulonglong2 q = a.slot_rec[2 * (size_t)s + 1];
+        const u32 c = (u32)r.y, m = (u32)(r.y >> 32) & 0xFFu, g0 = (u32)(r.y >> 40) & 0xFFu, vg = (u32)(r.y >> 48) & 0xFFu;
+        a.xrec[idx] = make_uint4(c, (u32)q.y, m | (g0 << 8) | (vg << 16), (u32)(q.y >> 32));
+    }
 }
 
 // ---- extension -----------------------------------------------------------------------------------
@@ -546,7 +555,7 @@ __device__ __forceinline__ bool rec_same_hash(const ulonglong2& p, const ulonglo
 
 // ---- per-rep records in (colour, slot) order: everything the extension and the resolve rounds need about a
 // rep, gathered once by a plain throughput kernel so that those kernels start from one coalesced load
-__global__ void __launch_bounds__(256) k_rep_setup(DedupArgs a) {
+__global__ void __launch_bounds__(256) k_rep_setup(DedupArgs a, GenomeTable gt) {
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n_rep) return;
     const u32 slot = (u32)a.s_key[i];
@@ -559,7 +568,12 @@ __global__ void __launch_bounds__(256) k_rep_setup(DedupArgs a) {
     a.minrank[i] = INF64; a.minrank[(size_t)a.n_rep + i] = INF64;
     a.reach[i] = 0;
     a.rstate[i] = 0;
-    a.xrec[i] = make_uint4(c, (u32)q.y, m | (g0 << 8) | (vg << 16), (u32)(q.y >> 32));
+    if (a.rows) a.xrec[i] = make_uint4(c, (u32)q.y, m | (g0 << 8) | (vg << 16), (u32)(q.y >> 32)); // owner side: k_extent_ranges follows
+    else { // the extension (slot order) has run: slot range of the extent
+        u32 rlo, rhi;
+        extent_slots(a, gt.vbase[vg] + (u32)(q.y >> 32), a.ext_l[c], a.ext_r[c], rlo, rhi);
+        a.rng_lo[i] = rlo; a.rng_hi[i] = rhi;
+    }
 }
 
 // multi-GPU source side: extension record of every candidate, straight from the CSR (rep index = candidate)
@@ -944,9 +958,9 @@ void launch_rep_keys(const DedupArgs& a, u64* skey, cudaStream_t st) {
 // k_extend over all reps, then DD_EXT_MORE launches over the shrinking list of unfinished reps (ping-pong lists
 // wd0 / wd1 with counters ctr[12] / ctr[13]), then the warp-per-rep kernel for what is left
 #define DD_EXT_MORE 3
-int extend_launches() { return 3 + DD_EXT_MORE; }
-void launch_rep_setup(const DedupArgs& a, cudaStream_t st) {
-    if (a.n_rep) k_rep_setup<<<div_up(a.n_rep, 256), 256, 0, st>>>(a);
+int extend_launches() { return 2 + DD_EXT_MORE; }
+void launch_rep_setup(const DedupArgs& a, const GenomeTable& gt, cudaStream_t st) {
+    if (a.n_rep) k_rep_setup<<<div_up(a.n_rep, 256), 256, 0, st>>>(a, gt);
 }
 void launch_cand_xrec(const DedupArgs& a, const GenomeTable& gt, cudaStream_t st) {
     if (a.n_cand) k_cand_xrec<<<div_up(a.n_cand, 256), 256, 0, st>>>(a, gt);
@@ -954,11 +968,10 @@ void launch_cand_xrec(const DedupArgs& a, const GenomeTable& gt, cudaStream_t st
 void launch_extent_ranges(const DedupArgs& a, const GenomeTable& gt, cudaStream_t st) {
     if (a.n_rep) k_extent_ranges<<<div_up(a.n_rep, 256), 256, 0, st>>>(a, gt);
 }
-void launch_extend(const DedupArgs& a, const GenomeTable& gt, const SeedDev& sd, cudaStream_t st, bool setup) {
+void launch_extend(const DedupArgs& a, const GenomeTable& gt, const SeedDev& sd, cudaStream_t st) {
     if (a.n_rep == 0) return;
     u32* list[2] = {a.wd0, a.wd1};
     u32* cnt[2] = {a.ctr + 12, a.ctr + 13};
-    if (setup) k_rep_setup<<<div_up(a.n_rep, 256), 256, 0, st>>>(a);
     k_extend<<<div_up(a.n_rep, DD_NT), DD_NT, 0, st>>>(a, gt, sd, list[0], cnt[0]);
     for (int r = 0; r < DD_EXT_MORE; ++r) {
         int in = r & 1, out = in ^ 1;
