@@ -110,8 +110,17 @@ int mb_set_seed(mb_ctx* ctx, uint64_t pattern);
  * GetMatchList (src/progressiveMauve.cpp:446-451,492-495; src/repeatoire.cpp:1850,1866-1867;
  * src/mauveAligner.cpp:465,585).  Equivalent to mb_find_device + mb_fetch_result. */
 int mb_find(mb_ctx* ctx, const mb_params* params, const mb_result** out);
+/* MemHash keeps its hash table across FindMatches calls until Clear() — the seed-family search relies on it
+ * (src/progressiveMauve.cpp:503-548: FindMatches per seed pattern, ClearSequences() in between, ONE GetMatchList and
+ * Clear() at the end).  on != 0: every MB_MODE_UNIQUE search of this context from now on drops the candidates whose
+ * seed lies inside a match of an earlier search (same genome set, strands and diagonal) before its own de-dup, and adds
+ * the matches it accepts to the table; each search still returns only its own matches (the host finder unions them,
+ * include/mems_compat/mems_compat.h).  on == 0: the table is forgotten (MemHash::Clear()).  Single-GPU searches only. */
+int mb_accumulate(mb_ctx* ctx, int on);
 /* Device part only: packed sequences resident in HBM -> canonical match CSR resident in HBM.
- * Asynchronous on the context stream. */
+ * Launches on the context stream; it reads a few counters back on the way (buffer sizes), so it returns with the stream
+ * drained up to the output stage.  FindMatchesFromPosition's start offsets (src/mauveAligner.cpp:585) have no
+ * counterpart: a search always covers the whole sequences. */
 int mb_find_device(mb_ctx* ctx, const mb_params* params);
 /* Device -> pinned host copy of the last mb_find_device result (synchronises the stream). */
 int mb_fetch_result(mb_ctx* ctx, const mb_result** out);

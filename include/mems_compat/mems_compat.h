@@ -23,6 +23,7 @@
 #ifndef MEMS_COMPAT_H
 #define MEMS_COMPAT_H
 
+#include <algorithm>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -429,17 +430,26 @@ public:
     MemHash(const MemHash& o) : MatchFinder(o), mask_(o.mask_) {}
     virtual MemHash* Clone() const { return new MemHash(*this); }
 
-    /* FindMatches(MatchList&): adds every sequence of the list, searches, and appends the matches to the list
-     * (GetMatchList semantics, src/progressiveMauve.cpp:538-547). */
+    /* FindMatches(MatchList&): adds every sequence of the list, searches, and fills the list with the matches found so
+     * far (GetMatchList semantics, src/progressiveMauve.cpp:538-547).  As in libMems the table persists until Clear():
+     * a second FindMatches (the seed-family search, src/progressiveMauve.cpp:503-548, makes three with ClearSequences()
+     * in between) drops every candidate that a match found so far contains — on the device, mb_accumulate — and
+     * GetMatchList returns the union of all calls in canonical order. */
     virtual boolean FindMatches(MatchList& match_list) {
         for (size_t i = 0; i < match_list.seq_table.size(); ++i)
             if (!AddSequence(match_list.sml_table[i], match_list.seq_table[i])) {
                 genome::ErrorMsg("Error adding " + (i < match_list.seq_filename.size() ? match_list.seq_filename[i] : std::string("sequence")) + "\n");
                 return false;
             }
-        found_.clear();
+        if (!more_.empty() && !found_.empty()) {
+            genome::ErrorMsg("FindMatches: a second search into the same table is not available with MAUVE_B200_DEVICES (call Clear() first)\n");
+            return false;
+        }
+        if (ctx_ && more_.empty()) mb_accumulate(ctx_, 1);
+        const size_t before = found_.size();
         mb_params p = {MB_MODE_UNIQUE, 0, 2, 1000, mask_};
         if (!run(p, found_, true)) return false;
+        if (before) std::sort(found_.begin(), found_.end(), canonical_less);
         GetMatchList(match_list);
         return true;
     }
@@ -450,8 +460,25 @@ public:
         ml.clear();
         for (Match* m : found_) ml.push_back(m->Copy());
     }
-    virtual void Clear() { for (Match* m : found_) m->Free(); found_.clear(); }
+    virtual void Clear() {
+        for (Match* m : found_) m->Free();
+        found_.clear();
+        if (ctx_) mb_accumulate(ctx_, 0);
+    }
     virtual ~MemHash() { for (Match* m : found_) m->Free(); }
+    /* canonical order of the match list: |start| per sequence, then signs, then length */
+    static bool canonical_less(const Match* a, const Match* b) {
+        const uint n = a->SeqCount();
+        for (uint i = 0; i < n; ++i) {
+            int64 x = a->Start(i) < 0 ? -a->Start(i) : a->Start(i), y = b->Start(i) < 0 ? -b->Start(i) : b->Start(i);
+            if (x != y) return x < y;
+        }
+        for (uint i = 0; i < n; ++i) {
+            bool x = a->Start(i) < 0, y = b->Start(i) < 0;
+            if (x != y) return y;
+        }
+        return a->Length() < b->Length();
+    }
 protected:
     uint64 mask_;
     MatchList found_;
@@ -465,7 +492,7 @@ public:
     virtual boolean FindMatches(MatchList& match_list) {
         for (size_t i = 0; i < match_list.seq_table.size(); ++i)
             if (!AddSequence(match_list.sml_table[i], match_list.seq_table[i])) return false;
-        found_.clear();
+        Clear(); /* pairs of one search only (no table across calls on this policy) */
         mb_params p = {MB_MODE_PAIRWISE, 0, 2, 1000, 0};
         if (!run(p, found_, true)) return false;
         GetMatchList(match_list);

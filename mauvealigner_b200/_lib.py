@@ -36,7 +36,7 @@ class MbStats(C.Structure):
                [("ms_radix_kernels", C.c_float), ("radix_launches", C.c_uint32)]
 
 
-EXPORTS = ["mb_ctx_create", "mb_ctx_destroy", "mb_set_stream", "mb_add_sequence", "mb_add_sequence_device", "mb_clear_sequences",
+EXPORTS = ["mb_ctx_create", "mb_ctx_destroy", "mb_set_stream", "mb_add_sequence", "mb_add_sequence_device", "mb_clear_sequences", "mb_accumulate",
            "mb_set_seed", "mb_find", "mb_find_device", "mb_fetch_result", "mb_get_sml", "mb_get_mers", "mb_get_stats", "mb_strerror",
            "mb_last_cuda_error", "mb_device_count", "mb_version",
            "mb_dist_extract", "mb_dist_extract_count", "mb_dist_partition", "mb_dist_p2p_recv_array",
@@ -60,6 +60,7 @@ def lib():
     L.mb_add_sequence.argtypes = [vp, vp, u64, i32, C.POINTER(i32)]
     L.mb_add_sequence_device.argtypes = [vp, vp, u64, C.POINTER(i32)]
     L.mb_clear_sequences.argtypes = [vp]
+    L.mb_accumulate.argtypes = [vp, i32]
     L.mb_set_seed.argtypes = [vp, u64]
     L.mb_find.argtypes = [vp, C.POINTER(MbParams), C.POINTER(C.POINTER(MbResult))]
     L.mb_find_device.argtypes = [vp, C.POINTER(MbParams)]

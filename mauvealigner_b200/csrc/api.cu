@@ -92,7 +92,8 @@ int mb_ctx_destroy(mb_ctx* c) {
                     &c->status, &c->scalars, &c->per_seq, &c->tile_first, &c->cand_run, &c->cand_off, &c->cand_aux, &c->comp_pos, &c->comp_gs,
                     &c->bitmap, &c->bmrank, &c->cand_at, &c->cstate, &c->covered, &c->ghash2, &c->rep_cand, &c->s_h2, &c->reach, &c->xstate, &c->xrec, &c->x_lut, &c->x_counts, &c->x_hdr_s, &c->x_comp_s, &c->x_hdr_r, &c->x_comp_r, &c->x_m, &c->x_key, &c->x_item, &c->x_peers, &c->x_recv, &c->q_off, &c->q_pos, &c->q_gs, &c->q_el, &c->q_er, &c->q_perm, &c->q_state, &c->q_item, &c->x_acc_s, &c->x_acc_r, &c->minrank, &c->ext_l, &c->ext_r, &c->wl_a, &c->wl_b, &c->wl_c, &c->wl_long, &c->wd_a, &c->wd_b, &c->wd_c, &c->live_bits, &c->trace, &c->ghash, &c->slot_gp, &c->slot_hash, &c->link_bits, &c->chain_min, &c->rep_bits, &c->rep_rank, &c->s_hash, &c->s_cand, &c->rng_lo, &c->rng_hi, &c->flags,
                     &c->match_idx, &c->sort_kA, &c->sort_kB, &c->sort_vA, &c->sort_vB, &c->ncomp, &c->mers_tmp, &c->out_len, &c->out_off,
-                    &c->out_seq, &c->out_start};
+                    &c->out_seq, &c->out_start, &c->fam_th1, &c->fam_th2, &c->fam_tx, &c->fam_tend, &c->fam_sh1, &c->fam_sh2, &c->fam_sx, &c->fam_send,
+                    &c->fam_spmax, &c->fam_srun0, &c->fam_drop};
     for (DBuf* b : bufs) free_buf(*b);
     void* hs[] = {c->h_len, c->h_off, c->h_seq, c->h_start, c->h_perseq, c->h_scal};
     for (void* h : hs) if (h) cudaFreeHost(h);
@@ -113,6 +114,17 @@ int mb_set_stream(mb_ctx* c, void* s) {
         CUDA_TRY(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         c->own_stream = true;
     }
+    return MB_OK;
+}
+
+/* The MemHash table of libMems persists across FindMatches calls until Clear() (the seed-family search of
+ * src/progressiveMauve.cpp:503-548 relies on it).  on != 0: every MB_MODE_UNIQUE search from now on drops the candidates
+ * whose seed lies inside a match of an earlier search of the same group and adds its own matches to the table;
+ * on == 0: the table is forgotten (MemHash::Clear()). */
+int mb_accumulate(mb_ctx* c, int on) {
+    if (!c) return MB_E_ARG;
+    if (on) { c->fam_on = true; return MB_OK; }
+    c->fam_on = false; c->fam_n = 0; c->fam_dirty = false; c->fam_pre = false;
     return MB_OK;
 }
 
@@ -453,13 +465,18 @@ int mb_find_device(mb_ctx* c, const mb_params* prm) {
         eu.cand_run = c->cand_run.as<u32>(); eu.cand_off = c->cand_off.as<u32>(); eu.cand_aux = mode == MB_MODE_PAIRWISE ? c->cand_aux.as<u32>() : nullptr;
         eu.totals = reinterpret_cast<u32*>(scal + SC_CAND);
         eu.mode = mode; eu.comp_pos = c->comp_pos.as<u32>(); eu.comp_gs = c->comp_gs.as<u8>(); eu.bitmap = c->bitmap.as<u64>(); eu.ghash = c->ghash.as<u64>(); eu.ghash2 = c->ghash2.as<u64>();
+        eu.seedL = L;
         launch_emit_unique(eu, fmt, gt, n_cand, st); LAUNCHED(c); CHECK_LAUNCH(c);
+        // ---- matches of earlier searches (mb_accumulate: the MemHash table persists until Clear())
+        c->fam_pre = false;
+        if (c->fam_on && mode == MB_MODE_UNIQUE) TRY(mbi_family_filter(c, n_cand));
         // ---- a10 + a11
         TRY(mbi_dedup(c, n_cand, bases));
         cudaEventRecord(c->ev[EV_DEDUP], st);
         // ---- a12
         TRY(mbi_output_unique(c, c->n_rep, maxlen));
         n_matches = (u32)c->r_matches; n_ocomp = c->r_comps;
+        if (c->fam_on && mode == MB_MODE_UNIQUE) TRY(mbi_family_append(c));
     } else {
         cudaEventRecord(c->ev_x[0], st);
         cudaEventRecord(c->ev[EV_DEDUP], st);
@@ -545,6 +562,7 @@ int mbi_dedup(mb_ctx* c, u32 n_cand, u64 bases, const u64* rows) {
     da.wd0 = c->wd_a.as<u32>(); da.wd1 = c->wd_b.as<u32>(); da.wd2 = c->wd_c.as<u32>();
     da.ctr = reinterpret_cast<u32*>(scal + SC_DDCTR);
     da.rows = rows;
+    da.pre_drop = (!rows && c->fam_pre) ? c->fam_drop.as<u8>() : nullptr;
     // ---- chains: slots, links, reps
     launch_slot_scatter(da, c->gt, st); LAUNCHED(c);
     {
@@ -608,6 +626,66 @@ int mbi_dedup(mb_ctx* c, u32 n_cand, u64 bases, const u64* rows) {
         cudaEventElapsedTime(&t_ext, c->ev_x[0], c->ev_x[3]);
         fprintf(stderr, "[dedup-trace] emit+chains+sort %.1f us, extend %.1f us\n", t_chain * 1e3, t_ext * 1e3);
     }
+    return MB_OK;
+}
+
+// ------------------------------------------------------------------ persistent MemHash table (seed family)
+static FamilyArgs family_args(mb_ctx* c) {
+    FamilyArgs f{};
+    f.t_h1 = c->fam_th1.as<u64>(); f.t_h2 = c->fam_th2.as<u64>(); f.t_x = c->fam_tx.as<u32>(); f.t_end = c->fam_tend.as<u32>();
+    f.s_h1 = c->fam_sh1.as<u64>(); f.s_h2 = c->fam_sh2.as<u64>(); f.s_x = c->fam_sx.as<u32>(); f.s_end = c->fam_send.as<u32>();
+    f.s_pmax = c->fam_spmax.as<u32>(); f.s_run0 = c->fam_srun0.as<u32>();
+    return f;
+}
+
+// Before the de-dup of a search: candidates whose seed lies inside a match of an earlier search (same group) are marked
+// dropped (c->fam_drop) and taken out of the chains.  The table is sorted here when it has grown since its last use.
+int mbi_family_filter(mb_ctx* c, u32 n_cand) {
+    const u32 nt = c->fam_n;
+    if (nt == 0 || n_cand == 0) return MB_OK;
+    cudaStream_t st = c->stream;
+    u64* scal = c->scalars.as<u64>();
+    if (c->fam_dirty) {
+        const size_t n8 = (size_t)nt + 8;
+        TRY(c->reserve(c->fam_sh1, n8 * 8)); TRY(c->reserve(c->fam_sh2, n8 * 8)); TRY(c->reserve(c->fam_sx, n8 * 4));
+        TRY(c->reserve(c->fam_send, n8 * 4)); TRY(c->reserve(c->fam_spmax, n8 * 4)); TRY(c->reserve(c->fam_srun0, n8 * 4));
+        TRY(c->reserve(c->sort_kA, n8 * 8)); TRY(c->reserve(c->sort_kB, n8 * 8)); TRY(c->reserve(c->sort_vA, n8 * 8)); TRY(c->reserve(c->sort_vB, n8 * 8));
+        TRY(c->reserve(c->lookback, (size_t)(div_up(nt, radix_tile_size()) + 1) * 256 * 8)); // the table may be larger than this search's seed list
+        FamilyArgs f = family_args(c);
+        u64 *kA = c->sort_kA.as<u64>(), *kB = c->sort_kB.as<u64>(), *vA = c->sort_vA.as<u64>(), *vB = c->sort_vB.as<u64>();
+        launch_family_key_x(f, nt, kA, vA, st); LAUNCHED(c);
+        TRY(mbi_sort_records(c, &kA, &kB, &vA, &vB, nt, 0, 32, false));
+        launch_family_key_h(f, nt, vA, kA, st); LAUNCHED(c);
+        TRY(mbi_sort_records(c, &kA, &kB, &vA, &vB, nt, 0, 64, false));
+        launch_family_gather(f, nt, vA, st); LAUNCHED(c); LAUNCHED(c);
+        CHECK_LAUNCH(c);
+        c->fam_dirty = false;
+    }
+    TRY(c->reserve(c->fam_drop, (size_t)n_cand + 8));
+    launch_family_filter(family_args(c), nt, n_cand, c->ghash.as<u64>(), c->ghash2.as<u64>(), c->cand_off.as<u32>(), c->comp_pos.as<u32>(), (u32)c->sd.L,
+                         c->fam_drop.as<u8>(), reinterpret_cast<u32*>(scal + SC_FAM) + 1, st);
+    LAUNCHED(c); CHECK_LAUNCH(c);
+    c->fam_pre = true;
+    return MB_OK;
+}
+
+// After a search: its accepted matches join the table (c->r_matches of them: the output stage has counted them).
+int mbi_family_append(mb_ctx* c) {
+    const u32 nm = (u32)c->r_matches;
+    if (nm == 0 || c->n_rep == 0) return MB_OK;
+    cudaStream_t st = c->stream;
+    u64* scal = c->scalars.as<u64>();
+    const size_t total = (size_t)c->fam_n + nm + 8;
+    TRY(c->reserve_keep(c->fam_th1, total * 8, (size_t)c->fam_n * 8)); TRY(c->reserve_keep(c->fam_th2, total * 8, (size_t)c->fam_n * 8));
+    TRY(c->reserve_keep(c->fam_tx, total * 4, (size_t)c->fam_n * 4)); TRY(c->reserve_keep(c->fam_tend, total * 4, (size_t)c->fam_n * 4));
+    c->fam_tmp = c->fam_n;
+    CUDA_TRY(c, cudaMemcpyAsync(scal + SC_FAM, &c->fam_tmp, 4, cudaMemcpyHostToDevice, st));
+    // (a dropped candidate's first hash is poisoned, but a dropped candidate is never accepted)
+    launch_family_append(family_args(c), c->s_cand.as<u8>(), c->rep_cand.as<u32>(), c->n_rep, c->ghash.as<u64>(), c->ghash2.as<u64>(), c->cand_off.as<u32>(),
+                         c->comp_pos.as<u32>(), c->ext_l.as<u32>(), c->ext_r.as<u32>(), (u32)c->sd.L, reinterpret_cast<u32*>(scal + SC_FAM), st);
+    LAUNCHED(c); CHECK_LAUNCH(c);
+    c->fam_n += nm;
+    c->fam_dirty = true;
     return MB_OK;
 }
 

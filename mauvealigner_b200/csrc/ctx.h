@@ -19,7 +19,7 @@ struct DBuf {
 
 enum { EV_START, EV_EXTRACT, EV_SORT, EV_BUCKET, EV_DEDUP, EV_OUTPUT, EV_COUNT };
 enum { SC_RUNS = 0 /*u32[2]*/, SC_CAND = 1 /*u32[2]*/, SC_NBUCKETS = 2, SC_UNDECIDED = 3, SC_EXTENDED = 4, SC_NMATCH = 5, SC_NCOMP = 6,
-       SC_BMTOTAL = 7, SC_DDCTR = 8 /* 16 x u32 */, SC_COUNT = 16 };
+       SC_BMTOTAL = 7, SC_DDCTR = 8 /* 16 x u32 */, SC_FAM = 16 /* u32[2]: table entries, candidates dropped by the table */, SC_COUNT = 18 };
 
 struct mb_ctx {
     int device = 0;
@@ -55,6 +55,11 @@ struct mb_ctx {
     DBuf wl_a, wl_b, wl_c, wl_long, wd_a, wd_b, wd_c, live_bits, ghash, slot_gp, slot_hash, link_bits, chain_min, rep_bits, rep_rank, s_hash, s_cand, rng_lo, rng_hi;
     DBuf flags, match_idx, sort_kA, sort_kB, sort_vA, sort_vB, ncomp, mers_tmp;
     DBuf out_len, out_off, out_seq, out_start;
+    // persistent MemHash table across searches (mb_accumulate; kernels_family.cu)
+    bool fam_on = false, fam_dirty = false, fam_pre = false;
+    u32 fam_n = 0;
+    u64 fam_tmp = 0;
+    DBuf fam_th1, fam_th2, fam_tx, fam_tend, fam_sh1, fam_sh2, fam_sx, fam_send, fam_spmax, fam_srun0, fam_drop;
     u32 ticket_next = 0;
     u64 tmp_u64 = 0;
     size_t status_next = 0;
@@ -92,6 +97,21 @@ struct mb_ctx {
         b.cap = want;
         return MB_OK;
     }
+    // grow a buffer whose first `keep` bytes must survive
+    int reserve_keep(DBuf& b, size_t bytes, size_t keep) {
+        if (bytes <= b.cap) return MB_OK;
+        DBuf nb;
+        int rc = reserve(nb, bytes + bytes / 2);
+        if (rc != MB_OK) return rc;
+        if (b.p && keep) {
+            cudaError_t e = cudaMemcpyAsync(nb.p, b.p, keep, cudaMemcpyDeviceToDevice, stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+            if (e != cudaSuccess) { set_cuda_error(e, "reserve_keep", __LINE__); cudaFree(nb.p); return MB_E_CUDA; }
+        }
+        if (b.p) cudaFree(b.p);
+        b = nb;
+        return MB_OK;
+    }
     int reserve_host(void*& p, size_t& cap, size_t bytes) {
         if (bytes <= cap) return MB_OK;
         if (p) cudaFreeHost(p);
@@ -125,3 +145,6 @@ int mbi_bits_for(u64 maxval);
 int mbi_reserve_candidates(mb_ctx* c, u32 n_cand, u32 n_ccomp, u64 bases);
 int mbi_dedup(mb_ctx* c, u32 n_cand, u64 bases, const u64* rows = nullptr);
 int mbi_output_unique(mb_ctx* c, u32 n_cand, u64 maxlen);
+// persistent MemHash table (mb_accumulate): drop the candidates contained in matches of earlier searches / add this search's matches
+int mbi_family_filter(mb_ctx* c, u32 n_cand);
+int mbi_family_append(mb_ctx* c);

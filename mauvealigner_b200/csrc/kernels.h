@@ -55,6 +55,8 @@ struct EmitUniqueArgs {
     u64* bitmap;
     u64* ghash;      // per candidate: hash of (genome set, strands, diagonal)
     u64* ghash2;     // second, independent hash of the same key (low 8 bits cleared)
+    u32 seedL;       // seed length: a reverse component enters the hashes with position + seedL + first position, which
+                     // extension leaves unchanged (so groups of different seed patterns meet, kernels_family.cu)
 };
 void launch_emit_unique(const EmitUniqueArgs& a, const RecFmt& fmt, const GenomeTable& gt, u32 n_cand_upper, cudaStream_t st);
 struct EmitEnumArgs {
@@ -101,10 +103,23 @@ struct DedupArgs {
     // and their counters (layout: see k_resolve)
     u32* wl0; u32* wl1; u32* wl2; u32* wd0; u32* wd1; u32* wd2; u32* wl_long; u32* ctr;
     u64* trace;         // optional phase trace (debug): [0] count, then (tag, ns) pairs
+    const u8* pre_drop; // per candidate, or null: dropped before the de-dup (contained in a match of an earlier call, kernels_family.cu)
     // multi-GPU owner side: the candidates arrive as 4-word rows (kernels_dist.cu) with their extents already
     // known and without component lists; null on the single-GPU path
     const u64* rows;
 };
+// persistent MemHash table across calls (kernels_family.cu): t_* = entries in arrival order, s_* = sorted by (hash, start)
+struct FamilyArgs {
+    u64* t_h1; u64* t_h2; u32* t_x; u32* t_end;
+    u64* s_h1; u64* s_h2; u32* s_x; u32* s_end; u32* s_pmax; u32* s_run0;
+};
+void launch_family_append(const FamilyArgs& f, const u8* rstate, const u32* s_cand, u32 n_rep, const u64* ghash, const u64* ghash2, const u32* cand_off,
+                          const u32* comp_pos, const u32* ext_l, const u32* ext_r, u32 L, u32* counter, cudaStream_t st);
+void launch_family_key_x(const FamilyArgs& f, u32 n, u64* key, u64* val, cudaStream_t st);
+void launch_family_key_h(const FamilyArgs& f, u32 n, const u64* val, u64* key, cudaStream_t st);
+void launch_family_gather(const FamilyArgs& f, u32 n, const u64* perm, cudaStream_t st);
+void launch_family_filter(const FamilyArgs& f, u32 n_tab, u32 n_cand, u64* ghash, const u64* ghash2, const u32* cand_off, const u32* comp_pos, u32 L,
+                          u8* pre_drop, u32* n_dropped, cudaStream_t st);
 void launch_slot_scatter(const DedupArgs& a, const GenomeTable& gt, cudaStream_t st);
 u32 chain_tile();
 void launch_chains(const DedupArgs& a, u64* status_fwd, u32* ticket_fwd, u64* status_bwd, u32* ticket_bwd, cudaStream_t st);

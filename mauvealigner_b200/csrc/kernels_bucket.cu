@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(256) k_emit_unique(EmitUniqueArgs a, RecFmt fm
         a.comp_pos[off + k] = p;
         a.comp_gs[off + k] = (u8)(g | (rev ? 0x80u : 0u));
         // hash of the D16 group key: genome, strand and diagonal of every component
-        u64 dg = rev ? (u64)p + x0 : (u64)(u32)(p - x0);
+        u64 dg = rev ? (u64)p + x0 + a.seedL : (u64)(u32)(p - x0);
         h ^= (dg << 8) | (u64)(g | (rev ? 0x80u : 0u));
         h *= 0xFF51AFD7ED558CCDull; h ^= h >> 29;
         h2 = (h2 + ((dg << 8) | (u64)(g | (rev ? 0x80u : 0u)))) * 0x9FB21C651E98DF25ull; h2 ^= h2 >> 32;

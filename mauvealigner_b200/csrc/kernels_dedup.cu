@@ -567,7 +567,7 @@ __global__ void __launch_bounds__(256) k_rep_setup(DedupArgs a, GenomeTable gt) 
     a.s_h2[i] = q.x;
     a.minrank[i] = INF64; a.minrank[(size_t)a.n_rep + i] = INF64;
     a.reach[i] = 0;
-    a.rstate[i] = 0;
+    a.rstate[i] = (a.pre_drop && a.pre_drop[c]) ? 2 : 0;
     if (a.rows) a.xrec[i] = make_uint4(c, (u32)q.y, m | (g0 << 8) | (vg << 16), (u32)(q.y >> 32)); // owner side: k_extent_ranges follows
     else { // the extension (slot order) has run: slot range of the extent
         u32 rlo, rhi;
@@ -891,6 +891,7 @@ __global__ void __launch_bounds__(DD_NT) k_resolve(DedupArgs a) {
             for (u32 i = gtid; i < n_narrow; i += gsz) {
                 u32 rlo = a.rng_lo[i], rhi = a.rng_hi[i];
                 if (rhi - rlo < 2) continue; // alone in its extent
+                if (a.pre_drop && a.rstate[i] != 0) continue; // dropped before the de-dup: claims nothing
                 ulonglong2 me = a.s_rec[i];
                 if (walk_neighbours<false, false>(a, i, me, rlo, rhi, mr_cur) < 0) { a.rstate[i] = RS_WIDE; wd[cur][atomicAdd(ctr + 3 + cur, 1u)] = i; }
             }

@@ -55,6 +55,11 @@ class Context:
     def clear_sequences(self):
         _check(self._h, L.lib().mb_clear_sequences(self._h))
 
+    def accumulate(self, on=True):
+        """MemHash table across searches (mb_accumulate): on = later MODE_UNIQUE searches drop what earlier matches
+        contain and add their own matches; off = forget the table (MemHash::Clear())."""
+        _check(self._h, L.lib().mb_accumulate(self._h, 1 if on else 0))
+
     def add_sequence(self, data, packed=False):
         """data: bytes / str / numpy uint8 (ASCII) or numpy uint64 words (packed=True, with length attr)."""
         if packed:
@@ -402,22 +407,44 @@ class MatchFinder:
             match_list.append(m)
 
 
+def _canonical_key(m):
+    """D18 canonical order of MODE_UNIQUE matches: |start| per sequence, then the sign vector, then the length."""
+    return (tuple(abs(x) for x in m._start), tuple(1 if x < 0 else 0 for x in m._start), m._length)
+
+
 class UniqueMatchFinder(MatchFinder):
-    """UniqueMatchFinder / MemHash: multi-MUMs with unique seeds (src/UniqueMatchFinder.cpp:36-60)."""
+    """UniqueMatchFinder / MemHash: multi-MUMs with unique seeds (src/UniqueMatchFinder.cpp:36-60).  As in libMems the
+    table persists across FindMatches calls until Clear(): a later call (the seed-family search of
+    src/progressiveMauve.cpp:503-548 makes three, with ClearSequences() in between) drops what the matches found so far
+    contain, and GetMatchList returns the union in canonical order."""
 
     def __init__(self, ctx=None):
         super().__init__(ctx)
         self._mask = 0
+        self._found = []
 
     def FindMatches(self, match_list):
         ctx = self._load(match_list)
+        ctx.accumulate(True)
         self.last = ctx.find(L.MODE_UNIQUE, nway_mask=self._mask)
-        self._fill(match_list, self.last, self.seq_count, dense=True)
+        new = MatchList()
+        self._fill(new, self.last, self.seq_count, dense=True)
+        first = not self._found
+        self._found.extend(new)
+        if not first:
+            self._found.sort(key=_canonical_key)
+        self.GetMatchList(match_list)
         return True
 
     def GetMatchList(self, match_list):
-        if self.last is not None:
-            self._fill(match_list, self.last, self.seq_count, dense=True)
+        del match_list[:]
+        match_list.extend(m.Copy() for m in self._found)
+
+    def Clear(self):
+        super().Clear()
+        self._found = []
+        if self._ctx is not None:
+            self._ctx.accumulate(False)
 
     def Clone(self):
         c = type(self)(self._ctx)
@@ -435,7 +462,9 @@ class PairwiseMatchFinder(UniqueMatchFinder):
     def FindMatches(self, match_list):
         ctx = self._load(match_list)
         self.last = ctx.find(L.MODE_PAIRWISE)
-        self._fill(match_list, self.last, self.seq_count, dense=True)
+        self._found = []
+        self._fill(self._found, self.last, self.seq_count, dense=True)
+        self.GetMatchList(match_list)
         return True
 
 

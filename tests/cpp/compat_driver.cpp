@@ -1,6 +1,7 @@
 // Reads sequences (one per line) from argv[2..] files' first line, runs the reference-shaped host API
 // (include/mems_compat/mems_compat.h) and prints match lists in WriteList form.  Used by the GPU tests;
 // the calls mirror src/progressiveMauve.cpp:437-558, src/repeatoire.cpp:1836-1867, src/uniqueMerCount.cpp:23-40.
+#include <algorithm>
 #include <fstream>
 #include <iostream>
 #include <string>
@@ -19,7 +20,7 @@ static string read_seq(const char* path) {
 }
 
 int main(int argc, char** argv) {
-    if (argc < 3) { cerr << "usage: compat_driver <umf|pmf|sme|count|sml> <weight> <rank> <seq files...> | smlcount <file.sslist> | readlist <file>\n"; return -1; }
+    if (argc < 3) { cerr << "usage: compat_driver <umf|pmf|sme|count|sml|family> <weight> <rank> <seq files...> | smlcount <file.sslist> | readlist <file>\n"; return -1; }
     string what = argv[1];
     if (what == "smlcount") {
         // src/uniqueMerCount.cpp:29-39, line for line
@@ -51,6 +52,34 @@ int main(int argc, char** argv) {
         ml.LoadSMLs(weight, &cerr, rank);
         ml.LoadSMLs(weight, &cerr, rank); // second call must find the files and not rebuild
         cout << endl << ml.sml_table[0]->UniqueMerCount() << endl;
+        return 0;
+    }
+    if (what == "family") {
+        // the seed-family search of src/progressiveMauve.cpp:503-548, call for call: the longest pattern first, ONE
+        // UniqueMatchFinder, ClearSequences() between the patterns, one GetMatchList + Clear() at the end
+        int mer_size = weight;
+        vector<pair<int, int> > length_ranks(3);
+        length_ranks[0] = make_pair(getSeedLength(getSeed(mer_size, 0)), 0);
+        length_ranks[1] = make_pair(getSeedLength(getSeed(mer_size, 1)), 1);
+        length_ranks[2] = make_pair(getSeedLength(getSeed(mer_size, 2)), 2);
+        std::sort(length_ranks.begin(), length_ranks.end());
+        UniqueMatchFinder umf;
+        for (int seedI = 2; seedI >= 0; seedI--) {
+            umf.LogProgress(nullptr);
+            MatchList cur_list;
+            cur_list.seq_filename = ml.seq_filename;
+            cur_list.seq_table = ml.seq_table;
+            cur_list.CreateMemorySMLs(mer_size, nullptr, length_ranks[seedI].second);
+            umf.FindMatches(cur_list);
+            umf.ClearSequences();
+            for (size_t smlI = 0; smlI < cur_list.sml_table.size(); smlI++) delete cur_list.sml_table[smlI];
+            for (size_t curI = 0; curI < cur_list.size(); curI++) cur_list[curI]->Free();
+        }
+        umf.GetMatchList(ml);
+        umf.Clear();
+        WriteList(ml, cout);
+        for (Match* m : ml) m->Free();
+        for (size_t i = 0; i < ml.seq_table.size(); ++i) delete ml.seq_table[i];
         return 0;
     }
     ml.CreateMemorySMLs(weight, nullptr, rank);

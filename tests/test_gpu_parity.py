@@ -282,11 +282,55 @@ def test_cpp_host_api_matches_oracle(tmp_path):
     out = subprocess.check_output([str(exe), "smlcount", files[0] + ".sslist"], text=True).split()
     assert int(out[0]) == uniq
     assert [int(x) for x in out[1:]] == O.sml(seqs[0], mb.get_seed(11, 0)).tolist()
+    # the seed-family search, call for call as src/progressiveMauve.cpp:503-548 (one finder, three patterns, longest first)
+    out = subprocess.check_output([str(exe), "family", "11", "0"] + files, text=True)
+    pats = [mb.get_seed(11, r) for _, r in sorted(((mb.seed_length(mb.get_seed(11, r)), r) for r in (0, 1, 2)), reverse=True)]
+    want = O.find_family(seqs, pats)
+    rows = []
+    for ln, comps in O.matches_as_list(want):
+        d = dict(comps)
+        rows.append([ln] + [d.get(g, 0) for g in range(3)])
+    assert parse(out) == rows and len(rows) > 10
     # WriteList -> ReadList -> WriteList round trip
     first = subprocess.check_output([str(exe), "umf", "11", "0"] + files, text=True)
     lst = tmp_path / "matches.mums"
     lst.write_text(first)
     assert subprocess.check_output([str(exe), "readlist", str(lst)], text=True) == first
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_seed_family_vs_oracle(seed):
+    """One finder, several seed patterns, the table persisting across the calls (src/progressiveMauve.cpp:503-548):
+    the device filter + the host union against orc_find_family, for families of equal and of different seed lengths."""
+    import mauvealigner_b200 as mb
+    rng = np.random.default_rng(4200 + seed)
+    k = 2 + seed
+    seqs = family(rng, 8000, k, sub=0.03, indel=0.004, inv=seed % 2)
+    if seed == 3:
+        seqs[1] = seqs[0]  # identical genomes: long matches of the first pattern contain almost every later candidate
+    families = [[mb.get_seed(11, 2), mb.get_seed(11, 1), mb.get_seed(11, 0)],
+                [mb.get_seed(13, 0), mb.get_seed(9, 2), mb.get_seed(11, 1)],   # not ordered by length
+                [mb.get_seed(9, 0), mb.get_seed(13, 1)],
+                [mb.get_seed(9, 0), mb.get_seed(9, 1), mb.get_seed(9, 2), mb.get_seed(15, 0), 0b11111]][seed]
+    want = O.find_family(seqs, families)
+    ml = mb.MatchList()
+    ml.seq_table = list(seqs)
+    umf = mb.UniqueMatchFinder()
+    for p in families:
+        ml.seed_pattern = p
+        umf.FindMatches(ml)
+        umf.ClearSequences()
+    out = mb.MatchList()
+    umf.GetMatchList(out)
+    got = [(m.Length(), [(g, m.Start(g)) for g in range(k) if m.Start(g) != 0]) for m in out]
+    assert got == [(ln, list(comps)) for ln, comps in O.matches_as_list(want)]
+    assert len(got) > 5
+    # Clear() forgets the table: the next search is a plain single-pattern one again
+    umf.Clear()
+    ml.seed_pattern = families[-1]
+    umf.FindMatches(ml)
+    single = O.find(seqs, families[-1], O.MODE_UNIQUE)
+    assert [(m.Length(), [(g, m.Start(g)) for g in range(k) if m.Start(g) != 0]) for m in ml] == [(ln, list(c)) for ln, c in O.matches_as_list(single)]
 
 
 def test_context_pool_many_small_problems():
