@@ -91,6 +91,16 @@ public:
     int Orientation(uint seqI) const { return start_[seqI] > 0 ? 0 : (start_[seqI] < 0 ? 1 : 2); }
     int64 LeftEnd(uint seqI) const { return start_[seqI] < 0 ? -start_[seqI] : start_[seqI]; }
     int64 RightEnd(uint seqI) const { return start_[seqI] == NO_MATCH ? NO_MATCH : LeftEnd(seqI) + (int64)length_ - 1; }
+    /* Match::CropStart / CropEnd: drop `n` columns at the start / end of the match.  A forward component moves its
+     * start with the match start; a reverse component, whose LEFT end is the match end, moves with the match end. */
+    void CropStart(gnSeqI n) {
+        for (int64& s : start_) if (s > 0) s += (int64)n;
+        length_ -= n;
+    }
+    void CropEnd(gnSeqI n) {
+        for (int64& s : start_) if (s < 0) s -= (int64)n;
+        length_ -= n;
+    }
     Match* Copy() const { return new Match(*this); }
     void Free() { delete this; }
     friend std::ostream& operator<<(std::ostream& os, const Match& m) {
@@ -281,6 +291,69 @@ inline void WriteList(const MatchList& ml, std::ostream& os) {
     }
     os << "MatchCount\t" << ml.size() << "\n";
     for (const Match* m : ml) os << *m << "\n";
+}
+
+/* EliminateOverlaps(MatchList&) (src/mauveAligner.cpp:594-596,611-612: "only count each base pair once"): after the call
+ * no two matches of the list overlap in any sequence.  libMems' body is not in the tree; the rule here:
+ * sequence by sequence, the matches present in it are swept by (left end, position in the list); the part of a match
+ * that earlier matches of the sweep already cover — always a prefix in that sequence's coordinates — is cropped off
+ * (CropStart for a forward component, CropEnd for a reverse one), a match covered entirely is released. */
+inline void EliminateOverlaps(MatchList& ml) {
+    const uint nseq = ml.empty() ? 0 : ml[0]->SeqCount();
+    for (uint seqI = 0; seqI < nseq; ++seqI) {
+        std::vector<size_t> order;
+        for (size_t i = 0; i < ml.size(); ++i) if (ml[i] && ml[i]->Start(seqI) != NO_MATCH) order.push_back(i);
+        std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return ml[a]->LeftEnd(seqI) < ml[b]->LeftEnd(seqI); });
+        int64 covered = 0; /* right end of everything swept so far */
+        for (size_t i : order) {
+            Match* m = ml[i];
+            const int64 l = m->LeftEnd(seqI), r = m->RightEnd(seqI);
+            if (r <= covered) { m->Free(); ml[i] = nullptr; continue; }
+            if (l <= covered) {
+                const gnSeqI ov = (gnSeqI)(covered - l + 1);
+                if (m->Orientation(seqI) == 0) m->CropStart(ov); else m->CropEnd(ov);
+            }
+            covered = r;
+        }
+    }
+    size_t kept = 0;
+    for (size_t i = 0; i < ml.size(); ++i) if (ml[i]) ml[kept++] = ml[i];
+    ml.resize(kept);
+}
+
+/* transposeMatches(MatchList&, seqI, seq_regions) (src/mauveAligner.cpp:628-637, src/transposeCoordinates.cpp:46-65): the
+ * sorted mer list of sequence seqI was built over a FILTERED sequence — the concatenation of the used regions
+ * seq_regions = {first_0, last_0, first_1, last_1, ...} (1-based, inclusive, ascending) of the original — and the
+ * matches carry filtered coordinates; put them back into the original coordinate system.  A match that runs across a
+ * region boundary is split there (every piece keeps the columns of all its components).  libMems' body is not in the
+ * tree; this is DESIGN.md D19. */
+inline void transposeMatches(MatchList& ml, uint seqI, const std::vector<int64>& seq_regions) {
+    if (seq_regions.size() < 2) return;
+    const size_t nreg = seq_regions.size() / 2;
+    std::vector<int64> cum(nreg + 1, 0); /* filtered coordinates before region k */
+    for (size_t k = 0; k < nreg; ++k) cum[k + 1] = cum[k] + (seq_regions[2 * k + 1] - seq_regions[2 * k] + 1);
+    std::vector<Match*> out;
+    for (Match* m : ml) {
+        if (m->Start(seqI) == NO_MATCH) { out.push_back(m); continue; }
+        while (m) {
+            const int64 l = m->LeftEnd(seqI);               /* filtered, 1-based */
+            size_t k = (size_t)(std::upper_bound(cum.begin(), cum.end(), l - 1) - cum.begin()) - 1;
+            if (k >= nreg) k = nreg - 1;                     /* beyond the last region: extrapolate from it */
+            const int64 room = cum[k + 1] - (l - 1);         /* columns left in region k */
+            Match* rest = nullptr;
+            if (k + 1 < nreg && (int64)m->Length() > room) { /* split at the boundary, in seqI's coordinates */
+                rest = m->Copy();
+                const gnSeqI tail = (gnSeqI)((int64)m->Length() - room);
+                if (m->Orientation(seqI) == 0) { m->CropEnd(tail); rest->CropStart((gnSeqI)room); }
+                else { m->CropStart(tail); rest->CropEnd((gnSeqI)room); }
+            }
+            const int64 nl = seq_regions[2 * k] + (m->LeftEnd(seqI) - 1 - cum[k]);
+            m->SetStart(seqI, m->Start(seqI) < 0 ? -nl : nl);
+            out.push_back(m);
+            m = rest;
+        }
+    }
+    ml.assign(out.begin(), out.end());
 }
 
 /* ReadList: the inverse of WriteList (match lines only; the header's file names refill seq_filename).  Used for the

@@ -294,6 +294,19 @@ class Match:
     def LeftEnd(self, i):
         return abs(self._start[i])
 
+    def RightEnd(self, i):
+        return NO_MATCH if self._start[i] == NO_MATCH else abs(self._start[i]) + self._length - 1
+
+    def CropStart(self, n):
+        """Match::CropStart: drop n columns at the match start (forward components move, reverse ones keep their left end)."""
+        self._start = [s + n if s > 0 else s for s in self._start]
+        self._length -= n
+
+    def CropEnd(self, n):
+        """Match::CropEnd: drop n columns at the match end (the LEFT end of a reverse component is the match end)."""
+        self._start = [s - n if s < 0 else s for s in self._start]
+        self._length -= n
+
     def Copy(self):
         m = Match(len(self._start))
         m._start = list(self._start)
@@ -326,6 +339,70 @@ class MatchList(list):
         self.sml_table = [SortedMerList(self, i) for i in range(len(self.seq_table))]
 
     LoadSMLs = CreateMemorySMLs
+
+
+def EliminateOverlaps(ml):
+    """EliminateOverlaps(MatchList&) (src/mauveAligner.cpp:594-596,611-612): afterwards no two matches overlap in any
+    sequence.  Rule (libMems' body is not in the tree): sequence by sequence, the matches present in it
+    are swept by (left end, position in the list); what earlier matches of the sweep already cover — a prefix in that
+    sequence's coordinates — is cropped off, a match covered entirely is dropped."""
+    nseq = ml[0].SeqCount() if len(ml) else 0
+    items = list(ml)
+    for g in range(nseq):
+        order = sorted((i for i, m in enumerate(items) if m is not None and m.Start(g) != NO_MATCH), key=lambda i: items[i].LeftEnd(g))
+        covered = 0
+        for i in order:
+            m = items[i]
+            l, r = m.LeftEnd(g), m.RightEnd(g)
+            if r <= covered:
+                items[i] = None
+                continue
+            if l <= covered:
+                ov = covered - l + 1
+                if m.Orientation(g) == 0:
+                    m.CropStart(ov)
+                else:
+                    m.CropEnd(ov)
+            covered = r
+    ml[:] = [m for m in items if m is not None]
+
+
+def transposeMatches(ml, seqI, seq_regions):
+    """transposeMatches(MatchList&, seqI, seq_regions) (src/mauveAligner.cpp:628-637, src/transposeCoordinates.cpp:46-65):
+    sequence seqI was searched in FILTERED form — the concatenation of its used regions (first_0, last_0, first_1, ...;
+    1-based, inclusive) — so the matches carry filtered coordinates; back to the original ones, splitting a match that
+    runs across a region boundary."""
+    import bisect
+    if len(seq_regions) < 2:
+        return
+    nreg = len(seq_regions) // 2
+    cum = [0]
+    for k in range(nreg):
+        cum.append(cum[-1] + seq_regions[2 * k + 1] - seq_regions[2 * k] + 1)
+    out = []
+    for m in ml:
+        if m.Start(seqI) == NO_MATCH:
+            out.append(m)
+            continue
+        while m is not None:
+            l = m.LeftEnd(seqI)
+            k = min(bisect.bisect_right(cum, l - 1) - 1, nreg - 1)
+            room = cum[k + 1] - (l - 1)
+            rest = None
+            if k + 1 < nreg and m.Length() > room:
+                rest = m.Copy()
+                tail = m.Length() - room
+                if m.Orientation(seqI) == 0:
+                    m.CropEnd(tail)
+                    rest.CropStart(room)
+                else:
+                    m.CropStart(tail)
+                    rest.CropEnd(room)
+            nl = seq_regions[2 * k] + (m.LeftEnd(seqI) - 1 - cum[k])
+            m.SetStart(seqI, -nl if m.Start(seqI) < 0 else nl)
+            out.append(m)
+            m = rest
+    ml[:] = out
 
 
 class SortedMerList:

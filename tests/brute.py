@@ -247,3 +247,78 @@ def find_family(seqs, patterns, nway_mask=0):
 
     accepted.sort(key=sort_key)
     return dict(matches=[(length, sorted(st.items())) for st, length in accepted])
+
+
+# ---- match-list post-filters, restated per base: a match is a list of COLUMNS, every column one
+# coordinate per sequence (None where the match is absent); cropping and splitting fall out of dropping / regrouping columns
+def _columns(length, starts):
+    cols = []
+    for j in range(length):
+        cols.append([None if s == 0 else (s + j if s > 0 else -s + (length - 1 - j)) for s in starts])
+    return cols
+
+
+def _from_columns(cols, starts):
+    """columns (a contiguous run of the original match, in match order) -> (length, starts)"""
+    n = len(cols)
+    out = []
+    for g, s in enumerate(starts):
+        if s == 0:
+            out.append(0)
+        elif s > 0:
+            out.append(cols[0][g])
+        else:
+            out.append(-cols[-1][g])
+    return n, out
+
+
+def eliminate_overlaps(matches):
+    """matches: [(length, [start per sequence])].  Per sequence g, in order of (left end, list position): every base of
+    g belongs to the first match of that order that covers it; a match keeps the columns whose base in g it owns."""
+    items = [(_columns(l, st), list(st)) for l, st in matches]
+    nseq = len(matches[0][1]) if matches else 0
+    for g in range(nseq):
+        order = sorted((i for i, (cols, st) in enumerate(items) if cols and st[g] != 0), key=lambda i: min(c[g] for c in items[i][0]))
+        owned = set()
+        for i in order:
+            cols, st = items[i]
+            keep = [c for c in cols if c[g] not in owned]
+            owned.update(c[g] for c in cols)
+            items[i] = (keep, st)
+    return [_from_columns(cols, st) for cols, st in items if cols]
+
+
+def transpose_matches(matches, seqI, regions):
+    """filtered -> original coordinates of sequence seqI, per column; a match is cut wherever consecutive columns fall
+    into different regions"""
+    if len(regions) < 2:
+        return [(l, list(st)) for l, st in matches]
+    orig = []
+    for k in range(len(regions) // 2):
+        orig.extend((k, x) for x in range(regions[2 * k], regions[2 * k + 1] + 1))
+    last_k, last_x = orig[-1]
+    out = []
+    for l, st in matches:
+        if st[seqI] == 0:
+            out.append((l, list(st)))
+            continue
+        cols = _columns(l, st)
+        tagged = []
+        for c in cols:
+            f = c[seqI]
+            k, x = orig[f - 1] if f - 1 < len(orig) else (last_k, last_x + (f - len(orig)))
+            c = list(c)
+            c[seqI] = x
+            tagged.append((k, c))
+        pieces, cur = [], [tagged[0]]
+        for t in tagged[1:]:
+            if t[0] != cur[-1][0]:
+                pieces.append(cur)
+                cur = []
+            cur.append(t)
+        pieces.append(cur)
+        if st[seqI] < 0:
+            pieces.reverse()  # pieces in ascending order of the seqI coordinate
+        for pc in pieces:
+            out.append(_from_columns([c for _, c in pc], st))
+    return out

@@ -39,6 +39,21 @@ int main(int argc, char** argv) {
         WriteList(in, cout);
         return 0;
     }
+    if (what == "overlaps" || what == "transpose") {
+        // the match-list post-filters of src/mauveAligner.cpp:594-596,628-637 / src/transposeCoordinates.cpp:46-65 (host only)
+        MatchList in;
+        ifstream f(argv[2]);
+        ReadList(in, f);
+        for (size_t i = 0; i < in.seq_filename.size(); ++i) in.seq_table.push_back(new gnSequence());
+        if (what == "overlaps") EliminateOverlaps(in);
+        else {
+            vector<int64> coords;
+            for (int i = 4; i < argc; ++i) coords.push_back(atoll(argv[i]));
+            transposeMatches(in, (uint)atoi(argv[3]), coords);
+        }
+        for (const Match* m : in) cout << *m << "\n";
+        return 0;
+    }
     if (argc < 5) return -1;
     int weight = atoi(argv[2]), rank = atoi(argv[3]);
     MatchList ml;

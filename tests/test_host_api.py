@@ -118,6 +118,103 @@ def test_multiplicity_filter():
     assert len(ml) == 0
 
 
+def _random_match_list(rng, nseq, n, maxpos=400, maxlen=40):
+    out = []
+    for _ in range(n):
+        ln = int(rng.integers(1, maxlen))
+        st = []
+        for g in range(nseq):
+            r = rng.random()
+            p = int(rng.integers(1, maxpos))
+            st.append(0 if r < 0.25 else (p if r < 0.7 else -p))
+        if sum(1 for x in st if x) >= 2:
+            out.append((ln, st))
+    return out
+
+
+def _as_matchlist(mb, matches):
+    ml = mb.MatchList()
+    for ln, st in matches:
+        m = mb.Match(len(st))
+        m.SetLength(ln)
+        for i, x in enumerate(st):
+            m.SetStart(i, x)
+        ml.append(m)
+    return ml
+
+
+def test_list_filters_python_cpp_and_per_base_restatement(tmp_path):
+    """EliminateOverlaps and transposeMatches (src/mauveAligner.cpp:594-596,628-637; src/transposeCoordinates.cpp:46-65):
+    the Python mirror, the C++ mirror (through the compiled driver, no GPU involved) and the per-base restatement of
+    tests/brute.py agree on random match lists; hand-checked cases pin the rules themselves."""
+    import numpy as np
+    import mauvealigner_b200 as mb
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import brute
+    _build()
+    exe = tmp_path / "compat_driver"
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "compat_driver.cpp"), "-o", str(exe),
+                           "-L", os.path.join(ROOT, "mauvealigner_b200"), "-lmauve_b200",
+                           "-Wl,-rpath," + os.path.join(ROOT, "mauvealigner_b200")])
+
+    def write_list(path, matches, nseq):
+        with open(path, "w") as f:
+            f.write(f"FormatVersion\t3\nSequenceCount\t{nseq}\n")
+            for i in range(nseq):
+                f.write(f"Sequence{i}File\ts{i}\nSequence{i}Length\t1000\n")
+            f.write(f"MatchCount\t{len(matches)}\n")
+            for ln, st in matches:
+                f.write("\t".join(str(x) for x in [ln] + st) + "\n")
+
+    def cpp(args):
+        out = subprocess.check_output([str(exe)] + args, text=True).strip()
+        return [(int(r[0]), [int(x) for x in r[1:]]) for r in (l.split("\t") for l in out.split("\n") if l)]
+
+    # hand-checked: [1..10] and [6..15] overlap in sequence 0 by 5 -> the second is cropped to [11..15]; its reverse
+    # component in sequence 1 (left end 40, length 10) loses the RIGHT 5 bases, i.e. keeps left end 40
+    ml = _as_matchlist(mb, [(10, [1, 20]), (10, [6, -40]), (4, [3, 70])])
+    mb.EliminateOverlaps(ml)
+    assert [(m.Length(), [m.Start(0), m.Start(1)]) for m in ml] == [(10, [1, 20]), (5, [11, -40])]
+    # hand-checked: regions 101..110 and 201..300 (filtered 1..10, 11..110); a forward match at filtered 8, length 6
+    # splits into original 108..110 and 201..203; sequence 1 follows column by column
+    ml = _as_matchlist(mb, [(6, [8, 50])])
+    mb.transposeMatches(ml, 0, [101, 110, 201, 300])
+    assert [(m.Length(), [m.Start(0), m.Start(1)]) for m in ml] == [(3, [108, 50]), (3, [201, 53])]
+    ml = _as_matchlist(mb, [(6, [-8, 50])])
+    mb.transposeMatches(ml, 0, [101, 110, 201, 300])
+    assert [(m.Length(), [m.Start(0), m.Start(1)]) for m in ml] == [(3, [-108, 53]), (3, [-201, 50])]
+
+    rng = np.random.default_rng(5)
+    for trial in range(12):
+        nseq = 2 + trial % 3
+        matches = _random_match_list(rng, nseq, 30 + 10 * trial)
+        lst = tmp_path / f"l{trial}.mums"
+        write_list(lst, matches, nseq)
+        ml = _as_matchlist(mb, matches)
+        mb.EliminateOverlaps(ml)
+        got = [(m.Length(), [m.Start(g) for g in range(nseq)]) for m in ml]
+        assert got == brute.eliminate_overlaps(matches)
+        assert got == cpp(["overlaps", str(lst)])
+        for g in range(nseq):  # no two matches overlap in any sequence any more
+            iv = sorted((abs(st[g]), abs(st[g]) + ln - 1) for ln, st in got if st[g])
+            assert all(a[1] < b[0] for a, b in zip(iv, iv[1:]))
+        regions = []
+        x = 1
+        for _ in range(6):
+            x += int(rng.integers(0, 50))
+            w = int(rng.integers(20, 120))
+            regions += [x, x + w - 1]
+            x += w
+        seqI = trial % nseq
+        ml = _as_matchlist(mb, matches)
+        mb.transposeMatches(ml, seqI, regions)
+        got = [(m.Length(), [m.Start(g) for g in range(nseq)]) for m in ml]
+        assert got == brute.transpose_matches(matches, seqI, regions)
+        assert got == cpp(["transpose", str(lst), str(seqI)] + [str(r) for r in regions])
+        assert sum(ln for ln, _ in got) == sum(ln for ln, _ in matches)  # splitting only
+
+
 def test_multi_gpu_entry_points_reject_bad_arguments():
     """argument checks of the multi-GPU entry points run before any device work (no GPU needed)"""
     import ctypes as C
