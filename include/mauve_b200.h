@@ -44,7 +44,10 @@ enum {
                                  MaskedMemHash (src/mauveAligner.cpp:523-531).                        */
     MB_MODE_SEED_ENUM = 1,    /* SeedMatchEnumerator::HashMatch (src/SeedMatchEnumerator.h:71-123)    */
     MB_MODE_UNIQUE_COUNT = 2, /* SortedMerList::UniqueMerCount (src/uniqueMerCount.cpp:39)            */
-    MB_MODE_PAIRWISE = 3      /* PairwiseMatchFinder (src/progressiveMauve.cpp:496-501); at most 8 sequences */
+    MB_MODE_PAIRWISE = 3,     /* PairwiseMatchFinder (src/progressiveMauve.cpp:496-501); at most 8 sequences */
+    MB_MODE_REPEAT = 4        /* RepeatHash (mauveAligner --repeats, src/mauveAligner.cpp:480-487): ONE sequence; every bucket of
+                               * min_multi..max_multi (at most 255) occurrences is one match with a component per occurrence,
+                               * extended and de-duplicated like a MemHash entry; result columns as MB_MODE_SEED_ENUM */
 };
 
 typedef struct mb_params {

@@ -573,6 +573,23 @@ public:
     }
 };
 
+/* mems::RepeatHash (mauveAligner --repeats, src/mauveAligner.cpp:480-487): repeats inside ONE sequence.  Every bucket of
+ * 2..255 occurrences becomes one match with a column per occurrence (Match(multiplicity), as SeedMatchEnumerator's),
+ * extended and de-duplicated like a MemHash entry. */
+class RepeatHash : public MatchFinder {
+public:
+    virtual RepeatHash* Clone() const { return new RepeatHash(*this); }
+    virtual boolean FindMatches(MatchList& match_list) {
+        for (size_t i = 0; i < match_list.seq_table.size(); ++i)
+            if (!AddSequence(match_list.sml_table[i], match_list.seq_table[i])) return false;
+        if (seq_count != 1) { genome::ErrorMsg("RepeatHash: exactly one sequence expected\n"); return false; }
+        for (Match* m : match_list) m->Free();
+        match_list.clear();
+        mb_params p = {MB_MODE_REPEAT, 0, 2, 255, 0};
+        return run(p, match_list, false);
+    }
+};
+
 class MaskedMemHash : public MemHash {
 public:
     virtual MaskedMemHash* Clone() const { return new MaskedMemHash(*this); }

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MAUVE_B200_LIB") or os.path.join(_HERE, "libmauve_b200.so")  # the override is a tuning aid
 
 MB_OK = 0
-MODE_UNIQUE, MODE_SEED_ENUM, MODE_UNIQUE_COUNT, MODE_PAIRWISE = 0, 1, 2, 3
+MODE_UNIQUE, MODE_SEED_ENUM, MODE_UNIQUE_COUNT, MODE_PAIRWISE, MODE_REPEAT = 0, 1, 2, 3, 4
 SOLID_SEED = 2 ** 31 - 1
 CODING_SEED = 3
 

@@ -322,9 +322,9 @@ extern "C" {
 int mb_find_device(mb_ctx* c, const mb_params* prm) {
     if (!c || !prm) return MB_E_ARG;
     const int mode = prm->mode;
-    if (mode < MB_MODE_UNIQUE || mode > MB_MODE_PAIRWISE) return MB_E_ARG;
+    if (mode < MB_MODE_UNIQUE || mode > MB_MODE_REPEAT) return MB_E_ARG;
     if (mode == MB_MODE_PAIRWISE && c->seq_len.size() > 8) return MB_E_SEQCOUNT; // the reference uses it for <= 4 genomes
-    if (mode == MB_MODE_SEED_ENUM && c->seq_len.size() > 1) return MB_E_SEQCOUNT;
+    if ((mode == MB_MODE_SEED_ENUM || mode == MB_MODE_REPEAT) && c->seq_len.size() > 1) return MB_E_SEQCOUNT;
     MbiRun run;
     TRY(mbi_setup_run(c, run));
     cudaStream_t st = c->stream;
@@ -705,6 +705,7 @@ int mbi_output_unique(mb_ctx* c, u32 n_cand, u64 maxlen) {
     oa.comp_gs = c->comp_gs.as<u8>();
     oa.ext_l = c->ext_l.as<u32>(); oa.ext_r = c->ext_r.as<u32>(); oa.flags = c->flags.as<u32>(); oa.match_idx = c->match_idx.as<u32>();
     oa.n_matches_ptr = scal + SC_NMATCH;
+    oa.repeat = c->last_mode == MB_MODE_REPEAT;
     launch_uniq_flags(oa, st); LAUNCHED(c);
     launch_scan_u32(oa.flags, n_cand, c->match_idx.as<u32>(), nullptr, c->status_slice(div_up(n_cand, scan_tile())), c->ticket(),
                     scal + SC_NMATCH, st);

@@ -7,6 +7,7 @@
 #define MB_MODE_SEED_ENUM_ 1
 #define MB_MODE_UNIQUE_COUNT_ 2
 #define MB_MODE_PAIRWISE_ 3
+#define MB_MODE_REPEAT_ 4
 
 // ---- kernels_seed.cu
 struct ExtractArgs;
@@ -65,6 +66,7 @@ struct EmitEnumArgs {
     u64* sort_key; u64* sort_val; u32* ncomp;
     const u64* sorted_val; const u64* out_off;
     u32* out_len; u32* out_seq; i64* out_start;
+    int repeat;               // MB_MODE_REPEAT: ties of the first start are ordered as for MB_MODE_SEED_ENUM (multiplicity, signed starts, length)
 };
 void launch_enum_keys(const EmitEnumArgs& a, const RecFmt& fmt, u32 n_upper, cudaStream_t st);
 void launch_enum_gather(const EmitEnumArgs& a, const RecFmt& fmt, u32 seedL, u32 n_upper, cudaStream_t st);
@@ -148,6 +150,7 @@ struct OutputArgs {
     u32* ncomp;
     const u64* out_off;
     u32* out_len; u32* out_seq; i64* out_start;
+    int repeat;               // MB_MODE_REPEAT: ties of the first start are ordered as for MB_MODE_SEED_ENUM (multiplicity, signed starts, length)
 };
 void launch_uniq_flags(const OutputArgs& a, cudaStream_t st);
 void launch_uniq_keys(const OutputArgs& a, int sbits, cudaStream_t st);

@@ -208,6 +208,10 @@ __global__ void __launch_bounds__(SL_NT) k_select(SelectArgs a, RecFmt fmt) {
                 }
             }
             ncand[j] = 1; ncomp[j] = m;
+        } else if (a.mode == MB_MODE_REPEAT_) {
+            // RepeatHash: every occurrence is a component (one sequence); the candidate formats hold up to 255 components
+            if ((u64)len > a.max_multi || (u64)len < a.min_multi || len > 255) continue;
+            ncand[j] = 1; ncomp[j] = len;
         } else {
             u32 u = a.run_u[r + 1] - a.run_u[r];
             if (u < 2) continue;
@@ -304,7 +308,7 @@ __global__ void __launch_bounds__(256) k_emit_unique(EmitUniqueArgs a, RecFmt fm
         bool first = g != prev_g;
         prev_g = g;
         bool lastg = i + 1 == e || rec_genome(fmt, fmt.wide ? a.vals[i + 1] : a.keys[i + 1]) != g;
-        if (!(first && lastg)) continue;
+        if (!(first && lastg) && a.mode != MB_MODE_REPEAT_) continue; // RepeatHash takes every occurrence (position order)
         bool take = pa < 0 || (int)ui == pa || (int)ui == pb;
         ++ui;
         if (!take) continue;

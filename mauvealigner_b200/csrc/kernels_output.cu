@@ -36,6 +36,16 @@ __device__ __forceinline__ u32 abs_start(const OutputArgs& a, const MView& v, u3
 // full D18 comparator: A < B ?
 __device__ bool d18_less(const OutputArgs& a, u32 ca, u32 cb, u32 L) {
     MView A = mview(a, ca), B = mview(a, cb);
+    if (a.repeat) { // one sequence, columns = occurrences: (first start — equal here), multiplicity, signed starts, length
+        if (A.m != B.m) return A.m < B.m;
+        for (u32 k = 1; k < A.m; ++k) {
+            i64 sa = abs_start(a, A, k), sb = abs_start(a, B, k);
+            if (a.comp_gs[A.off + k] & 0x80) sa = -sa;
+            if (a.comp_gs[B.off + k] & 0x80) sb = -sb;
+            if (sa != sb) return sa < sb;
+        }
+        return (A.el + A.er) < (B.el + B.er);
+    }
     u32 k = 0;
     for (;; ++k) {
         bool ea = k >= A.m, eb = k >= B.m;

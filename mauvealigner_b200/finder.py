@@ -566,6 +566,24 @@ class SeedMatchEnumerator(MatchFinder):
         return SeedMatchEnumerator(self._ctx)
 
 
+class RepeatHash(MatchFinder):
+    """libMems RepeatHash (mauveAligner --repeats, src/mauveAligner.cpp:480-487): repeats inside ONE sequence — every
+    bucket of min_multi..max_multi occurrences becomes one match with a column per occurrence, extended and
+    de-duplicated like a MemHash entry."""
+
+    def FindMatches(self, match_list, min_multi=2, max_multi=255):
+        del match_list[:]
+        if len(match_list.seq_table) != 1:
+            return False
+        ctx = self._load(match_list)
+        self.last = ctx.find(L.MODE_REPEAT, min_multi=min_multi, max_multi=max_multi)
+        self._fill(match_list, self.last, 1, dense=False)
+        return True
+
+    def Clone(self):
+        return RepeatHash(self._ctx)
+
+
 def find_multi(ctxs, nway_mask=0):
     """mb_find_multi: MODE_UNIQUE over one context per GPU (or several per GPU), driven by the library's own host threads
     with every exchange device to device over NVLink peer access — no torch.distributed, no NCCL.  The same sequences

@@ -163,11 +163,16 @@ static uint64_t hash_vec(const std::vector<int64_t>& v) {
     return h;
 }
 
+/* genome behind column `col` of a match: the column itself, except for RepeatHash matches (ORC_MODE_REPEAT), whose
+ * columns are the occurrences inside the one sequence (as for SeedMatchEnumerator, GetSar(i) = SML 0) */
+static inline uint32_t gm(const Ctx& c, uint32_t col) { return c.mode == ORC_MODE_REPEAT ? 0u : col; }
+
 /* D16 group key: invariant of a match under extension. */
 static void group_key(const Ctx& c, const std::vector<int64_t>& st, uint32_t length, std::vector<int64_t>& key) {
+    (void)c;
     key.clear();
     int first = -1;
-    for (uint32_t g = 0; g < c.nseq; ++g) {
+    for (uint32_t g = 0; g < st.size(); ++g) {
         if (st[g] == 0) continue;
         if (first < 0) first = (int)g;
         key.push_back((int64_t)g);
@@ -181,12 +186,12 @@ static void extend_match(const Ctx& c, std::vector<int64_t>& st, int64_t& length
     const int L = c.seed.L;
     const uint64_t mer_mask = ~1ull; /* key bits (left aligned) without the strand bit */
     std::vector<uint32_t> used;
-    for (uint32_t g = 0; g < c.nseq; ++g) if (st[g] != 0) used.push_back(g);
+    for (uint32_t g = 0; g < st.size(); ++g) if (st[g] != 0) used.push_back(g);
     int64_t jump = L;
     for (int dir = 0; dir < 4; ++dir) {
         int64_t maxlen = (dir < 2) ? INT64_MAX : (int64_t)L;
         for (uint32_t g : used) {
-            int64_t room = st[g] < 0 ? (int64_t)c.lens[g] - length + st[g] + 1 : st[g] - 1;
+            int64_t room = st[g] < 0 ? (int64_t)c.lens[gm(c, g)] - length + st[g] + 1 : st[g] - 1;
             if (room < maxlen) maxlen = room;
         }
         while (maxlen - jump >= 0) {
@@ -197,7 +202,7 @@ static void extend_match(const Ctx& c, std::vector<int64_t>& st, int64_t& length
             for (size_t i = 0; i < used.size(); ++i) {
                 uint32_t g = used[i];
                 int64_t pos = st[g] > 0 ? st[g] : -st[g] + length - L;
-                uint64_t m = c.mers[g][(size_t)(pos - 1)];
+                uint64_t m = c.mers[gm(c, g)][(size_t)(pos - 1)];
                 bool par = st[g] < 0 ? (m & 1) : !(m & 1);
                 m &= mer_mask;
                 if (i == 0) { ref_mer = m; ref_par = par; }
@@ -329,6 +334,22 @@ static void hash_match_enum(Ctx& c, std::vector<idmer>& bucket) {
     }
 }
 
+/* RepeatHash (mauveAligner --repeats, src/mauveAligner.cpp:480-487) [LM-recall, SURVEY A.2]: one sequence; every bucket
+ * of min_multi..max_multi occurrences (at most 255 here) becomes ONE entry with a component per occurrence in position
+ * order, signs as SeedMatchEnumerator::SetDirection (src/SeedMatchEnumerator.h:127-141), then it goes through the same
+ * AddHashEntry (containment de-dup D16 + ExtendMatch D14) as a MemHash entry. */
+static void hash_match_repeat(Ctx& c, std::vector<idmer>& bucket) {
+    std::stable_sort(bucket.begin(), bucket.end(), [](const idmer& a, const idmer& b) { return a.position < b.position; });
+    size_t m = bucket.size();
+    if (m < 2 || m < c.min_multi || m > c.max_multi || m > 255) return;
+    std::vector<int64_t> st(m);
+    for (size_t i = 0; i < m; ++i) st[i] = (int64_t)bucket[i].position + 1;
+    bool ref_forward = !(c.mers[0][(size_t)(st[0] - 1)] & 1);
+    for (size_t i = 1; i < m; ++i)
+        if (ref_forward == (bool)(c.mers[0][(size_t)(st[i] - 1)] & 1)) st[i] = -st[i];
+    add_hash_entry(c, st);
+}
+
 /* a6: MatchFinder::FindMatchSeeds — N-way merge of the SMLs, ascending masked mer. */
 static void find_match_seeds(Ctx& c) {
     struct Head { uint64_t key; uint32_t id; uint64_t idx; };
@@ -342,6 +363,7 @@ static void find_match_seeds(Ctx& c) {
         if (cur.size() > 1) {
             ++c.n_buckets;
             if (c.mode == ORC_MODE_SEED_ENUM) hash_match_enum(c, cur);
+            else if (c.mode == ORC_MODE_REPEAT) hash_match_repeat(c, cur);
             else enumerate_unique(c, cur);
         }
         cur.clear();
@@ -382,7 +404,7 @@ static bool less_enum(const MatchRec& a, const MatchRec& b) {
     if (a.start.size() != b.start.size()) return a.start.size() < b.start.size();
     for (size_t i = 1; i < a.start.size(); ++i)
         if (a.start[i] != b.start[i]) return a.start[i] < b.start[i];
-    return false;
+    return a.length < b.length; /* (extended RepeatHash matches; SeedMatchEnumerator matches all have the seed length) */
 }
 
 /* match records -> the CSR arrays of orc_result */
@@ -404,7 +426,7 @@ static void pack_result(const Ctx& c, int mode, orc_result* r) {
         r->comp_off[i] = k;
         for (size_t g = 0; g < m.start.size(); ++g)
             if (m.start[g] != 0) {
-                r->comp_seq[k] = mode == ORC_MODE_SEED_ENUM ? 0u : (uint32_t)g;
+                r->comp_seq[k] = (mode == ORC_MODE_SEED_ENUM || mode == ORC_MODE_REPEAT) ? 0u : (uint32_t)g;
                 r->comp_start[k] = m.start[g];
                 ++k;
             }
@@ -484,8 +506,8 @@ int orc_find(uint32_t nseq, const uint8_t* const* ascii, const uint64_t* lens,
     }
     double t2 = now_s();
 
-    if (mode == ORC_MODE_SEED_ENUM && nseq != 1) {
-        /* SeedMatchEnumerator::CreateMatches does nothing unless seq_count == 1 (:59-65) */
+    if ((mode == ORC_MODE_SEED_ENUM || mode == ORC_MODE_REPEAT) && nseq != 1) {
+        /* SeedMatchEnumerator::CreateMatches does nothing unless seq_count == 1 (:59-65); RepeatHash likewise */
     } else if (mode != ORC_MODE_UNIQUE_COUNT) {
         find_match_seeds(c);
     }
@@ -502,7 +524,7 @@ int orc_find(uint32_t nseq, const uint8_t* const* ascii, const uint64_t* lens,
             r->unique_mers = (uint64_t)(std::unique(all.begin(), all.end()) - all.begin());
         }
     }
-    if (mode == ORC_MODE_SEED_ENUM) std::sort(c.out.begin(), c.out.end(), less_enum);
+    if (mode == ORC_MODE_SEED_ENUM || mode == ORC_MODE_REPEAT) std::sort(c.out.begin(), c.out.end(), less_enum);
     else std::sort(c.out.begin(), c.out.end(), less_unique);
     double t3 = now_s();
 

@@ -26,7 +26,8 @@ enum {
     ORC_MODE_UNIQUE = 0,       /* UniqueMatchFinder / MemHash: unique filter + extend + dedup */
     ORC_MODE_SEED_ENUM = 1,    /* SeedMatchEnumerator: one un-extended match per bucket      */
     ORC_MODE_UNIQUE_COUNT = 2, /* SortedMerList::UniqueMerCount only                         */
-    ORC_MODE_PAIRWISE = 3      /* PairwiseMatchFinder: unique filter, HashMatch every pair   */
+    ORC_MODE_PAIRWISE = 3,     /* PairwiseMatchFinder: unique filter, HashMatch every pair   */
+    ORC_MODE_REPEAT = 4        /* RepeatHash: one sequence, every occurrence a component, extend + dedup */
 };
 
 typedef struct orc_result {

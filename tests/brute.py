@@ -10,7 +10,7 @@ Policy code follows /root/reference/src/UniqueMatchFinder.cpp:36-60 and
 """
 from __future__ import annotations
 
-MODE_UNIQUE, MODE_SEED_ENUM, MODE_UNIQUE_COUNT, MODE_PAIRWISE = 0, 1, 2, 3
+MODE_UNIQUE, MODE_SEED_ENUM, MODE_UNIQUE_COUNT, MODE_PAIRWISE, MODE_REPEAT = 0, 1, 2, 3, 4
 _CODE = {"A": 0, "C": 1, "G": 2, "T": 3, "a": 0, "c": 1, "g": 2, "t": 3}
 
 
@@ -157,6 +157,26 @@ def find(seqs, pattern, mode, min_multi=2, max_multi=1000, direct_only=False, nw
             else:
                 out.append((L, st))
         out.sort(key=lambda r: (r[1][0], len(r[1]), r[1][1:]))
+        res["matches"] = [(ln, [(0, s) for s in st]) for ln, st in out]
+        return res
+
+    if mode == MODE_REPEAT:
+        # RepeatHash: one sequence, every occurrence of a bucket a component (columns = occurrences in position order),
+        # then containment de-dup + extension exactly as for a multi-genome entry
+        if N != 1:
+            return res
+        accepted = []
+        for key in sorted(buckets):
+            b = sorted(buckets[key], key=lambda t: t[1])
+            m = len(b)
+            if m < 2 or m < min_multi or m > max_multi or m > 255:
+                continue
+            st = {i: (p + 1) if strand == b[0][2] else -(p + 1) for i, (_, p, strand) in enumerate(b)}
+            if any(_same_group_contains(e, st, L) for e in accepted):
+                continue
+            accepted.append(extend([mers[0]] * m, [lens[0]] * m, st, L))
+        out = [(length, [st[i] for i in range(len(st))]) for st, length in accepted]
+        out.sort(key=lambda r: (r[1][0], len(r[1]), r[1][1:], r[0]))
         res["matches"] = [(ln, [(0, s) for s in st]) for ln, st in out]
         return res
 

@@ -20,7 +20,7 @@ static string read_seq(const char* path) {
 }
 
 int main(int argc, char** argv) {
-    if (argc < 3) { cerr << "usage: compat_driver <umf|pmf|sme|count|sml|family> <weight> <rank> <seq files...> | smlcount <file.sslist> | readlist <file>\n"; return -1; }
+    if (argc < 3) { cerr << "usage: compat_driver <umf|pmf|sme|repeats|count|sml|family> <weight> <rank> <seq files...> | smlcount <file.sslist> | readlist <file>\n"; return -1; }
     string what = argv[1];
     if (what == "smlcount") {
         // src/uniqueMerCount.cpp:29-39, line for line
@@ -108,6 +108,12 @@ int main(int argc, char** argv) {
         umf.LogProgress(nullptr);
         if (!umf.FindMatches(ml)) return -2;
         umf.Clear();
+        WriteList(ml, cout);
+    } else if (what == "repeats") {
+        // src/mauveAligner.cpp:480-487
+        RepeatHash repeat_finder;
+        repeat_finder.LogProgress(nullptr);
+        repeat_finder.FindMatches(ml);
         WriteList(ml, cout);
     } else if (what == "sme") {
         SeedMatchEnumerator sme;

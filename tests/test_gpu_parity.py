@@ -184,6 +184,36 @@ def test_seed_enum_vs_oracle(ctx, seed):
         assert got["n_matches"] > 0
 
 
+@pytest.mark.parametrize("seed", range(6))
+def test_repeat_hash_vs_oracle(ctx, seed):
+    """MB_MODE_REPEAT (RepeatHash, src/mauveAligner.cpp:480-487) against the oracle: repeat families with diverged and
+    inverted copies, tandem arrays, low-complexity tracts; multiplicity windows"""
+    import mauvealigner_b200 as mb
+    rng = np.random.default_rng(7100 + seed)
+    units = [rand_seq(rng, int(rng.integers(60, 400))) for _ in range(6)]
+    parts = []
+    for _ in range(60):
+        parts.append(rand_seq(rng, int(rng.integers(50, 600))))
+        u = units[int(rng.integers(0, len(units)))]
+        c = mutate(rng, u, sub=0.03 * (seed % 3), indel=0.002 * (seed % 2))
+        parts.append(revcomp(c) if rng.random() < 0.3 else c)
+    parts.append(rand_seq(rng, 9) * 12 + "ACACACACACACACACACACACACACACAC" + "A" * 40)
+    s = "".join(parts)
+    pattern = [mb.get_seed(9, 0), mb.get_seed(11, 1), mb.get_seed(11, 2), mb.get_seed(13, 0), mb.get_seed(9, 2), 0b1011101][seed]
+    kw = dict(min_multi=2 + seed % 2, max_multi=[255, 1000, 4, 17, 255, 40][seed])
+    got = run(ctx, [s], pattern, mb.MODE_REPEAT, **kw)
+    want = O.find([s], pattern, O.MODE_REPEAT, **kw)
+    assert_same(got, want, f"repeat {seed}")
+    assert want["n_matches"] > 0 or seed == 5
+    # RepeatHash through the Python mirror
+    ml = mb.MatchList()
+    ml.seq_table = [s]
+    ml.seed_pattern = pattern
+    rh = mb.RepeatHash()
+    assert rh.FindMatches(ml, **kw)
+    assert [(m.Length(), [m.Start(i) for i in range(m.SeqCount())]) for m in ml] == [(ln, [st for _, st in comps]) for ln, comps in O.matches_as_list(want)]
+
+
 def test_edge_cases(ctx):
     import mauvealigner_b200 as mb
     # sequences shorter than the seed, empty sequences
@@ -260,6 +290,9 @@ def test_cpp_host_api_matches_oracle(tmp_path):
     assert parse(out) == rows and len(rows) > 10
     out = subprocess.check_output([str(exe), "sme", "9", "0", files[0]], text=True)
     want = O.find(seqs[:1], mb.get_seed(9, 0), O.MODE_SEED_ENUM, min_multi=2, max_multi=500)
+    assert parse(out) == [[ln] + [s for _, s in comps] for ln, comps in O.matches_as_list(want)]
+    out = subprocess.check_output([str(exe), "repeats", "9", "0", files[0]], text=True)
+    want = O.find(seqs[:1], mb.get_seed(9, 0), O.MODE_REPEAT, min_multi=2, max_multi=255)
     assert parse(out) == [[ln] + [s for _, s in comps] for ln, comps in O.matches_as_list(want)]
     out = subprocess.check_output([str(exe), "count", "9", "0", files[0]], text=True)
     assert int(out.split()[-1]) == O.find(seqs[:1], mb.get_seed(9, 0), O.MODE_UNIQUE_COUNT)["unique_mers"]

@@ -161,6 +161,24 @@ def test_seed_enum_vs_brute(seed):
     assert len(got) > 0
 
 
+@pytest.mark.parametrize("seed", range(8))
+def test_repeat_hash_vs_brute(seed):
+    """RepeatHash (mauveAligner --repeats, src/mauveAligner.cpp:480-487): one sequence, every occurrence a component,
+    extension + containment de-dup; direct, diverged and inverted copies, a tandem array and a low-complexity tail"""
+    rng = np.random.default_rng(900 + seed)
+    pattern = PATTERNS[seed % 4]
+    unit = rand_seq(rng, 60)
+    s = (rand_seq(rng, 80) + unit + rand_seq(rng, 40) + mutate(rng, unit, sub=0.04, indel=0) + rand_seq(rng, 30) + revcomp(unit) +
+         rand_seq(rng, 50) + unit[:35] + rand_seq(rng, 20) + (rand_seq(rng, 7) * 6) + "AT" * 15 + rand_seq(rng, 30))
+    kw = dict(min_multi=2 + seed % 2, max_multi=[1000, 6, 3][seed % 3])
+    got = as_brute_list(O.find([s], pattern, O.MODE_REPEAT, **kw))
+    want = brute.find([s], pattern, brute.MODE_REPEAT, **kw)["matches"]
+    assert got == want
+    assert len(got) > 0
+    assert brute.seed_len(pattern) < 7 or any(ln > brute.seed_len(pattern) for ln, _ in got)  # something was extended
+    assert O.find([s, s], pattern, O.MODE_REPEAT)["n_matches"] == 0  # one sequence only
+
+
 def test_seed_enum_needs_one_sequence():
     # SeedMatchEnumerator::CreateMatches is a no-op unless seq_count == 1 (SeedMatchEnumerator.h:59-65)
     r = O.find(["ACGTACGTACGTAAC", "ACGTACGTACGTAAC"], 0b111, O.MODE_SEED_ENUM)
