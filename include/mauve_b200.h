@@ -128,6 +128,31 @@ int mb_find_device(mb_ctx* ctx, const mb_params* params);
 /* Device -> pinned host copy of the last mb_find_device result (synchronises the stream). */
 int mb_fetch_result(mb_ctx* ctx, const mb_result** out);
 
+/* ---- many small problems in one pass (recursive anchoring: the aligners re-run the search inside every gap between
+ * anchors — `recursive` flag src/mauveAligner.cpp:94,698; SetRecursive src/progressiveMauve.cpp:661-664) ------------------
+ * mb_find_batch: n_problems independent searches, each over its own nseq sequences (seqs[i * nseq + g] / lens[i * nseq + g]:
+ * HOST ASCII of sequence g of problem i; a length of 0 = the problem has no sequence g), with one seed and one policy.
+ * The library lays the problems side by side, runs the pipeline ONCE (the problem index leads the sort key, windows and
+ * extension stop at the piece boundaries) and cuts the result by problem.  Every problem's matches are exactly those
+ * of its own mb_find, in its canonical order, with coordinates relative to its own sequences.
+ * Single GPU; not MB_MODE_UNIQUE_COUNT.  The result is owned by the context until its next batch / destroy. */
+typedef struct mb_batch_result {
+    uint64_t n_problems;
+    uint64_t n_matches, n_comps;
+    const uint64_t* match_off;   /* [n_problems + 1]: matches of problem i = [match_off[i], match_off[i + 1])      */
+    const uint32_t* length;      /* [n_matches]                                                                    */
+    const uint64_t* comp_off;    /* [n_matches + 1]                                                                */
+    const uint32_t* comp_seq;    /* [n_comps]                                                                      */
+    const int64_t* comp_start;   /* [n_comps] signed, 1-based, relative to the problem's own sequence              */
+} mb_batch_result;
+int mb_find_batch(mb_ctx* ctx, const mb_params* params, uint32_t n_problems, uint32_t nseq, const uint8_t* const* seqs, const uint64_t* lens,
+                  const mb_batch_result** out);
+/* The mechanism underneath, for callers that hold the concatenated sequences already: after the mb_add_sequence calls,
+ * bounds[g * (n_problems + 1) + i] = first base of piece i of sequence g (ascending, bounds[..][0] = 0, the last entry =
+ * the sequence length).  The following searches are segmented (coordinates stay those of the concatenations);
+ * n_problems = 0 or mb_clear_sequences ends it. */
+int mb_set_segments(mb_ctx* ctx, uint32_t n_problems, const uint64_t* bounds);
+
 /* ---- multi-GPU path ---------------------------------------------
  * One context per rank / GPU, the same sequences added to every context (replicated genomes).
  * The library runs the per-rank stages and owns the exchange buffers; the exchanges between the stages are

@@ -27,6 +27,12 @@ class MbResult(C.Structure):
                 ("unique_mers", C.c_uint64), ("unique_mers_per_seq", C.POINTER(C.c_uint64)), ("nseq", C.c_uint32)]
 
 
+class MbBatchResult(C.Structure):
+    _fields_ = [("n_problems", C.c_uint64), ("n_matches", C.c_uint64), ("n_comps", C.c_uint64), ("match_off", C.POINTER(C.c_uint64)),
+                ("length", C.POINTER(C.c_uint32)), ("comp_off", C.POINTER(C.c_uint64)), ("comp_seq", C.POINTER(C.c_uint32)),
+                ("comp_start", C.POINTER(C.c_int64))]
+
+
 class MbStats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("n_seeds", "n_runs", "n_buckets", "n_candidates", "n_extended", "n_matches", "n_comps")] + \
                [(n, C.c_uint32) for n in ("radix_passes", "record_bytes", "dedup_batches", "dedup_iters")] + \
@@ -40,7 +46,7 @@ EXPORTS = ["mb_ctx_create", "mb_ctx_destroy", "mb_set_stream", "mb_add_sequence"
            "mb_set_seed", "mb_find", "mb_find_device", "mb_fetch_result", "mb_get_sml", "mb_get_mers", "mb_get_stats", "mb_strerror",
            "mb_last_cuda_error", "mb_device_count", "mb_version",
            "mb_dist_extract", "mb_dist_extract_count", "mb_dist_partition", "mb_dist_p2p_recv_array",
-           "mb_dist_use_p2p_recv", "mb_ipc_export", "mb_ipc_import", "mb_ipc_close", "mb_dist_recv_buffer", "mb_dist_local", "mb_dist_rows_pack", "mb_dist_push", "mb_dist_resolve", "mb_dist_accept", "mb_dist_match_pack", "mb_dist_match_partition", "mb_dist_output", "mb_dist_stage_ms", "mb_find_multi", "mb_debug_radix"]
+           "mb_dist_use_p2p_recv", "mb_ipc_export", "mb_ipc_import", "mb_ipc_close", "mb_dist_recv_buffer", "mb_dist_local", "mb_dist_rows_pack", "mb_dist_push", "mb_dist_resolve", "mb_dist_accept", "mb_dist_match_pack", "mb_dist_match_partition", "mb_dist_output", "mb_dist_stage_ms", "mb_find_multi", "mb_debug_radix", "mb_find_batch", "mb_set_segments"]
 
 _lib = None
 
@@ -94,6 +100,8 @@ def lib():
     L.mb_find_multi.argtypes = [C.POINTER(vp), i32, C.POINTER(MbParams)]
     L.mb_dist_stage_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.mb_debug_radix.argtypes = [vp, u64, i32, i32, i32, C.POINTER(C.c_float)]
+    L.mb_find_batch.argtypes = [vp, C.POINTER(MbParams), C.c_uint32, C.c_uint32, C.POINTER(vp), pu64, C.POINTER(C.POINTER(MbBatchResult))]
+    L.mb_set_segments.argtypes = [vp, C.c_uint32, pu64]
     _lib = L
     return L
 

@@ -93,7 +93,7 @@ int mb_ctx_destroy(mb_ctx* c) {
                     &c->bitmap, &c->bmrank, &c->cand_at, &c->cstate, &c->covered, &c->ghash2, &c->rep_cand, &c->s_h2, &c->reach, &c->xstate, &c->xrec, &c->x_lut, &c->x_counts, &c->x_hdr_s, &c->x_comp_s, &c->x_hdr_r, &c->x_comp_r, &c->x_m, &c->x_key, &c->x_item, &c->x_peers, &c->x_recv, &c->q_off, &c->q_pos, &c->q_gs, &c->q_el, &c->q_er, &c->q_perm, &c->q_state, &c->q_item, &c->x_acc_s, &c->x_acc_r, &c->minrank, &c->ext_l, &c->ext_r, &c->wl_a, &c->wl_b, &c->wl_c, &c->wl_long, &c->wd_a, &c->wd_b, &c->wd_c, &c->live_bits, &c->trace, &c->ghash, &c->slot_gp, &c->slot_hash, &c->link_bits, &c->chain_min, &c->rep_bits, &c->rep_rank, &c->s_hash, &c->s_cand, &c->rng_lo, &c->rng_hi, &c->flags,
                     &c->match_idx, &c->sort_kA, &c->sort_kB, &c->sort_vA, &c->sort_vB, &c->ncomp, &c->mers_tmp, &c->out_len, &c->out_off,
                     &c->out_seq, &c->out_start, &c->fam_th1, &c->fam_th2, &c->fam_tx, &c->fam_tend, &c->fam_sh1, &c->fam_sh2, &c->fam_sx, &c->fam_send,
-                    &c->fam_spmax, &c->fam_srun0, &c->fam_drop};
+                    &c->fam_spmax, &c->fam_srun0, &c->fam_drop, &c->seg};
     for (DBuf* b : bufs) free_buf(*b);
     void* hs[] = {c->h_len, c->h_off, c->h_seq, c->h_start, c->h_perseq, c->h_scal};
     for (void* h : hs) if (h) cudaFreeHost(h);
@@ -131,6 +131,7 @@ int mb_accumulate(mb_ctx* c, int on) {
 int mb_clear_sequences(mb_ctx* c) {
     if (!c) return MB_E_ARG;
     c->seq_len.clear(); c->seq_word_base.clear(); c->words_used = 0; c->have_result = false;
+    c->n_seg = 0; c->h_seg.clear();
     c->stats.h2d_bytes = 0;
     return MB_OK;
 }
@@ -283,6 +284,7 @@ int mbi_setup_run(mb_ctx* c, MbiRun& r) {
     r.tile_first[nseq] = n_tiles;
     gt.pairwise = 0;
     for (u32 g = 0; g < nseq; ++g) gt.vbase[g] = gt.base_base[g];
+    if (c->n_seg && c->h_seg.size() != (size_t)nseq * (c->n_seg + 1)) return MB_E_STATE; // segments set for another sequence count
     if (n64 >= (1ull << 31)) return MB_E_TOOLONG;
     const u32 n = (u32)n64;
     r.n = n; r.n_tiles = n_tiles; r.bases = bases; r.maxlen = maxlen;
@@ -293,6 +295,15 @@ int mbi_setup_run(mb_ctx* c, MbiRun& r) {
     fmt.gbits = mbi_bits_for(nseq - 1);
     fmt.pbits = mbi_bits_for(maxlen ? maxlen - 1 : 0);
     if (fmt.pbits == 0) fmt.pbits = 1;
+    if (c->n_seg) { // segmented search: problem index | max(seed, genome + position) bits
+        gt.n_seg = c->n_seg;
+        gt.seg_field = (u32)std::max(fmt.kbits, fmt.gbits + fmt.pbits);
+        fmt.kbits = (int)gt.seg_field + mbi_bits_for(c->n_seg);
+        if (fmt.kbits > 64) return MB_E_TOOLONG;
+        TRY(c->reserve(c->seg, c->h_seg.size() * 4));
+        CUDA_TRY(c, cudaMemcpyAsync(c->seg.p, c->h_seg.data(), c->h_seg.size() * 4, cudaMemcpyHostToDevice, st));
+        gt.seg = c->seg.as<u32>();
+    }
     fmt.wide = (fmt.kbits + fmt.gbits + fmt.pbits + 1) > 64;
     fmt.kshift = fmt.wide ? 0 : fmt.gbits + fmt.pbits + 1;
     c->stats.record_bytes = fmt.wide ? 16 : 8;

@@ -30,6 +30,7 @@ extern "C" {
 int mb_dist_extract_count(mb_ctx* c, int rank, int world, uint64_t* h_counts) {
     if (!c || !h_counts || world < 1 || world > 256 || rank < 0 || rank >= world) return MB_E_ARG;
     MbiRun run;
+    if (c->n_seg) return MB_E_STATE; // segmented searches are single-GPU
     TRY(mbi_setup_run(c, run));
     if (c->fmt.wide) return MB_E_ARG;
     cudaStream_t st = c->stream;

@@ -60,7 +60,23 @@ struct GenomeTable {
     // where several candidates of one bucket share their first component)
     u32 pairwise;
     u64 vbase[MB_MAX_SEQ];       // first bitmap index of virtual genome v
+    // Segmented search (many small problems in one pass, mb_find_batch): every genome is a concatenation of n_seg
+    // segments, segment i of every genome forming problem i.  seg[g * (n_seg + 1) + i] = first base of segment i of
+    // genome g (ascending, the last entry = the genome's length).  Seeds only meet seeds of the same problem, a window
+    // never crosses a segment boundary and extension stops at it.  n_seg == 0: plain search.
+    const u32* seg;
+    u32 n_seg;
+    u32 seg_field;               // key bits below the problem index: max(2w, genome bits + position bits)
 };
+// segment [lo, hi) of genome g that holds base p (the whole genome without segments)
+__device__ __forceinline__ u32 seg_range(const GenomeTable& gt, u32 g, u32 p, u32& lo, u32& hi) {
+    if (!gt.n_seg) { lo = 0; hi = gt.len[g]; return 0; }
+    const u32* b = gt.seg + (size_t)g * (gt.n_seg + 1);
+    u32 a = 0, z = gt.n_seg; // largest i with b[i] <= p
+    while (z - a > 1) { u32 mid = (a + z) >> 1; if (b[mid] <= p) a = mid; else z = mid; }
+    lo = b[a]; hi = b[a + 1];
+    return a;
+}
 __host__ __device__ __forceinline__ u32 vgenome(const GenomeTable& gt, u32 g0, u32 g1) {
     return gt.pairwise ? g0 * gt.nseq - g0 * (g0 + 1) / 2 + (g1 - g0 - 1) : g0;
 }

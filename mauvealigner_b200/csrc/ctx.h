@@ -55,6 +55,16 @@ struct mb_ctx {
     DBuf wl_a, wl_b, wl_c, wl_long, wd_a, wd_b, wd_c, live_bits, ghash, slot_gp, slot_hash, link_bits, chain_min, rep_bits, rep_rank, s_hash, s_cand, rng_lo, rng_hi;
     DBuf flags, match_idx, sort_kA, sort_kB, sort_vA, sort_vB, ncomp, mers_tmp;
     DBuf out_len, out_off, out_seq, out_start;
+    // segmented search (mb_set_segments / mb_find_batch): host copy of the bounds [nseq][n_seg + 1], device copy
+    std::vector<u32> h_seg;
+    u32 n_seg = 0;
+    DBuf seg;
+    // result of mb_find_batch (host, owned by the context)
+    std::vector<u64> b_moff, b_coff;
+    std::vector<u32> b_len, b_seq;
+    std::vector<i64> b_start;
+    mb_batch_result bres{};
+    std::vector<u8> b_concat;
     // persistent MemHash table across searches (mb_accumulate; kernels_family.cu)
     bool fam_on = false, fam_dirty = false, fam_pre = false;
     u32 fam_n = 0;

@@ -298,8 +298,9 @@ __device__ u32 scan_steps(const u64* __restrict__ packed, const GenomeTable& gt,
 
 __device__ __forceinline__ void candidate_room(const GenomeTable& gt, u32 L, const u32* cpos, const u8* cgs, u32 k, u32& room_l, u32& room_r) {
     u8 gs = cgs[k];
-    u32 p = cpos[k], len = gt.len[gs & 0x7F];
-    u32 lroom = p, rroom = len - L - p;
+    u32 p = cpos[k], lo, hi;
+    seg_range(gt, gs & 0x7F, p, lo, hi);
+    u32 lroom = p - lo, rroom = hi - L - p;
     bool rev = gs & 0x80;
     room_l = min(room_l, rev ? rroom : lroom);
     room_r = min(room_r, rev ? lroom : rroom);
@@ -618,8 +619,10 @@ __device__ __forceinline__ void extend_rounds(const DedupArgs& a, const GenomeTa
     const u32 per_chunk = (3 * L <= 65) ? 2 : 1;
     if (FIRST) {
         // component 0 is forward
-        sRoom[lane][0] = x.st != ST_DONE ? x.p0 : INF32;
-        sRoom[lane][1] = x.st != ST_DONE ? gt.len[x.g0] - L - x.p0 : INF32;
+        u32 lo0 = 0, hi0 = 0;
+        if (x.st != ST_DONE) seg_range(gt, x.g0, x.p0, lo0, hi0);
+        sRoom[lane][0] = x.st != ST_DONE ? x.p0 - lo0 : INF32;
+        sRoom[lane][1] = x.st != ST_DONE ? hi0 - L - x.p0 : INF32;
     }
     for (int round = 0; round < max_rounds; ++round) {
         const bool want = x.st != ST_DONE;
@@ -661,8 +664,9 @@ __device__ __forceinline__ void extend_rounds(const DedupArgs& a, const GenomeTa
                 if (xb >> 32) atomicOr(&sMap[j][2], (u32)(xb >> 32));
                 if ((u32)xb) atomicOr(&sMap[j][3], (u32)xb);
                 if (FIRST && round == 0) {
-                    u32 len = gt.len[gs & 0x7F];
-                    u32 lroom = pk, rroom = len - L - pk;
+                    u32 lo, hi;
+                    seg_range(gt, gs & 0x7F, pk, lo, hi);
+                    u32 lroom = pk - lo, rroom = hi - L - pk;
                     bool rev = gs & 0x80;
                     atomicMin(&sRoom[j][0], rev ? rroom : lroom);
                     atomicMin(&sRoom[j][1], rev ? lroom : rroom);

@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(EX_NT) k_extract(ExtractArgs a, GenomeTable gt
     }
     __syncthreads();
 
-    const u32 kshift_la = 64 - fmt.kbits;
+    const u32 kshift_la = 64 - 2 * sd.w; // (fmt.kbits = 2w, plus the problem index bits of a segmented search)
 #pragma unroll 4
     for (int it = 0; it < EX_IPT; ++it) {
         u32 o = it * EX_NT + tid;
@@ -128,6 +128,11 @@ __global__ void __launch_bounds__(EX_NT) k_extract(ExtractArgs a, GenomeTable gt
         rh &= sd.mask_hi; rl &= sd.mask_lo;
         bool strand = (rh < fh) || (rh == fh && rl < fl);
         u64 key = gather_key(sd, strand ? rh : fh, strand ? rl : fl) >> kshift_la;
+        if (MODE != 2 && gt.n_seg) { // segmented search: the problem index leads the key; a window across a boundary gets a key of its own
+            u32 lo, hi;
+            const u32 si = seg_range(gt, g, p, lo, hi);
+            key = (p + sd.L <= hi) ? (((u64)si << gt.seg_field) | key) : (((u64)gt.n_seg << gt.seg_field) | ((u64)g << fmt.pbits) | p);
+        }
         if (MODE == 2) {
             a.mers[p] = (key << kshift_la) | (u64)strand;
         } else {

@@ -110,6 +110,41 @@ class Context:
         _check(self._h, L.lib().mb_find(self._h, C.byref(p), C.byref(out)))
         return self._wrap(out.contents, copy)
 
+    def find_batch(self, problems, mode=L.MODE_UNIQUE, min_multi=2, max_multi=1000, direct_only=False, nway_mask=0):
+        """mb_find_batch: many small independent searches (recursive anchoring, src/mauveAligner.cpp:94,698) in ONE pass of
+        the pipeline.  problems = list of lists of sequences (all lists of one length; an empty sequence = absent).
+        Returns one result dict per problem (n_matches, length, comp_off, comp_seq, comp_start), each exactly what find()
+        returns for that problem alone."""
+        nprob = len(problems)
+        nseq = len(problems[0]) if nprob else 1
+        keep, ptrs, lens = [], (C.c_void_p * max(1, nprob * nseq))(), (C.c_uint64 * max(1, nprob * nseq))()
+        for i, prob in enumerate(problems):
+            if len(prob) != nseq:
+                raise ValueError("every problem needs the same number of sequences")
+            for g, s in enumerate(prob):
+                a = np.frombuffer(s.encode() if isinstance(s, str) else bytes(s), dtype=np.uint8) if not isinstance(s, np.ndarray) else np.ascontiguousarray(s, dtype=np.uint8)
+                keep.append(a)
+                ptrs[i * nseq + g] = a.ctypes.data if a.size else None
+                lens[i * nseq + g] = a.size
+        out = C.POINTER(L.MbBatchResult)()
+        p = self._params(mode, min_multi, max_multi, direct_only, nway_mask)
+        _check(self._h, L.lib().mb_find_batch(self._h, C.byref(p), nprob, nseq, ptrs, lens, C.byref(out)))
+        r = out.contents
+
+        def arr(ptr, n, dt):
+            return np.ctypeslib.as_array(ptr, shape=(n,)).astype(dt, copy=True) if n else np.zeros(0, dtype=dt)
+
+        moff = arr(r.match_off, nprob + 1, np.uint64)
+        length, coff = arr(r.length, r.n_matches, np.uint32), arr(r.comp_off, r.n_matches + 1, np.uint64)
+        cseq, cstart = arr(r.comp_seq, r.n_comps, np.uint32), arr(r.comp_start, r.n_comps, np.int64)
+        res = []
+        for i in range(nprob):
+            a, b = int(moff[i]), int(moff[i + 1])
+            ca, cb = (int(coff[a]), int(coff[b])) if r.n_matches else (0, 0)
+            res.append(dict(n_matches=b - a, n_comps=cb - ca, length=length[a:b], comp_off=coff[a:b + 1] - np.uint64(ca) if b > a else np.zeros(1, dtype=np.uint64),
+                            comp_seq=cseq[ca:cb], comp_start=cstart[ca:cb]))
+        return res
+
     @staticmethod
     def _wrap(r, copy):
         nm, nc, ns = int(r.n_matches), int(r.n_comps), int(r.nseq)

@@ -366,6 +366,44 @@ def test_seed_family_vs_oracle(seed):
     assert [(m.Length(), [(g, m.Start(g)) for g in range(k) if m.Start(g) != 0]) for m in ml] == [(ln, list(c)) for ln, c in O.matches_as_list(single)]
 
 
+def test_find_batch_many_small_problems_one_pass():
+    """mb_find_batch (recursive anchoring: thousands of tiny searches, src/mauveAligner.cpp:94,698): all problems in ONE
+    pass of the pipeline; every problem's result equals its own search (oracle), whatever its neighbours are"""
+    import mauvealigner_b200 as mb
+    rng = np.random.default_rng(314)
+    ctx = mb.Context(0)
+    for mode, k, pattern in ((mb.MODE_UNIQUE, 3, 0b1011101), (mb.MODE_UNIQUE, 2, mb.get_seed(9, 0)), (mb.MODE_PAIRWISE, 3, 0b110111011),
+                             (mb.MODE_UNIQUE, 5, 0b1101011)):
+        problems = []
+        for i in range(150):
+            n = int(rng.integers(0, 700)) if i % 17 else int(rng.integers(0, 12))  # some shorter than the seed, some empty
+            seqs = family(rng, n, k, sub=0.04, indel=0.006, inv=i % 2) if n > 40 else [rand_seq(rng, n) for _ in range(k)]
+            if i % 11 == 3:
+                seqs[k - 1] = ""  # a problem without its last sequence
+            if i % 13 == 5:
+                seqs[0] = revcomp(seqs[0])
+            if i % 29 == 7 and i > 0:
+                seqs = list(problems[i - 1])  # the same problem twice, side by side: seeds must not meet across problems
+            problems.append(seqs)
+        ctx.set_seed(pattern)
+        got = ctx.find_batch(problems, mode)
+        assert len(got) == len(problems)
+        total = 0
+        for i, seqs in enumerate(problems):
+            want = O.find(seqs, pattern, mode)
+            assert_same(got[i], want, f"batch problem {i} mode {mode}")
+            total += want["n_matches"]
+        assert total > 200
+    # one sequence per problem: repeats (MB_MODE_REPEAT) and seed enumeration
+    singles = [[rand_seq(rng, 100) + u + rand_seq(rng, 30) + u + revcomp(u)] for u in (rand_seq(rng, 50) for _ in range(40))]
+    ctx.set_seed(0b1011101)
+    for mode, kw in ((mb.MODE_REPEAT, dict(max_multi=255)), (mb.MODE_SEED_ENUM, dict(max_multi=500))):
+        got = ctx.find_batch(singles, mode, **kw)
+        for i, seqs in enumerate(singles):
+            assert_same(got[i], O.find(seqs, 0b1011101, mode, **kw), f"batch single {i} mode {mode}")
+    ctx.close()
+
+
 def test_context_pool_many_small_problems():
     """f4 (many small problems, one search per inter-anchor gap): a pool of contexts on concurrent streams gives the
     results of the one-at-a-time searches, in order, for problems of mixed sizes (including empty ones)."""
