@@ -128,6 +128,13 @@ int mb_find_device(mb_ctx* ctx, const mb_params* params);
 /* Device -> pinned host copy of the last mb_find_device result (synchronises the stream). */
 int mb_fetch_result(mb_ctx* ctx, const mb_result** out);
 
+/* repeatoire's match position lookup table (src/repeatoire.cpp:1944-1966: every component of every seed match entered
+ * at its left end into a table over the sequence), built on the device from the last single-sequence result
+ * (MB_MODE_SEED_ENUM / MB_MODE_REPEAT).  n_pos = sequence length + 1; entry p (1-based left end) = index of the match — in
+ * result order, which is ascending LeftEnd(0), the order of repeatoire's seed_sort_list (:1920-1935) — and of its
+ * component that start at p; 0xFFFFFFFF where none does.  Pinned host arrays owned by the context. */
+int mb_position_table(mb_ctx* ctx, const uint32_t** match_of_pos, const uint32_t** comp_of_pos, uint64_t* n_pos);
+
 /* ---- many small problems in one pass (recursive anchoring: the aligners re-run the search inside every gap between
  * anchors — `recursive` flag src/mauveAligner.cpp:94,698; SetRecursive src/progressiveMauve.cpp:661-664) ------------------
  * mb_find_batch: n_problems independent searches, each over its own nseq sequences (seqs[i * nseq + g] / lens[i * nseq + g]:

@@ -635,6 +635,19 @@ public:
         }
         return false;
     }
+    /* repeatoire part 3 (src/repeatoire.cpp:1944-1966): the match position lookup table over the one sequence — entry p
+     * (1-based left end) = (match, component) that starts there, (NULL, 0) elsewhere — filled from the device-built index
+     * arrays; `ml` must be the list the last FindMatches produced (its order is repeatoire's seed_sort_list order). */
+    boolean GetMatchPositionLookupTable(const mems::MatchList& ml, std::vector<std::pair<mems::Match*, size_t> >& table) {
+        const uint32_t *mo = nullptr, *co = nullptr;
+        uint64_t n = 0;
+        int rc = ctx_ ? mb_position_table(ctx_, &mo, &co, &n) : MB_E_STATE;
+        if (rc != MB_OK) { report("GetMatchPositionLookupTable", rc); return false; }
+        table.assign(n, std::make_pair((mems::Match*)nullptr, (size_t)0));
+        for (uint64_t p = 0; p < n; ++p)
+            if (mo[p] != 0xFFFFFFFFu && mo[p] < ml.size()) table[p] = std::make_pair(ml[mo[p]], (size_t)co[p]);
+        return true;
+    }
 protected:
     mems::MatchList mlist;
 private:

@@ -46,7 +46,7 @@ EXPORTS = ["mb_ctx_create", "mb_ctx_destroy", "mb_set_stream", "mb_add_sequence"
            "mb_set_seed", "mb_find", "mb_find_device", "mb_fetch_result", "mb_get_sml", "mb_get_mers", "mb_get_stats", "mb_strerror",
            "mb_last_cuda_error", "mb_device_count", "mb_version",
            "mb_dist_extract", "mb_dist_extract_count", "mb_dist_partition", "mb_dist_p2p_recv_array",
-           "mb_dist_use_p2p_recv", "mb_ipc_export", "mb_ipc_import", "mb_ipc_close", "mb_dist_recv_buffer", "mb_dist_local", "mb_dist_rows_pack", "mb_dist_push", "mb_dist_resolve", "mb_dist_accept", "mb_dist_match_pack", "mb_dist_match_partition", "mb_dist_output", "mb_dist_stage_ms", "mb_find_multi", "mb_debug_radix", "mb_find_batch", "mb_set_segments"]
+           "mb_dist_use_p2p_recv", "mb_ipc_export", "mb_ipc_import", "mb_ipc_close", "mb_dist_recv_buffer", "mb_dist_local", "mb_dist_rows_pack", "mb_dist_push", "mb_dist_resolve", "mb_dist_accept", "mb_dist_match_pack", "mb_dist_match_partition", "mb_dist_output", "mb_dist_stage_ms", "mb_find_multi", "mb_debug_radix", "mb_find_batch", "mb_set_segments", "mb_position_table"]
 
 _lib = None
 
@@ -102,6 +102,7 @@ def lib():
     L.mb_debug_radix.argtypes = [vp, u64, i32, i32, i32, C.POINTER(C.c_float)]
     L.mb_find_batch.argtypes = [vp, C.POINTER(MbParams), C.c_uint32, C.c_uint32, C.POINTER(vp), pu64, C.POINTER(C.POINTER(MbBatchResult))]
     L.mb_set_segments.argtypes = [vp, C.c_uint32, pu64]
+    L.mb_position_table.argtypes = [vp, C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.POINTER(C.c_uint32)), pu64]
     _lib = L
     return L
 

@@ -93,9 +93,9 @@ int mb_ctx_destroy(mb_ctx* c) {
                     &c->bitmap, &c->bmrank, &c->cand_at, &c->cstate, &c->covered, &c->ghash2, &c->rep_cand, &c->s_h2, &c->reach, &c->xstate, &c->xrec, &c->x_lut, &c->x_counts, &c->x_hdr_s, &c->x_comp_s, &c->x_hdr_r, &c->x_comp_r, &c->x_m, &c->x_key, &c->x_item, &c->x_peers, &c->x_recv, &c->q_off, &c->q_pos, &c->q_gs, &c->q_el, &c->q_er, &c->q_perm, &c->q_state, &c->q_item, &c->x_acc_s, &c->x_acc_r, &c->minrank, &c->ext_l, &c->ext_r, &c->wl_a, &c->wl_b, &c->wl_c, &c->wl_long, &c->wd_a, &c->wd_b, &c->wd_c, &c->live_bits, &c->trace, &c->ghash, &c->slot_gp, &c->slot_hash, &c->link_bits, &c->chain_min, &c->rep_bits, &c->rep_rank, &c->s_hash, &c->s_cand, &c->rng_lo, &c->rng_hi, &c->flags,
                     &c->match_idx, &c->sort_kA, &c->sort_kB, &c->sort_vA, &c->sort_vB, &c->ncomp, &c->mers_tmp, &c->out_len, &c->out_off,
                     &c->out_seq, &c->out_start, &c->fam_th1, &c->fam_th2, &c->fam_tx, &c->fam_tend, &c->fam_sh1, &c->fam_sh2, &c->fam_sx, &c->fam_send,
-                    &c->fam_spmax, &c->fam_srun0, &c->fam_drop, &c->seg};
+                    &c->fam_spmax, &c->fam_srun0, &c->fam_drop, &c->seg, &c->pos_match, &c->pos_comp};
     for (DBuf* b : bufs) free_buf(*b);
-    void* hs[] = {c->h_len, c->h_off, c->h_seq, c->h_start, c->h_perseq, c->h_scal};
+    void* hs[] = {c->h_len, c->h_off, c->h_seq, c->h_start, c->h_perseq, c->h_scal, c->h_posm, c->h_posc};
     for (void* h : hs) if (h) cudaFreeHost(h);
     for (int i = 0; i < EV_COUNT; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (int i = 0; i < 4; ++i) if (c->ev_x[i]) cudaEventDestroy(c->ev_x[i]);
@@ -799,6 +799,28 @@ int mb_fetch_result(mb_ctx* c, const mb_result** out) {
     for (int i = 0; i < c->n_timed_passes; ++i) c->stats.ms_radix_kernels += ms(c->ev_r[2 * i], c->ev_r[2 * i + 1]);
     c->stats.radix_launches = c->n_timed_passes;
     *out = &c->res;
+    return MB_OK;
+}
+
+/* repeatoire's match position lookup table (src/repeatoire.cpp:1944-1966), built on the device from the last single-sequence
+ * result (MB_MODE_SEED_ENUM / MB_MODE_REPEAT): entry p (1-based left end; n_pos = sequence length + 1 entries) = index of the
+ * match and of its component that start at p, 0xFFFFFFFF where none does. */
+int mb_position_table(mb_ctx* c, const uint32_t** match_of_pos, const uint32_t** comp_of_pos, uint64_t* n_pos) {
+    if (!c || !match_of_pos || !comp_of_pos || !n_pos) return MB_E_ARG;
+    if (!c->have_result || c->seq_len.size() != 1 || (c->last_mode != MB_MODE_SEED_ENUM && c->last_mode != MB_MODE_REPEAT)) return MB_E_STATE;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const u64 np = c->seq_len[0] + 1;
+    TRY(c->reserve(c->pos_match, np * 4)); TRY(c->reserve(c->pos_comp, np * 4));
+    TRY(c->reserve_host(c->h_posm, c->h_posm_cap, np * 4)); TRY(c->reserve_host(c->h_posc, c->h_posc_cap, np * 4));
+    TRY(c->reserve(c->sort_kA, np * 8)); // scratch: (match + 1) << 32 | component per position
+    CUDA_TRY(c, cudaMemsetAsync(c->sort_kA.p, 0, np * 8, st));
+    launch_position_table(c->out_off.as<u64>(), c->out_start.as<i64>(), (u32)c->r_matches, c->sort_kA.as<u64>(), c->pos_match.as<u32>(), c->pos_comp.as<u32>(), np, st);
+    CHECK_LAUNCH(c);
+    CUDA_TRY(c, cudaMemcpyAsync(c->h_posm, c->pos_match.p, np * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaMemcpyAsync(c->h_posc, c->pos_comp.p, np * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaStreamSynchronize(st));
+    *match_of_pos = (const uint32_t*)c->h_posm; *comp_of_pos = (const uint32_t*)c->h_posc; *n_pos = np;
     return MB_OK;
 }
 

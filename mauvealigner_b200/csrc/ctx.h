@@ -65,6 +65,9 @@ struct mb_ctx {
     std::vector<i64> b_start;
     mb_batch_result bres{};
     std::vector<u8> b_concat;
+    DBuf pos_match, pos_comp;                 // mb_position_table
+    void* h_posm = nullptr; void* h_posc = nullptr;
+    size_t h_posm_cap = 0, h_posc_cap = 0;
     // persistent MemHash table across searches (mb_accumulate; kernels_family.cu)
     bool fam_on = false, fam_dirty = false, fam_pre = false;
     u32 fam_n = 0;

@@ -152,6 +152,7 @@ struct OutputArgs {
     u32* out_len; u32* out_seq; i64* out_start;
     int repeat;               // MB_MODE_REPEAT: ties of the first start are ordered as for MB_MODE_SEED_ENUM (multiplicity, signed starts, length)
 };
+void launch_position_table(const u64* out_off, const i64* out_start, u32 n_matches, u64* tab, u32* match_of, u32* comp_of, u64 n_pos, cudaStream_t st);
 void launch_uniq_flags(const OutputArgs& a, cudaStream_t st);
 void launch_uniq_keys(const OutputArgs& a, int sbits, cudaStream_t st);
 void launch_uniq_tiefix(const OutputArgs& a, const u64* skey, u64* sval, u32 L, u32 n_upper, cudaStream_t st);

@@ -128,6 +128,34 @@ __global__ void __launch_bounds__(256) k_uniq_gather(OutputArgs a, const u64* __
     }
 }
 
+// repeatoire's match position lookup table (/root/reference/src/repeatoire.cpp:1944-1966): for every position of the one
+// sequence, which match (index in the result order = ascending LeftEnd(0), the order of repeatoire's seed_sort_list,
+// :1920-1935) and which of its components starts there; 0xFFFFFFFF where none does.  Entry p = 1-based left end, entry 0 unused.
+__global__ void __launch_bounds__(256) k_position_table(const u64* __restrict__ out_off, const i64* __restrict__ out_start, u32 n_matches,
+                                                        unsigned long long* __restrict__ tab, u64 n_pos) {
+    const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_matches) return;
+    const u64 a = out_off[j], b = out_off[j + 1];
+    for (u64 k = a; k < b; ++k) {
+        const i64 s = out_start[k];
+        const u64 p = (u64)(s < 0 ? -s : s);
+        // components of two extended matches may share a left end: the later match of the list wins, as the last
+        // assignment of the reference's loop over its sorted component list does
+        if (p < n_pos) atomicMax(tab + p, ((unsigned long long)(j + 1) << 32) | (k - a));
+    }
+}
+__global__ void __launch_bounds__(256) k_position_split(const unsigned long long* __restrict__ tab, u32* __restrict__ match_of, u32* __restrict__ comp_of, u64 n_pos) {
+    const u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pos) return;
+    const unsigned long long v = tab[p];
+    match_of[p] = v ? (u32)(v >> 32) - 1 : 0xFFFFFFFFu;
+    comp_of[p] = v ? (u32)v : 0xFFFFFFFFu;
+}
+void launch_position_table(const u64* out_off, const i64* out_start, u32 n_matches, u64* tab, u32* match_of, u32* comp_of, u64 n_pos, cudaStream_t st) {
+    if (n_matches) k_position_table<<<div_up(n_matches, 256), 256, 0, st>>>(out_off, out_start, n_matches, reinterpret_cast<unsigned long long*>(tab), n_pos);
+    k_position_split<<<div_up(n_pos, 256), 256, 0, st>>>(reinterpret_cast<const unsigned long long*>(tab), match_of, comp_of, n_pos);
+}
+
 void launch_uniq_flags(const OutputArgs& a, cudaStream_t st) {
     if (a.n_items) k_uniq_flags<<<div_up(a.n_items, 256), 256, 0, st>>>(a);
 }

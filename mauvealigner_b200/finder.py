@@ -110,6 +110,13 @@ class Context:
         _check(self._h, L.lib().mb_find(self._h, C.byref(p), C.byref(out)))
         return self._wrap(out.contents, copy)
 
+    def position_table(self):
+        """mb_position_table: repeatoire's match position lookup table of the last single-sequence result
+        (src/repeatoire.cpp:1944-1966): (match_of_pos, comp_of_pos), entry p = 1-based left end, 0xFFFFFFFF = none."""
+        pm, pc, n = C.POINTER(C.c_uint32)(), C.POINTER(C.c_uint32)(), C.c_uint64(0)
+        _check(self._h, L.lib().mb_position_table(self._h, C.byref(pm), C.byref(pc), C.byref(n)))
+        return (np.ctypeslib.as_array(pm, shape=(n.value,)).copy(), np.ctypeslib.as_array(pc, shape=(n.value,)).copy())
+
     def find_batch(self, problems, mode=L.MODE_UNIQUE, min_multi=2, max_multi=1000, direct_only=False, nway_mask=0):
         """mb_find_batch: many small independent searches (recursive anchoring, src/mauveAligner.cpp:94,698) in ONE pass of
         the pipeline.  problems = list of lists of sequences (all lists of one length; an empty sequence = absent).

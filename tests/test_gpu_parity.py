@@ -214,6 +214,28 @@ def test_repeat_hash_vs_oracle(ctx, seed):
     assert [(m.Length(), [m.Start(i) for i in range(m.SeqCount())]) for m in ml] == [(ln, [st for _, st in comps]) for ln, comps in O.matches_as_list(want)]
 
 
+def test_position_lookup_table(ctx):
+    """mb_position_table against repeatoire's own three steps (src/repeatoire.cpp:1920-1966) applied to the oracle's list:
+    records sorted by LeftEnd(0), components sorted by left end, table[left end] = (record, component)"""
+    import mauvealigner_b200 as mb
+    rng = np.random.default_rng(99)
+    u = rand_seq(rng, 300)
+    s = rand_seq(rng, 2000) + u + rand_seq(rng, 500) + revcomp(u) + rand_seq(rng, 800) + mutate(rng, u, sub=0.02, indel=0) + "ACG" * 30
+    for mode, kw in ((mb.MODE_SEED_ENUM, dict(min_multi=2, max_multi=500)), (mb.MODE_REPEAT, dict(max_multi=255))):
+        got = run(ctx, [s], mb.get_seed(9, 0), mode, **kw)
+        want = O.find([s], mb.get_seed(9, 0), mode, **kw)
+        assert_same(got, want)
+        recs = sorted(((abs(comps[0][1]), j) for j, (_, comps) in enumerate(O.matches_as_list(want))))  # seed_sort_list
+        mplt = sorted((abs(st), order, k) for order, (_, j) in enumerate(recs) for k, (_, st) in enumerate(O.matches_as_list(want)[j][1]))
+        exp_m = np.full(len(s) + 1, 0xFFFFFFFF, dtype=np.uint32)
+        exp_c = np.full(len(s) + 1, 0xFFFFFFFF, dtype=np.uint32)
+        for left, order, k in mplt:
+            exp_m[left], exp_c[left] = order, k
+        mo, co = ctx.position_table()
+        assert np.array_equal(mo, exp_m) and np.array_equal(co, exp_c), (mode, np.flatnonzero(mo != exp_m)[:5], np.flatnonzero(co != exp_c)[:5])
+        assert (mo != 0xFFFFFFFF).sum() == want["n_comps"] or mode == mb.MODE_REPEAT
+
+
 def test_edge_cases(ctx):
     import mauvealigner_b200 as mb
     # sequences shorter than the seed, empty sequences
