@@ -73,7 +73,21 @@ static const int64 NO_MATCH = 0;
 static const int SOLID_SEED = MB_SOLID_SEED;
 static const int CODING_SEED = MB_CODING_SEED;
 
-inline int64 getSeed(int weight, int rank = 0) { return (int64)mb_get_seed(weight, rank); }
+/* getSeed(weight, rank): libMems' SeedMasks.h tables are not in the reference tree, so the patterns behind
+ * (weight, rank) and CODING_SEED are this library's own palindromic table (include/mauve_b200/seed_masks.h).  The same
+ * command line therefore searches with other patterns than stock Mauve and finds another — equally valid — match set, and
+ * .sslist files are not interchangeable.  Said once per process on stderr (MAUVE_B200_QUIET=1 silences it); every API
+ * also accepts a raw pattern for callers that hold the original tables. */
+inline void seed_table_notice() {
+    static bool said = false;
+    if (said) return;
+    said = true;
+    const char* q = getenv("MAUVE_B200_QUIET");
+    if (q && *q && *q != '0') return;
+    std::cerr << "mauve_b200: seed patterns come from this library's own table, not from libMems' SeedMasks.h "
+                 "(match sets differ from stock Mauve for the same --seed-weight; see INTEGRATION.md)\n";
+}
+inline int64 getSeed(int weight, int rank = 0) { seed_table_notice(); return (int64)mb_get_seed(weight, rank); }
 inline uint32 getSeedLength(int64 seed) { return (uint32)mb_seed_length((uint64_t)seed); }
 inline uint32 getDefaultSeedWeight(gnSeqI avg_len) { return (uint32)mb_default_seed_weight(avg_len); }
 
@@ -233,6 +247,7 @@ public:
      * mer lists themselves are built on the device inside FindMatches. mer_size 0 = default weight. */
     void CreateMemorySMLs(uint32 mer_size, std::ostream* log_stream, int seed_rank = 0) {
         if (mer_size == 0) mer_size = GetDefaultMerSize(seq_table);
+        seed_table_notice();
         uint64 seed = mb_get_seed((int)mer_size, seed_rank);
         if (!mb_seed_valid(seed)) throw genome::gnException("invalid seed weight / rank");
         for (SortedMerList* s : sml_table) delete s;

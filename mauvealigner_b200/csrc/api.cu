@@ -309,10 +309,13 @@ int mbi_setup_run(mb_ctx* c, MbiRun& r) {
     c->stats.record_bytes = fmt.wide ? 16 : 8;
     TRY(c->reserve(c->hist, 8 * 256 * 4));
     TRY(c->reserve(c->digit_base, 8 * 256 * 4));
-    TRY(c->reserve(c->lookback, (size_t)(div_up(n, radix_tile_size()) + 1) * 256 * 8));
+    // the scans and sorts of the later stages run over candidates, reps and matches: at most n / 2 of them, except for
+    // MB_MODE_PAIRWISE, where a bucket of u unique genomes yields u (u - 1) / 2 candidates (up to n (nseq - 1) / 2)
+    const u64 items = r.mode == MB_MODE_PAIRWISE ? std::max<u64>(n, (u64)n * (nseq - 1) / 2 + 2) : n;
+    TRY(c->reserve(c->lookback, (size_t)(div_up(items, radix_tile_size()) + 1) * 256 * 8));
     TRY(c->reserve(c->tickets, 256 * 4));
-    size_t status_words = (size_t)div_up(n, find_runs_tile()) + div_up(n, select_tile()) + 6 * (size_t)div_up(n, scan_tile()) +
-                          div_up(bases * std::min<u64>(nseq, 8) / 64 + 2, scan_tile()) + 2 * (size_t)div_up(n, chain_tile()) + 64;
+    size_t status_words = (size_t)div_up(n, find_runs_tile()) + div_up(n, select_tile()) + 6 * (size_t)div_up(items, scan_tile()) +
+                          div_up(bases * std::min<u64>(nseq, 8) / 64 + 2, scan_tile()) + 2 * (size_t)div_up(items, chain_tile()) + 64;
     TRY(c->reserve(c->status, status_words * 8));
     TRY(c->reserve(c->scalars, SC_COUNT * 8));
     TRY(c->reserve(c->per_seq, MB_MAX_SEQ * 8));
@@ -337,6 +340,7 @@ int mb_find_device(mb_ctx* c, const mb_params* prm) {
     if (mode == MB_MODE_PAIRWISE && c->seq_len.size() > 8) return MB_E_SEQCOUNT; // the reference uses it for <= 4 genomes
     if ((mode == MB_MODE_SEED_ENUM || mode == MB_MODE_REPEAT) && c->seq_len.size() > 1) return MB_E_SEQCOUNT;
     MbiRun run;
+    run.mode = mode;
     TRY(mbi_setup_run(c, run));
     cudaStream_t st = c->stream;
     const SeedDev& sd = c->sd;

@@ -21,19 +21,25 @@
 
 namespace {
 
+// Barrier of the rank threads that also makes the "has any rank failed" decision COLLECTIVE: the last arriver samples the
+// error word once, under the lock, and every rank leaves the barrier with that same value.  (Reading the word after the
+// barrier is a race: a fast rank can run its next step, fail and set the word before a slow rank has looked — the slow
+// rank then returns at barrier k while the fast ones wait at barrier k + 1 for ever.)  The sampled value of a generation
+// cannot be overwritten before every rank has read it: the next sample is taken when all ranks have arrived again.
 class HostBarrier {
 public:
     explicit HostBarrier(int n) : n_(n) {}
-    void wait() {
+    int wait(const std::atomic<int>& failed) {
         std::unique_lock<std::mutex> lk(m_);
         const unsigned gen = gen_;
-        if (++count_ == n_) { count_ = 0; ++gen_; cv_.notify_all(); }
+        if (++count_ == n_) { count_ = 0; decision_ = failed.load(); ++gen_; cv_.notify_all(); }
         else cv_.wait(lk, [&] { return gen_ != gen; });
+        return decision_;
     }
 private:
     std::mutex m_;
     std::condition_variable cv_;
-    int n_, count_ = 0;
+    int n_, count_ = 0, decision_ = MB_OK;
     unsigned gen_ = 0;
 };
 
@@ -66,7 +72,7 @@ int push_blocks(mb_ctx* c, const void* src, const uint64_t* counts, size_t unit_
 
 // every step of a rank: run it unless some rank has already failed, record the first error, always reach the barrier
 #define STEP(...) do { if (S.failed.load() == MB_OK) { int _rc = (__VA_ARGS__); if (_rc != MB_OK) { int ok = MB_OK; S.failed.compare_exchange_strong(ok, _rc); } } } while (0)
-#define MEET() do { S.bar.wait(); if (S.failed.load() != MB_OK) return; } while (0)
+#define MEET() do { if (S.bar.wait(S.failed) != MB_OK) return; } while (0)
 
 void rank_main(Shared& S, int r) {
     const int W = S.world;
@@ -171,7 +177,7 @@ void rank_main(Shared& S, int r) {
     // ---- stage 4
     STEP(mb_dist_output(c, n_match, n_mcomp));
     STEP(sync());
-    S.bar.wait();
+    S.bar.wait(S.failed);
 }
 
 } // namespace

@@ -149,7 +149,7 @@ struct mb_ctx {
 
 
 // helpers defined in api.cu
-struct MbiRun { std::vector<u32> tile_first; u32 n = 0, n_tiles = 0; u64 bases = 0, maxlen = 0; };
+struct MbiRun { std::vector<u32> tile_first; u32 n = 0, n_tiles = 0; u64 bases = 0, maxlen = 0; int mode = 0; };
 int mbi_setup_run(mb_ctx* c, MbiRun& r);
 int mbi_sort_records(mb_ctx* c, u64** kA, u64** kB, u64** vA, u64** vB, u32 n, int shift, int kbits, bool hist_ready, bool time_passes = false);
 int mbi_read_scalars(mb_ctx* c);

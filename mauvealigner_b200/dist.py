@@ -139,6 +139,16 @@ class TorchFabric:
         self.dist.all_gather(out, t, group=self.group)
         return torch.stack(out).tolist()
 
+    def bind_streams(self, ctxs):
+        """The NCCL exchanges and the barrier below are ordered on torch's CURRENT stream; the library stages must run
+        on that same stream, or a collective could read a send buffer before the pack kernel has finished (and a later
+        stage a receive buffer before NCCL has filled it).  find_unique calls this first."""
+        if self.device is None or torch.device(self.device).type != "cuda":
+            return  # host stand-ins (CPU tests over gloo) have no stream
+        cur = torch.cuda.current_stream(self.device).cuda_stream
+        for c in ctxs:
+            c.set_stream(cur)
+
     def barrier(self):
         # stream-ordered: completes on this rank only after every rank's earlier work on its stream (the peer stores
         # of its partition kernel) has completed
@@ -232,6 +242,8 @@ def find_unique(ctxs, fabric, device, nway_mask=0, p2p=None):
     ranks share the count matrix first and meet at a stream-ordered barrier afterwards), 0 = NCCL all-to-alls of
     local send buffers only."""
     W, R = fabric.world, fabric.local_ranks
+    if hasattr(fabric, "bind_streams"):
+        fabric.bind_streams(ctxs)  # library stages and NCCL exchanges on ONE stream (torch's current one)
     if p2p is None:
         p2p = p2p_default()
     p2p = int(p2p)
