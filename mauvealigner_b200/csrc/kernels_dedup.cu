@@ -49,12 +49,15 @@ __device__ __forceinline__ bool same_group(const DedupArgs& a, u32 j, u32 e) {
     return true;
 }
 
-// Two candidates are taken to be of the same D16 group when both of their independent 64-bit group hashes agree
-// (120 bits compared: a wrong drop needs a simultaneous collision of both); -DMB_VERIFY_GROUPS adds the exact
-// component-wise comparison on top.
+// Every decision that DROPS a candidate (a chain link, a containment) compares the two group hashes first — the fast
+// reject — and then the groups themselves, component by component (same_group): bit-exact results do not rest on a hash.
+// Measured cost of the exact comparison: C5 33.3 -> 35.7 ms (+ 7 %; tools/bench_variants.sh with -DMB_HASH_ONLY).
+// Hash equality alone (two independent 64-bit hashes, 120 bits compared) decides only where the component lists are not
+// at hand: on the owner side of the multi-GPU path (a.rows: the rows carry the hashes, the lists stay at their source)
+// and in builds with -DMB_HASH_ONLY.
 __device__ __forceinline__ bool groups_equal(const DedupArgs& a, u32 c1, u32 c2) {
-#ifdef MB_VERIFY_GROUPS
-    return same_group(a, c1, c2);
+#ifndef MB_HASH_ONLY
+    return a.rows ? true : same_group(a, c1, c2);
 #else
     (void)a; (void)c1; (void)c2;
     return true;
@@ -159,8 +162,8 @@ __global__ void __launch_bounds__(CH_NT) k_chain(DedupArgs a, u64* status, u32* 
             hs[k + 1] = r.x;
             v[k] = (u32)r.y;
             bool link = valid && s > 0 && (r.x & 1) && (hs[k] & HASH_MASK) == (r.x & HASH_MASK);
-#ifdef MB_VERIFY_LINKS
-            if (link) link = same_group(a, (u32)a.slot_rec[2 * (size_t)(s - 1)].y, v[k]);
+#ifndef MB_HASH_ONLY
+            if (link && !a.rows) link = same_group(a, (u32)a.slot_rec[2 * (size_t)(s - 1)].y, v[k]);
 #endif
             f[k] = !link;
             linkbits |= (link ? 1u : 0u) << k;
@@ -611,8 +614,31 @@ struct XLane {
     u32 b, el, er, room_l, room_r;
 };
 
+// The genome table arrives as a kernel argument, i.e. in the constant bank: gt.word_base[g] with a per-lane genome g is an
+// indexed constant load that replays once per distinct g of the warp (a rep's pairs sit on ~20 lanes with ~20 genomes; the
+// ncu source page had a quarter of the kernel's stall samples behind these loads).  The hot loop reads a shared-memory copy.
+struct GShared { u64 wbase[MB_MAX_SEQ]; u32 len[MB_MAX_SEQ]; };
+__device__ __forceinline__ void gshared_fill(GShared& gs, const GenomeTable& gt) {
+    for (u32 g = threadIdx.x; g < MB_MAX_SEQ; g += blockDim.x) { gs.wbase[g] = gt.word_base[g]; gs.len[g] = gt.len[g]; }
+    __syncthreads();
+}
+__device__ __forceinline__ void oriented_bases64_s(const u64* __restrict__ packed, const GShared& gs, u32 L, u32 g, u32 pos, bool rev, i64 i0, u64& a, u64& b) {
+    i64 q = (i64)gs.wbase[g] * 32 + (i64)pos + (rev ? (i64)L - 64 - i0 : i0);
+    const u64* w = packed + ((u64)q >> 5);
+    int sh = (int)(q & 31) * 2;
+    const u64 pol = l2_keep_policy();
+    u64 w0 = ld_keep(w, pol), w1 = ld_keep(w + 1, pol), w2 = ld_keep(w + 2, pol);
+    u64 fa = shl128_hi(w0, w1, sh), fb = shl128_hi(w1, w2, sh);
+    if (rev) { a = rc_word(fb); b = rc_word(fa); }
+    else { a = fa; b = fb; }
+}
+__device__ __forceinline__ void seg_range_s(const GenomeTable& gt, const GShared& gs, u32 g, u32 p, u32& lo, u32& hi) {
+    if (!gt.n_seg) { lo = 0; hi = gs.len[g]; }
+    else seg_range(gt, g, p, lo, hi);
+}
+
 template <bool FIRST> // FIRST: round 0 also reduces the rooms of the components
-__device__ __forceinline__ void extend_rounds(const DedupArgs& a, const GenomeTable& gt, const SeedDev& sd, XLane& x, int max_rounds,
+__device__ __forceinline__ void extend_rounds(const DedupArgs& a, const GenomeTable& gt, const GShared& gsh, const SeedDev& sd, XLane& x, int max_rounds,
                                               u32 (*sMap)[4], u32 (*sRoom)[2]) {
     const int lane = threadIdx.x & 31;
     const u32 L = sd.L;
@@ -620,7 +646,7 @@ __device__ __forceinline__ void extend_rounds(const DedupArgs& a, const GenomeTa
     if (FIRST) {
         // component 0 is forward
         u32 lo0 = 0, hi0 = 0;
-        if (x.st != ST_DONE) seg_range(gt, x.g0, x.p0, lo0, hi0);
+        if (x.st != ST_DONE) seg_range_s(gt, gsh, x.g0, x.p0, lo0, hi0);
         sRoom[lane][0] = x.st != ST_DONE ? x.p0 - lo0 : INF32;
         sRoom[lane][1] = x.st != ST_DONE ? hi0 - L - x.p0 : INF32;
     }
@@ -637,7 +663,7 @@ __device__ __forceinline__ void extend_rounds(const DedupArgs& a, const GenomeTa
         }
         const u32 start = incl - np, T = __shfl_sync(0xFFFFFFFFu, incl, 31);
         u64 a0 = 0, b0 = 0;
-        if (want) oriented_bases64(a.packed, gt, L, x.g0, x.p0, false, o_lo, a0, b0);
+        if (want) oriented_bases64_s(a.packed, gsh, L, x.g0, x.p0, false, o_lo, a0, b0);
         sMap[lane][0] = 0; sMap[lane][1] = 0; sMap[lane][2] = 0; sMap[lane][3] = 0;
         __syncwarp();
         for (u32 base = 0; base < T; base += 32) {
@@ -657,7 +683,7 @@ __device__ __forceinline__ void extend_rounds(const DedupArgs& a, const GenomeTa
                 u8 gs = a.comp_gs[offj + k];
                 u32 pk = a.comp_pos[offj + k];
                 u64 A, B;
-                oriented_bases64(a.packed, gt, L, gs & 0x7F, pk, gs & 0x80, oj, A, B);
+                oriented_bases64_s(a.packed, gsh, L, gs & 0x7F, pk, gs & 0x80, oj, A, B);
                 u64 xa = spread_nz(A ^ a0j), xb = spread_nz(B ^ b0j);
                 if (xa >> 32) atomicOr(&sMap[j][0], (u32)(xa >> 32));
                 if ((u32)xa) atomicOr(&sMap[j][1], (u32)xa);
@@ -665,7 +691,7 @@ __device__ __forceinline__ void extend_rounds(const DedupArgs& a, const GenomeTa
                 if ((u32)xb) atomicOr(&sMap[j][3], (u32)xb);
                 if (FIRST && round == 0) {
                     u32 lo, hi;
-                    seg_range(gt, gs & 0x7F, pk, lo, hi);
+                    seg_range_s(gt, gsh, gs & 0x7F, pk, lo, hi);
                     u32 lroom = pk - lo, rroom = hi - L - pk;
                     bool rev = gs & 0x80;
                     atomicMin(&sRoom[j][0], rev ? rroom : lroom);
@@ -727,6 +753,8 @@ __device__ __forceinline__ void extend_finish(const DedupArgs& a, const GenomeTa
 __global__ void __launch_bounds__(DD_NT) k_extend(DedupArgs a, GenomeTable gt, SeedDev sd, u32* out_list, u32* out_count) {
     __shared__ u32 sMap[DD_NT / 32][32][4];
     __shared__ u32 sRoom[DD_NT / 32][32][2];
+    __shared__ GShared gsh;
+    gshared_fill(gsh, gt);
     const int warp = threadIdx.x >> 5;
     const u32 i = blockIdx.x * DD_NT + threadIdx.x;
     const bool valid = i < a.n_rep;
@@ -741,7 +769,7 @@ __global__ void __launch_bounds__(DD_NT) k_extend(DedupArgs a, GenomeTable gt, S
         wl_push(a.wl_long, a.ctr + 6, valid, i);
         return;
     }
-    extend_rounds<true>(a, gt, sd, x, DD_EXT_FIRST_ROUNDS, sMap[warp], sRoom[warp]);
+    extend_rounds<true>(a, gt, gsh, sd, x, DD_EXT_FIRST_ROUNDS, sMap[warp], sRoom[warp]);
     extend_finish(a, gt, valid, i, x, out_list, out_count, false);
 }
 
@@ -749,6 +777,8 @@ __global__ void __launch_bounds__(DD_NT) k_extend(DedupArgs a, GenomeTable gt, S
 __global__ void __launch_bounds__(DD_NT) k_extend_more(DedupArgs a, GenomeTable gt, SeedDev sd, const u32* in_list, const u32* in_count, u32* out_list,
                                                        u32* out_count, int last) {
     __shared__ u32 sMap[DD_NT / 32][32][4];
+    __shared__ GShared gsh;
+    gshared_fill(gsh, gt);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const u32 n = *in_count;
     const u32 gwarp = (blockIdx.x * DD_NT + threadIdx.x) >> 5, nwarps = (gridDim.x * DD_NT) >> 5;
@@ -764,7 +794,7 @@ __global__ void __launch_bounds__(DD_NT) k_extend_more(DedupArgs a, GenomeTable 
             x.st = (int)(s.x & 3u); x.rj = (s.x & 4u) != 0; x.b = s.y; x.room_l = s.z; x.room_r = s.w;
             x.el = a.ext_l[x.c]; x.er = a.ext_r[x.c];
         }
-        extend_rounds<false>(a, gt, sd, x, DD_EXT_MORE_ROUNDS, sMap[warp], nullptr);
+        extend_rounds<false>(a, gt, gsh, sd, x, DD_EXT_MORE_ROUNDS, sMap[warp], nullptr);
         extend_finish(a, gt, valid, i, x, out_list, out_count, last != 0);
     }
 }
