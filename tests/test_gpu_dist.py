@@ -90,3 +90,46 @@ def test_find_multi_cpp_driver(world):
     want = O.find(seqs, pattern, O.MODE_UNIQUE)
     assert_same(got, want, f"find_multi world {world}")
     assert_same(again, want, f"find_multi world {world}, second run")
+
+
+def test_find_multi_on_distinct_devices():
+    """mb_find_multi with one context per PHYSICAL GPU (NVLink peer stores and copy-engine pushes between real devices);
+    needs at least two GPUs on the box."""
+    import mauvealigner_b200 as mb
+    ndev = mb.lib().mb_device_count()
+    if ndev < 2:
+        pytest.skip("one GPU on this box")
+    world = min(ndev, 4)
+    seqs = mb.synth_genomes(5, 40)
+    pattern = mb.get_seed(15, mb.CODING_SEED)
+    ctxs = [mb.Context(r) for r in range(world)]
+    try:
+        for c in ctxs:
+            for s in seqs:
+                c.add_sequence(s)
+            c.set_seed(pattern)
+        got = mb.find_multi(ctxs)
+        want = ctxs[0].find(mb.MODE_UNIQUE)
+    finally:
+        for c in ctxs:
+            c.close()
+    assert_same(got, want, f"find_multi on {world} devices")
+    assert want["n_matches"] > 1000
+
+
+def test_torchrun_nccl_path_on_two_gpus():
+    """The one-process-per-GPU path of bench.py (torchrun + NCCL + CUDA IPC peer stores) on two real GPUs, bit for bit
+    against the single-GPU path (tools/dist_check.py); needs at least two GPUs on the box."""
+    import os
+    import subprocess
+    import sys
+    import mauvealigner_b200 as mb
+    if mb.lib().mb_device_count() < 2:
+        pytest.skip("one GPU on this box")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p2p in ("1", "0"):
+        out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                              "--master-port", "29533", os.path.join(root, "tools", "dist_check.py"), "5", "20"],
+                             capture_output=True, text=True, timeout=600, env=dict(os.environ, MB_DIST_P2P=p2p))
+        assert out.returncode == 0, out.stderr[-2000:]
+        assert "OK bit-exact vs single-GPU path" in out.stdout, out.stdout[-2000:]
