@@ -617,20 +617,22 @@ struct XLane {
 // The genome table arrives as a kernel argument, i.e. in the constant bank: gt.word_base[g] with a per-lane genome g is an
 // indexed constant load that replays once per distinct g of the warp (a rep's pairs sit on ~20 lanes with ~20 genomes; the
 // ncu source page had a quarter of the kernel's stall samples behind these loads).  The hot loop reads a shared-memory copy.
-struct GShared { u64 wbase[MB_MAX_SEQ]; u32 len[MB_MAX_SEQ]; };
+struct GShared { u32 wbase[MB_MAX_SEQ]; u32 len[MB_MAX_SEQ]; }; // (packed words of all genomes < 2^32: at most 2^31 bases)
 __device__ __forceinline__ void gshared_fill(GShared& gs, const GenomeTable& gt) {
-    for (u32 g = threadIdx.x; g < MB_MAX_SEQ; g += blockDim.x) { gs.wbase[g] = gt.word_base[g]; gs.len[g] = gt.len[g]; }
+    for (u32 g = threadIdx.x; g < MB_MAX_SEQ; g += blockDim.x) { gs.wbase[g] = (u32)gt.word_base[g]; gs.len[g] = gt.len[g]; }
     __syncthreads();
 }
-__device__ __forceinline__ void oriented_bases64_s(const u64* __restrict__ packed, const GShared& gs, u32 L, u32 g, u32 pos, bool rev, i64 i0, u64& a, u64& b) {
-    i64 q = (i64)gs.wbase[g] * 32 + (i64)pos + (rev ? (i64)L - 64 - i0 : i0);
-    const u64* w = packed + ((u64)q >> 5);
-    int sh = (int)(q & 31) * 2;
-    const u64 pol = l2_keep_policy();
+// 64 oriented bases of component (g, pos) at match offset i0, as oriented_bases64 — with 32-bit index arithmetic (the
+// offset may be negative: every genome is preceded by padding words), the L2 policy created once by the caller, and the
+// reverse complement only computed when `any_rev` (warp-uniform: some lane of the warp holds a reverse component)
+__device__ __forceinline__ void oriented_bases64_s(const u64* __restrict__ packed, const GShared& gs, u32 L, u32 g, u32 pos, bool rev, int i0, u64 pol,
+                                                   bool any_rev, u64& a, u64& b) {
+    const int t = (int)pos + (rev ? (int)L - 64 - i0 : i0);
+    const u64* w = packed + (gs.wbase[g] + (u32)(t >> 5));
+    const int sh = (t & 31) * 2;
     u64 w0 = ld_keep(w, pol), w1 = ld_keep(w + 1, pol), w2 = ld_keep(w + 2, pol);
-    u64 fa = shl128_hi(w0, w1, sh), fb = shl128_hi(w1, w2, sh);
-    if (rev) { a = rc_word(fb); b = rc_word(fa); }
-    else { a = fa; b = fb; }
+    a = shl128_hi(w0, w1, sh); b = shl128_hi(w1, w2, sh);
+    if (any_rev && rev) { const u64 fa = a; a = rc_word(b); b = rc_word(fa); }
 }
 __device__ __forceinline__ void seg_range_s(const GenomeTable& gt, const GShared& gs, u32 g, u32 p, u32& lo, u32& hi) {
     if (!gt.n_seg) { lo = 0; hi = gs.len[g]; }
@@ -639,9 +641,10 @@ __device__ __forceinline__ void seg_range_s(const GenomeTable& gt, const GShared
 
 template <bool FIRST> // FIRST: round 0 also reduces the rooms of the components
 __device__ __forceinline__ void extend_rounds(const DedupArgs& a, const GenomeTable& gt, const GShared& gsh, const SeedDev& sd, XLane& x, int max_rounds,
-                                              u32 (*sMap)[4], u32 (*sRoom)[2]) {
+                                              u32 (*sMap)[4], u32 (*sRoom)[2], ulonglong2* sRepA, uint2* sRepB) {
     const int lane = threadIdx.x & 31;
     const u32 L = sd.L;
+    const u64 pol = l2_keep_policy();
     const u32 per_chunk = (3 * L <= 65) ? 2 : 1;
     if (FIRST) {
         // component 0 is forward
@@ -663,8 +666,11 @@ __device__ __forceinline__ void extend_rounds(const DedupArgs& a, const GenomeTa
         }
         const u32 start = incl - np, T = __shfl_sync(0xFFFFFFFFu, incl, 31);
         u64 a0 = 0, b0 = 0;
-        if (want) oriented_bases64_s(a.packed, gsh, L, x.g0, x.p0, false, o_lo, a0, b0);
+        if (want) oriented_bases64_s(a.packed, gsh, L, x.g0, x.p0, false, o_lo, pol, false, a0, b0);
         sMap[lane][0] = 0; sMap[lane][1] = 0; sMap[lane][2] = 0; sMap[lane][3] = 0;
+        // what the lanes that work on a rep's pairs need about it: one 16-byte and one 8-byte shared load instead of six shuffles
+        sRepA[lane] = make_ulonglong2(a0, b0);
+        sRepB[lane] = make_uint2(x.off, (u32)o_lo);
         __syncwarp();
         for (u32 base = 0; base < T; base += 32) {
             const u32 p = base + lane;
@@ -676,15 +682,17 @@ __device__ __forceinline__ void extend_rounds(const DedupArgs& a, const GenomeTa
                 if (j + step < 32 && sv <= p) j += step;
             }
             const u32 k = p - __shfl_sync(0xFFFFFFFFu, start, j) + 1;
-            const u32 offj = __shfl_sync(0xFFFFFFFFu, x.off, j);
-            const int oj = __shfl_sync(0xFFFFFFFFu, o_lo, j);
-            const u64 a0j = __shfl_sync(0xFFFFFFFFu, a0, j), b0j = __shfl_sync(0xFFFFFFFFu, b0, j);
+            const uint2 rb = sRepB[j];
+            const u32 offj = rb.x;
+            const int oj = (int)rb.y;
+            u32 gs = 0, pk = 0;
+            if (act) { gs = a.comp_gs[offj + k]; pk = a.comp_pos[offj + k]; }
+            const bool any_rev = __any_sync(0xFFFFFFFFu, (gs & 0x80u) != 0);
             if (act) {
-                u8 gs = a.comp_gs[offj + k];
-                u32 pk = a.comp_pos[offj + k];
+                const ulonglong2 ra = sRepA[j];
                 u64 A, B;
-                oriented_bases64_s(a.packed, gsh, L, gs & 0x7F, pk, gs & 0x80, oj, A, B);
-                u64 xa = spread_nz(A ^ a0j), xb = spread_nz(B ^ b0j);
+                oriented_bases64_s(a.packed, gsh, L, gs & 0x7F, pk, gs & 0x80, oj, pol, any_rev, A, B);
+                u64 xa = spread_nz(A ^ ra.x), xb = spread_nz(B ^ ra.y);
                 if (xa >> 32) atomicOr(&sMap[j][0], (u32)(xa >> 32));
                 if ((u32)xa) atomicOr(&sMap[j][1], (u32)xa);
                 if (xb >> 32) atomicOr(&sMap[j][2], (u32)(xb >> 32));
@@ -753,6 +761,8 @@ __device__ __forceinline__ void extend_finish(const DedupArgs& a, const GenomeTa
 __global__ void __launch_bounds__(DD_NT) k_extend(DedupArgs a, GenomeTable gt, SeedDev sd, u32* out_list, u32* out_count) {
     __shared__ u32 sMap[DD_NT / 32][32][4];
     __shared__ u32 sRoom[DD_NT / 32][32][2];
+    __shared__ ulonglong2 sRepA[DD_NT / 32][32];
+    __shared__ uint2 sRepB[DD_NT / 32][32];
     __shared__ GShared gsh;
     gshared_fill(gsh, gt);
     const int warp = threadIdx.x >> 5;
@@ -769,7 +779,7 @@ __global__ void __launch_bounds__(DD_NT) k_extend(DedupArgs a, GenomeTable gt, S
         wl_push(a.wl_long, a.ctr + 6, valid, i);
         return;
     }
-    extend_rounds<true>(a, gt, gsh, sd, x, DD_EXT_FIRST_ROUNDS, sMap[warp], sRoom[warp]);
+    extend_rounds<true>(a, gt, gsh, sd, x, DD_EXT_FIRST_ROUNDS, sMap[warp], sRoom[warp], sRepA[warp], sRepB[warp]);
     extend_finish(a, gt, valid, i, x, out_list, out_count, false);
 }
 
@@ -777,6 +787,8 @@ __global__ void __launch_bounds__(DD_NT) k_extend(DedupArgs a, GenomeTable gt, S
 __global__ void __launch_bounds__(DD_NT) k_extend_more(DedupArgs a, GenomeTable gt, SeedDev sd, const u32* in_list, const u32* in_count, u32* out_list,
                                                        u32* out_count, int last) {
     __shared__ u32 sMap[DD_NT / 32][32][4];
+    __shared__ ulonglong2 sRepA[DD_NT / 32][32];
+    __shared__ uint2 sRepB[DD_NT / 32][32];
     __shared__ GShared gsh;
     gshared_fill(gsh, gt);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -794,7 +806,7 @@ __global__ void __launch_bounds__(DD_NT) k_extend_more(DedupArgs a, GenomeTable 
             x.st = (int)(s.x & 3u); x.rj = (s.x & 4u) != 0; x.b = s.y; x.room_l = s.z; x.room_r = s.w;
             x.el = a.ext_l[x.c]; x.er = a.ext_r[x.c];
         }
-        extend_rounds<false>(a, gt, gsh, sd, x, DD_EXT_MORE_ROUNDS, sMap[warp], nullptr);
+        extend_rounds<false>(a, gt, gsh, sd, x, DD_EXT_MORE_ROUNDS, sMap[warp], nullptr, sRepA[warp], sRepB[warp]);
         extend_finish(a, gt, valid, i, x, out_list, out_count, last != 0);
     }
 }
