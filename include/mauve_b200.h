@@ -127,6 +127,23 @@ int mb_accumulate(mb_ctx* ctx, int on);
 int mb_find_device(mb_ctx* ctx, const mb_params* params);
 /* Device -> pinned host copy of the last mb_find_device result (synchronises the stream). */
 int mb_fetch_result(mb_ctx* ctx, const mb_result** out);
+/* The same result in the compact layout the device keeps it in: one byte per component for the sequence index (at most
+ * 64 sequences) and a 4-byte signed start (every sequence is shorter than 2^31 bases) — 5 instead of 12 bytes per
+ * component over PCIe (C5: 1.3 instead of 3.0 GB).  mems_compat.h builds its Match objects from this form.  The two
+ * result forms share the context's pinned buffers: a result is valid until the next fetch / search on the context. */
+typedef struct mb_result_compact {
+    uint64_t n_matches;
+    uint64_t n_comps;
+    const uint32_t* length;          /* [n_matches]      */
+    const uint64_t* comp_off;        /* [n_matches + 1]  */
+    const uint8_t* comp_seq8;        /* [n_comps]        */
+    const int32_t* comp_start32;     /* [n_comps] signed, 1-based; < 0 = reverse strand */
+    uint64_t unique_mers;
+    const uint64_t* unique_mers_per_seq;
+    uint32_t nseq;
+} mb_result_compact;
+int mb_fetch_result_compact(mb_ctx* ctx, const mb_result_compact** out);
+int mb_find_compact(mb_ctx* ctx, const mb_params* params, const mb_result_compact** out);
 
 /* repeatoire's match position lookup table (src/repeatoire.cpp:1944-1966: every component of every seed match entered
  * at its left end into a table over the sequence), built on the device from the last single-sequence result

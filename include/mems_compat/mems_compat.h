@@ -466,12 +466,13 @@ protected:
     void report(const char* what, int rc) const {
         genome::ErrorMsg(std::string(what) + ": " + mb_strerror(rc) + (ctx_ ? std::string(" ") + mb_last_cuda_error(ctx_) : "") + "\n");
     }
-    void append(const mb_result* r, MatchList& out, bool dense) const {
+    /* (the compact result form: 5 bytes per component over PCIe instead of 12) */
+    void append(const mb_result_compact* r, MatchList& out, bool dense) const {
         for (uint64_t i = 0; i < r->n_matches; ++i) {
             uint64_t a = r->comp_off[i], b = r->comp_off[i + 1];
             Match* m = new Match(dense ? seq_count : (uint)(b - a));
             m->SetLength(r->length[i]);
-            for (uint64_t k = a; k < b; ++k) m->SetStart(dense ? r->comp_seq[k] : (uint)(k - a), r->comp_start[k]);
+            for (uint64_t k = a; k < b; ++k) m->SetStart(dense ? r->comp_seq8[k] : (uint)(k - a), r->comp_start32[k]);
             out.push_back(m);
         }
     }
@@ -488,8 +489,8 @@ protected:
             if (rc != MB_OK) { report("FindMatches (multi-GPU)", rc); return false; }
             uint64_t total = 0;
             for (mb_ctx* c : all) {
-                const mb_result* r = nullptr;
-                rc = mb_fetch_result(c, &r);
+                const mb_result_compact* r = nullptr;
+                rc = mb_fetch_result_compact(c, &r);
                 if (rc != MB_OK) { report("mb_fetch_result", rc); return false; }
                 append(r, out, dense);
                 total += r->n_matches;
@@ -497,8 +498,8 @@ protected:
             if (log_) *log_ << total << " matches\n";
             return true;
         }
-        const mb_result* r = nullptr;
-        if (rc == MB_OK) rc = mb_find(ctx_, &p, &r);
+        const mb_result_compact* r = nullptr;
+        if (rc == MB_OK) rc = mb_find_compact(ctx_, &p, &r);
         if (rc != MB_OK) { report("FindMatches", rc); return false; }
         if (log_) *log_ << r->n_matches << " matches\n";
         append(r, out, dense);

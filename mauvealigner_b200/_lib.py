@@ -27,6 +27,12 @@ class MbResult(C.Structure):
                 ("unique_mers", C.c_uint64), ("unique_mers_per_seq", C.POINTER(C.c_uint64)), ("nseq", C.c_uint32)]
 
 
+class MbResultCompact(C.Structure):
+    _fields_ = [("n_matches", C.c_uint64), ("n_comps", C.c_uint64), ("length", C.POINTER(C.c_uint32)),
+                ("comp_off", C.POINTER(C.c_uint64)), ("comp_seq", C.POINTER(C.c_uint8)), ("comp_start", C.POINTER(C.c_int32)),
+                ("unique_mers", C.c_uint64), ("unique_mers_per_seq", C.POINTER(C.c_uint64)), ("nseq", C.c_uint32)]
+
+
 class MbBatchResult(C.Structure):
     _fields_ = [("n_problems", C.c_uint64), ("n_matches", C.c_uint64), ("n_comps", C.c_uint64), ("match_off", C.POINTER(C.c_uint64)),
                 ("length", C.POINTER(C.c_uint32)), ("comp_off", C.POINTER(C.c_uint64)), ("comp_seq", C.POINTER(C.c_uint32)),
@@ -46,7 +52,7 @@ EXPORTS = ["mb_ctx_create", "mb_ctx_destroy", "mb_set_stream", "mb_add_sequence"
            "mb_set_seed", "mb_find", "mb_find_device", "mb_fetch_result", "mb_get_sml", "mb_get_mers", "mb_get_stats", "mb_strerror",
            "mb_last_cuda_error", "mb_device_count", "mb_version",
            "mb_dist_extract", "mb_dist_extract_count", "mb_dist_partition", "mb_dist_p2p_recv_array",
-           "mb_dist_use_p2p_recv", "mb_ipc_export", "mb_ipc_import", "mb_ipc_close", "mb_dist_recv_buffer", "mb_dist_local", "mb_dist_rows_pack", "mb_dist_push", "mb_dist_resolve", "mb_dist_accept", "mb_dist_match_pack", "mb_dist_match_partition", "mb_dist_output", "mb_dist_stage_ms", "mb_find_multi", "mb_debug_radix", "mb_find_batch", "mb_set_segments", "mb_position_table"]
+           "mb_dist_use_p2p_recv", "mb_ipc_export", "mb_ipc_import", "mb_ipc_close", "mb_dist_recv_buffer", "mb_dist_local", "mb_dist_rows_pack", "mb_dist_push", "mb_dist_resolve", "mb_dist_accept", "mb_dist_match_pack", "mb_dist_match_partition", "mb_dist_output", "mb_dist_stage_ms", "mb_find_multi", "mb_debug_radix", "mb_find_batch", "mb_set_segments", "mb_position_table", "mb_fetch_result_compact", "mb_find_compact"]
 
 _lib = None
 
@@ -71,6 +77,8 @@ def lib():
     L.mb_find.argtypes = [vp, C.POINTER(MbParams), C.POINTER(C.POINTER(MbResult))]
     L.mb_find_device.argtypes = [vp, C.POINTER(MbParams)]
     L.mb_fetch_result.argtypes = [vp, C.POINTER(C.POINTER(MbResult))]
+    L.mb_fetch_result_compact.argtypes = [vp, C.POINTER(C.POINTER(MbResultCompact))]
+    L.mb_find_compact.argtypes = [vp, C.POINTER(MbParams), C.POINTER(C.POINTER(MbResultCompact))]
     L.mb_get_sml.argtypes = [vp, i32, vp, u64, C.POINTER(u64)]
     L.mb_get_mers.argtypes = [vp, i32, vp, u64, C.POINTER(u64)]
     L.mb_get_stats.argtypes = [vp, C.POINTER(MbStats)]

@@ -93,7 +93,7 @@ int mb_ctx_destroy(mb_ctx* c) {
                     &c->bitmap, &c->bmrank, &c->cand_at, &c->cstate, &c->covered, &c->ghash2, &c->rep_cand, &c->s_h2, &c->reach, &c->xstate, &c->xrec, &c->x_lut, &c->x_counts, &c->x_hdr_s, &c->x_comp_s, &c->x_hdr_r, &c->x_comp_r, &c->x_m, &c->x_key, &c->x_item, &c->x_peers, &c->x_recv, &c->q_off, &c->q_pos, &c->q_gs, &c->q_el, &c->q_er, &c->q_perm, &c->q_state, &c->q_item, &c->x_acc_s, &c->x_acc_r, &c->minrank, &c->ext_l, &c->ext_r, &c->wl_a, &c->wl_b, &c->wl_c, &c->wl_long, &c->wd_a, &c->wd_b, &c->wd_c, &c->live_bits, &c->trace, &c->ghash, &c->slot_gp, &c->slot_hash, &c->link_bits, &c->chain_min, &c->rep_bits, &c->rep_rank, &c->s_hash, &c->s_cand, &c->rng_lo, &c->rng_hi, &c->flags,
                     &c->match_idx, &c->sort_kA, &c->sort_kB, &c->sort_vA, &c->sort_vB, &c->ncomp, &c->mers_tmp, &c->out_len, &c->out_off,
                     &c->out_seq, &c->out_start, &c->fam_th1, &c->fam_th2, &c->fam_tx, &c->fam_tend, &c->fam_sh1, &c->fam_sh2, &c->fam_sx, &c->fam_send,
-                    &c->fam_spmax, &c->fam_srun0, &c->fam_drop, &c->seg, &c->pos_match, &c->pos_comp};
+                    &c->fam_spmax, &c->fam_srun0, &c->fam_drop, &c->seg, &c->pos_match, &c->pos_comp, &c->wide_seq, &c->wide_start};
     for (DBuf* b : bufs) free_buf(*b);
     void* hs[] = {c->h_len, c->h_off, c->h_seq, c->h_start, c->h_perseq, c->h_scal, c->h_posm, c->h_posc};
     for (void* h : hs) if (h) cudaFreeHost(h);
@@ -436,8 +436,8 @@ int mb_find_device(mb_ctx* c, const mb_params* prm) {
         TRY(c->reserve(c->ncomp, (size_t)(n_cand + 8) * 4));
         TRY(c->reserve(c->out_len, (size_t)(n_cand + 8) * 4));
         TRY(c->reserve(c->out_off, (size_t)(n_cand + 8) * 8));
-        TRY(c->reserve(c->out_seq, (size_t)(n_ccomp + 8) * 4));
-        TRY(c->reserve(c->out_start, (size_t)(n_ccomp + 8) * 8));
+        TRY(c->reserve(c->out_seq, (size_t)(n_ccomp + 8)));
+        TRY(c->reserve(c->out_start, (size_t)(n_ccomp + 8) * 4));
         if (n_cand) {
             EmitEnumArgs ea{};
             ea.keys = kA; ea.vals = vA; ea.run_start = run_start; ea.cand_run = c->cand_run.as<u32>(); ea.cand_off = c->cand_off.as<u32>();
@@ -458,7 +458,7 @@ int mb_find_device(mb_ctx* c, const mb_params* prm) {
                             scal + SC_NCOMP, st);
             LAUNCHED(c); CHECK_LAUNCH(c);
             ea.sorted_val = svA; ea.out_off = c->out_off.as<u64>();
-            ea.out_len = c->out_len.as<u32>(); ea.out_seq = c->out_seq.as<u32>(); ea.out_start = c->out_start.as<i64>();
+            ea.out_len = c->out_len.as<u32>(); ea.out_seq = c->out_seq.as<u8>(); ea.out_start = c->out_start.as<int32_t>();
             launch_enum_gather(ea, fmt, L, n_cand, st); LAUNCHED(c); CHECK_LAUNCH(c);
         }
         c->r_matches = n_cand; c->r_comps = n_ccomp;
@@ -750,10 +750,10 @@ int mbi_output_unique(mb_ctx* c, u32 n_cand, u64 maxlen) {
         LAUNCHED(c); CHECK_LAUNCH(c);
         TRY(mbi_read_scalars(c));
         n_ocomp = hs64[SC_NCOMP];
-        TRY(c->reserve(c->out_seq, (size_t)(n_ocomp + 8) * 4));
-        TRY(c->reserve(c->out_start, (size_t)(n_ocomp + 8) * 8));
-        oa.out_off = c->out_off.as<u64>(); oa.out_len = c->out_len.as<u32>(); oa.out_seq = c->out_seq.as<u32>();
-        oa.out_start = c->out_start.as<i64>();
+        TRY(c->reserve(c->out_seq, (size_t)(n_ocomp + 8)));
+        TRY(c->reserve(c->out_start, (size_t)(n_ocomp + 8) * 4));
+        oa.out_off = c->out_off.as<u64>(); oa.out_len = c->out_len.as<u32>(); oa.out_seq = c->out_seq.as<u8>();
+        oa.out_start = c->out_start.as<int32_t>();
         launch_uniq_gather(oa, svA, L, n_matches, st); LAUNCHED(c); CHECK_LAUNCH(c);
     }
     c->r_matches = n_matches; c->r_comps = n_ocomp;
@@ -762,34 +762,37 @@ int mbi_output_unique(mb_ctx* c, u32 n_cand, u64 maxlen) {
 
 extern "C" {
 
-int mb_fetch_result(mb_ctx* c, const mb_result** out) {
-    if (!c || !out) return MB_E_ARG;
+// Device -> pinned host copy of the last result.  compact: the device arrays as they are (u8 sequence, i32 start);
+// otherwise widened on the device to the u32 / i64 arrays of mb_result first.
+static int fetch_common(mb_ctx* c, bool compact) {
     if (!c->have_result) return MB_E_STATE;
     CUDA_TRY(c, cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
     u64 nm = c->r_matches, nc = c->r_comps;
     TRY(c->reserve_host(c->h_len, c->h_len_cap, (nm + 1) * 4));
     TRY(c->reserve_host(c->h_off, c->h_off_cap, (nm + 1) * 8));
-    TRY(c->reserve_host(c->h_seq, c->h_seq_cap, (nc + 1) * 4));
-    TRY(c->reserve_host(c->h_start, c->h_start_cap, (nc + 1) * 8));
+    TRY(c->reserve_host(c->h_seq, c->h_seq_cap, (nc + 1) * (compact ? 1 : 4)));
+    TRY(c->reserve_host(c->h_start, c->h_start_cap, (nc + 1) * (compact ? 4 : 8)));
     cudaEventRecord(c->ev_x[1], st);
     if (nm) {
         CUDA_TRY(c, cudaMemcpyAsync(c->h_len, c->out_len.p, nm * 4, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(c, cudaMemcpyAsync(c->h_off, c->out_off.p, (nm + 1) * 8, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(c, cudaMemcpyAsync(c->h_seq, c->out_seq.p, nc * 4, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(c, cudaMemcpyAsync(c->h_start, c->out_start.p, nc * 8, cudaMemcpyDeviceToHost, st));
+        if (compact) {
+            CUDA_TRY(c, cudaMemcpyAsync(c->h_seq, c->out_seq.p, nc, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(c, cudaMemcpyAsync(c->h_start, c->out_start.p, nc * 4, cudaMemcpyDeviceToHost, st));
+        } else {
+            TRY(c->reserve(c->wide_seq, (nc + 8) * 4)); TRY(c->reserve(c->wide_start, (nc + 8) * 8));
+            launch_expand_result(c->out_seq.as<u8>(), c->out_start.as<int32_t>(), nc, c->wide_seq.as<u32>(), c->wide_start.as<i64>(), st);
+            CHECK_LAUNCH(c);
+            CUDA_TRY(c, cudaMemcpyAsync(c->h_seq, c->wide_seq.p, nc * 4, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(c, cudaMemcpyAsync(c->h_start, c->wide_start.p, nc * 8, cudaMemcpyDeviceToHost, st));
+        }
     } else {
         ((u64*)c->h_off)[0] = 0;
     }
     cudaEventRecord(c->ev_x[2], st);
     CUDA_TRY(c, cudaStreamSynchronize(st));
-    c->stats.d2h_bytes = nm ? nm * 4 + (nm + 1) * 8 + nc * 12 : 0;
-    mb_result& r = c->res;
-    r.n_matches = nm; r.n_comps = nc;
-    r.length = (const u32*)c->h_len; r.comp_off = (const u64*)c->h_off; r.comp_seq = (const u32*)c->h_seq; r.comp_start = (const i64*)c->h_start;
-    r.unique_mers = c->r_unique;
-    r.unique_mers_per_seq = (const u64*)c->h_perseq;
-    r.nseq = (u32)c->seq_len.size();
+    c->stats.d2h_bytes = nm ? nm * 4 + (nm + 1) * 8 + nc * (compact ? 5 : 12) : 0;
     // stage timings
     auto ms = [&](cudaEvent_t a, cudaEvent_t b) { float t = 0; if (cudaEventElapsedTime(&t, a, b) != cudaSuccess) { cudaGetLastError(); t = 0; } return t; };
     c->stats.ms_extract = ms(c->ev[EV_START], c->ev[EV_EXTRACT]);
@@ -802,8 +805,38 @@ int mb_fetch_result(mb_ctx* c, const mb_result** out) {
     c->stats.ms_radix_kernels = 0;
     for (int i = 0; i < c->n_timed_passes; ++i) c->stats.ms_radix_kernels += ms(c->ev_r[2 * i], c->ev_r[2 * i + 1]);
     c->stats.radix_launches = c->n_timed_passes;
+    return MB_OK;
+}
+
+int mb_fetch_result(mb_ctx* c, const mb_result** out) {
+    if (!c || !out) return MB_E_ARG;
+    TRY(fetch_common(c, false));
+    mb_result& r = c->res;
+    r.n_matches = c->r_matches; r.n_comps = c->r_comps;
+    r.length = (const u32*)c->h_len; r.comp_off = (const u64*)c->h_off; r.comp_seq = (const u32*)c->h_seq; r.comp_start = (const i64*)c->h_start;
+    r.unique_mers = c->r_unique;
+    r.unique_mers_per_seq = (const u64*)c->h_perseq;
+    r.nseq = (u32)c->seq_len.size();
     *out = &c->res;
     return MB_OK;
+}
+
+int mb_fetch_result_compact(mb_ctx* c, const mb_result_compact** out) {
+    if (!c || !out) return MB_E_ARG;
+    TRY(fetch_common(c, true));
+    mb_result_compact& r = c->cres;
+    r.n_matches = c->r_matches; r.n_comps = c->r_comps;
+    r.length = (const u32*)c->h_len; r.comp_off = (const u64*)c->h_off; r.comp_seq8 = (const u8*)c->h_seq; r.comp_start32 = (const int32_t*)c->h_start;
+    r.unique_mers = c->r_unique;
+    r.unique_mers_per_seq = (const u64*)c->h_perseq;
+    r.nseq = (u32)c->seq_len.size();
+    *out = &c->cres;
+    return MB_OK;
+}
+
+int mb_find_compact(mb_ctx* c, const mb_params* prm, const mb_result_compact** out) {
+    TRY(mb_find_device(c, prm));
+    return mb_fetch_result_compact(c, out);
 }
 
 /* repeatoire's match position lookup table (src/repeatoire.cpp:1944-1966), built on the device from the last single-sequence
@@ -819,7 +852,7 @@ int mb_position_table(mb_ctx* c, const uint32_t** match_of_pos, const uint32_t**
     TRY(c->reserve_host(c->h_posm, c->h_posm_cap, np * 4)); TRY(c->reserve_host(c->h_posc, c->h_posc_cap, np * 4));
     TRY(c->reserve(c->sort_kA, np * 8)); // scratch: (match + 1) << 32 | component per position
     CUDA_TRY(c, cudaMemsetAsync(c->sort_kA.p, 0, np * 8, st));
-    launch_position_table(c->out_off.as<u64>(), c->out_start.as<i64>(), (u32)c->r_matches, c->sort_kA.as<u64>(), c->pos_match.as<u32>(), c->pos_comp.as<u32>(), np, st);
+    launch_position_table(c->out_off.as<u64>(), c->out_start.as<int32_t>(), (u32)c->r_matches, c->sort_kA.as<u64>(), c->pos_match.as<u32>(), c->pos_comp.as<u32>(), np, st);
     CHECK_LAUNCH(c);
     CUDA_TRY(c, cudaMemcpyAsync(c->h_posm, c->pos_match.p, np * 4, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(c, cudaMemcpyAsync(c->h_posc, c->pos_comp.p, np * 4, cudaMemcpyDeviceToHost, st));

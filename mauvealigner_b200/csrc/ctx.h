@@ -54,7 +54,9 @@ struct mb_ctx {
     cudaEvent_t ev_d[8] = {nullptr};
     DBuf wl_a, wl_b, wl_c, wl_long, wd_a, wd_b, wd_c, live_bits, ghash, slot_gp, slot_hash, link_bits, chain_min, rep_bits, rep_rank, s_hash, s_cand, rng_lo, rng_hi;
     DBuf flags, match_idx, sort_kA, sort_kB, sort_vA, sort_vB, ncomp, mers_tmp;
-    DBuf out_len, out_off, out_seq, out_start;
+    DBuf out_len, out_off, out_seq, out_start;   // device result: out_seq u8[], out_start i32[] (compact)
+    DBuf wide_seq, wide_start;                   // widened copies for mb_fetch_result
+    mb_result_compact cres{};
     // segmented search (mb_set_segments / mb_find_batch): host copy of the bounds [nseq][n_seg + 1], device copy
     std::vector<u32> h_seg;
     u32 n_seg = 0;

@@ -65,7 +65,7 @@ struct EmitEnumArgs {
     const u32* run_start; const u32* cand_run; const u32* cand_off; const u32* totals;
     u64* sort_key; u64* sort_val; u32* ncomp;
     const u64* sorted_val; const u64* out_off;
-    u32* out_len; u32* out_seq; i64* out_start;
+    u32* out_len; u8* out_seq; int32_t* out_start;   // the device result is compact: 1-byte sequence, 4-byte signed start per component
     int repeat;               // MB_MODE_REPEAT: ties of the first start are ordered as for MB_MODE_SEED_ENUM (multiplicity, signed starts, length)
 };
 void launch_enum_keys(const EmitEnumArgs& a, const RecFmt& fmt, u32 n_upper, cudaStream_t st);
@@ -149,10 +149,12 @@ struct OutputArgs {
     u64* sort_key; u64* sort_val;
     u32* ncomp;
     const u64* out_off;
-    u32* out_len; u32* out_seq; i64* out_start;
+    u32* out_len; u8* out_seq; int32_t* out_start;   // the device result is compact: 1-byte sequence, 4-byte signed start per component
     int repeat;               // MB_MODE_REPEAT: ties of the first start are ordered as for MB_MODE_SEED_ENUM (multiplicity, signed starts, length)
 };
-void launch_position_table(const u64* out_off, const i64* out_start, u32 n_matches, u64* tab, u32* match_of, u32* comp_of, u64 n_pos, cudaStream_t st);
+void launch_position_table(const u64* out_off, const int32_t* out_start, u32 n_matches, u64* tab, u32* match_of, u32* comp_of, u64 n_pos, cudaStream_t st);
+// compact device result -> the wide arrays of mb_result (u32 sequence, i64 start)
+void launch_expand_result(const u8* seq8, const int32_t* start32, u64 n_comps, u32* seq, i64* start, cudaStream_t st);
 void launch_uniq_flags(const OutputArgs& a, cudaStream_t st);
 void launch_uniq_keys(const OutputArgs& a, int sbits, cudaStream_t st);
 void launch_uniq_tiefix(const OutputArgs& a, const u64* skey, u64* sval, u32 L, u32 n_upper, cudaStream_t st);

@@ -369,7 +369,7 @@ __global__ void __launch_bounds__(256) k_enum_gather(EmitEnumArgs a, RecFmt fmt,
         u64 v = fmt.wide ? a.vals[i] : a.keys[i];
         bool rev = rec_strand(v) != s0;
         if (project && rev) continue;
-        i64 st = (i64)rec_pos(fmt, v) + 1;
+        const int32_t st = (int32_t)rec_pos(fmt, v) + 1;
         a.out_seq[o] = 0;
         a.out_start[o] = rev ? -st : st;
         ++o;

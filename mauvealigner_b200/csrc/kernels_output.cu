@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(256) k_uniq_gather(OutputArgs a, const u64* __
         const u32 off = __shfl_sync(0xFFFFFFFFu, v.off, t), el = __shfl_sync(0xFFFFFFFFu, v.el, t), er = __shfl_sync(0xFFFFFFFFu, v.er, t);
         if (p < T) {
             u8 gs = a.comp_gs[off + k];
-            i64 s = (i64)(a.comp_pos[off + k] - ((gs & 0x80) ? er : el) + 1);
+            const int32_t s = (int32_t)(a.comp_pos[off + k] - ((gs & 0x80) ? er : el) + 1);
             a.out_seq[o_first + p] = gs & 0x7F;
             a.out_start[o_first + p] = (gs & 0x80) ? -s : s;
         }
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(256) k_uniq_gather(OutputArgs a, const u64* __
 // repeatoire's match position lookup table (/root/reference/src/repeatoire.cpp:1944-1966): for every position of the one
 // sequence, which match (index in the result order = ascending LeftEnd(0), the order of repeatoire's seed_sort_list,
 // :1920-1935) and which of its components starts there; 0xFFFFFFFF where none does.  Entry p = 1-based left end, entry 0 unused.
-__global__ void __launch_bounds__(256) k_position_table(const u64* __restrict__ out_off, const i64* __restrict__ out_start, u32 n_matches,
+__global__ void __launch_bounds__(256) k_position_table(const u64* __restrict__ out_off, const int32_t* __restrict__ out_start, u32 n_matches,
                                                         unsigned long long* __restrict__ tab, u64 n_pos) {
     const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_matches) return;
@@ -151,9 +151,21 @@ __global__ void __launch_bounds__(256) k_position_split(const unsigned long long
     match_of[p] = v ? (u32)(v >> 32) - 1 : 0xFFFFFFFFu;
     comp_of[p] = v ? (u32)v : 0xFFFFFFFFu;
 }
-void launch_position_table(const u64* out_off, const i64* out_start, u32 n_matches, u64* tab, u32* match_of, u32* comp_of, u64 n_pos, cudaStream_t st) {
+void launch_position_table(const u64* out_off, const int32_t* out_start, u32 n_matches, u64* tab, u32* match_of, u32* comp_of, u64 n_pos, cudaStream_t st) {
     if (n_matches) k_position_table<<<div_up(n_matches, 256), 256, 0, st>>>(out_off, out_start, n_matches, reinterpret_cast<unsigned long long*>(tab), n_pos);
     k_position_split<<<div_up(n_pos, 256), 256, 0, st>>>(reinterpret_cast<const unsigned long long*>(tab), match_of, comp_of, n_pos);
+}
+
+// The device result keeps 5 bytes per component (1-byte sequence index, 4-byte signed 1-based start: every sequence is
+// shorter than 2^31 bases); mb_fetch_result widens it to the u32 / i64 arrays of mb_result on request,
+// mb_fetch_result_compact copies it as it is (less than half the bytes over PCIe).
+__global__ void __launch_bounds__(256) k_expand_result(const u8* __restrict__ seq8, const int32_t* __restrict__ start32, u64 n, u32* __restrict__ seq,
+                                                       i64* __restrict__ start) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { seq[i] = seq8[i]; start[i] = start32[i]; }
+}
+void launch_expand_result(const u8* seq8, const int32_t* start32, u64 n_comps, u32* seq, i64* start, cudaStream_t st) {
+    if (n_comps) k_expand_result<<<div_up(n_comps, 256), 256, 0, st>>>(seq8, start32, n_comps, seq, start);
 }
 
 void launch_uniq_flags(const OutputArgs& a, cudaStream_t st) {

@@ -99,15 +99,25 @@ class Context:
         p = self._params(mode, min_multi, max_multi, direct_only, nway_mask)
         _check(self._h, L.lib().mb_find_device(self._h, C.byref(p)))
 
-    def fetch(self, copy=True):
-        out = C.POINTER(L.MbResult)()
-        _check(self._h, L.lib().mb_fetch_result(self._h, C.byref(out)))
+    def fetch(self, copy=True, compact=False):
+        """compact: the layout the device keeps (comp_seq uint8, comp_start int32: 5 instead of 12 bytes per component
+        over PCIe); same values either way."""
+        if compact:
+            out = C.POINTER(L.MbResultCompact)()
+            _check(self._h, L.lib().mb_fetch_result_compact(self._h, C.byref(out)))
+        else:
+            out = C.POINTER(L.MbResult)()
+            _check(self._h, L.lib().mb_fetch_result(self._h, C.byref(out)))
         return self._wrap(out.contents, copy)
 
-    def find(self, mode, min_multi=2, max_multi=1000, direct_only=False, nway_mask=0, copy=True):
+    def find(self, mode, min_multi=2, max_multi=1000, direct_only=False, nway_mask=0, copy=True, compact=False):
         p = self._params(mode, min_multi, max_multi, direct_only, nway_mask)
-        out = C.POINTER(L.MbResult)()
-        _check(self._h, L.lib().mb_find(self._h, C.byref(p), C.byref(out)))
+        if compact:
+            out = C.POINTER(L.MbResultCompact)()
+            _check(self._h, L.lib().mb_find_compact(self._h, C.byref(p), C.byref(out)))
+        else:
+            out = C.POINTER(L.MbResult)()
+            _check(self._h, L.lib().mb_find(self._h, C.byref(p), C.byref(out)))
         return self._wrap(out.contents, copy)
 
     def position_table(self):

@@ -236,6 +236,22 @@ def test_position_lookup_table(ctx):
         assert (mo != 0xFFFFFFFF).sum() == want["n_comps"] or mode == mb.MODE_REPEAT
 
 
+def test_compact_result_form(ctx):
+    """mb_fetch_result_compact / mb_find_compact: the layout the device keeps (u8 sequence, i32 start) carries the same
+    values as the wide arrays of mb_result"""
+    import mauvealigner_b200 as mb
+    rng = np.random.default_rng(55)
+    seqs = family(rng, 20000, 5, sub=0.02, indel=0.003, inv=1)
+    seqs[2] = revcomp(seqs[2])
+    wide = run(ctx, seqs, mb.get_seed(11, 0), mb.MODE_UNIQUE)
+    compact = ctx.fetch(compact=True)
+    assert compact["comp_seq"].dtype == np.uint8 and compact["comp_start"].dtype == np.int32
+    assert_same(compact, wide)
+    again = ctx.find(mb.MODE_UNIQUE, compact=True)
+    assert_same(again, O.find(seqs, mb.get_seed(11, 0), O.MODE_UNIQUE))
+    assert (np.asarray(again["comp_start"]) < 0).any()
+
+
 def test_edge_cases(ctx):
     import mauvealigner_b200 as mb
     # sequences shorter than the seed, empty sequences
