@@ -33,18 +33,36 @@ __device__ __forceinline__ u32 slot_rank(const u64* __restrict__ bitmap, const u
     return bmrank[gp >> 6] + (u32)__popcll(w & ((1ull << (gp & 63)) - 1));
 }
 
-// D16 group test, exact: same genome set, same strands, same diagonal
+// D16 group test, exact: same genome set, same strands, same diagonal.  Four components per step with all loads issued
+// before the first comparison (the loop is latency-bound: a one-at-a-time walk with an early exit per component took
+// 1.3 ms in k_chain and 1.2 ms in k_resolve on C5).
 __device__ __forceinline__ bool same_group(const DedupArgs& a, u32 j, u32 e) {
-    u32 offj = a.cand_off[j], offe = a.cand_off[e];
-    u32 m = a.cand_off[e + 1] - offe;
+    const u32 offj = a.cand_off[j], offe = a.cand_off[e];
+    const u32 m = a.cand_off[e + 1] - offe;
     if (a.cand_off[j + 1] - offj != m) return false;
-    u32 xj = a.comp_pos[offj], xe = a.comp_pos[offe];
-    for (u32 k = 0; k < m; ++k) {
-        u8 gj = a.comp_gs[offj + k], ge = a.comp_gs[offe + k];
-        if (gj != ge) return false;
-        u32 pj = a.comp_pos[offj + k], pe = a.comp_pos[offe + k];
-        if (ge & 0x80) { if (pj + xj != pe + xe) return false; }
-        else if (pj - xj != pe - xe) return false;
+    const u32 xj = a.comp_pos[offj], xe = a.comp_pos[offe];
+    const u32* __restrict__ pj = a.comp_pos + offj;
+    const u32* __restrict__ pe = a.comp_pos + offe;
+    const u8* __restrict__ gj = a.comp_gs + offj;
+    const u8* __restrict__ ge = a.comp_gs + offe;
+    u32 k = 0;
+    for (; k + 4 <= m; k += 4) {
+        u32 vj[4], ve[4], sj[4], se[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) { vj[t] = pj[k + t]; ve[t] = pe[k + t]; sj[t] = gj[k + t]; se[t] = ge[k + t]; }
+        bool ok = true;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            ok &= sj[t] == se[t];
+            ok &= (se[t] & 0x80u) ? (vj[t] + xj == ve[t] + xe) : (vj[t] - xj == ve[t] - xe);
+        }
+        if (!ok) return false;
+    }
+    for (; k < m; ++k) {
+        const u32 s1 = gj[k], s2 = ge[k];
+        if (s1 != s2) return false;
+        if (s2 & 0x80u) { if (pj[k] + xj != pe[k] + xe) return false; }
+        else if (pj[k] - xj != pe[k] - xe) return false;
     }
     return true;
 }
