@@ -568,6 +568,46 @@ public:
         }
         return a->Length() < b->Length();
     }
+    /* Many small searches in ONE pass of the device pipeline (recursive anchoring re-runs the search inside every gap
+     * between anchors: `recursive` flag src/mauveAligner.cpp:94,698; SetRecursive src/progressiveMauve.cpp:661-664).
+     * problems[i] = the MatchList of gap i with seq_table / sml_table filled (the same number of sequences and the same
+     * seed everywhere; an empty sequence = the gap has none in that genome).  Every list receives exactly the matches its
+     * own FindMatches + Clear() would have produced. */
+    boolean FindMatchesBatch(std::vector<MatchList*>& problems) {
+        if (problems.empty()) return true;
+        if (!ensure_ctx()) return false;
+        const size_t nseq = problems[0]->seq_table.size();
+        std::vector<const uint8_t*> ptrs;
+        std::vector<uint64_t> lens;
+        uint64 seed = 0;
+        for (MatchList* ml : problems) {
+            if (ml->seq_table.size() != nseq || ml->sml_table.size() != nseq) { genome::ErrorMsg("FindMatchesBatch: every problem needs the same number of sequences\n"); return false; }
+            for (size_t g = 0; g < nseq; ++g) {
+                if (!seed) seed = ml->sml_table[g]->Seed();
+                else if (ml->sml_table[g]->Seed() != seed) { genome::ErrorMsg("FindMatchesBatch: one seed for the whole batch\n"); return false; }
+                ptrs.push_back((const uint8_t*)ml->seq_table[g]->data().data());
+                lens.push_back(ml->seq_table[g]->length());
+            }
+        }
+        int rc = mb_set_seed(ctx_, seed);
+        mb_params p = {MB_MODE_UNIQUE, 0, 2, 1000, mask_};
+        const mb_batch_result* r = nullptr;
+        if (rc == MB_OK) rc = mb_find_batch(ctx_, &p, (uint32_t)problems.size(), (uint32_t)nseq, ptrs.data(), lens.data(), &r);
+        if (rc != MB_OK) { report("FindMatchesBatch", rc); return false; }
+        for (size_t i = 0; i < problems.size(); ++i) {
+            MatchList& out = *problems[i];
+            for (Match* m : out) m->Free();
+            out.clear();
+            for (uint64_t j = r->match_off[i]; j < r->match_off[i + 1]; ++j) {
+                Match* m = new Match((uint)nseq);
+                m->SetLength(r->length[j]);
+                for (uint64_t k = r->comp_off[j]; k < r->comp_off[j + 1]; ++k) m->SetStart(r->comp_seq[k], r->comp_start[k]);
+                out.push_back(m);
+            }
+        }
+        seq_count = 0; /* the batch replaced the context's sequences */
+        return true;
+    }
 protected:
     uint64 mask_;
     MatchList found_;

@@ -20,7 +20,7 @@ static string read_seq(const char* path) {
 }
 
 int main(int argc, char** argv) {
-    if (argc < 3) { cerr << "usage: compat_driver <umf|pmf|sme|repeats|count|sml|family> <weight> <rank> <seq files...> | smlcount <file.sslist> | readlist <file>\n"; return -1; }
+    if (argc < 3) { cerr << "usage: compat_driver <umf|pmf|sme|repeats|count|sml|family|batch> <weight> <rank> <seq files...> | smlcount <file.sslist> | readlist <file>\n"; return -1; }
     string what = argv[1];
     if (what == "smlcount") {
         // src/uniqueMerCount.cpp:29-39, line for line
@@ -67,6 +67,28 @@ int main(int argc, char** argv) {
         ml.LoadSMLs(weight, &cerr, rank);
         ml.LoadSMLs(weight, &cerr, rank); // second call must find the files and not rebuild
         cout << endl << ml.sml_table[0]->UniqueMerCount() << endl;
+        return 0;
+    }
+    if (what == "batch") {
+        // recursive anchoring in miniature: every sequence file is cut into pieces of 400 bases, piece i of every file = gap i;
+        // all gaps searched in one pass (MemHash::FindMatchesBatch), printed gap by gap
+        const size_t piece = 400;
+        vector<string> full;
+        size_t ngap = 0;
+        for (int i = 4; i < argc; ++i) { full.push_back(read_seq(argv[i])); ngap = max(ngap, (full.back().size() + piece - 1) / piece); }
+        vector<MatchList> gaps(ngap);
+        vector<MatchList*> ptrs;
+        for (size_t gI = 0; gI < ngap; ++gI) {
+            for (const string& s : full) gaps[gI].seq_table.push_back(new gnSequence(gI * piece < s.size() ? s.substr(gI * piece, piece) : string()));
+            gaps[gI].CreateMemorySMLs(weight, nullptr, rank);
+            ptrs.push_back(&gaps[gI]);
+        }
+        UniqueMatchFinder umf;
+        if (!umf.FindMatchesBatch(ptrs)) return -2;
+        for (size_t gI = 0; gI < ngap; ++gI) {
+            cout << "Gap\t" << gI << "\t" << gaps[gI].size() << "\n";
+            for (const Match* m : gaps[gI]) cout << *m << "\n";
+        }
         return 0;
     }
     if (what == "family") {

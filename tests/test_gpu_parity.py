@@ -362,6 +362,23 @@ def test_cpp_host_api_matches_oracle(tmp_path):
         d = dict(comps)
         rows.append([ln] + [d.get(g, 0) for g in range(3)])
     assert parse(out) == rows and len(rows) > 10
+    # many small problems in one pass through the C++ mirror (MemHash::FindMatchesBatch): pieces of 400 bases as "gaps"
+    out = subprocess.check_output([str(exe), "batch", "7", "0"] + files, text=True).strip().split("\n")
+    k, gap = 0, 0
+    while k < len(out):
+        tag, gi, n = out[k].split("\t")
+        assert tag == "Gap" and int(gi) == gap
+        rows_g = [[int(x) for x in l.split("\t")] for l in out[k + 1:k + 1 + int(n)]]
+        pieces = [s[gap * 400:(gap + 1) * 400] for s in seqs]
+        want = O.find(pieces, mb.get_seed(7, 0), O.MODE_UNIQUE)
+        exp = []
+        for ln, comps in O.matches_as_list(want):
+            d = dict(comps)
+            exp.append([ln] + [d.get(g, 0) for g in range(3)])
+        assert rows_g == exp, gap
+        k += 1 + int(n)
+        gap += 1
+    assert gap == max((len(s) + 399) // 400 for s in seqs)
     # WriteList -> ReadList -> WriteList round trip
     first = subprocess.check_output([str(exe), "umf", "11", "0"] + files, text=True)
     lst = tmp_path / "matches.mums"

@@ -20,12 +20,33 @@ def main():
     ctx = mb.Context(0)
     for s in seqs:
         ctx.add_sequence(s)
-    for pattern in (0b110111011, mb.get_seed(15, 0), (1 << 40) - 1):
+    wide = sum(1 << (40 - j) for j in (0, 5, 13, 19, 20, 21, 27, 35, 40))  # L = 41 (> 32: the window-by-window extension), weight 9
+    for pattern in (0b110111011, mb.get_seed(15, 0), wide):
         ctx.set_seed(pattern)
-        for mode, kw in ((mb.MODE_UNIQUE, {}), (mb.MODE_PAIRWISE, {}), (mb.MODE_UNIQUE_COUNT, {}),
-                         (mb.MODE_SEED_ENUM, dict(min_multi=2, max_multi=50))):
+        for mode, kw in ((mb.MODE_UNIQUE, {}), (mb.MODE_PAIRWISE, {}), (mb.MODE_UNIQUE_COUNT, {})):
             r = ctx.find(mode, **kw)
             print("mode", mode, "pattern", bin(pattern)[:14], "matches", r["n_matches"], flush=True)
+    # the table persisting across searches (seed family), compact fetch
+    ctx.accumulate(True)
+    for pattern in (mb.get_seed(11, 2), mb.get_seed(11, 1), mb.get_seed(9, 0)):
+        ctx.set_seed(pattern)
+        r = ctx.find(mb.MODE_UNIQUE, compact=True)
+        print("family pass", bin(pattern)[:14], "matches", r["n_matches"], flush=True)
+    ctx.accumulate(False)
+    # one sequence: seed enumeration, RepeatHash, the position lookup table
+    ctx.clear_sequences()
+    ctx.add_sequence(seqs[0] + revcomp(seqs[0][1000:1400]) + seqs[0][2000:2300] + "AC" * 40)
+    ctx.set_seed(0b110111011)
+    for mode, kw in ((mb.MODE_SEED_ENUM, dict(min_multi=2, max_multi=50)), (mb.MODE_REPEAT, dict(max_multi=255))):
+        r = ctx.find(mode, **kw)
+        mo, co = ctx.position_table()
+        print("mode", mode, "matches", r["n_matches"], "table entries", int((mo != 0xFFFFFFFF).sum()), flush=True)
+    # many small problems in one pass
+    probs = [family(rng, int(rng.integers(0, 400)), 3, sub=0.04, indel=0.004, inv=0) for _ in range(40)]
+    probs[3][2] = ""
+    ctx.set_seed(0b1011101)
+    res = ctx.find_batch(probs, mb.MODE_UNIQUE)
+    print("batch of", len(probs), "matches", sum(r["n_matches"] for r in res), flush=True)
     ctx.close()
     for p2p in (0, 1, 2):
         r = dist.find_unique_emulated(seqs, 0b1101110111110111011, 3, p2p=p2p)
