@@ -75,7 +75,10 @@ int mb_find_batch(mb_ctx* c, const mb_params* prm, uint32_t n_problems, uint32_t
     }
     TRY(mb_set_segments(c, n_problems, bounds.data()));
     const mb_result* r = nullptr;
+    const bool fam = c->fam_on; // a batch is a set of independent searches: the table of mb_accumulate stays out of it
+    c->fam_on = false;
     int rc = mb_find(c, prm, &r);
+    c->fam_on = fam;
     if (rc != MB_OK) { mb_set_segments(c, 0, nullptr); return rc; }
     // ---- cut by problem (stable: the batch order restricted to a problem is the problem's canonical order)
     const u64 nm = r->n_matches;

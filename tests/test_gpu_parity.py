@@ -413,6 +413,18 @@ def test_seed_family_vs_oracle(seed):
     got = [(m.Length(), [(g, m.Start(g)) for g in range(k) if m.Start(g) != 0]) for m in out]
     assert got == [(ln, list(comps)) for ln, comps in O.matches_as_list(want)]
     assert len(got) > 5
+    if k >= 3:  # MaskedMemHash over a family: only matches present in exactly the masked genomes, table shared across the patterns
+        mask = 0b101
+        mmh = mb.MaskedMemHash()
+        mmh.SetMask(mask)
+        for p in families:
+            ml.seed_pattern = p
+            mmh.FindMatches(ml)
+            mmh.ClearSequences()
+        out = mb.MatchList()
+        mmh.GetMatchList(out)
+        want_m = O.find_family(seqs, families, nway_mask=mask)
+        assert [(m.Length(), [(g, m.Start(g)) for g in range(k) if m.Start(g) != 0]) for m in out] == [(ln, list(c)) for ln, c in O.matches_as_list(want_m)]
     # Clear() forgets the table: the next search is a plain single-pattern one again
     umf.Clear()
     ml.seed_pattern = families[-1]
