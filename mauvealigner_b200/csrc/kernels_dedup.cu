@@ -773,8 +773,12 @@ __device__ __forceinline__ void extend_finish(const DedupArgs& a, const GenomeTa
     wl_push(last ? a.wl_long : out_list, last ? a.ctr + 6 : out_count, more, i);
 }
 
-#define DD_EXT_FIRST_ROUNDS 2
-#define DD_EXT_MORE_ROUNDS 4
+#ifndef DD_EXT_FIRST_ROUNDS
+#define DD_EXT_FIRST_ROUNDS 6
+#endif
+#ifndef DD_EXT_MORE_ROUNDS
+#define DD_EXT_MORE_ROUNDS 8
+#endif
 
 __global__ void __launch_bounds__(DD_NT) k_extend(DedupArgs a, GenomeTable gt, SeedDev sd, u32* out_list, u32* out_count) {
     __shared__ u32 sMap[DD_NT / 32][32][4];
@@ -1022,7 +1026,9 @@ void launch_rep_keys(const DedupArgs& a, u64* skey, cudaStream_t st) {
 }
 // k_extend over all reps, then DD_EXT_MORE launches over the shrinking list of unfinished reps (ping-pong lists
 // wd0 / wd1 with counters ctr[12] / ctr[13]), then the warp-per-rep kernel for what is left
-#define DD_EXT_MORE 3
+#ifndef DD_EXT_MORE
+#define DD_EXT_MORE 2
+#endif
 int extend_launches() { return 2 + DD_EXT_MORE; }
 void launch_rep_setup(const DedupArgs& a, const GenomeTable& gt, cudaStream_t st) {
     if (a.n_rep) k_rep_setup<<<div_up(a.n_rep, 256), 256, 0, st>>>(a, gt);
