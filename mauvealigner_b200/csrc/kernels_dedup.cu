@@ -1029,6 +1029,12 @@ void launch_rep_keys(const DedupArgs& a, u64* skey, cudaStream_t st) {
 #ifndef DD_EXT_MORE
 #define DD_EXT_MORE 2
 #endif
+#ifndef DD_MORE_BLOCKS
+#define DD_MORE_BLOCKS 4 // grid of the continuation kernels, blocks per SM
+#endif
+#ifndef DD_LONG_BLOCKS
+#define DD_LONG_BLOCKS 4
+#endif
 int extend_launches() { return 2 + DD_EXT_MORE; }
 void launch_rep_setup(const DedupArgs& a, const GenomeTable& gt, cudaStream_t st) {
     if (a.n_rep) k_rep_setup<<<div_up(a.n_rep, 256), 256, 0, st>>>(a, gt);
@@ -1047,9 +1053,9 @@ void launch_extend(const DedupArgs& a, const GenomeTable& gt, const SeedDev& sd,
     for (int r = 0; r < DD_EXT_MORE; ++r) {
         int in = r & 1, out = in ^ 1;
         cudaMemsetAsync(cnt[out], 0, 4, st);
-        k_extend_more<<<148 * 4, DD_NT, 0, st>>>(a, gt, sd, list[in], cnt[in], list[out], cnt[out], r == DD_EXT_MORE - 1);
+        k_extend_more<<<148 * DD_MORE_BLOCKS, DD_NT, 0, st>>>(a, gt, sd, list[in], cnt[in], list[out], cnt[out], r == DD_EXT_MORE - 1);
     }
-    k_extend_long<<<148 * 4, DD_NT, 0, st>>>(a, gt, sd);
+    k_extend_long<<<148 * DD_LONG_BLOCKS, DD_NT, 0, st>>>(a, gt, sd);
 }
 cudaError_t launch_resolve(const DedupArgs& a, cudaStream_t st) {
     if (a.n_rep == 0) return cudaSuccess;
