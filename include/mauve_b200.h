@@ -100,7 +100,9 @@ int mb_set_stream(mb_ctx* ctx, void* cuda_stream);
  * case, anything else reads as A) or 2-bit words (is_packed = 1; 32 bases per uint64, first base
  * in the top bits).  The library copies to the device; the caller keeps ownership. */
 int mb_add_sequence(mb_ctx* ctx, const uint8_t* data, uint64_t len, int is_packed, int* out_id);
-/* Same, but `dev_ascii` is already DEVICE memory (used by the resident-input benchmark leg). */
+/* Same, but `dev_ascii` is already DEVICE memory (used by the resident-input benchmark leg).  The pack kernel is only
+ * ENQUEUED on the context stream: the buffer must stay valid until that stream has passed it (stream order is enough:
+ * free it with a stream-ordered free, or after any later synchronising call on the context). */
 int mb_add_sequence_device(mb_ctx* ctx, const void* dev_ascii, uint64_t len, int* out_id);
 /* MatchFinder::ClearSequences() (src/progressiveMauve.cpp:542) */
 int mb_clear_sequences(mb_ctx* ctx);

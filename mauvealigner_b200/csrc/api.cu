@@ -178,6 +178,7 @@ static int add_sequence_common(mb_ctx* c, const void* data, uint64_t len, int ki
     if (len) {
         if (kind == 1) {
             CUDA_TRY(c, cudaMemcpyAsync(dst, data, n_words * 8, cudaMemcpyHostToDevice, c->stream));
+            CUDA_TRY(c, cudaStreamSynchronize(c->stream)); // the caller keeps ownership of `data` (a pinned buffer would still be in flight)
             c->stats.h2d_bytes += n_words * 8;
         } else {
             const u8* d_ascii = (const u8*)data;
