@@ -471,6 +471,17 @@ def test_find_batch_many_small_problems_one_pass():
     ctx.close()
 
 
+def test_randomised_parity_sweep():
+    """tools/fuzz_parity.py: random genome counts, lengths around the kernels' tile sizes, random valid seed patterns, all
+    policies — 150 cases here (4000 were run for profiles/r02_fuzz_parity.txt)"""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_parity.py"), "150", "3"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "0 mismatches" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
 def test_context_pool_many_small_problems():
     """f4 (many small problems, one search per inter-anchor gap): a pool of contexts on concurrent streams gives the
     results of the one-at-a-time searches, in order, for problems of mixed sizes (including empty ones)."""
