@@ -104,6 +104,13 @@ int mb_add_sequence(mb_ctx* ctx, const uint8_t* data, uint64_t len, int is_packe
  * ENQUEUED on the context stream: the buffer must stay valid until that stream has passed it (stream order is enough:
  * free it with a stream-ordered free, or after any later synchronising call on the context). */
 int mb_add_sequence_device(mb_ctx* ctx, const void* dev_ascii, uint64_t len, int* out_id);
+/* The 2-bit words of a sequence as the context holds them on the device (32 bases per uint64, first base in the top
+ * bits; stream-ordered after the mb_add_sequence* call that produced them), and the way back in: a sequence given as
+ * packed words already in DEVICE memory.  With several GPUs every rank uploads and packs only its share of the genomes and
+ * the ranks exchange the packed words over NVLink (80 MB at C5) instead of every rank pulling every genome over PCIe. */
+int mb_get_packed_device(mb_ctx* ctx, int seq, const void** dev_words, uint64_t* n_words);
+int mb_copy_packed_device(mb_ctx* ctx, int seq, void* dst_dev);   /* the same words copied to dst_dev on the context stream */
+int mb_add_sequence_device_packed(mb_ctx* ctx, const void* dev_words, uint64_t len, int* out_id);
 /* MatchFinder::ClearSequences() (src/progressiveMauve.cpp:542) */
 int mb_clear_sequences(mb_ctx* ctx);
 /* getSeed() result handed to LoadSMLs/CreateMemorySMLs (src/mauveAligner.cpp:456,465): the raw

@@ -52,7 +52,7 @@ EXPORTS = ["mb_ctx_create", "mb_ctx_destroy", "mb_set_stream", "mb_add_sequence"
            "mb_set_seed", "mb_find", "mb_find_device", "mb_fetch_result", "mb_get_sml", "mb_get_mers", "mb_get_stats", "mb_strerror",
            "mb_last_cuda_error", "mb_device_count", "mb_version",
            "mb_dist_extract", "mb_dist_extract_count", "mb_dist_partition", "mb_dist_p2p_recv_array",
-           "mb_dist_use_p2p_recv", "mb_ipc_export", "mb_ipc_import", "mb_ipc_close", "mb_dist_recv_buffer", "mb_dist_local", "mb_dist_rows_pack", "mb_dist_push", "mb_dist_resolve", "mb_dist_accept", "mb_dist_match_pack", "mb_dist_match_partition", "mb_dist_output", "mb_dist_stage_ms", "mb_find_multi", "mb_debug_radix", "mb_find_batch", "mb_set_segments", "mb_position_table", "mb_fetch_result_compact", "mb_find_compact"]
+           "mb_dist_use_p2p_recv", "mb_ipc_export", "mb_ipc_import", "mb_ipc_close", "mb_dist_recv_buffer", "mb_dist_local", "mb_dist_rows_pack", "mb_dist_push", "mb_dist_resolve", "mb_dist_accept", "mb_dist_match_pack", "mb_dist_match_partition", "mb_dist_output", "mb_dist_stage_ms", "mb_find_multi", "mb_debug_radix", "mb_find_batch", "mb_set_segments", "mb_position_table", "mb_fetch_result_compact", "mb_find_compact", "mb_get_packed_device", "mb_add_sequence_device_packed", "mb_copy_packed_device"]
 
 _lib = None
 
@@ -71,6 +71,9 @@ def lib():
     L.mb_set_stream.argtypes = [vp, vp]
     L.mb_add_sequence.argtypes = [vp, vp, u64, i32, C.POINTER(i32)]
     L.mb_add_sequence_device.argtypes = [vp, vp, u64, C.POINTER(i32)]
+    L.mb_add_sequence_device_packed.argtypes = [vp, vp, u64, C.POINTER(i32)]
+    L.mb_get_packed_device.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(u64)]
+    L.mb_copy_packed_device.argtypes = [vp, i32, vp]
     L.mb_clear_sequences.argtypes = [vp]
     L.mb_accumulate.argtypes = [vp, i32]
     L.mb_set_seed.argtypes = [vp, u64]

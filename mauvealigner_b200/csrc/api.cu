@@ -162,7 +162,7 @@ static int grow_packed(mb_ctx* c, u64 need_words) {
     return MB_OK;
 }
 
-static int add_sequence_common(mb_ctx* c, const void* data, uint64_t len, int kind /*0 host ascii, 1 host packed, 2 device ascii*/, int* out_id) {
+static int add_sequence_common(mb_ctx* c, const void* data, uint64_t len, int kind /*0 host ascii, 1 host packed, 2 device ascii, 3 device packed*/, int* out_id) {
     if (!c || (!data && len)) return MB_E_ARG;
     if (len >= (1ull << 32)) return MB_E_TOOLONG;
     if (c->seq_len.size() >= MB_MAX_SEQ) return MB_E_SEQCOUNT;
@@ -176,7 +176,9 @@ static int add_sequence_common(mb_ctx* c, const void* data, uint64_t len, int ki
     // padding after the genome must read as zero
     CUDA_TRY(c, cudaMemsetAsync(dst, 0, (n_words + MB_PAD_WORDS) * 8, c->stream));
     if (len) {
-        if (kind == 1) {
+        if (kind == 3) {
+            CUDA_TRY(c, cudaMemcpyAsync(dst, data, n_words * 8, cudaMemcpyDeviceToDevice, c->stream));
+        } else if (kind == 1) {
             CUDA_TRY(c, cudaMemcpyAsync(dst, data, n_words * 8, cudaMemcpyHostToDevice, c->stream));
             CUDA_TRY(c, cudaStreamSynchronize(c->stream)); // the caller keeps ownership of `data` (a pinned buffer would still be in flight)
             c->stats.h2d_bytes += n_words * 8;
@@ -206,6 +208,22 @@ int mb_add_sequence(mb_ctx* c, const uint8_t* data, uint64_t len, int is_packed,
 }
 int mb_add_sequence_device(mb_ctx* c, const void* dev_ascii, uint64_t len, int* out_id) {
     return add_sequence_common(c, dev_ascii, len, 2, out_id);
+}
+int mb_add_sequence_device_packed(mb_ctx* c, const void* dev_words, uint64_t len, int* out_id) {
+    return add_sequence_common(c, dev_words, len, 3, out_id);
+}
+int mb_copy_packed_device(mb_ctx* c, int seq, void* dst_dev) {
+    if (!c || seq < 0 || (size_t)seq >= c->seq_len.size() || !dst_dev) return MB_E_ARG;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const u64 nw = (c->seq_len[seq] + 31) / 32;
+    if (nw) CUDA_TRY(c, cudaMemcpyAsync(dst_dev, c->packed.as<u64>() + c->seq_word_base[seq], nw * 8, cudaMemcpyDeviceToDevice, c->stream));
+    return MB_OK;
+}
+int mb_get_packed_device(mb_ctx* c, int seq, const void** dev_words, uint64_t* n_words) {
+    if (!c || seq < 0 || (size_t)seq >= c->seq_len.size() || !dev_words || !n_words) return MB_E_ARG;
+    *dev_words = c->packed.as<u64>() + c->seq_word_base[seq];
+    *n_words = (c->seq_len[seq] + 31) / 32;
+    return MB_OK;
 }
 
 } // extern "C"

@@ -89,6 +89,20 @@ class Context:
         _check(self._h, L.lib().mb_add_sequence_device(self._h, C.c_void_p(dev_ptr), int(length), C.byref(sid)))
         return sid.value
 
+    def add_sequence_device_packed(self, dev_ptr, length):
+        """A sequence given as 2-bit words already in device memory (mb_add_sequence_device_packed); length in bases."""
+        _check(self._h, L.lib().mb_add_sequence_device_packed(self._h, C.c_void_p(dev_ptr), length, None))
+
+    def copy_packed_device(self, seq, dst_dev_ptr):
+        """copy the packed words of sequence `seq` to device memory at dst_dev_ptr, on the context stream"""
+        _check(self._h, L.lib().mb_copy_packed_device(self._h, seq, C.c_void_p(dst_dev_ptr)))
+
+    def packed_device(self, seq):
+        """(device pointer, number of uint64 words) of the packed form of sequence `seq` (mb_get_packed_device)."""
+        p, n = C.c_void_p(), C.c_uint64(0)
+        _check(self._h, L.lib().mb_get_packed_device(self._h, seq, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
     def set_seed(self, pattern):
         _check(self._h, L.lib().mb_set_seed(self._h, int(pattern)))
 
