@@ -45,10 +45,12 @@ void launch_pack(const u8* d_ascii, u64 len, u64* d_words, u64 n_words, cudaStre
 }
 
 // --------------------------------------------------------------------------------------- extract
-// Tile = EX_TILE consecutive seed positions of one genome.  The tile's packed words (plus halo) are
-// staged in shared memory twice: forward, and reverse-complemented in reverse order, so that both
-// the forward window and the reverse-complement window of a position are one unaligned 128-bit
-// funnel extraction.  Thread t handles positions t, t+NT, ... so record stores are fully coalesced.
+// Tile = EX_TILE consecutive seed positions of one genome, its packed words (plus halo) staged in shared memory; the
+// forward window of a position is one unaligned 128-bit funnel extraction.  The pattern is palindromic, so the cared
+// bases of the reverse-complement window are the reverse complement of the cared bases of the forward window: the
+// reverse key is rc(forward key) — one bit reversal instead of a second window (no reverse-complemented copy of the
+// tile, no second extraction, mask and 128-bit compare).  Thread t handles positions t, t+NT, ... so record stores
+// are fully coalesced.
 #define EX_NT 256
 #define EX_IPT 16
 #define EX_TILE (EX_NT * EX_IPT)
@@ -84,7 +86,6 @@ __device__ __forceinline__ u64 gather_key(const SeedDev& sd, u64 hi, u64 lo) {
 template <int MODE> // 0: packed records, 1: wide records, 2: mers dump
 __global__ void __launch_bounds__(EX_NT) k_extract(ExtractArgs a, GenomeTable gt, SeedDev sd, RecFmt fmt, const u32* __restrict__ tile_first /*[nseq+1]*/) {
     __shared__ u64 sF[EX_WORDS + 2];
-    __shared__ u64 sR[EX_WORDS + 2];
     __shared__ u32 sHist[8 * 256];
     __shared__ u32 sG;
 
@@ -107,12 +108,7 @@ __global__ void __launch_bounds__(EX_NT) k_extract(ExtractArgs a, GenomeTable gt
     const u64* gw = a.packed + gt.word_base[g];
     const int m = EX_TILE / 32 + 2; // staged span in words (covers L-1 <= 63 halo bases)
 
-    for (int i = tid; i < m + 2; i += EX_NT) {
-        u64 w = gw[(p0 >> 5) + i]; // padding words after each genome keep this in bounds
-        sF[i] = w;
-        if (i < m) sR[m - 1 - i] = rc_word(w);
-        else sR[i] = 0;
-    }
+    for (int i = tid; i < m + 2; i += EX_NT) sF[i] = gw[(p0 >> 5) + i]; // padding words after each genome keep this in bounds
     __syncthreads();
 
     const u32 kshift_la = 64 - 2 * sd.w; // (fmt.kbits = 2w, plus the problem index bits of a segmented search)
@@ -121,13 +117,13 @@ __global__ void __launch_bounds__(EX_NT) k_extract(ExtractArgs a, GenomeTable gt
         u32 o = it * EX_NT + tid;
         u32 p = p0 + o;
         if (p >= nseeds) continue;
-        u64 fh, fl, rh, rl;
+        u64 fh, fl;
         load_window(sF, o, sd.wide, fh, fl);
-        load_window(sR, (u32)(32 * m) - sd.L - o, sd.wide, rh, rl);
-        fh &= sd.mask_hi; fl &= sd.mask_lo;
-        rh &= sd.mask_hi; rl &= sd.mask_lo;
-        bool strand = (rh < fh) || (rh == fh && rl < fl);
-        u64 key = gather_key(sd, strand ? rh : fh, strand ? rl : fl) >> kshift_la;
+        const u64 kf_la = gather_key(sd, fh & sd.mask_hi, fl & sd.mask_lo);     // forward key, left-aligned (2w bits at the top)
+        const u64 kf = kf_la >> kshift_la;
+        const u64 kr = rc_word(kf_la) & (~0ull >> kshift_la);                   // rc of the 32-base word: the key's rc in the low 2w bits
+        const bool strand = kr < kf;                                            // D4: the smaller of the two, ties forward
+        u64 key = strand ? kr : kf;
         if (MODE != 2 && gt.n_seg) { // segmented search: the problem index leads the key; a window across a boundary gets a key of its own
             u32 lo, hi;
             const u32 si = seg_range(gt, g, p, lo, hi);
