@@ -333,7 +333,7 @@ int mbi_setup_run(mb_ctx* c, MbiRun& r) {
     const u64 items = r.mode == MB_MODE_PAIRWISE ? std::max<u64>(n, (u64)n * (nseq - 1) / 2 + 2) : n;
     TRY(c->reserve(c->lookback, (size_t)(div_up(items, radix_tile_size()) + 1) * 256 * 8));
     TRY(c->reserve(c->tickets, 256 * 4));
-    size_t status_words = (size_t)div_up(n, find_runs_tile()) + div_up(n, select_tile()) + 6 * (size_t)div_up(items, scan_tile()) +
+    size_t status_words = find_runs_workspace_words(n) + div_up(n, select_tile()) + 6 * (size_t)div_up(items, scan_tile()) +
                           div_up(bases * std::min<u64>(nseq, 8) / 64 + 2, scan_tile()) + 2 * (size_t)div_up(items, chain_tile()) + 64;
     TRY(c->reserve(c->status, status_words * 8));
     TRY(c->reserve(c->scalars, SC_COUNT * 8));
@@ -406,9 +406,9 @@ int mb_find_device(mb_ctx* c, const mb_params* prm) {
     u32* run_u = fmt.wide ? reinterpret_cast<u32*>(vB) : run_start + (n + 2);
     bool need_u = mode == MB_MODE_UNIQUE || mode == MB_MODE_PAIRWISE;
     bool need_counts = mode == MB_MODE_UNIQUE_COUNT;
-    launch_find_runs(kA, vA, n, fmt, run_start, need_u ? run_u : nullptr, c->status_slice(div_up(n, find_runs_tile())), c->ticket(),
+    launch_find_runs(kA, vA, n, fmt, run_start, need_u ? run_u : nullptr, c->status_slice(find_runs_workspace_words(n)), c->ticket(),
                      need_counts ? c->per_seq.as<u64>() : nullptr, reinterpret_cast<u32*>(scal + SC_RUNS), st);
-    LAUNCHED(c); CHECK_LAUNCH(c);
+    LAUNCHED(c); LAUNCHED(c); LAUNCHED(c); CHECK_LAUNCH(c); // masks, one-block scan, compaction
 
     if (mode == MB_MODE_UNIQUE_COUNT) {
         for (int i = EV_BUCKET; i < EV_COUNT; ++i) cudaEventRecord(c->ev[i], st);

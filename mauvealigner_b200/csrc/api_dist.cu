@@ -209,9 +209,9 @@ int mb_dist_local(mb_ctx* c, const mb_params* prm, uint64_t n_recv, uint64_t* h_
     if (n == 0) { cudaEventRecord(c->ev_d[4], st); cudaEventRecord(c->ev_d[5], st); return MB_OK; }
     u32* run_start = reinterpret_cast<u32*>(kB);
     u32* run_u = run_start + (n + 2);
-    launch_find_runs(kA, nullptr, n, fmt, run_start, run_u, c->status_slice(div_up(n, find_runs_tile())), c->ticket(), nullptr,
+    launch_find_runs(kA, nullptr, n, fmt, run_start, run_u, c->status_slice(find_runs_workspace_words(n)), c->ticket(), nullptr,
                      reinterpret_cast<u32*>(scal + SC_RUNS), st);
-    LAUNCHED(c); CHECK_LAUNCH(c);
+    LAUNCHED(c); LAUNCHED(c); LAUNCHED(c); CHECK_LAUNCH(c);
     const u32 cand_cap = n / 2 + 2;
     TRY(c->reserve(c->cand_run, (size_t)cand_cap * 4));
     TRY(c->reserve(c->q_off, (size_t)(cand_cap + 1) * 4));

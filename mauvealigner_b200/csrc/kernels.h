@@ -31,6 +31,7 @@ cudaError_t launch_onesweep(const u64* kin, u64* kout, const u64* vin, u64* vout
 
 // ---- kernels_bucket.cu
 u32 find_runs_tile();
+size_t find_runs_workspace_words(u32 n);
 void launch_find_runs(const u64* keys, const u64* vals, u32 n, const RecFmt& fmt, u32* run_start, u32* run_u, u64* status, u32* ticket,
                       u64* per_seq_count, u32* totals, cudaStream_t st);
 struct SelectArgs {

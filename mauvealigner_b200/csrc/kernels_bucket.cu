@@ -36,18 +36,22 @@ __device__ __forceinline__ Rec load_rec(const RecFmt& f, const u64* __restrict__
     return r;
 }
 
-__global__ void __launch_bounds__(FR_NT) k_find_runs(const u64* __restrict__ keys, const u64* __restrict__ vals, u32 n, RecFmt fmt,
-                                                     u32* __restrict__ run_start, u32* __restrict__ run_u, u64* status, u32* ticket,
-                                                     u64* __restrict__ per_seq_count /*[nseq] or null*/, u32* __restrict__ totals /*[2]*/) {
+// Two streaming kernels and a one-block scan between them instead of one kernel with a decoupled look-back: the ncu
+// source page of the single-pass version had 62 % of its stall samples at the barrier behind the warp that waits for its
+// predecessors (tiles of 2048 records are over before the look-back answers).  Pass A reads the records once and leaves
+// two bytes per thread (head / unique masks of its 8 records) and one (heads, uniques) pair per tile; pass B turns the
+// masks into the compact run arrays with the scanned tile offsets — no dependency between tiles.
+__global__ void __launch_bounds__(FR_NT) k_find_runs_a(const u64* __restrict__ keys, const u64* __restrict__ vals, u32 n, RecFmt fmt,
+                                                       unsigned short* __restrict__ masks, u64* __restrict__ tile_counts,
+                                                       u64* __restrict__ per_seq_count /*[nseq] or null*/) {
     __shared__ u32 sWarp[FR_NT / 32];
     __shared__ u32 sSeq[MB_MAX_SEQ];
-    __shared__ u32 sTile;
-    __shared__ u64 sExcl;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) sTile = atomicAdd(ticket, 1u);
-    if (tid < MB_MAX_SEQ) sSeq[tid] = 0;
-    __syncthreads();
-    const u32 tile = sTile;
+    if (per_seq_count) {
+        if (tid < MB_MAX_SEQ) sSeq[tid] = 0;
+        __syncthreads();
+    }
+    const u32 tile = blockIdx.x;
     const u64 base = (u64)tile * FR_TILE;
     const u64 i0 = base + (u64)tid * FR_IPT;
     // records i0 .. i0+7 (keys beyond n read as a key no record has)
@@ -102,7 +106,49 @@ __global__ void __launch_bounds__(FR_NT) k_find_runs(const u64* __restrict__ key
         }
     }
     if (per_seq_count && run_c) atomicAdd(&sSeq[run_g], run_c);
-    // scan of (heads | uniques << 16) over the block
+    masks[(u64)tile * FR_NT + tid] = (unsigned short)(headm | (uniqm << 8));
+    // tile totals (heads | uniques << 16)
+    u32 x = __reduce_add_sync(0xFFFFFFFFu, (u32)__popc(headm) | ((u32)__popc(uniqm) << 16));
+    if (lane == 0) sWarp[warp] = x;
+    __syncthreads();
+    if (tid == 0) {
+        u32 tot = 0;
+#pragma unroll
+        for (int w = 0; w < FR_NT / 32; ++w) tot += sWarp[w];
+        tile_counts[tile] = (u64)(tot & 0xFFFF) | ((u64)(tot >> 16) << 32);
+    }
+    if (per_seq_count && tid < MB_MAX_SEQ && sSeq[tid]) atomicAdd((unsigned long long*)&per_seq_count[tid], (unsigned long long)sSeq[tid]);
+}
+
+// exclusive scan of the tile pairs (one block), totals and sentinels
+__global__ void __launch_bounds__(1024) k_find_runs_scan(u64* __restrict__ tile_counts, u32 n_tiles, u32 n, u32* __restrict__ run_start,
+                                                         u32* __restrict__ run_u, u32* __restrict__ totals) {
+    __shared__ u64 scratch[1024 / 32 + 1];
+    u64 carry = 0;
+    for (u32 base = 0; base < n_tiles; base += 1024) {
+        const u32 t = base + threadIdx.x;
+        const u64 v = t < n_tiles ? tile_counts[t] : 0;
+        u64 total;
+        const u64 ex = block_excl_scan_u64<1024>(v, scratch, total);
+        if (t < n_tiles) tile_counts[t] = carry + ex;
+        carry += total;
+    }
+    if (threadIdx.x == 0) {
+        const u32 nr = (u32)carry, nu = (u32)(carry >> 32);
+        totals[0] = nr; totals[1] = nu;
+        run_start[nr] = n;
+        if (run_u) run_u[nr] = nu;
+    }
+}
+
+__global__ void __launch_bounds__(FR_NT) k_find_runs_b(const unsigned short* __restrict__ masks, const u64* __restrict__ tile_excl, u32 n,
+                                                       u32* __restrict__ run_start, u32* __restrict__ run_u) {
+    __shared__ u32 sWarp[FR_NT / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 tile = blockIdx.x;
+    const u64 i0 = (u64)tile * FR_TILE + (u64)tid * FR_IPT;
+    const u32 mk = masks[(u64)tile * FR_NT + tid];
+    const u32 headm = mk & 0xFFu, uniqm = mk >> 8;
     const u32 mine = (u32)__popc(headm) | ((u32)__popc(uniqm) << 16);
     u32 x = mine;
 #pragma unroll
@@ -112,31 +158,12 @@ __global__ void __launch_bounds__(FR_NT) k_find_runs(const u64* __restrict__ key
     }
     if (lane == 31) sWarp[warp] = x;
     __syncthreads();
-    if (warp == 0) {
-        u32 w = lane < FR_NT / 32 ? sWarp[lane] : 0, xs = w;
+    u32 wpre = 0;
 #pragma unroll
-        for (int o = 1; o < FR_NT / 32; o <<= 1) {
-            u32 y = __shfl_up_sync(0xFFFFFFFFu, xs, o);
-            if (lane >= o) xs += y;
-        }
-        if (lane < FR_NT / 32) sWarp[lane] = xs - w;
-        u32 tot = __shfl_sync(0xFFFFFFFFu, xs, FR_NT / 32 - 1);
-        u64 agg = (u64)(tot & 0xFFFF) | ((u64)(tot >> 16) << 31);
-        u64 excl = lookback_exclusive(status, tile, agg);
-        if (lane == 0) {
-            sExcl = excl;
-            if (base + FR_TILE >= n) { // last tile: totals + sentinels
-                u64 t2 = excl + agg;
-                u32 nr = (u32)(t2 & 0x7FFFFFFFu), nu = (u32)(t2 >> 31);
-                totals[0] = nr; totals[1] = nu;
-                run_start[nr] = n;
-                if (run_u) run_u[nr] = nu;
-            }
-        }
-    }
-    __syncthreads();
-    const u32 pre = sWarp[warp] + x - mine;
-    u32 rh = (u32)(sExcl & 0x7FFFFFFFu) + (pre & 0xFFFF), ru = (u32)(sExcl >> 31) + (pre >> 16);
+    for (int w = 0; w < FR_NT / 32; ++w) wpre += (w < warp) ? sWarp[w] : 0u;
+    const u32 pre = wpre + x - mine;
+    const u64 te = tile_excl[tile];
+    u32 rh = (u32)te + (pre & 0xFFFF), ru = (u32)(te >> 32) + (pre >> 16);
 #pragma unroll
     for (int k = 0; k < FR_IPT; ++k) {
         if ((headm >> k) & 1) {
@@ -146,13 +173,25 @@ __global__ void __launch_bounds__(FR_NT) k_find_runs(const u64* __restrict__ key
         }
         ru += (uniqm >> k) & 1;
     }
-    if (per_seq_count && tid < MB_MAX_SEQ && sSeq[tid]) atomicAdd((unsigned long long*)&per_seq_count[tid], (unsigned long long)sSeq[tid]);
+    (void)n;
 }
 
+// status: workspace of at least 2 * tiles + FR_NT/4 * tiles ... words (see find_runs_workspace_words)
 void launch_find_runs(const u64* keys, const u64* vals, u32 n, const RecFmt& fmt, u32* run_start, u32* run_u, u64* status,
                       u32* ticket, u64* per_seq_count, u32* totals, cudaStream_t st) {
+    (void)ticket;
     if (n == 0) return;
-    k_find_runs<<<div_up(n, FR_TILE), FR_NT, 0, st>>>(keys, vals, n, fmt, run_start, run_u, status, ticket, per_seq_count, totals);
+    const u32 tiles = div_up(n, FR_TILE);
+    u64* tile_counts = status;                                                   // [tiles]
+    unsigned short* masks = reinterpret_cast<unsigned short*>(status + tiles + 1); // [tiles * FR_NT]
+    k_find_runs_a<<<tiles, FR_NT, 0, st>>>(keys, vals, n, fmt, masks, tile_counts, per_seq_count);
+    k_find_runs_scan<<<1, 1024, 0, st>>>(tile_counts, tiles, n, run_start, run_u, totals);
+    k_find_runs_b<<<tiles, FR_NT, 0, st>>>(masks, tile_counts, n, run_start, run_u);
+}
+// 8-byte words of workspace launch_find_runs needs behind `status`
+size_t find_runs_workspace_words(u32 n) {
+    const size_t tiles = div_up(n, FR_TILE);
+    return tiles + 1 + (tiles * FR_NT * 2 + 7) / 8 + 1;
 }
 u32 find_runs_tile() { return FR_TILE; }
 
