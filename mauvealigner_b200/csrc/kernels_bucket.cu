@@ -125,12 +125,18 @@ __global__ void __launch_bounds__(1024) k_find_runs_scan(u64* __restrict__ tile_
                                                          u32* __restrict__ run_u, u32* __restrict__ totals) {
     __shared__ u64 scratch[1024 / 32 + 1];
     u64 carry = 0;
-    for (u32 base = 0; base < n_tiles; base += 1024) {
-        const u32 t = base + threadIdx.x;
-        const u64 v = t < n_tiles ? tile_counts[t] : 0;
+    for (u32 base = 0; base < n_tiles; base += 1024 * 8) { // 8 consecutive tiles per thread and step
+        const u32 t0 = base + threadIdx.x * 8;
+        u64 v[8], sum = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { v[j] = t0 + j < n_tiles ? tile_counts[t0 + j] : 0; sum += v[j]; }
         u64 total;
-        const u64 ex = block_excl_scan_u64<1024>(v, scratch, total);
-        if (t < n_tiles) tile_counts[t] = carry + ex;
+        u64 ex = carry + block_excl_scan_u64<1024>(sum, scratch, total);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (t0 + j < n_tiles) tile_counts[t0 + j] = ex;
+            ex += v[j];
+        }
         carry += total;
     }
     if (threadIdx.x == 0) {
