@@ -406,7 +406,7 @@ int mb_find_device(mb_ctx* c, const mb_params* prm) {
     u32* run_u = fmt.wide ? reinterpret_cast<u32*>(vB) : run_start + (n + 2);
     bool need_u = mode == MB_MODE_UNIQUE || mode == MB_MODE_PAIRWISE;
     bool need_counts = mode == MB_MODE_UNIQUE_COUNT;
-    launch_find_runs(kA, vA, n, fmt, run_start, need_u ? run_u : nullptr, c->status_slice(find_runs_workspace_words(n)), c->ticket(),
+    const unsigned short* run_masks = launch_find_runs(kA, vA, n, fmt, run_start, need_u ? run_u : nullptr, c->status_slice(find_runs_workspace_words(n)), c->ticket(),
                      need_counts ? c->per_seq.as<u64>() : nullptr, reinterpret_cast<u32*>(scal + SC_RUNS), st);
     LAUNCHED(c); LAUNCHED(c); LAUNCHED(c); CHECK_LAUNCH(c); // masks, one-block scan, compaction
 
@@ -499,7 +499,7 @@ int mb_find_device(mb_ctx* c, const mb_params* prm) {
         eu.cand_run = c->cand_run.as<u32>(); eu.cand_off = c->cand_off.as<u32>(); eu.cand_aux = mode == MB_MODE_PAIRWISE ? c->cand_aux.as<u32>() : nullptr;
         eu.totals = reinterpret_cast<u32*>(scal + SC_CAND);
         eu.mode = mode; eu.comp_pos = c->comp_pos.as<u32>(); eu.comp_gs = c->comp_gs.as<u8>(); eu.bitmap = c->bitmap.as<u64>(); eu.ghash = c->ghash.as<u64>(); eu.ghash2 = c->ghash2.as<u64>();
-        eu.seedL = L;
+        eu.seedL = L; eu.masks = run_masks;
         launch_emit_unique(eu, fmt, gt, n_cand, st); LAUNCHED(c); CHECK_LAUNCH(c);
         // ---- matches of earlier searches (mb_accumulate: the MemHash table persists until Clear())
         c->fam_pre = false;

@@ -209,7 +209,7 @@ int mb_dist_local(mb_ctx* c, const mb_params* prm, uint64_t n_recv, uint64_t* h_
     if (n == 0) { cudaEventRecord(c->ev_d[4], st); cudaEventRecord(c->ev_d[5], st); return MB_OK; }
     u32* run_start = reinterpret_cast<u32*>(kB);
     u32* run_u = run_start + (n + 2);
-    launch_find_runs(kA, nullptr, n, fmt, run_start, run_u, c->status_slice(find_runs_workspace_words(n)), c->ticket(), nullptr,
+    const unsigned short* run_masks = launch_find_runs(kA, nullptr, n, fmt, run_start, run_u, c->status_slice(find_runs_workspace_words(n)), c->ticket(), nullptr,
                      reinterpret_cast<u32*>(scal + SC_RUNS), st);
     LAUNCHED(c); LAUNCHED(c); LAUNCHED(c); CHECK_LAUNCH(c);
     const u32 cand_cap = n / 2 + 2;
@@ -251,7 +251,7 @@ int mb_dist_local(mb_ctx* c, const mb_params* prm, uint64_t n_recv, uint64_t* h_
     eu.cand_run = c->cand_run.as<u32>(); eu.cand_off = c->q_off.as<u32>(); eu.cand_aux = nullptr;
     eu.totals = reinterpret_cast<u32*>(scal + SC_CAND);
     eu.mode = prm->mode; eu.comp_pos = c->q_pos.as<u32>(); eu.comp_gs = c->q_gs.as<u8>(); eu.bitmap = nullptr; eu.ghash = c->ghash.as<u64>(); eu.ghash2 = c->ghash2.as<u64>();
-    eu.seedL = (u32)c->sd.L;
+    eu.seedL = (u32)c->sd.L; eu.masks = run_masks;
     launch_emit_unique(eu, fmt, c->gt, n_cand, st); LAUNCHED(c); CHECK_LAUNCH(c);
     cudaEventRecord(c->ev_d[4], st);
     // extension of every candidate (rep index = candidate; no slot axis here: the owner derives the slot ranges)

@@ -32,7 +32,7 @@ cudaError_t launch_onesweep(const u64* kin, u64* kout, const u64* vin, u64* vout
 // ---- kernels_bucket.cu
 u32 find_runs_tile();
 size_t find_runs_workspace_words(u32 n);
-void launch_find_runs(const u64* keys, const u64* vals, u32 n, const RecFmt& fmt, u32* run_start, u32* run_u, u64* status, u32* ticket,
+const unsigned short* launch_find_runs(const u64* keys, const u64* vals, u32 n, const RecFmt& fmt, u32* run_start, u32* run_u, u64* status, u32* ticket,
                       u64* per_seq_count, u32* totals, cudaStream_t st);
 struct SelectArgs {
     const u64* keys; const u64* vals;
@@ -57,6 +57,7 @@ struct EmitUniqueArgs {
     u64* bitmap;
     u64* ghash;      // per candidate: hash of (genome set, strands, diagonal)
     u64* ghash2;     // second, independent hash of the same key (low 8 bits cleared)
+    const unsigned short* masks; // per 8 sorted records: head / unique-genome flags (launch_find_runs)
     u32 seedL;       // seed length: a reverse component enters the hashes with position + seedL + first position, which
                      // extension leaves unchanged (so groups of different seed patterns meet, kernels_family.cu)
 };

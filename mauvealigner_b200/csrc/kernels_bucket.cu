@@ -183,16 +183,17 @@ __global__ void __launch_bounds__(FR_NT) k_find_runs_b(const unsigned short* __r
 }
 
 // status: workspace of at least 2 * tiles + FR_NT/4 * tiles ... words (see find_runs_workspace_words)
-void launch_find_runs(const u64* keys, const u64* vals, u32 n, const RecFmt& fmt, u32* run_start, u32* run_u, u64* status,
-                      u32* ticket, u64* per_seq_count, u32* totals, cudaStream_t st) {
+const unsigned short* launch_find_runs(const u64* keys, const u64* vals, u32 n, const RecFmt& fmt, u32* run_start, u32* run_u, u64* status,
+                                       u32* ticket, u64* per_seq_count, u32* totals, cudaStream_t st) {
     (void)ticket;
-    if (n == 0) return;
+    if (n == 0) return nullptr;
     const u32 tiles = div_up(n, FR_TILE);
     u64* tile_counts = status;                                                   // [tiles]
     unsigned short* masks = reinterpret_cast<unsigned short*>(status + tiles + 1); // [tiles * FR_NT]
     k_find_runs_a<<<tiles, FR_NT, 0, st>>>(keys, vals, n, fmt, masks, tile_counts, per_seq_count);
     k_find_runs_scan<<<1, 1024, 0, st>>>(tile_counts, tiles, n, run_start, run_u, totals);
     k_find_runs_b<<<tiles, FR_NT, 0, st>>>(masks, tile_counts, n, run_start, run_u);
+    return masks; // one 16-bit word per 8 records: bit k = record 8 j + k heads a run, bit 8 + k = it is the only record of its genome in its run
 }
 // 8-byte words of workspace launch_find_runs needs behind `status`
 size_t find_runs_workspace_words(u32 n) {
@@ -343,17 +344,15 @@ __global__ void __launch_bounds__(256) k_emit_unique(EmitUniqueArgs a, RecFmt fm
         while (t >= u - 1 - x) { t -= u - 1 - x; ++x; }
         pa = (int)x; pb = (int)(x + 1 + t);
     }
-    u32 prev_g = 0xFFFFFFFFu;
     u32 ui = 0;
     u32 x0 = 0, g_first = 0, g_second = 0;
     u64 h = 0x9E3779B97F4A7C15ull, h2 = 0xC2B2AE3D27D4EB4Full;
     for (u32 i = s; i < e; ++i) {
+        // "the only record of its genome in its bucket" was worked out by k_find_runs_a: bit 8 + (i & 7) of the mask word of
+        // the 8 records around i (RepeatHash takes every occurrence, in position order)
+        if (a.mode != MB_MODE_REPEAT_ && !((a.masks[i >> 3] >> (8 + (i & 7))) & 1u)) continue;
         u64 v = fmt.wide ? a.vals[i] : a.keys[i];
         u32 g = rec_genome(fmt, v);
-        bool first = g != prev_g;
-        prev_g = g;
-        bool lastg = i + 1 == e || rec_genome(fmt, fmt.wide ? a.vals[i + 1] : a.keys[i + 1]) != g;
-        if (!(first && lastg) && a.mode != MB_MODE_REPEAT_) continue; // RepeatHash takes every occurrence (position order)
         bool take = pa < 0 || (int)ui == pa || (int)ui == pb;
         ++ui;
         if (!take) continue;
