@@ -622,7 +622,11 @@ int mbi_dedup(mb_ctx* c, u32 n_cand, u64 bases, const u64* rows) {
         DedupArgs dx = da;
         dx.bitmap = nullptr; // extents only; the slot ranges follow in (colour, slot) order below
         launch_extend(dx, c->gt, c->sd, st);
-        if (n_rep) c->stats.kernel_launches += extend_launches();
+        if (n_rep) {
+            c->stats.kernel_launches += extend_launches();
+            TRY(mbi_extend_long(c, dx));
+            if (c->shadow_on) da.shadow = c->shadow.as<u8>();
+        }
     }
     // ---- reps in (group colour, slot) order, per-rep records, slot ranges of the extents
     TRY(mbi_sort_records(c, &skA, &skB, nullptr, nullptr, n_rep, 32, 16, false));
@@ -720,6 +724,37 @@ int mbi_family_append(mb_ctx* c) {
     LAUNCHED(c); CHECK_LAUNCH(c);
     c->fam_n += nm;
     c->fam_dirty = true;
+    return MB_OK;
+}
+
+// The reps whose extension the bounded rounds did not finish.  Few: one warp per rep.  Many (long window-consistent runs
+// full of reps of one group): sorted into classes that share their walks (kernels_dedup.cu, k_extend_long_classes).
+int mbi_extend_long(mb_ctx* c, const DedupArgs& da_in) {
+    cudaStream_t st = c->stream;
+    DedupArgs da = da_in;
+    u32 n_long = 0;
+    c->shadow_on = false;
+    CUDA_TRY(c, cudaMemcpyAsync(&c->tmp_u64, da.ctr + 6, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(c, cudaStreamSynchronize(st));
+    n_long = (u32)c->tmp_u64;
+    if (n_long == 0) return MB_OK;
+    // short lists: one warp per rep, no sort.  MB_LONG_CLASSES_MIN (test knob) moves the threshold.
+    const char* knob = getenv("MB_LONG_CLASSES_MIN");
+    const u32 classes_min = knob ? (u32)atoi(knob) : 256u;
+    if (n_long < classes_min) {
+        launch_extend_long(da, c->gt, c->sd, st); LAUNCHED(c); CHECK_LAUNCH(c);
+        return MB_OK;
+    }
+    TRY(c->reserve(c->sort_vA, (size_t)(n_long + 8) * 8)); TRY(c->reserve(c->sort_vB, (size_t)(n_long + 8) * 8));
+    TRY(c->reserve(c->lookback, (size_t)(div_up(n_long, radix_tile_size()) + 1) * 256 * 8));
+    u64 *kA = c->sort_vA.as<u64>(), *kB = c->sort_vB.as<u64>();
+    TRY(c->reserve(c->shadow, (size_t)da.n_cand + 8));
+    CUDA_TRY(c, cudaMemsetAsync(c->shadow.p, 0, (size_t)da.n_cand + 8, st));
+    da.shadow = c->shadow.as<u8>();
+    c->shadow_on = true;
+    launch_long_keys(da, (u32)c->sd.L, n_long, kA, st); LAUNCHED(c);
+    TRY(mbi_sort_records(c, &kA, &kB, nullptr, nullptr, n_long, 0, 64, false));
+    launch_extend_long_classes(da, c->gt, c->sd, kA, n_long, st); LAUNCHED(c); CHECK_LAUNCH(c);
     return MB_OK;
 }
 

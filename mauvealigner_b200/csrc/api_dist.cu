@@ -264,8 +264,10 @@ int mb_dist_local(mb_ctx* c, const mb_params* prm, uint64_t n_recv, uint64_t* h_
     da.wd0 = c->wd_a.as<u32>(); da.wd1 = c->wd_b.as<u32>(); da.wl_long = c->wl_long.as<u32>();
     da.ctr = reinterpret_cast<u32*>(scal + SC_DDCTR);
     launch_cand_xrec(da, c->gt, st);
+    da.ghash = c->ghash.as<u64>(); da.ghash2 = c->ghash2.as<u64>();
     launch_extend(da, c->gt, c->sd, st);
     c->stats.kernel_launches += extend_launches();
+    if (n_cand) TRY(mbi_extend_long(c, da));
     CHECK_LAUNCH(c);
     c->stats.n_extended = n_cand;
     cudaEventRecord(c->ev_d[5], st);

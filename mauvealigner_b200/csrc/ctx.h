@@ -39,7 +39,8 @@ struct mb_ctx {
     // workspace
     DBuf keysA, keysB, valsA, valsB, hist, digit_base, lookback, tickets, status, scalars, per_seq, tile_first;
     DBuf cand_run, cand_off, cand_aux, comp_pos, comp_gs, bitmap, bmrank, cand_at, cstate, covered, minrank, ext_l, ext_r;
-    DBuf trace, ghash2, rep_cand, s_h2, reach, xstate, xrec;
+    DBuf trace, ghash2, rep_cand, s_h2, reach, xstate, xrec, shadow;
+    bool shadow_on = false;                 // this search's long extensions left shadow flags (mbi_extend_long)
     u32 n_rep = 0;
     DBuf x_lut, x_counts, x_hdr_s, x_comp_s, x_hdr_r, x_comp_r, x_m, x_key, x_item, x_peers, x_recv; // multi-GPU exchange buffers (api_dist.cu)
     // source-side candidate arrays of the distributed path: they must outlive the owner stage that runs in between
@@ -160,6 +161,8 @@ int mbi_bits_for(u64 maxval);
 int mbi_reserve_candidates(mb_ctx* c, u32 n_cand, u32 n_ccomp, u64 bases);
 int mbi_dedup(mb_ctx* c, u32 n_cand, u64 bases, const u64* rows = nullptr);
 int mbi_output_unique(mb_ctx* c, u32 n_cand, u64 maxlen);
+// finishes the extensions launch_extend left on the long list (reads its length back; uses sort_vA / sort_vB as scratch)
+int mbi_extend_long(mb_ctx* c, const DedupArgs& da);
 // persistent MemHash table (mb_accumulate): drop the candidates contained in matches of earlier searches / add this search's matches
 int mbi_family_filter(mb_ctx* c, u32 n_cand);
 int mbi_family_append(mb_ctx* c);

@@ -107,6 +107,8 @@ struct DedupArgs {
     // and their counters (layout: see k_resolve)
     u32* wl0; u32* wl1; u32* wl2; u32* wd0; u32* wd1; u32* wd2; u32* wl_long; u32* ctr;
     u64* trace;         // optional phase trace (debug): [0] count, then (tag, ns) pairs
+    u8* shadow;         // per candidate, or null: set by the shared long walks for a rep whose round-0 claims a lower-rank rep of the
+                        // same group and extent makes anyway (k_extend_long_classes); k_resolve skips those claims
     const u8* pre_drop; // per candidate, or null: dropped before the de-dup (contained in a match of an earlier call, kernels_family.cu)
     // multi-GPU owner side: the candidates arrive as 4-word rows (kernels_dist.cu) with their extents already
     // known and without component lists; null on the single-GPU path
@@ -132,6 +134,11 @@ int extend_launches();
 // extends the a.n_rep items of a.xrec (filled by launch_rep_keys in slot order, or by launch_cand_xrec); a.bitmap == null:
 // extents only, the slot ranges are derived later (launch_rep_setup / launch_extent_ranges)
 void launch_extend(const DedupArgs& a, const GenomeTable& gt, const SeedDev& sd, cudaStream_t st);
+// the reps the bounded rounds of launch_extend left unfinished (a.ctr[6] of them on a.wl_long): warp per rep, or classes
+// of reps of one group that share a walk (keys from launch_long_keys, sorted by the caller)
+void launch_extend_long(const DedupArgs& a, const GenomeTable& gt, const SeedDev& sd, cudaStream_t st);
+void launch_long_keys(const DedupArgs& a, u32 L, u32 n_long, u64* keys, cudaStream_t st);
+void launch_extend_long_classes(const DedupArgs& a, const GenomeTable& gt, const SeedDev& sd, const u64* sorted_keys, u32 n_long, cudaStream_t st);
 void launch_rep_setup(const DedupArgs& a, const GenomeTable& gt, cudaStream_t st);
 // multi-GPU source side: every candidate is its own "rep" (a.n_rep = a.n_cand, extension records straight from the CSR)
 void launch_cand_xrec(const DedupArgs& a, const GenomeTable& gt, cudaStream_t st);

@@ -864,6 +864,105 @@ __global__ void __launch_bounds__(DD_NT) k_extend_long(DedupArgs a, GenomeTable 
     }
 }
 
+// ---- long extensions, shared inside a group -----------------------------------------------------------------------
+// The sequential reference extends only candidates no accepted match contains; here every rep is extended first, so a
+// long window-consistent run that holds thousands of reps of ONE group (two identical genomes, a recent duplication) would
+// be walked from end to end once per rep (the "cliff").  But two reps of one group whose seeds lie k L bases
+// apart inside one run walk the same lattice of jump windows: they stop at the same windows on both sides and so reach
+// the SAME extent.  The reps that are still unfinished after the bounded rounds are therefore sorted by (hash of group and
+// position mod L, rep index); one warp takes a class, walks the first member to the end, and every later member of the
+// same group (hashes, then the exact comparison) whose seed lies inside that extent takes it over; a member outside
+// starts a new walk.  L classes per group instead of one walk per rep.
+__global__ void __launch_bounds__(256) k_long_keys(DedupArgs a, u32 L, u64* __restrict__ keys) {
+    const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.ctr[6]) return;
+    const u32 i = a.wl_long[t];
+    const uint4 q = a.xrec[i];
+    u64 h = a.ghash[q.x] ^ ((u64)(q.w % L) * 0x9E3779B97F4A7C15ull);
+    h ^= h >> 32; h *= 0xD6E8FEB86659FD93ull; h ^= h >> 32;
+    keys[t] = (h << 32) | i;
+}
+
+__global__ void __launch_bounds__(DD_NT) k_extend_long_classes(DedupArgs a, GenomeTable gt, SeedDev sd, const u64* __restrict__ keys, u32 n) {
+    const int lane = threadIdx.x & 31;
+    const u32 t0 = (blockIdx.x * DD_NT + threadIdx.x) >> 5;
+    if (t0 >= n) return;
+    const u32 cls = (u32)(keys[t0] >> 32);
+    if (t0 > 0 && (u32)(keys[t0 - 1] >> 32) == cls) return; // not the first member of its class
+    const u32 L = sd.L;
+    // the last finished walk of this class: its rep, seed position, hashes, extent [lend, rend), and the lowest candidate
+    // index among the members that share it so far (members dropped before the de-dup do not count: they claim nothing)
+    bool has = false;
+    u32 c_lead = 0, x_lead = 0, lend = 0, rend = 0, c_min = INF32;
+    u64 h1_lead = 0, h2_lead = 0;
+    for (u32 base = t0; base < n; base += 32) { // 32 members at a time, one per lane
+        const u32 t = base + lane;
+        const u64 key = t < n ? keys[t] : 0;
+        const bool mine = t < n && (u32)(key >> 32) == cls;
+        const u32 i = (u32)key;
+        u32 c = 0, x = 0, vg = 0;
+        u64 h1 = 0, h2 = 0;
+        bool pd = false;
+        if (mine) {
+            const uint4 q = a.xrec[i];
+            c = q.x; x = q.w; vg = q.z >> 16;
+            h1 = a.ghash[c]; h2 = a.ghash2[c];
+            pd = a.pre_drop && a.pre_drop[c];
+        }
+        bool pending = mine;
+        for (;;) {
+            bool reuse = false;
+            if (pending && has && x >= lend && x + L <= rend && (x >= x_lead ? x - x_lead : x_lead - x) % L == 0 && h1 == h1_lead && h2 == h2_lead)
+                reuse = same_group(a, c, c_lead);
+            c_min = min(c_min, __reduce_min_sync(0xFFFFFFFFu, reuse && !pd ? c : INF32));
+            if (reuse) {
+                const u32 el = x - lend, er = rend - (x + L);
+                a.ext_l[c] = el; a.ext_r[c] = er;
+                if (a.shadow && c > c_min) a.shadow[c] = 1;
+                if (a.bitmap) {
+                    u32 rlo, rhi;
+                    extent_slots(a, gt.vbase[vg] + x, el, er, rlo, rhi);
+                    a.rng_lo[i] = rlo; a.rng_hi[i] = rhi;
+                }
+                pending = false;
+            }
+            const unsigned rest = __ballot_sync(0xFFFFFFFFu, pending);
+            if (!rest) break;
+            // the first member left starts a new walk, by the whole warp
+            const int src = __ffs(rest) - 1;
+            const u32 wc = __shfl_sync(0xFFFFFFFFu, c, src), wx = __shfl_sync(0xFFFFFFFFu, x, src), wi = __shfl_sync(0xFFFFFFFFu, i, src);
+            const bool wpd = __shfl_sync(0xFFFFFFFFu, pd ? 1 : 0, src) != 0;
+            const u32 off = a.cand_off[wc], m = a.cand_off[wc + 1] - off;
+            const u32* cpos = a.comp_pos + off;
+            const u8* cgs = a.comp_gs + off;
+            u32 el, er;
+            if (L > 32) extend_candidate_warp(a.packed, gt, sd, cpos, cgs, m, el, er);
+            else {
+                u32 room_l = INF32, room_r = INF32;
+                for (u32 k = lane; k < m; k += 32) candidate_room(gt, L, cpos, cgs, k, room_l, room_r);
+                room_l = __reduce_min_sync(0xFFFFFFFFu, room_l);
+                room_r = __reduce_min_sync(0xFFFFFFFFu, room_r);
+                el = grow_warp(a.packed, gt, sd, cpos, cgs, m, -1, room_l);
+                er = grow_warp(a.packed, gt, sd, cpos, cgs, m, +1, room_r);
+            }
+            has = true; c_lead = wc; x_lead = wx; lend = wx - el; rend = wx + L + er;
+            h1_lead = __shfl_sync(0xFFFFFFFFu, h1, src); h2_lead = __shfl_sync(0xFFFFFFFFu, h2, src);
+            c_min = wpd ? INF32 : wc;
+            if (lane == src) {
+                a.ext_l[wc] = el; a.ext_r[wc] = er;
+                if (a.bitmap) {
+                    u32 rlo, rhi;
+                    extent_slots(a, gt.vbase[vgenome(gt, cgs[0] & 0x7F, cgs[1] & 0x7F)] + cpos[0], el, er, rlo, rhi);
+                    a.rng_lo[wi] = rlo; a.rng_hi[wi] = rhi;
+                }
+                pending = false;
+            }
+            __syncwarp();
+        }
+        if (!__all_sync(0xFFFFFFFFu, mine)) break; // the class ended inside this batch
+    }
+}
+
 // Rep state: 0 undecided, 1 accepted, 2 dropped; flag bit 6: lives on the wide list.
 #define RS_MASK 0x0Fu
 #define RS_WIDE 0x40u
@@ -961,6 +1060,9 @@ __global__ void __launch_bounds__(DD_NT) k_resolve(DedupArgs a) {
                 if (rhi - rlo < 2) continue; // alone in its extent
                 if (a.pre_drop && a.rstate[i] != 0) continue; // dropped before the de-dup: claims nothing
                 ulonglong2 me = a.s_rec[i];
+                // a lower-rank rep of the same group with the same extent makes every claim of this one, with a lower value;
+                // this rep is itself claimed, so it cannot be accepted in this round, and claims again in the next if it is left
+                if (a.shadow && a.shadow[(u32)me.y]) continue;
                 if (walk_neighbours<false, false>(a, i, me, rlo, rhi, mr_cur) < 0) { a.rstate[i] = RS_WIDE; wd[cur][atomicAdd(ctr + 3 + cur, 1u)] = i; }
             }
         } else {
@@ -1035,7 +1137,7 @@ void launch_rep_keys(const DedupArgs& a, u64* skey, cudaStream_t st) {
 #ifndef DD_LONG_BLOCKS
 #define DD_LONG_BLOCKS 4
 #endif
-int extend_launches() { return 2 + DD_EXT_MORE; }
+int extend_launches() { return 1 + DD_EXT_MORE; }
 void launch_rep_setup(const DedupArgs& a, const GenomeTable& gt, cudaStream_t st) {
     if (a.n_rep) k_rep_setup<<<div_up(a.n_rep, 256), 256, 0, st>>>(a, gt);
 }
@@ -1055,7 +1157,17 @@ void launch_extend(const DedupArgs& a, const GenomeTable& gt, const SeedDev& sd,
         cudaMemsetAsync(cnt[out], 0, 4, st);
         k_extend_more<<<148 * DD_MORE_BLOCKS, DD_NT, 0, st>>>(a, gt, sd, list[in], cnt[in], list[out], cnt[out], r == DD_EXT_MORE - 1);
     }
-    k_extend_long<<<148 * DD_LONG_BLOCKS, DD_NT, 0, st>>>(a, gt, sd);
+}
+// what the bounded rounds left unfinished (a.ctr[6] reps on a.wl_long): one warp per rep ...
+void launch_extend_long(const DedupArgs& a, const GenomeTable& gt, const SeedDev& sd, cudaStream_t st) {
+    if (a.n_rep) k_extend_long<<<148 * DD_LONG_BLOCKS, DD_NT, 0, st>>>(a, gt, sd);
+}
+// ... or, for long lists, classes of reps that share their walks: keys (class hash << 32 | rep), sorted by the caller
+void launch_long_keys(const DedupArgs& a, u32 L, u32 n_long, u64* keys, cudaStream_t st) {
+    if (n_long) k_long_keys<<<div_up(n_long, 256), 256, 0, st>>>(a, L, keys);
+}
+void launch_extend_long_classes(const DedupArgs& a, const GenomeTable& gt, const SeedDev& sd, const u64* sorted_keys, u32 n_long, cudaStream_t st) {
+    if (n_long) k_extend_long_classes<<<div_up((u64)n_long * 32, DD_NT), DD_NT, 0, st>>>(a, gt, sd, sorted_keys, n_long);
 }
 cudaError_t launch_resolve(const DedupArgs& a, cudaStream_t st) {
     if (a.n_rep == 0) return cudaSuccess;

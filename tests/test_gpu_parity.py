@@ -471,6 +471,52 @@ def test_find_batch_many_small_problems_one_pass():
     ctx.close()
 
 
+def test_long_consistent_runs_share_their_walks(ctx):
+    """The 'cliff' of DESIGN.md §4: thousands of reps of ONE group inside one very long window-consistent run (identical
+    genomes; two identical genomes among diverged ones; an exact duplication inside otherwise diverged genomes).  Reps
+    whose seeds lie a multiple of the seed length apart share one walk (k_extend_long_classes): bit-exact against the
+    oracle, and in bounded time."""
+    import mauvealigner_b200 as mb
+    rng = np.random.default_rng(2024)
+    a = rand_seq(rng, 150000)
+    dup = rand_seq(rng, 40000)
+    cases = {"2 identical": [a, a],
+             "2 identical + 2 at 3 %": [a, a, mutate(rng, a, sub=0.03, indel=0.0), mutate(rng, a, sub=0.03, indel=0.0)],
+             "reverse-complemented copy": [a, revcomp(a)],
+             "1 SNP per 4 kb": [a, mutate(rng, a, sub=0.00025, indel=0.0)],  # many runs: several walks per class, extents that differ by residue
+             "1 SNP per 4 kb, three-way": [a, mutate(rng, a, sub=0.00025, indel=0.0), mutate(rng, a, sub=0.00025, indel=0.0)],
+             "exact duplication in diverged genomes": [rand_seq(rng, 30000) + dup + rand_seq(rng, 20000), rand_seq(rng, 10000) + dup + rand_seq(rng, 45000),
+                                                       rand_seq(rng, 50000) + mutate(rng, dup, sub=0.002, indel=0.0) + rand_seq(rng, 5000)]}
+    import os
+    for pattern in (mb.get_seed(15, 0), mb.get_seed(11, 1)):
+        for name, seqs in cases.items():
+            want = O.find(seqs, pattern, O.MODE_UNIQUE)
+            for knob in (None, "1"):  # the default threshold (lists of >= 256 long reps share walks), then every long rep
+                if knob:
+                    os.environ["MB_LONG_CLASSES_MIN"] = knob
+                try:
+                    got = run(ctx, seqs, pattern, mb.MODE_UNIQUE)
+                finally:
+                    os.environ.pop("MB_LONG_CLASSES_MIN", None)
+                st = ctx.stats()
+                assert_same(got, want, name)
+                assert st["ms_total_device"] < 60.0, (name, st["ms_total_device"], st["n_extended"])
+    # the same with the table persisting across two patterns: the second search's long runs hold reps dropped before the de-dup
+    seqs = cases["2 identical + 2 at 3 %"]
+    fam = [mb.get_seed(15, 0), mb.get_seed(11, 1)]
+    want = O.find_family(seqs, fam)
+    ml = mb.MatchList()
+    ml.seq_table = list(seqs)
+    umf = mb.UniqueMatchFinder()
+    for p in fam:
+        ml.seed_pattern = p
+        umf.FindMatches(ml)
+        umf.ClearSequences()
+    out = mb.MatchList()
+    umf.GetMatchList(out)
+    assert [(m.Length(), [(g, m.Start(g)) for g in range(4) if m.Start(g) != 0]) for m in out] == [(ln, list(c)) for ln, c in O.matches_as_list(want)]
+
+
 def test_randomised_parity_sweep():
     """tools/fuzz_parity.py: random genome counts, lengths around the kernels' tile sizes, random valid seed patterns, all
     policies — 150 cases here (4000 were run for profiles/r02_fuzz_parity.txt)"""
@@ -479,6 +525,10 @@ def test_randomised_parity_sweep():
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_parity.py"), "150", "3"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "0 mismatches" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+    # and with every unfinished extension sent through the shared long walks (normally only lists of 256 reps and more)
+    env = dict(os.environ, MB_LONG_CLASSES_MIN="1")
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_parity.py"), "100", "11"], capture_output=True, text=True, timeout=600, env=env)
     assert out.returncode == 0 and "0 mismatches" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
 
 

@@ -1,5 +1,5 @@
 """Timing of inputs with very long window-consistent runs (DESIGN.md §4 'known cliff'): identical genomes, and two
-identical genomes among diverged ones.  python tools/stress_cliff.py [LEN]"""
+identical genomes among diverged ones.  python tools/stress_cliff.py [LEN [CASE-SUBSTRING]]"""
 import os
 import sys
 import time
@@ -28,9 +28,13 @@ cases = {"2 identical": [a, a.copy()], "3 identical": [a, a.copy(), a.copy()],
 ctx = mb.Context(0)
 ctx.set_seed(mb.get_seed(15, 0))
 for name, seqs in cases.items():
+    if len(sys.argv) > 2 and sys.argv[2] not in name:
+        continue
     ctx.clear_sequences()
     for s in seqs:
         ctx.add_sequence(s)
+    ctx.find_device(mb.MODE_UNIQUE)  # warm-up: the first search of a size allocates the workspaces
+    ctx.fetch()
     t0 = time.perf_counter()
     ctx.find_device(mb.MODE_UNIQUE)
     r = ctx.fetch()
