@@ -214,6 +214,21 @@ int mb_set_segments(mb_ctx* ctx, uint32_t n_problems, const uint64_t* bounds);
  *     range, after which mb_fetch_result works as for mb_find_device.  The ranks' pieces, concatenated in
  *     rank order, are the result. */
 int mb_dist_extract(mb_ctx* ctx, int rank, int world, void** d_send, uint64_t* h_counts);
+/* MB_MODE_UNIQUE_COUNT and MB_MODE_SEED_ENUM over several GPUs (no exchange after the first — the ranks' counts
+ * add up, their match lists are disjoint), for 8-byte and 16-byte seed records (long genomes / heavy seeds: the BASELINE
+ * configs C3 and C4):
+ *   1 mb_dist_extract_records = mb_dist_extract for either format: *d_send_keys (and, for 16-byte records, *d_send_vals;
+ *     NULL otherwise) hold the slice's records grouped by destination key range, h_counts[world] records each   (exchange 1)
+ *   2 mb_dist_recv_buffer(0, n) (and (2, n)) receive them in source-rank order; mb_dist_enum_local sorts them and runs the
+ *     mode's tail over this key range, after which mb_fetch_result works as for mb_find_device:
+ *       MB_MODE_UNIQUE_COUNT  unique_mers and unique_mers_per_seq of the key range — SUM them over the ranks;
+ *       MB_MODE_SEED_ENUM     this rank's matches in canonical order (by first position).  The ranks' pieces are disjoint and
+ *                             their union is the result; merging them by first position (unique per match) gives the
+ *                             canonical list of the single-GPU search.
+ * Replaces, per rank, the SortedMerList creation + UniqueMerCount / SeedMatchEnumerator::FindMatches of
+ * /root/reference/src/uniqueMerCount.cpp:35-43 and /root/reference/src/SeedMatchEnumerator.h:19-33,59-68. */
+int mb_dist_extract_records(mb_ctx* ctx, int rank, int world, void** d_send_keys, void** d_send_vals, uint64_t* h_counts);
+int mb_dist_enum_local(mb_ctx* ctx, const mb_params* params, uint64_t n_recv);
 /* Stage 1 in two steps, for the fused exchange: mb_dist_extract_count extracts the slice and counts it per
  * destination; after the ranks have shared their counts, mb_dist_partition either fills the local send buffer
  * (peer_bases = NULL, as mb_dist_extract does) or writes every record straight into its destination rank's
@@ -228,7 +243,8 @@ int mb_dist_use_p2p_recv(mb_ctx* ctx, int on);
 int mb_ipc_export(mb_ctx* ctx, void* d_ptr, uint8_t* handle64);
 int mb_ipc_import(mb_ctx* ctx, const uint8_t* handle64, void** d_ptr);
 int mb_ipc_close(mb_ctx* ctx, void* d_ptr);
-/* which: 0 seed records, 1 candidate rows, 3 match headers, 4 match components (n = 8-byte words), 5 verdicts (n = bytes) */
+/* which: 0 seed records (first words), 2 second words of 16-byte seed records, 1 candidate rows, 3 match headers,
+ * 4 match components (n = 8-byte words), 5 verdicts (n = bytes) */
 int mb_dist_recv_buffer(mb_ctx* ctx, int which, uint64_t n, void** d_ptr);
 int mb_dist_local(mb_ctx* ctx, const mb_params* params, uint64_t n_recv, uint64_t* h_row_counts);
 /* Last step of stage 2: write the rows in owner order into this rank's send buffer (*d_rows; peer_bases = NULL) or,

@@ -51,7 +51,7 @@ class MbStats(C.Structure):
 EXPORTS = ["mb_ctx_create", "mb_ctx_destroy", "mb_set_stream", "mb_add_sequence", "mb_add_sequence_device", "mb_clear_sequences", "mb_accumulate",
            "mb_set_seed", "mb_find", "mb_find_device", "mb_fetch_result", "mb_get_sml", "mb_get_mers", "mb_get_stats", "mb_strerror",
            "mb_last_cuda_error", "mb_device_count", "mb_version",
-           "mb_dist_extract", "mb_dist_extract_count", "mb_dist_partition", "mb_dist_p2p_recv_array",
+           "mb_dist_extract", "mb_dist_extract_records", "mb_dist_enum_local", "mb_dist_extract_count", "mb_dist_partition", "mb_dist_p2p_recv_array",
            "mb_dist_use_p2p_recv", "mb_ipc_export", "mb_ipc_import", "mb_ipc_close", "mb_dist_recv_buffer", "mb_dist_local", "mb_dist_rows_pack", "mb_dist_push", "mb_dist_resolve", "mb_dist_accept", "mb_dist_match_pack", "mb_dist_match_partition", "mb_dist_output", "mb_dist_stage_ms", "mb_find_multi", "mb_debug_radix", "mb_find_batch", "mb_set_segments", "mb_position_table", "mb_fetch_result_compact", "mb_find_compact", "mb_get_packed_device", "mb_add_sequence_device_packed", "mb_copy_packed_device"]
 
 _lib = None
@@ -92,6 +92,8 @@ def lib():
     L.mb_version.restype = C.c_char_p
     pu64 = C.POINTER(u64)
     L.mb_dist_extract.argtypes = [vp, i32, i32, C.POINTER(vp), pu64]
+    L.mb_dist_extract_records.argtypes = [vp, i32, i32, C.POINTER(vp), C.POINTER(vp), pu64]
+    L.mb_dist_enum_local.argtypes = [vp, C.POINTER(MbParams), u64]
     L.mb_dist_extract_count.argtypes = [vp, i32, i32, pu64]
     L.mb_dist_partition.argtypes = [vp, C.POINTER(vp), pu64, C.POINTER(vp)]
     L.mb_dist_p2p_recv_array.argtypes = [vp, u64, C.POINTER(vp)]

@@ -93,7 +93,7 @@ int mb_ctx_destroy(mb_ctx* c) {
                     &c->bitmap, &c->bmrank, &c->cand_at, &c->cstate, &c->covered, &c->ghash2, &c->rep_cand, &c->s_h2, &c->reach, &c->xstate, &c->xrec, &c->x_lut, &c->x_counts, &c->x_hdr_s, &c->x_comp_s, &c->x_hdr_r, &c->x_comp_r, &c->x_m, &c->x_key, &c->x_item, &c->x_peers, &c->x_recv, &c->q_off, &c->q_pos, &c->q_gs, &c->q_el, &c->q_er, &c->q_perm, &c->q_state, &c->q_item, &c->x_acc_s, &c->x_acc_r, &c->minrank, &c->ext_l, &c->ext_r, &c->wl_a, &c->wl_b, &c->wl_c, &c->wl_long, &c->wd_a, &c->wd_b, &c->wd_c, &c->live_bits, &c->trace, &c->ghash, &c->slot_gp, &c->slot_hash, &c->link_bits, &c->chain_min, &c->rep_bits, &c->rep_rank, &c->s_hash, &c->s_cand, &c->rng_lo, &c->rng_hi, &c->flags,
                     &c->match_idx, &c->sort_kA, &c->sort_kB, &c->sort_vA, &c->sort_vB, &c->ncomp, &c->mers_tmp, &c->out_len, &c->out_off,
                     &c->out_seq, &c->out_start, &c->fam_th1, &c->fam_th2, &c->fam_tx, &c->fam_tend, &c->fam_sh1, &c->fam_sh2, &c->fam_sx, &c->fam_send,
-                    &c->fam_spmax, &c->fam_srun0, &c->fam_drop, &c->seg, &c->pos_match, &c->pos_comp, &c->wide_seq, &c->wide_start};
+                    &c->fam_spmax, &c->fam_srun0, &c->fam_drop, &c->seg, &c->pos_match, &c->pos_comp, &c->wide_seq, &c->wide_start, &c->shadow, &c->cell_r, &c->cell_new};
     for (DBuf* b : bufs) free_buf(*b);
     void* hs[] = {c->h_len, c->h_off, c->h_seq, c->h_start, c->h_perseq, c->h_scal, c->h_posm, c->h_posc};
     for (void* h : hs) if (h) cudaFreeHost(h);
@@ -350,6 +350,99 @@ int mbi_setup_run(mb_ctx* c, MbiRun& r) {
     return MB_OK;
 }
 
+// MB_MODE_UNIQUE_COUNT / MB_MODE_SEED_ENUM over n sorted seed records (kA / vA; kB / vB = the free ping-pong buffers): runs of
+// equal seed -> counts, or bucket policy -> matches in canonical order (by first position) + CSR.  Shared by mb_find_device
+// and by the multi-GPU path (mb_dist_enum_local, where the records are one key range of the whole set).
+int mbi_count_or_enum(mb_ctx* c, const mb_params* prm, u64* kA, u64* kB, u64* vA, u64* vB, u32 n) {
+    cudaStream_t st = c->stream;
+    const RecFmt& fmt = c->fmt;
+    const int mode = prm->mode;
+    const u32 L = c->sd.L;
+    u64* scal = c->scalars.as<u64>();
+    u32* run_start = reinterpret_cast<u32*>(kB);
+    u32* run_u = fmt.wide ? reinterpret_cast<u32*>(vB) : run_start + (n + 2);
+    const bool need_counts = mode == MB_MODE_UNIQUE_COUNT;
+    launch_find_runs(kA, vA, n, fmt, run_start, nullptr, c->status_slice(find_runs_workspace_words(n)), c->ticket(),
+                     need_counts ? c->per_seq.as<u64>() : nullptr, reinterpret_cast<u32*>(scal + SC_RUNS), st);
+    LAUNCHED(c); LAUNCHED(c); LAUNCHED(c); CHECK_LAUNCH(c); // masks, one-block scan, compaction
+
+    if (mode == MB_MODE_UNIQUE_COUNT) {
+        for (int i = EV_BUCKET; i < EV_COUNT; ++i) cudaEventRecord(c->ev[i], st);
+        CUDA_TRY(c, cudaMemcpyAsync(c->h_perseq, c->per_seq.p, MB_MAX_SEQ * 8, cudaMemcpyDeviceToHost, st));
+        TRY(mbi_read_scalars(c));
+        c->r_unique = reinterpret_cast<u32*>((u64*)c->h_scal + SC_RUNS)[0];
+        c->stats.n_runs = c->r_unique;
+        c->have_result = true;
+        return MB_OK;
+    }
+
+
+    const size_t cand_cap = (size_t)n / 2 + 2; // one candidate per selected bucket
+    if (cand_cap >= (1ull << 30)) return MB_E_TOOLONG;
+    TRY(c->reserve(c->cand_run, cand_cap * 4));
+    TRY(c->reserve(c->cand_off, (cand_cap + 1) * 4));
+    SelectArgs sa{};
+    sa.keys = kA; sa.vals = vA; sa.run_start = run_start; sa.run_u = run_u;
+    sa.n_runs_ptr = reinterpret_cast<u32*>(scal + SC_RUNS);
+    sa.mode = mode; sa.direct_only = prm->direct_only;
+    sa.min_multi = prm->min_multi; sa.max_multi = prm->max_multi; sa.nway_mask = prm->nway_mask;
+    sa.status = c->status_slice(div_up(n, select_tile())); sa.ticket = c->ticket();
+    sa.n_buckets = scal + SC_NBUCKETS;
+    sa.totals = reinterpret_cast<u32*>(scal + SC_CAND);
+    sa.cand_run = c->cand_run.as<u32>(); sa.cand_off = c->cand_off.as<u32>(); sa.cand_aux = nullptr;
+    launch_select(sa, fmt, n, st);
+    LAUNCHED(c); CHECK_LAUNCH(c);
+    memset(c->h_perseq, 0, MB_MAX_SEQ * 8); // per-sequence counts are a MODE_UNIQUE_COUNT product
+    TRY(mbi_read_scalars(c));
+    const u32* hs32 = reinterpret_cast<const u32*>(c->h_scal);
+    const u64* hs64 = reinterpret_cast<const u64*>(c->h_scal);
+    const u32 n_runs = hs32[2 * SC_RUNS], n_cand = hs32[2 * SC_CAND], n_ccomp = hs32[2 * SC_CAND + 1];
+    c->stats.n_runs = n_runs; c->stats.n_buckets = hs64[SC_NBUCKETS]; c->stats.n_candidates = n_cand;
+    c->r_unique = n_runs;
+    cudaEventRecord(c->ev[EV_BUCKET], st);
+
+    {
+        cudaEventRecord(c->ev[EV_DEDUP], st);
+        // matches = selected buckets; canonical order (D18) = by first position
+        TRY(c->reserve(c->sort_kA, (size_t)(n_cand + 8) * 8)); TRY(c->reserve(c->sort_kB, (size_t)(n_cand + 8) * 8));
+        TRY(c->reserve(c->sort_vA, (size_t)(n_cand + 8) * 8)); TRY(c->reserve(c->sort_vB, (size_t)(n_cand + 8) * 8));
+        TRY(c->reserve(c->ncomp, (size_t)(n_cand + 8) * 4));
+        TRY(c->reserve(c->out_len, (size_t)(n_cand + 8) * 4));
+        TRY(c->reserve(c->out_off, (size_t)(n_cand + 8) * 8));
+        TRY(c->reserve(c->out_seq, (size_t)(n_ccomp + 8)));
+        TRY(c->reserve(c->out_start, (size_t)(n_ccomp + 8) * 4));
+        if (n_cand) {
+            EmitEnumArgs ea{};
+            ea.keys = kA; ea.vals = vA; ea.run_start = run_start; ea.cand_run = c->cand_run.as<u32>(); ea.cand_off = c->cand_off.as<u32>();
+            ea.totals = reinterpret_cast<u32*>(scal + SC_CAND);
+            u64 *skA = c->sort_kA.as<u64>(), *skB = c->sort_kB.as<u64>(), *svA = c->sort_vA.as<u64>(), *svB = c->sort_vB.as<u64>();
+            ea.sort_key = skA; ea.sort_val = svA; ea.ncomp = c->ncomp.as<u32>();
+            launch_enum_keys(ea, fmt, n_cand, st); LAUNCHED(c); CHECK_LAUNCH(c);
+            TRY(mbi_sort_records(c, &skA, &skB, &svA, &svB, n_cand, 0, fmt.pbits, false));
+            // component counts in sorted order -> offsets
+            // (ncomp was written in candidate order; permute through the sorted values inside the gather scan input)
+            OutputArgs oa{};
+            oa.n_items = n_cand; oa.cand_off = c->cand_off.as<u32>(); oa.ncomp = c->ncomp.as<u32>();
+            oa.n_matches_ptr = scal + SC_NMATCH;
+            c->tmp_u64 = n_cand;
+            CUDA_TRY(c, cudaMemcpyAsync(scal + SC_NMATCH, &c->tmp_u64, 8, cudaMemcpyHostToDevice, st));
+            launch_uniq_ncomp(oa, svA, n_cand, st); LAUNCHED(c); CHECK_LAUNCH(c);
+            launch_scan_u32(c->ncomp.as<u32>(), n_cand, nullptr, c->out_off.as<u64>(), c->status_slice(div_up(n_cand, scan_tile())), c->ticket(),
+                            scal + SC_NCOMP, st);
+            LAUNCHED(c); CHECK_LAUNCH(c);
+            ea.sorted_val = svA; ea.out_off = c->out_off.as<u64>();
+            ea.out_len = c->out_len.as<u32>(); ea.out_seq = c->out_seq.as<u8>(); ea.out_start = c->out_start.as<int32_t>();
+            launch_enum_gather(ea, fmt, L, n_cand, st); LAUNCHED(c); CHECK_LAUNCH(c);
+        }
+        c->r_matches = n_cand; c->r_comps = n_ccomp;
+        cudaEventRecord(c->ev[EV_OUTPUT], st);
+        c->stats.n_matches = n_cand; c->stats.n_comps = n_ccomp;
+        c->have_result = true;
+        return MB_OK;
+    }
+
+}
+
 extern "C" {
 
 int mb_find_device(mb_ctx* c, const mb_params* prm) {
@@ -401,24 +494,16 @@ int mb_find_device(mb_ctx* c, const mb_params* prm) {
         return MB_OK;
     }
 
+    if (mode == MB_MODE_UNIQUE_COUNT || mode == MB_MODE_SEED_ENUM) return mbi_count_or_enum(c, prm, kA, kB, vA, vB, n);
+
     // ---- a5/a6: runs of equal seed.  run arrays live in the now-free ping-pong buffer.
     u32* run_start = reinterpret_cast<u32*>(kB);
     u32* run_u = fmt.wide ? reinterpret_cast<u32*>(vB) : run_start + (n + 2);
     bool need_u = mode == MB_MODE_UNIQUE || mode == MB_MODE_PAIRWISE;
-    bool need_counts = mode == MB_MODE_UNIQUE_COUNT;
+    bool need_counts = false;
     const unsigned short* run_masks = launch_find_runs(kA, vA, n, fmt, run_start, need_u ? run_u : nullptr, c->status_slice(find_runs_workspace_words(n)), c->ticket(),
                      need_counts ? c->per_seq.as<u64>() : nullptr, reinterpret_cast<u32*>(scal + SC_RUNS), st);
     LAUNCHED(c); LAUNCHED(c); LAUNCHED(c); CHECK_LAUNCH(c); // masks, one-block scan, compaction
-
-    if (mode == MB_MODE_UNIQUE_COUNT) {
-        for (int i = EV_BUCKET; i < EV_COUNT; ++i) cudaEventRecord(c->ev[i], st);
-        CUDA_TRY(c, cudaMemcpyAsync(c->h_perseq, c->per_seq.p, MB_MAX_SEQ * 8, cudaMemcpyDeviceToHost, st));
-        TRY(mbi_read_scalars(c));
-        c->r_unique = reinterpret_cast<u32*>((u64*)c->h_scal + SC_RUNS)[0];
-        c->stats.n_runs = c->r_unique;
-        c->have_result = true;
-        return MB_OK;
-    }
 
     // ---- a7/a8: per-bucket policy -> candidates
     // one candidate per bucket; PAIRWISE: one per pair of unique genomes of a bucket (u (u-1) / 2 <= records * (nseq-1) / 2)
@@ -446,46 +531,6 @@ int mb_find_device(mb_ctx* c, const mb_params* prm) {
     c->stats.n_runs = n_runs; c->stats.n_buckets = hs64[SC_NBUCKETS]; c->stats.n_candidates = n_cand;
     c->r_unique = n_runs;
     cudaEventRecord(c->ev[EV_BUCKET], st);
-
-    if (mode == MB_MODE_SEED_ENUM) {
-        cudaEventRecord(c->ev[EV_DEDUP], st);
-        // matches = selected buckets; canonical order (D18) = by first position
-        TRY(c->reserve(c->sort_kA, (size_t)(n_cand + 8) * 8)); TRY(c->reserve(c->sort_kB, (size_t)(n_cand + 8) * 8));
-        TRY(c->reserve(c->sort_vA, (size_t)(n_cand + 8) * 8)); TRY(c->reserve(c->sort_vB, (size_t)(n_cand + 8) * 8));
-        TRY(c->reserve(c->ncomp, (size_t)(n_cand + 8) * 4));
-        TRY(c->reserve(c->out_len, (size_t)(n_cand + 8) * 4));
-        TRY(c->reserve(c->out_off, (size_t)(n_cand + 8) * 8));
-        TRY(c->reserve(c->out_seq, (size_t)(n_ccomp + 8)));
-        TRY(c->reserve(c->out_start, (size_t)(n_ccomp + 8) * 4));
-        if (n_cand) {
-            EmitEnumArgs ea{};
-            ea.keys = kA; ea.vals = vA; ea.run_start = run_start; ea.cand_run = c->cand_run.as<u32>(); ea.cand_off = c->cand_off.as<u32>();
-            ea.totals = reinterpret_cast<u32*>(scal + SC_CAND);
-            u64 *skA = c->sort_kA.as<u64>(), *skB = c->sort_kB.as<u64>(), *svA = c->sort_vA.as<u64>(), *svB = c->sort_vB.as<u64>();
-            ea.sort_key = skA; ea.sort_val = svA; ea.ncomp = c->ncomp.as<u32>();
-            launch_enum_keys(ea, fmt, n_cand, st); LAUNCHED(c); CHECK_LAUNCH(c);
-            TRY(mbi_sort_records(c, &skA, &skB, &svA, &svB, n_cand, 0, fmt.pbits, false));
-            // component counts in sorted order -> offsets
-            // (ncomp was written in candidate order; permute through the sorted values inside the gather scan input)
-            OutputArgs oa{};
-            oa.n_items = n_cand; oa.cand_off = c->cand_off.as<u32>(); oa.ncomp = c->ncomp.as<u32>();
-            oa.n_matches_ptr = scal + SC_NMATCH;
-            c->tmp_u64 = n_cand;
-            CUDA_TRY(c, cudaMemcpyAsync(scal + SC_NMATCH, &c->tmp_u64, 8, cudaMemcpyHostToDevice, st));
-            launch_uniq_ncomp(oa, svA, n_cand, st); LAUNCHED(c); CHECK_LAUNCH(c);
-            launch_scan_u32(c->ncomp.as<u32>(), n_cand, nullptr, c->out_off.as<u64>(), c->status_slice(div_up(n_cand, scan_tile())), c->ticket(),
-                            scal + SC_NCOMP, st);
-            LAUNCHED(c); CHECK_LAUNCH(c);
-            ea.sorted_val = svA; ea.out_off = c->out_off.as<u64>();
-            ea.out_len = c->out_len.as<u32>(); ea.out_seq = c->out_seq.as<u8>(); ea.out_start = c->out_start.as<int32_t>();
-            launch_enum_gather(ea, fmt, L, n_cand, st); LAUNCHED(c); CHECK_LAUNCH(c);
-        }
-        c->r_matches = n_cand; c->r_comps = n_ccomp;
-        cudaEventRecord(c->ev[EV_OUTPUT], st);
-        c->stats.n_matches = n_cand; c->stats.n_comps = n_ccomp;
-        c->have_result = true;
-        return MB_OK;
-    }
 
     // ---- MODE_UNIQUE: a9 candidates (HashMatch + SetDirection)
     TRY(mbi_reserve_candidates(c, n_cand, n_ccomp, bases));
@@ -615,7 +660,21 @@ int mbi_dedup(mb_ctx* c, u32 n_cand, u64 bases, const u64* rows) {
     da.n_rep = n_rep;
     // ---- sort keys of the reps (group colour, slot) and, single-GPU path, their extension records in slot order
     u64 *skA = c->sort_kA.as<u64>(), *skB = c->sort_kB.as<u64>();
-    launch_rep_keys(da, skA, st); LAUNCHED(c);
+#ifndef DD_XORDER
+#define DD_XORDER 1
+#endif
+    const u32 nvirt = c->gt.pairwise ? c->gt.nseq * (c->gt.nseq - 1) / 2 : c->gt.nseq;
+    if (DD_XORDER && !rows && n_rep && nvirt > 1 && nvirt <= 256) {
+        // extension records by (block of positions, first genome, slot): see k_cell_bounds
+        u64 maxlen = 0;
+        for (u32 g = 0; g < c->gt.nseq; ++g) maxlen = std::max<u64>(maxlen, c->gt.len[g]);
+        const size_t cells = extension_cells(nvirt, maxlen);
+        TRY(c->reserve(c->cell_r, (cells + 8) * 4)); TRY(c->reserve(c->cell_new, (cells + 8) * 4));
+        launch_extension_cells(da, c->gt, nvirt, maxlen, bases, c->cell_r.as<u32>(), c->cell_new.as<u32>(), st); LAUNCHED(c); LAUNCHED(c);
+        launch_rep_keys(da, skA, st, c->cell_r.as<u32>(), c->cell_new.as<u32>(), nvirt); LAUNCHED(c);
+    } else {
+        launch_rep_keys(da, skA, st); LAUNCHED(c);
+    }
     cudaEventRecord(c->ev_x[0], st);
     // ---- extend every rep (in slot order: neighbouring reps share genome sectors)
     if (!rows) {

@@ -32,7 +32,6 @@ int mb_dist_extract_count(mb_ctx* c, int rank, int world, uint64_t* h_counts) {
     MbiRun run;
     if (c->n_seg) return MB_E_STATE; // segmented searches are single-GPU
     TRY(mbi_setup_run(c, run));
-    if (c->fmt.wide) return MB_E_ARG;
     cudaStream_t st = c->stream;
     const RecFmt& fmt = c->fmt;
     c->d_rank = rank; c->d_world = world; c->d_bases = run.bases; c->d_maxlen = run.maxlen;
@@ -51,8 +50,9 @@ int mb_dist_extract_count(mb_ctx* c, int rank, int world, uint64_t* h_counts) {
     const u32 ns = (u32)(r1 - r0);
     c->d_nslice = ns;
     TRY(c->reserve(c->keysA, ((size_t)ns + 8) * 8));
-    launch_extract_records(c->packed.as<u64>(), c->keysA.as<u64>(), nullptr, nullptr, 0, c->gt, c->sd, fmt, c->tile_first.as<u32>(), t1 - t0, st, t0,
-                           (u32)r0);
+    if (fmt.wide) TRY(c->reserve(c->valsA, ((size_t)ns + 8) * 8)); // 16-byte records: (seed, genome | position | strand)
+    launch_extract_records(c->packed.as<u64>(), c->keysA.as<u64>(), fmt.wide ? c->valsA.as<u64>() : nullptr, nullptr, 0, c->gt, c->sd, fmt,
+                           c->tile_first.as<u32>(), t1 - t0, st, t0, (u32)r0);
     if (t1 > t0) { LAUNCHED(c); CHECK_LAUNCH(c); }
     // destination of every value of the top tb key bits: splitters of F(x) = 1 - (1 - x)^2
     const int tb = std::min(8, fmt.kbits);
@@ -81,6 +81,7 @@ int mb_dist_extract_count(mb_ctx* c, int rank, int world, uint64_t* h_counts) {
 // into the kernel.  The caller synchronises all ranks before anyone reads its receive array.
 int mb_dist_partition(mb_ctx* c, void* const* peer_bases, const uint64_t* peer_offsets, void** d_send) {
     if (!c || (peer_bases && !peer_offsets) || (!peer_bases && !d_send)) return MB_E_ARG;
+    if (peer_bases && c->fmt.wide) return MB_E_ARG; // 16-byte records travel through local send buffers (mb_dist_extract_records)
     CUDA_TRY(c, cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
     const RecFmt& fmt = c->fmt;
@@ -103,12 +104,13 @@ int mb_dist_partition(mb_ctx* c, void* const* peer_bases, const uint64_t* peer_o
         d_peers = c->x_peers.as<u64*>();
     } else {
         TRY(c->reserve(c->keysB, ((size_t)ns + 8) * 8));
+        if (fmt.wide) TRY(c->reserve(c->valsB, ((size_t)ns + 8) * 8));
     }
     if (ns) {
         u32 tiles = div_up(ns, radix_tile_size());
         CUDA_TRY(c, cudaMemsetAsync(c->lookback.p, 0, (size_t)tiles * 256 * 8, st));
-        cudaError_t e = launch_onesweep(c->keysA.as<u64>(), c->keysB.as<u64>(), nullptr, nullptr, ns, c->digit_base.as<u32>(), c->lookback.as<u64>(),
-                                        c->ticket(), shift, tb, st, c->x_lut.as<u8>(), d_peers);
+        cudaError_t e = launch_onesweep(c->keysA.as<u64>(), c->keysB.as<u64>(), fmt.wide ? c->valsA.as<u64>() : nullptr, fmt.wide ? c->valsB.as<u64>() : nullptr, ns,
+                                        c->digit_base.as<u32>(), c->lookback.as<u64>(), c->ticket(), shift, tb, st, c->x_lut.as<u8>(), d_peers);
         LAUNCHED(c);
         if (e != cudaSuccess) { c->set_cuda_error(e, "onesweep(partition)", __LINE__); return MB_E_CUDA; }
     }
@@ -121,7 +123,17 @@ int mb_dist_partition(mb_ctx* c, void* const* peer_bases, const uint64_t* peer_o
 int mb_dist_extract(mb_ctx* c, int rank, int world, void** d_send, uint64_t* h_counts) {
     if (!d_send) return MB_E_ARG;
     TRY(mb_dist_extract_count(c, rank, world, h_counts));
+    if (c->fmt.wide) return MB_E_ARG; // use mb_dist_extract_records
     TRY(mb_dist_partition(c, nullptr, nullptr, d_send));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return MB_OK;
+}
+// the same for either record format: *d_send_vals = the second words of 16-byte records in the same order, or NULL
+int mb_dist_extract_records(mb_ctx* c, int rank, int world, void** d_send_keys, void** d_send_vals, uint64_t* h_counts) {
+    if (!d_send_keys || !d_send_vals) return MB_E_ARG;
+    TRY(mb_dist_extract_count(c, rank, world, h_counts));
+    TRY(mb_dist_partition(c, nullptr, nullptr, d_send_keys));
+    *d_send_vals = c->fmt.wide ? c->valsB.p : nullptr;
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return MB_OK;
 }
@@ -171,12 +183,12 @@ int mb_dist_use_p2p_recv(mb_ctx* c, int on) {
 }
 
 // receive buffers (library-owned device memory the caller's all-to-all writes into)
-//   which: 0 seed records, 1 candidate rows, 3 match headers, 4 match components (n_words 8-byte words each),
-//          5 verdict bytes (n_words = BYTES)
+//   which: 0 seed records (first words), 2 second words of 16-byte seed records, 1 candidate rows, 3 match headers,
+//          4 match components (n_words 8-byte words each), 5 verdict bytes (n_words = BYTES)
 int mb_dist_recv_buffer(mb_ctx* c, int which, uint64_t n_words, void** d_ptr) {
-    if (!c || !d_ptr || which < 0 || which > 5 || which == 2) return MB_E_ARG;
+    if (!c || !d_ptr || which < 0 || which > 5) return MB_E_ARG;
     CUDA_TRY(c, cudaSetDevice(c->device));
-    DBuf* b = which == 0 ? &c->keysA : which == 5 ? &c->x_acc_r : (which == 1 || which == 3) ? &c->x_hdr_r : &c->x_comp_r;
+    DBuf* b = which == 0 ? &c->keysA : which == 2 ? &c->valsA : which == 5 ? &c->x_acc_r : (which == 1 || which == 3) ? &c->x_hdr_r : &c->x_comp_r;
     TRY(c->reserve(*b, which == 5 ? (size_t)n_words + 64 : ((size_t)n_words + 16) * 8));
     *d_ptr = b->p;
     return MB_OK;
@@ -284,6 +296,41 @@ int mb_dist_local(mb_ctx* c, const mb_params* prm, uint64_t n_recv, uint64_t* h_
     for (int r = 0; r < world; ++r) { h_row_counts[r] = oh[r]; acc += oh[r]; c->d_bound[r + 1] = acc; }
     if (acc != n_cand) return MB_E_STATE;
     return MB_OK;
+}
+
+// stage 2 of MB_MODE_UNIQUE_COUNT / MB_MODE_SEED_ENUM: n_recv seed records of this rank's key range (receive buffers 0 and,
+// for 16-byte records, 2).  Equal seeds all live on one rank, so the counts of the ranks ADD UP (the caller's all-reduce of
+// mb_fetch_result's unique_mers / unique_mers_per_seq) and the ranks' match lists are disjoint: every rank's piece is in
+// canonical order (by first position); the union of the pieces is the result ("sum / concat only").
+int mb_dist_enum_local(mb_ctx* c, const mb_params* prm, uint64_t n_recv) {
+    if (!c || !prm) return MB_E_ARG;
+    if (prm->mode != MB_MODE_UNIQUE_COUNT && prm->mode != MB_MODE_SEED_ENUM) return MB_E_ARG;
+    if (prm->mode == MB_MODE_SEED_ENUM && c->seq_len.size() > 1) return MB_E_SEQCOUNT;
+    if (n_recv >= (1ull << 31)) return MB_E_TOOLONG;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const RecFmt& fmt = c->fmt;
+    const u32 n = (u32)n_recv;
+    for (int i = EV_START; i <= EV_EXTRACT; ++i) cudaEventRecord(c->ev[i], st);
+    cudaEventRecord(c->ev_d[2], st);
+    TRY(c->reserve(c->keysB, ((size_t)n + 8) * 8));
+    if (fmt.wide) TRY(c->reserve(c->valsB, ((size_t)n + 8) * 8));
+    if ((size_t)(n + 8) * 8 > c->keysA.cap || (fmt.wide && (size_t)(n + 8) * 8 > c->valsA.cap)) return MB_E_STATE; // receive buffers not set up
+    u64 *kA = c->keysA.as<u64>(), *kB = c->keysB.as<u64>(), *vA = fmt.wide ? c->valsA.as<u64>() : nullptr, *vB = fmt.wide ? c->valsB.as<u64>() : nullptr;
+    TRY(mbi_sort_records(c, &kA, &kB, fmt.wide ? &vA : nullptr, fmt.wide ? &vB : nullptr, n, fmt.kshift, fmt.kbits, false, true));
+    c->sorted_keys = kA; c->sorted_vals = vA;
+    c->n_seeds = n;
+    cudaEventRecord(c->ev[EV_SORT], st);
+    cudaEventRecord(c->ev_d[3], st);
+    c->last_mode = prm->mode;
+    c->r_matches = 0; c->r_comps = 0; c->r_unique = 0;
+    if (n == 0) {
+        for (int i = EV_BUCKET; i < EV_COUNT; ++i) cudaEventRecord(c->ev[i], st);
+        memset(c->h_perseq, 0, MB_MAX_SEQ * 8);
+        c->have_result = true;
+        return MB_OK;
+    }
+    return mbi_count_or_enum(c, prm, kA, kB, vA, vB, n);
 }
 
 // destination table of a pack kernel -> device (x_peers).  bases == NULL: everything into this rank's own send

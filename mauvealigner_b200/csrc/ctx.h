@@ -39,7 +39,7 @@ struct mb_ctx {
     // workspace
     DBuf keysA, keysB, valsA, valsB, hist, digit_base, lookback, tickets, status, scalars, per_seq, tile_first;
     DBuf cand_run, cand_off, cand_aux, comp_pos, comp_gs, bitmap, bmrank, cand_at, cstate, covered, minrank, ext_l, ext_r;
-    DBuf trace, ghash2, rep_cand, s_h2, reach, xstate, xrec, shadow;
+    DBuf trace, ghash2, rep_cand, s_h2, reach, xstate, xrec, shadow, cell_r, cell_new;
     bool shadow_on = false;                 // this search's long extensions left shadow flags (mbi_extend_long)
     u32 n_rep = 0;
     DBuf x_lut, x_counts, x_hdr_s, x_comp_s, x_hdr_r, x_comp_r, x_m, x_key, x_item, x_peers, x_recv; // multi-GPU exchange buffers (api_dist.cu)
@@ -157,6 +157,7 @@ int mbi_setup_run(mb_ctx* c, MbiRun& r);
 int mbi_sort_records(mb_ctx* c, u64** kA, u64** kB, u64** vA, u64** vB, u32 n, int shift, int kbits, bool hist_ready, bool time_passes = false);
 int mbi_read_scalars(mb_ctx* c);
 int mbi_bits_for(u64 maxval);
+int mbi_count_or_enum(mb_ctx* c, const mb_params* prm, u64* kA, u64* kB, u64* vA, u64* vB, u32 n);
 // stages of the MODE_UNIQUE tail, shared by the single-GPU and the distributed drivers
 int mbi_reserve_candidates(mb_ctx* c, u32 n_cand, u32 n_ccomp, u64 bases);
 int mbi_dedup(mb_ctx* c, u32 n_cand, u64 bases, const u64* rows = nullptr);

@@ -129,7 +129,10 @@ void launch_family_filter(const FamilyArgs& f, u32 n_tab, u32 n_cand, u64* ghash
 void launch_slot_scatter(const DedupArgs& a, const GenomeTable& gt, cudaStream_t st);
 u32 chain_tile();
 void launch_chains(const DedupArgs& a, u64* status_fwd, u32* ticket_fwd, u64* status_bwd, u32* ticket_bwd, cudaStream_t st);
-void launch_rep_keys(const DedupArgs& a, u64* skey, cudaStream_t st);
+void launch_rep_keys(const DedupArgs& a, u64* skey, cudaStream_t st, const u32* cellR = nullptr, const u32* cellNew = nullptr, u32 V = 0);
+// layout of the extension records by (block of positions, first genome, slot): cell tables for launch_rep_keys (two launches)
+u32 extension_cells(u32 V, u64 maxlen);
+void launch_extension_cells(const DedupArgs& a, const GenomeTable& gt, u32 V, u64 maxlen, u64 axis_end, u32* cellR, u32* cellNew, cudaStream_t st);
 int extend_launches();
 // extends the a.n_rep items of a.xrec (filled by launch_rep_keys in slot order, or by launch_cand_xrec); a.bitmap == null:
 // extents only, the slot ranges are derived later (launch_rep_setup / launch_extent_ranges)

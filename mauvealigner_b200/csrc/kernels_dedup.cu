@@ -254,7 +254,62 @@ __global__ void __launch_bounds__(CH_NT) k_chain(DedupArgs a, u64* status, u32* 
 // Single-GPU path: also the extension record of the rep, in SLOT order — the extension runs over the reps in
 // (first genome, position) order, where neighbouring reps read the same genome sectors (L1 hits) instead of the
 // (colour, slot) order of the resolve step, where every component window is a random L2 access.
-__global__ void __launch_bounds__(256) k_rep_keys(DedupArgs a, u64* __restrict__ skey) {
+// Extension order.  In slot order the reps of ONE first genome are neighbours, but a sector of genome 40 is also read by the
+// reps whose first genome is 0, 1, ... 39 — one pass over the slot axis later each time, long after the sector has left
+// the L2 (C5: 9 GB of DRAM reads for 80 MB of packed genomes).  Related genomes are roughly collinear, so the extension
+// records are laid out by (block of 4096 positions, first genome, slot) instead: the reps around one position of ALL
+// first genomes run together and find each other's sectors in the L2.  Only a layout of xrec: any order gives the same
+// extents.  Cells (virtual genome v, block b), index t = b * V + v: cellR[t] = reps before the cell in slot order,
+// cellNew[t] = reps before it in the new order (k_cell_bounds counts, k_cell_scan scans).
+#ifndef XO_SHIFT
+#define XO_SHIFT 12
+#endif
+__global__ void __launch_bounds__(256) k_cell_bounds(DedupArgs a, GenomeTable gt, u32 V, u32 NB, u64 axis_end, u32* __restrict__ cellR,
+                                                      u32* __restrict__ cellCnt) {
+    const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= V * NB) return;
+    const u32 b = t / V, v = t % V;
+    const u64 v0 = gt.vbase[v], v1 = v + 1 < V ? gt.vbase[v + 1] : axis_end;
+    const u64 lo = min(v0 + ((u64)b << XO_SHIFT), v1), hi = min(v0 + ((u64)(b + 1) << XO_SHIFT), v1);
+    u32 r[2];
+    for (int k = 0; k < 2; ++k) {
+        const u32 s = slot_rank(a.bitmap, a.bmrank, k ? hi : lo);
+        r[k] = a.rep_rank[s >> 6] + (u32)__popcll(a.rep_bits[s >> 6] & ((1ull << (s & 63)) - 1));
+    }
+    cellR[t] = r[0];
+    cellCnt[t] = r[1] - r[0];
+}
+// exclusive scan in place, one block (the table is small: axis length / 4096 entries)
+__global__ void __launch_bounds__(1024) k_cell_scan(u32* __restrict__ v, u32 n) {
+    __shared__ u32 swarp[32];
+    __shared__ u32 carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (u32 base = 0; base < n; base += 4096) {
+        const u32 i0 = base + threadIdx.x * 4;
+        u32 x[4];
+        u32 sum = 0;
+        for (int k = 0; k < 4; ++k) { x[k] = i0 + k < n ? v[i0 + k] : 0; sum += x[k]; }
+        u32 inc = sum;
+        for (int d = 1; d < 32; d <<= 1) { u32 y = __shfl_up_sync(0xFFFFFFFFu, inc, d); if (lane >= d) inc += y; }
+        if (lane == 31) swarp[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            u32 w = swarp[lane], winc = w;
+            for (int d = 1; d < 32; d <<= 1) { u32 y = __shfl_up_sync(0xFFFFFFFFu, winc, d); if (lane >= d) winc += y; }
+            swarp[lane] = winc - w;
+        }
+        __syncthreads();
+        u32 ex = carry + swarp[warp] + inc - sum;
+        for (int k = 0; k < 4; ++k) { if (i0 + k < n) v[i0 + k] = ex; ex += x[k]; }
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = ex;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) k_rep_keys(DedupArgs a, u64* __restrict__ skey, const u32* __restrict__ cellR, const u32* __restrict__ cellNew, u32 V) {
     u32 s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= a.n_cand) return;
     u64 w = a.rep_bits[s >> 6];
@@ -265,7 +320,13 @@ __global__ void __launch_bounds__(256) k_rep_keys(DedupArgs a, u64* __restrict__
     if (!a.rows) {
         const ulonglong2 q = a.slot_rec[2 * (size_t)s + 1];
         const u32 c = (u32)r.y, m = (u32)(r.y >> 32) & 0xFFu, g0 = (u32)(r.y >> 40) & 0xFFu, vg = (u32)(r.y >> 48) & 0xFFu;
-        a.xrec[idx] = make_uint4(c, (u32)q.y, m | (g0 << 8) | (vg << 16), (u32)(q.y >> 32));
+        const u32 p0 = (u32)(q.y >> 32);
+        u32 at = idx;
+        if (cellR) {
+            const u32 t = (p0 >> XO_SHIFT) * V + vg;
+            at = cellNew[t] + (idx - cellR[t]);
+        }
+        a.xrec[at] = make_uint4(c, (u32)q.y, m | (g0 << 8) | (vg << 16), p0);
     }
 }
 
@@ -1123,8 +1184,14 @@ void launch_chains(const DedupArgs& a, u64* status_fwd, u32* ticket_fwd, u64* st
     k_chain<false><<<tiles, CH_NT, 0, st>>>(a, status_fwd, ticket_fwd);
     k_chain<true><<<tiles, CH_NT, 0, st>>>(a, status_bwd, ticket_bwd);
 }
-void launch_rep_keys(const DedupArgs& a, u64* skey, cudaStream_t st) {
-    if (a.n_cand) k_rep_keys<<<div_up(a.n_cand, 256), 256, 0, st>>>(a, skey);
+void launch_rep_keys(const DedupArgs& a, u64* skey, cudaStream_t st, const u32* cellR, const u32* cellNew, u32 V) {
+    if (a.n_cand) k_rep_keys<<<div_up(a.n_cand, 256), 256, 0, st>>>(a, skey, cellR, cellNew, V);
+}
+u32 extension_cells(u32 V, u64 maxlen) { return V * (u32)((maxlen >> XO_SHIFT) + 1); }
+void launch_extension_cells(const DedupArgs& a, const GenomeTable& gt, u32 V, u64 maxlen, u64 axis_end, u32* cellR, u32* cellNew, cudaStream_t st) {
+    const u32 NB = (u32)((maxlen >> XO_SHIFT) + 1), cells = V * NB;
+    k_cell_bounds<<<div_up(cells, 256), 256, 0, st>>>(a, gt, V, NB, axis_end, cellR, cellNew);
+    k_cell_scan<<<1, 1024, 0, st>>>(cellNew, cells);
 }
 // k_extend over all reps, then DD_EXT_MORE launches over the shrinking list of unfinished reps (ping-pong lists
 // wd0 / wd1 with counters ctr[12] / ctr[13]), then the warp-per-rep kernel for what is left

@@ -272,21 +272,22 @@ void launch_scan_hist(const u32* d_hist, u32* d_base, int npass, cudaStream_t st
 
 // the dynamic shared memory opt-in is per function AND per device (a process may hold contexts on several devices)
 #define RS_MAX_DEV 64
-static bool g_attr_set[RS_MAX_DEV][3] = {};
+static bool g_attr_set[RS_MAX_DEV][4] = {};
 
 cudaError_t launch_onesweep(const u64* kin, u64* kout, const u64* vin, u64* vout, u32 n, const u32* d_digit_base,
                             u64* d_lookback, u32* d_ticket, int shift, int bits, cudaStream_t st, const u8* lut, u64* const* peers) {
     if (n == 0) return cudaSuccess;
     bool hv = vin != nullptr;
-    if (lut && hv) return cudaErrorInvalidValue;
+    if (lut && hv && peers) return cudaErrorInvalidValue; // 16-byte records are partitioned into local send buffers only
     size_t smem = radix_smem_bytes(hv);
-    int variant = lut ? 2 : (hv ? 1 : 0);
+    int variant = lut ? (hv ? 3 : 2) : (hv ? 1 : 0);
     int dev = 0;
     cudaError_t de = cudaGetDevice(&dev);
     if (de != cudaSuccess) return de;
     const bool tracked = dev >= 0 && dev < RS_MAX_DEV;
     if (!tracked || !g_attr_set[dev][variant]) {
-        cudaError_t e = variant == 2 ? cudaFuncSetAttribute(k_onesweep<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+        cudaError_t e = variant == 3 ? cudaFuncSetAttribute(k_onesweep<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                      : variant == 2 ? cudaFuncSetAttribute(k_onesweep<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                       : variant == 1 ? cudaFuncSetAttribute(k_onesweep<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                                      : cudaFuncSetAttribute(k_onesweep<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -294,7 +295,8 @@ cudaError_t launch_onesweep(const u64* kin, u64* kout, const u64* vin, u64* vout
     }
     u32 tiles = div_up(n, RS_TILE);
     u32 dmask = (1u << bits) - 1;
-    if (variant == 2) k_onesweep<false, true><<<tiles, RS_NT, smem, st>>>(kin, kout, vin, vout, n, d_digit_base, d_lookback, d_ticket, shift, dmask, lut, peers);
+    if (variant == 3) k_onesweep<true, true><<<tiles, RS_NT, smem, st>>>(kin, kout, vin, vout, n, d_digit_base, d_lookback, d_ticket, shift, dmask, lut, peers);
+    else if (variant == 2) k_onesweep<false, true><<<tiles, RS_NT, smem, st>>>(kin, kout, vin, vout, n, d_digit_base, d_lookback, d_ticket, shift, dmask, lut, peers);
     else if (variant == 1) k_onesweep<true, false><<<tiles, RS_NT, smem, st>>>(kin, kout, vin, vout, n, d_digit_base, d_lookback, d_ticket, shift, dmask, lut, peers);
     else k_onesweep<false, false><<<tiles, RS_NT, smem, st>>>(kin, kout, vin, vout, n, d_digit_base, d_lookback, d_ticket, shift, dmask, lut, peers);
     return cudaGetLastError();

@@ -362,6 +362,95 @@ def find_unique(ctxs, fabric, device, nway_mask=0, p2p=None):
     return info
 
 
+def find_enum(ctxs, fabric, device, mode, min_multi=2, max_multi=1000, direct_only=False):
+    """MODE_UNIQUE_COUNT / MODE_SEED_ENUM over the ranks of `fabric` (8-byte or 16-byte seed records): one exchange — the
+    seed records by key range — then every rank runs the mode's tail over its range.  Equal seeds meet on one rank, so
+    the counts add up (summed here: every rank's info carries the totals) and the match lists are disjoint (fetch every
+    rank's piece; merge_enum_results gives the canonical list).  Returns per-local-rank info dicts."""
+    from . import _lib as L
+    W, R = fabric.world, fabric.local_ranks
+    if mode not in (L.MODE_UNIQUE_COUNT, L.MODE_SEED_ENUM):
+        raise ValueError("find_enum: MODE_UNIQUE_COUNT or MODE_SEED_ENUM")
+    if hasattr(fabric, "bind_streams"):
+        fabric.bind_streams(ctxs)
+    s1 = [c.dist_extract_records(r, W) for c, r in zip(ctxs, R)]
+    sc = [cnt for _, _, cnt in s1]
+    rc = fabric.counts(sc)
+    wide = bool(s1[0][1])
+    for which, col in ((0, 0), (2, 1)) if wide else ((0, 0),):
+        sends = [dev_words(t[col], sum(t[2]), device) for t in s1]
+        recvs = [dev_words(c.dist_recv_buffer(which, sum(k)), sum(k), device) for c, k in zip(ctxs, rc)]
+        fabric.words(sends, sc, recvs, rc)
+    for c, k in zip(ctxs, rc):
+        c.dist_enum_local(sum(k), mode, min_multi=min_multi, max_multi=max_multi, direct_only=direct_only)
+    info = [dict(rank=r, seeds_sent=sum(sc[i]), seeds_received=sum(rc[i]), record_bytes=16 if wide else 8) for i, r in enumerate(R)]
+    if mode == L.MODE_UNIQUE_COUNT:
+        import numpy as np
+        pieces = [c.fetch() for c in ctxs]
+        nseq = len(pieces[0]["unique_mers_per_seq"])
+        host = _is_host(device)
+        ts = []
+        for p in pieces:
+            v = np.concatenate([[p["unique_mers"]], np.asarray(p["unique_mers_per_seq"], dtype=np.int64)]).astype(np.int64)
+            ts.append(torch.from_numpy(v) if host else torch.from_numpy(v).to(device))
+        fabric.allreduce_sum(ts)
+        for i, t in enumerate(ts):
+            tot = t.cpu().numpy()
+            info[i]["unique_mers"] = int(tot[0])
+            info[i]["unique_mers_per_seq"] = tot[1:1 + nseq].astype(np.uint64)
+            info[i]["unique_mers_local"] = int(pieces[i]["unique_mers"])
+    return info
+
+
+def merge_enum_results(pieces):
+    """The ranks' MODE_SEED_ENUM pieces (each in canonical order, disjoint) -> the canonical list of the single-GPU search:
+    a stable merge by first position, which is unique per match."""
+    import numpy as np
+    cat = concat_results(pieces)
+    n = cat["n_matches"]
+    if n == 0:
+        return cat
+    off = np.asarray(cat["comp_off"], dtype=np.int64)
+    first = np.abs(np.asarray(cat["comp_start"], dtype=np.int64)[off[:-1]])
+    order = np.argsort(first, kind="stable")
+    cnt = (off[1:] - off[:-1])[order]
+    new_off = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
+    idx = np.repeat(off[:-1][order] - new_off[:-1], cnt) + np.arange(int(new_off[-1]), dtype=np.int64)
+    out = dict(n_matches=n, n_comps=cat["n_comps"])
+    out["length"] = np.asarray(cat["length"])[order]
+    out["comp_off"] = new_off.astype(np.uint64)
+    out["comp_seq"] = np.asarray(cat["comp_seq"])[idx]
+    out["comp_start"] = np.asarray(cat["comp_start"])[idx]
+    return out
+
+
+def find_enum_emulated(seqs, pattern, world, mode, device=0, **kw):
+    """All `world` ranks of find_enum inside this process on one GPU (parity tests): MODE_UNIQUE_COUNT -> rank 0's info;
+    MODE_SEED_ENUM -> the merged result dict."""
+    from . import _lib as L
+    from .finder import Context
+    dev = torch.device("cuda", device)
+    ctxs = [Context(device) for _ in range(world)]
+    stream = torch.cuda.Stream(dev)
+    try:
+        with torch.cuda.stream(stream):
+            for c in ctxs:
+                c.set_stream(stream.cuda_stream)
+                for s in seqs:
+                    c.add_sequence(s)
+                c.set_seed(pattern)
+            info = find_enum(ctxs, LocalFabric(world), dev, mode, **kw)
+            stream.synchronize()
+            if mode == L.MODE_UNIQUE_COUNT:
+                return info[0]
+            res = merge_enum_results([c.fetch() for c in ctxs])
+        res["info"] = info
+        return res
+    finally:
+        for c in ctxs:
+            c.close()
+
+
 def concat_results(pieces):
     """The ranks' CSR pieces in rank order -> one result dict (numpy, host)."""
     import numpy as np

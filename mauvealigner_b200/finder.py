@@ -198,6 +198,19 @@ class Context:
         _check(self._h, L.lib().mb_dist_extract(self._h, int(rank), int(world), C.byref(ptr), counts))
         return ptr.value or 0, [int(x) for x in counts]
 
+    def dist_extract_records(self, rank, world):
+        """stage 1 for either record format -> (pointer of the first words, pointer of the second words of 16-byte records or
+        0, records per destination rank)"""
+        kp, vp = C.c_void_p(), C.c_void_p()
+        counts = (C.c_uint64 * world)()
+        _check(self._h, L.lib().mb_dist_extract_records(self._h, int(rank), int(world), C.byref(kp), C.byref(vp), counts))
+        return kp.value or 0, vp.value or 0, [int(x) for x in counts]
+
+    def dist_enum_local(self, n_recv, mode, min_multi=2, max_multi=1000, direct_only=False):
+        """stage 2 of MODE_UNIQUE_COUNT / MODE_SEED_ENUM over the received key range; fetch() afterwards"""
+        p = self._params(mode, min_multi, max_multi, direct_only, 0)
+        _check(self._h, L.lib().mb_dist_enum_local(self._h, C.byref(p), int(n_recv)))
+
     def dist_extract_count(self, rank, world):
         """stage 1a -> records of this rank's slice per destination rank (the slice stays in library memory)"""
         counts = (C.c_uint64 * world)()

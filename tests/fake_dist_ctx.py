@@ -61,6 +61,27 @@ class FakeCtx:
         arr = np.array([word(1, rank, d, i) for d in range(world) for i in range(counts[d])], dtype=np.int64)
         return self._send(arr), counts
 
+    # ---- find_enum (MODE_UNIQUE_COUNT / MODE_SEED_ENUM): one exchange of 8-byte or 16-byte records, then a local tail
+    wide = False
+
+    def dist_extract_records(self, rank, world):
+        kp, counts = self.dist_extract(rank, world)
+        vp = 0
+        if self.wide:
+            vp = self._send(np.array([word(6, rank, d, i) for d in range(world) for i in range(counts[d])], dtype=np.int64))
+        return kp, vp, counts
+
+    def dist_enum_local(self, n_recv, mode, min_multi=2, max_multi=1000, direct_only=False):
+        assert n_recv == sum(n_seeds(s, self.rank) for s in range(self.world))
+        self._expect(0, 1, n_seeds, what="seed records")
+        if self.wide:
+            self._expect(2, 6, n_seeds, what="second words of the seed records")
+        self.mode, self.done = mode, True
+
+    def fetch(self):
+        # this rank's share of the counts: 10 r + 1 distinct seeds, (r + 1, 2 r) per sequence
+        return dict(unique_mers=10 * self.rank + 1, unique_mers_per_seq=np.array([self.rank + 1, 2 * self.rank], dtype=np.uint64))
+
     def dist_recv_buffer(self, which, n):
         self.bufs[which] = np.full(int(n) + 4, 255, dtype=np.uint8) if which == 5 else np.full(int(n) + 4, -1, dtype=np.int64)
         return self.bufs[which].ctypes.data

@@ -79,6 +79,84 @@ def test_orchestration_in_process_world3():
             assert info[r]["matches"] == sum(n_match(s, r) for s in range(world))
 
 
+def test_enum_orchestration_in_process_world3():
+    """find_enum (MODE_UNIQUE_COUNT / MODE_SEED_ENUM over several ranks) over the stand-in contexts: both record formats
+    arrive in source-rank order, the counts are summed over the ranks"""
+    from fake_dist_ctx import FakeCtx, n_seeds
+    from mauvealigner_b200 import MODE_SEED_ENUM, MODE_UNIQUE_COUNT
+    from mauvealigner_b200.dist import find_enum
+    world = 3
+    for wide in (False, True):
+        ctxs = [FakeCtx() for _ in range(world)]
+        for c in ctxs:
+            c.wide = wide
+        info = find_enum(ctxs, LocalFabric(world), torch.device("cpu"), MODE_UNIQUE_COUNT)
+        assert all(c.done for c in ctxs)
+        for r in range(world):
+            assert info[r]["record_bytes"] == (16 if wide else 8)
+            assert info[r]["seeds_received"] == sum(n_seeds(s, r) for s in range(world))
+            assert info[r]["unique_mers"] == sum(10 * q + 1 for q in range(world)) and info[r]["unique_mers_local"] == 10 * r + 1
+            assert info[r]["unique_mers_per_seq"].tolist() == [sum(q + 1 for q in range(world)), sum(2 * q for q in range(world))]
+        info = find_enum(ctxs, LocalFabric(world), torch.device("cpu"), MODE_SEED_ENUM, min_multi=2, max_multi=9)
+        assert all(c.done and c.mode == MODE_SEED_ENUM for c in ctxs) and "unique_mers" not in info[0]
+    with pytest.raises(ValueError):
+        find_enum(ctxs, LocalFabric(world), torch.device("cpu"), 0)
+
+
+def test_merge_enum_results_restores_canonical_order():
+    """the ranks' MODE_SEED_ENUM pieces (sorted by first position, disjoint) merge into one list sorted by first position"""
+    from mauvealigner_b200.dist import merge_enum_results
+    a = dict(n_matches=2, n_comps=5, length=np.array([9, 7]), comp_off=np.array([0, 2, 5], dtype=np.uint64), comp_seq=np.zeros(5, dtype=np.uint32),
+             comp_start=np.array([3, -40, 20, 25, -90], dtype=np.int64))
+    b = dict(n_matches=0, n_comps=0, length=np.zeros(0, dtype=np.uint32), comp_off=np.zeros(1, dtype=np.uint64), comp_seq=np.zeros(0, dtype=np.uint32),
+             comp_start=np.zeros(0, dtype=np.int64))
+    c = dict(n_matches=2, n_comps=4, length=np.array([5, 6]), comp_off=np.array([0, 2, 4], dtype=np.uint64), comp_seq=np.zeros(4, dtype=np.uint32),
+             comp_start=np.array([1, 2, 10, -11], dtype=np.int64))
+    m = merge_enum_results([a, b, c])
+    assert m["n_matches"] == 4 and m["n_comps"] == 9
+    assert m["length"].tolist() == [5, 9, 6, 7]
+    assert m["comp_off"].tolist() == [0, 2, 4, 6, 9]
+    assert m["comp_start"].tolist() == [1, 2, 3, -40, 10, -11, 20, 25, -90]
+    assert merge_enum_results([b, b])["n_matches"] == 0
+
+
+def _enum_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from fake_dist_ctx import FakeCtx
+        from mauvealigner_b200 import MODE_UNIQUE_COUNT
+        from mauvealigner_b200.dist import find_enum
+        ctx = FakeCtx()
+        ctx.wide = True
+        info = find_enum([ctx], TorchFabric(), torch.device("cpu"), MODE_UNIQUE_COUNT)
+        ok = ctx.done and info[0]["unique_mers"] == sum(10 * q + 1 for q in range(world)) and info[0]["unique_mers_per_seq"].tolist() == [3, 2]
+        out.put((rank, bool(ok)))
+    except Exception as e:
+        out.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_enum_orchestration_gloo_world2():
+    """find_enum over two real processes (gloo): 16-byte records through two all-to-alls, counts through the all-reduce"""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_enum_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=100) for _ in range(2))
+    for p in procs:
+        p.join(timeout=30)
+    assert res == {0: True, 1: True}
+
+
 def _orchestration_worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     import torch.distributed as dist

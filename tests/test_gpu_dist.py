@@ -40,6 +40,52 @@ def test_emulated_world_nccl_style_exchange1():
         assert_same(got, want, f"p2p={p2p}")
 
 
+SOLID31 = (1 << 31) - 1  # weight 31: 62 seed bits, so (seed, genome, position, strand) needs 16-byte records
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_emulated_unique_count(world):
+    """MB_MODE_UNIQUE_COUNT over several ranks (the counts of the key ranges add up), 8-byte and 16-byte records"""
+    import mauvealigner_b200 as mb
+    from mauvealigner_b200 import dist
+    rng = np.random.default_rng(640 + world)
+    seqs = family(rng, 30000, 3, sub=0.05, indel=0.004, inv=1)
+    seqs[0] = seqs[0] + seqs[0][2000:9000] + revcomp(seqs[0][100:3000])  # repeated mers inside one genome
+    for pattern, rec in ((0b110111011, 8), (mb.get_seed(15, 0), 8), (SOLID31, 16)):
+        got = dist.find_enum_emulated(seqs, pattern, world, mb.MODE_UNIQUE_COUNT)
+        want = O.find(seqs, pattern, O.MODE_UNIQUE_COUNT)
+        assert got["record_bytes"] == rec
+        assert got["unique_mers"] == want["unique_mers"], (world, pattern)
+        assert np.array_equal(np.asarray(got["unique_mers_per_seq"], dtype=np.int64), np.asarray(want["unique_mers_per_seq"], dtype=np.int64))
+    # one genome (the uniqueMerCount tool), fewer tiles than ranks
+    got = dist.find_enum_emulated([seqs[0][:700]], 0b1011101, world, mb.MODE_UNIQUE_COUNT)
+    assert got["unique_mers"] == O.find([seqs[0][:700]], 0b1011101, O.MODE_UNIQUE_COUNT)["unique_mers"]
+
+
+@pytest.mark.parametrize("world", [1, 2, 5])
+def test_emulated_seed_enum(world):
+    """MB_MODE_SEED_ENUM over several ranks: the ranks' pieces (key ranges) are disjoint; merged by first position they are
+    the single-GPU list — multiplicity windows, direct_only, both record formats"""
+    import mauvealigner_b200 as mb
+    from mauvealigner_b200 import dist
+    from toygen import mutate
+    rng = np.random.default_rng(760 + world)
+    unit = rand_seq(rng, 400)
+    s = (rand_seq(rng, 20000) + unit + rand_seq(rng, 900) + mutate(rng, unit, sub=0.04, indel=0) + revcomp(unit) + rand_seq(rng, 5000) + "AT" * 200 + unit +
+         rand_seq(rng, 3000) + "ACG" * 100)
+    for pattern, kw in ((0b110111011, dict(min_multi=2, max_multi=500)), (mb.get_seed(11, 1), dict(min_multi=3, max_multi=1000)),
+                        (mb.get_seed(9, 0), dict(min_multi=2, max_multi=4, direct_only=True)), (SOLID31, dict(min_multi=2, max_multi=1000))):
+        got = dist.find_enum_emulated([s], pattern, world, mb.MODE_SEED_ENUM, **kw)
+        want = O.find([s], pattern, O.MODE_SEED_ENUM, **kw)
+        assert_same(got, want, f"world {world} pattern {pattern:b}")
+        assert got["n_matches"] > 0
+        assert sum(i["seeds_received"] for i in got["info"]) == len(s) - pattern.bit_length() + 1
+    # nothing to report, and a sequence shorter than the seed
+    for short in (rand_seq(rng, 300), "ACGTAC"):
+        got = dist.find_enum_emulated([short], mb.get_seed(15, 0), world, mb.MODE_SEED_ENUM, min_multi=2, max_multi=10)
+        assert_same(got, O.find([short], mb.get_seed(15, 0), O.MODE_SEED_ENUM, min_multi=2, max_multi=10))
+
+
 def test_emulated_edge_cases():
     from mauvealigner_b200 import dist
     rng = np.random.default_rng(9)
