@@ -21,7 +21,10 @@
 //                              by destination = range of the canonical order           --> exchange 3
 //   stage 4  mb_dist_output    every rank: canonical order (D18) + CSR of its key range; the pieces in
 //                              rank order are the result (mb_fetch_result per rank)
-// MODE_UNIQUE with 8-byte records only (every BASELINE config that names several GPUs).
+// The stages above serve MODE_UNIQUE with 8-byte records (C5, the BASELINE config that names several GPUs).
+// MODE_UNIQUE_COUNT / MODE_SEED_ENUM, with 8- or 16-byte records, need stage 1 and exchange 1 only:
+//   mb_dist_extract_records -> exchange 1 (one all-to-all per record word) -> mb_dist_enum_local (sort + the mode's tail
+//   over the key range); counts add up over the ranks, match lists are disjoint.
 #include "ctx.h"
 
 extern "C" {
@@ -330,7 +333,10 @@ int mb_dist_enum_local(mb_ctx* c, const mb_params* prm, uint64_t n_recv) {
         c->have_result = true;
         return MB_OK;
     }
-    return mbi_count_or_enum(c, prm, kA, kB, vA, vB, n);
+    TRY(mbi_count_or_enum(c, prm, kA, kB, vA, vB, n));
+    cudaEventRecord(c->ev_d[4], st); // "buckets" of mb_dist_stage_ms: runs / policy / output of the key range
+    cudaEventRecord(c->ev_d[5], st);
+    return MB_OK;
 }
 
 // destination table of a pack kernel -> device (x_peers).  bases == NULL: everything into this rank's own send

@@ -397,7 +397,7 @@ def find_enum(ctxs, fabric, device, mode, min_multi=2, max_multi=1000, direct_on
         for i, t in enumerate(ts):
             tot = t.cpu().numpy()
             info[i]["unique_mers"] = int(tot[0])
-            info[i]["unique_mers_per_seq"] = tot[1:1 + nseq].astype(np.uint64)
+            info[i]["unique_mers_per_seq"] = [int(x) for x in tot[1:1 + nseq]]
             info[i]["unique_mers_local"] = int(pieces[i]["unique_mers"])
     return info
 
@@ -513,7 +513,7 @@ def add_sequences_shared(ctx, packer, host_seqs, world, rank, dev):
     return recv  # keep it alive until the stream has passed the copies
 
 
-def gather_result_digest(res, world, rank, B, config, mode, scale):
+def gather_result_digest(res, world, rank, B, config, mode, scale, merge=False):
     """Rank 0 receives every rank's CSR piece over a gloo group (host memory, outside every timed region), joins them in
     rank order (= canonical order) and hashes the whole result exactly like the single-GPU line does: the only proof that
     the NCCL + peer-memory path is bit-exact on real GPUs."""
@@ -540,7 +540,7 @@ def gather_result_digest(res, world, rank, B, config, mode, scale):
             dist.send(t, dst=0, group=g)
     out = None
     if rank == 0:
-        out = B.parity_of(concat_results(pieces), config, mode, scale)
+        out = B.parity_of(merge_enum_results(pieces) if merge else concat_results(pieces), config, mode, scale)
     dist.barrier(group=g)
     return out
 
@@ -561,8 +561,12 @@ def bench_main(args, B):
     W = max(3, args.warmup)
     config = args.config
     pattern, mode, kw = B.config_params(None, config)
-    if mode != mb.MODE_UNIQUE:
-        raise SystemExit("the multi-GPU path covers MODE_UNIQUE (config 1, 2, 5)")
+    enum = mode != mb.MODE_UNIQUE  # C3 (MODE_UNIQUE_COUNT, 16-byte records) and C4 (MODE_SEED_ENUM): find_enum
+
+    def parity_check(res, info):
+        if mode == mb.MODE_UNIQUE_COUNT:  # the summed count is the result
+            return B.parity_of(dict(n_matches=0, n_comps=0, unique_mers=info[0]["unique_mers"]), config, mode, args.scale) if rank == 0 else None
+        return gather_result_digest(res, world, rank, B, config, mode, args.scale, merge=enum)
     seqs = B.synth.synth_genomes(config, args.scale)
     bp = sum(len(s) for s in seqs)
     ctx = mb.Context(local)
@@ -582,7 +586,7 @@ def bench_main(args, B):
     torch.cuda.synchronize()
 
     def step():
-        return find_unique([ctx], fabric, dev)
+        return find_enum([ctx], fabric, dev, mode, **kw) if enum else find_unique([ctx], fabric, dev)
 
     for _ in range(W):
         step()
@@ -611,7 +615,7 @@ def bench_main(args, B):
     launches = torch.tensor([float(st["kernel_launches"])], device=dev)
     dist.all_reduce(launches, op=dist.ReduceOp.SUM)
     res = ctx.fetch(copy=False)
-    parity = gather_result_digest(res, world, rank, B, config, mode, args.scale)
+    parity = parity_check(res, info)
 
     # ---- e2e: pinned host ASCII on every rank -> C ABI stages + exchanges -> every rank's piece of the CSR in host memory
     pinned = [torch.from_numpy(s).pin_memory() for s in seqs]
@@ -623,9 +627,10 @@ def bench_main(args, B):
     def e2e_step():
         # every rank uploads 1 / world of the genomes; the packed words travel over NVLink
         keep[:] = [add_sequences_shared(ctx, packer, pinned, world, rank, dev)]
-        find_unique([ctx], fabric, dev)
+        e2e_info[:] = step()
         return ctx.fetch(copy=False, compact=True)  # the compact result form (5 B / component over PCIe)
 
+    e2e_info = []
     e2e_step()
     torch.cuda.synchronize()
     dist.barrier()
@@ -643,7 +648,7 @@ def bench_main(args, B):
     h2d_total = float(h2d_t.item())
     d2h = torch.tensor([float(st2["d2h_bytes"])], device=dev)
     dist.all_reduce(d2h, op=dist.ReduceOp.SUM)
-    e2e_parity = gather_result_digest(r, world, rank, B, config, mode, args.scale)
+    e2e_parity = parity_check(r, e2e_info)
     if sampler:
         sampler.stop_flag = True
         sampler.join(timeout=2)
@@ -671,8 +676,10 @@ def bench_main(args, B):
             "metric": B.METRIC, "value": bp / (ms_per_step * 1e-3) / 1e9, "unit": "Gbp/s", "n_gpus": world,
             "steps": args.steps, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic", "config": cfg,
-            "parallelism": f"key-range x{world} (seeds), group-hash x{world} (de-dup), canonical-range x{world} (output); result = the ranks' CSR "
-                           "pieces in rank order (BASELINE.md §3)",
+            "parallelism": (f"key-range x{world} (seeds); result = the sum of the ranks' counts / the ranks' disjoint match lists, merged by first "
+                            "position for the digest" if enum else
+                            f"key-range x{world} (seeds), group-hash x{world} (de-dup), canonical-range x{world} (output); result = the ranks' CSR "
+                            "pieces in rank order (BASELINE.md §3)"),
             "parity": parity, "roofline": roofline, "path_roofline": path, "cpu_baseline": cpu,
             "e2e": {"value": bp / (e2e_ms * 1e-3) / 1e9, "unit": "Gbp/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h2d_total),
                     "d2h_bytes_per_step": int(d2h.item()), "digest_ok": e2e_parity["digest_ok"]},

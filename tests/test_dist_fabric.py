@@ -96,7 +96,7 @@ def test_enum_orchestration_in_process_world3():
             assert info[r]["record_bytes"] == (16 if wide else 8)
             assert info[r]["seeds_received"] == sum(n_seeds(s, r) for s in range(world))
             assert info[r]["unique_mers"] == sum(10 * q + 1 for q in range(world)) and info[r]["unique_mers_local"] == 10 * r + 1
-            assert info[r]["unique_mers_per_seq"].tolist() == [sum(q + 1 for q in range(world)), sum(2 * q for q in range(world))]
+            assert info[r]["unique_mers_per_seq"] == [sum(q + 1 for q in range(world)), sum(2 * q for q in range(world))]
         info = find_enum(ctxs, LocalFabric(world), torch.device("cpu"), MODE_SEED_ENUM, min_multi=2, max_multi=9)
         assert all(c.done and c.mode == MODE_SEED_ENUM for c in ctxs) and "unique_mers" not in info[0]
     with pytest.raises(ValueError):
@@ -131,7 +131,7 @@ def _enum_worker(rank, world, port, out):
         ctx = FakeCtx()
         ctx.wide = True
         info = find_enum([ctx], TorchFabric(), torch.device("cpu"), MODE_UNIQUE_COUNT)
-        ok = ctx.done and info[0]["unique_mers"] == sum(10 * q + 1 for q in range(world)) and info[0]["unique_mers_per_seq"].tolist() == [3, 2]
+        ok = ctx.done and info[0]["unique_mers"] == sum(10 * q + 1 for q in range(world)) and info[0]["unique_mers_per_seq"] == [3, 2]
         out.put((rank, bool(ok)))
     except Exception as e:
         out.put((rank, repr(e)))
