@@ -841,7 +841,11 @@ __device__ __forceinline__ void extend_finish(const DedupArgs& a, const GenomeTa
 #define DD_EXT_MORE_ROUNDS 8
 #endif
 
-__global__ void __launch_bounds__(DD_NT) k_extend(DedupArgs a, GenomeTable gt, SeedDev sd, u32* out_list, u32* out_count) {
+#ifndef DD_EXT_MINB
+#define DD_EXT_MINB 5 // 48 registers, no spills.  6 / 8 blocks (40 / 32 registers, a few spilled words) measured within 0.1 ms on C5: occupancy is
+#endif                // not what k_extend waits for; 1 lets ptxas take 68 registers and costs 1.2 ms
+
+__global__ void __launch_bounds__(DD_NT, DD_EXT_MINB) k_extend(DedupArgs a, GenomeTable gt, SeedDev sd, u32* out_list, u32* out_count) {
     __shared__ u32 sMap[DD_NT / 32][32][4];
     __shared__ u32 sRoom[DD_NT / 32][32][2];
     __shared__ ulonglong2 sRepA[DD_NT / 32][32];
