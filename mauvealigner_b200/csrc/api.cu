@@ -812,6 +812,7 @@ int mbi_extend_long(mb_ctx* c, const DedupArgs& da_in) {
     da.shadow = c->shadow.as<u8>();
     c->shadow_on = true;
     launch_long_keys(da, (u32)c->sd.L, n_long, kA, st); LAUNCHED(c);
+    // by (class, rep index): inside a class the members of one run must stay together (one walk per run), and the work list is in push order
     TRY(mbi_sort_records(c, &kA, &kB, nullptr, nullptr, n_long, 0, 64, false));
     launch_extend_long_classes(da, c->gt, c->sd, kA, n_long, st); LAUNCHED(c); CHECK_LAUNCH(c);
     return MB_OK;
