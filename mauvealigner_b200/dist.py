@@ -626,17 +626,35 @@ def bench_main(args, B):
 
     def e2e_step():
         # every rank uploads 1 / world of the genomes; the packed words travel over NVLink
+        t_ = [time.perf_counter()]
+
+        def lap():
+            if e2e_trace:
+                torch.cuda.synchronize()
+                t_.append(time.perf_counter())
+
         keep[:] = [add_sequences_shared(ctx, packer, pinned, world, rank, dev)]
+        lap()
         e2e_info[:] = step()
-        return ctx.fetch(copy=False, compact=True)  # the compact result form (5 B / component over PCIe)
+        lap()
+        out = ctx.fetch(copy=False, compact=True)  # the compact result form (5 B / component over PCIe)
+        lap()
+        if e2e_trace and rank == 0:
+            print("[e2e-trace] upload+share %.2f ms, search %.2f ms, fetch %.2f ms" % tuple(1e3 * (b - a) for a, b in zip(t_, t_[1:])), file=sys.stderr, flush=True)
+        return out
 
     e2e_info = []
-    e2e_step()
+    e2e_trace = bool(os.environ.get("MB_E2E_TRACE"))
+    for _ in range(W):  # first calls: pinned result buffers, the packer's workspaces, NCCL's set-up for the new message sizes
+        e2e_step()
     torch.cuda.synchronize()
     dist.barrier()
     t0 = time.perf_counter()
+    e2e_steps = []
     for _ in range(args.steps):
-        r = e2e_step()
+        t1 = time.perf_counter()
+        r = e2e_step()  # ends with the fetch, which waits for the stream
+        e2e_steps.append(round((time.perf_counter() - t1) * 1e3, 2))
     torch.cuda.synchronize()
     dist.barrier()
     e2e_ms = torch.tensor([(time.perf_counter() - t0) * 1e3 / args.steps], device=dev)
@@ -682,7 +700,7 @@ def bench_main(args, B):
                             "pieces in rank order (BASELINE.md §3)"),
             "parity": parity, "roofline": roofline, "path_roofline": path, "cpu_baseline": cpu,
             "e2e": {"value": bp / (e2e_ms * 1e-3) / 1e9, "unit": "Gbp/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h2d_total),
-                    "d2h_bytes_per_step": int(d2h.item()), "digest_ok": e2e_parity["digest_ok"]},
+                    "d2h_bytes_per_step": int(d2h.item()), "digest_ok": e2e_parity["digest_ok"], "rank0_ms_steps": e2e_steps},
             "gpu_launches": int(launches.item()) * args.steps, "stages_ms_rank0": {k: round(v, 4) for k, v in stage.items()},
             "rank0": {k: v for k, v in info[0].items()}, "wall_ms_per_step": wall_ms / args.steps, "clocks": sampler.summary(),
         }
