@@ -120,6 +120,21 @@ def test_unique_vs_brute(seed):
 
 
 @pytest.mark.parametrize("seed", range(6))
+def test_long_consistent_runs_vs_brute(seed):
+    """Long window-consistent runs holding many candidates of ONE group (identical genomes, two identical genomes among
+    diverged ones, sparse SNPs, a reverse-complemented copy): the structure behind the shared long walks of the CUDA path
+    (kernels_dedup.cu, k_extend_long_classes) — the checker itself is pinned against the brute force here."""
+    rng = np.random.default_rng(900 + seed)
+    pattern = PATTERNS[seed % len(PATTERNS)]
+    a = rand_seq(rng, int(rng.integers(500, 900)))
+    cases = [[a, a], [a, a, mutate(rng, a, sub=0.03, indel=0.0), mutate(rng, a, sub=0.03, indel=0.0)], [a, mutate(rng, a, sub=0.004, indel=0.0)],
+             [a, revcomp(a)], [a, mutate(rng, a, sub=0.004, indel=0.0), revcomp(mutate(rng, a, sub=0.004, indel=0.0))]]
+    for seqs in cases:
+        got = as_brute_list(O.find(seqs, pattern, O.MODE_UNIQUE))
+        assert got == brute.find(seqs, pattern, brute.MODE_UNIQUE)["matches"]
+
+
+@pytest.mark.parametrize("seed", range(6))
 def test_unique_low_complexity_vs_brute(seed):
     # 2-letter alphabet + short seeds: many non-unique buckets, ties, overlapping diagonals
     rng = np.random.default_rng(200 + seed)
